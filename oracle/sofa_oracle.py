@@ -1,0 +1,482 @@
+"""CPU ORACLE for the SOFA preprocess/analyze hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is the checker, never the product: only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / `--impl reference` legs may import it.  The product
+path (sofa_b200.sofa_preprocess / sofa_analyze) calls libsofa_b200.so and fails
+loudly when the CUDA library is missing; it never falls back to this file.
+
+It restates the reference's per-record algorithms in plain Python/numpy/pandas,
+using the same library calls where the reference's *output bytes* are defined by a
+library (pandas `to_csv(float_format='%.6f')`, `to_json`, `json.dump`, Python
+`float()`, `np.log10`, `np.interp`).  Every function cites the reference lines it
+follows (paths relative to /root/reference/bin).
+
+Pinning: the reference has no golden vectors of its own.  This
+oracle is pinned against outputs of the UNMODIFIED reference run in the build
+container on synthetic logdirs: tests/golden/make_golden.py generates
+tests/golden/<case>/{cputrace,gputrace,nettrace}.csv, report.js, comm.csv and the
+gpu_profile/comm_profile feature table; tests/test_oracle_golden.py requires this
+oracle to reproduce them byte for byte.
+"""
+import json
+import math
+import multiprocessing as mp
+import os
+import re
+from functools import partial
+
+import numpy as np
+import pandas as pd
+
+FIELDNAMES = ["timestamp", "event", "duration", "deviceId", "copyKind", "payload",
+              "bandwidth", "pkt_src", "pkt_dst", "pid", "tid", "name", "category"]
+
+_CPU_COL = re.compile(r'\[\d+\]')
+
+
+# --------------------------------------------------------------------------- a1
+def parse_perf_sample(sample, absolute_timestamp, time_base, t_offset, mhz_xp, mhz_fp,
+                      perf_events):
+    """One `perf script` line -> 13-col row.  sofa_preprocess.py:110-154."""
+    tok = sample.split()
+    shift = 1 if _CPU_COL.match(tok[1]) is not None else 0      # :114 all-CPU mode
+    t = float(tok[1 + shift].split(':')[0])                      # :115 / :120
+    name = '[%s]' % tok[3 + shift].replace('-', '_') + tok[5 + shift] + tok[6 + shift]
+    counts = float(tok[2 + shift])                               # :117 / :122
+    event_raw = 1.0 * int("0x01" + tok[4 + shift], 16)           # :118 / :123
+    if not absolute_timestamp:
+        t = t - time_base                                        # :125-126
+    t_begin = t + t_offset                                       # :128
+    if len(mhz_xp) > 1:
+        duration = counts / (np.interp(t_begin, mhz_xp, mhz_fp) * 1e6)   # :131-132
+    else:
+        duration = counts / (3000.0 * 1e6)                       # :134
+    event = np.log10(event_raw)                                  # :136
+    if perf_events.find('cycles') == -1:
+        duration = np.log2(event_raw / 1e14)                     # :138-139
+    ids = tok[0].split('/')
+    return [t_begin, event, duration, -1, -1, 0, 0, -1, -1, int(ids[0]), int(ids[1]), name, 0]
+
+
+# --------------------------------------------------------------------------- a3
+def parse_net_packet(packet, absolute_timestamp, time_base, t_offset):
+    """One `tcpdump -q -n -tt` line -> row, or [] (non-IP / unknown protocol).
+    sofa_preprocess.py:156-201."""
+    tok = packet.split()
+    t = float(tok[0])
+    if not absolute_timestamp:
+        t = t - time_base
+    t_begin = t + t_offset
+    if tok[1] != 'IP':
+        return []                                                # :167-168
+    proto = tok[5]
+    if proto == 'UDP,':
+        payload = int(tok[7])
+    elif proto == 'tcp':
+        payload = int(tok[6])
+    else:
+        return []                                                # :175-176
+    duration = float(payload / 128.0e6)
+    src = 0
+    dst = 0
+    a = tok[2].split('.')
+    b = tok[4].split('.')
+    for i in range(4):                                           # :182-186 (np.int64 sums)
+        src = src + int(a[i]) * np.power(1000, 3 - i)
+        dst = dst + int(b[i]) * np.power(1000, 3 - i)
+    return [t_begin, payload * 100 + 17, duration, -1, -1, payload, 128.0e6, src, dst, -1, -1,
+            "network:%s:%d_to_%d_with_%d" % (proto, src, dst, payload), 0]
+
+
+# --------------------------------------------------------------------------- a2
+def parse_gpu_record(record, absolute_timestamp, time_base, indices, n_cudaproc, ts_rescale,
+                     dt_rescale, payload_unit, t_offset):
+    """One `nvprof --csv --print-gpu-trace` row -> row.  sofa_preprocess.py:249-341."""
+    v = record.replace('"', '').split(',')                       # :258 (no strip: Name keeps '\n')
+    name = v[indices.index('Name')]
+    t = float(v[indices.index('Start')]) / ts_rescale + t_offset
+    if not absolute_timestamp:
+        t = t - time_base
+    duration = float(v[indices.index('Duration')]) / dt_rescale
+    try:
+        payload = int(float(v[indices.index('Size')]) * payload_unit)
+    except BaseException:
+        payload = 0
+    try:
+        bandwidth = float(v[indices.index('Throughput')])
+    except BaseException:
+        bandwidth = 0
+    try:
+        dev = int(float(v[indices.index('Context')]))
+    except BaseException:
+        dev = -1
+    try:
+        tid = int(float(v[indices.index('Stream')]))
+    except BaseException:
+        tid = -1
+    src = dst = kind = 0
+    if name.find('HtoD') != -1:                                  # :293-323 tagging order
+        kind, src, dst = 1, 0, dev
+        name = "CUDA_COPY_H2D_%dB" % payload
+    elif name.find('DtoH') != -1:
+        kind, src, dst = 2, dev, 0
+        name = "CUDA_COPY_D2H_%dB" % payload
+    elif name.find('DtoD') != -1:
+        kind, src, dst = 8, dev, dev
+        name = "CUDA_COPY_D2D_%dB" % payload
+    elif name.find('PtoP') != -1:
+        kind = 10
+        try:
+            src = int(v[indices.index('Src Ctx')])
+        except BaseException:
+            src = 0
+        try:
+            dst = int(v[indices.index('Dst Ctx')])
+        except BaseException:
+            dst = 0
+        name = "[CUDA_COPY_P2P]from_gpu%d_to_gpu%d_%dB" % (src, dst, payload)
+    if dev != -1:
+        name = '[gpu%d]' % dev + name                            # :325-326
+    return [t, payload * 100 + 17, duration, dev, kind, payload, bandwidth, src, dst,
+            n_cudaproc, tid, name, 0]
+
+
+def gpu_units(unit_row):
+    """Unit row -> (ts_rescale, dt_rescale, payload_unit).  sofa_preprocess.py:1392-1415."""
+    u = unit_row.split(',')
+    pu = {'GB': np.power(1024, 3), 'MB': np.power(1024, 2), 'KB': np.power(1024, 1), 'B': 1}
+    if u[11] not in pu:
+        raise ValueError("The payload unit in gputrace.tmp was not recognized!")
+    scale = {'ms': 1.0e3, 'us': 1.0e6}
+    return scale.get(u[0], 1.0), scale.get(u[1], 1.0), pu[u[11]]
+
+
+# --------------------------------------------------------------------------- a6 / a7 / a9
+def downsample(rows, ratio):
+    """sofa_preprocess.py:51-57."""
+    return [rows[i] for i in range(len(rows)) if i % ratio == 0]
+
+
+def frame(rows):
+    df = pd.DataFrame(rows)
+    df.columns = FIELDNAMES
+    return df
+
+
+def write_trace_csv(df, path):
+    """sofa_preprocess.py:1206-1211 / 1439-1444 / 1802-1807."""
+    df.to_csv(path, mode='w', header=True, index=False, float_format='%.6f')
+
+
+def viz_name(x, demangle):
+    """sofa_preprocess.py:1811-1816: text between the first ']' and the first '+',
+    cut at '@', demangled."""
+    return demangle(str(x[x.find(']') + 1: x.find('+')].split('@')[0]))
+
+
+# --------------------------------------------------------------------------- a10
+class Series:
+    """One report.js series (sofa_models.py:1-7)."""
+    def __init__(self, name, title, color, data, x_field='timestamp', y_field='duration'):
+        self.name, self.title, self.color, self.data = name, title, color, data
+        self.x_field, self.y_field = x_field, y_field
+
+
+def write_report_js(series, path):
+    """sofa_preprocess.py:343-374."""
+    if len(series) == 0:
+        return
+    with open(path, 'w') as f:
+        for s in series:
+            if len(s.data) > 0:
+                f.write(s.name + " = ")
+                d = s.data.rename(columns={s.x_field: 'x', s.y_field: 'y'})
+                json.dump({"name": s.title, "color": s.color,
+                           "data": json.loads(d.to_json(orient='records'))}, f)
+            f.write("\n\n")
+        f.write("sofa_traces = [ ")
+        for s in series:
+            if len(s.data) > 0:
+                f.write(s.name + ",")
+        f.write(" ]")
+
+
+# --------------------------------------------------------------------------- driver
+class OracleConfig:
+    """The cfg attributes the hot path reads (bin/sofa:159-312 defaults)."""
+    def __init__(self, logdir, **kw):
+        self.logdir = logdir if logdir.endswith('/') else logdir + '/'
+        self.absolute_timestamp = False
+        self.cpu_time_offset = 0.0
+        self.plot_ratio = 1
+        self.cpu_filters = [("idle", "black")]
+        self.gpu_filters = [("CUDA_COPY_H2D", "Red"), ("CUDA_COPY_D2H", "Peru"),
+                            ("CUDA_COPY_P2P", "Purple"), ("_fw_", "royalblue"),
+                            ("_bw_", "darkviolet"), ("AllReduceKernel", "indigo")]
+        self.enable_mpstat = True
+        self.enable_diskstat = True
+        self.enable_vmstat = False
+        self.enable_encode_decode = False
+        self.cuda_api_tracing = False
+        self.verbose = False
+        self.nprocs = None
+        for k, v in kw.items():
+            if k == 'cpu_filters' and isinstance(v, str):
+                v = [tuple(p.split(':')) for p in v.split(',')]
+            setattr(self, k, v)
+
+
+def _pmap(fn, items, nprocs):
+    if nprocs == 1 or len(items) < 64:
+        return [fn(x) for x in items]
+    with mp.Pool(processes=nprocs or mp.cpu_count()) as pool:    # :1196, :1420, :1791
+        return pool.map(fn, items)
+
+
+def read_time_bases(cfg):
+    """time_base (:418-422), cpuinfo table (:424-436), perf_events (:1545-1551),
+    perf_timebase.txt (:1766-1784)."""
+    logdir = cfg.logdir
+    with open(logdir + 'sofa_time.txt') as f:
+        time_base = float(f.readlines()[0]) + cfg.cpu_time_offset
+    xp, fp = [0.0], [3000.0]
+    try:
+        with open(logdir + 'cpuinfo.txt') as f:
+            for line in f.readlines():
+                t = line.split()
+                xp.append(float(t[0]))
+                fp.append(float(t[1]))
+    except Exception:
+        pass
+    with open(logdir + 'perf_events_used.txt') as f:
+        lines = f.readlines()
+        perf_events = lines[0] if lines else ''
+    uptime = unix = 0
+    with open(logdir + 'perf_timebase.txt') as f:
+        lines = f.readlines()
+        if len(lines) <= 3 or lines[0].find('WARNING') != -1:
+            uptime = unix = 0
+        else:
+            try:
+                uptime = float(lines[-2].split()[2].split(':')[0])
+                unix = float(lines[-1].split()[0])
+            except Exception:
+                pass
+    return time_base, xp, fp, perf_events, unix - uptime
+
+
+def preprocess(cfg, demangle=lambda s: s, emit_json=True):
+    """perf / nvprof-gpu / tcpdump sources of sofa_preprocess (sofa_preprocess.py:377-2106),
+    reading the pre-dumped text (`gputrace.tmp`, `net.tmp`) instead of shelling out.
+    Returns the list of Series written to report.js."""
+    logdir = cfg.logdir
+    time_base, xp, fp, perf_events, cpu_t_offset = read_time_bases(cfg)
+    net_traces = []
+    filtered_net_groups = []
+    cpu_viz = []
+    filtered_cpu = []
+    gpu_viz = []
+    filtered_gpu = []
+
+    # ---- network  :1187-1232  (nettrace.csv holds the DOWN-SAMPLED rows)
+    if os.path.isfile(logdir + 'sofa.pcap') and os.path.isfile(logdir + 'net.tmp'):
+        with open(logdir + 'net.tmp') as f:
+            packets = f.readlines()
+        if packets:
+            res = _pmap(partial(parse_net_packet, absolute_timestamp=cfg.absolute_timestamp,
+                                time_base=time_base, t_offset=0), packets, cfg.nprocs)
+            net_traces = frame(downsample(res, cfg.plot_ratio))
+            write_trace_csv(net_traces, logdir + 'nettrace.csv')
+
+    # ---- GPU  :1343-1457 (single nvvp; t_glb_gpu_base = 0 when sqlite tables are unreadable)
+    if os.path.isfile(logdir + 'gputrace.tmp'):
+        with open(logdir + 'gputrace.tmp') as f:
+            records = f.readlines()
+        if len(records) > 0 and records[1].split(',')[0] == '"Start"':
+            indices = records[1].replace('"', '').replace('\n', '').split(',')
+            ts_rescale, dt_rescale, payload_unit = gpu_units(records[2])
+            records = records[3:]
+            t_base = float(records[0].split(',')[0])             # :1419 (un-rescaled)
+            res = _pmap(partial(parse_gpu_record, absolute_timestamp=cfg.absolute_timestamp,
+                                time_base=time_base, indices=indices, n_cudaproc=1,
+                                ts_rescale=ts_rescale, dt_rescale=dt_rescale,
+                                payload_unit=payload_unit, t_offset=0 - t_base),
+                        records, cfg.nprocs)
+            gpu_traces = frame(res)
+            gpu_viz = frame(downsample(res, cfg.plot_ratio))
+            write_trace_csv(gpu_traces, logdir + 'gputrace.csv')
+            for kw, color in cfg.gpu_filters:                    # :1446-1452
+                filtered_gpu.append((kw, color, gpu_traces[gpu_traces['name'].str.contains(kw)]))
+
+    # ---- CPU  :1786-1838
+    if os.path.isfile(logdir + 'perf.script'):
+        with open(logdir + 'perf.script') as f:
+            samples = f.readlines()
+        if len(samples) > 0:
+            res = _pmap(partial(parse_perf_sample, absolute_timestamp=cfg.absolute_timestamp,
+                                time_base=time_base, t_offset=cpu_t_offset, mhz_xp=xp, mhz_fp=fp,
+                                perf_events=perf_events), samples, cfg.nprocs)
+            cpu_traces = frame(res)
+            write_trace_csv(cpu_traces, logdir + 'cputrace.csv')
+            cpu_viz = frame(downsample(res, cfg.plot_ratio))
+            cpu_viz['name'] = cpu_viz['name'].apply(lambda x: viz_name(x, demangle))
+            for kw, color in cfg.cpu_filters:                    # :1819-1827
+                filtered_cpu.append((kw, color, cpu_viz[cpu_viz['name'].str.contains(kw)]))
+
+    # ---- series list  :1849-2102 (sources outside the hot path are empty placeholders)
+    series = []
+    if len(cpu_viz) > 0:
+        series.append(Series('cpu_trace', 'CPU', 'DarkGray', cpu_viz))
+        for kw, color, grp in filtered_cpu:
+            series.append(Series(kw, '[keyword]' + kw, color, grp.copy()))
+    for nm, title, color in (('blktrace_starting_block', 'BLKTRACE_STARTING_BLOCK', 'Green'),
+                             ('blktrace_time', 'BLKTRACE_TIME', 'DodgerBlue'),
+                             ('vmstat_cs', 'VMSTAT_CS', 'Pink'),
+                             ('vmstat_bi', 'VMSTAT_BI', 'DarkOrange'),
+                             ('vmstat_bo', 'VMSTAT_BO', 'DarkOrchid')):
+        series.append(Series(nm, title, color, []))
+    if cfg.enable_mpstat:
+        series.append(Series('mpstat_usr', 'MPSTAT_USR', 'Cyan', []))
+    if cfg.enable_diskstat:
+        series.append(Series('diskstat', 'DISKSTAT', 'GreenYellow', [], y_field='bandwidth'))
+    if cfg.enable_vmstat:
+        for nm in ('vmstat_usr', 'vmstat_sys', 'vmstat_in', 'vmstat_cs'):
+            series.append(Series(nm, nm.upper(), '', []))
+    for nm in ('strace', 'pystacks', 'nvsmi_mem', 'nvsmi_sm'):
+        series.append(Series(nm, nm, '', []))
+    if cfg.enable_encode_decode:
+        series.append(Series('nvsmi_enc', '', '', []))
+        series.append(Series('nvsmi_dec', '', '', []))
+    series.append(Series('net_trace', 'NET', 'blue', net_traces))
+    series.append(Series('tx_bandwidth', 'tx Bandwidth', 'rgba(135,206,250,0.8)', [], y_field='bandwidth'))
+    series.append(Series('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)', [], y_field='bandwidth'))
+    series.append(Series('gpu_kernel_trace', 'GPU kernel', 'rgba(0,180,0,0.8)', gpu_viz))
+    for kw, color, grp in filtered_gpu:
+        series.append(Series(kw, '[keyword]' + kw, color, grp.copy()))
+    if emit_json:
+        write_report_js(series, logdir + 'report.js')
+    return series
+
+
+# --------------------------------------------------------------------------- a11-a13
+def top_k_events(df, topk):
+    """sofa_analyze.py:34-44: names ordered by summed duration, descending."""
+    agg = df.groupby(['name'])['duration'].sum()
+    return agg.sort_values(ascending=False).head(topk)
+
+
+def comm_profile(df_gpu, logdir=None):
+    """sofa_common.py:23-177 -> (features dict, payload matrix, count matrix, bw matrix,
+    bw-count matrix).  Writes comm.csv when logdir is given (:160-167)."""
+    n_gpus = 0
+    dev = df_gpu['deviceId'].to_numpy()
+    for i in range(len(dev)):                                    # :54-56
+        if dev[i] > n_gpus:
+            n_gpus = int(dev[i])
+    if n_gpus == 0:
+        return None
+    kinds = (1, 2, 8, 10)
+    payload_table = {k: 0 for k in kinds}
+    for key, grp in df_gpu.groupby(by='copyKind')['payload']:    # :65-71
+        if key in payload_table:
+            payload_table[key] = grp.sum()
+    bw_table = {k: 0 for k in kinds}
+    for key, grp in df_gpu.query('payload > 64000').groupby(by='copyKind')['bandwidth']:   # :76-82
+        if key in bw_table:
+            bw_table[key] = grp.mean()
+    duration_table = {k: 0 for k in kinds}
+    for key, grp in df_gpu.groupby(by='copyKind')['duration']:   # :87-93
+        if key in duration_table:
+            duration_table[key] = grp.sum()
+    accum = np.zeros((1 + n_gpus, 1 + n_gpus))
+    accum_bw = np.zeros((1 + n_gpus, 1 + n_gpus))
+    accum_count = np.zeros((1 + n_gpus, 1 + n_gpus))
+    accum_bw_count = np.zeros((1 + n_gpus, 1 + n_gpus))
+    ck = df_gpu['copyKind'].to_numpy()
+    srcs = df_gpu['pkt_src'].to_numpy()
+    dsts = df_gpu['pkt_dst'].to_numpy()
+    pls = df_gpu['payload'].to_numpy()
+    bws = df_gpu['bandwidth'].to_numpy()
+    for i in range(len(df_gpu)):                                 # :108-119 (row order)
+        if ck[i] == 0 or ck[i] == 8:
+            continue
+        s, d = srcs[i], dsts[i]
+        accum[s][d] = float(accum[s][d] + pls[i])
+        accum_count[s][d] = int(accum_count[s][d] + 1)
+        if pls[i] > 64000:
+            accum_bw[s][d] = float(accum_bw[s][d] + bws[i])
+            accum_bw_count[s][d] = int(accum_bw_count[s][d] + 1)
+    if logdir is not None:
+        df_gpu.to_csv(logdir + '/' + 'comm.csv',
+                      columns=["timestamp", "pkt_src", "pkt_dst", "payload", "bandwidth"])
+    feats = {}
+    for nm, k in (('h2d', 1), ('d2h', 2), ('d2d', 8), ('p2p', 10)):
+        feats[nm + '_payload'] = payload_table[k]
+        feats[nm + '_bandwidth'] = bw_table[k]
+        feats[nm + '_time'] = duration_table[k]
+    return feats, accum, accum_count, accum_bw, accum_bw_count
+
+
+def gpu_profile(df_gpu, logdir=None):
+    """sofa_analyze.py:343-377 -> ordered list of (feature, value)."""
+    gpu_time = 0
+    groups = df_gpu.groupby("deviceId")["duration"]
+    for key, grp in groups:                                      # :347-355
+        gpu_time = gpu_time + grp.sum()
+    num_gpus = len(groups)
+    kernel_time = 0
+    for key, grp in df_gpu.groupby("copyKind")["duration"]:      # :357-361
+        if key == 0:
+            kernel_time = grp.sum()
+    nccl_time = 0
+    for key, grp in df_gpu.groupby("name")["duration"]:          # :363-368
+        if key.find("nccl") != -1:
+            nccl_time = nccl_time + grp.sum()
+    out = []
+    cp = comm_profile(df_gpu, logdir)
+    if cp is not None:
+        f = cp[0]
+        for nm in ('h2d_payload', 'd2h_payload', 'd2d_payload', 'p2p_payload',
+                   'h2d_bandwidth', 'd2h_bandwidth', 'd2d_bandwidth', 'p2p_bandwidth',
+                   'h2d_time', 'd2h_time', 'd2d_time', 'p2p_time'):
+            out.append((nm, f[nm]))
+    out += [('gpu_time', gpu_time), ('num_gpus', num_gpus), ('kernel_time', kernel_time),
+            ('nccl_time', nccl_time)]
+    return out
+
+
+def cpu_profile(df):
+    """sofa_analyze.py:694-710 -> (total_exec_time, top-20 frame by duration)."""
+    total = 0
+    for key, grp in df.groupby("deviceId")["duration"]:
+        total = total + grp.sum()
+    d = df[['timestamp', 'duration', 'name']].sort_values(by=['duration'], ascending=False)
+    return total, d[:20]
+
+
+# --------------------------------------------------------------------------- ujson double
+def ujson_double_str(value, precision=10):
+    """pandas' vendored ultrajson Buffer_AppendDoubleUnchecked (what `to_json` prints for a
+    float64, double_precision=10) restated for the fixed-notation range; used to pin the
+    device JSON float codec.  Returns None outside 1e-15 <= |v| <= 1e16-1 (printf path)."""
+    if value != value or value in (math.inf, -math.inf):
+        return 'null'
+    neg = value < 0
+    if neg:
+        value = -value
+    if value > 1e16 - 1 or (value != 0.0 and value < 1e-15):
+        return None
+    p10 = float(10 ** precision)
+    whole = int(value)
+    tmp = (value - whole) * p10
+    frac = int(tmp)
+    diff = tmp - frac
+    if diff > 0.5:
+        frac += 1
+    elif diff == 0.5 and (frac == 0 or (frac & 1)):
+        frac += 1
+    if frac >= p10:
+        frac = 0
+        whole += 1
+    fs = ('%0*d' % (precision, frac)).rstrip('0') or '0'
+    return ('-' if neg else '') + '%d.%s' % (whole, fs)

@@ -1,0 +1,258 @@
+"""Deterministic synthetic SOFA logdirs (test / bench infrastructure, not product).
+
+The reference ships no sample logdir, so every parity input is
+generated.  The generator is a pure function of (seed, stream, row, field)
+through a splitmix64 finaliser, so the same spec can be restated on the device
+(`csrc/synth.cu`) and the two can be compared byte for byte.
+
+File formats follow what the reference's parsers consume:
+  perf.script   -> sofa_preprocess.py:110-154  (cpu_trace_read)
+  gputrace.tmp  -> sofa_preprocess.py:249-341  (gpu_trace_read), header/unit
+                   rows :1385-1417
+  net.tmp       -> sofa_preprocess.py:156-201  (net_trace_read)
+side files: misc.txt (:387-392), sofa_time.txt (:418-422),
+perf_events_used.txt (:1545-1551), perf_timebase.txt (:1766-1784).
+"""
+import os
+
+M64 = (1 << 64) - 1
+GOLDEN = 0x9E3779B97F4A7C15
+
+STREAM_PERF = 1
+STREAM_GPU = 2
+STREAM_NET = 3
+
+TIME_BASE = 1600000000.0          # sofa_time.txt
+PERF_T0_US = 5000 * 1000000       # perf clock origin (uptime seconds)
+PERF_GAP_US = 17
+GPU_GAP_US = 23
+NET_T0_US = 1600000000 * 1000000 + 250000
+NET_GAP_US = 211
+
+WORDS = ["do_syscall_64", "schedule", "page_fault", "tcp_sendmsg",
+         "PyEval_EvalFrameDefault", "cudaLaunchKernel", "ioctl", "futex_wait",
+         "copy_user_enhanced_fast_string", "__libc_start_main",
+         "pthread_mutex_lock", "vfs_read"]
+LIBS = ["c", "pthread", "cuda", "cudart", "python3.6m", "tensorflow_framework",
+        "stdc++", "nccl"]
+KERNELS = ["volta_sgemm_128x64_nn", "volta_scudnn_128x64_relu_interior_nn_v1",
+           "maxwell_gcgemm_32x32_nt", "ncclAllReduceKernel_sum_f32",
+           "void tensorflow::functor::FillPhiloxRandomKernelLaunch<float, int=4>(float*, long)",
+           "void cudnn::detail::implicit_convolve_sgemm<float, float, int=128, int=6>(int, int)",
+           "cudnn_fw_conv_kernel", "cudnn_bw_data_kernel",
+           "void Eigen::internal::EigenMetaKernel<Eigen::TensorEvaluator>(float)",
+           "AllReduceKernel_ring_ll", "gemv2T_kernel_val", "relu_fw_elementwise"]
+NVPROF_HEADER = ('"Start","Duration","Grid X","Grid Y","Grid Z","Block X","Block Y",'
+                 '"Block Z","Registers Per Thread","Static SMem","Dynamic SMem","Size",'
+                 '"Throughput","SrcMemType","DstMemType","Device","Context","Stream","Name"')
+NVPROF_HEADER_P2P = ('"Start","Duration","Grid X","Grid Y","Grid Z","Block X","Block Y",'
+                     '"Block Z","Registers Per Thread","Static SMem","Dynamic SMem","Size",'
+                     '"Throughput","SrcMemType","DstMemType","Device","Context","Stream",'
+                     '"Src Dev","Src Ctx","Dst Dev","Dst Ctx","Name"')
+
+
+def mix64(x):
+    x &= M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
+    return x ^ (x >> 31)
+
+
+def rnd(seed, stream, i, f):
+    """64 random bits for (seed, stream, row i, field f)."""
+    return mix64(seed + ((stream << 58) ^ ((i * 16 + f + 1) * GOLDEN)))
+
+
+def perf_symbol(k):
+    """Symbol text for dictionary slot k in [0, 4096). Returns (sym, has_off)."""
+    t = k % 16
+    if t == 0:
+        return "[unknown]", False
+    if t == 1:
+        return "cpu_idle_poll_%d" % k, True
+    if t == 2:
+        nm = "Op%dKernel" % k
+        return "_ZN10tensorflow%d%s7ComputeEv" % (len(nm), nm), True
+    if t == 3:
+        nm = "gemm_pack_%d" % k
+        return "_ZN5Eigen8internal%d%s3runEv" % (len(nm), nm), True
+    if t == 4:
+        return "memcpy_%d@plt" % k, True
+    return "%s_%d" % (WORDS[k % 12], k), True
+
+
+def perf_line(seed, i, cpu_col=False):
+    r0 = rnd(seed, STREAM_PERF, i, 0)
+    r1 = rnd(seed, STREAM_PERF, i, 1)
+    r2 = rnd(seed, STREAM_PERF, i, 2)
+    r3 = rnd(seed, STREAM_PERF, i, 3)
+    pid = 4242
+    tid = 4242 + (((r0 & 63) * ((r0 >> 6) & 63)) >> 6)
+    us = PERF_T0_US + i * PERF_GAP_US + (r0 >> 12) % PERF_GAP_US
+    period = 1 + (r1 % 3000000)
+    kernel_ip = (r2 % 10) < 3
+    if kernel_ip:
+        ip = 0xffffffff80000000 | ((r2 >> 8) & 0x0fffffff)
+    else:
+        ip = 0x7f0000000000 | ((r2 >> 8) & 0xffffffffff)
+    r20 = r3 & 0xfffff
+    k = (r20 * r20 * r20) >> 48
+    sym, has_off = perf_symbol(k)
+    if has_off:
+        sym = "%s+0x%x" % (sym, (r3 >> 20) & 0xfff)
+    if kernel_ip:
+        dso = "([kernel.kallsyms])"
+    else:
+        j = (r3 >> 32) & 63
+        dso = "(/usr/lib/x86_64-linux-gnu/lib%s.so.%d)" % (LIBS[j & 7], j)
+    cpu = " [%03d]" % ((r1 >> 32) & 63) if cpu_col else ""
+    return "%5d/%-5d%s %7d.%06d: %10d cycles:  %16x %s %s\n" % (
+        pid, tid, cpu, us // 1000000, us % 1000000, period, ip, sym, dso)
+
+
+def gpu_header(units="s_ms", p2p_cols=False):
+    """Three header rows of `nvprof --csv --print-gpu-trace` (banner, names, units)."""
+    hdr = NVPROF_HEADER_P2P if p2p_cols else NVPROF_HEADER
+    ncol = hdr.count(',') + 1
+    if units == "s_ms":
+        u = ["s", "ms", "", "", "", "", "", "", "", "B", "B", "MB", "GB/s"]
+    elif units == "ms_us_KB":
+        u = ["ms", "us", "", "", "", "", "", "", "", "B", "B", "KB", "GB/s"]
+    elif units == "us_us_B":
+        u = ["us", "us", "", "", "", "", "", "", "", "B", "B", "B", "GB/s"]
+    else:
+        raise ValueError(units)
+    u = u + [""] * (ncol - len(u))
+    return "==4242== Profiling result:\n" + hdr + "\n" + ",".join(u) + "\n"
+
+
+def gpu_line(seed, i, units="s_ms", p2p_cols=False):
+    r0 = rnd(seed, STREAM_GPU, i, 0)
+    r1 = rnd(seed, STREAM_GPU, i, 1)
+    r2 = rnd(seed, STREAM_GPU, i, 2)
+    us = 350000 + i * GPU_GAP_US + (r0 >> 12) % GPU_GAP_US   # since CUPTI start
+    dur_ns = 800 + (r1 % 4000) * (1 + ((r1 >> 16) & 255))
+    if units == "s_ms":
+        start = "%d.%06d" % (us // 1000000, us % 1000000)
+        dur = "%d.%06d" % (dur_ns // 1000000, dur_ns % 1000000)
+    elif units == "ms_us_KB":
+        start = "%d.%03d" % (us // 1000, us % 1000)
+        dur = "%d.%03d" % (dur_ns // 1000, dur_ns % 1000)
+    else:
+        start = "%d.000000" % us
+        dur = "%d.%03d" % (dur_ns // 1000, dur_ns % 1000)
+    ctx = 1 + ((r0 >> 4) & 7)
+    stream = 7 + ((r0 >> 7) & 31)
+    dev = '"Tesla V100-SXM2-16GB (%d)"' % (ctx - 1)
+    kind = r2 % 100
+    p2p = ",,,," if p2p_cols else ""
+    if kind < 85:
+        k = (r2 >> 8) % 512
+        base = KERNELS[k % 12]
+        name = base if k < 12 else "%s_v%d" % (base, k)
+        gx = 1 + ((r2 >> 20) & 1023)
+        bx = 32 << ((r2 >> 30) & 3)
+        regs = 16 + ((r2 >> 32) & 63)
+        return '%s,%s,%d,1,1,%d,1,1,%d,0,0,,,,,%s,"%d","%d",%s"%s"\n' % (
+            start, dur, gx, bx, regs, dev, ctx, stream, p2p, name)
+    nbytes = 4 << ((r2 >> 8) % 24)
+    if units == "s_ms":
+        size = "%d.%06d" % (nbytes >> 20, ((nbytes & 0xfffff) * 1000000) >> 20)
+    elif units == "ms_us_KB":
+        size = "%d.%06d" % (nbytes >> 10, ((nbytes & 0x3ff) * 1000000) >> 10)
+    else:
+        size = "%d" % nbytes
+    thr = 1000 + (r2 >> 40) % 24000000
+    thr_s = "%d.%06d" % (thr // 1000000, thr % 1000000)
+    if kind < 91:
+        name, sm, dm = "[CUDA memcpy HtoD]", "Pageable", "Device"
+    elif kind < 96:
+        name, sm, dm = "[CUDA memcpy DtoH]", "Device", "Pageable"
+    elif kind < 98:
+        name, sm, dm = "[CUDA memcpy DtoD]", "Device", "Device"
+    else:
+        name, sm, dm = "[CUDA memcpy PtoP]", "Device", "Device"
+        if p2p_cols:
+            sc = 1 + ((r2 >> 16) & 7)
+            dc = 1 + ((r2 >> 19) & 7)
+            p2p = '"dev (%d)","%d","dev (%d)","%d",' % (sc - 1, sc, dc - 1, dc)
+    return '%s,%s,,,,,,,,,,%s,%s,"%s","%s",%s,"%d","%d",%s"%s"\n' % (
+        start, dur, size, thr_s, sm, dm, dev, ctx, stream, p2p, name)
+
+
+def net_line(seed, i, non_ip_pct=1):
+    r0 = rnd(seed, STREAM_NET, i, 0)
+    r1 = rnd(seed, STREAM_NET, i, 1)
+    us = NET_T0_US + i * NET_GAP_US + (r0 >> 12) % NET_GAP_US
+    ts = "%d.%06d" % (us // 1000000, us % 1000000)
+    sel = r1 % 100
+    if sel < non_ip_pct:
+        if (r1 >> 8) & 1:
+            return "%s ARP, Request who-has 10.0.0.%d tell 10.0.0.%d, length 28\n" % (
+                ts, 1 + ((r1 >> 16) & 15), 1 + ((r1 >> 20) & 15))
+        return "%s IP 10.0.0.%d > 10.0.0.%d: ICMP echo request, id 7, seq %d, length 64\n" % (
+            ts, 1 + ((r1 >> 16) & 15), 1 + ((r1 >> 20) & 15), (r1 >> 24) & 1023)
+    src = "10.0.%d.%d" % ((r0 >> 4) & 1, 1 + ((r0 >> 5) & 15))
+    dst = "10.0.%d.%d" % ((r0 >> 9) & 1, 1 + ((r0 >> 10) & 15))
+    sport = 1024 + ((r1 >> 8) & 0x7fff)
+    dport = 1024 + ((r1 >> 24) & 0x7fff)
+    if (r1 >> 40) % 4 == 0:
+        return "%s IP %s.%d > %s.%d: UDP, length %d\n" % (
+            ts, src, sport, dst, dport, (r1 >> 44) % 1473)
+    return "%s IP %s.%d > %s.%d: tcp %d\n" % (
+        ts, src, sport, dst, dport, (r1 >> 44) % 65536)
+
+
+def perf_text(seed, n, cpu_col=False):
+    return "".join(perf_line(seed, i, cpu_col) for i in range(n))
+
+
+def gpu_text(seed, n, units="s_ms", p2p_cols=False):
+    return gpu_header(units, p2p_cols) + "".join(
+        gpu_line(seed, i, units, p2p_cols) for i in range(n))
+
+
+def net_text(seed, n, non_ip_pct=1):
+    return "".join(net_line(seed, i, non_ip_pct) for i in range(n))
+
+
+def write_side_files(logdir, elapsed=12.5, perf_events="cycles", cpuinfo=None):
+    """misc.txt / sofa_time.txt / perf_events_used.txt / perf_timebase.txt as the
+    recorder writes them (sofa_record.py:236-247, 356-357, 416-431)."""
+    os.makedirs(logdir, exist_ok=True)
+    with open(os.path.join(logdir, "misc.txt"), "w") as f:
+        f.write("elapsed_time %.6f\ncores 64\nvcores 64\npid 4242\n" % elapsed)
+    with open(os.path.join(logdir, "sofa_time.txt"), "w") as f:
+        f.write("%.1f\n" % TIME_BASE)
+    with open(os.path.join(logdir, "perf_events_used.txt"), "w") as f:
+        f.write(perf_events)
+    with open(os.path.join(logdir, "perf_timebase.txt"), "w") as f:
+        # last two lines: a perf-script sample (uptime clock) and a unix timestamp
+        f.write("[ perf record: Woken up 1 times to write data ]\n")
+        f.write("[ perf record: Captured and wrote 0.012 MB perf.data (8 samples) ]\n")
+        f.write("ls  4300 4999.500000:     1 cycles:  ffffffff8106315a native_write_msr_safe\n")
+        f.write("1600000000.250000 0\n")
+    if cpuinfo:
+        with open(os.path.join(logdir, "cpuinfo.txt"), "w") as f:
+            for t, mhz in cpuinfo:
+                f.write("%.6f %.3f\n" % (t, mhz))
+
+
+def make_logdir(logdir, seed, n_perf=0, n_gpu=0, n_net=0, cpu_col=False,
+                units="s_ms", p2p_cols=False, non_ip_pct=1, perf_events="cycles",
+                cpuinfo=None):
+    """Write a complete synthetic logdir. GPU / net sources are written as the
+    text dumps (`gputrace.tmp`, `net.tmp`) plus the marker files the reference
+    globs for (`gputrace1.nvvp`, `sofa.pcap`)."""
+    write_side_files(logdir, perf_events=perf_events, cpuinfo=cpuinfo)
+    if n_perf:
+        with open(os.path.join(logdir, "perf.script"), "w") as f:
+            f.write(perf_text(seed, n_perf, cpu_col))
+    if n_gpu:
+        with open(os.path.join(logdir, "gputrace.tmp"), "w") as f:
+            f.write(gpu_text(seed, n_gpu, units, p2p_cols))
+        open(os.path.join(logdir, "gputrace1.nvvp"), "w").close()
+    if n_net:
+        with open(os.path.join(logdir, "net.tmp"), "w") as f:
+            f.write(net_text(seed, n_net, non_ip_pct))
+        open(os.path.join(logdir, "sofa.pcap"), "w").close()

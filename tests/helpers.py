@@ -1,0 +1,59 @@
+"""Shared test helpers: golden cases, oracle runner, libstdc++ demangler."""
+import ctypes
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from sofa_b200 import synth  # noqa: E402
+
+
+def golden_cases():
+    out = []
+    for name in sorted(os.listdir(GOLDEN)):
+        p = os.path.join(GOLDEN, name, "case.json")
+        if os.path.isfile(p):
+            out.append(name)
+    return out
+
+
+def load_case(name):
+    with open(os.path.join(GOLDEN, name, "case.json")) as f:
+        return json.load(f)
+
+
+def golden_bytes(name, fn):
+    p = os.path.join(GOLDEN, name, fn)
+    if not os.path.isfile(p):
+        return None
+    with open(p, "rb") as f:
+        return f.read()
+
+
+def demangle(name):
+    """libstdc++ __cxa_demangle, i.e. what cxxfilt.demangle wraps."""
+    if not name.startswith("_Z"):
+        return name
+    lib = ctypes.CDLL("libstdc++.so.6")
+    libc = ctypes.CDLL("libc.so.6")
+    lib.__cxa_demangle.restype = ctypes.c_void_p
+    status = ctypes.c_int(0)
+    p = lib.__cxa_demangle(name.encode(), None, None, ctypes.byref(status))
+    if status.value != 0 or not p:
+        raise ValueError("InvalidName: %s" % name)
+    s = ctypes.string_at(p).decode()
+    libc.free.argtypes = [ctypes.c_void_p]
+    libc.free(p)
+    return s
+
+
+def build_case_logdir(name, tmpdir):
+    case = load_case(name)
+    logdir = os.path.join(str(tmpdir), "sofalog") + "/"
+    synth.make_logdir(logdir, **case["make_logdir"])
+    return case, logdir

@@ -1,0 +1,42 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden)."""
+import os
+
+import pandas as pd
+import pytest
+
+from helpers import golden_cases, golden_bytes, build_case_logdir, demangle
+from oracle import sofa_oracle as orc
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_reproduces_reference_files(name, tmp_path):
+    case, logdir = build_case_logdir(name, tmp_path)
+    cfg = orc.OracleConfig(logdir, nprocs=1, **case["cfg"])
+    orc.preprocess(cfg, demangle=demangle)
+    checked = 0
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+        want = golden_bytes(name, fn)
+        if want is None:
+            assert not os.path.isfile(logdir + fn)
+            continue
+        with open(logdir + fn, "rb") as f:
+            got = f.read()
+        assert got == want, "%s/%s differs from the reference's output" % (name, fn)
+        checked += 1
+    assert checked >= 2
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if golden_bytes(n, "gputrace.csv")])
+def test_oracle_gpu_profile_matches_reference(name, tmp_path):
+    case, logdir = build_case_logdir(name, tmp_path)
+    cfg = orc.OracleConfig(logdir, nprocs=1, **case["cfg"])
+    orc.preprocess(cfg, demangle=demangle, emit_json=False)
+    df = pd.read_csv(logdir + "gputrace.csv")
+    feats = dict(orc.gpu_profile(df, logdir))
+    want = case["features"]
+    for k, v in want.items():
+        if k == "elapsed_time":
+            continue
+        assert float(feats[k]) == v, k
+    with open(logdir + "comm.csv", "rb") as f:
+        assert f.read() == golden_bytes(name, "comm.csv")
