@@ -1,0 +1,542 @@
+// Exact number codecs shared by every kernel (and compiled for the host by the
+// CPU unit-test harness tests/hostsim.cpp, so the arithmetic is checked in the
+// build container as well as on the B200).
+//
+//   parse_double   == Python float(str)            (sofa_preprocess.py:115,117,161,261,266,...)
+//   parse_i64      == Python int(str)              (:150-151,171-173,183-186,306-312)
+//   fmt_fixed6     == glibc printf("%.6f")         (to_csv float_format, :1206-1211,1439-1444,1802-1807)
+//   json_double    == pandas to_json (ujson, 10 digits) -> json.loads -> float.__repr__  (:343-374)
+//   log10_cr/log2_cr == correctly rounded log (np.log10 :136, np.log2 :139)
+//   interp1        == np.interp scalar path (:132)
+//
+// All double arithmetic that must match the reference operation-for-operation goes
+// through d_add/d_mul/d_div so that nvcc never contracts it into FMAs.
+#pragma once
+#include <stdint.h>
+#include "log_tables.inc"
+
+#if defined(__CUDACC__)
+#define SOFA_HD __host__ __device__ __forceinline__
+#else
+#define SOFA_HD inline
+#endif
+
+namespace sofa {
+
+typedef unsigned __int128 u128;
+
+enum { P_OK = 0, P_INVALID = 1, P_UNSUPPORTED = 2 };
+
+// ----------------------------------------------------------------------------- tables
+#define SOFA_P10D_INIT {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, \
+                        1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22}
+#define SOFA_P10U_INIT {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, \
+                        100000000ull, 1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, \
+                        10000000000000ull, 100000000000000ull, 1000000000000000ull, 10000000000000000ull, \
+                        100000000000000000ull, 1000000000000000000ull, 10000000000000000000ull}
+static const double h_P10D[23] = SOFA_P10D_INIT;
+static const uint64_t h_P10U[20] = SOFA_P10U_INIT;
+static const double h_LOG_INV[128] = SOFA_LOG_INV_INIT;
+static const double h_L10_HI[128] = SOFA_L10_HI_INIT;
+static const double h_L10_LO[128] = SOFA_L10_LO_INIT;
+static const double h_L2_HI[128] = SOFA_L2_HI_INIT;
+static const double h_L2_LO[128] = SOFA_L2_LO_INIT;
+#if defined(__CUDACC__)
+static __device__ const double d_P10D[23] = SOFA_P10D_INIT;
+static __device__ const uint64_t d_P10U[20] = SOFA_P10U_INIT;
+static __device__ const double d_LOG_INV[128] = SOFA_LOG_INV_INIT;
+static __device__ const double d_L10_HI[128] = SOFA_L10_HI_INIT;
+static __device__ const double d_L10_LO[128] = SOFA_L10_LO_INIT;
+static __device__ const double d_L2_HI[128] = SOFA_L2_HI_INIT;
+static __device__ const double d_L2_LO[128] = SOFA_L2_LO_INIT;
+#endif
+#if defined(__CUDA_ARCH__)
+#define SOFA_TAB(name) d_##name
+#else
+#define SOFA_TAB(name) h_##name
+#endif
+
+// ----------------------------------------------------------------------------- IEEE ops
+SOFA_HD double d_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+SOFA_HD double d_sub(double a, double b) { return d_add(a, -b); }
+SOFA_HD double d_mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+SOFA_HD double d_div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+SOFA_HD double d_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+SOFA_HD uint64_t d_bits(double x) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u; __builtin_memcpy(&u, &x, 8); return u;
+#endif
+}
+SOFA_HD double bits_d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double x; __builtin_memcpy(&x, &u, 8); return x;
+#endif
+}
+SOFA_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+SOFA_HD int bitlen128(u128 v) {
+    uint64_t hi = (uint64_t)(v >> 64), lo = (uint64_t)v;
+    return hi ? 128 - clz64(hi) : 64 - clz64(lo);
+}
+// exact 2^e for -1022 <= e <= 1023
+SOFA_HD double pow2d(int e) { return bits_d((uint64_t)(e + 1023) << 52); }
+
+SOFA_HD bool is_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31); }
+
+// Round the integer q * 2^e2 (sticky = "there are non-zero bits below q") to the nearest
+// double, ties to even.  Result must be a normal double (callers guarantee the range).
+SOFA_HD double round_u128(u128 q, int e2, bool sticky) {
+    int bl = bitlen128(q);
+    if (bl <= 53) {
+        // exact unless sticky (callers only pass sticky with bl >= 64)
+        return d_mul((double)(uint64_t)q, pow2d(e2));
+    }
+    int sh = bl - 53;
+    uint64_t mant = (uint64_t)(q >> sh);
+    bool rb = (uint64_t)(q >> (sh - 1)) & 1;
+    bool st = sticky || ((q & ((((u128)1) << (sh - 1)) - 1)) != 0);
+    if (rb && (st || (mant & 1))) mant++;
+    return d_mul((double)mant, pow2d(e2 + sh));
+}
+
+// ----------------------------------------------------------------------------- decimal -> double
+// value = (-1)^neg * w * 10^e10, correctly rounded.  Supported: w < 2^53 with |e10| <= 22
+// (one exact IEEE operation) or |e10| <= 19 (128-bit integer arithmetic).
+SOFA_HD int dec_to_double(uint64_t w, int e10, bool neg, double* out) {
+    double r;
+    if (w == 0) {
+        r = 0.0;
+    } else if (w < (1ull << 53) && e10 >= -22 && e10 <= 22) {
+        r = (double)w;
+        r = e10 < 0 ? d_div(r, SOFA_TAB(P10D)[-e10]) : d_mul(r, SOFA_TAB(P10D)[e10]);
+    } else if (e10 >= 0 && e10 <= 19) {
+        r = round_u128((u128)w * SOFA_TAB(P10U)[e10], 0, false);
+    } else if (e10 < 0 && e10 >= -19) {
+        uint64_t d = SOFA_TAB(P10U)[-e10];
+        int s = 64 + clz64(w);                 // w << s has its top bit at bit 127
+        u128 num = (u128)w << s;
+        u128 q = num / d;
+        u128 rem = num - q * d;
+        r = round_u128(q, -s, rem != 0);
+    } else {
+        return P_UNSUPPORTED;
+    }
+    *out = neg ? -r : r;
+    return P_OK;
+}
+
+// Python float(s[0:n]).  P_INVALID = Python raises ValueError; P_UNSUPPORTED = Python
+// accepts it (underscores, inf/nan, > 19 significant digits, huge exponents) but this
+// codec does not: callers must fail loudly.
+template <typename S>
+SOFA_HD int parse_double(S s, int n, double* out) {
+    int i = 0;
+    while (i < n && is_space((unsigned char)s[i])) i++;
+    while (n > i && is_space((unsigned char)s[n - 1])) n--;
+    if (i >= n) return P_INVALID;
+    bool neg = false;
+    if (s[i] == '+' || s[i] == '-') { neg = (s[i] == '-'); i++; }
+    uint64_t w = 0;
+    int nd = 0, e10 = 0;
+    bool any = false, lost = false;
+    for (; i < n; i++) {
+        unsigned c = (unsigned char)s[i] - '0';
+        if (c > 9) break;
+        any = true;
+        if (nd < 19) { if (w | c) { w = w * 10 + c; nd++; } }
+        else { e10++; lost |= (c != 0); }
+    }
+    if (i < n && s[i] == '.') {
+        i++;
+        for (; i < n; i++) {
+            unsigned c = (unsigned char)s[i] - '0';
+            if (c > 9) break;
+            any = true;
+            if (nd < 19) { if (w | c) { w = w * 10 + c; nd++; } e10--; }
+            else lost |= (c != 0);
+        }
+    }
+    if (any && i < n && (s[i] == 'e' || s[i] == 'E')) {
+        int j = i + 1;
+        bool eneg = false;
+        if (j < n && (s[j] == '+' || s[j] == '-')) { eneg = (s[j] == '-'); j++; }
+        int ex = 0, nde = 0;
+        for (; j < n; j++) {
+            unsigned c = (unsigned char)s[j] - '0';
+            if (c > 9) break;
+            if (ex < 100000) ex = ex * 10 + (int)c;
+            nde++;
+        }
+        if (nde == 0) return P_INVALID;
+        e10 += eneg ? -ex : ex;
+        i = j;
+    }
+    if (!any || i != n) {
+        // Python-valid spellings this codec refuses: digit-group underscores, inf / nan.
+        for (int k = 0; k < n; k++) {
+            char c = s[k];
+            if (c == '_' || c == 'i' || c == 'I' || c == 'n' || c == 'N') return P_UNSUPPORTED;
+        }
+        return P_INVALID;
+    }
+    if (lost) {
+        // > 19 significant digits: the value lies strictly between w and w+1 (times 10^e10);
+        // accept when both ends round to the same double, refuse otherwise.
+        double a, b;
+        int s1 = dec_to_double(w, e10, neg, &a);
+        int s2 = dec_to_double(w + 1, e10, neg, &b);
+        if (s1 != P_OK || s2 != P_OK || a != b) return P_UNSUPPORTED;
+        *out = a;
+        return P_OK;
+    }
+    return dec_to_double(w, e10, neg, out);
+}
+
+// Python int(s[0:n]) for plain decimal spellings.
+template <typename S>
+SOFA_HD int parse_i64(S s, int n, int64_t* out) {
+    int i = 0;
+    while (i < n && is_space((unsigned char)s[i])) i++;
+    while (n > i && is_space((unsigned char)s[n - 1])) n--;
+    if (i >= n) return P_INVALID;
+    bool neg = false;
+    if (s[i] == '+' || s[i] == '-') { neg = (s[i] == '-'); i++; }
+    if (i >= n) return P_INVALID;
+    uint64_t v = 0;
+    for (; i < n; i++) {
+        unsigned c = (unsigned char)s[i] - '0';
+        if (c > 9) return s[i] == '_' ? P_UNSUPPORTED : P_INVALID;
+        if (v > 922337203685477580ull) return P_UNSUPPORTED;
+        v = v * 10 + c;
+    }
+    if (v > 9223372036854775807ull) return P_UNSUPPORTED;
+    *out = neg ? -(int64_t)v : (int64_t)v;
+    return P_OK;
+}
+
+// ----------------------------------------------------------------------------- integer -> text
+SOFA_HD int ndigits_u64(uint64_t v) {
+    int n = 1;
+    if (v >= 10000000000000000ull) { v /= 10000000000000000ull; n += 16; }
+    if (v >= 100000000ull) { v /= 100000000ull; n += 8; }
+    if (v >= 10000ull) { v /= 10000ull; n += 4; }
+    if (v >= 100ull) { v /= 100ull; n += 2; }
+    if (v >= 10ull) n += 1;
+    return n;
+}
+template <typename O>
+SOFA_HD int fmt_u64(uint64_t v, O out) {
+    int n = ndigits_u64(v);
+    for (int i = n - 1; i >= 0; i--) { out[i] = (char)('0' + (v % 10)); v /= 10; }
+    return n;
+}
+template <typename O>
+SOFA_HD void fmt_u64_pad(uint64_t v, int width, O out) {       // zero padded, exactly `width`
+    for (int i = width - 1; i >= 0; i--) { out[i] = (char)('0' + (v % 10)); v /= 10; }
+}
+template <typename O>
+SOFA_HD int fmt_i64(int64_t v, O out) {
+    if (v < 0) { out[0] = '-'; return 1 + fmt_u64((uint64_t)0 - (uint64_t)v, out + 1); }
+    return fmt_u64((uint64_t)v, out);
+}
+SOFA_HD int len_i64(int64_t v) {
+    return v < 0 ? 1 + ndigits_u64((uint64_t)0 - (uint64_t)v) : ndigits_u64((uint64_t)v);
+}
+
+// ----------------------------------------------------------------------------- "%.6f"
+// Splits |x| (finite, < 2^63) into integer part and round-half-even(frac * 10^6) on the
+// exact binary value, as glibc does.  Returns false when |x| >= 2^63.
+SOFA_HD bool fixed6_parts(double x, bool* neg, uint64_t* ip, uint32_t* fp) {
+    uint64_t b = d_bits(x);
+    *neg = (b >> 63) != 0;
+    int be = (int)((b >> 52) & 0x7ff);
+    uint64_t m = b & 0xfffffffffffffull;
+    int e;
+    if (be == 0) { e = -1074; } else { m |= 1ull << 52; e = be - 1075; }
+    if (e >= 11) return false;
+    uint64_t I, F = 0;
+    if (e >= 0) {
+        I = m << e;
+    } else {
+        int s = -e;
+        uint64_t fm;
+        if (s >= 64) { I = 0; fm = m; } else { I = m >> s; fm = m & ((1ull << s) - 1); }
+        if (s < 74) {
+            u128 P = (u128)fm * 1000000u;
+            u128 q = P >> s;
+            u128 rem = P - (q << s);
+            u128 half = ((u128)1) << (s - 1);
+            if (rem > half || (rem == half && ((uint64_t)q & 1))) q += 1;
+            F = (uint64_t)q;
+            if (F == 1000000u) { I++; F = 0; }
+        }
+    }
+    *ip = I; *fp = (uint32_t)F;
+    return true;
+}
+SOFA_HD int len_fixed6(double x) {          // length of "%.6f" (x finite, |x| < 2^63), -1 otherwise
+    bool neg; uint64_t I; uint32_t F;
+    if (!fixed6_parts(x, &neg, &I, &F)) return -1;
+    return (neg ? 1 : 0) + ndigits_u64(I) + 7;
+}
+template <typename O>
+SOFA_HD int fmt_fixed6(double x, O out) {
+    bool neg; uint64_t I; uint32_t F;
+    if (!fixed6_parts(x, &neg, &I, &F)) return -1;
+    int n = 0;
+    if (neg) out[n++] = '-';
+    n += fmt_u64(I, out + n);
+    out[n++] = '.';
+    fmt_u64_pad(F, 6, out + n);
+    return n + 6;
+}
+
+// ----------------------------------------------------------------------------- report.js floats
+// pandas to_json prints float64 with its vendored ultrajson: whole part, then
+// (value - whole) * 1e10 evaluated in double with its own half rule; json.loads turns that
+// decimal string back into a double y; json.dump prints repr(y) (shortest round trip).
+// Returns the length written (<= 32), or -1 for magnitudes outside the fixed-notation
+// range of ultrajson (|v| > 1e16 or 0 < |v| < 1e-15), which this codec does not cover.
+template <typename O>
+SOFA_HD int json_double(double x, O out) {
+    uint64_t xb = d_bits(x);
+    if (((xb >> 52) & 0x7ff) == 0x7ff) { out[0] = 'n'; out[1] = 'u'; out[2] = 'l'; out[3] = 'l'; return 4; }
+    bool neg = x < 0;
+    double v = neg ? -x : x;
+    if (v > 1e16 || (v != 0.0 && v < 1e-15)) return -1;
+    uint64_t whole = (uint64_t)v;
+    double tmp = d_mul(d_sub(v, (double)whole), 1e10);
+    uint64_t frac = (uint64_t)tmp;
+    double diff = d_sub(tmp, (double)frac);
+    if (diff > 0.5) ++frac;
+    else if (diff == 0.5 && (frac == 0 || (frac & 1))) ++frac;
+    if (frac >= 10000000000ull) { frac = 0; ++whole; }
+    int n = 0;
+    if (neg) out[n++] = '-';
+    if (whole < 100000ull) {
+        // <= 15 significant digits: the decimal string itself is the shortest repr of y
+        if (whole > 0 || frac >= 1000000ull || frac == 0) {
+            n += fmt_u64(whole, out + n);
+            out[n++] = '.';
+            if (frac == 0) { out[n++] = '0'; return n; }
+            int nz = 10;
+            while (frac % 10 == 0) { frac /= 10; nz--; }
+            fmt_u64_pad(frac, nz, out + n);
+            return n + nz;
+        }
+        // 0 < y < 1e-4: Python repr switches to exponent notation ("2.9e-09", "1e-10")
+        int ex = 11 - ndigits_u64(frac);          // 5..10
+        while (frac % 10 == 0) frac /= 10;
+        int L = ndigits_u64(frac);
+        char ds[8];
+        fmt_u64(frac, ds);
+        out[n++] = ds[0];
+        if (L > 1) { out[n++] = '.'; for (int k = 1; k < L; k++) out[n++] = ds[k]; }
+        out[n++] = 'e'; out[n++] = '-';
+        out[n++] = (char)('0' + ex / 10); out[n++] = (char)('0' + ex % 10);
+        return n;
+    }
+    // ---- whole >= 1e5: y = v when v >= 2^19 (the 10-digit decimal is within half an ulp),
+    // else y = (whole*1e10 + frac) / 1e10 (numerator < 2^53, one exact division)
+    double y = v;
+    if (whole < 524288ull) y = d_div((double)(whole * 10000000000ull + frac), 1e10);
+    uint64_t yb = d_bits(y);
+    int e = (int)((yb >> 52) & 0x7ff) - 1075;
+    uint64_t m = (yb & 0xfffffffffffffull) | (1ull << 52);
+    if (e >= 0) {                       // integer valued (< 1e16): all digits, then ".0"
+        n += fmt_u64(m << e, out + n);
+        out[n++] = '.'; out[n++] = '0';
+        return n;
+    }
+    int s = -e;                         // 1..36 because y >= 1e5 > 2^16
+    uint64_t I = m >> s;
+    uint64_t r0 = m & ((1ull << s) - 1);
+    if (r0 == 0) {
+        n += fmt_u64(I, out + n);
+        out[n++] = '.'; out[n++] = '0';
+        return n;
+    }
+    bool even = (m & 1) == 0;
+    bool pow2 = (m == (1ull << 52));    // lower neighbour is half as far
+    u128 one = ((u128)1) << s;
+    uint64_t p10 = 1;
+    for (int j = 1; j <= 12; j++) {
+        p10 *= 10;
+        u128 F = (u128)r0 * p10;
+        u128 fl = F >> s;
+        u128 rem = F - (fl << s);
+        u128 up = one - rem;
+        // candidate below y: distance rem / (2^s 10^j); half gap 2^-(s+1) (2^-(s+2) at a power of two)
+        u128 lo_lhs = pow2 ? rem * 4 : rem * 2;
+        bool lo_ok = (lo_lhs < (u128)p10) || (even && lo_lhs == (u128)p10);
+        u128 hi_lhs = up * 2;
+        bool hi_ok = (hi_lhs < (u128)p10) || (even && hi_lhs == (u128)p10);
+        if (!(lo_ok || hi_ok)) continue;
+        uint64_t dg = (uint64_t)fl;
+        bool take_hi;
+        if (lo_ok && hi_ok) take_hi = (up < rem) || (up == rem && (dg & 1));
+        else take_hi = hi_ok;
+        if (take_hi) dg++;
+        if (dg == p10) { I++; n += fmt_u64(I, out + n); out[n++] = '.'; out[n++] = '0'; return n; }
+        n += fmt_u64(I, out + n);
+        out[n++] = '.';
+        fmt_u64_pad(dg, j, out + n);
+        return n + j;
+    }
+    return -1;
+}
+
+// ----------------------------------------------------------------------------- double-double
+struct dd { double hi, lo; };
+SOFA_HD dd two_sum(double a, double b) {
+    double s = d_add(a, b);
+    double bb = d_sub(s, a);
+    double e = d_add(d_sub(a, d_sub(s, bb)), d_sub(b, bb));
+    return dd{s, e};
+}
+SOFA_HD dd fast_two_sum(double a, double b) {      // |a| >= |b|
+    double s = d_add(a, b);
+    return dd{s, d_sub(b, d_sub(s, a))};
+}
+SOFA_HD dd two_prod(double a, double b) {
+    double p = d_mul(a, b);
+    return dd{p, d_fma(a, b, -p)};
+}
+SOFA_HD dd dd_add(dd a, dd b) {
+    dd s = two_sum(a.hi, b.hi);
+    dd t = two_sum(a.lo, b.lo);
+    s.lo = d_add(s.lo, t.hi);
+    s = fast_two_sum(s.hi, s.lo);
+    s.lo = d_add(s.lo, t.lo);
+    return fast_two_sum(s.hi, s.lo);
+}
+SOFA_HD dd dd_add_d(dd a, double b) {
+    dd s = two_sum(a.hi, b);
+    s.lo = d_add(s.lo, a.lo);
+    return fast_two_sum(s.hi, s.lo);
+}
+SOFA_HD dd dd_mul(dd a, dd b) {
+    dd p = two_prod(a.hi, b.hi);
+    p.lo = d_add(p.lo, d_add(d_mul(a.hi, b.lo), d_mul(a.lo, b.hi)));
+    return fast_two_sum(p.hi, p.lo);
+}
+SOFA_HD dd dd_mul_d(dd a, double b) {
+    dd p = two_prod(a.hi, b);
+    p.lo = d_add(p.lo, d_mul(a.lo, b));
+    return fast_two_sum(p.hi, p.lo);
+}
+
+// ln(1 + r) as a double-double, |r| <= 2^-7, absolute error < 2^-80.
+SOFA_HD dd log1p_dd(double r) {
+    dd r2 = two_prod(r, r);
+    dd r3 = dd_mul_d(r2, r);
+    dd t3 = dd_mul(r3, dd{SOFA_THIRD_HI, SOFA_THIRD_LO});
+    // tail = r^4 * (-1/4 + r/5 - r^2/6 + ... + r^9/13)
+    double t = 1.0 / 13.0;
+    t = d_fma(t, r, -1.0 / 12.0);
+    t = d_fma(t, r, 1.0 / 11.0);
+    t = d_fma(t, r, -1.0 / 10.0);
+    t = d_fma(t, r, 1.0 / 9.0);
+    t = d_fma(t, r, -1.0 / 8.0);
+    t = d_fma(t, r, 1.0 / 7.0);
+    t = d_fma(t, r, -1.0 / 6.0);
+    t = d_fma(t, r, 1.0 / 5.0);
+    t = d_fma(t, r, -1.0 / 4.0);
+    double tail = d_mul(d_mul(r2.hi, r2.hi), t);
+    dd q = dd_add(dd{r, 0.0}, dd{-0.5 * r2.hi, -0.5 * r2.lo});
+    q = dd_add(q, t3);
+    return dd_add_d(q, tail);
+}
+
+// x = m * 2^E, m in [1,2); idx = top 7 fraction bits; r = m*inv[idx] - 1 exactly.
+SOFA_HD void log_reduce(double x, int* E, int* idx, double* r) {
+    uint64_t b = d_bits(x);
+    int be = (int)((b >> 52) & 0x7ff);
+    *E = be - 1023;
+    *idx = (int)((b >> 45) & 127);
+    double m = bits_d((b & 0xfffffffffffffull) | (1023ull << 52));
+    *r = d_fma(m, SOFA_TAB(LOG_INV)[*idx], -1.0);
+}
+
+// log10(x) for normal positive x, rounded from a ~2^-80-accurate double-double.
+SOFA_HD double log10_cr(double x) {
+    int E, idx; double r;
+    log_reduce(x, &E, &idx, &r);
+    dd l = dd_mul(log1p_dd(r), dd{SOFA_INV_LN10_HI, SOFA_INV_LN10_LO});
+    double fe = (double)E;
+    dd acc = two_sum(d_mul(fe, SOFA_LOG10_2_HI), SOFA_TAB(L10_HI)[idx]);      // E*HI is exact
+    dd e2 = two_prod(fe, SOFA_LOG10_2_MID);
+    e2.lo = d_add(e2.lo, d_mul(fe, SOFA_LOG10_2_LO));
+    acc = dd_add(acc, e2);
+    acc = dd_add(acc, dd{SOFA_TAB(L10_LO)[idx], 0.0});
+    acc = dd_add(acc, l);
+    return d_add(acc.hi, acc.lo);
+}
+SOFA_HD double log2_cr(double x) {
+    int E, idx; double r;
+    log_reduce(x, &E, &idx, &r);
+    dd l = dd_mul(log1p_dd(r), dd{SOFA_INV_LN2_HI, SOFA_INV_LN2_LO});
+    dd acc = two_sum((double)E, SOFA_TAB(L2_HI)[idx]);
+    acc = dd_add(acc, dd{SOFA_TAB(L2_LO)[idx], 0.0});
+    acc = dd_add(acc, l);
+    return d_add(acc.hi, acc.lo);
+}
+
+// ----------------------------------------------------------------------------- np.interp (scalar x)
+// numpy/_core/src/multiarray/compiled_base.c arr_interp, scalar-x path (slopes not cached).
+SOFA_HD double interp1(double x, const double* xp, const double* fp, int n) {
+    if (x > xp[n - 1]) return fp[n - 1];
+    if (x < xp[0]) return fp[0];
+    int lo = 0, hi = n;               // largest j with xp[j] <= x
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (xp[mid] <= x) lo = mid; else hi = mid; }
+    int j = lo;
+    if (j == n - 1) return fp[j];
+    if (xp[j] == x) return fp[j];
+    double slope = d_div(d_sub(fp[j + 1], fp[j]), d_sub(xp[j + 1], xp[j]));
+    double res = d_add(d_mul(slope, d_sub(x, xp[j])), fp[j]);
+    if (res != res) {
+        res = d_add(d_mul(slope, d_sub(x, xp[j + 1])), fp[j + 1]);
+        if (res != res && fp[j] == fp[j + 1]) res = fp[j];
+    }
+    return res;
+}
+
+// event_raw = 1.0 * int("0x01" + hex, 16): (16^h + ip) rounded to double (sofa_preprocess.py:118).
+SOFA_HD double ip_event_raw(uint64_t ip, int hexdigits) {
+    u128 v = (((u128)1) << (4 * hexdigits)) | (u128)ip;
+    return round_u128(v, 0, false);
+}
+}  // namespace sofa

@@ -1,0 +1,665 @@
+// Per-record logic of the SOFA preprocess hot path as __host__ __device__ functions:
+// the kernels in kernels.cu are thin tiling/scan wrappers around these, and
+// tests/hostsim.cpp compiles the same code for the CPU unit tests.
+//
+//   parse_perf  == cpu_trace_read   sofa_preprocess.py:110-154
+//   parse_gpu   == gpu_trace_read   sofa_preprocess.py:249-341
+//   parse_net   == net_trace_read   sofa_preprocess.py:156-201
+//   csv_row*    == DataFrame.to_csv(index=False, float_format='%.6f') rows  (:1206,1439,1802)
+//   json_row*   == to_json(orient='records') -> json.loads -> json.dump records (:343-374)
+#pragma once
+#include "num.cuh"
+
+namespace sofa {
+
+enum { SRC_PERF = 0, SRC_GPU = 1, SRC_NET = 2 };
+
+// row-level error codes (the reference raises for all of these; we fail loudly with the row)
+enum {
+    E_OK = 0,
+    E_FEW_TOKENS = 1,       // IndexError in the reference
+    E_BAD_FLOAT = 2,        // float() ValueError
+    E_BAD_INT = 3,          // int() ValueError
+    E_UNSUPPORTED_NUM = 4,  // Python accepts the spelling, this codec does not
+    E_BAD_HEX = 5,          // int("0x01"+ip, 16) ValueError
+    E_LINE_TOO_LONG = 6,
+    E_RANGE = 7,            // integer outside the column's storage range
+    E_CR = 8,               // '\r' in the text (universal-newline handling not supported)
+    E_TOO_MANY_LINES = 9,   // > capacity short lines in one tile (all would be E_FEW_TOKENS)
+    E_FORMAT = 10,          // value outside the supported range of a text codec
+    E_UTF8 = 11             // invalid UTF-8 in a name
+};
+
+struct IngestCfg {
+    double time_base;        // cfg.time_base (sofa_preprocess.py:418-422)
+    double t_offset;         // perf: unix-uptime (:1796); gpu: t_glb_gpu_base - t_base (:1430); net: 0
+    int absolute_timestamp;
+    // perf
+    int perf_has_cycles;     // cfg.perf_events.find('cycles') != -1 (:138)
+    int n_mhz;               // len(cpu_mhz_xp) (:131)
+    const double* mhz_xp;
+    const double* mhz_fp;
+    // nvprof gpu trace
+    double ts_rescale, dt_rescale, payload_unit;    // (:1392-1415)
+    int n_cudaproc;                                   // pid column (:288)
+    int idx_start, idx_dur, idx_size, idx_thr, idx_ctx, idx_stream, idx_name, idx_srcctx, idx_dstctx;
+};
+
+struct Tok { int a, b; };
+
+// str.split() with no argument (ASCII whitespace); returns number of tokens, capped at maxt.
+template <typename S>
+SOFA_HD int tokenize(S s, int n, Tok* t, int maxt) {
+    int k = 0, i = 0;
+    while (i < n && k < maxt) {
+        while (i < n && is_space((unsigned char)s[i])) i++;
+        if (i >= n) break;
+        int a = i;
+        while (i < n && !is_space((unsigned char)s[i])) i++;
+        t[k].a = a; t[k].b = i; k++;
+    }
+    return k;
+}
+
+SOFA_HD int num_status_to_err(int st, bool is_float) {
+    if (st == P_OK) return E_OK;
+    if (st == P_UNSUPPORTED) return E_UNSUPPORTED_NUM;
+    return is_float ? E_BAD_FLOAT : E_BAD_INT;
+}
+
+// ============================================================================ perf
+struct PerfRow {
+    double ts, event, dur;
+    int32_t pid, tid;
+    uint16_t evt_off, evt_len, sym_off, sym_len, dso_off, dso_len;   // relative to the line start
+};
+
+template <typename S>
+SOFA_HD int parse_perf(S s, int n, const IngestCfg& c, PerfRow* r) {
+    if (n > 65535) return E_LINE_TOO_LONG;
+    Tok t[8];
+    int nt = tokenize(s, n, t, 8);
+    if (nt < 2) return E_FEW_TOKENS;
+    int sh = 0;
+    {   // re.match('\[\d+\]', fields[1])  (:114)
+        int a = t[1].a, b = t[1].b;
+        if (b - a >= 3 && s[a] == '[') {
+            int i = a + 1;
+            while (i < b && (unsigned)((unsigned char)s[i] - '0') <= 9) i++;
+            if (i > a + 1 && i < b && s[i] == ']') sh = 1;
+        }
+    }
+    if (nt < 7 + sh) return E_FEW_TOKENS;
+    double time, counts;
+    {
+        int a = t[1 + sh].a, b = t[1 + sh].b, e = a;
+        while (e < b && s[e] != ':') e++;                    // .split(':')[0]
+        int st = parse_double(s + a, e - a, &time);
+        if (st) return num_status_to_err(st, true);
+        st = parse_double(s + t[2 + sh].a, t[2 + sh].b - t[2 + sh].a, &counts);
+        if (st) return num_status_to_err(st, true);
+    }
+    uint64_t ip = 0;
+    int hd = t[4 + sh].b - t[4 + sh].a;
+    {
+        int a = t[4 + sh].a;
+        if (hd > 16) return E_UNSUPPORTED_NUM;
+        for (int i = 0; i < hd; i++) {
+            unsigned char ch = (unsigned char)s[a + i];
+            unsigned v;
+            if (ch >= '0' && ch <= '9') v = ch - '0';
+            else if (ch >= 'a' && ch <= 'f') v = ch - 'a' + 10;
+            else if (ch >= 'A' && ch <= 'F') v = ch - 'A' + 10;
+            else return ch == '_' ? E_UNSUPPORTED_NUM : E_BAD_HEX;
+            ip = (ip << 4) | v;
+        }
+    }
+    double event_raw = ip_event_raw(ip, hd);
+    if (!c.absolute_timestamp) time = d_sub(time, c.time_base);
+    double t_begin = d_add(time, c.t_offset);
+    double dur;
+    if (c.n_mhz > 1) dur = d_div(counts, d_mul(interp1(t_begin, c.mhz_xp, c.mhz_fp, c.n_mhz), 1e6));
+    else dur = d_div(counts, 3000.0 * 1e6);
+    if (!c.perf_has_cycles) dur = log2_cr(d_div(event_raw, 1e14));
+    r->ts = t_begin;
+    r->event = log10_cr(event_raw);
+    r->dur = dur;
+    {   // int(fields[0].split('/')[0]), int(fields[0].split('/')[1])
+        int a = t[0].a, b = t[0].b, s1 = a;
+        while (s1 < b && s[s1] != '/') s1++;
+        if (s1 >= b) return E_FEW_TOKENS;
+        int s2 = s1 + 1;
+        while (s2 < b && s[s2] != '/') s2++;
+        int64_t p, q;
+        int st = parse_i64(s + a, s1 - a, &p);
+        if (st) return num_status_to_err(st, false);
+        st = parse_i64(s + s1 + 1, s2 - s1 - 1, &q);
+        if (st) return num_status_to_err(st, false);
+        if (p < -2147483647 || p > 2147483647 || q < -2147483647 || q > 2147483647) return E_RANGE;
+        r->pid = (int32_t)p; r->tid = (int32_t)q;
+    }
+    r->evt_off = (uint16_t)t[3 + sh].a; r->evt_len = (uint16_t)(t[3 + sh].b - t[3 + sh].a);
+    r->sym_off = (uint16_t)t[5 + sh].a; r->sym_len = (uint16_t)(t[5 + sh].b - t[5 + sh].a);
+    r->dso_off = (uint16_t)t[6 + sh].a; r->dso_len = (uint16_t)(t[6 + sh].b - t[6 + sh].a);
+    return E_OK;
+}
+
+// name = '[%s]' % evt.replace('-','_') + sym + dso   (:116,121)
+template <typename S>
+struct PerfName {
+    S line; PerfRow r;
+    template <class K> SOFA_HD void gen(K& k) const {
+        k.put('[');
+        for (int i = 0; i < r.evt_len; i++) { char ch = line[r.evt_off + i]; k.put(ch == '-' ? '_' : ch); }
+        k.put(']');
+        for (int i = 0; i < r.sym_len; i++) k.put(line[r.sym_off + i]);
+        for (int i = 0; i < r.dso_len; i++) k.put(line[r.dso_off + i]);
+    }
+};
+
+// viz name = name[name.find(']')+1 : name.find('+')].split('@')[0]  (:1811-1816), before demangling
+struct FindSink {
+    int pos, first_rb, first_plus;
+    SOFA_HD FindSink() : pos(0), first_rb(-1), first_plus(-1) {}
+    SOFA_HD void put(char ch) {
+        if (ch == ']' && first_rb < 0) first_rb = pos;
+        if (ch == '+' && first_plus < 0) first_plus = pos;
+        pos++;
+    }
+};
+template <class K>
+struct SliceSink {          // forwards characters [a, b) until the first '@'
+    K* k; int pos, a, b; bool stop;
+    SOFA_HD void put(char ch) {
+        if (pos >= a && pos < b && !stop) { if (ch == '@') stop = true; else k->put(ch); }
+        pos++;
+    }
+};
+template <typename S>
+struct PerfVizName {
+    PerfName<S> full;
+    template <class K> SOFA_HD void gen(K& k) const {
+        FindSink f; full.gen(f);
+        int len = f.pos;
+        int a = f.first_rb + 1;                         // find()==-1 -> 0
+        int b = f.first_plus >= 0 ? f.first_plus : len - 1;   // [a:-1]
+        if (b < 0) b = 0;
+        SliceSink<K> sl{&k, 0, a, b, false};
+        full.gen(sl);
+    }
+};
+
+// ============================================================================ nvprof gpu trace
+struct GpuRow {
+    double ts, dur, bw;
+    int64_t payload;
+    int32_t dev, tid, src, dst;
+    uint8_t kind, bw_is_float;
+    uint16_t name_off, name_len;      // raw span of the Name field (quotes still inside)
+};
+
+// parse a numeric field whose '"' characters have been removed (record.replace('"',''))
+template <typename S>
+SOFA_HD int parse_double_q(S s, int a, int b, double* out) {
+    char buf[48];
+    int m = 0;
+    for (int i = a; i < b; i++) { char ch = s[i]; if (ch != '"') { if (m >= 47) return P_UNSUPPORTED; buf[m++] = ch; } }
+    return parse_double((const char*)buf, m, out);
+}
+template <typename S>
+SOFA_HD int parse_i64_q(S s, int a, int b, int64_t* out) {
+    char buf[32];
+    int m = 0;
+    for (int i = a; i < b; i++) { char ch = s[i]; if (ch != '"') { if (m >= 31) return P_UNSUPPORTED; buf[m++] = ch; } }
+    return parse_i64((const char*)buf, m, out);
+}
+// int(float(x)) inside try/except -> (ok, value)
+SOFA_HD bool float_to_int_trunc(double v, int64_t* out, int* err) {
+    uint64_t b = d_bits(v);
+    if (((b >> 52) & 0x7ff) == 0x7ff) return false;            // inf/nan -> exception -> default
+    if (v >= 9223372036854775808.0 || v <= -9223372036854775808.0) { *err = E_RANGE; return false; }
+    *out = (int64_t)v;
+    return true;
+}
+
+// `n` includes the trailing '\n' when the line has one (the Name field keeps it, :258).
+template <typename S>
+SOFA_HD int parse_gpu(S s, int n, const IngestCfg& c, GpuRow* r) {
+    if (n > 65535) return E_LINE_TOO_LONG;
+    // field spans for the wanted columns (split(',') after the quotes are dropped)
+    int fa[9], fb[9];
+    int want[9] = {c.idx_start, c.idx_dur, c.idx_size, c.idx_thr, c.idx_ctx, c.idx_stream,
+                   c.idx_name, c.idx_srcctx, c.idx_dstctx};
+    for (int k = 0; k < 9; k++) { fa[k] = -1; fb[k] = -1; }
+    int f = 0, a = 0;
+    for (int i = 0; i <= n; i++) {
+        if (i == n || s[i] == ',') {
+            for (int k = 0; k < 9; k++) if (want[k] == f) { fa[k] = a; fb[k] = i; }
+            f++; a = i + 1;
+        }
+    }
+    if (fa[6] < 0 || fa[0] < 0 || fa[1] < 0) return E_FEW_TOKENS;
+    double start, dur;
+    int st = parse_double_q(s, fa[0], fb[0], &start);
+    if (st) return num_status_to_err(st, true);
+    double time = d_add(d_div(start, c.ts_rescale), c.t_offset);
+    if (!c.absolute_timestamp) time = d_sub(time, c.time_base);
+    st = parse_double_q(s, fa[1], fb[1], &dur);
+    if (st) return num_status_to_err(st, true);
+    r->ts = time;
+    r->dur = d_div(dur, c.dt_rescale);
+    int err = E_OK;
+    double v; int64_t iv;
+    r->payload = 0;
+    if (fa[2] >= 0) {
+        st = parse_double_q(s, fa[2], fb[2], &v);
+        if (st == P_UNSUPPORTED) return E_UNSUPPORTED_NUM;
+        if (st == P_OK && float_to_int_trunc(d_mul(v, c.payload_unit), &iv, &err)) r->payload = iv;
+    }
+    r->bw = 0.0; r->bw_is_float = 0;
+    if (fa[3] >= 0) {
+        st = parse_double_q(s, fa[3], fb[3], &v);
+        if (st == P_UNSUPPORTED) return E_UNSUPPORTED_NUM;
+        if (st == P_OK) { r->bw = v; r->bw_is_float = 1; }
+    }
+    int64_t dev = -1, tid = -1;
+    if (fa[4] >= 0) {
+        st = parse_double_q(s, fa[4], fb[4], &v);
+        if (st == P_UNSUPPORTED) return E_UNSUPPORTED_NUM;
+        if (st == P_OK && float_to_int_trunc(v, &iv, &err)) dev = iv;
+    }
+    if (fa[5] >= 0) {
+        st = parse_double_q(s, fa[5], fb[5], &v);
+        if (st == P_UNSUPPORTED) return E_UNSUPPORTED_NUM;
+        if (st == P_OK && float_to_int_trunc(v, &iv, &err)) tid = iv;
+    }
+    if (err) return err;
+    if (dev < -2147483647 || dev > 2147483647 || tid < -2147483647 || tid > 2147483647) return E_RANGE;
+    // substring tags on the quote-free name (:293-323)
+    bool h2d = false, d2h = false, d2d = false, p2p = false;
+    {
+        uint32_t w = 0;
+        for (int i = fa[6]; i < fb[6]; i++) {
+            char ch = s[i];
+            if (ch == '"') continue;
+            w = (w << 8) | (unsigned char)ch;
+            h2d |= (w == 0x48746f44u);   // "HtoD"
+            d2h |= (w == 0x44746f48u);   // "DtoH"
+            d2d |= (w == 0x44746f44u);   // "DtoD"
+            p2p |= (w == 0x50746f50u);   // "PtoP"
+        }
+    }
+    int64_t src = 0, dst = 0;
+    int kind = 0;
+    if (h2d) { kind = 1; src = 0; dst = dev; }
+    else if (d2h) { kind = 2; src = dev; dst = 0; }
+    else if (d2d) { kind = 8; src = dev; dst = dev; }
+    else if (p2p) {
+        kind = 10;
+        if (fa[7] >= 0) { st = parse_i64_q(s, fa[7], fb[7], &iv); if (st == P_UNSUPPORTED) return E_UNSUPPORTED_NUM; if (st == P_OK) src = iv; }
+        if (fa[8] >= 0) { st = parse_i64_q(s, fa[8], fb[8], &iv); if (st == P_UNSUPPORTED) return E_UNSUPPORTED_NUM; if (st == P_OK) dst = iv; }
+        if (src < -2147483647 || src > 2147483647 || dst < -2147483647 || dst > 2147483647) return E_RANGE;
+    }
+    r->dev = (int32_t)dev; r->tid = (int32_t)tid; r->src = (int32_t)src; r->dst = (int32_t)dst;
+    r->kind = (uint8_t)kind;
+    r->name_off = (uint16_t)fa[6]; r->name_len = (uint16_t)(fb[6] - fa[6]);
+    return E_OK;
+}
+
+template <class K> SOFA_HD void put_lit(K& k, const char* lit) { for (int i = 0; lit[i]; i++) k.put(lit[i]); }
+template <class K> SOFA_HD void put_i64(K& k, int64_t v) {
+    char b[24]; int n = fmt_i64(v, (char*)b);
+    for (int i = 0; i < n; i++) k.put(b[i]);
+}
+
+template <typename S>
+struct GpuName {
+    S line; GpuRow r;
+    template <class K> SOFA_HD void gen(K& k) const {
+        if (r.dev != -1) { put_lit(k, "[gpu"); put_i64(k, r.dev); k.put(']'); }        // :325-326
+        if (r.kind == 0) {
+            for (int i = 0; i < r.name_len; i++) { char ch = line[r.name_off + i]; if (ch != '"') k.put(ch); }
+        } else if (r.kind == 10) {
+            put_lit(k, "[CUDA_COPY_P2P]from_gpu"); put_i64(k, r.src); put_lit(k, "_to_gpu"); put_i64(k, r.dst);
+            k.put('_'); put_i64(k, r.payload); k.put('B');
+        } else {
+            put_lit(k, r.kind == 1 ? "CUDA_COPY_H2D_" : (r.kind == 2 ? "CUDA_COPY_D2H_" : "CUDA_COPY_D2D_"));
+            put_i64(k, r.payload); k.put('B');
+        }
+    }
+};
+
+// ============================================================================ tcpdump
+struct NetRow { double ts; int64_t payload, src, dst; uint8_t proto; };   // proto 0 = [] row, 1 = UDP, 2 = tcp
+
+template <typename S>
+SOFA_HD int dotted4(S s, int a, int b, int64_t* out) {           // sum int(part_i) * 1000^(3-i)
+    int64_t acc = 0;
+    int p = a;
+    for (int i = 0; i < 4; i++) {
+        if (p > b) return E_FEW_TOKENS;
+        int e = p;
+        while (e < b && s[e] != '.') e++;
+        int64_t v;
+        int st = parse_i64(s + p, e - p, &v);
+        if (st) return num_status_to_err(st, false);
+        if (v < -1000000 || v > 1000000) return E_RANGE;
+        acc = acc * 1000 + v;
+        p = e + 1;           // next part starts after the dot; p > b means "no more parts"
+        if (e >= b) p = b + 1;
+    }
+    *out = acc;
+    return E_OK;
+}
+
+template <typename S>
+SOFA_HD int parse_net(S s, int n, const IngestCfg& c, NetRow* r) {
+    Tok t[8];
+    int nt = tokenize(s, n, t, 8);
+    if (nt < 1) return E_FEW_TOKENS;
+    double time;
+    int st = parse_double(s + t[0].a, t[0].b - t[0].a, &time);
+    if (st) return num_status_to_err(st, true);
+    if (!c.absolute_timestamp) time = d_sub(time, c.time_base);
+    r->ts = d_add(time, c.t_offset);
+    r->proto = 0; r->payload = 0; r->src = 0; r->dst = 0;
+    if (nt < 2) return E_FEW_TOKENS;
+    if (!(t[1].b - t[1].a == 2 && s[t[1].a] == 'I' && s[t[1].a + 1] == 'P')) return E_OK;     // [] row
+    if (nt < 6) return E_FEW_TOKENS;
+    int a = t[5].a, l = t[5].b - t[5].a;
+    int ptok;
+    if (l == 4 && s[a] == 'U' && s[a + 1] == 'D' && s[a + 2] == 'P' && s[a + 3] == ',') { r->proto = 1; ptok = 7; }
+    else if (l == 3 && s[a] == 't' && s[a + 1] == 'c' && s[a + 2] == 'p') { r->proto = 2; ptok = 6; }
+    else return E_OK;                                                                            // [] row
+    if (nt <= ptok) return E_FEW_TOKENS;
+    int64_t pl;
+    st = parse_i64(s + t[ptok].a, t[ptok].b - t[ptok].a, &pl);
+    if (st) return num_status_to_err(st, false);
+    if (pl > 90000000000000000ll || pl < -90000000000000000ll) return E_RANGE;
+    r->payload = pl;
+    int e = dotted4(s, t[2].a, t[2].b, &r->src);
+    if (e) return e;
+    e = dotted4(s, t[4].a, t[4].b, &r->dst);
+    if (e) return e;
+    return E_OK;
+}
+
+struct NetName {
+    NetRow r;
+    template <class K> SOFA_HD void gen(K& k) const {     // "network:%s:%d_to_%d_with_%d" (:198)
+        put_lit(k, r.proto == 1 ? "network:UDP,:" : "network:tcp:");
+        put_i64(k, r.src); put_lit(k, "_to_"); put_i64(k, r.dst); put_lit(k, "_with_"); put_i64(k, r.payload);
+    }
+};
+
+// ============================================================================ 13-column row values
+struct RowVals {
+    bool valid;              // false: the all-NaN row a `[]` record becomes
+    double ts, dur;          // columns 0, 2 (always float)
+    bool ev_is_f; double ev_f; int64_t ev_i;       // column 1
+    int64_t dev, kind, payload;                     // 3, 4, 5
+    bool bw_is_f; double bw_f; int64_t bw_i;        // 6
+    int64_t src, dst, pid, tid;                     // 7..10
+    // 11 = name (generator), 12 = category (always 0)
+};
+SOFA_HD RowVals vals_perf(const PerfRow& r) {
+    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.ev_is_f = true; v.ev_f = r.event; v.ev_i = 0;
+    v.dev = -1; v.kind = -1; v.payload = 0; v.bw_is_f = false; v.bw_f = 0; v.bw_i = 0;
+    v.src = -1; v.dst = -1; v.pid = r.pid; v.tid = r.tid; return v;
+}
+SOFA_HD RowVals vals_gpu(const GpuRow& r, int n_cudaproc) {
+    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.ev_is_f = false; v.ev_f = 0;
+    v.ev_i = r.payload * 100 + 17;                                   // :329
+    v.dev = r.dev; v.kind = r.kind; v.payload = r.payload; v.bw_is_f = r.bw_is_float != 0; v.bw_f = r.bw; v.bw_i = 0;
+    v.src = r.src; v.dst = r.dst; v.pid = n_cudaproc; v.tid = r.tid; return v;
+}
+SOFA_HD RowVals vals_net(const NetRow& r) {
+    RowVals v; v.valid = r.proto != 0; v.ts = r.ts;
+    v.dur = d_div((double)r.payload, 128.0e6);                       // :178
+    v.ev_is_f = false; v.ev_f = 0; v.ev_i = r.payload * 100 + 17;
+    v.dev = -1; v.kind = -1; v.payload = r.payload; v.bw_is_f = true; v.bw_f = 128.0e6; v.bw_i = 0;
+    v.src = r.src; v.dst = r.dst; v.pid = -1; v.tid = -1; return v;
+}
+
+// column c of the row as (is_float, f, i) under the file's float-column mask
+SOFA_HD void col_value(const RowVals& v, int c, uint32_t fmask, bool* isf, double* f, int64_t* i) {
+    bool nat_f = false; double nf = 0; int64_t ni = 0;
+    switch (c) {
+        case 0: nat_f = true; nf = v.ts; break;
+        case 1: nat_f = v.ev_is_f; nf = v.ev_f; ni = v.ev_i; break;
+        case 2: nat_f = true; nf = v.dur; break;
+        case 3: ni = v.dev; break;
+        case 4: ni = v.kind; break;
+        case 5: ni = v.payload; break;
+        case 6: nat_f = v.bw_is_f; nf = v.bw_f; ni = v.bw_i; break;
+        case 7: ni = v.src; break;
+        case 8: ni = v.dst; break;
+        case 9: ni = v.pid; break;
+        case 10: ni = v.tid; break;
+        default: ni = 0; break;        // 12: category
+    }
+    bool colf = ((fmask >> c) & 1) != 0 || nat_f;
+    *isf = colf;
+    *f = nat_f ? nf : (double)ni;
+    *i = ni;
+}
+
+// ============================================================================ CSV (QUOTE_MINIMAL)
+struct CsvCount {
+    int len; bool special;
+    SOFA_HD CsvCount() : len(0), special(false) {}
+    SOFA_HD void put(char ch) {
+        len++;
+        if (ch == '"') { len++; special = true; }
+        else if (ch == ',' || ch == '\n' || ch == '\r') special = true;
+    }
+};
+template <typename O>
+struct CsvWrite {
+    O out; int n;
+    SOFA_HD void put(char ch) { if (ch == '"') out[n++] = '"'; out[n++] = ch; }
+};
+
+// returns total row length (incl. '\n'), or -1 on an unformattable value; *name_special out
+template <class NG>
+SOFA_HD int csv_row_len(const RowVals& v, uint32_t fmask, const NG& ng, bool* name_special) {
+    *name_special = false;
+    if (!v.valid) return 13;                       // twelve commas + '\n'
+    int n = 0;
+    for (int c = 0; c < 13; c++) {
+        if (c == 11) {
+            CsvCount k; ng.gen(k);
+            n += k.len + (k.special ? 2 : 0);
+            *name_special = k.special;
+        } else {
+            bool isf; double f; int64_t i;
+            col_value(v, c, fmask, &isf, &f, &i);
+            if (isf) { int l = len_fixed6(f); if (l < 0) return -1; n += l; }
+            else n += len_i64(i);
+        }
+        n += 1;                                    // ',' or '\n'
+    }
+    return n;
+}
+template <class NG, typename O>
+SOFA_HD int csv_row_write(const RowVals& v, uint32_t fmask, const NG& ng, bool name_special, O out) {
+    if (!v.valid) { for (int i = 0; i < 12; i++) out[i] = ','; out[12] = '\n'; return 13; }
+    int n = 0;
+    for (int c = 0; c < 13; c++) {
+        if (c == 11) {
+            if (name_special) out[n++] = '"';
+            CsvWrite<O> k{out + n, 0}; ng.gen(k); n += k.n;
+            if (name_special) out[n++] = '"';
+        } else {
+            bool isf; double f; int64_t i;
+            col_value(v, c, fmask, &isf, &f, &i);
+            if (isf) n += fmt_fixed6(f, out + n); else n += fmt_i64(i, out + n);
+        }
+        out[n++] = (c == 12) ? '\n' : ',';
+    }
+    return n;
+}
+
+// ============================================================================ JSON records
+// Final escaping is json.dump's (ensure_ascii=True): \" \\ \n \r \t \b \f, other chars
+// outside ' '..'~' as \uXXXX (UTF-8 decoded, surrogate pairs above U+FFFF).
+struct JsonEsc {
+    uint32_t cp; int need; bool bad;
+    SOFA_HD JsonEsc() : cp(0), need(0), bad(false) {}
+    // feeds one byte; returns number of output chars into buf (<= 12)
+    SOFA_HD int feed(unsigned char b, char* buf) {
+        const char* hexd = "0123456789abcdef";
+        if (need > 0) {
+            if ((b & 0xC0) != 0x80) { bad = true; need = 0; return 0; }
+            cp = (cp << 6) | (b & 0x3F);
+            if (--need > 0) return 0;
+            int n = 0;
+            uint32_t u = cp;
+            if (u >= 0x10000) {
+                u -= 0x10000;
+                uint32_t hi = 0xD800 + (u >> 10), lo = 0xDC00 + (u & 0x3FF);
+                buf[n++] = '\\'; buf[n++] = 'u';
+                buf[n++] = hexd[(hi >> 12) & 15]; buf[n++] = hexd[(hi >> 8) & 15]; buf[n++] = hexd[(hi >> 4) & 15]; buf[n++] = hexd[hi & 15];
+                u = lo;
+            }
+            buf[n++] = '\\'; buf[n++] = 'u';
+            buf[n++] = hexd[(u >> 12) & 15]; buf[n++] = hexd[(u >> 8) & 15]; buf[n++] = hexd[(u >> 4) & 15]; buf[n++] = hexd[u & 15];
+            return n;
+        }
+        if (b < 0x80) {
+            if (b == '"') { buf[0] = '\\'; buf[1] = '"'; return 2; }
+            if (b == '\\') { buf[0] = '\\'; buf[1] = '\\'; return 2; }
+            if (b >= 0x20 && b <= 0x7e) { buf[0] = (char)b; return 1; }
+            buf[0] = '\\';
+            switch (b) {
+                case '\n': buf[1] = 'n'; return 2;
+                case '\r': buf[1] = 'r'; return 2;
+                case '\t': buf[1] = 't'; return 2;
+                case '\b': buf[1] = 'b'; return 2;
+                case '\f': buf[1] = 'f'; return 2;
+                default: break;
+            }
+            buf[1] = 'u'; buf[2] = '0'; buf[3] = '0'; buf[4] = hexd[b >> 4]; buf[5] = hexd[b & 15];
+            return 6;
+        }
+        if ((b & 0xE0) == 0xC0) { cp = b & 0x1F; need = 1; return 0; }
+        if ((b & 0xF0) == 0xE0) { cp = b & 0x0F; need = 2; return 0; }
+        if ((b & 0xF8) == 0xF0) { cp = b & 0x07; need = 3; return 0; }
+        bad = true;
+        return 0;
+    }
+};
+struct JsonCount {
+    JsonEsc e; int len;
+    SOFA_HD JsonCount() : len(0) {}
+    SOFA_HD void put(char ch) { char b[12]; len += e.feed((unsigned char)ch, b); }
+};
+template <typename O>
+struct JsonWrite {
+    O out; int n; JsonEsc e;
+    SOFA_HD void put(char ch) { char b[12]; int l = e.feed((unsigned char)ch, b); for (int i = 0; i < l; i++) out[n++] = b[i]; }
+};
+
+// key text that precedes column c in a record (x=timestamp, y=duration renamed, :351-355)
+SOFA_HD const char* json_key(int c) {
+    switch (c) {
+        case 0: return "{\"x\": ";
+        case 1: return ", \"event\": ";
+        case 2: return ", \"y\": ";
+        case 3: return ", \"deviceId\": ";
+        case 4: return ", \"copyKind\": ";
+        case 5: return ", \"payload\": ";
+        case 6: return ", \"bandwidth\": ";
+        case 7: return ", \"pkt_src\": ";
+        case 8: return ", \"pkt_dst\": ";
+        case 9: return ", \"pid\": ";
+        case 10: return ", \"tid\": ";
+        case 11: return ", \"name\": ";
+        default: return ", \"category\": ";
+    }
+}
+SOFA_HD int json_key_len(int c) {
+    const int L[13] = {6, 11, 7, 14, 14, 13, 15, 13, 13, 9, 9, 10, 14};
+    return L[c];
+}
+
+// A record is emitted as ", " + {...}; the series writer drops the first two bytes.
+// returns length, or -1 (unformattable number) / -2 (invalid UTF-8)
+template <class NG, typename O>
+SOFA_HD int json_row_write(const RowVals& v, uint32_t fmask, const NG& ng, O out) {
+    int n = 0;
+    out[n++] = ','; out[n++] = ' ';
+    for (int c = 0; c < 13; c++) {
+        const char* k = json_key(c);
+        for (int i = 0; k[i]; i++) out[n++] = k[i];
+        if (!v.valid) { out[n++] = 'n'; out[n++] = 'u'; out[n++] = 'l'; out[n++] = 'l'; continue; }
+        if (c == 11) {
+            out[n++] = '"';
+            JsonWrite<O> w{out + n, 0, JsonEsc()}; ng.gen(w);
+            if (w.e.bad || w.e.need) return -2;
+            n += w.n;
+            out[n++] = '"';
+        } else {
+            bool isf; double f; int64_t i;
+            col_value(v, c, fmask, &isf, &f, &i);
+            if (isf) { int l = json_double(f, out + n); if (l < 0) return -1; n += l; }
+            else n += fmt_i64(i, out + n);
+        }
+    }
+    out[n++] = '}';
+    return n;
+}
+template <class NG>
+SOFA_HD int json_row_len(const RowVals& v, uint32_t fmask, const NG& ng) {
+    int n = 2 + 1;                                   // ", " and '}'
+    for (int c = 0; c < 13; c++) {
+        n += json_key_len(c);
+        if (!v.valid) { n += 4; continue; }
+        if (c == 11) {
+            JsonCount k; ng.gen(k);
+            if (k.e.bad || k.e.need) return -2;
+            n += k.len + 2;
+        } else {
+            bool isf; double f; int64_t i;
+            col_value(v, c, fmask, &isf, &f, &i);
+            if (isf) { char b[40]; int l = json_double(f, (char*)b); if (l < 0) return -1; n += l; }
+            else n += len_i64(i);
+        }
+    }
+    return n;
+}
+
+// ============================================================================ keyword filters
+// Series.str.contains(keyword) for metacharacter-free keywords == byte-substring search
+// (SURVEY.md A.4).  Shift-and matcher over up to 8 keywords of <= 32 bytes.
+struct FilterTable {
+    uint32_t mask[8][256];
+    uint32_t final_bit[8];
+    int nk;
+};
+struct MatchSink {
+    const FilterTable* t; uint32_t st[8]; uint32_t hit;
+    SOFA_HD MatchSink(const FilterTable* tt) : t(tt), hit(0) { for (int k = 0; k < 8; k++) st[k] = 0; }
+    SOFA_HD void put(char ch) {
+        unsigned char b = (unsigned char)ch;
+        for (int k = 0; k < t->nk; k++) {
+            st[k] = ((st[k] << 1) | 1u) & t->mask[k][b];
+            if (st[k] & t->final_bit[k]) hit |= 1u << k;
+        }
+    }
+};
+
+// FNV-1a 64 over generated characters (name dictionary keys)
+struct HashSink {
+    uint64_t h; int len; char c0, c1;
+    SOFA_HD HashSink() : h(1469598103934665603ull), len(0), c0(0), c1(0) {}
+    SOFA_HD void put(char ch) {
+        if (len == 0) c0 = ch; else if (len == 1) c1 = ch;
+        h = (h ^ (unsigned char)ch) * 1099511628211ull; len++;
+    }
+};
+template <typename O>
+struct RawWrite { O out; int n; SOFA_HD void put(char ch) { out[n++] = ch; } };
+struct LenSink { int len; SOFA_HD LenSink() : len(0) {} SOFA_HD void put(char) { len++; } };
+
+}  // namespace sofa

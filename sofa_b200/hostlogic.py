@@ -1,0 +1,100 @@
+"""Host-side scalars that parameterise the device ingest (no per-record work here).
+
+Follows sofa_preprocess.py: time_base :418-422, cpuinfo table :424-436,
+perf_events :1545-1551, perf_timebase.txt :1766-1784, nvprof header/unit rows
+:1385-1417, t_base :1419 (reference paths relative to /root/reference/bin).
+"""
+import os
+
+SRC_PERF, SRC_GPU, SRC_NET = 0, 1, 2
+
+GPU_COLS = ('Start', 'Duration', 'Size', 'Throughput', 'Context', 'Stream', 'Name', 'Src Ctx', 'Dst Ctx')
+
+
+class PreprocessError(RuntimeError):
+    pass
+
+
+def read_time_base(logdir, cpu_time_offset):
+    with open(logdir + 'sofa_time.txt') as f:
+        return float(f.readlines()[0]) + cpu_time_offset
+
+
+def read_cpuinfo(logdir):
+    xp, fp = [0.0], [3000.0]
+    try:
+        with open(logdir + 'cpuinfo.txt') as f:
+            for line in f.readlines():
+                fields = line.split()
+                xp.append(float(fields[0]))
+                fp.append(float(fields[1]))
+    except Exception:
+        pass
+    return xp, fp
+
+
+def read_perf_events(logdir):
+    with open(logdir + 'perf_events_used.txt', 'r') as f:
+        lines = f.readlines()
+    return lines[0] if lines else ''
+
+
+def read_perf_timebase(logdir):
+    """-> perf_timebase_unix - perf_timebase_uptime (the cuhello sync path needs nvprof's
+    sqlite export and is not supported; perf_timebase.txt is the reference's fallback)."""
+    uptime = unix = 0
+    with open(logdir + 'perf_timebase.txt') as f:
+        lines = f.readlines()
+    if len(lines) <= 3 or lines[0].find('WARNING') != -1:
+        return 0
+    try:
+        uptime = float(lines[-2].split()[2].split(':')[0])
+        unix = float(lines[-1].split()[0])
+    except Exception:
+        pass
+    return unix - uptime
+
+
+def base_params(kind, time_base, absolute_timestamp, t_offset=0.0):
+    return dict(kind=kind, time_base=float(time_base), t_offset=float(t_offset),
+                absolute_timestamp=1 if absolute_timestamp else 0, perf_has_cycles=1,
+                mhz_xp=[0.0], mhz_fp=[3000.0], ts_rescale=1.0, dt_rescale=1.0, payload_unit=1.0,
+                n_cudaproc=1, idx=[-1] * 9)
+
+
+def gpu_header(head):
+    """Parse the three header rows from the first bytes of gputrace.tmp.
+
+    Returns (params-update dict, data_offset) or None when the file holds no kernel
+    trace (reference prints a warning and skips, :1453-1456)."""
+    text = head.decode('utf-8', errors='replace')
+    rows = text.split('\n', 3)
+    if len(rows) < 4 and not text.endswith('\n'):
+        if len(rows) < 3:
+            return None
+    if len(rows) < 2 or rows[1].split(',')[0] != '"Start"':
+        return None
+    indices = rows[1].replace('"', '').replace('\n', '').split(',')
+    units = rows[2].split(',')
+    pu = {'GB': 1024.0 ** 3, 'MB': 1024.0 ** 2, 'KB': 1024.0, 'B': 1.0}
+    if len(units) <= 11 or units[11] not in pu:
+        raise PreprocessError("The payload unit in gputrace.tmp was not recognized!")
+    scale = {'ms': 1.0e3, 'us': 1.0e6}
+    idx = [indices.index(c) if c in indices else -1 for c in GPU_COLS]
+    if idx[0] < 0 or idx[1] < 0 or idx[6] < 0:
+        raise PreprocessError("gputrace.tmp header lacks Start/Duration/Name")
+    data_off = len(rows[0].encode()) + len(rows[1].encode()) + len(rows[2].encode()) + 3
+    first = rows[3] if len(rows) > 3 else ''
+    if not first:
+        raise PreprocessError("gputrace.tmp has a header but no records")   # records[0] IndexError
+    t_base = float(first.split(',')[0])                      # :1419, not rescaled
+    return dict(ts_rescale=scale.get(units[0], 1.0), dt_rescale=scale.get(units[1], 1.0),
+                payload_unit=pu[units[11]], idx=idx, t_base=t_base), data_off
+
+
+ROW_ERRORS = {1: "too few fields (IndexError in the reference)", 2: "float() ValueError",
+              3: "int() ValueError", 4: "number spelling not supported by the device codec",
+              5: "int('0x01'+ip, 16) ValueError", 6: "line longer than 65535 bytes / tile overlap",
+              7: "integer out of range", 8: "carriage return in trace text",
+              9: "too many short lines in one tile", 10: "value outside the text codec's range",
+              11: "invalid UTF-8 in a name"}

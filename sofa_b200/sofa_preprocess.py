@@ -1,0 +1,282 @@
+"""Drop-in `sofa_preprocess(cfg)` (reference: bin/sofa_preprocess.py:377-2106).
+
+Same entry point, same `cfg` attributes, same files in `cfg.logdir`; every per-record
+step (line split, tokenise, float/int parse, time-base maths, tagging, name synthesis,
+keyword filters, down-sampling, CSV and report.js text) runs in sm_100a CUDA kernels
+behind libsofa_b200.so.  The host keeps only what the reference does once per file:
+reading side files, the nvprof header rows, demangling the unique mangled symbols, and
+writing the series wrappers of report.js.  There is no CPU fallback: without the CUDA
+library this module raises.
+
+Hot-path sources handled: perf.script (a1), nvprof gpu trace (a2), tcpdump text (a3).
+Sources SURVEY.md §8(f) ranks "next" (mpstat, vmstat, diskstat, nvsmi, netstat, strace,
+blktrace, pystacks) raise NotImplementedError when their input files are present, rather
+than silently producing a report.js that differs from the reference's.
+"""
+import ctypes
+import glob
+import os
+import subprocess
+
+from . import hostlogic as hl
+from .hostlogic import SRC_PERF, SRC_GPU, SRC_NET, PreprocessError
+from .sofa_print import print_main_progress, print_progress, print_info, print_warning
+
+sofa_fieldnames = ["timestamp", "event", "duration", "deviceId", "copyKind", "payload",
+                   "bandwidth", "pkt_src", "pkt_dst", "pid", "tid", "name", "category"]
+CSV_HEADER = (",".join(sofa_fieldnames) + "\n").encode()
+
+NOT_YET = ['mpstat.txt', 'vmstat.txt', 'diskstat.txt', 'nvsmi_query.txt', 'nvsmi.txt',
+           'netstat.txt', 'strace.txt', 'blktrace.txt', 'pystacks.txt']
+
+_libstdcxx = None
+
+
+def demangle(name):
+    """cxxfilt.demangle: libstdc++ __cxa_demangle on names starting with _Z (:1811-1816)."""
+    global _libstdcxx
+    if not name.startswith('_Z'):
+        return name
+    if _libstdcxx is None:
+        _libstdcxx = ctypes.CDLL('libstdc++.so.6')
+        _libstdcxx.__cxa_demangle.restype = ctypes.c_void_p
+    status = ctypes.c_int(0)
+    p = _libstdcxx.__cxa_demangle(name.encode(), None, None, ctypes.byref(status))
+    if status.value != 0 or not p:
+        raise PreprocessError("cxxfilt.InvalidName: %s" % name)
+    s = ctypes.string_at(p).decode()
+    libc = ctypes.CDLL('libc.so.6')
+    libc.free.argtypes = [ctypes.c_void_p]
+    libc.free(p)
+    return s
+
+
+class SeriesOut:
+    """One report.js series (sofa_models.py:1-7): device-produced record bytes."""
+    def __init__(self, name, title, color, records=None, nrec=0):
+        self.name, self.title, self.color = name, title, color
+        self.records, self.nrec = records, nrec
+
+
+def _json_str(s):
+    import json
+    return json.dumps(s)
+
+
+def write_report_js(series, path):
+    """traces_to_json (:343-374): records come from the device, wrappers from here."""
+    if len(series) == 0:
+        return
+    with open(path, 'wb') as f:
+        for s in series:
+            if s.nrec > 0:
+                f.write(("%s = {\"name\": %s, \"color\": %s, \"data\": [" %
+                         (s.name, _json_str(s.title), _json_str(s.color))).encode())
+                f.write(memoryview(s.records))
+                f.write(b"]}")
+            f.write(b"\n\n")
+        f.write(b"sofa_traces = [ ")
+        for s in series:
+            if s.nrec > 0:
+                f.write((s.name + ",").encode())
+        f.write(b" ]")
+
+
+def _read_bytes(path):
+    with open(path, 'rb') as f:
+        return f.read()
+
+
+def _check_keyword(kw):
+    if any(ch in kw for ch in '.^$*+?{}[]\\|()'):
+        raise PreprocessError("filter keyword %r contains regex metacharacters; the device "
+                              "matcher implements literal substring search only" % kw)
+    if len(kw.encode()) > 32 or len(kw) == 0:
+        raise PreprocessError("filter keyword %r must be 1..32 bytes" % kw)
+
+
+def gpu_first_timestamp(nvvp):
+    """First CUPTI activity start / 1e9 (:1355-1380) via stdlib sqlite3; 0 when the tables
+    cannot be read (the reference swallows every exception)."""
+    import sqlite3
+    bases = []
+    for tbl in ('CUPTI_ACTIVITY_KIND_MEMSET', 'CUPTI_ACTIVITY_KIND_MEMCPY',
+                'CUPTI_ACTIVITY_KIND_CONCURRENT_KERNEL', 'CUPTI_ACTIVITY_KIND_KERNEL'):
+        try:
+            con = sqlite3.connect('file:%s?mode=ro' % nvvp, uri=True)
+            try:
+                row = con.execute('SELECT start FROM %s LIMIT 1' % tbl).fetchone()
+            finally:
+                con.close()
+            if row is not None:
+                bases.append(row[0])
+        except Exception:
+            pass
+    return sorted(bases)[0] * 1.0 / 1e+9 if bases else 0
+
+
+def sofa_preprocess(cfg, engine=None):
+    print_main_progress('SOFA preprocessing...')
+    own_engine = engine is None
+    if own_engine:
+        from .engine import CudaEngine
+        engine = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
+    try:
+        return _preprocess(cfg, engine)
+    finally:
+        if own_engine:
+            engine.close()
+
+
+def _preprocess(cfg, eng):
+    cfg.time_base = 0
+    logdir = cfg.logdir
+    with open(logdir + 'misc.txt', 'r') as f:
+        lines = f.readlines()
+        if len(lines) == 4:
+            cfg.pid = int(lines[3].split()[1])
+        else:
+            print_warning(cfg, 'Incorrect misc.txt content. Some profiling information may not be available.')
+    for fn in NOT_YET:
+        if os.path.isfile(logdir + fn) and os.path.getsize(logdir + fn) > 0:
+            raise NotImplementedError("%s: this source is not on the accelerated hot path yet "
+                                      "(SURVEY.md §8f N1); remove it or use the reference" % fn)
+    if int(os.system('command -v perf 1> /dev/null')) == 0 and os.path.isfile(logdir + 'perf.data'):
+        with open(logdir + 'perf.script', 'w') as logfile:
+            subprocess.call('perf script -F time,pid,tid,event,ip,sym,dso,symoff,period,brstack,brstacksym '
+                            '-i %s/perf.data --kallsym %s/kallsyms' % (logdir, logdir),
+                            shell=True, stdout=logfile, stderr=subprocess.DEVNULL)
+    cfg.time_base = hl.read_time_base(logdir, cfg.cpu_time_offset)
+    print_info(cfg, 'Time offset applied to timestamp (s):' + str(cfg.cpu_time_offset))
+    print_info(cfg, 'SOFA global time base (s):' + str(cfg.time_base))
+    mhz_xp, mhz_fp = hl.read_cpuinfo(logdir)
+    ratio = int(cfg.plot_ratio)
+    if ratio < 1:
+        raise PreprocessError("plot_ratio must be >= 1")
+
+    net_series = SeriesOut('net_trace', 'NET', 'blue')
+    gpu_series = SeriesOut('gpu_kernel_trace', 'GPU kernel', 'rgba(0,180,0,0.8)')
+    gpu_filter_series = []
+    cpu_series = []
+
+    # ---------------- network (:1187-1232): nettrace.csv holds the down-sampled rows
+    if os.path.isfile('%s/sofa.pcap' % logdir):
+        if not os.path.isfile(logdir + 'net.tmp') or os.path.getsize(logdir + 'sofa.pcap') > 0:
+            with open(logdir + 'net.tmp', 'w') as f:
+                subprocess.check_call(["tcpdump", "-q", "-n", "-tt", "-r", "%s/sofa.pcap" % logdir],
+                                      stdout=f, stderr=subprocess.DEVNULL)
+        text = _read_bytes(logdir + 'net.tmp')
+        print_info(cfg, "Length of net_traces = %d" % text.count(b'\n'))
+        if len(text) > 0:
+            if getattr(cfg, 'net_filters', None):
+                raise NotImplementedError("network_filters series are not implemented")
+            p = hl.base_params(SRC_NET, cfg.time_base, cfg.absolute_timestamp, 0.0)
+            eng.load(SRC_NET, text, p)
+            body = eng.csv(SRC_NET, ratio)
+            with open(logdir + 'nettrace.csv', 'wb') as f:
+                f.write(CSV_HEADER)
+                f.write(memoryview(body))
+            net_series.records, net_series.nrec = eng.json(SRC_NET, ratio, -1)
+    else:
+        print_warning(cfg, "no network traces were recorded.")
+
+    # ---------------- GPU (:1343-1457)
+    nvvps = glob.glob(logdir + "gputrace*[0-9].nvvp")
+    if len(nvvps) > 1:
+        raise NotImplementedError("more than one gputrace*.nvvp: the reference overwrites gputrace.csv "
+                                  "per file in glob order (SURVEY.md §7); not supported")
+    for nvvp in nvvps:
+        print_progress(cfg, "Read " + nvvp + " by nvprof -- begin")
+        if not os.path.isfile(logdir + 'gputrace.tmp') or os.path.getsize(nvvp) > 0:
+            with open(logdir + "gputrace.tmp", "w") as f:
+                subprocess.call(["nvprof", "--csv", "--print-gpu-trace", "-i", nvvp], stderr=f)
+        t_glb_gpu_base = gpu_first_timestamp(nvvp)
+        print_info(cfg, "Timestamp of the first GPU trace = " + str(t_glb_gpu_base))
+        print_progress(cfg, "Read " + nvvp + " by nvprof -- end")
+        text = _read_bytes(logdir + 'gputrace.tmp')
+        hdr = hl.gpu_header(text[:1 << 16]) if len(text) > 0 else None
+        if hdr is None:
+            print_warning(cfg, "gputrace existed, but no kernel traces were recorded.")
+            continue
+        upd, data_off = hdr
+        p = hl.base_params(SRC_GPU, cfg.time_base, cfg.absolute_timestamp, t_glb_gpu_base - upd.pop('t_base'))
+        p.update(upd)
+        p['n_cudaproc'] = 1
+        n_rows, _ = eng.load(SRC_GPU, text, p, data_off)
+        print_info(cfg, "Length of gpu_traces = %d" % n_rows)
+        body = eng.csv(SRC_GPU, 1)
+        with open(logdir + 'gputrace.csv', 'wb') as f:
+            f.write(CSV_HEADER)
+            f.write(memoryview(body))
+        gpu_series.records, gpu_series.nrec = eng.json(SRC_GPU, ratio, -1)
+        kws = [flt.keyword for flt in cfg.gpu_filters]
+        for kw in kws:
+            _check_keyword(kw)
+        if kws:
+            eng.set_filters(SRC_GPU, 1, kws)                   # on the FULL frame (:1446-1452)
+            for i, flt in enumerate(cfg.gpu_filters):
+                rec, nrec = eng.json(SRC_GPU, 1, i)
+                gpu_filter_series.append(SeriesOut(flt.keyword, '[keyword]' + flt.keyword, flt.color, rec, nrec))
+
+    if getattr(cfg, 'cuda_api_tracing', False):
+        raise NotImplementedError("cuda_api_tracing (a4) is not implemented")
+
+    # ---------------- CPU (:1544-1551, 1766-1838)
+    cfg.perf_events = hl.read_perf_events(logdir)
+    print_info(cfg, 'perf_events_used: %s' % (cfg.perf_events))
+    if glob.glob(logdir + "cuhello*[0-9].nvvp"):
+        print_warning(cfg, "cuhello nvvp clock sync needs nvprof's sqlite export; using perf_timebase.txt")
+    t_offset = hl.read_perf_timebase(logdir)
+    try:
+        if not os.path.isfile(logdir + 'perf.script'):
+            raise IOError('perf.script')
+        text = _read_bytes(logdir + 'perf.script')
+        print_info(cfg, "Length of cpu_traces = %d" % text.count(b'\n'))
+        if len(text) > 0:
+            p = hl.base_params(SRC_PERF, cfg.time_base, cfg.absolute_timestamp, t_offset)
+            p['perf_has_cycles'] = 1 if cfg.perf_events.find('cycles') != -1 else 0
+            p['mhz_xp'], p['mhz_fp'] = mhz_xp, mhz_fp
+            eng.load(SRC_PERF, text, p)
+            body = eng.csv(SRC_PERF, 1)
+            with open(logdir + 'cputrace.csv', 'wb') as f:
+                f.write(CSV_HEADER)
+                f.write(memoryview(body))
+            mangled = eng.viz_mangled(ratio)                  # unique _Z... viz names
+            eng.set_demangled([(m, demangle(m)) for m in mangled])
+            rec, nrec = eng.json(SRC_PERF, ratio, -1)
+            cpu_series.append(SeriesOut('cpu_trace', 'CPU', 'DarkGray', rec, nrec))
+            kws = [flt.keyword for flt in cfg.cpu_filters]
+            for kw in kws:
+                _check_keyword(kw)
+            if kws:
+                eng.set_filters(SRC_PERF, ratio, kws)         # on the viz frame (:1819-1827)
+                for i, flt in enumerate(cfg.cpu_filters):
+                    rec, nrec = eng.json(SRC_PERF, ratio, i)
+                    cpu_series.append(SeriesOut(flt.keyword, '[keyword]' + flt.keyword, flt.color, rec, nrec))
+    except IOError:
+        print_warning(cfg, 'no perf traces.')
+
+    print_progress(cfg, "Export Overhead Dynamics JSON File of CPU, Network and GPU traces -- begin")
+    # ---------------- series list (:1849-2102); sources off the hot path are empty here
+    series = list(cpu_series)
+    for nm in ('blktrace_starting_block', 'blktrace_time', 'vmstat_cs', 'vmstat_bi', 'vmstat_bo'):
+        series.append(SeriesOut(nm, nm, ''))
+    if cfg.enable_mpstat:
+        series.append(SeriesOut('mpstat_usr', 'MPSTAT_USR', 'Cyan'))
+    if cfg.enable_diskstat:
+        series.append(SeriesOut('diskstat', 'DISKSTAT', 'GreenYellow'))
+    if cfg.enable_vmstat:
+        for nm in ('vmstat_usr', 'vmstat_sys', 'vmstat_in', 'vmstat_cs'):
+            series.append(SeriesOut(nm, nm, ''))
+    for nm in ('strace', 'pystacks', 'nvsmi_mem', 'nvsmi_sm'):
+        series.append(SeriesOut(nm, nm, ''))
+    if getattr(cfg, 'enable_encode_decode', False):
+        series.append(SeriesOut('nvsmi_enc', '', ''))
+        series.append(SeriesOut('nvsmi_dec', '', ''))
+    series.append(net_series)
+    series.append(SeriesOut('tx_bandwidth', 'tx Bandwidth', 'rgba(135,206,250,0.8)'))
+    series.append(SeriesOut('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)'))
+    series.append(gpu_series)
+    series.extend(gpu_filter_series)
+    write_report_js(series, logdir + 'report.js')
+    print_progress(cfg, "Export Overhead Dynamics JSON File of CPU, Network and GPU traces -- end")

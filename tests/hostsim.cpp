@@ -1,0 +1,127 @@
+// CPU unit-test harness (TEST INFRASTRUCTURE): compiles the __host__ __device__ codecs of
+// sofa_b200/csrc/*.cuh with g++ so their exact arithmetic can be checked against
+// Python/numpy/pandas in the build container.  Never loaded by the product path.
+#include <string.h>
+#include "../sofa_b200/csrc/num.cuh"
+using namespace sofa;
+extern "C" {
+int hs_parse_double(const char* s, int n, double* out) { return parse_double(s, n, out); }
+int hs_parse_i64(const char* s, int n, long long* out) { int64_t v = 0; int r = parse_i64(s, n, &v); *out = v; return r; }
+int hs_fmt_fixed6(double x, char* out) { return fmt_fixed6(x, out); }
+int hs_len_fixed6(double x) { return len_fixed6(x); }
+int hs_fmt_i64(long long v, char* out) { return fmt_i64((int64_t)v, out); }
+int hs_json_double(double x, char* out) { return json_double(x, out); }
+double hs_log10(double x) { return log10_cr(x); }
+double hs_log2(double x) { return log2_cr(x); }
+double hs_interp(double x, const double* xp, const double* fp, int n) { return interp1(x, xp, fp, n); }
+double hs_ip_event_raw(unsigned long long ip, int h) { return ip_event_raw(ip, h); }
+void hs_log10_many(const double* x, double* y, long n) { for (long i = 0; i < n; i++) y[i] = log10_cr(x[i]); }
+void hs_log2_many(const double* x, double* y, long n) { for (long i = 0; i < n; i++) y[i] = log2_cr(x[i]); }
+// batch helpers: strings are packed back to back, off[i]..off[i+1]
+void hs_json_many(const double* x, long n, char* out, long* off) {
+    long o = 0;
+    for (long i = 0; i < n; i++) { off[i] = o; int l = json_double(x[i], out + o); if (l > 0) o += l; else { out[o++] = '?'; } }
+    off[n] = o;
+}
+void hs_fixed6_many(const double* x, long n, char* out, long* off) {
+    long o = 0;
+    for (long i = 0; i < n; i++) { off[i] = o; int l = fmt_fixed6(x[i], out + o); if (l > 0) o += l; else { out[o++] = '?'; } }
+    off[n] = o;
+}
+}
+
+// ---------------------------------------------------------------- row-level harness
+#include "../sofa_b200/csrc/rows.cuh"
+#include <vector>
+#include <string>
+struct HsCfg {
+    double time_base, t_offset; int absolute_timestamp, perf_has_cycles, n_mhz;
+    const double* mhz_xp; const double* mhz_fp;
+    double ts_rescale, dt_rescale, payload_unit; int n_cudaproc;
+    int idx[9];
+};
+static IngestCfg mk(const HsCfg* h) {
+    IngestCfg c; c.time_base = h->time_base; c.t_offset = h->t_offset; c.absolute_timestamp = h->absolute_timestamp;
+    c.perf_has_cycles = h->perf_has_cycles; c.n_mhz = h->n_mhz; c.mhz_xp = h->mhz_xp; c.mhz_fp = h->mhz_fp;
+    c.ts_rescale = h->ts_rescale; c.dt_rescale = h->dt_rescale; c.payload_unit = h->payload_unit; c.n_cudaproc = h->n_cudaproc;
+    c.idx_start = h->idx[0]; c.idx_dur = h->idx[1]; c.idx_size = h->idx[2]; c.idx_thr = h->idx[3]; c.idx_ctx = h->idx[4];
+    c.idx_stream = h->idx[5]; c.idx_name = h->idx[6]; c.idx_srcctx = h->idx[7]; c.idx_dstctx = h->idx[8];
+    return c;
+}
+// demangle table for viz names: sorted FNV hashes -> strings
+struct HsDict { int n; const unsigned long long* hash; const long* off; const char* blob; };
+struct DictVizName {
+    PerfVizName<const char*> raw; const HsDict* d;
+    template <class K> void gen(K& k) const {
+        HashSink h; raw.gen(h);
+        if (h.len >= 2 && h.c0 == '_' && h.c1 == 'Z' && d) {
+            for (int i = 0; i < d->n; i++) if (d->hash[i] == h.h) { for (long j = d->off[i]; j < d->off[i + 1]; j++) k.put(d->blob[j]); return; }
+        }
+        raw.gen(k);
+    }
+};
+extern "C" {
+// mode 0: CSV of all rows (stride applies to net only, as in the reference); mode 1: JSON records of
+// rows i%stride==0 (perf: viz names); mode 2: JSON records of rows whose name contains `kw`
+// (perf: on the down-sampled viz frame; gpu: on the full frame).  Returns -1 or (1000*row + err).
+long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mode, int stride, unsigned fmask,
+                const char* kw, const HsDict* dict, char* out, long* outlen, unsigned* flags, long* nrec) {
+    IngestCfg c = mk(h);
+    long o = 0, row = 0, pos = 0, cnt = 0;
+    unsigned fl = 0;
+    FilterTable ft; memset(&ft, 0, sizeof(ft));
+    if (kw) { int L = (int)strlen(kw); ft.nk = 1; for (int i = 0; i < L; i++) ft.mask[0][(unsigned char)kw[i]] |= 1u << i; ft.final_bit[0] = 1u << (L - 1); }
+    while (pos < nbytes) {
+        long e = pos; while (e < nbytes && text[e] != '\n') e++;
+        long linelen = e - pos;                    // without '\n'
+        long with_nl = (e < nbytes) ? linelen + 1 : linelen;
+        const char* line = text + pos;
+        int err = 0, len = 0;
+        bool sel = (row % stride) == 0;
+        if (kind == SRC_PERF) {
+            PerfRow r; err = parse_perf(line, (int)linelen, c, &r);
+            if (!err) {
+                RowVals v = vals_perf(r);
+                PerfName<const char*> ng{line, r};
+                if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
+                else if (sel) {
+                    DictVizName vz{PerfVizName<const char*>{ng}, dict};
+                    bool take = true;
+                    if (mode == 2) { MatchSink ms(&ft); vz.gen(ms); take = ms.hit != 0; }
+                    if (take) { int l = json_row_len(v, fmask, vz); if (l < 0) err = E_FORMAT; else { len = json_row_write(v, fmask, vz, out + o); if (len != l) err = 99; } }
+                }
+            }
+        } else if (kind == SRC_GPU) {
+            GpuRow r; err = parse_gpu(line, (int)with_nl, c, &r);
+            if (!err) {
+                if (sel) fl |= r.bw_is_float ? 1u : 0u;
+                RowVals v = vals_gpu(r, c.n_cudaproc);
+                GpuName<const char*> ng{line, r};
+                if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
+                else {
+                    bool take = (mode == 1) ? sel : true;
+                    if (mode == 2) { MatchSink ms(&ft); ng.gen(ms); take = ms.hit != 0; }
+                    if (take) { int l = json_row_len(v, fmask, ng); if (l < 0) err = E_FORMAT; else { len = json_row_write(v, fmask, ng, out + o); if (len != l) err = 99; } }
+                }
+            }
+        } else {
+            NetRow r; err = parse_net(line, (int)linelen, c, &r);
+            if (!err) {
+                if (sel) fl |= r.proto == 0 ? 2u : 4u;
+                RowVals v = vals_net(r);
+                NetName ng{r};
+                if (sel) {
+                    if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
+                    else { int l = json_row_len(v, fmask, ng); if (l < 0) err = E_FORMAT; else { len = json_row_write(v, fmask, ng, out + o); if (len != l) err = 99; } }
+                }
+            }
+        }
+        if (err) return row * 1000 + err;
+        o += len; row++; if (len > 0) cnt++;
+        pos = e + 1;
+    }
+    *outlen = o; *flags = fl; *nrec = cnt;
+    return -1;
+}
+unsigned long long hs_fnv(const char* s, long n) { HashSink h; for (long i = 0; i < n; i++) h.put(s[i]); return h.h; }
+}

@@ -1,0 +1,141 @@
+"""Engine with the CudaEngine interface, backed by the CPU build of the row codecs
+(tests/hostsim.cpp).  TEST INFRASTRUCTURE: lets the `not gpu` suite drive the product's
+host logic (sofa_b200.sofa_preprocess) and check the device row functions' arithmetic and
+text output against the reference's golden files without a GPU.  The product never
+imports this module."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class HsCfg(ctypes.Structure):
+    _fields_ = [("time_base", ctypes.c_double), ("t_offset", ctypes.c_double),
+                ("absolute_timestamp", ctypes.c_int), ("perf_has_cycles", ctypes.c_int),
+                ("n_mhz", ctypes.c_int), ("mhz_xp", ctypes.c_void_p), ("mhz_fp", ctypes.c_void_p),
+                ("ts_rescale", ctypes.c_double), ("dt_rescale", ctypes.c_double),
+                ("payload_unit", ctypes.c_double), ("n_cudaproc", ctypes.c_int),
+                ("idx", ctypes.c_int * 9)]
+
+
+class HsDict(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int), ("hash", ctypes.c_void_p), ("off", ctypes.c_void_p),
+                ("blob", ctypes.c_char_p)]
+
+
+def build_hostsim():
+    so = os.path.join(HERE, "_build", "libhostsim.so")
+    src = os.path.join(HERE, "hostsim.cpp")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    deps = [src] + [os.path.join(HERE, "..", "sofa_b200", "csrc", f) for f in ("num.cuh", "rows.cuh")]
+    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
+                               "-o", so, src])
+    lib = ctypes.CDLL(so)
+    lib.hs_process.restype = ctypes.c_long
+    lib.hs_fnv.restype = ctypes.c_ulonglong
+    return lib
+
+
+class HostSimError(RuntimeError):
+    pass
+
+
+class HostSimEngine:
+    def __init__(self):
+        self.lib = build_hostsim()
+        self.src = {}
+        self.filters = {}
+        self.dict = None
+        self._keep = []
+
+    def close(self):
+        pass
+
+    def _cfg(self, p):
+        c = HsCfg()
+        c.time_base, c.t_offset = p['time_base'], p['t_offset']
+        c.absolute_timestamp, c.perf_has_cycles = p['absolute_timestamp'], p['perf_has_cycles']
+        xp = np.array(p['mhz_xp'], dtype=np.float64)
+        fp = np.array(p['mhz_fp'], dtype=np.float64)
+        self._keep += [xp, fp]
+        c.n_mhz, c.mhz_xp, c.mhz_fp = len(xp), xp.ctypes.data, fp.ctypes.data
+        c.ts_rescale, c.dt_rescale, c.payload_unit = p['ts_rescale'], p['dt_rescale'], p['payload_unit']
+        c.n_cudaproc = p['n_cudaproc']
+        for i in range(9):
+            c.idx[i] = p['idx'][i]
+        return c
+
+    def _run(self, kind, mode, stride, fmask, kw=None):
+        text, cfg = self.src[kind]
+        out = ctypes.create_string_buffer(len(text) * 6 + 4096)
+        outlen = ctypes.c_long()
+        flags = ctypes.c_uint()
+        nrec = ctypes.c_long()
+        d = ctypes.byref(self.dict) if (self.dict is not None and kind == 0) else None
+        r = self.lib.hs_process(kind, text, ctypes.c_long(len(text)), ctypes.byref(cfg), mode, stride,
+                                ctypes.c_uint(fmask), kw.encode() if kw else None, d, out,
+                                ctypes.byref(outlen), ctypes.byref(flags), ctypes.byref(nrec))
+        if r != -1:
+            raise HostSimError("row %d: error %d" % (r // 1000, r % 1000))
+        return np.frombuffer(out.raw[:outlen.value], dtype=np.uint8), flags.value, nrec.value
+
+    def load(self, kind, text, params, data_off=0):
+        text = bytes(text)[data_off:]
+        self.src[kind] = (text, self._cfg(params))
+        _, flags, n = self._run(kind, 0, 1, 0x1fff)
+        return n, flags
+
+    def _fmask(self, kind, stride):
+        _, flags, _ = self._run(kind, 0 if kind == 2 else 1, stride, 0x1fff)
+        if kind == 0:
+            return 0b111
+        if kind == 1:
+            return 0b101 | (0b1000000 if flags & 1 else 0)
+        if flags & 2:
+            if not flags & 4:
+                raise HostSimError("every down-sampled packet row is empty")
+            return 0x17ff            # every numeric column (0..10, 12)
+        return 0b1000101
+
+    def csv(self, kind, stride):
+        return self._run(kind, 0, stride, self._fmask(kind, stride))[0]
+
+    def set_filters(self, kind, stride, kws):
+        self.filters[kind] = (stride, list(kws))
+
+    def json(self, kind, stride, filt):
+        if filt < 0:
+            out, _, n = self._run(kind, 1, stride, self._fmask(kind, stride))
+        else:
+            fstride, kws = self.filters[kind]
+            assert fstride == stride
+            out, _, n = self._run(kind, 2, stride, self._fmask(kind, stride), kws[filt])
+        return out[2:], n
+
+    def viz_mangled(self, stride):
+        text, _ = self.src[0]
+        names = set()
+        for i, line in enumerate(text.decode().split('\n')):
+            if not line or i % stride:
+                continue
+            tok = line.split()
+            sh = 1 if (tok[1].startswith('[') and tok[1].endswith(']')) else 0
+            x = '[%s]' % tok[3 + sh].replace('-', '_') + tok[5 + sh] + tok[6 + sh]
+            v = x[x.find(']') + 1: x.find('+')].split('@')[0]
+            if v.startswith('_Z'):
+                names.add(v)
+        return sorted(names)
+
+    def set_demangled(self, pairs):
+        pairs = sorted(pairs, key=lambda p: self.lib.hs_fnv(p[0].encode(), ctypes.c_long(len(p[0].encode()))))
+        hashes = np.array([self.lib.hs_fnv(m.encode(), ctypes.c_long(len(m.encode()))) for m, _ in pairs], dtype=np.uint64)
+        blob = b"".join(d.encode() for _, d in pairs)
+        off = np.zeros(len(pairs) + 1, dtype=np.int64)
+        for i, (_, d) in enumerate(pairs):
+            off[i + 1] = off[i] + len(d.encode())
+        self._keep += [hashes, off, blob]
+        self.dict = HsDict(len(pairs), hashes.ctypes.data, off.ctypes.data, blob)
