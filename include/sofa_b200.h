@@ -1,0 +1,152 @@
+/* libsofa_b200.so - C ABI of the B200-native SOFA trace preprocess/analyze hot path.
+ *
+ * The reference (cyliustack/sofa) has no FFI: its hot path is the pair of Python entry
+ * points sofa_preprocess(cfg) (bin/sofa_preprocess.py:377) and sofa_analyze(cfg)
+ * (bin/sofa_analyze.py:793).  This library is what those entry points bind through
+ * ctypes; each entry below names the reference code it replaces.
+ *
+ * Conventions: every function returns 0 on success or a negative SOFA_ERR_* code; the
+ * message is available from sofa_b200_last_error().  No exception crosses the boundary.
+ * The caller owns host buffers, the library owns device buffers behind an opaque
+ * sofa_ctx (one per GPU; not thread-safe per ctx, safe across ctxs).  All calls are
+ * synchronous on the ctx's stream.  Plain pointers and sizes only - no torch types.
+ */
+#ifndef SOFA_B200_H
+#define SOFA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOFA_B200_ABI_VERSION 1
+
+#define SOFA_OK 0
+#define SOFA_ERR_CUDA (-1)   /* CUDA runtime error */
+#define SOFA_ERR_ARG (-2)    /* bad argument */
+#define SOFA_ERR_ROW (-3)    /* a record the reference would raise on; see sofa_b200_error_row */
+#define SOFA_ERR_STATE (-4)  /* call order (e.g. emit before parse) */
+#define SOFA_ERR_CAP (-5)    /* caller buffer too small */
+
+enum { SOFA_SRC_PERF = 0, SOFA_SRC_GPU = 1, SOFA_SRC_NET = 2 };
+
+typedef struct sofa_ctx sofa_ctx;
+
+/* Scalars that parameterise one source's ingest (computed once per file by the host,
+ * reference sofa_preprocess.py:418-436, 1385-1419, 1545-1551, 1766-1796). */
+typedef struct {
+    double time_base;            /* cfg.time_base */
+    double t_offset;             /* perf: unix-uptime; gpu: t_glb_gpu_base - t_base; net: 0 */
+    int32_t absolute_timestamp;  /* cfg.absolute_timestamp */
+    int32_t perf_has_cycles;     /* cfg.perf_events.find('cycles') != -1 */
+    int32_t n_mhz;               /* len(cpu_mhz_xp), >= 1 */
+    int32_t n_cudaproc;          /* pid column of gpu rows */
+    const double* mhz_xp;        /* host pointers, n_mhz entries each */
+    const double* mhz_fp;
+    double ts_rescale, dt_rescale, payload_unit;
+    int32_t idx[9];              /* Start, Duration, Size, Throughput, Context, Stream, Name, Src Ctx, Dst Ctx; -1 = absent */
+    int32_t reserved;
+} sofa_ingest_params_t;
+
+/* gpu_profile (sofa_analyze.py:343-377) + comm_profile (sofa_common.py:23-177) results */
+typedef struct {
+    double gpu_time, kernel_time, nccl_time;
+    int64_t num_gpus;            /* number of distinct deviceId values */
+    int64_t n_gpus_max;          /* max(deviceId) (comm_profile n_gpus); 0 -> no comm report */
+    double payload[4];           /* H2D, D2H, D2D, P2P summed payload */
+    double bandwidth[4];         /* mean bandwidth where payload > 64000 */
+    double duration[4];          /* summed duration */
+    /* (1+n) x (1+n) row-major matrices, n = min(n_gpus_max, 15): payload sum, count, bw sum, bw count */
+    double accum[256], accum_count[256], accum_bw[256], accum_bw_count[256];
+} sofa_gpu_profile_t;
+
+typedef struct {
+    uint64_t launches[32];       /* kernel launches per kernel kind */
+    double ms[32];               /* CUDA-event time per kernel kind (profiling on) */
+    uint64_t h2d_bytes, d2h_bytes;
+} sofa_stats_t;
+
+int sofa_b200_abi_version(void);
+const char* sofa_b200_last_error(void);
+/* row index and row error code of the last SOFA_ERR_ROW */
+int sofa_b200_error_row(sofa_ctx*, uint64_t* row, int32_t* code);
+
+int sofa_b200_create(sofa_ctx** out, int device);
+int sofa_b200_destroy(sofa_ctx*);
+
+/* pinned host memory for callers that want full-speed H2D/D2H */
+void* sofa_b200_host_alloc(uint64_t nbytes);
+void sofa_b200_host_free(void*);
+
+/* Copy one source's raw text to the device; records start at data_off (nvprof: after the
+ * three header rows).  Replaces f.readlines() of perf.script / gputrace.tmp / net.tmp
+ * (sofa_preprocess.py:1194, 1383, 1788). */
+int sofa_b200_upload(sofa_ctx*, int src, const void* text, uint64_t nbytes, uint64_t data_off);
+
+/* Line split + per-record parse into SoA columns on the device.  Replaces
+ * Pool.map(cpu_trace_read | gpu_trace_read | net_trace_read) (:110-341, 1196-1202,
+ * 1420-1432, 1791-1799). */
+int sofa_b200_parse(sofa_ctx*, int src, const sofa_ingest_params_t*, uint64_t* n_rows);
+
+/* Column dtype flags over rows i % stride == 0 (pandas dtype inference):
+ * bit0 some Throughput parsed as float (gpu), bit1 some [] packet row (net),
+ * bit2 some valid packet row (net). */
+int sofa_b200_row_flags(sofa_ctx*, int src, uint32_t stride, uint32_t* flags);
+
+/* <src>trace.csv body (no header line) of rows i % stride == 0, formatted on the device
+ * into output buffer 0.  Replaces DataFrame(...).to_csv(float_format='%.6f')
+ * (:1204-1211, 1433-1444, 1800-1807). */
+int sofa_b200_emit_csv(sofa_ctx*, int src, uint32_t stride, uint64_t* nbytes);
+
+/* Keyword filters, Series.str.contains(literal) (:1446-1452 gpu, full frame;
+ * :1819-1827 cpu, down-sampled demangled viz frame).  counts[k] = matching rows. */
+int sofa_b200_set_filters(sofa_ctx*, int src, uint32_t stride, int32_t nkw, const char* const* keywords,
+                          uint64_t* counts);
+
+/* Unique mangled (_Z...) viz names of perf rows i % stride == 0, '\n'-separated, into
+ * output buffer 2 (host demangles them once each: cxxfilt.demangle, :1811-1816). */
+int sofa_b200_viz_mangled(sofa_ctx*, uint32_t stride, uint64_t* nbytes, uint32_t* n_names);
+int sofa_b200_set_demangled(sofa_ctx*, uint32_t n, const char* mangled, const uint64_t* moff,
+                            const char* demangled, const uint64_t* doff);
+
+/* report.js records ("{...}, {...}") of one series into output buffer 1: rows
+ * i % stride == 0, restricted to filter `filter_idx` when >= 0.  Replaces
+ * json.loads(df.to_json(orient='records')) + json.dump (:343-374). */
+int sofa_b200_emit_json(sofa_ctx*, int src, uint32_t stride, int32_t filter_idx, uint64_t* nbytes,
+                        uint64_t* n_records);
+
+/* D2H of an output buffer (0 csv, 1 json, 2 names) */
+int sofa_b200_fetch(sofa_ctx*, int which, void* host_out, uint64_t cap);
+
+/* Raw device column to host (parity tests). perf: 0 ts,1 event,2 dur (f64), 9 pid, 10 tid (i32);
+ * gpu: 0 ts,2 dur,6 bw (f64), 5 payload (i64), 3 dev,10 tid,7 src,8 dst (i32), 4 kind (u8);
+ * net: 0 ts (f64), 5 payload,7 src,8 dst (i64), 4 proto (u8). */
+int sofa_b200_get_column(sofa_ctx*, int src, int col, void* host_out, uint64_t cap_bytes);
+
+/* gpu_profile + comm_profile features on the parsed gpu rows (sofa_analyze.py:343-377,
+ * sofa_common.py:23-177). */
+int sofa_b200_gpu_profile(sofa_ctx*, sofa_gpu_profile_t* out);
+
+/* get_top_k_events (sofa_analyze.py:34-44): names by summed duration, descending.
+ * names: '\n'-separated into output buffer 2; sums[k] their totals. */
+int sofa_b200_top_k(sofa_ctx*, int src, uint32_t k, double* sums, uint64_t* nbytes, uint32_t* n_out);
+
+/* cpu_profile (sofa_analyze.py:694-710): total duration and the k largest-duration rows
+ * (row indices, descending duration; ties by row index). */
+int sofa_b200_cpu_profile(sofa_ctx*, uint32_t k, double* total, uint64_t* rows, uint32_t* n_out);
+
+int sofa_b200_set_profiling(sofa_ctx*, int on);
+int sofa_b200_get_stats(sofa_ctx*, sofa_stats_t* out);
+int sofa_b200_reset_stats(sofa_ctx*);
+const char* sofa_b200_kernel_name(int kind);
+
+/* Synthetic trace text generated on the device (bench / test infrastructure; same spec as
+ * sofa_b200/synth.py).  variant: perf 0/1 = without/with [cpu] column; gpu 0 = s/ms/MB,
+ * 1 = ms/us/KB + P2P columns; net = percent of non-IP lines. */
+int sofa_b200_synth(sofa_ctx*, int src, uint64_t seed, uint64_t n_rows, int variant, uint64_t* nbytes);
+int sofa_b200_text_fetch(sofa_ctx*, int src, void* host_out, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

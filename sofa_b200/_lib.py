@@ -1,0 +1,97 @@
+"""ctypes binding of libsofa_b200.so (include/sofa_b200.h).  Fails loudly when the CUDA
+library is missing or no GPU is present: there is no CPU fallback."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsofa_b200.so")
+
+SOFA_OK, SOFA_ERR_CUDA, SOFA_ERR_ARG, SOFA_ERR_ROW, SOFA_ERR_STATE, SOFA_ERR_CAP = 0, -1, -2, -3, -4, -5
+
+EXPORTS = [
+    "sofa_b200_abi_version", "sofa_b200_last_error", "sofa_b200_error_row", "sofa_b200_create",
+    "sofa_b200_destroy", "sofa_b200_host_alloc", "sofa_b200_host_free", "sofa_b200_upload",
+    "sofa_b200_parse", "sofa_b200_row_flags", "sofa_b200_emit_csv", "sofa_b200_set_filters",
+    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_fetch",
+    "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
+    "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
+    "sofa_b200_synth", "sofa_b200_text_fetch",
+]
+
+
+class IngestParams(ctypes.Structure):
+    _fields_ = [("time_base", ctypes.c_double), ("t_offset", ctypes.c_double),
+                ("absolute_timestamp", ctypes.c_int32), ("perf_has_cycles", ctypes.c_int32),
+                ("n_mhz", ctypes.c_int32), ("n_cudaproc", ctypes.c_int32),
+                ("mhz_xp", ctypes.c_void_p), ("mhz_fp", ctypes.c_void_p),
+                ("ts_rescale", ctypes.c_double), ("dt_rescale", ctypes.c_double),
+                ("payload_unit", ctypes.c_double), ("idx", ctypes.c_int32 * 9),
+                ("reserved", ctypes.c_int32)]
+
+
+class GpuProfile(ctypes.Structure):
+    _fields_ = [("gpu_time", ctypes.c_double), ("kernel_time", ctypes.c_double),
+                ("nccl_time", ctypes.c_double), ("num_gpus", ctypes.c_int64),
+                ("n_gpus_max", ctypes.c_int64), ("payload", ctypes.c_double * 4),
+                ("bandwidth", ctypes.c_double * 4), ("duration", ctypes.c_double * 4),
+                ("accum", ctypes.c_double * 256), ("accum_count", ctypes.c_double * 256),
+                ("accum_bw", ctypes.c_double * 256), ("accum_bw_count", ctypes.c_double * 256)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("launches", ctypes.c_uint64 * 32), ("ms", ctypes.c_double * 32),
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+
+
+class SofaB200Error(RuntimeError):
+    def __init__(self, code, msg, row=None, row_code=None):
+        RuntimeError.__init__(self, "libsofa_b200 error %d: %s" % (code, msg))
+        self.code, self.row, self.row_code = code, row, row_code
+
+
+_lib = None
+
+
+def load_lib():
+    """Load libsofa_b200.so; raise if it has not been built (python __graft_entry__.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                          "sofa_b200 has no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    vp = ctypes.c_void_p
+    lib.sofa_b200_last_error.restype = ctypes.c_char_p
+    lib.sofa_b200_kernel_name.restype = ctypes.c_char_p
+    lib.sofa_b200_host_alloc.restype = ctypes.c_void_p
+    lib.sofa_b200_host_alloc.argtypes = [ctypes.c_uint64]
+    lib.sofa_b200_host_free.argtypes = [vp]
+    lib.sofa_b200_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    lib.sofa_b200_destroy.argtypes = [vp]
+    lib.sofa_b200_error_row.argtypes = [vp, u64p, ctypes.POINTER(ctypes.c_int32)]
+    lib.sofa_b200_upload.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_uint64]
+    lib.sofa_b200_parse.argtypes = [vp, ctypes.c_int, ctypes.POINTER(IngestParams), u64p]
+    lib.sofa_b200_row_flags.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, u32p]
+    lib.sofa_b200_emit_csv.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, u64p]
+    lib.sofa_b200_set_filters.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32,
+                                          ctypes.POINTER(ctypes.c_char_p), u64p]
+    lib.sofa_b200_viz_mangled.argtypes = [vp, ctypes.c_uint32, u64p, u32p]
+    lib.sofa_b200_set_demangled.argtypes = [vp, ctypes.c_uint32, ctypes.c_char_p, u64p, ctypes.c_char_p, u64p]
+    lib.sofa_b200_emit_json.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32, u64p, u64p]
+    lib.sofa_b200_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
+    lib.sofa_b200_get_column.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64]
+    lib.sofa_b200_gpu_profile.argtypes = [vp, ctypes.POINTER(GpuProfile)]
+    lib.sofa_b200_top_k.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p, u32p]
+    lib.sofa_b200_cpu_profile.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p, u32p]
+    lib.sofa_b200_set_profiling.argtypes = [vp, ctypes.c_int]
+    lib.sofa_b200_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    lib.sofa_b200_reset_stats.argtypes = [vp]
+    lib.sofa_b200_synth.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, u64p]
+    lib.sofa_b200_text_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
+    if lib.sofa_b200_abi_version() != 1:
+        raise ImportError("libsofa_b200.so ABI version mismatch")
+    _lib = lib
+    return lib

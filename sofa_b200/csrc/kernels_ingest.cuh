@@ -1,0 +1,185 @@
+// Ingest: newline index + per-record parse into SoA columns.
+//
+// The text of one source sits in HBM as one byte buffer.  It is cut into fixed-size byte
+// tiles; a line belongs to the tile its first byte falls in.  k_count_lines counts the
+// line starts of every tile (128-bit loads, SWAR newline compare), a scan turns counts
+// into first-row indices, and k_parse<KIND> stages each tile (+ an overlap window for the
+// last line) in shared memory with coalesced 128-bit loads, finds the line starts with a
+// block scan and parses one record per thread out of shared memory, writing the columns
+// with coalesced stores (row i of the tile -> thread i).
+#pragma once
+#include "rows.cuh"
+#include "devutil.cuh"
+
+namespace sofa {
+
+struct PerfCols {
+    double *ts, *event, *dur; int32_t *pid, *tid; uint64_t* line_start; uint16_t* pieces;   // 6 u16 per row
+};
+struct GpuCols {
+    double *ts, *dur, *bw; int64_t* payload; int32_t *dev, *tid, *src, *dst; uint8_t *kind, *bwf;
+    uint64_t* line_start; uint16_t *noff, *nlen;
+};
+struct NetCols { double* ts; int64_t *payload, *src, *dst; uint8_t* proto; };
+
+struct AllCols { PerfCols p; GpuCols g; NetCols n; };
+
+__device__ __forceinline__ uint32_t newline_mask4(uint32_t w) {       // 0xff in every byte equal to '\n'
+    return __vcmpeq4(w, 0x0a0a0a0au);
+}
+
+// Line starts owned by tile t: `begin` itself (first tile) and q+1 for every newline at
+// q in [max(b0-1,begin), min(b1-1,end-1)).
+__global__ void __launch_bounds__(PARSE_TPB)
+k_count_lines(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t tile_bytes,
+              uint64_t* __restrict__ tile_counts, unsigned int* __restrict__ cr_flag) {
+    __shared__ uint32_t sm[33];
+    uint64_t t = blockIdx.x;
+    uint64_t b0 = begin + t * (uint64_t)tile_bytes;
+    uint64_t b1 = b0 + tile_bytes < end ? b0 + tile_bytes : end;
+    uint64_t qlo = (b0 == begin) ? begin : b0 - 1;
+    uint64_t qhi = (b1 - 1 < end - 1) ? b1 - 1 : end - 1;
+    uint32_t cnt = 0;
+    bool cr = false;
+    uint64_t a0 = qlo & ~15ull;
+    const uint4* t4 = reinterpret_cast<const uint4*>(text);
+    for (uint64_t p = a0 + 16ull * threadIdx.x; p < qhi; p += 16ull * blockDim.x) {
+        uint4 v = t4[p >> 4];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t m = newline_mask4(w[k]);
+            uint32_t c = __vcmpeq4(w[k], 0x0d0d0d0du);
+            uint64_t q = p + 4 * k;
+            if (q < qlo || q + 4 > qhi) {            // partial word: drop bytes outside [qlo, qhi)
+                uint32_t keep = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (q + j >= qlo && q + j < qhi) keep |= 0xffu << (8 * j);
+                m &= keep; c &= keep;
+            }
+            cnt += __popc(m) >> 3;
+            cr |= (c != 0);
+        }
+    }
+    if (threadIdx.x == 0 && b0 == begin && begin < end) cnt += 1;
+    uint32_t total;
+    block_excl_scan(cnt, &total, sm);
+    if (threadIdx.x == 0) tile_counts[t] = total;
+    if (cr) atomicOr(cr_flag, 1u);
+}
+
+// In-place exclusive scan of a[0..n) (single block); a[n] = total.
+__global__ void __launch_bounds__(1024) k_scan_u64(uint64_t* a, uint64_t n) {
+    __shared__ uint64_t sm[33];
+    constexpr int PER = 8;
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < n; base += 1024ull * PER) {
+        uint64_t v[PER];
+        uint64_t i0 = base + (uint64_t)threadIdx.x * PER;
+        uint64_t s = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { v[k] = (i0 + k < n) ? a[i0 + k] : 0; s += v[k]; }
+        uint64_t total;
+        uint64_t ex = block_excl_scan64(s, &total, sm) + carry;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { if (i0 + k < n) a[i0 + k] = ex; ex += v[k]; }
+        carry += total;
+    }
+    if (threadIdx.x == 0) a[n] = carry;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PARSE_TPB)
+k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t tile_bytes, uint32_t max_lines,
+        const uint64_t* __restrict__ tile_row_base, IngestCfg cfg, AllCols cols, unsigned long long* err) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t sm[33];
+    uint64_t t = blockIdx.x;
+    uint64_t b0 = begin + t * (uint64_t)tile_bytes;
+    uint64_t b1 = b0 + tile_bytes < end ? b0 + tile_bytes : end;
+    uint64_t qlo = (b0 == begin) ? begin : b0 - 1;
+    uint64_t qhi = (b1 - 1 < end - 1) ? b1 - 1 : end - 1;
+    uint64_t s0 = qlo & ~15ull;
+    uint64_t s1 = b1 + OVERLAP_BYTES < end ? b1 + OVERLAP_BYTES : end;
+    uint32_t stage_len = (uint32_t)(((s1 + 15) & ~15ull) - s0);
+    unsigned char* stage = smem;
+    uint32_t* lstart = reinterpret_cast<uint32_t*>(smem + (((size_t)tile_bytes + OVERLAP_BYTES + 48) & ~(size_t)15));
+    {   // coalesced 128-bit staging (buffer is padded past `end`)
+        const uint4* g4 = reinterpret_cast<const uint4*>(text + s0);
+        uint4* s4 = reinterpret_cast<uint4*>(stage);
+        for (uint32_t i = threadIdx.x; i < (stage_len >> 4); i += blockDim.x) s4[i] = g4[i];
+    }
+    __syncthreads();
+    // each thread scans a word-aligned chunk of the staged bytes for newlines in [qlo, qhi)
+    uint32_t scan_len = (uint32_t)(qhi > s0 ? qhi - s0 : 0);
+    uint32_t chunk = ((scan_len + blockDim.x - 1) / blockDim.x + 3) & ~3u;
+    if (((chunk >> 2) & 1u) == 0) chunk += 4;          // odd word stride: bank-conflict-free chunk scan
+    uint32_t c0 = threadIdx.x * chunk, c1 = c0 + chunk < scan_len ? c0 + chunk : scan_len;
+    uint32_t lo_rel = (uint32_t)(qlo - s0);
+    uint32_t cnt = 0;
+    for (uint32_t i = c0; i < c1; i++) cnt += (i >= lo_rel && stage[i] == '\n');
+    if (threadIdx.x == 0 && b0 == begin && begin < end) cnt += 1;
+    uint32_t total;
+    uint32_t ex = block_excl_scan(cnt, &total, sm);
+    if (total > max_lines) {
+        if (threadIdx.x == 0) report_error(err, tile_row_base[t], E_TOO_MANY_LINES);
+        return;
+    }
+    {
+        uint32_t k = ex;
+        if (threadIdx.x == 0 && b0 == begin && begin < end) lstart[k++] = (uint32_t)(begin - s0);
+        for (uint32_t i = c0; i < c1; i++) if (i >= lo_rel && stage[i] == '\n') lstart[k++] = i + 1;
+    }
+    __syncthreads();
+    uint32_t stage_end = (uint32_t)(s1 - s0);           // staged bytes that belong to the text
+    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+        uint32_t ls = lstart[j], le;
+        bool has_nl = true;
+        int code = E_OK;
+        if (j + 1 < total) {
+            le = lstart[j + 1] - 1;
+        } else {
+            le = ls;
+            while (le < stage_end && stage[le] != '\n') le++;
+            if (le >= stage_end) {
+                if (s1 >= end) has_nl = false;            // last line of the file without '\n'
+                else code = E_LINE_TOO_LONG;
+            }
+        }
+        uint64_t row = tile_row_base[t] + j;
+        const char* line = reinterpret_cast<const char*>(stage + ls);
+        int n = (int)(le - ls);
+        if (code == E_OK) {
+            if (KIND == SRC_PERF) {
+                PerfRow r;
+                code = parse_perf(line, n, cfg, &r);
+                if (code == E_OK) {
+                    cols.p.ts[row] = r.ts; cols.p.event[row] = r.event; cols.p.dur[row] = r.dur;
+                    cols.p.pid[row] = r.pid; cols.p.tid[row] = r.tid;
+                    cols.p.line_start[row] = s0 + ls;
+                    uint16_t* pc = cols.p.pieces + row * 6;
+                    pc[0] = r.evt_off; pc[1] = r.evt_len; pc[2] = r.sym_off; pc[3] = r.sym_len; pc[4] = r.dso_off; pc[5] = r.dso_len;
+                }
+            } else if (KIND == SRC_GPU) {
+                GpuRow r;
+                code = parse_gpu(line, n + (has_nl ? 1 : 0), cfg, &r);
+                if (code == E_OK) {
+                    cols.g.ts[row] = r.ts; cols.g.dur[row] = r.dur; cols.g.bw[row] = r.bw; cols.g.payload[row] = r.payload;
+                    cols.g.dev[row] = r.dev; cols.g.tid[row] = r.tid; cols.g.src[row] = r.src; cols.g.dst[row] = r.dst;
+                    cols.g.kind[row] = r.kind; cols.g.bwf[row] = r.bw_is_float;
+                    cols.g.line_start[row] = s0 + ls; cols.g.noff[row] = r.name_off; cols.g.nlen[row] = r.name_len;
+                }
+            } else {
+                NetRow r;
+                code = parse_net(line, n, cfg, &r);
+                if (code == E_OK) {
+                    cols.n.ts[row] = r.ts; cols.n.payload[row] = r.payload; cols.n.src[row] = r.src; cols.n.dst[row] = r.dst;
+                    cols.n.proto[row] = r.proto;
+                }
+            }
+        }
+        if (code != E_OK) report_error(err, row, code);
+    }
+}
+
+}  // namespace sofa

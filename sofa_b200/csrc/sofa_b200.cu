@@ -1,0 +1,649 @@
+// libsofa_b200.so: C ABI (include/sofa_b200.h) over the sm_100a kernels.
+// Single translation unit; CUDA runtime only (no torch, no thrust/cub).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/sofa_b200.h"
+#include "kernels_emit.cuh"
+#include "kernels_analyze.cuh"
+#include "synth.cuh"
+
+using namespace sofa;
+
+static thread_local std::string g_last_error;
+
+enum {
+    K_COUNT = 0, K_SCAN, K_PARSE, K_FLAGS, K_CSV_SIZE, K_CSV_WRITE, K_JSON_SIZE, K_JSON_WRITE, K_FILTER,
+    K_VIZ, K_ANALYZE, K_SORT, K_SYNTH, K_NKINDS
+};
+static const char* KERNEL_NAMES[K_NKINDS] = {
+    "count_lines", "scan", "parse", "row_flags", "csv_size", "csv_write", "json_size", "json_write", "filter",
+    "viz_dict", "analyze", "sort", "synth"};
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Source {
+    DevBuf text; uint64_t nbytes = 0, data_off = 0;
+    bool uploaded = false, parsed = false;
+    uint64_t n_rows = 0;
+    DevBuf cols[16];
+    IngestCfg cfg;
+    DevBuf mhz;
+    DevBuf mask; uint32_t mask_stride = 0; int nkw = 0;      // filter masks
+    DevBuf vizhash, viz_id; uint32_t viz_stride = 0; bool viz_ready = false;
+    DevBuf dict_hash, dict_off, dict_blob; int dict_n = 0;
+};
+
+struct TimedEvent { int kind; cudaEvent_t a, b; };
+
+struct sofa_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Source src[3];
+    DevBuf out[3]; uint64_t out_n[3] = {0, 0, 0};
+    DevBuf tiles, rowlen, blockoff, scratch, ftable, keys, rows;
+    unsigned long long* d_err = nullptr;        // [0] error slot, [1] counter, [2..9] filter counts, [10] misc
+    unsigned int* d_flags = nullptr;            // [0] cr flag, [1] row flags, [2] overflow, [3] count
+    uint64_t err_row = 0; int err_code = 0;
+    bool profiling = false;
+    std::vector<TimedEvent> events;
+    std::vector<cudaEvent_t> pool;
+    sofa_stats_t stats;
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            g_last_error = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return SOFA_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+#define FAIL(code, msg) do { g_last_error = (msg); return (code); } while (0)
+#define ENSURE(buf, n) do { if ((buf).ensure(n)) FAIL(SOFA_ERR_CUDA, "cudaMalloc failed (" #buf ")"); } while (0)
+
+static cudaEvent_t get_event(sofa_ctx* c) {
+    if (!c->pool.empty()) { cudaEvent_t e = c->pool.back(); c->pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct LaunchTimer {
+    sofa_ctx* c; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchTimer(sofa_ctx* ctx, int k) : c(ctx), kind(k) {
+        c->stats.launches[kind]++;
+        if (c->profiling) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~LaunchTimer() { if (c->profiling) { cudaEventRecord(b, c->stream); c->events.push_back({kind, a, b}); } }
+};
+#define LAUNCH(ctx, kind, ...) do { LaunchTimer lt_(ctx, kind); __VA_ARGS__; } while (0)
+
+static int drain_events(sofa_ctx* c) {
+    if (c->events.empty()) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& ev : c->events) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev.a, ev.b);
+        c->stats.ms[ev.kind] += ms;
+        c->pool.push_back(ev.a); c->pool.push_back(ev.b);
+    }
+    c->events.clear();
+    return 0;
+}
+
+static int check_kernel_error(sofa_ctx* c, const char* what) {
+    unsigned long long e = ~0ull;
+    CK(cudaMemcpyAsync(&e, c->d_err, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    if (e != ~0ull) {
+        c->err_row = e >> 8; c->err_code = (int)(e & 0xff);
+        char buf[160];
+        snprintf(buf, sizeof buf, "%s: record %llu: error %d", what, (unsigned long long)c->err_row, c->err_code);
+        g_last_error = buf;
+        return SOFA_ERR_ROW;
+    }
+    return 0;
+}
+static int reset_err(sofa_ctx* c) {
+    CK(cudaMemsetAsync(c->d_err, 0xff, 8, c->stream));
+    CK(cudaMemsetAsync(c->d_err + 1, 0, 8 * 15, c->stream));
+    CK(cudaMemsetAsync(c->d_flags, 0, 4 * 8, c->stream));
+    return 0;
+}
+
+// column slots
+enum { PC_TS = 0, PC_EVENT, PC_DUR, PC_PID, PC_TID, PC_LS, PC_PIECES };
+enum { GC_TS = 0, GC_DUR, GC_BW, GC_PAYLOAD, GC_DEV, GC_TID, GC_SRC, GC_DST, GC_KIND, GC_BWF, GC_LS, GC_NOFF, GC_NLEN };
+enum { NC_TS = 0, NC_PAYLOAD, NC_SRC, NC_DST, NC_PROTO };
+
+static AllCols all_cols(sofa_ctx* c) {
+    AllCols a;
+    Source& p = c->src[0]; Source& g = c->src[1]; Source& n = c->src[2];
+    a.p.ts = p.cols[PC_TS].as<double>(); a.p.event = p.cols[PC_EVENT].as<double>(); a.p.dur = p.cols[PC_DUR].as<double>();
+    a.p.pid = p.cols[PC_PID].as<int32_t>(); a.p.tid = p.cols[PC_TID].as<int32_t>();
+    a.p.line_start = p.cols[PC_LS].as<uint64_t>(); a.p.pieces = p.cols[PC_PIECES].as<uint16_t>();
+    a.g.ts = g.cols[GC_TS].as<double>(); a.g.dur = g.cols[GC_DUR].as<double>(); a.g.bw = g.cols[GC_BW].as<double>();
+    a.g.payload = g.cols[GC_PAYLOAD].as<int64_t>(); a.g.dev = g.cols[GC_DEV].as<int32_t>(); a.g.tid = g.cols[GC_TID].as<int32_t>();
+    a.g.src = g.cols[GC_SRC].as<int32_t>(); a.g.dst = g.cols[GC_DST].as<int32_t>(); a.g.kind = g.cols[GC_KIND].as<uint8_t>();
+    a.g.bwf = g.cols[GC_BWF].as<uint8_t>(); a.g.line_start = g.cols[GC_LS].as<uint64_t>();
+    a.g.noff = g.cols[GC_NOFF].as<uint16_t>(); a.g.nlen = g.cols[GC_NLEN].as<uint16_t>();
+    a.n.ts = n.cols[NC_TS].as<double>(); a.n.payload = n.cols[NC_PAYLOAD].as<int64_t>(); a.n.src = n.cols[NC_SRC].as<int64_t>();
+    a.n.dst = n.cols[NC_DST].as<int64_t>(); a.n.proto = n.cols[NC_PROTO].as<uint8_t>();
+    return a;
+}
+static SrcView make_view(sofa_ctx* c, int k, bool with_viz) {
+    SrcView v;
+    Source& s = c->src[k];
+    v.text = s.text.as<char>();
+    v.n_rows = s.n_rows;
+    v.c = all_cols(c);
+    v.viz_id = (with_viz && k == SRC_PERF && s.viz_ready) ? s.viz_id.as<int32_t>() : nullptr;
+    v.dict.n = s.dict_n; v.dict.hash = s.dict_hash.as<uint64_t>(); v.dict.off = s.dict_off.as<uint64_t>();
+    v.dict.blob = s.dict_blob.as<char>();
+    v.n_cudaproc = s.cfg.n_cudaproc;
+    return v;
+}
+
+static int alloc_cols(sofa_ctx* c, int k, uint64_t n) {
+    Source& s = c->src[k];
+    uint64_t m = n ? n : 1;
+    if (k == SRC_PERF) {
+        ENSURE(s.cols[PC_TS], m * 8); ENSURE(s.cols[PC_EVENT], m * 8); ENSURE(s.cols[PC_DUR], m * 8);
+        ENSURE(s.cols[PC_PID], m * 4); ENSURE(s.cols[PC_TID], m * 4); ENSURE(s.cols[PC_LS], m * 8);
+        ENSURE(s.cols[PC_PIECES], m * 12);
+    } else if (k == SRC_GPU) {
+        ENSURE(s.cols[GC_TS], m * 8); ENSURE(s.cols[GC_DUR], m * 8); ENSURE(s.cols[GC_BW], m * 8);
+        ENSURE(s.cols[GC_PAYLOAD], m * 8); ENSURE(s.cols[GC_DEV], m * 4); ENSURE(s.cols[GC_TID], m * 4);
+        ENSURE(s.cols[GC_SRC], m * 4); ENSURE(s.cols[GC_DST], m * 4); ENSURE(s.cols[GC_KIND], m);
+        ENSURE(s.cols[GC_BWF], m); ENSURE(s.cols[GC_LS], m * 8); ENSURE(s.cols[GC_NOFF], m * 2); ENSURE(s.cols[GC_NLEN], m * 2);
+    } else {
+        ENSURE(s.cols[NC_TS], m * 8); ENSURE(s.cols[NC_PAYLOAD], m * 8); ENSURE(s.cols[NC_SRC], m * 8);
+        ENSURE(s.cols[NC_DST], m * 8); ENSURE(s.cols[NC_PROTO], m);
+    }
+    return 0;
+}
+
+static inline uint64_t cdiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+extern "C" {
+
+int sofa_b200_abi_version(void) { return SOFA_B200_ABI_VERSION; }
+const char* sofa_b200_last_error(void) { return g_last_error.c_str(); }
+const char* sofa_b200_kernel_name(int kind) { return (kind >= 0 && kind < K_NKINDS) ? KERNEL_NAMES[kind] : ""; }
+
+int sofa_b200_error_row(sofa_ctx* c, uint64_t* row, int32_t* code) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    if (row) *row = c->err_row;
+    if (code) *code = c->err_code;
+    return 0;
+}
+
+int sofa_b200_create(sofa_ctx** out, int device) {
+    if (!out) FAIL(SOFA_ERR_ARG, "null out");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) FAIL(SOFA_ERR_CUDA, "no CUDA device: libsofa_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) FAIL(SOFA_ERR_ARG, "bad device index");
+    CK(cudaSetDevice(device));
+    sofa_ctx* c = new sofa_ctx();
+    c->device = device;
+    memset(&c->stats, 0, sizeof c->stats);
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->d_err, 8 * 16));
+    CK(cudaMalloc(&c->d_flags, 4 * 8));
+    // dynamic shared memory opt-in for the parse kernels
+    int maxsm = 0;
+    CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CK(cudaFuncSetAttribute(k_parse<SRC_PERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_parse<SRC_GPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_parse<SRC_NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    *out = c;
+    return 0;
+}
+
+int sofa_b200_destroy(sofa_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto& e : c->pool) cudaEventDestroy(e);
+    for (int k = 0; k < 3; k++) {
+        Source& s = c->src[k];
+        s.text.release(); s.mhz.release(); s.mask.release(); s.vizhash.release(); s.viz_id.release();
+        s.dict_hash.release(); s.dict_off.release(); s.dict_blob.release();
+        for (auto& b : s.cols) b.release();
+        c->out[k].release();
+    }
+    c->tiles.release(); c->rowlen.release(); c->blockoff.release(); c->scratch.release(); c->ftable.release();
+    c->keys.release(); c->rows.release();
+    cudaFree(c->d_err); cudaFree(c->d_flags);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+void* sofa_b200_host_alloc(uint64_t nbytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void sofa_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
+    if (!c || k < 0 || k > 2 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload: bad argument");
+    if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload: data_off beyond the text");
+    CK(cudaSetDevice(c->device));
+    Source& s = c->src[k];
+    ENSURE(s.text, nbytes + 64);
+    if (nbytes) CK(cudaMemcpyAsync(s.text.p, text, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(s.text.as<char>() + nbytes, '\n', 64, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += nbytes;
+    s.nbytes = nbytes; s.data_off = data_off; s.uploaded = true; s.parsed = false; s.viz_ready = false; s.n_rows = 0;
+    s.mask_stride = 0; s.nkw = 0;
+    return 0;
+}
+
+static uint32_t pick_tile_bytes(int k) { return k == SRC_NET ? 16384u : 24576u; }
+
+int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t* n_rows) {
+    if (!c || k < 0 || k > 2 || !p) FAIL(SOFA_ERR_ARG, "parse: bad argument");
+    Source& s = c->src[k];
+    if (!s.uploaded) FAIL(SOFA_ERR_STATE, "parse: nothing uploaded for this source");
+    CK(cudaSetDevice(c->device));
+    IngestCfg cfg;
+    cfg.time_base = p->time_base; cfg.t_offset = p->t_offset; cfg.absolute_timestamp = p->absolute_timestamp;
+    cfg.perf_has_cycles = p->perf_has_cycles; cfg.n_mhz = p->n_mhz > 0 ? p->n_mhz : 1;
+    cfg.ts_rescale = p->ts_rescale; cfg.dt_rescale = p->dt_rescale; cfg.payload_unit = p->payload_unit;
+    cfg.n_cudaproc = p->n_cudaproc;
+    cfg.idx_start = p->idx[0]; cfg.idx_dur = p->idx[1]; cfg.idx_size = p->idx[2]; cfg.idx_thr = p->idx[3];
+    cfg.idx_ctx = p->idx[4]; cfg.idx_stream = p->idx[5]; cfg.idx_name = p->idx[6]; cfg.idx_srcctx = p->idx[7];
+    cfg.idx_dstctx = p->idx[8];
+    if (k == SRC_GPU && (cfg.idx_start < 0 || cfg.idx_dur < 0 || cfg.idx_name < 0))
+        FAIL(SOFA_ERR_ARG, "parse: gpu trace needs Start, Duration and Name columns");
+    ENSURE(s.mhz, 16 * (size_t)cfg.n_mhz + 16);
+    if (p->n_mhz > 0 && p->mhz_xp && p->mhz_fp) {
+        CK(cudaMemcpyAsync(s.mhz.p, p->mhz_xp, 8 * (size_t)cfg.n_mhz, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.mhz.as<double>() + cfg.n_mhz, p->mhz_fp, 8 * (size_t)cfg.n_mhz, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        double d[2] = {0.0, 3000.0};
+        CK(cudaMemcpyAsync(s.mhz.p, &d[0], 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.mhz.as<double>() + 1, &d[1], 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    cfg.mhz_xp = s.mhz.as<double>(); cfg.mhz_fp = s.mhz.as<double>() + cfg.n_mhz;
+    s.cfg = cfg;
+    s.parsed = false; s.viz_ready = false; s.mask_stride = 0;
+    uint64_t begin = s.data_off, end = s.nbytes;
+    if (end <= begin) { s.n_rows = 0; s.parsed = true; if (n_rows) *n_rows = 0; return 0; }
+    uint32_t tile = pick_tile_bytes(k);
+    uint64_t ntiles = cdiv(end - begin, tile);
+    if (ntiles > 0x7fffffffull) FAIL(SOFA_ERR_ARG, "parse: source too large for one call");
+    ENSURE(c->tiles, (ntiles + 2) * 8);
+    if (reset_err(c)) return SOFA_ERR_CUDA;
+    LAUNCH(c, K_COUNT, (k_count_lines<<<(unsigned)ntiles, PARSE_TPB, 0, c->stream>>>(
+        s.text.as<char>(), begin, end, tile, c->tiles.as<uint64_t>(), c->d_flags)));
+    LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(c->tiles.as<uint64_t>(), ntiles)));
+    uint64_t total = 0; unsigned int cr = 0;
+    CK(cudaMemcpyAsync(&total, c->tiles.as<uint64_t>() + ntiles, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&cr, c->d_flags, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    if (cr) { c->err_row = 0; c->err_code = E_CR; FAIL(SOFA_ERR_ROW, "parse: carriage return in trace text (not supported)"); }
+    if (alloc_cols(c, k, total)) return SOFA_ERR_CUDA;
+    s.n_rows = total;
+    uint32_t max_lines = tile / 8;
+    size_t smem = (((size_t)tile + OVERLAP_BYTES + 48) & ~(size_t)15) + (size_t)max_lines * 4;
+    AllCols cols = all_cols(c);
+    if (k == SRC_PERF)
+        LAUNCH(c, K_PARSE, (k_parse<SRC_PERF><<<(unsigned)ntiles, PARSE_TPB, smem, c->stream>>>(
+            s.text.as<char>(), begin, end, tile, max_lines, c->tiles.as<uint64_t>(), cfg, cols, c->d_err)));
+    else if (k == SRC_GPU)
+        LAUNCH(c, K_PARSE, (k_parse<SRC_GPU><<<(unsigned)ntiles, PARSE_TPB, smem, c->stream>>>(
+            s.text.as<char>(), begin, end, tile, max_lines, c->tiles.as<uint64_t>(), cfg, cols, c->d_err)));
+    else
+        LAUNCH(c, K_PARSE, (k_parse<SRC_NET><<<(unsigned)ntiles, PARSE_TPB, smem, c->stream>>>(
+            s.text.as<char>(), begin, end, tile, max_lines, c->tiles.as<uint64_t>(), cfg, cols, c->d_err)));
+    int r = check_kernel_error(c, "parse");
+    if (r) return r;
+    s.parsed = true;
+    if (n_rows) *n_rows = total;
+    return 0;
+}
+
+static int need_parsed(sofa_ctx* c, int k) {
+    if (!c || k < 0 || k > 2) FAIL(SOFA_ERR_ARG, "bad source");
+    if (!c->src[k].parsed) FAIL(SOFA_ERR_STATE, "source not parsed");
+    CK(cudaSetDevice(c->device));
+    return 0;
+}
+
+int sofa_b200_row_flags(sofa_ctx* c, int k, uint32_t stride, uint32_t* flags) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (stride == 0 || !flags) FAIL(SOFA_ERR_ARG, "row_flags: bad argument");
+    Source& s = c->src[k];
+    *flags = 0;
+    if (k == SRC_PERF || s.n_rows == 0) return 0;
+    uint64_t ncand = cdiv(s.n_rows, stride);
+    CK(cudaMemsetAsync(c->d_flags + 1, 0, 4, c->stream));
+    SrcView v = make_view(c, k, false);
+    if (k == SRC_GPU) LAUNCH(c, K_FLAGS, (k_row_flags<SRC_GPU><<<(unsigned)cdiv(ncand, 256), 256, 0, c->stream>>>(v, ncand, stride, c->d_flags + 1)));
+    else LAUNCH(c, K_FLAGS, (k_row_flags<SRC_NET><<<(unsigned)cdiv(ncand, 256), 256, 0, c->stream>>>(v, ncand, stride, c->d_flags + 1)));
+    CK(cudaMemcpyAsync(flags, c->d_flags + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int fmask_for(sofa_ctx* c, int k, uint32_t stride, uint32_t* fmask) {
+    if (k == SRC_PERF) { *fmask = 0x7; return 0; }
+    uint32_t fl = 0;
+    int r = sofa_b200_row_flags(c, k, stride, &fl);
+    if (r) return r;
+    if (k == SRC_GPU) { *fmask = 0x5u | ((fl & 1) ? 0x40u : 0u); return 0; }
+    if (fl & 2) {
+        if (!(fl & 4)) FAIL(SOFA_ERR_ROW, "every selected packet row is empty: the reference raises (0 columns)");
+        *fmask = 0x17ff;
+    } else *fmask = 0x45;
+    return 0;
+}
+
+}  // extern "C"
+
+template <int FMT>
+static int emit_common(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, int bit, uint32_t fmask,
+                       int outslot, uint64_t* nbytes, uint64_t* nrec) {
+    Source& s = c->src[k];
+    uint64_t ncand = cdiv(s.n_rows, stride);
+    c->out_n[outslot] = 0;
+    if (nbytes) *nbytes = 0;
+    if (nrec) *nrec = 0;
+    if (ncand == 0) return 0;
+    uint64_t nblocks = cdiv(ncand, EMIT_TPB);
+    ENSURE(c->rowlen, ncand * 4);
+    ENSURE(c->blockoff, (nblocks + 2) * 8);
+    if (reset_err(c)) return SOFA_ERR_CUDA;
+    SrcView v = make_view(c, k, true);
+    EmitArgs a;
+    a.ncand = ncand; a.stride = stride; a.fmask = fmask; a.mask = mask; a.bit = bit;
+    a.rowlen = c->rowlen.as<uint32_t>(); a.blockoff = c->blockoff.as<uint64_t>(); a.out = nullptr;
+    a.err = c->d_err; a.count = c->d_err + 1;
+    int ks = FMT == FMT_CSV ? K_CSV_SIZE : K_JSON_SIZE, kw = FMT == FMT_CSV ? K_CSV_WRITE : K_JSON_WRITE;
+    unsigned g = (unsigned)nblocks;
+    if (k == SRC_PERF) LAUNCH(c, ks, (k_emit_size<SRC_PERF, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
+    else if (k == SRC_GPU) LAUNCH(c, ks, (k_emit_size<SRC_GPU, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
+    else LAUNCH(c, ks, (k_emit_size<SRC_NET, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
+    LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(c->blockoff.as<uint64_t>(), nblocks)));
+    uint64_t total = 0; unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&total, c->blockoff.as<uint64_t>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&cnt, c->d_err + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    int r = check_kernel_error(c, FMT == FMT_CSV ? "emit_csv" : "emit_json");
+    if (r) return r;
+    ENSURE(c->out[outslot], total + 64);
+    a.out = c->out[outslot].as<char>();
+    if (total) {
+        if (k == SRC_PERF) LAUNCH(c, kw, (k_emit_write<SRC_PERF, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
+        else if (k == SRC_GPU) LAUNCH(c, kw, (k_emit_write<SRC_GPU, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
+        else LAUNCH(c, kw, (k_emit_write<SRC_NET, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+    }
+    c->out_n[outslot] = total;
+    if (nbytes) *nbytes = total;
+    if (nrec) *nrec = cnt;
+    return 0;
+}
+
+extern "C" {
+
+int sofa_b200_emit_csv(sofa_ctx* c, int k, uint32_t stride, uint64_t* nbytes) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (stride == 0) FAIL(SOFA_ERR_ARG, "emit_csv: stride must be >= 1");
+    uint32_t fmask = 0;
+    r = fmask_for(c, k, stride, &fmask); if (r) return r;
+    return emit_common<FMT_CSV>(c, k, stride, nullptr, 0, fmask, 0, nbytes, nullptr);
+}
+
+int sofa_b200_emit_json(sofa_ctx* c, int k, uint32_t stride, int32_t filter_idx, uint64_t* nbytes, uint64_t* nrec) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (stride == 0) FAIL(SOFA_ERR_ARG, "emit_json: stride must be >= 1");
+    Source& s = c->src[k];
+    if (k == SRC_PERF && !(s.viz_ready && s.viz_stride == stride))
+        FAIL(SOFA_ERR_STATE, "emit_json(perf): call viz_mangled + set_demangled for this stride first");
+    const uint8_t* mask = nullptr;
+    if (filter_idx >= 0) {
+        if (filter_idx >= s.nkw || s.mask_stride != stride) FAIL(SOFA_ERR_STATE, "emit_json: filter not set for this stride");
+        mask = s.mask.as<uint8_t>();
+    }
+    uint32_t fmask = 0;
+    r = fmask_for(c, k, stride, &fmask); if (r) return r;
+    uint64_t nb = 0, nr = 0;
+    r = emit_common<FMT_JSON>(c, k, stride, mask, filter_idx >= 0 ? filter_idx : 0, fmask, 1, &nb, &nr);
+    if (r) return r;
+    if (nbytes) *nbytes = nb >= 2 ? nb - 2 : 0;       // the leading ", " is dropped by fetch
+    if (nrec) *nrec = nr;
+    return 0;
+}
+
+int sofa_b200_fetch(sofa_ctx* c, int which, void* host_out, uint64_t cap) {
+    if (!c || which < 0 || which > 2 || !host_out) FAIL(SOFA_ERR_ARG, "fetch: bad argument");
+    CK(cudaSetDevice(c->device));
+    uint64_t n = c->out_n[which], skip = 0;
+    if (which == 1) { skip = n >= 2 ? 2 : n; n -= skip; }
+    if (cap < n) FAIL(SOFA_ERR_CAP, "fetch: buffer too small");
+    if (n) {
+        CK(cudaMemcpyAsync(host_out, c->out[which].as<char>() + skip, n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->stats.d2h_bytes += n;
+    }
+    return 0;
+}
+
+int sofa_b200_set_filters(sofa_ctx* c, int k, uint32_t stride, int32_t nkw, const char* const* kws, uint64_t* counts) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (stride == 0 || nkw < 0 || nkw > 8 || (nkw && !kws)) FAIL(SOFA_ERR_ARG, "set_filters: 0..8 keywords");
+    Source& s = c->src[k];
+    if (k == SRC_PERF && !(s.viz_ready && s.viz_stride == stride))
+        FAIL(SOFA_ERR_STATE, "set_filters(perf): call viz_mangled + set_demangled for this stride first");
+    FilterTable ft;
+    memset(&ft, 0, sizeof ft);
+    ft.nk = nkw;
+    for (int i = 0; i < nkw; i++) {
+        size_t L = strlen(kws[i]);
+        if (L == 0 || L > 32) FAIL(SOFA_ERR_ARG, "set_filters: keyword length must be 1..32 bytes");
+        for (size_t j = 0; j < L; j++) ft.mask[i][(unsigned char)kws[i][j]] |= 1u << j;
+        ft.final_bit[i] = 1u << (L - 1);
+    }
+    uint64_t ncand = cdiv(s.n_rows, stride);
+    ENSURE(c->ftable, sizeof(FilterTable));
+    ENSURE(s.mask, ncand + 16);
+    if (reset_err(c)) return SOFA_ERR_CUDA;
+    CK(cudaMemcpyAsync(c->ftable.p, &ft, sizeof ft, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (ncand) {
+        SrcView v = make_view(c, k, true);
+        unsigned g = (unsigned)cdiv(ncand, 256);
+        const FilterTable* dft = c->ftable.as<FilterTable>();
+        if (k == SRC_PERF) LAUNCH(c, K_FILTER, (k_filter<SRC_PERF><<<g, 256, 0, c->stream>>>(v, ncand, stride, dft, s.mask.as<uint8_t>(), c->d_err + 2)));
+        else if (k == SRC_GPU) LAUNCH(c, K_FILTER, (k_filter<SRC_GPU><<<g, 256, 0, c->stream>>>(v, ncand, stride, dft, s.mask.as<uint8_t>(), c->d_err + 2)));
+        else LAUNCH(c, K_FILTER, (k_filter<SRC_NET><<<g, 256, 0, c->stream>>>(v, ncand, stride, dft, s.mask.as<uint8_t>(), c->d_err + 2)));
+    }
+    unsigned long long cn[8] = {0};
+    CK(cudaMemcpyAsync(cn, c->d_err + 2, 64, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    if (counts) for (int i = 0; i < nkw; i++) counts[i] = cn[i];
+    s.mask_stride = stride; s.nkw = nkw;
+    return 0;
+}
+
+int sofa_b200_viz_mangled(sofa_ctx* c, uint32_t stride, uint64_t* nbytes, uint32_t* n_names) {
+    int r = need_parsed(c, SRC_PERF); if (r) return r;
+    if (stride == 0) FAIL(SOFA_ERR_ARG, "viz_mangled: stride must be >= 1");
+    Source& s = c->src[SRC_PERF];
+    uint64_t ncand = cdiv(s.n_rows, stride);
+    s.viz_ready = false; s.viz_stride = stride;
+    c->out_n[2] = 0;
+    if (nbytes) *nbytes = 0;
+    if (n_names) *n_names = 0;
+    ENSURE(s.vizhash, (ncand + 1) * 8);
+    ENSURE(s.viz_id, (ncand + 1) * 4);
+    if (ncand == 0) return 0;
+    SrcView v = make_view(c, SRC_PERF, false);
+    for (uint64_t cap = 1ull << 16;; cap <<= 2) {
+        if (cap > (1ull << 30)) FAIL(SOFA_ERR_CUDA, "viz dictionary overflow");
+        ENSURE(c->keys, cap * 8); ENSURE(c->rows, cap * 8);
+        if (reset_err(c)) return SOFA_ERR_CUDA;
+        CK(cudaMemsetAsync(c->keys.p, 0, cap * 8, c->stream));
+        CK(cudaMemsetAsync(c->rows.p, 0xff, cap * 8, c->stream));
+        LAUNCH(c, K_VIZ, (k_viz_hash<<<(unsigned)cdiv(ncand, 256), 256, 0, c->stream>>>(
+            v, ncand, stride, s.vizhash.as<uint64_t>(), c->keys.as<unsigned long long>(), c->rows.as<unsigned long long>(),
+            cap - 1, c->d_flags + 2)));
+        unsigned int ovf = 0;
+        CK(cudaMemcpyAsync(&ovf, c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+        if (!ovf) {
+            LAUNCH(c, K_VIZ, (k_dict_len<<<(unsigned)cdiv(cap, 256), 256, 0, c->stream>>>(
+                v, c->keys.as<unsigned long long>(), c->rows.as<unsigned long long>(), cap, c->d_err + 1, c->d_flags + 3)));
+            unsigned long long total = 0; unsigned int n = 0;
+            CK(cudaMemcpyAsync(&total, c->d_err + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(&n, c->d_flags + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            // occupancy above 50% makes probing slow and overflow likely next time: grow
+            if ((uint64_t)n * 2 > cap) continue;
+            ENSURE(c->out[2], total + 64);
+            CK(cudaMemsetAsync(c->d_err + 1, 0, 8, c->stream));
+            if (total)
+                LAUNCH(c, K_VIZ, (k_dict_write<<<(unsigned)cdiv(cap, 256), 256, 0, c->stream>>>(
+                    v, c->keys.as<unsigned long long>(), c->rows.as<unsigned long long>(), cap, c->d_err + 1, c->out[2].as<char>())));
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaGetLastError());
+            c->out_n[2] = total;
+            if (nbytes) *nbytes = total;
+            if (n_names) *n_names = n;
+            return 0;
+        }
+    }
+}
+
+int sofa_b200_set_demangled(sofa_ctx* c, uint32_t n, const char* mangled, const uint64_t* moff,
+                            const char* demangled, const uint64_t* doff) {
+    int r = need_parsed(c, SRC_PERF); if (r) return r;
+    Source& s = c->src[SRC_PERF];
+    if (s.viz_stride == 0) FAIL(SOFA_ERR_STATE, "set_demangled: call viz_mangled first");
+    if (n && (!mangled || !moff || !demangled || !doff)) FAIL(SOFA_ERR_ARG, "set_demangled: null table");
+    std::vector<std::pair<uint64_t, uint32_t>> order(n);
+    for (uint32_t i = 0; i < n; i++) {
+        HashSink h;
+        for (uint64_t j = moff[i]; j < moff[i + 1]; j++) h.put(mangled[j]);
+        order[i] = {h.h ? h.h : 1, i};
+    }
+    std::sort(order.begin(), order.end());
+    std::vector<uint64_t> hashes(n + 1), offs(n + 2);
+    std::string blob;
+    for (uint32_t i = 0; i < n; i++) {
+        if (i && order[i].first == order[i - 1].first) FAIL(SOFA_ERR_ARG, "set_demangled: duplicate or colliding names");
+        hashes[i] = order[i].first;
+        offs[i] = blob.size();
+        uint32_t src = order[i].second;
+        blob.append(demangled + doff[src], demangled + doff[src + 1]);
+    }
+    offs[n] = blob.size();
+    ENSURE(s.dict_hash, (n + 1) * 8); ENSURE(s.dict_off, (n + 2) * 8); ENSURE(s.dict_blob, blob.size() + 16);
+    if (n) {
+        CK(cudaMemcpyAsync(s.dict_hash.p, hashes.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.dict_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaMemcpyAsync(s.dict_off.p, offs.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    s.dict_n = (int)n;
+    uint64_t ncand = cdiv(s.n_rows, s.viz_stride);
+    if (ncand) {
+        if (reset_err(c)) return SOFA_ERR_CUDA;
+        DictView d{(int)n, s.dict_hash.as<uint64_t>(), s.dict_off.as<uint64_t>(), s.dict_blob.as<char>()};
+        LAUNCH(c, K_VIZ, (k_viz_resolve<<<(unsigned)cdiv(ncand, 256), 256, 0, c->stream>>>(
+            s.vizhash.as<uint64_t>(), ncand, d, s.viz_id.as<int32_t>(), c->d_err)));
+        r = check_kernel_error(c, "set_demangled (a mangled viz name has no demangled entry)");
+        if (r) return r;
+    }
+    s.viz_ready = true;
+    return 0;
+}
+
+int sofa_b200_get_column(sofa_ctx* c, int k, int col, void* host_out, uint64_t cap_bytes) {
+    int r = need_parsed(c, k); if (r) return r;
+    Source& s = c->src[k];
+    int slot = -1; size_t w = 0;
+    if (k == SRC_PERF) {
+        switch (col) { case 0: slot = PC_TS; w = 8; break; case 1: slot = PC_EVENT; w = 8; break; case 2: slot = PC_DUR; w = 8; break;
+                       case 9: slot = PC_PID; w = 4; break; case 10: slot = PC_TID; w = 4; break; }
+    } else if (k == SRC_GPU) {
+        switch (col) { case 0: slot = GC_TS; w = 8; break; case 2: slot = GC_DUR; w = 8; break; case 6: slot = GC_BW; w = 8; break;
+                       case 5: slot = GC_PAYLOAD; w = 8; break; case 3: slot = GC_DEV; w = 4; break; case 10: slot = GC_TID; w = 4; break;
+                       case 7: slot = GC_SRC; w = 4; break; case 8: slot = GC_DST; w = 4; break; case 4: slot = GC_KIND; w = 1; break; }
+    } else {
+        switch (col) { case 0: slot = NC_TS; w = 8; break; case 5: slot = NC_PAYLOAD; w = 8; break; case 7: slot = NC_SRC; w = 8; break;
+                       case 8: slot = NC_DST; w = 8; break; case 4: slot = NC_PROTO; w = 1; break; }
+    }
+    if (slot < 0) FAIL(SOFA_ERR_ARG, "get_column: no such stored column for this source");
+    uint64_t nb = s.n_rows * w;
+    if (cap_bytes < nb) FAIL(SOFA_ERR_CAP, "get_column: buffer too small");
+    if (nb) { CK(cudaMemcpyAsync(host_out, s.cols[slot].p, nb, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return 0;
+}
+
+int sofa_b200_set_profiling(sofa_ctx* c, int on) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (drain_events(c)) return SOFA_ERR_CUDA;
+    c->profiling = on != 0;
+    return 0;
+}
+int sofa_b200_get_stats(sofa_ctx* c, sofa_stats_t* out) {
+    if (!c || !out) FAIL(SOFA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    if (drain_events(c)) return SOFA_ERR_CUDA;
+    *out = c->stats;
+    return 0;
+}
+int sofa_b200_reset_stats(sofa_ctx* c) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (drain_events(c)) return SOFA_ERR_CUDA;
+    memset(&c->stats, 0, sizeof c->stats);
+    return 0;
+}
+
+int sofa_b200_text_fetch(sofa_ctx* c, int k, void* host_out, uint64_t cap) {
+    if (!c || k < 0 || k > 2 || !host_out) FAIL(SOFA_ERR_ARG, "text_fetch: bad argument");
+    Source& s = c->src[k];
+    if (!s.uploaded) FAIL(SOFA_ERR_STATE, "text_fetch: no text");
+    if (cap < s.nbytes) FAIL(SOFA_ERR_CAP, "text_fetch: buffer too small");
+    CK(cudaSetDevice(c->device));
+    if (s.nbytes) { CK(cudaMemcpyAsync(host_out, s.text.p, s.nbytes, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return 0;
+}
+
+#include "capi_analyze.inc"
+#include "capi_synth.inc"
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""CudaEngine: the object sofa_preprocess / sofa_analyze drive.  A thin veneer over the
+C ABI: host buffers in, numpy byte arrays out.  No record-level work happens in Python."""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+from .hostlogic import ROW_ERRORS
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'd memory exposed as a numpy uint8 array."""
+    def __init__(self, lib, nbytes):
+        self.lib = lib
+        self.ptr = lib.sofa_b200_host_alloc(ctypes.c_uint64(max(1, nbytes)))
+        if not self.ptr:
+            raise MemoryError("cudaHostAlloc(%d) failed" % nbytes)
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * max(1, nbytes)).from_address(self.ptr))[:nbytes]
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.sofa_b200_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class CudaEngine:
+    def __init__(self, device=0):
+        self.lib = L.load_lib()
+        self.ctx = ctypes.c_void_p()
+        rc = self.lib.sofa_b200_create(ctypes.byref(self.ctx), int(device))
+        if rc != 0:
+            self.ctx = None
+            raise L.SofaB200Error(rc, self.lib.sofa_b200_last_error().decode())
+        self._keep = []
+
+    def close(self):
+        if self.ctx:
+            self.lib.sofa_b200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = self.lib.sofa_b200_last_error().decode()
+        if rc == L.SOFA_ERR_ROW:
+            row = ctypes.c_uint64()
+            code = ctypes.c_int32()
+            self.lib.sofa_b200_error_row(self.ctx, ctypes.byref(row), ctypes.byref(code))
+            msg += " (%s)" % ROW_ERRORS.get(code.value, "?")
+            raise L.SofaB200Error(rc, msg, row.value, code.value)
+        raise L.SofaB200Error(rc, msg)
+
+    # ---- ingest
+    @staticmethod
+    def _ptr(buf):
+        if isinstance(buf, np.ndarray):
+            return buf.ctypes.data, buf.nbytes, buf
+        if isinstance(buf, (bytes, bytearray)):
+            a = np.frombuffer(buf, dtype=np.uint8)
+            return a.ctypes.data, a.nbytes, a
+        a = np.frombuffer(memoryview(buf), dtype=np.uint8)
+        return a.ctypes.data, a.nbytes, a
+
+    def upload(self, kind, text, data_off=0):
+        ptr, n, keep = self._ptr(text)
+        self._check(self.lib.sofa_b200_upload(self.ctx, kind, ctypes.c_void_p(ptr), n, data_off))
+
+    def make_params(self, p):
+        ip = L.IngestParams()
+        ip.time_base, ip.t_offset = p['time_base'], p['t_offset']
+        ip.absolute_timestamp, ip.perf_has_cycles = p['absolute_timestamp'], p['perf_has_cycles']
+        xp = np.ascontiguousarray(p['mhz_xp'], dtype=np.float64)
+        fp = np.ascontiguousarray(p['mhz_fp'], dtype=np.float64)
+        self._keep = [xp, fp]
+        ip.n_mhz, ip.mhz_xp, ip.mhz_fp = len(xp), xp.ctypes.data, fp.ctypes.data
+        ip.n_cudaproc = p['n_cudaproc']
+        ip.ts_rescale, ip.dt_rescale, ip.payload_unit = p['ts_rescale'], p['dt_rescale'], p['payload_unit']
+        for i in range(9):
+            ip.idx[i] = p['idx'][i]
+        return ip
+
+    def parse(self, kind, params):
+        ip = params if isinstance(params, L.IngestParams) else self.make_params(params)
+        n = ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_parse(self.ctx, kind, ctypes.byref(ip), ctypes.byref(n)))
+        return n.value
+
+    def load(self, kind, text, params, data_off=0):
+        self.upload(kind, text, data_off)
+        n = self.parse(kind, params)
+        return n, self.row_flags(kind, 1)
+
+    def row_flags(self, kind, stride):
+        f = ctypes.c_uint32()
+        self._check(self.lib.sofa_b200_row_flags(self.ctx, kind, stride, ctypes.byref(f)))
+        return f.value
+
+    # ---- outputs
+    def _fetch(self, which, n, out=None):
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        elif out.nbytes < n:
+            raise ValueError("output buffer too small")
+        self._check(self.lib.sofa_b200_fetch(self.ctx, which, ctypes.c_void_p(out.ctypes.data), out.nbytes))
+        return out[:n]
+
+    def csv_device(self, kind, stride):
+        n = ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_emit_csv(self.ctx, kind, stride, ctypes.byref(n)))
+        return n.value
+
+    def csv(self, kind, stride, out=None):
+        return self._fetch(0, self.csv_device(kind, stride), out)
+
+    def json_device(self, kind, stride, filt):
+        n = ctypes.c_uint64()
+        nrec = ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_emit_json(self.ctx, kind, stride, filt, ctypes.byref(n), ctypes.byref(nrec)))
+        return n.value, nrec.value
+
+    def json(self, kind, stride, filt, out=None):
+        n, nrec = self.json_device(kind, stride, filt)
+        return self._fetch(1, n, out), nrec
+
+    def set_filters(self, kind, stride, kws):
+        arr = (ctypes.c_char_p * max(1, len(kws)))(*[k.encode() if isinstance(k, str) else k for k in kws])
+        counts = (ctypes.c_uint64 * 8)()
+        self._check(self.lib.sofa_b200_set_filters(self.ctx, kind, stride, len(kws), arr, counts))
+        return [counts[i] for i in range(len(kws))]
+
+    def viz_mangled(self, stride):
+        n = ctypes.c_uint64()
+        cnt = ctypes.c_uint32()
+        self._check(self.lib.sofa_b200_viz_mangled(self.ctx, stride, ctypes.byref(n), ctypes.byref(cnt)))
+        if n.value == 0:
+            return []
+        raw = self._fetch(2, n.value).tobytes()
+        names = raw.decode().split('\n')[:-1]
+        assert len(names) == cnt.value
+        return names
+
+    def set_demangled(self, pairs):
+        mb = b"".join(m.encode() for m, _ in pairs)
+        db = b"".join(d.encode() for _, d in pairs)
+        moff = (ctypes.c_uint64 * (len(pairs) + 1))()
+        doff = (ctypes.c_uint64 * (len(pairs) + 1))()
+        for i, (m, d) in enumerate(pairs):
+            moff[i + 1] = moff[i] + len(m.encode())
+            doff[i + 1] = doff[i] + len(d.encode())
+        self._check(self.lib.sofa_b200_set_demangled(self.ctx, len(pairs), mb, moff, db, doff))
+
+    _COLTYPES = {0: {0: 'f8', 1: 'f8', 2: 'f8', 9: 'i4', 10: 'i4'},
+                 1: {0: 'f8', 2: 'f8', 6: 'f8', 5: 'i8', 3: 'i4', 10: 'i4', 7: 'i4', 8: 'i4', 4: 'u1'},
+                 2: {0: 'f8', 5: 'i8', 7: 'i8', 8: 'i8', 4: 'u1'}}
+
+    def column(self, kind, col, n_rows):
+        dt = np.dtype(self._COLTYPES[kind][col])
+        out = np.empty(n_rows, dtype=dt)
+        self._check(self.lib.sofa_b200_get_column(self.ctx, kind, col, ctypes.c_void_p(out.ctypes.data), out.nbytes))
+        return out
+
+    # ---- analyze
+    def gpu_profile(self):
+        gp = L.GpuProfile()
+        self._check(self.lib.sofa_b200_gpu_profile(self.ctx, ctypes.byref(gp)))
+        return gp
+
+    def top_k(self, kind, k):
+        sums = (ctypes.c_double * max(1, k))()
+        n = ctypes.c_uint64()
+        cnt = ctypes.c_uint32()
+        self._check(self.lib.sofa_b200_top_k(self.ctx, kind, k, sums, ctypes.byref(n), ctypes.byref(cnt)))
+        names = self._fetch(2, n.value).tobytes().decode().split('\x00')[:-1] if n.value else []
+        return list(zip(names, [sums[i] for i in range(cnt.value)]))
+
+    def cpu_profile(self, k):
+        total = ctypes.c_double()
+        rows = (ctypes.c_uint64 * max(1, k))()
+        cnt = ctypes.c_uint32()
+        self._check(self.lib.sofa_b200_cpu_profile(self.ctx, k, ctypes.byref(total), rows, ctypes.byref(cnt)))
+        return total.value, [rows[i] for i in range(cnt.value)]
+
+    # ---- stats / synth
+    def set_profiling(self, on):
+        self._check(self.lib.sofa_b200_set_profiling(self.ctx, 1 if on else 0))
+
+    def reset_stats(self):
+        self._check(self.lib.sofa_b200_reset_stats(self.ctx))
+
+    def stats(self):
+        st = L.Stats()
+        self._check(self.lib.sofa_b200_get_stats(self.ctx, ctypes.byref(st)))
+        out = {}
+        for i in range(32):
+            nm = self.lib.sofa_b200_kernel_name(i).decode()
+            if nm and st.launches[i]:
+                out[nm] = (int(st.launches[i]), float(st.ms[i]))
+        return out, int(st.h2d_bytes), int(st.d2h_bytes)
+
+    def synth(self, kind, seed, n_rows, variant=0):
+        n = ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_synth(self.ctx, kind, seed, n_rows, variant, ctypes.byref(n)))
+        return n.value
+
+    def text_fetch(self, kind, nbytes, out=None):
+        if out is None:
+            out = np.empty(nbytes, dtype=np.uint8)
+        self._check(self.lib.sofa_b200_text_fetch(self.ctx, kind, ctypes.c_void_p(out.ctypes.data), out.nbytes))
+        return out[:nbytes]
+
+    def pinned(self, nbytes):
+        return PinnedBuffer(self.lib, nbytes)

@@ -1,0 +1,114 @@
+"""GPU parity: the product path (sofa_preprocess -> ctypes -> libsofa_b200.so -> sm_100a
+kernels) against (1) the reference's golden files, (2) the CPU oracle on larger seeded
+logdirs, (3) column-level bit equality."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import golden_cases, golden_bytes, build_case_logdir
+from sofa_b200 import synth
+from sofa_b200.sofa_config import default_report_config
+from sofa_b200.sofa_preprocess import sofa_preprocess, demangle
+from oracle import sofa_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _diff(name, fn, got, want):
+    if got == want:
+        return
+    n = min(len(got), len(want))
+    i = next((k for k in range(n) if got[k] != want[k]), n)
+    raise AssertionError("%s/%s differs at byte %d (len %d vs %d): got %r want %r" % (
+        name, fn, i, len(got), len(want), got[max(0, i - 80):i + 40], want[max(0, i - 80):i + 40]))
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_cuda_path_reproduces_reference_files(name, tmp_path):
+    case, logdir = build_case_logdir(name, tmp_path)
+    ov = dict(case["cfg"])
+    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None))
+    for k, v in ov.items():
+        setattr(cfg, k, v)
+    sofa_preprocess(cfg)
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+        want = golden_bytes(name, fn)
+        if want is None:
+            assert not os.path.isfile(logdir + fn)
+            continue
+        with open(logdir + fn, "rb") as f:
+            _diff(name, fn, f.read(), want)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=101, n_perf=30000, n_gpu=20000, n_net=10000, non_ip_pct=1),
+    dict(seed=102, n_perf=25000, cpu_col=True, n_gpu=15000, units="ms_us_KB", p2p_cols=True, n_net=5000, non_ip_pct=0),
+])
+@pytest.mark.parametrize("ratio", [1, 7])
+def test_cuda_path_matches_oracle_on_larger_logs(kw, ratio, tmp_path):
+    a = os.path.join(str(tmp_path), "gpu") + "/"
+    b = os.path.join(str(tmp_path), "cpu") + "/"
+    for d in (a, b):
+        synth.make_logdir(d, **kw)
+    cfg = default_report_config(a, cpu_filters="idle:black,tensorflow:orange")
+    cfg.plot_ratio = ratio
+    sofa_preprocess(cfg)
+    ocfg = orc.OracleConfig(b, plot_ratio=ratio, cpu_filters="idle:black,tensorflow:orange")
+    orc.preprocess(ocfg, demangle=demangle)
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+        with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
+            _diff("seed%d" % kw["seed"], fn, f.read(), g.read())
+
+
+def test_columns_bit_exact(tmp_path):
+    from sofa_b200.engine import CudaEngine
+    from sofa_b200 import hostlogic as hl
+    logdir = os.path.join(str(tmp_path), "l") + "/"
+    synth.make_logdir(logdir, seed=9, n_perf=5000)
+    eng = CudaEngine(0)
+    try:
+        p = hl.base_params(hl.SRC_PERF, 1600000000.0, False, hl.read_perf_timebase(logdir))
+        with open(logdir + "perf.script", "rb") as f:
+            text = f.read()
+        n, _ = eng.load(hl.SRC_PERF, text, p)
+        assert n == 5000
+        rows = [orc.parse_perf_sample(l, False, 1600000000.0, p['t_offset'], [0.0], [3000.0], 'cycles')
+                for l in text.decode().splitlines()]
+        for col in (0, 1, 2):
+            want = np.array([r[col] for r in rows], dtype=np.float64)
+            got = eng.column(hl.SRC_PERF, col, n)
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), col
+        assert np.array_equal(eng.column(hl.SRC_PERF, 10, n), np.array([r[10] for r in rows], dtype=np.int32))
+    finally:
+        eng.close()
+
+
+def test_malformed_line_fails_loudly(tmp_path):
+    from sofa_b200._lib import SofaB200Error
+    logdir = os.path.join(str(tmp_path), "l") + "/"
+    synth.make_logdir(logdir, seed=9, n_perf=100)
+    with open(logdir + "perf.script", "a") as f:
+        f.write("garbage line\n")
+    cfg = default_report_config(logdir)
+    with pytest.raises(SofaB200Error) as ei:
+        sofa_preprocess(cfg)
+    assert ei.value.row == 100
+
+
+def test_empty_and_unterminated_inputs(tmp_path):
+    logdir = os.path.join(str(tmp_path), "l") + "/"
+    b = os.path.join(str(tmp_path), "o") + "/"
+    for d in (logdir, b):
+        synth.make_logdir(d, seed=3, n_perf=50, n_net=40)
+        for fn in ("perf.script", "net.tmp"):         # drop the final newline
+            with open(d + fn, "rb") as f:
+                t = f.read()
+            with open(d + fn, "wb") as f:
+                f.write(t[:-1])
+    cfg = default_report_config(logdir)
+    sofa_preprocess(cfg)
+    orc.preprocess(orc.OracleConfig(b, nprocs=1), demangle=demangle)
+    for fn in ("cputrace.csv", "nettrace.csv", "report.js"):
+        with open(logdir + fn, "rb") as f, open(b + fn, "rb") as g:
+            _diff("unterminated", fn, f.read(), g.read())
