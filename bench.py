@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py - trace events/s of the SOFA preprocess+analyze hot path on B200.
+
+Workload (BASELINE.json configs[2]): 100 M-event mixed synthetic trace - 60 M perf samples
++ 35 M nvprof gpu activities + 5 M tcpdump packets (1 % non-IP) - with
+cpu_filters=idle,tensorflow and the default gpu_filters.  One step = one full pass:
+line index + parse of the three sources, cputrace/gputrace/nettrace CSV bodies, viz-name
+dictionary + demangle, keyword filters, every report.js series (cpu_trace, 2 cpu filters,
+net_trace, gpu_kernel_trace, 6 gpu filters) and gpu_profile/comm_profile.
+
+  value : events/s with the raw text already resident in HBM (device-timed, CUDA events)
+  e2e   : same pass through the public engine API from PINNED HOST text, with H2D of the
+          text and D2H of every CSV/JSON output inside the timed region
+  roofline     : dominant kernel's algorithmic bytes / its measured launch time vs measured HBM peak
+  cpu_baseline : the CPU oracle (port of the reference's pandas path) on a bounded sample
+
+Multi-GPU: one process per GPU (torchrun); every rank processes its own 100 M-event trace
+(weak scaling, no data-path collective: preprocess rows are independent).
+`--impl reference` times the reference-path CPU port (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+SEED = 20260921 + 3
+MIX = (0.60, 0.35, 0.05)          # perf, gpu, net
+CPU_FILTERS = "idle:black,tensorflow:orange"
+GPU_KWS = ["CUDA_COPY_H2D", "CUDA_COPY_D2H", "CUDA_COPY_P2P", "_fw_", "_bw_", "AllReduceKernel"]
+CPU_KWS = ["idle", "tensorflow"]
+TIME_BASE = 1600000000.0
+PERF_T_OFFSET = 1600000000.25 - 4999.5
+
+
+def split_events(n):
+    a = int(n * MIX[0])
+    b = int(n * MIX[1])
+    return a, b, n - a - b
+
+
+def env_rank():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- device arm
+class Workload:
+    """Holds the engine, the params of the three sources and (for e2e) pinned host buffers."""
+    def __init__(self, eng, events, seed):
+        from sofa_b200 import hostlogic as hl
+        self.eng, self.hl = eng, hl
+        self.n = split_events(events)
+        self.seed = seed
+        self.params = {}
+        self.text_bytes = {}
+        self.data_off = {}
+        self.host_text = {}
+        self.out_bytes = {"csv": 0, "json": 0}
+        self.demangled = {}
+
+    def generate(self):
+        hl, eng = self.hl, self.eng
+        for kind, n, variant in ((hl.SRC_PERF, self.n[0], 0), (hl.SRC_GPU, self.n[1], 0), (hl.SRC_NET, self.n[2], 1)):
+            self.text_bytes[kind] = eng.synth(kind, self.seed, n, variant)
+        p = hl.base_params(hl.SRC_PERF, TIME_BASE, False, PERF_T_OFFSET)
+        self.params[hl.SRC_PERF] = eng.make_params(p); self._keep = [eng._keep]
+        self.data_off[hl.SRC_PERF] = 0
+        p = hl.base_params(hl.SRC_NET, TIME_BASE, False, 0.0)
+        self.params[hl.SRC_NET] = eng.make_params(p); self._keep.append(eng._keep)
+        self.data_off[hl.SRC_NET] = 0
+
+    def fetch_host_text(self):
+        """Synthetic text -> pinned host buffers (untimed; the e2e arm uploads from these)."""
+        hl, eng = self.hl, self.eng
+        for kind in (hl.SRC_PERF, hl.SRC_GPU, hl.SRC_NET):
+            pb = eng.pinned(self.text_bytes[kind])
+            eng.text_fetch(kind, self.text_bytes[kind], pb.array)
+            self.host_text[kind] = pb
+        upd, off = hl.gpu_header(self.host_text[hl.SRC_GPU].array[:1 << 16].tobytes())
+        p = hl.base_params(hl.SRC_GPU, TIME_BASE, False, 0 - upd.pop('t_base'))
+        p.update(upd)
+        self.params[hl.SRC_GPU] = eng.make_params(p); self._keep.append(eng._keep)
+        self.data_off[hl.SRC_GPU] = off
+
+    def _demangle_all(self, names):
+        from sofa_b200.sofa_preprocess import demangle
+        out = []
+        for m in names:
+            d = self.demangled.get(m)
+            if d is None:
+                d = self.demangled[m] = demangle(m)
+            out.append((m, d))
+        return out
+
+    def step(self, e2e, out_buf=None):
+        """One full pass.  e2e=False: text already on the device, outputs stay there.
+        e2e=True: upload from pinned host text, fetch every output into pinned host memory."""
+        hl, eng = self.hl, self.eng
+        nb = {"csv": 0, "json": 0, "h2d": 0}
+        counts = {}
+
+        def csv(kind, stride):
+            n = eng.csv_device(kind, stride)
+            nb["csv"] += n
+            if e2e:
+                eng._fetch(0, n, out_buf)
+
+        def js(kind, stride, filt):
+            n, nrec = eng.json_device(kind, stride, filt)
+            nb["json"] += n
+            if e2e and n:
+                eng._fetch(1, n, out_buf)
+            return nrec
+
+        for kind in (hl.SRC_NET, hl.SRC_GPU, hl.SRC_PERF):          # the reference's source order
+            if e2e:
+                eng.upload(kind, self.host_text[kind].array, self.data_off[kind])
+                nb["h2d"] += self.text_bytes[kind]
+            rows = eng.parse(kind, self.params[kind])
+            counts[kind] = rows
+            if kind == hl.SRC_NET:
+                csv(kind, 1); js(kind, 1, -1)
+            elif kind == hl.SRC_GPU:
+                csv(kind, 1); js(kind, 1, -1)
+                eng.set_filters(kind, 1, GPU_KWS)
+                for i in range(len(GPU_KWS)):
+                    js(kind, 1, i)
+            else:
+                csv(kind, 1)
+                eng.set_demangled(self._demangle_all(eng.viz_mangled(1)))
+                js(kind, 1, -1)
+                eng.set_filters(kind, 1, CPU_KWS)
+                for i in range(len(CPU_KWS)):
+                    js(kind, 1, i)
+        gp = eng.gpu_profile()
+        self.out_bytes = nb
+        return counts, gp
+
+
+def run_ours(args):
+    import numpy as np
+    rank, local_rank, world = env_rank()
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from sofa_b200.engine import CudaEngine
+    eng = CudaEngine(local_rank)
+    wl = Workload(eng, args.events, SEED + 1000 * rank)
+    wl.generate()
+    wl.fetch_host_text()
+    total_events = sum(wl.n)
+    text_total = sum(wl.text_bytes.values())
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: W warm-up, K timed steps between CUDA events on the engine's stream
+    for kind in wl.host_text:                                   # text resident on the device
+        eng.upload(kind, wl.host_text[kind].array, wl.data_off[kind])
+    for _ in range(args.warmup):
+        counts, gp = wl.step(False)
+    assert [counts[k] for k in (0, 1, 2)] == list(wl.n), (counts, wl.n)
+    eng.reset_stats()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    eng.mark(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wl.step(False)
+    eng.mark(1)
+    dev_ms = eng.elapsed_ms()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop()
+    stats, _, _ = eng.stats()
+    launches = sum(v[0] for v in stats.values())
+    dev_ms = max_over_ranks(dev_ms)
+    out_bytes = dict(wl.out_bytes)
+
+    # ---- per-kernel timing pass (profiling on: CUDA events around every launch)
+    eng.set_profiling(True)
+    eng.reset_stats()
+    wl.step(False)
+    kstats, _, _ = eng.stats()
+    eng.set_profiling(False)
+
+    # ---- end-to-end arm: pinned host text in, every output fetched to pinned host memory
+    out_cap = max(wl.n[0] * 400, 1 << 20)
+    out_pin = eng.pinned(out_cap)
+    for _ in range(max(1, min(args.warmup, 2))):
+        wl.step(True, out_pin.array)
+    barrier()
+    eng.mark(0)
+    for _ in range(args.steps):
+        wl.step(True, out_pin.array)
+    eng.mark(1)
+    e2e_ms = max_over_ranks(eng.elapsed_ms())
+    barrier()
+    nb = wl.out_bytes
+
+    if rank != 0:
+        eng.close()
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # algorithmic bytes per kernel kind for ONE step: text in for the ingest
+    # kernels, text out for the emit kernels
+    algo = {"count_lines": text_total, "parse": text_total,
+            "csv_size": out_bytes["csv"], "csv_write": out_bytes["csv"],
+            "json_size": out_bytes["json"], "json_write": out_bytes["json"]}
+    dom = max(kstats.items(), key=lambda kv: kv[1][1])
+    dname, (dl, dms) = dom
+    dbytes = algo.get(dname, 0)
+    achieved = (dbytes / max(dl, 1)) / ((dms / max(dl, 1)) * 1e-3) / 1e9 if dms > 0 else 0.0
+    ms_step = dev_ms / args.steps
+    value = world * total_events / (ms_step * 1e-3)
+    e2e_value = world * total_events / (e2e_ms / args.steps * 1e-3)
+    cpu = cpu_baseline_sample(args, wl)
+    line = {
+        "metric": "trace events/s (preprocess+analyze)", "value": value, "unit": "events/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64/int64",
+        "data": "synthetic",
+        "config": {"workload": "100 M-event mixed perf+CUPTI+tcpdump trace with cpu_filters/gpu_filters tagging (BASELINE configs[2])",
+                   "events_per_gpu": total_events, "perf": wl.n[0], "gpu": wl.n[1], "net": wl.n[2],
+                   "cpu_filters": CPU_FILTERS, "gpu_filters": GPU_KWS, "plot_ratio": 1,
+                   "cache": "inputs_larger_than_L2 (%.1f GB text per step)" % (text_total / 1e9),
+                   "parallelism": "one trace per GPU, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": nb["h2d"],
+                "d2h_bytes_per_step": nb["csv"] + nb["json"], "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "algorithmic_bytes_per_launch": dbytes / max(dl, 1), "launch_ms": dms / max(dl, 1),
+                     "peak_source": peak_src,
+                     "all_kernels_ms": {k: round(v[1], 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][1])},
+                     "whole_step_algorithmic_GBps": (text_total + out_bytes["csv"] + out_bytes["json"]) / (ms_step * 1e-3) / 1e9},
+        "cpu_baseline": cpu,
+        "wall_ms_per_step": wall_ms / args.steps,
+    }
+    print(json.dumps(line))
+    eng.close()
+
+
+# --------------------------------------------------------------------------- CPU arm
+def write_sample_logdir(logdir, n_events, seed, wl=None):
+    """A bounded sample of the same workload: the first rows of the same synthetic streams."""
+    from sofa_b200 import synth
+    n_perf, n_gpu, n_net = split_events(n_events)
+    synth.write_side_files(logdir)
+    if wl is not None:                      # slice the device-generated text at a line boundary
+        import numpy as np
+        for kind, fn, n in ((0, "perf.script", n_perf), (1, "gputrace.tmp", n_gpu), (2, "net.tmp", n_net)):
+            arr = wl.host_text[kind].array
+            extra = 3 if kind == 1 else 0
+            take = min(len(arr), (n + extra) * 200)
+            chunk = arr[:take]
+            nl = np.flatnonzero(chunk == 10)
+            cut = int(nl[n + extra - 1]) + 1
+            with open(os.path.join(logdir, fn), "wb") as f:
+                f.write(chunk[:cut].tobytes())
+    else:
+        with open(os.path.join(logdir, "perf.script"), "w") as f:
+            f.write(synth.perf_text(seed, n_perf))
+        with open(os.path.join(logdir, "gputrace.tmp"), "w") as f:
+            f.write(synth.gpu_text(seed, n_gpu))
+        with open(os.path.join(logdir, "net.tmp"), "w") as f:
+            f.write(synth.net_text(seed, n_net, 1))
+    open(os.path.join(logdir, "gputrace1.nvvp"), "w").close()
+    open(os.path.join(logdir, "sofa.pcap"), "w").close()
+
+
+def oracle_pass(logdir, nprocs):
+    """preprocess + gpu_profile of the CPU oracle (reference-path port) on `logdir`."""
+    import pandas as pd
+    from oracle import sofa_oracle as orc
+    from sofa_b200.sofa_preprocess import demangle
+    cfg = orc.OracleConfig(logdir, cpu_filters=CPU_FILTERS, nprocs=nprocs)
+    orc.preprocess(cfg, demangle=demangle)
+    df = pd.read_csv(logdir + "/gputrace.csv")
+    orc.gpu_profile(df, logdir)
+
+
+def cpu_baseline_sample(args, wl):
+    import multiprocessing as mp
+    n = args.cpu_sample
+    if n <= 0:
+        return None
+    work = tempfile.mkdtemp(prefix="sofa_cpu_")
+    logdir = os.path.join(work, "sofalog") + "/"
+    os.makedirs(logdir)
+    write_sample_logdir(logdir, n, SEED, wl)
+    cores = mp.cpu_count()
+    t0 = time.perf_counter()
+    oracle_pass(logdir, cores)
+    dt = time.perf_counter() - t0
+    import shutil
+    shutil.rmtree(work, ignore_errors=True)
+    return {"value": n / dt, "unit": "events/s", "cores": cores, "kind": "port",
+            "sample": "first %d events of the same mixed trace (60/35/5), oracle preprocess + gpu_profile, %.1f s" % (n, dt)}
+
+
+def run_reference(args):
+    import multiprocessing as mp
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    cores = mp.cpu_count()
+    n = args.cpu_sample
+    work = tempfile.mkdtemp(prefix="sofa_ref_")
+    logdir = os.path.join(work, "sofalog") + "/"
+    os.makedirs(logdir)
+    write_sample_logdir(logdir, n, SEED)
+    for _ in range(args.warmup):
+        oracle_pass(logdir, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_pass(logdir, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    import shutil
+    shutil.rmtree(work, ignore_errors=True)
+    v = n / dt
+    sample = "each step = first %d events of the mixed trace (60/35/5) through the CPU port of the reference path" % n
+    line = {"impl": "reference", "metric": "trace events/s (preprocess+analyze)", "value": v, "unit": "events/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64/int64", "data": "synthetic",
+            "config": {"workload": "100 M-event mixed perf+CUPTI+tcpdump trace with cpu_filters/gpu_filters tagging (BASELINE configs[2])",
+                       "sample": sample, "cpu_filters": CPU_FILTERS, "gpu_filters": GPU_KWS, "plot_ratio": 1},
+            "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--events", type=int, default=100000000, help="events per GPU (default: BASELINE configs[2])")
+    ap.add_argument("--cpu-sample", type=int, default=150000, help="events in the CPU baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,10 @@ int sofa_b200_top_k(sofa_ctx*, int src, uint32_t k, double* sums, uint64_t* nbyt
  * (row indices, descending duration; ties by row index). */
 int sofa_b200_cpu_profile(sofa_ctx*, uint32_t k, double* total, uint64_t* rows, uint32_t* n_out);
 
+/* CUDA-event stopwatch on the ctx stream: mark(0) ... mark(1); elapsed = ms between them */
+int sofa_b200_mark(sofa_ctx*, int which);
+int sofa_b200_elapsed_ms(sofa_ctx*, double* ms);
+
 int sofa_b200_set_profiling(sofa_ctx*, int on);
 int sofa_b200_get_stats(sofa_ctx*, sofa_stats_t* out);
 int sofa_b200_reset_stats(sofa_ctx*);

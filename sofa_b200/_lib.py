@@ -15,7 +15,7 @@ EXPORTS = [
     "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_fetch",
     "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
-    "sofa_b200_synth", "sofa_b200_text_fetch",
+    "sofa_b200_synth", "sofa_b200_text_fetch", "sofa_b200_mark", "sofa_b200_elapsed_ms",
 ]
 
 
@@ -86,6 +86,8 @@ def load_lib():
     lib.sofa_b200_gpu_profile.argtypes = [vp, ctypes.POINTER(GpuProfile)]
     lib.sofa_b200_top_k.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p, u32p]
     lib.sofa_b200_cpu_profile.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p, u32p]
+    lib.sofa_b200_mark.argtypes = [vp, ctypes.c_int]
+    lib.sofa_b200_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.sofa_b200_set_profiling.argtypes = [vp, ctypes.c_int]
     lib.sofa_b200_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.sofa_b200_reset_stats.argtypes = [vp]

@@ -1,3 +1,179 @@
+// Analyze primitives on the resident columns (sofa_analyze.py:343-377 gpu_profile,
+// sofa_common.py:23-177 comm_profile, sofa_analyze.py:34-44 top-k, :694-710 cpu_profile).
+//
+// The reference analyses pd.read_csv(<src>trace.csv), i.e. values that went through
+// "%.6f": every float is read through round6_value().  Float sums reproduce numpy's
+// pairwise tree exactly (stream-compact the group's rows in row order, evaluate 2^d
+// sub-trees in parallel, combine in tree order); integer sums and counts use atomics.
 #pragma once
 #include "kernels_emit.cuh"
-namespace sofa {}
+
+namespace sofa {
+
+enum { P_ALL = 0, P_DEV_EQ, P_KIND_EQ, P_KIND_BIG, P_NAMEHASH, P_CELL_BIG };
+enum { V_GPU_DUR = 0, V_GPU_BW = 1, V_PERF_DUR = 2 };
+
+struct SelArgs {
+    int pred, vsel;
+    int64_t a0, a1;
+    uint64_t h;
+    const uint64_t* namehash;
+    int bw_col_is_float;          // gputrace.csv bandwidth column printed as float (else the CSV holds int 0)
+};
+
+__device__ __forceinline__ bool sel_pred(const SrcView& s, const SelArgs& a, uint64_t row) {
+    switch (a.pred) {
+        case P_ALL: return true;
+        case P_DEV_EQ: return s.c.g.dev[row] == (int32_t)a.a0;
+        case P_KIND_EQ: return s.c.g.kind[row] == (uint8_t)a.a0;
+        case P_KIND_BIG: return s.c.g.kind[row] == (uint8_t)a.a0 && s.c.g.payload[row] > 64000;
+        case P_NAMEHASH: return a.namehash[row] == a.h;
+        default: {
+            uint8_t k = s.c.g.kind[row];
+            return k != 0 && k != 8 && s.c.g.src[row] == (int32_t)a.a0 && s.c.g.dst[row] == (int32_t)a.a1 &&
+                   s.c.g.payload[row] > 64000;
+        }
+    }
+}
+__device__ __forceinline__ double sel_value(const SrcView& s, const SelArgs& a, uint64_t row) {
+    if (a.vsel == V_GPU_DUR) return round6_value(s.c.g.dur[row]);
+    if (a.vsel == V_GPU_BW) return a.bw_col_is_float ? round6_value(s.c.g.bw[row]) : 0.0;
+    return round6_value(s.c.p.dur[row]);
+}
+
+__global__ void __launch_bounds__(256) k_select_count(SrcView src, uint64_t n, SelArgs a, uint64_t* blockoff) {
+    __shared__ uint32_t sm[33];
+    uint64_t row = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t f = (row < n && sel_pred(src, a, row)) ? 1u : 0u;
+    uint32_t total;
+    block_excl_scan(f, &total, sm);
+    if (threadIdx.x == 0) blockoff[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) k_select_write(SrcView src, uint64_t n, SelArgs a, const uint64_t* blockoff,
+                                                      double* __restrict__ out) {
+    __shared__ uint32_t sm[33];
+    uint64_t row = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    bool f = row < n && sel_pred(src, a, row);
+    uint32_t total;
+    uint32_t ex = block_excl_scan(f ? 1u : 0u, &total, sm);
+    if (f) out[blockoff[blockIdx.x] + ex] = sel_value(src, a, row);
+}
+
+// 2^depth sub-trees of numpy's pairwise tree, one thread each; then the combine sweep.
+__global__ void __launch_bounds__(128) k_pairwise_top(const double* __restrict__ a, uint64_t n, int depth, double* partial) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (1u << depth)) return;
+    uint64_t s, l;
+    pairwise_subtree(n, depth, t, &s, &l);
+    // pairwise_sum adds the 0.0 identity; harmless on an inner node (x + 0.0 == x for x != -0.0,
+    // and -0.0 can only come from an all -0.0 sub-tree, which durations never are)
+    partial[t] = pairwise_sum(a + s, l);
+}
+__global__ void k_pairwise_combine(double* partial, int depth, double* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int lev = depth - 1; lev >= 0; lev--)
+        for (uint32_t i = 0; i < (1u << lev); i++) partial[i] = d_add(partial[2 * i], partial[2 * i + 1]);
+    *out = d_add(0.0, partial[0]);
+}
+// python-loop accumulation in row order (sofa_common.py:108-119 accum_bw)
+__global__ void k_seq_sum(const double* __restrict__ a, uint64_t n, double* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = 0.0;
+    for (uint64_t i = 0; i < n; i++) s = d_add(s, a[i]);
+    *out = s;
+}
+
+struct GpuStats {
+    unsigned long long dev_hist[4096];     // deviceId + 1 in [0, 4096)
+    long long max_dev;
+    unsigned long long kind_count[16], big_count[16];
+    unsigned long long payload_sum[16];    // two's complement int64 sums per copyKind
+    unsigned long long cell_payload[256], cell_count[256], cell_big[256];   // (src, dst) in [0,16)^2
+    unsigned int bad_dev, bad_cell;
+};
+
+__global__ void __launch_bounds__(256) k_gpu_stats(SrcView src, uint64_t n, GpuStats* st) {
+    __shared__ unsigned int hist[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    long long mx = -0x7fffffffffffffffll;
+    for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+        int32_t dev = src.c.g.dev[row];
+        uint8_t k = src.c.g.kind[row];
+        int64_t pl = src.c.g.payload[row];
+        if (dev < -1 || dev > 4094) atomicOr(&st->bad_dev, 1u); else atomicAdd(&hist[dev + 1], 1u);
+        if (dev > mx) mx = dev;
+        atomicAdd(&st->kind_count[k & 15], 1ull);
+        if (pl > 64000) atomicAdd(&st->big_count[k & 15], 1ull);
+        if (k != 0) atomicAdd(&st->payload_sum[k & 15], (unsigned long long)pl);
+        if (k != 0 && k != 8) {
+            int32_t s = src.c.g.src[row], d = src.c.g.dst[row];
+            if (s < 0 || s > 15 || d < 0 || d > 15) atomicOr(&st->bad_cell, 1u);
+            else {
+                int c = s * 16 + d;
+                atomicAdd(&st->cell_payload[c], (unsigned long long)pl);
+                atomicAdd(&st->cell_count[c], 1ull);
+                if (pl > 64000) atomicAdd(&st->cell_big[c], 1ull);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) if (hist[i]) atomicAdd(&st->dev_hist[i], (unsigned long long)hist[i]);
+    atomicMax(&st->max_dev, mx);
+}
+
+// hash + "contains nccl" over the generated name in one pass
+struct NcclHashSink {
+    HashSink h; uint32_t w; bool hit;
+    __device__ NcclHashSink() : w(0), hit(false) {}
+    __device__ __forceinline__ void put(char ch) { h.put(ch); w = (w << 8) | (unsigned char)ch; hit |= (w == 0x6e63636cu); }
+};
+// namehash[row] = FNV-1a of the full name when it contains "nccl" (else 0); distinct hashes
+// go into an open-addressing table (value = smallest row).
+__global__ void __launch_bounds__(256) k_nccl_hash(SrcView src, uint64_t n, uint64_t* __restrict__ namehash,
+                                                   unsigned long long* keys, unsigned long long* rows, uint64_t cap_mask,
+                                                   unsigned int* overflow) {
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    uint64_t key = 0;
+    if (src.c.g.kind[row] == 0) {
+        GpuRow r = load_gpu(src, row);
+        GpuName<const char*> ng{src.text + src.c.g.line_start[row], r};
+        NcclHashSink s; ng.gen(s);
+        if (s.hit) {
+            key = s.h.h ? s.h.h : 1;
+            uint64_t slot = key & cap_mask;
+            bool done = false;
+            for (uint64_t probe = 0; probe <= cap_mask && probe < 8192; probe++) {
+                unsigned long long prev = atomicCAS(&keys[slot], 0ull, (unsigned long long)key);
+                if (prev == 0ull || prev == key) { atomicMin(&rows[slot], (unsigned long long)row); done = true; break; }
+                slot = (slot + 1) & cap_mask;
+            }
+            if (!done) atomicOr(overflow, 1u);
+        }
+    }
+    namehash[row] = key;
+}
+// names of the table's representative rows, each followed by '\0' (gpu names may hold '\n');
+// order[] receives the slot of every exported name in output order.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_table_names(SrcView src, const unsigned long long* keys, const unsigned long long* rows,
+                                                     uint64_t cap, unsigned long long* cursor, unsigned int* n_out, char* out,
+                                                     uint64_t out_cap, uint64_t* name_off, uint32_t* name_slot) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= cap || keys[s] == 0ull) return;
+    uint64_t row = rows[s];
+    with_row<KIND, false>(src, row, row, [&](const RowVals&, const auto& ng) {
+        LenSink l; ng.gen(l);
+        unsigned long long off = atomicAdd(cursor, (unsigned long long)(l.len + 1));
+        unsigned int idx = atomicAdd(n_out, 1u);
+        if (out && off + l.len + 1 <= out_cap) {
+            RawWrite<char*> w{out + off, 0}; ng.gen(w);
+            out[off + l.len] = '\0';
+            name_off[idx] = off; name_slot[idx] = (uint32_t)s;
+        }
+    });
+}
+
+}  // namespace sofa

@@ -539,4 +539,71 @@ SOFA_HD double ip_event_raw(uint64_t ip, int hexdigits) {
     u128 v = (((u128)1) << (4 * hexdigits)) | (u128)ip;
     return round_u128(v, 0, false);
 }
+
+// ----------------------------------------------------------------------------- values as read back from a trace CSV
+// sofa_analyze works on pd.read_csv(<src>trace.csv): every float column has been through
+// "%.6f" and a correctly rounded strtod (sofa_analyze.py:898-977).
+SOFA_HD double round6_value(double x) {
+    bool neg; uint64_t I; uint32_t F;
+    if (!fixed6_parts(x, &neg, &I, &F)) return x;          // |x| >= 2^63: caller's emit fails loudly first
+    double r;
+    if (I < 9000000000ull) r = d_div((double)(I * 1000000ull + F), 1e6);
+    else {
+        u128 N = (u128)I * 1000000u + F;
+        if ((N >> 64) != 0) return x;
+        dec_to_double((uint64_t)N, -6, false, &r);
+    }
+    return neg ? -r : r;
+}
+
+// ----------------------------------------------------------------------------- numpy pairwise summation
+// np.add.reduce over a contiguous float64 array: 0.0 + pairwise_sum (numpy/_core/src/umath/
+// loops_utils.h DOUBLE_pairwise_sum): blocks of <= 128 with 8 accumulators, halves rounded
+// down to a multiple of 8.  Series.sum(), get_group(k).sum() and aggregate(np.sum) all end here.
+template <typename A>
+SOFA_HD double pairwise_leaf(A a, uint64_t n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (uint64_t i = 0; i < n; i++) r = d_add(r, a[i]);
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    uint64_t i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] = d_add(r[j], a[i + j]);
+    double res = d_add(d_add(d_add(r[0], r[1]), d_add(r[2], r[3])), d_add(d_add(r[4], r[5]), d_add(r[6], r[7])));
+    for (; i < n; i++) res = d_add(res, a[i]);
+    return res;
+}
+SOFA_HD uint64_t pairwise_split(uint64_t n) { uint64_t n2 = n / 2; return n2 - (n2 % 8); }
+
+template <typename A>
+SOFA_HD double pairwise_sum(A a, uint64_t n) {
+    struct Fr { uint64_t s, n; int st; double left; };
+    Fr stk[64];
+    int sp = 0;
+    stk[0].s = 0; stk[0].n = n; stk[0].st = 0; stk[0].left = 0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        Fr& f = stk[sp];
+        if (f.n <= 128) { ret = pairwise_leaf(a + f.s, f.n); sp--; continue; }
+        uint64_t n2 = pairwise_split(f.n);
+        if (f.st == 0) { f.st = 1; stk[sp + 1].s = f.s; stk[sp + 1].n = n2; stk[sp + 1].st = 0; sp++; continue; }
+        if (f.st == 1) { f.left = ret; f.st = 2; stk[sp + 1].s = f.s + n2; stk[sp + 1].n = f.n - n2; stk[sp + 1].st = 0; sp++; continue; }
+        ret = d_add(f.left, ret);
+        sp--;
+    }
+    return d_add(0.0, ret);
+}
+// sub-tree `t` (0 <= t < 2^depth) of the pairwise tree over n elements; every node above
+// `depth` must be longer than 128 (callers pick depth with n >> depth >= 1024).
+SOFA_HD void pairwise_subtree(uint64_t n, int depth, uint32_t t, uint64_t* start, uint64_t* len) {
+    uint64_t s = 0, l = n;
+    for (int lev = depth - 1; lev >= 0; lev--) {
+        uint64_t n2 = pairwise_split(l);
+        if ((t >> lev) & 1) { s += n2; l -= n2; } else l = n2;
+    }
+    *start = s; *len = l;
+}
 }  // namespace sofa

@@ -65,6 +65,7 @@ struct sofa_ctx {
     unsigned int* d_flags = nullptr;            // [0] cr flag, [1] row flags, [2] overflow, [3] count
     uint64_t err_row = 0; int err_code = 0;
     bool profiling = false;
+    cudaEvent_t mark[2] = {nullptr, nullptr};
     std::vector<TimedEvent> events;
     std::vector<cudaEvent_t> pool;
     sofa_stats_t stats;
@@ -225,6 +226,7 @@ int sofa_b200_destroy(sofa_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& e : c->pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
     for (int k = 0; k < 3; k++) {
         Source& s = c->src[k];
         s.text.release(); s.mhz.release(); s.mask.release(); s.vizhash.release(); s.viz_id.release();
@@ -608,6 +610,23 @@ int sofa_b200_get_column(sofa_ctx* c, int k, int col, void* host_out, uint64_t c
     uint64_t nb = s.n_rows * w;
     if (cap_bytes < nb) FAIL(SOFA_ERR_CAP, "get_column: buffer too small");
     if (nb) { CK(cudaMemcpyAsync(host_out, s.cols[slot].p, nb, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return 0;
+}
+
+int sofa_b200_mark(sofa_ctx* c, int which) {
+    if (!c || which < 0 || which > 1) FAIL(SOFA_ERR_ARG, "mark: bad argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->mark[which]) CK(cudaEventCreate(&c->mark[which]));
+    CK(cudaEventRecord(c->mark[which], c->stream));
+    return 0;
+}
+int sofa_b200_elapsed_ms(sofa_ctx* c, double* ms) {
+    if (!c || !ms || !c->mark[0] || !c->mark[1]) FAIL(SOFA_ERR_ARG, "elapsed_ms: marks not set");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->mark[1]));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->mark[0], c->mark[1]));
+    *ms = f;
     return 0;
 }
 

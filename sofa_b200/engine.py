@@ -188,6 +188,15 @@ class CudaEngine:
         self._check(self.lib.sofa_b200_cpu_profile(self.ctx, k, ctypes.byref(total), rows, ctypes.byref(cnt)))
         return total.value, [rows[i] for i in range(cnt.value)]
 
+    # ---- stopwatch (CUDA events on the engine's stream)
+    def mark(self, which):
+        self._check(self.lib.sofa_b200_mark(self.ctx, which))
+
+    def elapsed_ms(self):
+        ms = ctypes.c_double()
+        self._check(self.lib.sofa_b200_elapsed_ms(self.ctx, ctypes.byref(ms)))
+        return ms.value
+
     # ---- stats / synth
     def set_profiling(self, on):
         self._check(self.lib.sofa_b200_set_profiling(self.ctx, 1 if on else 0))

@@ -125,7 +125,10 @@ def sofa_preprocess(cfg, engine=None):
         return _preprocess(cfg, engine)
     finally:
         if own_engine:
-            engine.close()
+            if getattr(cfg, 'keep_engine', False):
+                cfg._sofa_b200_engine = engine      # `sofa report`: sofa_analyze reuses the resident columns
+            else:
+                engine.close()
 
 
 def _preprocess(cfg, eng):

@@ -125,3 +125,29 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
 }
 unsigned long long hs_fnv(const char* s, long n) { HashSink h; for (long i = 0; i < n; i++) h.put(s[i]); return h.h; }
 }
+
+// ---------------------------------------------------------------- synthetic generator spec
+#include "../sofa_b200/csrc/synth.cuh"
+extern "C" long hs_synth(int src, unsigned long long seed, unsigned long long i0, unsigned long long n, int variant, char* out) {
+    RawWrite<char*> w{out, 0};
+    for (unsigned long long i = i0; i < i0 + n; i++) synth_line(w, src, seed, i, variant);
+    return w.n;
+}
+
+// ---------------------------------------------------------------- analyze primitives
+extern "C" {
+double hs_pairwise(const double* a, unsigned long long n) { return pairwise_sum(a, n); }
+double hs_pairwise_par(const double* a, unsigned long long n, int depth) {
+    // emulates the two-kernel device evaluation: 2^depth sub-trees, then the combine sweep
+    std::vector<double> part((size_t)1 << depth);
+    for (uint32_t t = 0; t < (1u << depth); t++) {
+        uint64_t s, l; pairwise_subtree(n, depth, t, &s, &l);
+        double v = pairwise_sum(a + s, l);
+        part[t] = v;
+    }
+    for (int lev = depth - 1; lev >= 0; lev--)
+        for (uint32_t i = 0; i < (1u << lev); i++) part[i] = part[2 * i] + part[2 * i + 1];
+    return 0.0 + part[0];
+}
+double hs_round6(double x) { return round6_value(x); }
+}

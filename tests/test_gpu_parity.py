@@ -112,3 +112,51 @@ def test_empty_and_unterminated_inputs(tmp_path):
     for fn in ("cputrace.csv", "nettrace.csv", "report.js"):
         with open(logdir + fn, "rb") as f, open(b + fn, "rb") as g:
             _diff("unterminated", fn, f.read(), g.read())
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if golden_bytes(n, "gputrace.csv")])
+def test_gpu_profile_features_match_reference(name, tmp_path, capsys):
+    from helpers import load_case
+    from sofa_b200.sofa_analyze import sofa_analyze
+    case, logdir = build_case_logdir(name, tmp_path)
+    ov = dict(case["cfg"])
+    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None))
+    for k, v in ov.items():
+        setattr(cfg, k, v)
+    sofa_preprocess(cfg)
+    feats = dict(sofa_analyze(cfg))
+    for k, v in case["features"].items():
+        if k != "elapsed_time":
+            assert float(feats[k]) == v, (k, feats[k], v)
+    assert "Complete!!" in capsys.readouterr().out
+
+
+def test_gpu_profile_matches_oracle_on_larger_log(tmp_path):
+    import pandas as pd
+    from sofa_b200.sofa_analyze import sofa_analyze
+    a = os.path.join(str(tmp_path), "gpu") + "/"
+    synth.make_logdir(a, seed=202, n_gpu=150000, units="ms_us_KB", p2p_cols=True)
+    cfg = default_report_config(a)
+    sofa_preprocess(cfg)
+    feats = dict(sofa_analyze(cfg))
+    df = pd.read_csv(a + "gputrace.csv")
+    want = dict(orc.gpu_profile(df))
+    for k, v in want.items():
+        assert float(feats[k]) == float(v), (k, feats[k], v)
+
+
+def test_device_synth_matches_python_generator():
+    from sofa_b200.engine import CudaEngine
+    eng = CudaEngine(0)
+    try:
+        for kind, variant, ref in [(0, 0, lambda n: synth.perf_text(77, n)),
+                                   (0, 1, lambda n: synth.perf_text(77, n, True)),
+                                   (1, 0, lambda n: synth.gpu_text(77, n)),
+                                   (1, 1, lambda n: synth.gpu_text(77, n, "ms_us_KB", True)),
+                                   (2, 1, lambda n: synth.net_text(77, n, 1))]:
+            n = 20011
+            nb = eng.synth(kind, 77, n, variant)
+            got = eng.text_fetch(kind, nb).tobytes()
+            assert got == ref(n).encode(), (kind, variant)
+    finally:
+        eng.close()

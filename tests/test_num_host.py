@@ -210,3 +210,44 @@ def test_interp_matches_numpy(hs):
     for x in xs:
         got = hs.hs_interp(x, xp.ctypes.data_as(ctypes.c_void_p), fp.ctypes.data_as(ctypes.c_void_p), len(xp))
         assert got == float(np.interp(x, xp, fp)), x
+
+
+def test_device_synth_spec_matches_python_generator(hs):
+    from sofa_b200 import synth
+    hs.hs_synth.restype = ctypes.c_long
+    for src, variant, ref in [(0, 0, lambda i: synth.perf_line(33, i)),
+                              (0, 1, lambda i: synth.perf_line(33, i, True)),
+                              (1, 0, lambda i: synth.gpu_line(33, i)),
+                              (1, 1, lambda i: synth.gpu_line(33, i, "ms_us_KB", True)),
+                              (2, 0, lambda i: synth.net_line(33, i, 0)),
+                              (2, 5, lambda i: synth.net_line(33, i, 5))]:
+        n = 3000
+        buf = ctypes.create_string_buffer(n * 400)
+        L = hs.hs_synth(src, ctypes.c_ulonglong(33), ctypes.c_ulonglong(0), ctypes.c_ulonglong(n), variant, buf)
+        want = "".join(ref(i) for i in range(n)).encode()
+        assert buf.raw[:L] == want, (src, variant)
+
+
+def test_pairwise_sum_is_numpy_sum(hs):
+    hs.hs_pairwise.restype = ctypes.c_double
+    hs.hs_pairwise_par.restype = ctypes.c_double
+    rng = np.random.default_rng(5)
+    for n in [0, 1, 5, 7, 8, 9, 64, 127, 128, 129, 136, 255, 256, 1000, 1024, 4097, 65537, 300001, 2000003]:
+        a = rng.random(n) * 10.0 ** rng.integers(-6, 3)
+        want = float(np.sum(a)) if n else 0.0
+        got = hs.hs_pairwise(a.ctypes.data_as(ctypes.c_void_p), ctypes.c_ulonglong(n))
+        assert got == want, n
+        for depth in (1, 3, 6):
+            if n >> depth >= 1024:
+                got = hs.hs_pairwise_par(a.ctypes.data_as(ctypes.c_void_p), ctypes.c_ulonglong(n), depth)
+                assert got == want, (n, depth)
+
+
+def test_round6_is_csv_roundtrip(hs):
+    hs.hs_round6.restype = ctypes.c_double
+    hs.hs_round6.argtypes = [ctypes.c_double]
+    rng = random.Random(31)
+    for x in rand_doubles(rng, 20000) + [0.0, -0.0, 0.0078125, 1e10, 9.5e9, -1599999999.99955, 1e-7]:
+        if abs(x) >= 2.0 ** 62:
+            continue
+        assert hs.hs_round6(x) == float("%.6f" % x), x
