@@ -149,7 +149,7 @@ class Workload:
             out.append((m, d))
         return out
 
-    def step(self, e2e, out_buf=None):
+    def step(self, e2e, out_buf=None, kinds=None, analyze=True):
         """One full pass.  e2e=False: text already on the device, outputs stay there.
         e2e=True: upload from pinned host text, fetch every output into pinned host memory."""
         hl, eng = self.hl, self.eng
@@ -170,6 +170,8 @@ class Workload:
             return nrec
 
         for kind in (hl.SRC_NET, hl.SRC_GPU, hl.SRC_PERF):          # the reference's source order
+            if kinds is not None and kind not in kinds:
+                continue
             if e2e:
                 eng.upload(kind, self.host_text[kind].array, self.data_off[kind])
                 nb["h2d"] += self.text_bytes[kind]
@@ -189,7 +191,7 @@ class Workload:
                 eng.set_filters(kind, 1, CPU_KWS)
                 for i in range(len(CPU_KWS)):
                     js(kind, 1, i)
-        gp = eng.gpu_profile()
+        gp = eng.gpu_profile() if analyze else None
         self.out_bytes = nb
         return counts, gp
 
