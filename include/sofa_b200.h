@@ -124,16 +124,19 @@ int sofa_b200_fetch(sofa_ctx*, int which, void* host_out, uint64_t cap);
 int sofa_b200_get_column(sofa_ctx*, int src, int col, void* host_out, uint64_t cap_bytes);
 
 /* gpu_profile + comm_profile features on the parsed gpu rows (sofa_analyze.py:343-377,
- * sofa_common.py:23-177). */
-int sofa_b200_gpu_profile(sofa_ctx*, sofa_gpu_profile_t* out);
+ * sofa_common.py:23-177).  want_matrices: also fill the (src,dst) matrices that the
+ * reference prints only with --verbose (python-loop sums, row order). */
+int sofa_b200_gpu_profile(sofa_ctx*, sofa_gpu_profile_t* out, int want_matrices);
 
 /* get_top_k_events (sofa_analyze.py:34-44): names by summed duration, descending.
- * names: '\n'-separated into output buffer 2; sums[k] their totals. */
+ * names: '\0'-terminated, in order, into output buffer 2; sums[k] their totals. */
 int sofa_b200_top_k(sofa_ctx*, int src, uint32_t k, double* sums, uint64_t* nbytes, uint32_t* n_out);
 
 /* cpu_profile (sofa_analyze.py:694-710): total duration and the k largest-duration rows
- * (row indices, descending duration; ties by row index). */
-int sofa_b200_cpu_profile(sofa_ctx*, uint32_t k, double* total, uint64_t* rows, uint32_t* n_out);
+ * (descending duration, ties by row index): row index, timestamp and duration as read from
+ * cputrace.csv; their names '\0'-terminated into output buffer 2. */
+int sofa_b200_cpu_profile(sofa_ctx*, uint32_t k, double* total, uint64_t* rows, double* ts, double* dur,
+                          uint64_t* names_nbytes, uint32_t* n_out);
 
 /* CUDA-event stopwatch on the ctx stream: mark(0) ... mark(1); elapsed = ms between them */
 int sofa_b200_mark(sofa_ctx*, int which);

@@ -361,8 +361,8 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
 # --------------------------------------------------------------------------- a11-a13
 def top_k_events(df, topk):
     """sofa_analyze.py:34-44: names ordered by summed duration, descending."""
-    agg = df.groupby(['name'])['duration'].sum()
-    return agg.sort_values(ascending=False).head(topk)
+    agg = df.groupby(['name']).aggregate(np.sum)               # :37 (np.sum per group = pairwise)
+    return agg.sort_values(by=['duration'], ascending=False)['duration'].head(topk)
 
 
 def comm_profile(df_gpu, logdir=None):

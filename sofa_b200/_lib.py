@@ -83,9 +83,10 @@ def load_lib():
     lib.sofa_b200_emit_json.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32, u64p, u64p]
     lib.sofa_b200_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
     lib.sofa_b200_get_column.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64]
-    lib.sofa_b200_gpu_profile.argtypes = [vp, ctypes.POINTER(GpuProfile)]
+    lib.sofa_b200_gpu_profile.argtypes = [vp, ctypes.POINTER(GpuProfile), ctypes.c_int]
     lib.sofa_b200_top_k.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p, u32p]
-    lib.sofa_b200_cpu_profile.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p, u32p]
+    lib.sofa_b200_cpu_profile.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p,
+                                          ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), u64p, u32p]
     lib.sofa_b200_mark.argtypes = [vp, ctypes.c_int]
     lib.sofa_b200_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.sofa_b200_set_profiling.argtypes = [vp, ctypes.c_int]

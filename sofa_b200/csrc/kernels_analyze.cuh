@@ -93,34 +93,55 @@ struct GpuStats {
 };
 
 __global__ void __launch_bounds__(256) k_gpu_stats(SrcView src, uint64_t n, GpuStats* st) {
+    // block-private accumulators in shared memory, one flush per block
     __shared__ unsigned int hist[4096];
+    __shared__ unsigned long long s_kind[16], s_big[16], s_pay[16];
+    __shared__ unsigned long long s_cpay[256], s_ccnt[256], s_cbig[256];
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x < 16) { s_kind[threadIdx.x] = 0; s_big[threadIdx.x] = 0; s_pay[threadIdx.x] = 0; }
+    s_cpay[threadIdx.x] = 0; s_ccnt[threadIdx.x] = 0; s_cbig[threadIdx.x] = 0;
     __syncthreads();
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     long long mx = -0x7fffffffffffffffll;
+    unsigned int bad_dev = 0, bad_cell = 0;
     for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
         int32_t dev = src.c.g.dev[row];
         uint8_t k = src.c.g.kind[row];
         int64_t pl = src.c.g.payload[row];
-        if (dev < -1 || dev > 4094) atomicOr(&st->bad_dev, 1u); else atomicAdd(&hist[dev + 1], 1u);
+        if (dev < -1 || dev > 4094) bad_dev = 1; else atomicAdd(&hist[dev + 1], 1u);
         if (dev > mx) mx = dev;
-        atomicAdd(&st->kind_count[k & 15], 1ull);
-        if (pl > 64000) atomicAdd(&st->big_count[k & 15], 1ull);
-        if (k != 0) atomicAdd(&st->payload_sum[k & 15], (unsigned long long)pl);
+        atomicAdd(&s_kind[k & 15], 1ull);
+        if (pl > 64000) atomicAdd(&s_big[k & 15], 1ull);
+        if (k != 0) atomicAdd(&s_pay[k & 15], (unsigned long long)pl);
         if (k != 0 && k != 8) {
             int32_t s = src.c.g.src[row], d = src.c.g.dst[row];
-            if (s < 0 || s > 15 || d < 0 || d > 15) atomicOr(&st->bad_cell, 1u);
+            if (s < 0 || s > 15 || d < 0 || d > 15) bad_cell = 1;
             else {
                 int c = s * 16 + d;
-                atomicAdd(&st->cell_payload[c], (unsigned long long)pl);
-                atomicAdd(&st->cell_count[c], 1ull);
-                if (pl > 64000) atomicAdd(&st->cell_big[c], 1ull);
+                atomicAdd(&s_cpay[c], (unsigned long long)pl);
+                atomicAdd(&s_ccnt[c], 1ull);
+                if (pl > 64000) atomicAdd(&s_cbig[c], 1ull);
             }
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) if (hist[i]) atomicAdd(&st->dev_hist[i], (unsigned long long)hist[i]);
-    atomicMax(&st->max_dev, mx);
+    if (threadIdx.x < 16) {
+        if (s_kind[threadIdx.x]) atomicAdd(&st->kind_count[threadIdx.x], s_kind[threadIdx.x]);
+        if (s_big[threadIdx.x]) atomicAdd(&st->big_count[threadIdx.x], s_big[threadIdx.x]);
+        if (s_pay[threadIdx.x]) atomicAdd(&st->payload_sum[threadIdx.x], s_pay[threadIdx.x]);
+    }
+    if (s_ccnt[threadIdx.x]) {
+        atomicAdd(&st->cell_payload[threadIdx.x], s_cpay[threadIdx.x]);
+        atomicAdd(&st->cell_count[threadIdx.x], s_ccnt[threadIdx.x]);
+        if (s_cbig[threadIdx.x]) atomicAdd(&st->cell_big[threadIdx.x], s_cbig[threadIdx.x]);
+    }
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 16)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 4)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    if (lane_id() == 0) atomicMax(&st->max_dev, mx);
+    if (bad_dev) atomicOr(&st->bad_dev, 1u);
+    if (bad_cell) atomicOr(&st->bad_cell, 1u);
 }
 
 // hash + "contains nccl" over the generated name in one pass
@@ -141,8 +162,8 @@ __global__ void __launch_bounds__(256) k_nccl_hash(SrcView src, uint64_t n, uint
         GpuRow r = load_gpu(src, row);
         GpuName<const char*> ng{src.text + src.c.g.line_start[row], r};
         NcclHashSink s; ng.gen(s);
-        if (s.hit) {
-            key = s.h.h ? s.h.h : 1;
+        if (s.hit) key = s.h.h ? s.h.h : 1;
+        if (s.hit && keys) {
             uint64_t slot = key & cap_mask;
             bool done = false;
             for (uint64_t probe = 0; probe <= cap_mask && probe < 8192; probe++) {

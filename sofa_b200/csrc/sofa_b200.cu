@@ -11,6 +11,7 @@
 #include "../../include/sofa_b200.h"
 #include "kernels_emit.cuh"
 #include "kernels_analyze.cuh"
+#include "kernels_sort.cuh"
 #include "synth.cuh"
 
 using namespace sofa;
@@ -61,6 +62,7 @@ struct sofa_ctx {
     Source src[3];
     DevBuf out[3]; uint64_t out_n[3] = {0, 0, 0};
     DevBuf tiles, rowlen, blockoff, scratch, ftable, keys, rows;
+    DevBuf sk0, sv0, sk1, sv1, hist, segs, sums, small;
     unsigned long long* d_err = nullptr;        // [0] error slot, [1] counter, [2..9] filter counts, [10] misc
     unsigned int* d_flags = nullptr;            // [0] cr flag, [1] row flags, [2] overflow, [3] count
     uint64_t err_row = 0; int err_code = 0;
@@ -236,6 +238,8 @@ int sofa_b200_destroy(sofa_ctx* c) {
     }
     c->tiles.release(); c->rowlen.release(); c->blockoff.release(); c->scratch.release(); c->ftable.release();
     c->keys.release(); c->rows.release();
+    c->sk0.release(); c->sv0.release(); c->sk1.release(); c->sv1.release(); c->hist.release(); c->segs.release();
+    c->sums.release(); c->small.release();
     cudaFree(c->d_err); cudaFree(c->d_flags);
     cudaStreamDestroy(c->stream);
     delete c;

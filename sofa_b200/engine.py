@@ -168,12 +168,13 @@ class CudaEngine:
         return out
 
     # ---- analyze
-    def gpu_profile(self):
+    def gpu_profile(self, want_matrices=False):
         gp = L.GpuProfile()
-        self._check(self.lib.sofa_b200_gpu_profile(self.ctx, ctypes.byref(gp)))
+        self._check(self.lib.sofa_b200_gpu_profile(self.ctx, ctypes.byref(gp), 1 if want_matrices else 0))
         return gp
 
     def top_k(self, kind, k):
+        """[(name, summed duration)] by descending sum (get_top_k_events)."""
         sums = (ctypes.c_double * max(1, k))()
         n = ctypes.c_uint64()
         cnt = ctypes.c_uint32()
@@ -182,11 +183,17 @@ class CudaEngine:
         return list(zip(names, [sums[i] for i in range(cnt.value)]))
 
     def cpu_profile(self, k):
+        """(total duration, [(row, timestamp, duration, name)] by descending duration)."""
         total = ctypes.c_double()
         rows = (ctypes.c_uint64 * max(1, k))()
+        ts = (ctypes.c_double * max(1, k))()
+        dur = (ctypes.c_double * max(1, k))()
+        nb = ctypes.c_uint64()
         cnt = ctypes.c_uint32()
-        self._check(self.lib.sofa_b200_cpu_profile(self.ctx, k, ctypes.byref(total), rows, ctypes.byref(cnt)))
-        return total.value, [rows[i] for i in range(cnt.value)]
+        self._check(self.lib.sofa_b200_cpu_profile(self.ctx, k, ctypes.byref(total), rows, ts, dur,
+                                                   ctypes.byref(nb), ctypes.byref(cnt)))
+        names = self._fetch(2, nb.value).tobytes().decode().split('\x00')[:-1] if nb.value else []
+        return total.value, [(rows[i], ts[i], dur[i], names[i]) for i in range(cnt.value)]
 
     # ---- stopwatch (CUDA events on the engine's stream)
     def mark(self, which):

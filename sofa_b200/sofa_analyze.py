@@ -69,7 +69,7 @@ def comm_profile_report(cfg, gp):
 
 def gpu_profile(cfg, eng):
     """sofa_analyze.py:343-377 on the engine's parsed gpu rows -> ordered feature list."""
-    gp = eng.gpu_profile()
+    gp = eng.gpu_profile(want_matrices=bool(cfg.verbose))
     if cfg.verbose:
         print_title('GPU Profiling')
         print('Per-GPU time (s):')
@@ -80,9 +80,44 @@ def gpu_profile(cfg, eng):
         raise TypeError("comm_profile: no GPU communication traces (deviceId never > 0); the "
                         "reference raises TypeError at sofa_common.py:59")
     feats += comm_profile_report(cfg, gp)
+    if cfg.verbose:                                   # get_top_k_events (sofa_analyze.py:34-44)
+        print("Top %d Events: " % 10)
+        for name, total in eng.top_k(SRC_GPU, 10):
+            print("%-60s %.6f" % (name.rstrip('\n')[:60], total))
     feats += [('gpu_time', gp.gpu_time), ('num_gpus', gp.num_gpus), ('kernel_time', gp.kernel_time),
               ('nccl_time', gp.nccl_time)]
     return feats
+
+
+def cpu_profile(cfg, eng):
+    """sofa_analyze.py:694-710 (verbose only): total execution time and the 20 longest samples."""
+    total, rows = eng.cpu_profile(cfg.cpu_top_k if hasattr(cfg, 'cpu_top_k') else 20)
+    print_title('CPU Profiling:')
+    print('elapsed_time (s) = %.6lf' % cfg.elapsed_time)
+    print("[%d]: %lf" % (-1, total))
+    print("total execution time (s) = %.3lf" % total)
+    print("%12s %10s %10s  %s" % ('timestamp', 'ratio(%)', 'duration', 'name'))
+    for _, ts, dur, name in rows:
+        print("%12.6f %10.6f %10.6f  %s" % (ts, dur / total * 100 if total else 0.0, dur, name))
+    return total, rows
+
+
+def load_perf_source(cfg, eng):
+    """(Re-)ingest perf.script exactly as sofa_preprocess does (sofa_preprocess.py:1786-1807)."""
+    logdir = cfg.logdir
+    if not os.path.isfile(logdir + 'perf.script'):
+        return False
+    with open(logdir + 'perf.script', 'rb') as f:
+        text = f.read()
+    if not text:
+        return False
+    from .hostlogic import SRC_PERF
+    time_base = hl.read_time_base(logdir, cfg.cpu_time_offset)
+    p = hl.base_params(SRC_PERF, time_base, cfg.absolute_timestamp, hl.read_perf_timebase(logdir))
+    p['perf_has_cycles'] = 1 if hl.read_perf_events(logdir).find('cycles') != -1 else 0
+    p['mhz_xp'], p['mhz_fp'] = hl.read_cpuinfo(logdir)
+    eng.load(SRC_PERF, text, p)
+    return True
 
 
 def load_gpu_source(cfg, eng):
@@ -116,6 +151,14 @@ def sofa_analyze(cfg, engine=None):
     own = False
     eng = engine or getattr(cfg, '_sofa_b200_engine', None)
     try:
+        if cfg.verbose and os.path.isfile(logdir + "cputrace.csv"):
+            if eng is None:
+                from .engine import CudaEngine
+                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
+                own = True
+            if own or engine is not None:
+                load_perf_source(cfg, eng)
+            cpu_profile(cfg, eng)
         if os.path.isfile(logdir + "gputrace.csv"):
             if eng is None:
                 from .engine import CudaEngine

@@ -143,6 +143,8 @@ def run_reference(logdir, overrides, analyze=True):
         with contextlib.redirect_stdout(io.StringIO()):
             features = ref_an.gpu_profile(logdir, cfg, df_gpu, features)
         feats = {str(n): float(v) for n, v in zip(features['name'], features['value'])}
+        with contextlib.redirect_stdout(io.StringIO()):
+            feats['__top10_names__'] = ref_an.get_top_k_events(cfg, df_gpu, 10)
     return feats
 
 

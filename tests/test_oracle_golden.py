@@ -37,6 +37,13 @@ def test_oracle_gpu_profile_matches_reference(name, tmp_path):
     for k, v in want.items():
         if k == "elapsed_time":
             continue
+        if k == "__top10_names__":
+            top = orc.top_k_events(df, 10)
+            vals = list(top.values)
+            for i, nm in enumerate(v):                 # tie order is unpinned (unstable sort)
+                if vals.count(vals[i]) == 1:
+                    assert top.index[i] == nm
+            continue
         assert float(feats[k]) == v, k
     with open(logdir + "comm.csv", "rb") as f:
         assert f.read() == golden_bytes(name, "comm.csv")
