@@ -118,6 +118,18 @@ int sofa_b200_emit_json(sofa_ctx*, int src, uint32_t stride, int32_t filter_idx,
 /* D2H of an output buffer (0 csv, 1 json, 2 names) */
 int sofa_b200_fetch(sofa_ctx*, int which, void* host_out, uint64_t cap);
 
+/* Overlapped transfers (pinned host memory): uploads run on an H2D copy stream (parse waits
+ * for its source's upload), fetches of output buffers 0/1 run on a D2H copy stream while the
+ * next emit fills the other half of a double buffer.  `ticket` identifies the fetch for
+ * sofa_b200_wait_fetch; sofa_b200_sync drains every stream of the ctx. */
+/* Optional device arena for csv/json outputs: every emit bump-allocates its buffer from it,
+ * so any number of asynchronous fetches can be in flight; sofa_b200_sync rewinds it. */
+int sofa_b200_set_output_arena(sofa_ctx*, uint64_t nbytes);
+int sofa_b200_upload_async(sofa_ctx*, int src, const void* text, uint64_t nbytes, uint64_t data_off);
+int sofa_b200_fetch_async(sofa_ctx*, int which, void* host_out, uint64_t cap, int32_t* ticket);
+int sofa_b200_wait_fetch(sofa_ctx*, int32_t ticket);
+int sofa_b200_sync(sofa_ctx*);
+
 /* Raw device column to host (parity tests). perf: 0 ts,1 event,2 dur (f64), 9 pid, 10 tid (i32);
  * gpu: 0 ts,2 dur,6 bw (f64), 5 payload (i64), 3 dev,10 tid,7 src,8 dst (i32), 4 kind (u8);
  * net: 0 ts (f64), 5 payload,7 src,8 dst (i64), 4 proto (u8). */

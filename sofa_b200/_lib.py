@@ -16,6 +16,7 @@ EXPORTS = [
     "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
     "sofa_b200_synth", "sofa_b200_text_fetch", "sofa_b200_mark", "sofa_b200_elapsed_ms",
+    "sofa_b200_upload_async", "sofa_b200_fetch_async", "sofa_b200_wait_fetch", "sofa_b200_sync", "sofa_b200_set_output_arena",
 ]
 
 
@@ -87,6 +88,11 @@ def load_lib():
     lib.sofa_b200_top_k.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p, u32p]
     lib.sofa_b200_cpu_profile.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p,
                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), u64p, u32p]
+    lib.sofa_b200_upload_async.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_uint64]
+    lib.sofa_b200_fetch_async.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int32)]
+    lib.sofa_b200_wait_fetch.argtypes = [vp, ctypes.c_int32]
+    lib.sofa_b200_sync.argtypes = [vp]
+    lib.sofa_b200_set_output_arena.argtypes = [vp, ctypes.c_uint64]
     lib.sofa_b200_mark.argtypes = [vp, ctypes.c_int]
     lib.sofa_b200_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.sofa_b200_set_profiling.argtypes = [vp, ctypes.c_int]

@@ -25,7 +25,7 @@ template <typename S>
 struct DevVizName {
     PerfVizName<S> raw; int id; DictView d;
     template <class K> __device__ __forceinline__ void gen(K& k) const {
-        if (id >= 0) { for (uint64_t j = d.off[id]; j < d.off[id + 1]; j++) k.put(d.blob[j]); }
+        if (id >= 0) put_span(k, d.blob + d.off[id], (int)(d.off[id + 1] - d.off[id]), true);
         else raw.gen(k);
     }
 };
@@ -34,8 +34,11 @@ __device__ __forceinline__ PerfRow load_perf(const SrcView& s, uint64_t row) {
     PerfRow r;
     r.ts = s.c.p.ts[row]; r.event = s.c.p.event[row]; r.dur = s.c.p.dur[row];
     r.pid = s.c.p.pid[row]; r.tid = s.c.p.tid[row];
-    const uint16_t* pc = s.c.p.pieces + row * 6;
-    r.evt_off = pc[0]; r.evt_len = pc[1]; r.sym_off = pc[2]; r.sym_len = pc[3]; r.dso_off = pc[4]; r.dso_len = pc[5];
+    const uint4 pv = __ldg(reinterpret_cast<const uint4*>(s.c.p.pieces) + row);       // 8 x u16
+    r.evt_off = (uint16_t)(pv.x & 0xffff); r.evt_len = (uint16_t)(pv.x >> 16);
+    r.sym_off = (uint16_t)(pv.y & 0xffff); r.sym_len = (uint16_t)(pv.y >> 16);
+    r.dso_off = (uint16_t)(pv.z & 0xffff); r.dso_len = (uint16_t)(pv.z >> 16);
+    r.va_len = (uint16_t)(pv.w & 0xffff); r.vb_len = (uint16_t)(pv.w >> 16);
     return r;
 }
 __device__ __forceinline__ GpuRow load_gpu(const SrcView& s, uint64_t row) {
@@ -61,7 +64,7 @@ __device__ __forceinline__ void with_row(const SrcView& s, uint64_t row, uint64_
         PerfRow r = load_perf(s, row);
         const char* line = s.text + s.c.p.line_start[row];
         RowVals v = vals_perf(r);
-        PerfName<const char*> full{line, r};
+        PerfName<const char*> full{line, r, true};
         if constexpr (VIZ) {
             DevVizName<const char*> ng{PerfVizName<const char*>{full}, s.viz_id ? s.viz_id[cand] : -1, s.dict};
             f(v, ng);
@@ -72,7 +75,7 @@ __device__ __forceinline__ void with_row(const SrcView& s, uint64_t row, uint64_
         GpuRow r = load_gpu(s, row);
         const char* line = s.text + s.c.g.line_start[row];
         RowVals v = vals_gpu(r, s.n_cudaproc);
-        GpuName<const char*> ng{line, r};
+        GpuName<const char*> ng{line, r, true};
         f(v, ng);
     } else {
         NetRow r = load_net(s, row);
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(256) k_viz_hash(SrcView src, uint64_t ncand, u
     uint64_t row = c * stride;
     PerfRow r = load_perf(src, row);
     const char* line = src.text + src.c.p.line_start[row];
-    PerfVizName<const char*> vz{PerfName<const char*>{line, r}};
+    PerfVizName<const char*> vz{PerfName<const char*>{line, r, true}};
     HashSink h; vz.gen(h);
     uint64_t key = 0;
     if (h.len >= 2 && h.c0 == '_' && h.c1 == 'Z') {
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(256) k_dict_len(SrcView src, const unsigned lo
     if (s >= cap || keys[s] == 0ull) return;
     uint64_t row = rows[s];
     PerfRow r = load_perf(src, row);
-    PerfVizName<const char*> vz{PerfName<const char*>{src.text + src.c.p.line_start[row], r}};
+    PerfVizName<const char*> vz{PerfName<const char*>{src.text + src.c.p.line_start[row], r, true}};
     LenSink l; vz.gen(l);
     atomicAdd(total, (unsigned long long)(l.len + 1));
     atomicAdd(n, 1u);
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(256) k_dict_write(SrcView src, const unsigned 
     if (s >= cap || keys[s] == 0ull) return;
     uint64_t row = rows[s];
     PerfRow r = load_perf(src, row);
-    PerfVizName<const char*> vz{PerfName<const char*>{src.text + src.c.p.line_start[row], r}};
+    PerfVizName<const char*> vz{PerfName<const char*>{src.text + src.c.p.line_start[row], r, true}};
     LenSink l; vz.gen(l);
     unsigned long long off = atomicAdd(cursor, (unsigned long long)(l.len + 1));
     RawWrite<char*> w{out + off, 0}; vz.gen(w);
@@ -253,6 +256,203 @@ __global__ void __launch_bounds__(256) k_viz_resolve(const uint64_t* __restrict_
         if (id < 0) report_error(err, c, E_FORMAT);
     }
     viz_id[c] = id;
+}
+
+}  // namespace sofa
+
+// ============================================================================ single-pass emit
+// One kernel per output: every thread formats its row ONCE into a private slot of dynamic
+// shared memory (st.shared byte stores), a block scan of the exact lengths packs the rows,
+// a decoupled look-back over per-block totals (dynamic block tickets, so predecessors are
+// always resident) yields the block's global byte offset, and each warp copies its rows out
+// with coalesced byte stores.  No size pass, no per-row length array.
+namespace sofa {
+
+struct SmemRef {
+    uint32_t a;
+    __device__ __forceinline__ void operator=(char ch) const {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"((int)(unsigned char)ch) : "memory");
+    }
+};
+struct SmemPtr {
+    uint32_t a;
+    __device__ __forceinline__ SmemRef operator[](int i) const { return SmemRef{a + (uint32_t)i}; }
+    __device__ __forceinline__ SmemPtr operator+(int i) const { return SmemPtr{a + (uint32_t)i}; }
+};
+
+struct FusedArgs {
+    uint64_t ncand; uint32_t stride; uint32_t fmask;
+    const uint8_t* mask; int bit;
+    const uint32_t* index;         // optional compacted candidate list (ncand = its length)
+    char* out; uint64_t cap;
+    unsigned long long* state;     // per block: flag << 62 | bytes   (1 = aggregate, 2 = inclusive prefix)
+    unsigned int* ticket;
+    unsigned long long* err;
+    unsigned long long* count;
+    unsigned long long* total;
+    unsigned int* overflow;
+    uint32_t slot_bytes;           // dynamic shared memory available for slots
+};
+
+constexpr unsigned long long LB_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// upper bound of the numeric part + exact escaped name length (+ CSV quoting flag)
+template <int FMT, class NG>
+__device__ __forceinline__ uint32_t emit_upper_bound(const RowVals& v, uint32_t fmask, const NG& ng, bool* special, int* bad) {
+    *special = false;
+    if (FMT == FMT_CSV) {
+        if (!v.valid) return 13;
+        CsvCount k; ng.gen(k);
+        *special = k.special;
+        uint32_t n = (uint32_t)k.len + (k.special ? 2u : 0u) + 13u;
+        for (int c = 0; c < 13; c++) {
+            if (c == 11) continue;
+            bool isf; double f; int64_t i;
+            col_value(v, c, fmask, &isf, &f, &i);
+            n += isf ? 28u : (uint32_t)len_i64(i);
+        }
+        return n;
+    } else {
+        if (!v.valid) return SOFA_JSON_FIXED + 13 * 4;
+        JsonCount k; ng.gen(k);
+        if (k.e.bad || k.e.need) *bad = 1;
+        uint32_t n = SOFA_JSON_FIXED + (uint32_t)k.len + 2u;
+        for (int c = 0; c < 13; c++) {
+            if (c == 11) continue;
+            bool isf; double f; int64_t i;
+            col_value(v, c, fmask, &isf, &f, &i);
+            n += isf ? 26u : (uint32_t)len_i64(i);
+        }
+        return n;
+    }
+}
+
+// candidate indices whose filter bit is set, ascending (two-pass compaction)
+__global__ void __launch_bounds__(256) k_mask_count(const uint8_t* __restrict__ mask, int bit, uint64_t n, uint64_t* blockoff) {
+    __shared__ uint32_t sm[33];
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t total;
+    block_excl_scan((i < n && ((mask[i] >> bit) & 1)) ? 1u : 0u, &total, sm);
+    if (threadIdx.x == 0) blockoff[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) k_mask_write(const uint8_t* __restrict__ mask, int bit, uint64_t n, const uint64_t* blockoff,
+                                                    uint32_t* __restrict__ index) {
+    __shared__ uint32_t sm[33];
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    bool f = i < n && ((mask[i] >> bit) & 1);
+    uint32_t total;
+    uint32_t ex = block_excl_scan(f ? 1u : 0u, &total, sm);
+    if (f) index[blockoff[blockIdx.x] + ex] = (uint32_t)i;
+}
+
+template <int KIND, int FMT>
+__global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs a) {
+    extern __shared__ __align__(16) unsigned char slots[];
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const uint32_t b = s_tile;
+    const uint64_t ci = (uint64_t)b * EMIT_TPB + threadIdx.x;
+    const bool inr = ci < a.ncand;
+    const uint64_t c = a.index ? (inr ? a.index[ci] : 0) : ci;
+    const bool sel = inr && (a.index != nullptr || a.mask == nullptr || ((a.mask[c] >> a.bit) & 1));
+    const uint64_t row = c * a.stride;
+    uint32_t ub = 0;
+    bool special = false;
+    int bad = 0;
+    if (sel) {
+        with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
+            ub = emit_upper_bound<FMT>(v, a.fmask, ng, &special, &bad);
+        });
+        if (bad) { report_error(a.err, row, E_UTF8); ub = 0; }
+    }
+    const bool live = sel && !bad;
+    uint32_t ub_total, cnt_total;
+    uint32_t slot_off = block_excl_scan(ub, &ub_total, sm);
+    block_excl_scan(live ? 1u : 0u, &cnt_total, sm);
+    const bool staged = ub_total <= a.slot_bytes;
+    uint32_t len = 0;
+    if (live) {
+        int l = 0;
+        with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
+            if (staged) {
+                SmemPtr dst{(uint32_t)__cvta_generic_to_shared(slots) + slot_off};
+                if constexpr (FMT == FMT_CSV) l = csv_row_write(v, a.fmask, ng, special, dst);
+                else l = json_row_write(v, a.fmask, ng, dst);
+            } else {
+                if constexpr (FMT == FMT_CSV) { bool sp; l = csv_row_len(v, a.fmask, ng, &sp); }
+                else l = json_row_len(v, a.fmask, ng);
+            }
+        });
+        if (l < 0) { report_error(a.err, row, l == -2 ? E_UTF8 : E_FORMAT); l = 0; }
+        len = (uint32_t)l;
+    }
+    uint32_t total;
+    uint32_t ex = block_excl_scan(len, &total, sm);
+    if (threadIdx.x < 32) {
+        // decoupled look-back, one warp: 32 predecessors per probe
+        const uint32_t lane = threadIdx.x;
+        unsigned long long base = 0;
+        if (b > 0) {
+            if (lane == 0) st_release_u64(&a.state[b], (1ull << 62) | (unsigned long long)total);
+            long long j = (long long)b - 1;
+            while (true) {
+                long long idx = j - (long long)lane;
+                unsigned long long v = idx >= 0 ? ld_acquire_u64(&a.state[idx]) : (2ull << 62);
+                unsigned int f = (unsigned int)(v >> 62);
+                unsigned int pmask = __ballot_sync(0xffffffffu, f == 2);
+                unsigned int emask = __ballot_sync(0xffffffffu, f == 0);
+                int first = pmask ? (__ffs(pmask) - 1) : 32;
+                unsigned int need = first >= 31 ? 0xffffffffu : ((1u << (first + 1)) - 1u);
+                if (emask & need) continue;                      // a needed predecessor has not published yet
+                unsigned long long contrib = ((int)lane <= first) ? (v & LB_MASK) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                base += contrib;
+                if (first < 32) break;
+                j -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_release_u64(&a.state[b], (2ull << 62) | (base + total));
+            s_base = base;
+            if (cnt_total) atomicAdd(a.count, (unsigned long long)cnt_total);
+            if ((uint64_t)b + 1 == (a.ncand + EMIT_TPB - 1) / EMIT_TPB) *a.total = base + total;
+        }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+    if (base + total > a.cap) { if (threadIdx.x == 0) atomicOr(a.overflow, 1u); return; }
+    if (staged) {
+        // warp-cooperative copy-out: the warp walks its 32 rows, lanes stride the bytes
+        const uint32_t lane = lane_id();
+        for (int r = 0; r < 32; r++) {
+            uint32_t rl = __shfl_sync(0xffffffffu, len, r);
+            if (rl == 0) continue;
+            uint32_t so = __shfl_sync(0xffffffffu, slot_off, r);
+            uint32_t eo = __shfl_sync(0xffffffffu, ex, r);
+            char* g = a.out + base + eo;
+            const unsigned char* s = slots + so;
+            for (uint32_t i = lane; i < rl; i += 32) g[i] = (char)s[i];
+        }
+    } else if (len) {
+        char* dst = a.out + base + ex;
+        with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
+            if constexpr (FMT == FMT_CSV) csv_row_write(v, a.fmask, ng, special, dst);
+            else json_row_write(v, a.fmask, ng, dst);
+        });
+    }
 }
 
 }  // namespace sofa

@@ -14,7 +14,7 @@
 namespace sofa {
 
 struct PerfCols {
-    double *ts, *event, *dur; int32_t *pid, *tid; uint64_t* line_start; uint16_t* pieces;   // 6 u16 per row
+    double *ts, *event, *dur; int32_t *pid, *tid; uint64_t* line_start; uint16_t* pieces;   // 8 u16 per row (one 16-byte vector)
 };
 struct GpuCols {
     double *ts, *dur, *bw; int64_t* payload; int32_t *dev, *tid, *src, *dst; uint8_t *kind, *bwf;
@@ -157,8 +157,10 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
                     cols.p.ts[row] = r.ts; cols.p.event[row] = r.event; cols.p.dur[row] = r.dur;
                     cols.p.pid[row] = r.pid; cols.p.tid[row] = r.tid;
                     cols.p.line_start[row] = s0 + ls;
-                    uint16_t* pc = cols.p.pieces + row * 6;
-                    pc[0] = r.evt_off; pc[1] = r.evt_len; pc[2] = r.sym_off; pc[3] = r.sym_len; pc[4] = r.dso_off; pc[5] = r.dso_len;
+                    uint4 pv;
+                    pv.x = r.evt_off | ((uint32_t)r.evt_len << 16); pv.y = r.sym_off | ((uint32_t)r.sym_len << 16);
+                    pv.z = r.dso_off | ((uint32_t)r.dso_len << 16); pv.w = r.va_len | ((uint32_t)r.vb_len << 16);
+                    reinterpret_cast<uint4*>(cols.p.pieces)[row] = pv;
                 }
             } else if (KIND == SRC_GPU) {
                 GpuRow r;

@@ -248,24 +248,54 @@ SOFA_HD int parse_i64(S s, int n, int64_t* out) {
 }
 
 // ----------------------------------------------------------------------------- integer -> text
+// 32-bit fast paths: almost every value in a trace row fits 32 bits, and 32-bit
+// divide-by-constant is a multiply + shift on the GPU (64-bit is several instructions).
+SOFA_HD int ndigits_u32(uint32_t v) {
+    if (v < 10u) return 1;
+    if (v < 100u) return 2;
+    if (v < 1000u) return 3;
+    if (v < 10000u) return 4;
+    if (v < 100000u) return 5;
+    if (v < 1000000u) return 6;
+    if (v < 10000000u) return 7;
+    if (v < 100000000u) return 8;
+    if (v < 1000000000u) return 9;
+    return 10;
+}
 SOFA_HD int ndigits_u64(uint64_t v) {
-    int n = 1;
-    if (v >= 10000000000000000ull) { v /= 10000000000000000ull; n += 16; }
-    if (v >= 100000000ull) { v /= 100000000ull; n += 8; }
-    if (v >= 10000ull) { v /= 10000ull; n += 4; }
-    if (v >= 100ull) { v /= 100ull; n += 2; }
-    if (v >= 10ull) n += 1;
-    return n;
+    if ((v >> 32) == 0) return ndigits_u32((uint32_t)v);
+    if (v < 100000000000000ull) {                 // 10..14 digits
+        uint32_t hi = (uint32_t)(v / 100000ull);  // < 1e9
+        return 5 + ndigits_u32(hi);
+    }
+    uint64_t hi = v / 1000000000ull;              // >= 1e5
+    return 9 + ndigits_u32((uint32_t)(hi > 0xffffffffull ? 0xffffffffu : hi)) + (hi > 9999999999ull ? 1 : 0);
 }
 template <typename O>
-SOFA_HD int fmt_u64(uint64_t v, O out) {
-    int n = ndigits_u64(v);
-    for (int i = n - 1; i >= 0; i--) { out[i] = (char)('0' + (v % 10)); v /= 10; }
+SOFA_HD void fmt_u32_pad(uint32_t v, int width, O out) {       // zero padded, exactly `width` (<= 10)
+    for (int i = width - 1; i >= 0; i--) { uint32_t q = v / 10u; out[i] = (char)('0' + (v - q * 10u)); v = q; }
+}
+template <typename O>
+SOFA_HD int fmt_u32(uint32_t v, O out) {
+    int n = ndigits_u32(v);
+    fmt_u32_pad(v, n, out);
     return n;
 }
 template <typename O>
 SOFA_HD void fmt_u64_pad(uint64_t v, int width, O out) {       // zero padded, exactly `width`
-    for (int i = width - 1; i >= 0; i--) { out[i] = (char)('0' + (v % 10)); v /= 10; }
+    while (width > 9) {
+        uint64_t q = v / 1000000000ull;
+        fmt_u32_pad((uint32_t)(v - q * 1000000000ull), 9, out + (width - 9));
+        v = q; width -= 9;
+    }
+    fmt_u32_pad((uint32_t)v, width, out);
+}
+template <typename O>
+SOFA_HD int fmt_u64(uint64_t v, O out) {
+    if ((v >> 32) == 0) return fmt_u32((uint32_t)v, out);
+    int n = ndigits_u64(v);
+    fmt_u64_pad(v, n, out);
+    return n;
 }
 template <typename O>
 SOFA_HD int fmt_i64(int64_t v, O out) {

@@ -47,6 +47,30 @@ struct IngestCfg {
 
 struct Tok { int a, b; };
 
+// Feed the bytes p[0..len) to a sink.  On the device, global-memory spans are read as aligned
+// 64-bit words (8x fewer load instructions than byte loads; the text buffer is padded, so the
+// over-read of the last word is safe).  `wide` is false for shared-memory / local spans.
+template <class K>
+SOFA_HD void put_span(K& k, const char* p, int len, bool wide) {
+#if defined(__CUDA_ARCH__)
+    if (wide && len > 0) {
+        unsigned long long a = (unsigned long long)p;
+        const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a & ~7ull);
+        int sh = (int)(a & 7);
+        unsigned long long cur = __ldg(w++) >> (8 * sh);
+        int avail = 8 - sh;
+        for (int i = 0; i < len; i++) {
+            if (avail == 0) { cur = __ldg(w++); avail = 8; }
+            k.put((char)(cur & 0xff));
+            cur >>= 8; avail--;
+        }
+        return;
+    }
+#endif
+    (void)wide;
+    for (int i = 0; i < len; i++) k.put(p[i]);
+}
+
 // str.split() with no argument (ASCII whitespace); returns number of tokens, capped at maxt.
 template <typename S>
 SOFA_HD int tokenize(S s, int n, Tok* t, int maxt) {
@@ -72,6 +96,9 @@ struct PerfRow {
     double ts, event, dur;
     int32_t pid, tid;
     uint16_t evt_off, evt_len, sym_off, sym_len, dso_off, dso_len;   // relative to the line start
+    // viz name (:1811-1816) = sym[0:va_len) + dso[0:vb_len) in the common case where the event
+    // token holds neither ']' nor '+'; va_len == 0xffff selects the generic slicer.
+    uint16_t va_len, vb_len;
 };
 
 template <typename S>
@@ -141,19 +168,38 @@ SOFA_HD int parse_perf(S s, int n, const IngestCfg& c, PerfRow* r) {
     r->evt_off = (uint16_t)t[3 + sh].a; r->evt_len = (uint16_t)(t[3 + sh].b - t[3 + sh].a);
     r->sym_off = (uint16_t)t[5 + sh].a; r->sym_len = (uint16_t)(t[5 + sh].b - t[5 + sh].a);
     r->dso_off = (uint16_t)t[6 + sh].a; r->dso_len = (uint16_t)(t[6 + sh].b - t[6 + sh].a);
+    {   // precompute the viz slice: name = '[' evt ']' sym dso ; [find(']')+1 : find('+')] cut at '@'
+        bool exotic = false;
+        for (int i = 0; i < r->evt_len; i++) { char ch = s[r->evt_off + i]; if (ch == ']' || ch == '+') exotic = true; }
+        if (exotic) { r->va_len = 0xffff; r->vb_len = 0; }
+        else {
+            int sl = r->sym_len, dl = r->dso_len;
+            int plus = -1;
+            for (int i = 0; i < sl && plus < 0; i++) if (s[r->sym_off + i] == '+') plus = i;
+            for (int i = 0; i < dl && plus < 0; i++) if (s[r->dso_off + i] == '+') plus = sl + i;
+            int b = plus >= 0 ? plus : sl + dl - 1;           // [a:-1] when there is no '+'
+            if (b < 0) b = 0;
+            int va = b < sl ? b : sl, vb = b > sl ? b - sl : 0;
+            int at = -1;
+            for (int i = 0; i < va && at < 0; i++) if (s[r->sym_off + i] == '@') at = i;
+            if (at >= 0) { va = at; vb = 0; }
+            else { for (int i = 0; i < vb && at < 0; i++) if (s[r->dso_off + i] == '@') at = i; if (at >= 0) vb = at; }
+            r->va_len = (uint16_t)va; r->vb_len = (uint16_t)vb;
+        }
+    }
     return E_OK;
 }
 
 // name = '[%s]' % evt.replace('-','_') + sym + dso   (:116,121)
 template <typename S>
 struct PerfName {
-    S line; PerfRow r;
+    S line; PerfRow r; bool wide;
     template <class K> SOFA_HD void gen(K& k) const {
         k.put('[');
         for (int i = 0; i < r.evt_len; i++) { char ch = line[r.evt_off + i]; k.put(ch == '-' ? '_' : ch); }
         k.put(']');
-        for (int i = 0; i < r.sym_len; i++) k.put(line[r.sym_off + i]);
-        for (int i = 0; i < r.dso_len; i++) k.put(line[r.dso_off + i]);
+        put_span(k, line + r.sym_off, r.sym_len, wide);
+        put_span(k, line + r.dso_off, r.dso_len, wide);
     }
 };
 
@@ -179,6 +225,11 @@ template <typename S>
 struct PerfVizName {
     PerfName<S> full;
     template <class K> SOFA_HD void gen(K& k) const {
+        if (full.r.va_len != 0xffff) {
+            put_span(k, full.line + full.r.sym_off, full.r.va_len, full.wide);
+            put_span(k, full.line + full.r.dso_off, full.r.vb_len, full.wide);
+            return;
+        }
         FindSink f; full.gen(f);
         int len = f.pos;
         int a = f.first_rb + 1;                         // find()==-1 -> 0
@@ -312,13 +363,16 @@ template <class K> SOFA_HD void put_i64(K& k, int64_t v) {
     for (int i = 0; i < n; i++) k.put(b[i]);
 }
 
+template <class K>
+struct QuoteFilter { K* k; SOFA_HD void put(char ch) { if (ch != '"') k->put(ch); } };
 template <typename S>
 struct GpuName {
-    S line; GpuRow r;
+    S line; GpuRow r; bool wide;
     template <class K> SOFA_HD void gen(K& k) const {
         if (r.dev != -1) { put_lit(k, "[gpu"); put_i64(k, r.dev); k.put(']'); }        // :325-326
         if (r.kind == 0) {
-            for (int i = 0; i < r.name_len; i++) { char ch = line[r.name_off + i]; if (ch != '"') k.put(ch); }
+            QuoteFilter<K> q{&k};
+            put_span(q, line + r.name_off, r.name_len, wide);
         } else if (r.kind == 10) {
             put_lit(k, "[CUDA_COPY_P2P]from_gpu"); put_i64(k, r.src); put_lit(k, "_to_gpu"); put_i64(k, r.dst);
             k.put('_'); put_i64(k, r.payload); k.put('B');
@@ -549,72 +603,70 @@ struct JsonEsc {
         return 0;
     }
 };
+SOFA_HD bool json_plain(unsigned char b) { return b >= 0x20 && b < 0x7f && b != '"' && b != '\\'; }
 struct JsonCount {
     JsonEsc e; int len;
     SOFA_HD JsonCount() : len(0) {}
-    SOFA_HD void put(char ch) { char b[12]; len += e.feed((unsigned char)ch, b); }
+    SOFA_HD void put(char ch) {
+        if (e.need == 0 && json_plain((unsigned char)ch)) { len++; return; }
+        char b[12]; len += e.feed((unsigned char)ch, b);
+    }
 };
 template <typename O>
 struct JsonWrite {
     O out; int n; JsonEsc e;
-    SOFA_HD void put(char ch) { char b[12]; int l = e.feed((unsigned char)ch, b); for (int i = 0; i < l; i++) out[n++] = b[i]; }
+    SOFA_HD void put(char ch) {
+        if (e.need == 0 && json_plain((unsigned char)ch)) { out[n++] = ch; return; }
+        char b[12]; int l = e.feed((unsigned char)ch, b); for (int i = 0; i < l; i++) out[n++] = b[i];
+    }
 };
 
-// key text that precedes column c in a record (x=timestamp, y=duration renamed, :351-355)
-SOFA_HD const char* json_key(int c) {
-    switch (c) {
-        case 0: return "{\"x\": ";
-        case 1: return ", \"event\": ";
-        case 2: return ", \"y\": ";
-        case 3: return ", \"deviceId\": ";
-        case 4: return ", \"copyKind\": ";
-        case 5: return ", \"payload\": ";
-        case 6: return ", \"bandwidth\": ";
-        case 7: return ", \"pkt_src\": ";
-        case 8: return ", \"pkt_dst\": ";
-        case 9: return ", \"pid\": ";
-        case 10: return ", \"tid\": ";
-        case 11: return ", \"name\": ";
-        default: return ", \"category\": ";
-    }
-}
-SOFA_HD int json_key_len(int c) {
-    const int L[13] = {6, 11, 7, 14, 14, 13, 15, 13, 13, 9, 9, 10, 14};
-    return L[c];
-}
+// Record text: {"x": V, "event": V, "y": V, "deviceId": V, ... "name": "S", "category": V}
+// (x=timestamp, y=duration renamed, :351-355).  Keys are written with fully unrolled
+// constant stores (one store per byte, no loads).
+#define SOFA_JKEY(lit) do { const char k_[] = lit; _Pragma("unroll") for (int i_ = 0; i_ < (int)sizeof(k_) - 1; i_++) out[n + i_] = k_[i_]; n += (int)sizeof(k_) - 1; } while (0)
+#define SOFA_JNUM(c) do { \
+        if (!v.valid) { out[n] = 'n'; out[n + 1] = 'u'; out[n + 2] = 'l'; out[n + 3] = 'l'; n += 4; } \
+        else { bool isf; double f; int64_t i; col_value(v, c, fmask, &isf, &f, &i); \
+               if (isf) { int l = json_double(f, out + n); if (l < 0) return -1; n += l; } else n += fmt_i64(i, out + n); } \
+    } while (0)
 
 // A record is emitted as ", " + {...}; the series writer drops the first two bytes.
 // returns length, or -1 (unformattable number) / -2 (invalid UTF-8)
 template <class NG, typename O>
 SOFA_HD int json_row_write(const RowVals& v, uint32_t fmask, const NG& ng, O out) {
     int n = 0;
-    out[n++] = ','; out[n++] = ' ';
-    for (int c = 0; c < 13; c++) {
-        const char* k = json_key(c);
-        for (int i = 0; k[i]; i++) out[n++] = k[i];
-        if (!v.valid) { out[n++] = 'n'; out[n++] = 'u'; out[n++] = 'l'; out[n++] = 'l'; continue; }
-        if (c == 11) {
-            out[n++] = '"';
-            JsonWrite<O> w{out + n, 0, JsonEsc()}; ng.gen(w);
-            if (w.e.bad || w.e.need) return -2;
-            n += w.n;
-            out[n++] = '"';
-        } else {
-            bool isf; double f; int64_t i;
-            col_value(v, c, fmask, &isf, &f, &i);
-            if (isf) { int l = json_double(f, out + n); if (l < 0) return -1; n += l; }
-            else n += fmt_i64(i, out + n);
-        }
+    SOFA_JKEY(", {\"x\": "); SOFA_JNUM(0);
+    SOFA_JKEY(", \"event\": "); SOFA_JNUM(1);
+    SOFA_JKEY(", \"y\": "); SOFA_JNUM(2);
+    SOFA_JKEY(", \"deviceId\": "); SOFA_JNUM(3);
+    SOFA_JKEY(", \"copyKind\": "); SOFA_JNUM(4);
+    SOFA_JKEY(", \"payload\": "); SOFA_JNUM(5);
+    SOFA_JKEY(", \"bandwidth\": "); SOFA_JNUM(6);
+    SOFA_JKEY(", \"pkt_src\": "); SOFA_JNUM(7);
+    SOFA_JKEY(", \"pkt_dst\": "); SOFA_JNUM(8);
+    SOFA_JKEY(", \"pid\": "); SOFA_JNUM(9);
+    SOFA_JKEY(", \"tid\": "); SOFA_JNUM(10);
+    SOFA_JKEY(", \"name\": ");
+    if (!v.valid) { out[n] = 'n'; out[n + 1] = 'u'; out[n + 2] = 'l'; out[n + 3] = 'l'; n += 4; }
+    else {
+        out[n++] = '"';
+        JsonWrite<O> w{out + n, 0, JsonEsc()}; ng.gen(w);
+        if (w.e.bad || w.e.need) return -2;
+        n += w.n;
+        out[n++] = '"';
     }
+    SOFA_JKEY(", \"category\": "); SOFA_JNUM(12);
     out[n++] = '}';
     return n;
 }
+// total bytes of the 13 key texts + ", " + "{" ... "}" framing
+#define SOFA_JSON_FIXED (2 + 6 + 11 + 7 + 14 + 14 + 13 + 15 + 13 + 13 + 9 + 9 + 10 + 14 + 1)
 template <class NG>
 SOFA_HD int json_row_len(const RowVals& v, uint32_t fmask, const NG& ng) {
-    int n = 2 + 1;                                   // ", " and '}'
+    int n = SOFA_JSON_FIXED;
+    if (!v.valid) return n + 13 * 4;
     for (int c = 0; c < 13; c++) {
-        n += json_key_len(c);
-        if (!v.valid) { n += 4; continue; }
         if (c == 11) {
             JsonCount k; ng.gen(k);
             if (k.e.bad || k.e.need) return -2;

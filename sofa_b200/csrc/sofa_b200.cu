@@ -50,6 +50,7 @@ struct Source {
     IngestCfg cfg;
     DevBuf mhz;
     DevBuf mask; uint32_t mask_stride = 0; int nkw = 0;      // filter masks
+    uint64_t filter_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     DevBuf vizhash, viz_id; uint32_t viz_stride = 0; bool viz_ready = false;
     DevBuf dict_hash, dict_off, dict_blob; int dict_n = 0;
 };
@@ -61,6 +62,22 @@ struct sofa_ctx {
     cudaStream_t stream = nullptr;
     Source src[3];
     DevBuf out[3]; uint64_t out_n[3] = {0, 0, 0};
+    // overlapped transfers: copy streams, the idle halves of the csv/json double buffers and the
+    // D2H-complete event of each half
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    DevBuf out_alt[2];
+    cudaEvent_t out_ev[2] = {nullptr, nullptr}, out_alt_ev[2] = {nullptr, nullptr};
+    bool out_busy[2] = {false, false}, out_alt_busy[2] = {false, false};
+    cudaEvent_t up_ev[3] = {nullptr, nullptr, nullptr};
+    bool up_pending[3] = {false, false, false};
+    cudaEvent_t fetch_ev[16]; bool fetch_used[16]; int fetch_next = 0;
+    DevBuf arena; uint64_t arena_cur = 0; bool arena_on = false;
+    // small host<->device traffic goes through mapped pinned memory + a copy kernel, never the
+    // DMA engines (a tiny read-back queued behind a multi-GB transfer would stall the host)
+    unsigned char* stage_h = nullptr; unsigned char* stage_d = nullptr; size_t stage_cap = 8u << 20, stage_cur = 0;
+    struct SmallXfer { void* dst; size_t off, n; };
+    std::vector<SmallXfer> pending;
+    char* out_ptr[3] = {nullptr, nullptr, nullptr};
     DevBuf tiles, rowlen, blockoff, scratch, ftable, keys, rows;
     DevBuf sk0, sv0, sk1, sv1, hist, segs, sums, small;
     unsigned long long* d_err = nullptr;        // [0] error slot, [1] counter, [2..9] filter counts, [10] misc
@@ -84,6 +101,41 @@ struct sofa_ctx {
 #define FAIL(code, msg) do { g_last_error = (msg); return (code); } while (0)
 #define ENSURE(buf, n) do { if ((buf).ensure(n)) FAIL(SOFA_ERR_CUDA, "cudaMalloc failed (" #buf ")"); } while (0)
 
+#define CK_S(call) do { int r_s_ = (call); if (r_s_) return r_s_; } while (0)
+
+__global__ void k_copy_small(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static int stream_sync(sofa_ctx* c) {
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& x : c->pending) memcpy(x.dst, c->stage_h + x.off, x.n);
+    c->pending.clear();
+    c->stage_cur = 0;
+    return 0;
+}
+static int small_d2h(sofa_ctx* c, void* host_dst, const void* dev_src, size_t n) {
+    if (n == 0) return 0;
+    if (n > c->stage_cap / 2) { CK(cudaMemcpyAsync(host_dst, dev_src, n, cudaMemcpyDeviceToHost, c->stream)); return 0; }
+    size_t off = (c->stage_cur + 15) & ~(size_t)15;
+    if (off + n > c->stage_cap) { CK_S(stream_sync(c)); off = 0; }
+    unsigned g = (unsigned)((n + 255) / 256); if (g > 64) g = 64;
+    k_copy_small<<<g, 256, 0, c->stream>>>(c->stage_d + off, (const unsigned char*)dev_src, n);
+    c->pending.push_back({host_dst, off, n});
+    c->stage_cur = off + n;
+    return 0;
+}
+static int small_h2d(sofa_ctx* c, void* dev_dst, const void* host_src, size_t n) {
+    if (n == 0) return 0;
+    if (n > c->stage_cap / 2) { CK(cudaMemcpyAsync(dev_dst, host_src, n, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); return 0; }
+    size_t off = (c->stage_cur + 15) & ~(size_t)15;
+    if (off + n > c->stage_cap) { CK_S(stream_sync(c)); off = 0; }
+    memcpy(c->stage_h + off, host_src, n);
+    unsigned g = (unsigned)((n + 255) / 256); if (g > 64) g = 64;
+    k_copy_small<<<g, 256, 0, c->stream>>>((unsigned char*)dev_dst, c->stage_d + off, n);
+    c->stage_cur = off + n;
+    return 0;
+}
+
 static cudaEvent_t get_event(sofa_ctx* c) {
     if (!c->pool.empty()) { cudaEvent_t e = c->pool.back(); c->pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -100,7 +152,7 @@ struct LaunchTimer {
 
 static int drain_events(sofa_ctx* c) {
     if (c->events.empty()) return 0;
-    CK(cudaStreamSynchronize(c->stream));
+    CK_S(stream_sync(c));
     for (auto& ev : c->events) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ev.a, ev.b);
@@ -113,8 +165,8 @@ static int drain_events(sofa_ctx* c) {
 
 static int check_kernel_error(sofa_ctx* c, const char* what) {
     unsigned long long e = ~0ull;
-    CK(cudaMemcpyAsync(&e, c->d_err, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK_S(small_d2h(c, &e, c->d_err, 8));
+    CK_S(stream_sync(c));
     CK(cudaGetLastError());
     if (e != ~0ull) {
         c->err_row = e >> 8; c->err_code = (int)(e & 0xff);
@@ -171,7 +223,7 @@ static int alloc_cols(sofa_ctx* c, int k, uint64_t n) {
     if (k == SRC_PERF) {
         ENSURE(s.cols[PC_TS], m * 8); ENSURE(s.cols[PC_EVENT], m * 8); ENSURE(s.cols[PC_DUR], m * 8);
         ENSURE(s.cols[PC_PID], m * 4); ENSURE(s.cols[PC_TID], m * 4); ENSURE(s.cols[PC_LS], m * 8);
-        ENSURE(s.cols[PC_PIECES], m * 12);
+        ENSURE(s.cols[PC_PIECES], m * 16);
     } else if (k == SRC_GPU) {
         ENSURE(s.cols[GC_TS], m * 8); ENSURE(s.cols[GC_DUR], m * 8); ENSURE(s.cols[GC_BW], m * 8);
         ENSURE(s.cols[GC_PAYLOAD], m * 8); ENSURE(s.cols[GC_DEV], m * 4); ENSURE(s.cols[GC_TID], m * 4);
@@ -185,6 +237,45 @@ static int alloc_cols(sofa_ctx* c, int k, uint64_t n) {
 }
 
 static inline uint64_t cdiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// Flip the double buffer of output slot `s` (0 csv, 1 json) before an emit overwrites it: the
+// emit goes into the half whose last asynchronous fetch is oldest, after that fetch completed.
+static int flip_output(sofa_ctx* c, int s) {
+    if (s > 1 || c->arena_on) return 0;
+    if (!c->out_busy[s]) return 0;                 // current half was never fetched asynchronously
+    std::swap(c->out[s], c->out_alt[s]);
+    std::swap(c->out_ev[s], c->out_alt_ev[s]);
+    std::swap(c->out_busy[s], c->out_alt_busy[s]);
+    if (c->out_busy[s]) { CK(cudaEventSynchronize(c->out_ev[s])); c->out_busy[s] = false; }
+    return 0;
+}
+// Buffer for an emit into output slot s with capacity `cap`: from the arena (bump allocation;
+// wraps after draining the D2H stream) when one is set, else the slot's own (double) buffer.
+static int out_alloc(sofa_ctx* c, int s, uint64_t cap, char** p) {
+    if (c->arena_on && s < 2) {
+        uint64_t need = (cap + 64 + 255) & ~255ull;
+        if (c->arena_cur + need > c->arena.cap) {
+            CK(cudaStreamSynchronize(c->d2h));
+            c->arena_cur = 0;
+            if (need > c->arena.cap) { CK_S(stream_sync(c)); ENSURE(c->arena, need); }
+        }
+        *p = c->arena.as<char>() + c->arena_cur;
+        c->out_ptr[s] = *p;
+        return 0;
+    }
+    ENSURE(c->out[s], cap + 64);
+    *p = c->out[s].as<char>();
+    c->out_ptr[s] = *p;
+    return 0;
+}
+static void out_commit(sofa_ctx* c, int s, uint64_t total) {
+    c->out_n[s] = total;
+    if (c->arena_on && s < 2) c->arena_cur += (total + 64 + 255) & ~255ull;
+}
+static int wait_upload(sofa_ctx* c, int k) {
+    if (c->up_pending[k]) { CK(cudaStreamWaitEvent(c->stream, c->up_ev[k], 0)); c->up_pending[k] = false; }
+    return 0;
+}
 
 extern "C" {
 
@@ -210,6 +301,13 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     c->device = device;
     memset(&c->stats, 0, sizeof c->stats);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->out_ev[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_alt_ev[i], cudaEventDisableTiming)); }
+    for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 16; i++) { CK(cudaEventCreateWithFlags(&c->fetch_ev[i], cudaEventDisableTiming)); c->fetch_used[i] = false; }
+    CK(cudaHostAlloc((void**)&c->stage_h, c->stage_cap, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&c->stage_d, c->stage_h, 0));
     CK(cudaMalloc(&c->d_err, 8 * 16));
     CK(cudaMalloc(&c->d_flags, 4 * 8));
     // dynamic shared memory opt-in for the parse kernels
@@ -218,6 +316,12 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaFuncSetAttribute(k_parse<SRC_PERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_parse<SRC_GPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_parse<SRC_NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_PERF, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_PERF, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_GPU, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_GPU, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_NET, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_NET, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     *out = c;
     return 0;
 }
@@ -226,6 +330,11 @@ int sofa_b200_destroy(sofa_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
+    if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
+    for (int i = 0; i < 2; i++) { if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); if (c->out_alt_ev[i]) cudaEventDestroy(c->out_alt_ev[i]); c->out_alt[i].release(); }
+    for (int i = 0; i < 3; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
+    for (int i = 0; i < 16; i++) cudaEventDestroy(c->fetch_ev[i]);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& e : c->pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
@@ -239,8 +348,9 @@ int sofa_b200_destroy(sofa_ctx* c) {
     c->tiles.release(); c->rowlen.release(); c->blockoff.release(); c->scratch.release(); c->ftable.release();
     c->keys.release(); c->rows.release();
     c->sk0.release(); c->sv0.release(); c->sk1.release(); c->sv1.release(); c->hist.release(); c->segs.release();
-    c->sums.release(); c->small.release();
+    c->sums.release(); c->small.release(); c->arena.release();
     cudaFree(c->d_err); cudaFree(c->d_flags);
+    if (c->stage_h) cudaFreeHost(c->stage_h);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -261,7 +371,7 @@ int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint
     ENSURE(s.text, nbytes + 64);
     if (nbytes) CK(cudaMemcpyAsync(s.text.p, text, nbytes, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(s.text.as<char>() + nbytes, '\n', 64, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK_S(stream_sync(c));
     c->stats.h2d_bytes += nbytes;
     s.nbytes = nbytes; s.data_off = data_off; s.uploaded = true; s.parsed = false; s.viz_ready = false; s.n_rows = 0;
     s.mask_stride = 0; s.nkw = 0;
@@ -275,6 +385,7 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     Source& s = c->src[k];
     if (!s.uploaded) FAIL(SOFA_ERR_STATE, "parse: nothing uploaded for this source");
     CK(cudaSetDevice(c->device));
+    c->pending.clear(); c->stage_cur = 0;
     IngestCfg cfg;
     cfg.time_base = p->time_base; cfg.t_offset = p->t_offset; cfg.absolute_timestamp = p->absolute_timestamp;
     cfg.perf_has_cycles = p->perf_has_cycles; cfg.n_mhz = p->n_mhz > 0 ? p->n_mhz : 1;
@@ -287,17 +398,18 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
         FAIL(SOFA_ERR_ARG, "parse: gpu trace needs Start, Duration and Name columns");
     ENSURE(s.mhz, 16 * (size_t)cfg.n_mhz + 16);
     if (p->n_mhz > 0 && p->mhz_xp && p->mhz_fp) {
-        CK(cudaMemcpyAsync(s.mhz.p, p->mhz_xp, 8 * (size_t)cfg.n_mhz, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.mhz.as<double>() + cfg.n_mhz, p->mhz_fp, 8 * (size_t)cfg.n_mhz, cudaMemcpyHostToDevice, c->stream));
+        CK_S(small_h2d(c, s.mhz.p, p->mhz_xp, 8 * (size_t)cfg.n_mhz));
+        CK_S(small_h2d(c, s.mhz.as<double>() + cfg.n_mhz, p->mhz_fp, 8 * (size_t)cfg.n_mhz));
     } else {
         double d[2] = {0.0, 3000.0};
-        CK(cudaMemcpyAsync(s.mhz.p, &d[0], 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.mhz.as<double>() + 1, &d[1], 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK_S(small_h2d(c, s.mhz.p, &d[0], 8));
+        CK_S(small_h2d(c, s.mhz.as<double>() + 1, &d[1], 8));
+        CK_S(stream_sync(c));
     }
     cfg.mhz_xp = s.mhz.as<double>(); cfg.mhz_fp = s.mhz.as<double>() + cfg.n_mhz;
     s.cfg = cfg;
     s.parsed = false; s.viz_ready = false; s.mask_stride = 0;
+    if (wait_upload(c, k)) return SOFA_ERR_CUDA;
     uint64_t begin = s.data_off, end = s.nbytes;
     if (end <= begin) { s.n_rows = 0; s.parsed = true; if (n_rows) *n_rows = 0; return 0; }
     uint32_t tile = pick_tile_bytes(k);
@@ -309,9 +421,9 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
         s.text.as<char>(), begin, end, tile, c->tiles.as<uint64_t>(), c->d_flags)));
     LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(c->tiles.as<uint64_t>(), ntiles)));
     uint64_t total = 0; unsigned int cr = 0;
-    CK(cudaMemcpyAsync(&total, c->tiles.as<uint64_t>() + ntiles, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&cr, c->d_flags, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK_S(small_d2h(c, &total, c->tiles.as<uint64_t>() + ntiles, 8));
+    CK_S(small_d2h(c, &cr, c->d_flags, 4));
+    CK_S(stream_sync(c));
     CK(cudaGetLastError());
     if (cr) { c->err_row = 0; c->err_code = E_CR; FAIL(SOFA_ERR_ROW, "parse: carriage return in trace text (not supported)"); }
     if (alloc_cols(c, k, total)) return SOFA_ERR_CUDA;
@@ -339,6 +451,7 @@ static int need_parsed(sofa_ctx* c, int k) {
     if (!c || k < 0 || k > 2) FAIL(SOFA_ERR_ARG, "bad source");
     if (!c->src[k].parsed) FAIL(SOFA_ERR_STATE, "source not parsed");
     CK(cudaSetDevice(c->device));
+    c->pending.clear(); c->stage_cur = 0;          // drop read-backs orphaned by an earlier failed call
     return 0;
 }
 
@@ -353,8 +466,8 @@ int sofa_b200_row_flags(sofa_ctx* c, int k, uint32_t stride, uint32_t* flags) {
     SrcView v = make_view(c, k, false);
     if (k == SRC_GPU) LAUNCH(c, K_FLAGS, (k_row_flags<SRC_GPU><<<(unsigned)cdiv(ncand, 256), 256, 0, c->stream>>>(v, ncand, stride, c->d_flags + 1)));
     else LAUNCH(c, K_FLAGS, (k_row_flags<SRC_NET><<<(unsigned)cdiv(ncand, 256), 256, 0, c->stream>>>(v, ncand, stride, c->d_flags + 1)));
-    CK(cudaMemcpyAsync(flags, c->d_flags + 1, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK_S(small_d2h(c, flags, c->d_flags + 1, 4));
+    CK_S(stream_sync(c));
     CK(cudaGetLastError());
     return 0;
 }
@@ -382,6 +495,7 @@ static int emit_common(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask,
     c->out_n[outslot] = 0;
     if (nbytes) *nbytes = 0;
     if (nrec) *nrec = 0;
+    if (flip_output(c, outslot)) return SOFA_ERR_CUDA;
     if (ncand == 0) return 0;
     uint64_t nblocks = cdiv(ncand, EMIT_TPB);
     ENSURE(c->rowlen, ncand * 4);
@@ -399,23 +513,99 @@ static int emit_common(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask,
     else LAUNCH(c, ks, (k_emit_size<SRC_NET, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
     LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(c->blockoff.as<uint64_t>(), nblocks)));
     uint64_t total = 0; unsigned long long cnt = 0;
-    CK(cudaMemcpyAsync(&total, c->blockoff.as<uint64_t>() + nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&cnt, c->d_err + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK_S(small_d2h(c, &total, c->blockoff.as<uint64_t>() + nblocks, 8));
+    CK_S(small_d2h(c, &cnt, c->d_err + 1, 8));
     int r = check_kernel_error(c, FMT == FMT_CSV ? "emit_csv" : "emit_json");
     if (r) return r;
-    ENSURE(c->out[outslot], total + 64);
-    a.out = c->out[outslot].as<char>();
+    { int ra = out_alloc(c, outslot, total, &a.out); if (ra) return ra; }
     if (total) {
         if (k == SRC_PERF) LAUNCH(c, kw, (k_emit_write<SRC_PERF, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
         else if (k == SRC_GPU) LAUNCH(c, kw, (k_emit_write<SRC_GPU, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
         else LAUNCH(c, kw, (k_emit_write<SRC_NET, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
-        CK(cudaStreamSynchronize(c->stream));
+        CK_S(stream_sync(c));
         CK(cudaGetLastError());
     }
-    c->out_n[outslot] = total;
+    out_commit(c, outslot, total);
     if (nbytes) *nbytes = total;
     if (nrec) *nrec = cnt;
     return 0;
+}
+
+
+constexpr uint32_t FUSED_SLOT_BYTES = 64 * 1024;
+
+template <int FMT>
+static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, int bit, uint32_t fmask,
+                      int outslot, uint64_t sel_hint, uint64_t* nbytes, uint64_t* nrec) {
+    Source& s = c->src[k];
+    uint64_t ncand = cdiv(s.n_rows, stride);
+    c->out_n[outslot] = 0;
+    if (nbytes) *nbytes = 0;
+    if (nrec) *nrec = 0;
+    if (flip_output(c, outslot)) return SOFA_ERR_CUDA;
+    if (ncand == 0) return 0;
+    if (ncand >= 0xffffffffull) FAIL(SOFA_ERR_ARG, "emit: too many rows for one call");
+    uint64_t text_share = s.nbytes > s.data_off ? s.nbytes - s.data_off : 0;
+    const uint32_t* index = nullptr;
+    uint64_t nitems = ncand;
+    if (mask) {
+        // filtered series: compact the selected candidates first so the emit grid is dense
+        uint64_t nb = cdiv(ncand, 256);
+        ENSURE(c->blockoff, (nb + 2) * 8);
+        LAUNCH(c, K_FILTER, (k_mask_count<<<(unsigned)nb, 256, 0, c->stream>>>(mask, bit, ncand, c->blockoff.as<uint64_t>())));
+        LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(c->blockoff.as<uint64_t>(), nb)));
+        uint64_t cnt = 0;
+        CK_S(small_d2h(c, &cnt, c->blockoff.as<uint64_t>() + nb, 8));
+        CK_S(stream_sync(c));
+        if (cnt == 0) return 0;
+        ENSURE(c->rowlen, cnt * 4 + 16);
+        LAUNCH(c, K_FILTER, (k_mask_write<<<(unsigned)nb, 256, 0, c->stream>>>(mask, bit, ncand, c->blockoff.as<uint64_t>(), c->rowlen.as<uint32_t>())));
+        index = c->rowlen.as<uint32_t>();
+        nitems = cnt;
+        text_share = (uint64_t)((double)text_share * ((double)cnt / (double)ncand) * 2.0) + (1 << 20);
+        sel_hint = cnt;
+    }
+    uint64_t nblocks = cdiv(nitems, EMIT_TPB);
+    ENSURE(c->tiles, (nblocks + 2) * 8);
+    SrcView v = make_view(c, k, true);
+    uint64_t per_row = FMT == FMT_CSV ? 96 : 230;
+    uint64_t cap = sel_hint * per_row + text_share + (1 << 16);
+    uint32_t slot_bytes = k == SRC_GPU ? 64 * 1024 : 48 * 1024;
+    for (int attempt = 0; attempt < 6; attempt++, cap *= 2) {
+        char* outp = nullptr;
+        { int ra = out_alloc(c, outslot, cap, &outp); if (ra) return ra; }
+        if (reset_err(c)) return SOFA_ERR_CUDA;
+        CK(cudaMemsetAsync(c->tiles.p, 0, (nblocks + 1) * 8, c->stream));
+        FusedArgs a;
+        a.ncand = nitems; a.stride = stride; a.fmask = fmask; a.mask = nullptr; a.bit = 0; a.index = index;
+        a.out = outp; a.cap = cap;
+        a.state = c->tiles.as<unsigned long long>(); a.ticket = c->d_flags + 4;
+        a.err = c->d_err; a.count = c->d_err + 1; a.total = c->d_err + 11; a.overflow = c->d_flags + 2;
+        a.slot_bytes = slot_bytes;
+        int kk = FMT == FMT_CSV ? K_CSV_WRITE : K_JSON_WRITE;
+        unsigned g = (unsigned)nblocks;
+        if (k == SRC_PERF) LAUNCH(c, kk, (k_emit_fused<SRC_PERF, FMT><<<g, EMIT_TPB, slot_bytes, c->stream>>>(v, a)));
+        else if (k == SRC_GPU) LAUNCH(c, kk, (k_emit_fused<SRC_GPU, FMT><<<g, EMIT_TPB, slot_bytes, c->stream>>>(v, a)));
+        else LAUNCH(c, kk, (k_emit_fused<SRC_NET, FMT><<<g, EMIT_TPB, slot_bytes, c->stream>>>(v, a)));
+        unsigned long long total = 0, cnt = 0; unsigned int ovf = 0;
+        CK_S(small_d2h(c, &total, c->d_err + 11, 8));
+        CK_S(small_d2h(c, &cnt, c->d_err + 1, 8));
+        CK_S(small_d2h(c, &ovf, c->d_flags + 2, 4));
+        int r = check_kernel_error(c, FMT == FMT_CSV ? "emit_csv" : "emit_json");
+        if (r) return r;
+        if (ovf) { if (total + 64 > cap * 2) cap = total / 2 + 64; continue; }
+        out_commit(c, outslot, total);
+        if (nbytes) *nbytes = total;
+        if (nrec) *nrec = cnt;
+        return 0;
+    }
+    FAIL(SOFA_ERR_CAP, "emit: output capacity estimate failed repeatedly");
+}
+
+static bool use_fused() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SOFA_B200_EMIT"); v = (e && strcmp(e, "twopass") == 0) ? 0 : 1; }
+    return v == 1;
 }
 
 extern "C" {
@@ -425,6 +615,7 @@ int sofa_b200_emit_csv(sofa_ctx* c, int k, uint32_t stride, uint64_t* nbytes) {
     if (stride == 0) FAIL(SOFA_ERR_ARG, "emit_csv: stride must be >= 1");
     uint32_t fmask = 0;
     r = fmask_for(c, k, stride, &fmask); if (r) return r;
+    if (use_fused()) return emit_fused<FMT_CSV>(c, k, stride, nullptr, 0, fmask, 0, cdiv(c->src[k].n_rows, stride), nbytes, nullptr);
     return emit_common<FMT_CSV>(c, k, stride, nullptr, 0, fmask, 0, nbytes, nullptr);
 }
 
@@ -442,7 +633,11 @@ int sofa_b200_emit_json(sofa_ctx* c, int k, uint32_t stride, int32_t filter_idx,
     uint32_t fmask = 0;
     r = fmask_for(c, k, stride, &fmask); if (r) return r;
     uint64_t nb = 0, nr = 0;
-    r = emit_common<FMT_JSON>(c, k, stride, mask, filter_idx >= 0 ? filter_idx : 0, fmask, 1, &nb, &nr);
+    if (use_fused()) {
+        uint64_t hint = filter_idx >= 0 ? s.filter_counts[filter_idx] : cdiv(s.n_rows, stride);
+        r = emit_fused<FMT_JSON>(c, k, stride, mask, filter_idx >= 0 ? filter_idx : 0, fmask, 1, hint, &nb, &nr);
+    } else
+        r = emit_common<FMT_JSON>(c, k, stride, mask, filter_idx >= 0 ? filter_idx : 0, fmask, 1, &nb, &nr);
     if (r) return r;
     if (nbytes) *nbytes = nb >= 2 ? nb - 2 : 0;       // the leading ", " is dropped by fetch
     if (nrec) *nrec = nr;
@@ -456,10 +651,74 @@ int sofa_b200_fetch(sofa_ctx* c, int which, void* host_out, uint64_t cap) {
     if (which == 1) { skip = n >= 2 ? 2 : n; n -= skip; }
     if (cap < n) FAIL(SOFA_ERR_CAP, "fetch: buffer too small");
     if (n) {
-        CK(cudaMemcpyAsync(host_out, c->out[which].as<char>() + skip, n, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        const char* srcp = which < 2 ? c->out_ptr[which] : c->out[which].as<char>();
+        CK(cudaMemcpyAsync(host_out, srcp + skip, n, cudaMemcpyDeviceToHost, c->stream));
+        CK_S(stream_sync(c));
         c->stats.d2h_bytes += n;
     }
+    return 0;
+}
+
+int sofa_b200_upload_async(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
+    if (!c || k < 0 || k > 2 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
+    if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload_async: data_off beyond the text");
+    CK(cudaSetDevice(c->device));
+    Source& s = c->src[k];
+    if (nbytes + 64 > s.text.cap) { CK_S(stream_sync(c)); CK(cudaStreamSynchronize(c->h2d)); ENSURE(s.text, nbytes + 64); }
+    // the copy must not overtake kernels of an earlier pass that still read this buffer
+    CK(cudaEventRecord(c->up_ev[k], c->stream));
+    CK(cudaStreamWaitEvent(c->h2d, c->up_ev[k], 0));
+    if (nbytes) CK(cudaMemcpyAsync(s.text.p, text, nbytes, cudaMemcpyHostToDevice, c->h2d));
+    CK(cudaMemsetAsync(s.text.as<char>() + nbytes, '\n', 64, c->h2d));
+    CK(cudaEventRecord(c->up_ev[k], c->h2d));
+    c->up_pending[k] = true;
+    c->stats.h2d_bytes += nbytes;
+    s.nbytes = nbytes; s.data_off = data_off; s.uploaded = true; s.parsed = false; s.viz_ready = false; s.n_rows = 0;
+    s.mask_stride = 0; s.nkw = 0;
+    return 0;
+}
+
+int sofa_b200_fetch_async(sofa_ctx* c, int which, void* host_out, uint64_t cap, int32_t* ticket) {
+    if (!c || which < 0 || which > 1 || !host_out) FAIL(SOFA_ERR_ARG, "fetch_async: output buffer 0 or 1");
+    CK(cudaSetDevice(c->device));
+    uint64_t n = c->out_n[which], skip = 0;
+    if (which == 1) { skip = n >= 2 ? 2 : n; n -= skip; }
+    if (cap < n) FAIL(SOFA_ERR_CAP, "fetch_async: buffer too small");
+    int t = c->fetch_next;
+    c->fetch_next = (c->fetch_next + 1) & 15;
+    if (c->fetch_used[t]) CK(cudaEventSynchronize(c->fetch_ev[t]));
+    if (n) CK(cudaMemcpyAsync(host_out, c->out_ptr[which] + skip, n, cudaMemcpyDeviceToHost, c->d2h));
+    CK(cudaEventRecord(c->out_ev[which], c->d2h));
+    CK(cudaEventRecord(c->fetch_ev[t], c->d2h));
+    c->out_busy[which] = true;
+    c->fetch_used[t] = true;
+    c->stats.d2h_bytes += n;
+    if (ticket) *ticket = t;
+    return 0;
+}
+int sofa_b200_wait_fetch(sofa_ctx* c, int32_t ticket) {
+    if (!c || ticket < 0 || ticket > 15) FAIL(SOFA_ERR_ARG, "wait_fetch: bad ticket");
+    CK(cudaSetDevice(c->device));
+    if (c->fetch_used[ticket]) CK(cudaEventSynchronize(c->fetch_ev[ticket]));
+    return 0;
+}
+int sofa_b200_sync(sofa_ctx* c) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->h2d));
+    CK_S(stream_sync(c));
+    CK(cudaStreamSynchronize(c->d2h));
+    c->arena_cur = 0;
+    return 0;
+}
+int sofa_b200_set_output_arena(sofa_ctx* c, uint64_t nbytes) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK_S(stream_sync(c));
+    CK(cudaStreamSynchronize(c->d2h));
+    if (nbytes == 0) { c->arena.release(); c->arena_on = false; c->arena_cur = 0; return 0; }
+    ENSURE(c->arena, nbytes);
+    c->arena_on = true; c->arena_cur = 0;
     return 0;
 }
 
@@ -482,8 +741,8 @@ int sofa_b200_set_filters(sofa_ctx* c, int k, uint32_t stride, int32_t nkw, cons
     ENSURE(c->ftable, sizeof(FilterTable));
     ENSURE(s.mask, ncand + 16);
     if (reset_err(c)) return SOFA_ERR_CUDA;
-    CK(cudaMemcpyAsync(c->ftable.p, &ft, sizeof ft, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK_S(small_h2d(c, c->ftable.p, &ft, sizeof ft));
+    CK_S(stream_sync(c));
     if (ncand) {
         SrcView v = make_view(c, k, true);
         unsigned g = (unsigned)cdiv(ncand, 256);
@@ -493,10 +752,11 @@ int sofa_b200_set_filters(sofa_ctx* c, int k, uint32_t stride, int32_t nkw, cons
         else LAUNCH(c, K_FILTER, (k_filter<SRC_NET><<<g, 256, 0, c->stream>>>(v, ncand, stride, dft, s.mask.as<uint8_t>(), c->d_err + 2)));
     }
     unsigned long long cn[8] = {0};
-    CK(cudaMemcpyAsync(cn, c->d_err + 2, 64, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK_S(small_d2h(c, cn, c->d_err + 2, 64));
+    CK_S(stream_sync(c));
     CK(cudaGetLastError());
     if (counts) for (int i = 0; i < nkw; i++) counts[i] = cn[i];
+    for (int i = 0; i < 8; i++) s.filter_counts[i] = i < nkw ? cn[i] : 0;
     s.mask_stride = stride; s.nkw = nkw;
     return 0;
 }
@@ -524,16 +784,16 @@ int sofa_b200_viz_mangled(sofa_ctx* c, uint32_t stride, uint64_t* nbytes, uint32
             v, ncand, stride, s.vizhash.as<uint64_t>(), c->keys.as<unsigned long long>(), c->rows.as<unsigned long long>(),
             cap - 1, c->d_flags + 2)));
         unsigned int ovf = 0;
-        CK(cudaMemcpyAsync(&ovf, c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK_S(small_d2h(c, &ovf, c->d_flags + 2, 4));
+        CK_S(stream_sync(c));
         CK(cudaGetLastError());
         if (!ovf) {
             LAUNCH(c, K_VIZ, (k_dict_len<<<(unsigned)cdiv(cap, 256), 256, 0, c->stream>>>(
                 v, c->keys.as<unsigned long long>(), c->rows.as<unsigned long long>(), cap, c->d_err + 1, c->d_flags + 3)));
             unsigned long long total = 0; unsigned int n = 0;
-            CK(cudaMemcpyAsync(&total, c->d_err + 1, 8, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(&n, c->d_flags + 3, 4, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
+            CK_S(small_d2h(c, &total, c->d_err + 1, 8));
+            CK_S(small_d2h(c, &n, c->d_flags + 3, 4));
+            CK_S(stream_sync(c));
             // occupancy above 50% makes probing slow and overflow likely next time: grow
             if ((uint64_t)n * 2 > cap) continue;
             ENSURE(c->out[2], total + 64);
@@ -541,7 +801,7 @@ int sofa_b200_viz_mangled(sofa_ctx* c, uint32_t stride, uint64_t* nbytes, uint32
             if (total)
                 LAUNCH(c, K_VIZ, (k_dict_write<<<(unsigned)cdiv(cap, 256), 256, 0, c->stream>>>(
                     v, c->keys.as<unsigned long long>(), c->rows.as<unsigned long long>(), cap, c->d_err + 1, c->out[2].as<char>())));
-            CK(cudaStreamSynchronize(c->stream));
+            CK_S(stream_sync(c));
             CK(cudaGetLastError());
             c->out_n[2] = total;
             if (nbytes) *nbytes = total;
@@ -576,11 +836,11 @@ int sofa_b200_set_demangled(sofa_ctx* c, uint32_t n, const char* mangled, const 
     offs[n] = blob.size();
     ENSURE(s.dict_hash, (n + 1) * 8); ENSURE(s.dict_off, (n + 2) * 8); ENSURE(s.dict_blob, blob.size() + 16);
     if (n) {
-        CK(cudaMemcpyAsync(s.dict_hash.p, hashes.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.dict_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+        CK_S(small_h2d(c, s.dict_hash.p, hashes.data(), n * 8));
+        CK_S(small_h2d(c, s.dict_blob.p, blob.data(), blob.size()));
     }
-    CK(cudaMemcpyAsync(s.dict_off.p, offs.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK_S(small_h2d(c, s.dict_off.p, offs.data(), (n + 1) * 8));
+    CK_S(stream_sync(c));
     s.dict_n = (int)n;
     uint64_t ncand = cdiv(s.n_rows, s.viz_stride);
     if (ncand) {
@@ -613,7 +873,7 @@ int sofa_b200_get_column(sofa_ctx* c, int k, int col, void* host_out, uint64_t c
     if (slot < 0) FAIL(SOFA_ERR_ARG, "get_column: no such stored column for this source");
     uint64_t nb = s.n_rows * w;
     if (cap_bytes < nb) FAIL(SOFA_ERR_CAP, "get_column: buffer too small");
-    if (nb) { CK(cudaMemcpyAsync(host_out, s.cols[slot].p, nb, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    if (nb) { CK(cudaMemcpyAsync(host_out, s.cols[slot].p, nb, cudaMemcpyDeviceToHost, c->stream)); CK_S(stream_sync(c)); }
     return 0;
 }
 
@@ -662,7 +922,7 @@ int sofa_b200_text_fetch(sofa_ctx* c, int k, void* host_out, uint64_t cap) {
     if (!s.uploaded) FAIL(SOFA_ERR_STATE, "text_fetch: no text");
     if (cap < s.nbytes) FAIL(SOFA_ERR_CAP, "text_fetch: buffer too small");
     CK(cudaSetDevice(c->device));
-    if (s.nbytes) { CK(cudaMemcpyAsync(host_out, s.text.p, s.nbytes, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    if (s.nbytes) { CK(cudaMemcpyAsync(host_out, s.text.p, s.nbytes, cudaMemcpyDeviceToHost, c->stream)); CK_S(stream_sync(c)); }
     return 0;
 }
 

@@ -73,6 +73,29 @@ class CudaEngine:
         ptr, n, keep = self._ptr(text)
         self._check(self.lib.sofa_b200_upload(self.ctx, kind, ctypes.c_void_p(ptr), n, data_off))
 
+    def upload_async(self, kind, text, data_off=0):
+        """H2D on the copy stream (text must stay alive and should be pinned); parse() waits for it."""
+        ptr, n, keep = self._ptr(text)
+        self._check(self.lib.sofa_b200_upload_async(self.ctx, kind, ctypes.c_void_p(ptr), n, data_off))
+
+    def fetch_async(self, which, n, out):
+        """D2H of output buffer `which` (0 csv, 1 json) on the copy stream -> ticket."""
+        if out.nbytes < n:
+            raise ValueError("output buffer too small")
+        t = ctypes.c_int32()
+        self._check(self.lib.sofa_b200_fetch_async(self.ctx, which, ctypes.c_void_p(out.ctypes.data), out.nbytes,
+                                                   ctypes.byref(t)))
+        return t.value
+
+    def wait_fetch(self, ticket):
+        self._check(self.lib.sofa_b200_wait_fetch(self.ctx, ticket))
+
+    def set_output_arena(self, nbytes):
+        self._check(self.lib.sofa_b200_set_output_arena(self.ctx, int(nbytes)))
+
+    def sync(self):
+        self._check(self.lib.sofa_b200_sync(self.ctx))
+
     def make_params(self, p):
         ip = L.IngestParams()
         ip.time_base, ip.t_offset = p['time_base'], p['t_offset']

@@ -82,7 +82,7 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
             PerfRow r; err = parse_perf(line, (int)linelen, c, &r);
             if (!err) {
                 RowVals v = vals_perf(r);
-                PerfName<const char*> ng{line, r};
+                PerfName<const char*> ng{line, r, false};
                 if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
                 else if (sel) {
                     DictVizName vz{PerfVizName<const char*>{ng}, dict};
@@ -96,7 +96,7 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
             if (!err) {
                 if (sel) fl |= r.bw_is_float ? 1u : 0u;
                 RowVals v = vals_gpu(r, c.n_cudaproc);
-                GpuName<const char*> ng{line, r};
+                GpuName<const char*> ng{line, r, false};
                 if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
                 else {
                     bool take = (mode == 1) ? sel : true;

@@ -209,3 +209,41 @@ def test_verbose_analyze_runs(tmp_path, capsys):
     sofa_analyze(cfg)
     out = capsys.readouterr().out
     assert "Data-copy payload matrix" in out and "Top 10 Events" in out and "total execution time" in out
+
+
+def test_async_transfers_give_identical_outputs(tmp_path):
+    """upload_async / fetch_async (copy streams, double-buffered outputs) vs the synchronous calls."""
+    from sofa_b200.engine import CudaEngine
+    from sofa_b200 import hostlogic as hl
+    eng = CudaEngine(0)
+    try:
+        text = synth.perf_text(12, 40000).encode()
+        p = hl.base_params(hl.SRC_PERF, 1600000000.0, False, 1599995000.75)
+        pin = eng.pinned(len(text))
+        pin.array[:] = np.frombuffer(text, dtype=np.uint8)
+        eng.load(hl.SRC_PERF, text, p)
+        want_csv = eng.csv(hl.SRC_PERF, 1).copy()
+        eng.set_demangled([(m, demangle(m)) for m in eng.viz_mangled(1)])
+        want_js, _ = eng.json(hl.SRC_PERF, 1, -1)
+        want_js = want_js.copy()
+        outs = [eng.pinned(len(want_js) + 64) for _ in range(4)]
+        for rep in range(4):
+            if rep == 2:
+                eng.set_output_arena(3 * (len(want_js) + len(want_csv)))      # small: forces a wrap
+            eng.upload_async(hl.SRC_PERF, pin.array, 0)
+            assert eng.parse(hl.SRC_PERF, p) == 40000
+            n0 = eng.csv_device(hl.SRC_PERF, 1)
+            t0 = eng.fetch_async(0, n0, outs[0].array)
+            eng.set_demangled([(m, demangle(m)) for m in eng.viz_mangled(1)])
+            n1, _ = eng.json_device(hl.SRC_PERF, 1, -1)
+            t1 = eng.fetch_async(1, n1, outs[1].array)
+            n2 = eng.csv_device(hl.SRC_PERF, 1)          # second emit into the other half
+            t2 = eng.fetch_async(0, n2, outs[2].array)
+            n3, _ = eng.json_device(hl.SRC_PERF, 1, -1)
+            t3 = eng.fetch_async(1, n3, outs[3].array)
+            eng.sync()
+            assert n0 == n2 == len(want_csv) and n1 == n3 == len(want_js)
+            for o, w in ((outs[0], want_csv), (outs[2], want_csv), (outs[1], want_js), (outs[3], want_js)):
+                assert np.array_equal(o.array[:len(w)], w)
+    finally:
+        eng.close()
