@@ -305,37 +305,6 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// upper bound of the numeric part + exact escaped name length (+ CSV quoting flag)
-template <int FMT, class NG>
-__device__ __forceinline__ uint32_t emit_upper_bound(const RowVals& v, uint32_t fmask, const NG& ng, bool* special, int* bad) {
-    *special = false;
-    if (FMT == FMT_CSV) {
-        if (!v.valid) return 13;
-        CsvCount k; ng.gen(k);
-        *special = k.special;
-        uint32_t n = (uint32_t)k.len + (k.special ? 2u : 0u) + 13u;
-        for (int c = 0; c < 13; c++) {
-            if (c == 11) continue;
-            bool isf; double f; int64_t i;
-            col_value(v, c, fmask, &isf, &f, &i);
-            n += isf ? 28u : (uint32_t)len_i64(i);
-        }
-        return n;
-    } else {
-        if (!v.valid) return SOFA_JSON_FIXED + 13 * 4;
-        JsonCount k; ng.gen(k);
-        if (k.e.bad || k.e.need) *bad = 1;
-        uint32_t n = SOFA_JSON_FIXED + (uint32_t)k.len + 2u;
-        for (int c = 0; c < 13; c++) {
-            if (c == 11) continue;
-            bool isf; double f; int64_t i;
-            col_value(v, c, fmask, &isf, &f, &i);
-            n += isf ? 26u : (uint32_t)len_i64(i);
-        }
-        return n;
-    }
-}
-
 // candidate indices whose filter bit is set, ascending (two-pass compaction)
 __global__ void __launch_bounds__(256) k_mask_count(const uint8_t* __restrict__ mask, int bit, uint64_t n, uint64_t* blockoff) {
     __shared__ uint32_t sm[33];
@@ -354,9 +323,12 @@ __global__ void __launch_bounds__(256) k_mask_write(const uint8_t* __restrict__ 
     if (f) index[blockoff[blockIdx.x] + ex] = (uint32_t)i;
 }
 
+template <int FMT> struct RowPlanOf { typedef CsvRowPlan type; };
+template <> struct RowPlanOf<FMT_JSON> { typedef JsonRowPlan type; };
+
 template <int KIND, int FMT>
 __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs a) {
-    extern __shared__ __align__(16) unsigned char slots[];
+    extern __shared__ __align__(16) unsigned char stage[];      // packed image of this block's output range
     __shared__ uint32_t sm[33];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
@@ -368,40 +340,22 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
     const uint64_t c = a.index ? (inr ? a.index[ci] : 0) : ci;
     const bool sel = inr && (a.index != nullptr || a.mask == nullptr || ((a.mask[c] >> a.bit) & 1));
     const uint64_t row = c * a.stride;
-    uint32_t ub = 0;
-    bool special = false;
-    int bad = 0;
+    // ---- phase 1: digit plans + exact row length (every float is analysed once)
+    typename RowPlanOf<FMT>::type plan;
+    plan.len = 0;
     if (sel) {
         with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
-            ub = emit_upper_bound<FMT>(v, a.fmask, ng, &special, &bad);
+            if constexpr (FMT == FMT_CSV) plan = csv_row_plan(v, a.fmask, ng);
+            else plan = json_row_plan(v, a.fmask, ng);
         });
-        if (bad) { report_error(a.err, row, E_UTF8); ub = 0; }
+        if (plan.len < 0) { report_error(a.err, row, plan.len == -2 ? E_UTF8 : E_FORMAT); plan.len = 0; }
     }
-    const bool live = sel && !bad;
-    uint32_t ub_total, cnt_total;
-    uint32_t slot_off = block_excl_scan(ub, &ub_total, sm);
-    block_excl_scan(live ? 1u : 0u, &cnt_total, sm);
-    const bool staged = ub_total <= a.slot_bytes;
-    uint32_t len = 0;
-    if (live) {
-        int l = 0;
-        with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
-            if (staged) {
-                SmemPtr dst{(uint32_t)__cvta_generic_to_shared(slots) + slot_off};
-                if constexpr (FMT == FMT_CSV) l = csv_row_write(v, a.fmask, ng, special, dst);
-                else l = json_row_write(v, a.fmask, ng, dst);
-            } else {
-                if constexpr (FMT == FMT_CSV) { bool sp; l = csv_row_len(v, a.fmask, ng, &sp); }
-                else l = json_row_len(v, a.fmask, ng);
-            }
-        });
-        if (l < 0) { report_error(a.err, row, l == -2 ? E_UTF8 : E_FORMAT); l = 0; }
-        len = (uint32_t)l;
-    }
-    uint32_t total;
-    uint32_t ex = block_excl_scan(len, &total, sm);
+    const uint32_t len = (uint32_t)plan.len;
+    uint32_t total, cnt_total;
+    const uint32_t ex = block_excl_scan(len, &total, sm);
+    block_excl_scan(len ? 1u : 0u, &cnt_total, sm);
+    // ---- phase 2: global byte offset of this block (decoupled look-back, one warp)
     if (threadIdx.x < 32) {
-        // decoupled look-back, one warp: 32 predecessors per probe
         const uint32_t lane = threadIdx.x;
         unsigned long long base = 0;
         if (b > 0) {
@@ -434,25 +388,25 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
     __syncthreads();
     const unsigned long long base = s_base;
     if (base + total > a.cap) { if (threadIdx.x == 0) atomicOr(a.overflow, 1u); return; }
-    if (staged) {
-        // warp-cooperative copy-out: the warp walks its 32 rows, lanes stride the bytes
-        const uint32_t lane = lane_id();
-        for (int r = 0; r < 32; r++) {
-            uint32_t rl = __shfl_sync(0xffffffffu, len, r);
-            if (rl == 0) continue;
-            uint32_t so = __shfl_sync(0xffffffffu, slot_off, r);
-            uint32_t eo = __shfl_sync(0xffffffffu, ex, r);
-            char* g = a.out + base + eo;
-            const unsigned char* s = slots + so;
-            for (uint32_t i = lane; i < rl; i += 32) g[i] = (char)s[i];
-        }
-    } else if (len) {
-        char* dst = a.out + base + ex;
+    // ---- phase 3: print the row at its final position (shared-memory image, or global when the
+    // block's range does not fit)
+    const bool staged = total + 16 <= a.slot_bytes;
+    if (len) {
         with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
-            if constexpr (FMT == FMT_CSV) csv_row_write(v, a.fmask, ng, special, dst);
-            else json_row_write(v, a.fmask, ng, dst);
+            if (staged) {
+                SmemPtr dst{(uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)(base & 15) + ex};
+                if constexpr (FMT == FMT_CSV) csv_row_emit(v, a.fmask, ng, plan, dst);
+                else json_row_emit(v, a.fmask, ng, plan, dst);
+            } else {
+                char* dst = a.out + base + ex;
+                if constexpr (FMT == FMT_CSV) csv_row_emit(v, a.fmask, ng, plan, dst);
+                else json_row_emit(v, a.fmask, ng, plan, dst);
+            }
         });
     }
+    __syncthreads();
+    // ---- phase 4: 128-bit coalesced flush
+    if (staged && total) flush_staged(stage, a.out, base, total);
 }
 
 }  // namespace sofa

@@ -337,36 +337,56 @@ SOFA_HD bool fixed6_parts(double x, bool* neg, uint64_t* ip, uint32_t* fp) {
     *ip = I; *fp = (uint32_t)F;
     return true;
 }
+// "%.6f" split into a plan (sign, integer part, 6 fraction digits, exact length) and an emit
+// step, so kernels can size a row first and print its digits exactly once afterwards.
+struct F6Plan { uint64_t I; uint32_t F; uint8_t neg, ok, len; };
+SOFA_HD F6Plan fixed6_plan(double x) {
+    F6Plan p; bool neg;
+    p.ok = fixed6_parts(x, &neg, &p.I, &p.F) ? 1 : 0;
+    p.neg = neg ? 1 : 0;
+    p.len = (uint8_t)(p.neg + ndigits_u64(p.I) + 7);
+    return p;
+}
+template <typename O>
+SOFA_HD int fixed6_emit(const F6Plan& p, O out) {
+    int n = 0;
+    if (p.neg) out[n++] = '-';
+    n += fmt_u64(p.I, out + n);
+    out[n++] = '.';
+    fmt_u32_pad(p.F, 6, out + n);
+    return n + 6;
+}
 SOFA_HD int len_fixed6(double x) {          // length of "%.6f" (x finite, |x| < 2^63), -1 otherwise
-    bool neg; uint64_t I; uint32_t F;
-    if (!fixed6_parts(x, &neg, &I, &F)) return -1;
-    return (neg ? 1 : 0) + ndigits_u64(I) + 7;
+    F6Plan p = fixed6_plan(x);
+    return p.ok ? p.len : -1;
 }
 template <typename O>
 SOFA_HD int fmt_fixed6(double x, O out) {
-    bool neg; uint64_t I; uint32_t F;
-    if (!fixed6_parts(x, &neg, &I, &F)) return -1;
-    int n = 0;
-    if (neg) out[n++] = '-';
-    n += fmt_u64(I, out + n);
-    out[n++] = '.';
-    fmt_u64_pad(F, 6, out + n);
-    return n + 6;
+    F6Plan p = fixed6_plan(x);
+    if (!p.ok) return -1;
+    return fixed6_emit(p, out);
 }
 
 // ----------------------------------------------------------------------------- report.js floats
 // pandas to_json prints float64 with its vendored ultrajson: whole part, then
 // (value - whole) * 1e10 evaluated in double with its own half rule; json.loads turns that
 // decimal string back into a double y; json.dump prints repr(y) (shortest round trip).
-// Returns the length written (<= 32), or -1 for magnitudes outside the fixed-notation
-// range of ultrajson (|v| > 1e16 or 0 < |v| < 1e-15), which this codec does not cover.
-template <typename O>
-SOFA_HD int json_double(double x, O out) {
+// json_plan decides the digits (kind 0 = outside the fixed-notation range of ultrajson,
+// |v| > 1e16 or 0 < |v| < 1e-15, which this codec does not cover); json_emit prints them.
+enum { JP_BAD = 0, JP_NULL = 1, JP_FIXED = 2, JP_SCI = 3 };
+struct JPlan { uint64_t I, dg; uint8_t kind, neg, nd, ex, len; };
+SOFA_HD JPlan jp_fixed(bool neg, uint64_t I, uint64_t dg, int nd) {
+    JPlan p; p.kind = JP_FIXED; p.neg = neg ? 1 : 0; p.I = I; p.dg = dg; p.nd = (uint8_t)nd; p.ex = 0;
+    p.len = (uint8_t)(p.neg + ndigits_u64(I) + 1 + nd);
+    return p;
+}
+SOFA_HD JPlan json_plan(double x) {
+    JPlan p; p.I = 0; p.dg = 0; p.neg = 0; p.nd = 0; p.ex = 0; p.len = 0; p.kind = JP_BAD;
     uint64_t xb = d_bits(x);
-    if (((xb >> 52) & 0x7ff) == 0x7ff) { out[0] = 'n'; out[1] = 'u'; out[2] = 'l'; out[3] = 'l'; return 4; }
+    if (((xb >> 52) & 0x7ff) == 0x7ff) { p.kind = JP_NULL; p.len = 4; return p; }
     bool neg = x < 0;
     double v = neg ? -x : x;
-    if (v > 1e16 || (v != 0.0 && v < 1e-15)) return -1;
+    if (v > 1e16 || (v != 0.0 && v < 1e-15)) return p;
     uint64_t whole = (uint64_t)v;
     double tmp = d_mul(d_sub(v, (double)whole), 1e10);
     uint64_t frac = (uint64_t)tmp;
@@ -374,30 +394,21 @@ SOFA_HD int json_double(double x, O out) {
     if (diff > 0.5) ++frac;
     else if (diff == 0.5 && (frac == 0 || (frac & 1))) ++frac;
     if (frac >= 10000000000ull) { frac = 0; ++whole; }
-    int n = 0;
-    if (neg) out[n++] = '-';
     if (whole < 100000ull) {
         // <= 15 significant digits: the decimal string itself is the shortest repr of y
         if (whole > 0 || frac >= 1000000ull || frac == 0) {
-            n += fmt_u64(whole, out + n);
-            out[n++] = '.';
-            if (frac == 0) { out[n++] = '0'; return n; }
+            if (frac == 0) return jp_fixed(neg, whole, 0, 1);
             int nz = 10;
             while (frac % 10 == 0) { frac /= 10; nz--; }
-            fmt_u64_pad(frac, nz, out + n);
-            return n + nz;
+            return jp_fixed(neg, whole, frac, nz);
         }
         // 0 < y < 1e-4: Python repr switches to exponent notation ("2.9e-09", "1e-10")
         int ex = 11 - ndigits_u64(frac);          // 5..10
         while (frac % 10 == 0) frac /= 10;
         int L = ndigits_u64(frac);
-        char ds[8];
-        fmt_u64(frac, ds);
-        out[n++] = ds[0];
-        if (L > 1) { out[n++] = '.'; for (int k = 1; k < L; k++) out[n++] = ds[k]; }
-        out[n++] = 'e'; out[n++] = '-';
-        out[n++] = (char)('0' + ex / 10); out[n++] = (char)('0' + ex % 10);
-        return n;
+        p.kind = JP_SCI; p.neg = neg ? 1 : 0; p.dg = frac; p.nd = (uint8_t)L; p.ex = (uint8_t)ex;
+        p.len = (uint8_t)(p.neg + L + (L > 1 ? 1 : 0) + 4);
+        return p;
     }
     // ---- whole >= 1e5: y = v when v >= 2^19 (the 10-digit decimal is within half an ulp),
     // else y = (whole*1e10 + frac) / 1e10 (numerator < 2^53, one exact division)
@@ -406,19 +417,11 @@ SOFA_HD int json_double(double x, O out) {
     uint64_t yb = d_bits(y);
     int e = (int)((yb >> 52) & 0x7ff) - 1075;
     uint64_t m = (yb & 0xfffffffffffffull) | (1ull << 52);
-    if (e >= 0) {                       // integer valued (< 1e16): all digits, then ".0"
-        n += fmt_u64(m << e, out + n);
-        out[n++] = '.'; out[n++] = '0';
-        return n;
-    }
+    if (e >= 0) return jp_fixed(neg, m << e, 0, 1);        // integer valued (< 1e16): digits + ".0"
     int s = -e;                         // 1..36 because y >= 1e5 > 2^16
     uint64_t I = m >> s;
     uint64_t r0 = m & ((1ull << s) - 1);
-    if (r0 == 0) {
-        n += fmt_u64(I, out + n);
-        out[n++] = '.'; out[n++] = '0';
-        return n;
-    }
+    if (r0 == 0) return jp_fixed(neg, I, 0, 1);
     bool even = (m & 1) == 0;
     bool pow2 = (m == (1ull << 52));    // lower neighbour is half as far
     u128 one = ((u128)1) << s;
@@ -440,13 +443,35 @@ SOFA_HD int json_double(double x, O out) {
         if (lo_ok && hi_ok) take_hi = (up < rem) || (up == rem && (dg & 1));
         else take_hi = hi_ok;
         if (take_hi) dg++;
-        if (dg == p10) { I++; n += fmt_u64(I, out + n); out[n++] = '.'; out[n++] = '0'; return n; }
-        n += fmt_u64(I, out + n);
-        out[n++] = '.';
-        fmt_u64_pad(dg, j, out + n);
-        return n + j;
+        if (dg == p10) return jp_fixed(neg, I + 1, 0, 1);
+        return jp_fixed(neg, I, dg, j);
     }
-    return -1;
+    return p;
+}
+template <typename O>
+SOFA_HD int json_emit(const JPlan& p, O out) {
+    if (p.kind == JP_NULL) { out[0] = 'n'; out[1] = 'u'; out[2] = 'l'; out[3] = 'l'; return 4; }
+    int n = 0;
+    if (p.neg) out[n++] = '-';
+    if (p.kind == JP_FIXED) {
+        n += fmt_u64(p.I, out + n);
+        out[n++] = '.';
+        fmt_u64_pad(p.dg, p.nd, out + n);
+        return n + p.nd;
+    }
+    char ds[8];
+    fmt_u32_pad((uint32_t)p.dg, p.nd, ds);
+    out[n++] = ds[0];
+    if (p.nd > 1) { out[n++] = '.'; for (int k = 1; k < p.nd; k++) out[n++] = ds[k]; }
+    out[n++] = 'e'; out[n++] = '-';
+    out[n++] = (char)('0' + p.ex / 10); out[n++] = (char)('0' + p.ex % 10);
+    return n;
+}
+template <typename O>
+SOFA_HD int json_double(double x, O out) {
+    JPlan p = json_plan(x);
+    if (p.kind == JP_BAD) return -1;
+    return json_emit(p, out);
 }
 
 // ----------------------------------------------------------------------------- double-double

@@ -514,44 +514,71 @@ struct CsvWrite {
     SOFA_HD void put(char ch) { if (ch == '"') out[n++] = '"'; out[n++] = ch; }
 };
 
-// returns total row length (incl. '\n'), or -1 on an unformattable value; *name_special out
+// Float columns that can hold non-integral values (timestamp, event, duration, bandwidth) get
+// a cached digit plan; other columns are integers even when the file prints them as floats.
+SOFA_HD int fslot(int c) { return c <= 2 ? c : (c == 6 ? 3 : -1); }
+
+struct CsvRowPlan { int len; bool special; F6Plan f[4]; };
+
+// exact row length (incl. '\n') and the digit plans; len = -1 on an unformattable value
 template <class NG>
-SOFA_HD int csv_row_len(const RowVals& v, uint32_t fmask, const NG& ng, bool* name_special) {
-    *name_special = false;
-    if (!v.valid) return 13;                       // twelve commas + '\n'
-    int n = 0;
+SOFA_HD CsvRowPlan csv_row_plan(const RowVals& v, uint32_t fmask, const NG& ng) {
+    CsvRowPlan p; p.special = false;
+    if (!v.valid) { p.len = 13; return p; }          // twelve commas + '\n'
+    int n = 13;                                      // separators
+    bool bad = false;
+#pragma unroll
     for (int c = 0; c < 13; c++) {
         if (c == 11) {
             CsvCount k; ng.gen(k);
             n += k.len + (k.special ? 2 : 0);
-            *name_special = k.special;
+            p.special = k.special;
         } else {
             bool isf; double f; int64_t i;
             col_value(v, c, fmask, &isf, &f, &i);
-            if (isf) { int l = len_fixed6(f); if (l < 0) return -1; n += l; }
-            else n += len_i64(i);
+            if (isf) {
+                F6Plan q = fixed6_plan(f);
+                if (!q.ok) bad = true;
+                n += q.len;
+                if (fslot(c) >= 0) p.f[fslot(c)] = q;
+            } else n += len_i64(i);
         }
-        n += 1;                                    // ',' or '\n'
     }
-    return n;
+    p.len = bad ? -1 : n;
+    return p;
 }
 template <class NG, typename O>
-SOFA_HD int csv_row_write(const RowVals& v, uint32_t fmask, const NG& ng, bool name_special, O out) {
+SOFA_HD int csv_row_emit(const RowVals& v, uint32_t fmask, const NG& ng, const CsvRowPlan& p, O out) {
     if (!v.valid) { for (int i = 0; i < 12; i++) out[i] = ','; out[12] = '\n'; return 13; }
     int n = 0;
+#pragma unroll
     for (int c = 0; c < 13; c++) {
         if (c == 11) {
-            if (name_special) out[n++] = '"';
+            if (p.special) out[n++] = '"';
             CsvWrite<O> k{out + n, 0}; ng.gen(k); n += k.n;
-            if (name_special) out[n++] = '"';
+            if (p.special) out[n++] = '"';
         } else {
             bool isf; double f; int64_t i;
             col_value(v, c, fmask, &isf, &f, &i);
-            if (isf) n += fmt_fixed6(f, out + n); else n += fmt_i64(i, out + n);
+            if (isf) n += (fslot(c) >= 0) ? fixed6_emit(p.f[fslot(c)], out + n) : fmt_fixed6(f, out + n);
+            else n += fmt_i64(i, out + n);
         }
         out[n++] = (c == 12) ? '\n' : ',';
     }
     return n;
+}
+// returns total row length (incl. '\n'), or -1 on an unformattable value; *name_special out
+template <class NG>
+SOFA_HD int csv_row_len(const RowVals& v, uint32_t fmask, const NG& ng, bool* name_special) {
+    CsvRowPlan p = csv_row_plan(v, fmask, ng);
+    *name_special = p.special;
+    return p.len;
+}
+template <class NG, typename O>
+SOFA_HD int csv_row_write(const RowVals& v, uint32_t fmask, const NG& ng, bool name_special, O out) {
+    CsvRowPlan p = csv_row_plan(v, fmask, ng);
+    (void)name_special;
+    return csv_row_emit(v, fmask, ng, p, out);
 }
 
 // ============================================================================ JSON records
@@ -623,18 +650,48 @@ struct JsonWrite {
 
 // Record text: {"x": V, "event": V, "y": V, "deviceId": V, ... "name": "S", "category": V}
 // (x=timestamp, y=duration renamed, :351-355).  Keys are written with fully unrolled
-// constant stores (one store per byte, no loads).
+// constant stores (one store per byte, no loads).  A record is emitted as ", " + {...}; the
+// series writer drops the first two bytes.
 #define SOFA_JKEY(lit) do { const char k_[] = lit; _Pragma("unroll") for (int i_ = 0; i_ < (int)sizeof(k_) - 1; i_++) out[n + i_] = k_[i_]; n += (int)sizeof(k_) - 1; } while (0)
 #define SOFA_JNUM(c) do { \
         if (!v.valid) { out[n] = 'n'; out[n + 1] = 'u'; out[n + 2] = 'l'; out[n + 3] = 'l'; n += 4; } \
         else { bool isf; double f; int64_t i; col_value(v, c, fmask, &isf, &f, &i); \
-               if (isf) { int l = json_double(f, out + n); if (l < 0) return -1; n += l; } else n += fmt_i64(i, out + n); } \
+               if (isf) n += (fslot(c) >= 0) ? json_emit(p.f[fslot(c) < 0 ? 0 : fslot(c)], out + n) : json_double(f, out + n); \
+               else n += fmt_i64(i, out + n); } \
     } while (0)
+// total bytes of the 13 key texts + ", " + "{" ... "}" framing
+#define SOFA_JSON_FIXED (2 + 6 + 11 + 7 + 14 + 14 + 13 + 15 + 13 + 13 + 9 + 9 + 10 + 14 + 1)
 
-// A record is emitted as ", " + {...}; the series writer drops the first two bytes.
-// returns length, or -1 (unformattable number) / -2 (invalid UTF-8)
+struct JsonRowPlan { int len; JPlan f[4]; };     // len: -1 unformattable number, -2 invalid UTF-8
+
+template <class NG>
+SOFA_HD JsonRowPlan json_row_plan(const RowVals& v, uint32_t fmask, const NG& ng) {
+    JsonRowPlan p;
+    int n = SOFA_JSON_FIXED;
+    if (!v.valid) { p.len = n + 13 * 4; return p; }
+    int bad = 0;
+#pragma unroll
+    for (int c = 0; c < 13; c++) {
+        if (c == 11) {
+            JsonCount k; ng.gen(k);
+            if (k.e.bad || k.e.need) bad = -2;
+            n += k.len + 2;
+        } else {
+            bool isf; double f; int64_t i;
+            col_value(v, c, fmask, &isf, &f, &i);
+            if (isf) {
+                JPlan q = json_plan(f);
+                if (q.kind == JP_BAD && !bad) bad = -1;
+                n += q.len;
+                if (fslot(c) >= 0) p.f[fslot(c)] = q;
+            } else n += len_i64(i);
+        }
+    }
+    p.len = bad ? bad : n;
+    return p;
+}
 template <class NG, typename O>
-SOFA_HD int json_row_write(const RowVals& v, uint32_t fmask, const NG& ng, O out) {
+SOFA_HD int json_row_emit(const RowVals& v, uint32_t fmask, const NG& ng, const JsonRowPlan& p, O out) {
     int n = 0;
     SOFA_JKEY(", {\"x\": "); SOFA_JNUM(0);
     SOFA_JKEY(", \"event\": "); SOFA_JNUM(1);
@@ -652,7 +709,6 @@ SOFA_HD int json_row_write(const RowVals& v, uint32_t fmask, const NG& ng, O out
     else {
         out[n++] = '"';
         JsonWrite<O> w{out + n, 0, JsonEsc()}; ng.gen(w);
-        if (w.e.bad || w.e.need) return -2;
         n += w.n;
         out[n++] = '"';
     }
@@ -660,25 +716,16 @@ SOFA_HD int json_row_write(const RowVals& v, uint32_t fmask, const NG& ng, O out
     out[n++] = '}';
     return n;
 }
-// total bytes of the 13 key texts + ", " + "{" ... "}" framing
-#define SOFA_JSON_FIXED (2 + 6 + 11 + 7 + 14 + 14 + 13 + 15 + 13 + 13 + 9 + 9 + 10 + 14 + 1)
+// returns length, or -1 (unformattable number) / -2 (invalid UTF-8)
+template <class NG, typename O>
+SOFA_HD int json_row_write(const RowVals& v, uint32_t fmask, const NG& ng, O out) {
+    JsonRowPlan p = json_row_plan(v, fmask, ng);
+    if (p.len < 0) return p.len;
+    return json_row_emit(v, fmask, ng, p, out);
+}
 template <class NG>
 SOFA_HD int json_row_len(const RowVals& v, uint32_t fmask, const NG& ng) {
-    int n = SOFA_JSON_FIXED;
-    if (!v.valid) return n + 13 * 4;
-    for (int c = 0; c < 13; c++) {
-        if (c == 11) {
-            JsonCount k; ng.gen(k);
-            if (k.e.bad || k.e.need) return -2;
-            n += k.len + 2;
-        } else {
-            bool isf; double f; int64_t i;
-            col_value(v, c, fmask, &isf, &f, &i);
-            if (isf) { char b[40]; int l = json_double(f, (char*)b); if (l < 0) return -1; n += l; }
-            else n += len_i64(i);
-        }
-    }
-    return n;
+    return json_row_plan(v, fmask, ng).len;
 }
 
 // ============================================================================ keyword filters

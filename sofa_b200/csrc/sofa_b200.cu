@@ -570,7 +570,7 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
     SrcView v = make_view(c, k, true);
     uint64_t per_row = FMT == FMT_CSV ? 96 : 230;
     uint64_t cap = sel_hint * per_row + text_share + (1 << 16);
-    uint32_t slot_bytes = k == SRC_GPU ? 64 * 1024 : 48 * 1024;
+    uint32_t slot_bytes = 40 * 1024;
     for (int attempt = 0; attempt < 6; attempt++, cap *= 2) {
         char* outp = nullptr;
         { int ra = out_alloc(c, outslot, cap, &outp); if (ra) return ra; }
@@ -584,9 +584,9 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
         a.slot_bytes = slot_bytes;
         int kk = FMT == FMT_CSV ? K_CSV_WRITE : K_JSON_WRITE;
         unsigned g = (unsigned)nblocks;
-        if (k == SRC_PERF) LAUNCH(c, kk, (k_emit_fused<SRC_PERF, FMT><<<g, EMIT_TPB, slot_bytes, c->stream>>>(v, a)));
-        else if (k == SRC_GPU) LAUNCH(c, kk, (k_emit_fused<SRC_GPU, FMT><<<g, EMIT_TPB, slot_bytes, c->stream>>>(v, a)));
-        else LAUNCH(c, kk, (k_emit_fused<SRC_NET, FMT><<<g, EMIT_TPB, slot_bytes, c->stream>>>(v, a)));
+        if (k == SRC_PERF) LAUNCH(c, kk, (k_emit_fused<SRC_PERF, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+        else if (k == SRC_GPU) LAUNCH(c, kk, (k_emit_fused<SRC_GPU, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+        else LAUNCH(c, kk, (k_emit_fused<SRC_NET, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
         unsigned long long total = 0, cnt = 0; unsigned int ovf = 0;
         CK_S(small_d2h(c, &total, c->d_err + 11, 8));
         CK_S(small_d2h(c, &cnt, c->d_err + 1, 8));

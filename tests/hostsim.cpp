@@ -20,12 +20,12 @@ void hs_log2_many(const double* x, double* y, long n) { for (long i = 0; i < n; 
 // batch helpers: strings are packed back to back, off[i]..off[i+1]
 void hs_json_many(const double* x, long n, char* out, long* off) {
     long o = 0;
-    for (long i = 0; i < n; i++) { off[i] = o; int l = json_double(x[i], out + o); if (l > 0) o += l; else { out[o++] = '?'; } }
+    for (long i = 0; i < n; i++) { off[i] = o; int l = json_double(x[i], out + o); JPlan p = json_plan(x[i]); if (l > 0 && p.len == l) o += l; else { out[o++] = '?'; } }
     off[n] = o;
 }
 void hs_fixed6_many(const double* x, long n, char* out, long* off) {
     long o = 0;
-    for (long i = 0; i < n; i++) { off[i] = o; int l = fmt_fixed6(x[i], out + o); if (l > 0) o += l; else { out[o++] = '?'; } }
+    for (long i = 0; i < n; i++) { off[i] = o; int l = fmt_fixed6(x[i], out + o); if (l > 0 && len_fixed6(x[i]) == l) o += l; else { out[o++] = '?'; } }
     off[n] = o;
 }
 }
