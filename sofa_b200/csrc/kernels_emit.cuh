@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) k_filter(SrcView src, uint64_t ncand, uin
     if (c < ncand) {
         uint64_t row = c * stride;
         with_row<KIND, true>(src, row, c, [&](const RowVals& v, const auto& ng) {
-            if (v.valid) { MatchSink ms(&sft); ng.gen(ms); hit = ms.hit; }
+            if (v.valid) { MatchSink ms(&sft); ng.gen(ms); hit = ms.hits(); }
         });
         mask[c] = (uint8_t)hit;
     }

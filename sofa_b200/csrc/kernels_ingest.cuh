@@ -110,14 +110,21 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
         for (uint32_t i = threadIdx.x; i < (stage_len >> 4); i += blockDim.x) s4[i] = g4[i];
     }
     __syncthreads();
-    // each thread scans a word-aligned chunk of the staged bytes for newlines in [qlo, qhi)
+    // each thread scans an 8-byte-aligned chunk of the staged bytes for newlines in [qlo, qhi),
+    // one 64-bit shared-memory load per 8 bytes (odd word stride: conflict free)
     uint32_t scan_len = (uint32_t)(qhi > s0 ? qhi - s0 : 0);
-    uint32_t chunk = ((scan_len + blockDim.x - 1) / blockDim.x + 3) & ~3u;
-    if (((chunk >> 2) & 1u) == 0) chunk += 4;          // odd word stride: bank-conflict-free chunk scan
+    uint32_t chunk = ((scan_len + blockDim.x - 1) / blockDim.x + 7) & ~7u;
+    if (((chunk >> 3) & 1u) == 0) chunk += 8;
     uint32_t c0 = threadIdx.x * chunk, c1 = c0 + chunk < scan_len ? c0 + chunk : scan_len;
     uint32_t lo_rel = (uint32_t)(qlo - s0);
     uint32_t cnt = 0;
-    for (uint32_t i = c0; i < c1; i++) cnt += (i >= lo_rel && stage[i] == '\n');
+    const uint64_t* st8 = reinterpret_cast<const uint64_t*>(stage);
+    for (uint32_t i = c0; i < c1; i += 8) {
+        uint32_t m = eq8(st8[i >> 3], '\n');
+        if (i < lo_rel) m &= (lo_rel - i >= 8) ? 0u : ~((1u << (lo_rel - i)) - 1u);
+        if (i + 8 > c1) m &= (1u << (c1 - i)) - 1u;
+        cnt += __popc(m);
+    }
     if (threadIdx.x == 0 && b0 == begin && begin < end) cnt += 1;
     uint32_t total;
     uint32_t ex = block_excl_scan(cnt, &total, sm);
@@ -128,7 +135,12 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
     {
         uint32_t k = ex;
         if (threadIdx.x == 0 && b0 == begin && begin < end) lstart[k++] = (uint32_t)(begin - s0);
-        for (uint32_t i = c0; i < c1; i++) if (i >= lo_rel && stage[i] == '\n') lstart[k++] = i + 1;
+        for (uint32_t i = c0; i < c1; i += 8) {
+            uint32_t m = eq8(st8[i >> 3], '\n');
+            if (i < lo_rel) m &= (lo_rel - i >= 8) ? 0u : ~((1u << (lo_rel - i)) - 1u);
+            if (i + 8 > c1) m &= (1u << (c1 - i)) - 1u;
+            while (m) { lstart[k++] = i + (uint32_t)ctz32(m) + 1; m &= m - 1; }
+        }
     }
     __syncthreads();
     uint32_t stage_end = (uint32_t)(s1 - s0);           // staged bytes that belong to the text

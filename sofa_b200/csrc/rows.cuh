@@ -71,18 +71,96 @@ SOFA_HD void put_span(K& k, const char* p, int len, bool wide) {
     for (int i = 0; i < len; i++) k.put(p[i]);
 }
 
+// ---------------------------------------------------------------------------- SWAR line scanning
+// Lines are scanned 8 bytes at a time: aligned 64-bit loads (shared memory on the device),
+// byte classes evaluated on all 8 lanes with carry-free 7-bit arithmetic, the 8 flag bits
+// gathered with one multiply.  Word j of a line covers positions [8j - sh, 8j - sh + 8), where
+// sh is the misalignment of the line's first byte; positions outside [0, n) are masked off.
+SOFA_HD uint64_t line_word(const char* s, int n, int sh, int j) {
+#if defined(__CUDA_ARCH__)
+    (void)n;
+    return *reinterpret_cast<const uint64_t*>(s - sh + 8 * j);
+#else
+    uint64_t w = 0;
+    for (int b = 0; b < 8; b++) { int p = 8 * j - sh + b; if (p >= 0 && p < n) w |= (uint64_t)(unsigned char)s[p] << (8 * b); }
+    return w;
+#endif
+}
+SOFA_HD int line_misalign(const char* s) {
+#if defined(__CUDA_ARCH__)
+    return (int)((unsigned long long)s & 7ull);
+#else
+    return (int)((unsigned long long)s & 7ull);        // exercised by the CPU fuzz tests as well
+#endif
+}
+SOFA_HD uint32_t valid8(int n, int sh, int j) {           // bit b set iff 0 <= 8j - sh + b < n
+    int lo = sh - 8 * j; if (lo < 0) lo = 0;
+    int hi = n + sh - 8 * j; if (hi > 8) hi = 8;
+    if (hi <= lo) return 0;
+    return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+}
+SOFA_HD uint32_t gather8(uint64_t hb) {                   // bit 7 of byte b -> bit b
+    return (uint32_t)((((hb >> 7) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
+}
+SOFA_HD uint32_t eq8(uint64_t w, unsigned char c) {       // lanes equal to c (c < 128)
+    const uint64_t K7 = 0x7f7f7f7f7f7f7f7full, K8 = 0x8080808080808080ull;
+    uint64_t t = (w & K7) ^ (0x0101010101010101ull * c);
+    uint64_t ne = ((t + K7) | w) & K8;                    // low 7 bits differ, or byte >= 128
+    return gather8(~ne & K8);
+}
+SOFA_HD uint32_t nonspace8(uint64_t w) {                  // lanes that are NOT str.split() whitespace
+    const uint64_t K7 = 0x7f7f7f7f7f7f7f7full, K8 = 0x8080808080808080ull;
+    uint64_t L = w & K7;
+    uint64_t eq20 = ~(((L ^ 0x2020202020202020ull) + K7)) & K8;
+    uint64_t r1 = (L + 0x7777777777777777ull) & ~(L + 0x7272727272727272ull) & K8;     // 9..13
+    uint64_t r2 = (L + 0x6464646464646464ull) & ~(L + 0x6060606060606060ull) & K8;     // 28..31
+    uint64_t sp = (eq20 | r1 | r2) & ~w & K8;             // bytes >= 128 are never whitespace
+    return gather8(~sp & K8);
+}
+SOFA_HD int ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
 // str.split() with no argument (ASCII whitespace); returns number of tokens, capped at maxt.
 template <typename S>
 SOFA_HD int tokenize(S s, int n, Tok* t, int maxt) {
-    int k = 0, i = 0;
-    while (i < n && k < maxt) {
-        while (i < n && is_space((unsigned char)s[i])) i++;
-        if (i >= n) break;
-        int a = i;
-        while (i < n && !is_space((unsigned char)s[i])) i++;
-        t[k].a = a; t[k].b = i; k++;
+    int k = 0;
+    const int sh = line_misalign(s);
+    const int nw = (n + sh + 7) >> 3;
+    uint32_t in = 0;                                      // class of the previous byte (1 = token)
+    bool open = false;
+    int start = 0;
+    for (int j = 0; j < nw; j++) {
+        uint32_t m = nonspace8(line_word(s, n, sh, j)) & valid8(n, sh, j);
+        uint32_t tr = (m ^ ((m << 1) | in)) & 0xffu;      // byte positions where the class changes
+        in = (m >> 7) & 1u;
+        while (tr) {
+            int p = 8 * j - sh + ctz32(tr);
+            tr &= tr - 1;
+            if (!open) { start = p; open = true; }
+            else { t[k].a = start; t[k].b = p; k++; open = false; if (k >= maxt) return k; }
+        }
     }
+    if (open && k < maxt) { t[k].a = start; t[k].b = n; k++; }
     return k;
+}
+
+// first position in [from, to) holding byte c (c < 128), or -1; 8 bytes per step
+SOFA_HD int find_char(const char* s, int n, int from, int to, unsigned char c) {
+    if (from >= to) return -1;
+    const int sh = line_misalign(s);
+    int j0 = (from + sh) >> 3, j1 = (to - 1 + sh) >> 3;
+    for (int j = j0; j <= j1; j++) {
+        uint32_t m = eq8(line_word(s, n, sh, j), c) & valid8(to, sh, j);
+        int base = 8 * j - sh;
+        if (base < from) m &= ~((1u << (from - base)) - 1u);
+        if (m) return base + ctz32(m);
+    }
+    return -1;
 }
 
 SOFA_HD int num_status_to_err(int st, bool is_float) {
@@ -119,8 +197,9 @@ SOFA_HD int parse_perf(S s, int n, const IngestCfg& c, PerfRow* r) {
     if (nt < 7 + sh) return E_FEW_TOKENS;
     double time, counts;
     {
-        int a = t[1 + sh].a, b = t[1 + sh].b, e = a;
-        while (e < b && s[e] != ':') e++;                    // .split(':')[0]
+        int a = t[1 + sh].a, b = t[1 + sh].b;
+        int e = find_char(s, n, a, b, ':');                  // .split(':')[0]
+        if (e < 0) e = b;
         int st = parse_double(s + a, e - a, &time);
         if (st) return num_status_to_err(st, true);
         st = parse_double(s + t[2 + sh].a, t[2 + sh].b - t[2 + sh].a, &counts);
@@ -152,11 +231,11 @@ SOFA_HD int parse_perf(S s, int n, const IngestCfg& c, PerfRow* r) {
     r->event = log10_cr(event_raw);
     r->dur = dur;
     {   // int(fields[0].split('/')[0]), int(fields[0].split('/')[1])
-        int a = t[0].a, b = t[0].b, s1 = a;
-        while (s1 < b && s[s1] != '/') s1++;
-        if (s1 >= b) return E_FEW_TOKENS;
-        int s2 = s1 + 1;
-        while (s2 < b && s[s2] != '/') s2++;
+        int a = t[0].a, b = t[0].b;
+        int s1 = find_char(s, n, a, b, '/');
+        if (s1 < 0) return E_FEW_TOKENS;
+        int s2 = find_char(s, n, s1 + 1, b, '/');
+        if (s2 < 0) s2 = b;
         int64_t p, q;
         int st = parse_i64(s + a, s1 - a, &p);
         if (st) return num_status_to_err(st, false);
@@ -169,21 +248,20 @@ SOFA_HD int parse_perf(S s, int n, const IngestCfg& c, PerfRow* r) {
     r->sym_off = (uint16_t)t[5 + sh].a; r->sym_len = (uint16_t)(t[5 + sh].b - t[5 + sh].a);
     r->dso_off = (uint16_t)t[6 + sh].a; r->dso_len = (uint16_t)(t[6 + sh].b - t[6 + sh].a);
     {   // precompute the viz slice: name = '[' evt ']' sym dso ; [find(']')+1 : find('+')] cut at '@'
-        bool exotic = false;
-        for (int i = 0; i < r->evt_len; i++) { char ch = s[r->evt_off + i]; if (ch == ']' || ch == '+') exotic = true; }
+        int eo = r->evt_off, el = r->evt_len;
+        bool exotic = find_char(s, n, eo, eo + el, ']') >= 0 || find_char(s, n, eo, eo + el, '+') >= 0;
         if (exotic) { r->va_len = 0xffff; r->vb_len = 0; }
         else {
-            int sl = r->sym_len, dl = r->dso_len;
-            int plus = -1;
-            for (int i = 0; i < sl && plus < 0; i++) if (s[r->sym_off + i] == '+') plus = i;
-            for (int i = 0; i < dl && plus < 0; i++) if (s[r->dso_off + i] == '+') plus = sl + i;
+            int so = r->sym_off, sl = r->sym_len, dof = r->dso_off, dl = r->dso_len;
+            int plus = find_char(s, n, so, so + sl, '+');
+            if (plus >= 0) plus -= so;
+            else { plus = find_char(s, n, dof, dof + dl, '+'); if (plus >= 0) plus = sl + (plus - dof); }
             int b = plus >= 0 ? plus : sl + dl - 1;           // [a:-1] when there is no '+'
             if (b < 0) b = 0;
             int va = b < sl ? b : sl, vb = b > sl ? b - sl : 0;
-            int at = -1;
-            for (int i = 0; i < va && at < 0; i++) if (s[r->sym_off + i] == '@') at = i;
-            if (at >= 0) { va = at; vb = 0; }
-            else { for (int i = 0; i < vb && at < 0; i++) if (s[r->dso_off + i] == '@') at = i; if (at >= 0) vb = at; }
+            int at = find_char(s, n, so, so + va, '@');
+            if (at >= 0) { va = at - so; vb = 0; }
+            else { at = find_char(s, n, dof, dof + vb, '@'); if (at >= 0) vb = at - dof; }
             r->va_len = (uint16_t)va; r->vb_len = (uint16_t)vb;
         }
     }
@@ -283,11 +361,19 @@ SOFA_HD int parse_gpu(S s, int n, const IngestCfg& c, GpuRow* r) {
                    c.idx_name, c.idx_srcctx, c.idx_dstctx};
     for (int k = 0; k < 9; k++) { fa[k] = -1; fb[k] = -1; }
     int f = 0, a = 0;
-    for (int i = 0; i <= n; i++) {
-        if (i == n || s[i] == ',') {
-            for (int k = 0; k < 9; k++) if (want[k] == f) { fa[k] = a; fb[k] = i; }
-            f++; a = i + 1;
+    {
+        const int sh = line_misalign(s);
+        const int nw = (n + sh + 7) >> 3;
+        for (int j = 0; j < nw; j++) {
+            uint32_t m = eq8(line_word(s, n, sh, j), ',') & valid8(n, sh, j);
+            while (m) {
+                int i = 8 * j - sh + ctz32(m);
+                m &= m - 1;
+                for (int k = 0; k < 9; k++) if (want[k] == f) { fa[k] = a; fb[k] = i; }
+                f++; a = i + 1;
+            }
         }
+        for (int k = 0; k < 9; k++) if (want[k] == f) { fa[k] = a; fb[k] = n; }
     }
     if (fa[6] < 0 || fa[0] < 0 || fa[1] < 0) return E_FEW_TOKENS;
     double start, dur;
@@ -735,18 +821,54 @@ struct FilterTable {
     uint32_t mask[8][256];
     uint32_t final_bit[8];
     int nk;
+    // packed variant: all keywords laid side by side in one 64-bit shift-and state (used when the
+    // summed keyword length is <= 64): one table load + 4 ALU ops per byte for every keyword at once
+    uint64_t pmask[256];
+    uint64_t pstart, pfinal;
+    uint8_t pfinal_pos[8];
+    int packed;
 };
 struct MatchSink {
-    const FilterTable* t; uint32_t st[8]; uint32_t hit;
-    SOFA_HD MatchSink(const FilterTable* tt) : t(tt), hit(0) { for (int k = 0; k < 8; k++) st[k] = 0; }
+    const FilterTable* t; uint32_t st[8]; uint32_t hit; uint64_t ps, phit;
+    SOFA_HD MatchSink(const FilterTable* tt) : t(tt), hit(0), ps(0), phit(0) { for (int k = 0; k < 8; k++) st[k] = 0; }
     SOFA_HD void put(char ch) {
         unsigned char b = (unsigned char)ch;
+        if (t->packed) {
+            ps = ((ps << 1) | t->pstart) & t->pmask[b];
+            phit |= ps & t->pfinal;
+            return;
+        }
         for (int k = 0; k < t->nk; k++) {
             st[k] = ((st[k] << 1) | 1u) & t->mask[k][b];
             if (st[k] & t->final_bit[k]) hit |= 1u << k;
         }
     }
+    SOFA_HD uint32_t hits() const {
+        if (!t->packed) return hit;
+        uint32_t h = 0;
+        for (int k = 0; k < t->nk; k++) if ((phit >> t->pfinal_pos[k]) & 1) h |= 1u << k;
+        return h;
+    }
 };
+// host-side table construction (keywords: 1..32 bytes each, at most 8)
+inline void filter_table_build(FilterTable* ft, int nkw, const char* const* kws, const size_t* lens) {
+    for (int i = 0; i < 8; i++) { ft->final_bit[i] = 0; ft->pfinal_pos[i] = 0; for (int c = 0; c < 256; c++) ft->mask[i][c] = 0; }
+    for (int c = 0; c < 256; c++) ft->pmask[c] = 0;
+    ft->nk = nkw; ft->pstart = 0; ft->pfinal = 0;
+    size_t tot = 0;
+    for (int i = 0; i < nkw; i++) tot += lens[i];
+    ft->packed = (nkw > 0 && tot <= 64) ? 1 : 0;
+    size_t pos = 0;
+    for (int i = 0; i < nkw; i++) {
+        for (size_t j = 0; j < lens[i]; j++) {
+            ft->mask[i][(unsigned char)kws[i][j]] |= 1u << j;
+            if (ft->packed) ft->pmask[(unsigned char)kws[i][j]] |= 1ull << (pos + j);
+        }
+        ft->final_bit[i] = 1u << (lens[i] - 1);
+        if (ft->packed) { ft->pstart |= 1ull << pos; ft->pfinal |= 1ull << (pos + lens[i] - 1); ft->pfinal_pos[i] = (uint8_t)(pos + lens[i] - 1); }
+        pos += lens[i];
+    }
+}
 
 // FNV-1a 64 over generated characters (name dictionary keys)
 struct HashSink {

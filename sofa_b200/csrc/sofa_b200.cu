@@ -51,6 +51,7 @@ struct Source {
     DevBuf mhz;
     DevBuf mask; uint32_t mask_stride = 0; int nkw = 0;      // filter masks
     uint64_t filter_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t flags_stride[2] = {0, 0}, flags_val[2] = {0, 0};      // cached sofa_b200_row_flags results
     DevBuf vizhash, viz_id; uint32_t viz_stride = 0; bool viz_ready = false;
     DevBuf dict_hash, dict_off, dict_blob; int dict_n = 0;
 };
@@ -409,6 +410,7 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     cfg.mhz_xp = s.mhz.as<double>(); cfg.mhz_fp = s.mhz.as<double>() + cfg.n_mhz;
     s.cfg = cfg;
     s.parsed = false; s.viz_ready = false; s.mask_stride = 0;
+    s.flags_stride[0] = s.flags_stride[1] = 0;
     if (wait_upload(c, k)) return SOFA_ERR_CUDA;
     uint64_t begin = s.data_off, end = s.nbytes;
     if (end <= begin) { s.n_rows = 0; s.parsed = true; if (n_rows) *n_rows = 0; return 0; }
@@ -461,6 +463,7 @@ int sofa_b200_row_flags(sofa_ctx* c, int k, uint32_t stride, uint32_t* flags) {
     Source& s = c->src[k];
     *flags = 0;
     if (k == SRC_PERF || s.n_rows == 0) return 0;
+    for (int i = 0; i < 2; i++) if (s.flags_stride[i] == stride) { *flags = s.flags_val[i]; return 0; }
     uint64_t ncand = cdiv(s.n_rows, stride);
     CK(cudaMemsetAsync(c->d_flags + 1, 0, 4, c->stream));
     SrcView v = make_view(c, k, false);
@@ -469,6 +472,7 @@ int sofa_b200_row_flags(sofa_ctx* c, int k, uint32_t stride, uint32_t* flags) {
     CK_S(small_d2h(c, flags, c->d_flags + 1, 4));
     CK_S(stream_sync(c));
     CK(cudaGetLastError());
+    { int slot = s.flags_stride[0] == 0 ? 0 : 1; s.flags_stride[slot] = stride; s.flags_val[slot] = *flags; }
     return 0;
 }
 
@@ -730,13 +734,12 @@ int sofa_b200_set_filters(sofa_ctx* c, int k, uint32_t stride, int32_t nkw, cons
         FAIL(SOFA_ERR_STATE, "set_filters(perf): call viz_mangled + set_demangled for this stride first");
     FilterTable ft;
     memset(&ft, 0, sizeof ft);
-    ft.nk = nkw;
+    size_t lens[8] = {0};
     for (int i = 0; i < nkw; i++) {
-        size_t L = strlen(kws[i]);
-        if (L == 0 || L > 32) FAIL(SOFA_ERR_ARG, "set_filters: keyword length must be 1..32 bytes");
-        for (size_t j = 0; j < L; j++) ft.mask[i][(unsigned char)kws[i][j]] |= 1u << j;
-        ft.final_bit[i] = 1u << (L - 1);
+        lens[i] = strlen(kws[i]);
+        if (lens[i] == 0 || lens[i] > 32) FAIL(SOFA_ERR_ARG, "set_filters: keyword length must be 1..32 bytes");
     }
+    filter_table_build(&ft, nkw, kws, lens);
     uint64_t ncand = cdiv(s.n_rows, stride);
     ENSURE(c->ftable, sizeof(FilterTable));
     ENSURE(s.mask, ncand + 16);

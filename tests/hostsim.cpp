@@ -70,7 +70,7 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
     long o = 0, row = 0, pos = 0, cnt = 0;
     unsigned fl = 0;
     FilterTable ft; memset(&ft, 0, sizeof(ft));
-    if (kw) { int L = (int)strlen(kw); ft.nk = 1; for (int i = 0; i < L; i++) ft.mask[0][(unsigned char)kw[i]] |= 1u << i; ft.final_bit[0] = 1u << (L - 1); }
+    if (kw) { size_t L = strlen(kw); const char* ks[1] = {kw}; filter_table_build(&ft, 1, ks, &L); }
     while (pos < nbytes) {
         long e = pos; while (e < nbytes && text[e] != '\n') e++;
         long linelen = e - pos;                    // without '\n'
@@ -87,7 +87,7 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
                 else if (sel) {
                     DictVizName vz{PerfVizName<const char*>{ng}, dict};
                     bool take = true;
-                    if (mode == 2) { MatchSink ms(&ft); vz.gen(ms); take = ms.hit != 0; }
+                    if (mode == 2) { MatchSink ms(&ft); vz.gen(ms); take = ms.hits() != 0; }
                     if (take) { int l = json_row_len(v, fmask, vz); if (l < 0) err = E_FORMAT; else { len = json_row_write(v, fmask, vz, out + o); if (len != l) err = 99; } }
                 }
             }
@@ -100,7 +100,7 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
                 if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
                 else {
                     bool take = (mode == 1) ? sel : true;
-                    if (mode == 2) { MatchSink ms(&ft); ng.gen(ms); take = ms.hit != 0; }
+                    if (mode == 2) { MatchSink ms(&ft); ng.gen(ms); take = ms.hits() != 0; }
                     if (take) { int l = json_row_len(v, fmask, ng); if (l < 0) err = E_FORMAT; else { len = json_row_write(v, fmask, ng, out + o); if (len != l) err = 99; } }
                 }
             }
@@ -150,4 +150,12 @@ double hs_pairwise_par(const double* a, unsigned long long n, int depth) {
     return 0.0 + part[0];
 }
 double hs_round6(double x) { return round6_value(x); }
+}
+
+// ---------------------------------------------------------------- tokenizer fuzz hook
+extern "C" int hs_tokenize(const char* s, int n, int* ab, int maxt) {
+    Tok t[16];
+    int k = tokenize(s, n, t, maxt > 16 ? 16 : maxt);
+    for (int i = 0; i < k; i++) { ab[2 * i] = t[i].a; ab[2 * i + 1] = t[i].b; }
+    return k;
 }

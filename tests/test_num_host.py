@@ -251,3 +251,29 @@ def test_round6_is_csv_roundtrip(hs):
         if abs(x) >= 2.0 ** 62:
             continue
         assert hs.hs_round6(x) == float("%.6f" % x), x
+
+
+def test_swar_tokenizer_matches_str_split(hs):
+    rng = random.Random(41)
+    alphabet = " \t\n\r\x0b\x0c\x1c\x1d\x1e\x1f" + "ab01:/[]+-_().,\x7f\x01\x08\x0e\x1b\x21"
+    ab = (ctypes.c_int * 32)()
+    for trial in range(20000):
+        n = rng.randint(0, 90)
+        s = "".join(rng.choice(alphabet) if rng.random() < 0.6 else rng.choice("xyz") for _ in range(n))
+        b = s.encode("latin-1")
+        pad = rng.randint(0, 7)                        # vary the pointer alignment
+        buf = ctypes.create_string_buffer(b"\n" * pad + b + b"\n" * 8)
+        k = hs.hs_tokenize(ctypes.cast(ctypes.addressof(buf) + pad, ctypes.c_char_p), len(b), ab, 8)
+        want = []
+        pos = 0
+        for tok in s.split():
+            a = s.index(tok, pos)
+            want.append((a, a + len(tok)))
+            pos = a + len(tok)
+        want = want[:8]
+        got = [(ab[2 * i], ab[2 * i + 1]) for i in range(k)]
+        assert got == want, (s, got, want)
+    # bytes >= 128 are not whitespace for the byte-level tokenizer
+    b = b"ab\xc2\xa0cd \xe2\x80\x83ef"
+    k = hs.hs_tokenize(b, len(b), ab, 8)
+    assert [(ab[2 * i], ab[2 * i + 1]) for i in range(k)] == [(0, 6), (7, 12)]
