@@ -146,9 +146,11 @@ __global__ void __launch_bounds__(256) k_gpu_stats(SrcView src, uint64_t n, GpuS
 
 // hash + "contains nccl" over the generated name in one pass
 struct NcclHashSink {
+    static constexpr bool WORDS = false;
     HashSink h; uint32_t w; bool hit;
     __device__ NcclHashSink() : w(0), hit(false) {}
     __device__ __forceinline__ void put(char ch) { h.put(ch); w = (w << 8) | (unsigned char)ch; hit |= (w == 0x6e63636cu); }
+    __device__ __forceinline__ void put_word(uint64_t ww, int nb) { put_word_bytes(*this, ww, nb); }
 };
 // namehash[row] = FNV-1a of the full name when it contains "nccl" (else 0); distinct hashes
 // go into an open-addressing table (value = smallest row).

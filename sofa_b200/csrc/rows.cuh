@@ -47,25 +47,56 @@ struct IngestCfg {
 
 struct Tok { int a, b; };
 
+// SWAR byte-class tests on a 64-bit word (bit 7 of each lane set where the test holds)
+SOFA_HD uint64_t lanes_eq(uint64_t w, unsigned char c) {       // lane == c  (c < 128)
+    const uint64_t K7 = 0x7f7f7f7f7f7f7f7full, K8 = 0x8080808080808080ull;
+    uint64_t t = (w & K7) ^ (0x0101010101010101ull * c);
+    return ~((t + K7) | w) & K8;
+}
+SOFA_HD uint64_t lanes_first(int nb) { return nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull); }
+
+// Default word feeder: byte by byte.  Sinks with cheap whole-word paths define put_word.
+template <class K> SOFA_HD void put_word_bytes(K& k, uint64_t w, int nb) {
+    for (int b = 0; b < nb; b++) { k.put((char)(w & 0xff)); w >>= 8; }
+}
+
 // Feed the bytes p[0..len) to a sink.  On the device, global-memory spans are read as aligned
 // 64-bit words (8x fewer load instructions than byte loads; the text buffer is padded, so the
-// over-read of the last word is safe).  `wide` is false for shared-memory / local spans.
+// over-read of the last word is safe) and handed to the sink a word at a time (put_word).
+// `wide` is false for shared-memory / local spans.
 template <class K>
 SOFA_HD void put_span(K& k, const char* p, int len, bool wide) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) || defined(SOFA_HOST_WIDE)
+#if !defined(__CUDA_ARCH__)
+#define __ldg(ptr) (*(ptr))
+#endif
     if (wide && len > 0) {
         unsigned long long a = (unsigned long long)p;
         const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a & ~7ull);
         int sh = (int)(a & 7);
         unsigned long long cur = __ldg(w++) >> (8 * sh);
         int avail = 8 - sh;
-        for (int i = 0; i < len; i++) {
-            if (avail == 0) { cur = __ldg(w++); avail = 8; }
-            k.put((char)(cur & 0xff));
-            cur >>= 8; avail--;
+        if constexpr (K::WORDS) {
+            while (true) {
+                int take = avail < len ? avail : len;
+                len -= take;
+                unsigned long long nxt = len > 0 ? __ldg(w++) : 0ull;     // issue the next load early
+                k.put_word(cur, take);
+                if (len <= 0) break;
+                cur = nxt; avail = 8;
+            }
+        } else {
+            for (int i = 0; i < len; i++) {
+                if (avail == 0) { cur = __ldg(w++); avail = 8; }
+                k.put((char)(cur & 0xff));
+                cur >>= 8; avail--;
+            }
         }
         return;
     }
+#if !defined(__CUDA_ARCH__)
+#undef __ldg
+#endif
 #endif
     (void)wide;
     for (int i = 0; i < len; i++) k.put(p[i]);
@@ -100,7 +131,9 @@ SOFA_HD uint32_t valid8(int n, int sh, int j) {           // bit b set iff 0 <= 
     return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
 }
 SOFA_HD uint32_t gather8(uint64_t hb) {                   // bit 7 of byte b -> bit b
-    return (uint32_t)((((hb >> 7) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
+    uint64_t x = (hb >> 7) & 0x0101010101010101ull;
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);          // two 32-bit multiplies (1 instruction each)
+    return ((lo * 0x01020408u) >> 24) | (((hi * 0x01020408u) >> 24) << 4);
 }
 SOFA_HD uint32_t eq8(uint64_t w, unsigned char c) {       // lanes equal to c (c < 128)
     const uint64_t K7 = 0x7f7f7f7f7f7f7f7full, K8 = 0x8080808080808080ull;
@@ -283,6 +316,7 @@ struct PerfName {
 
 // viz name = name[name.find(']')+1 : name.find('+')].split('@')[0]  (:1811-1816), before demangling
 struct FindSink {
+    static constexpr bool WORDS = false;
     int pos, first_rb, first_plus;
     SOFA_HD FindSink() : pos(0), first_rb(-1), first_plus(-1) {}
     SOFA_HD void put(char ch) {
@@ -290,14 +324,17 @@ struct FindSink {
         if (ch == '+' && first_plus < 0) first_plus = pos;
         pos++;
     }
+    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
 };
 template <class K>
 struct SliceSink {          // forwards characters [a, b) until the first '@'
+    static constexpr bool WORDS = false;
     K* k; int pos, a, b; bool stop;
     SOFA_HD void put(char ch) {
         if (pos >= a && pos < b && !stop) { if (ch == '@') stop = true; else k->put(ch); }
         pos++;
     }
+    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
 };
 template <typename S>
 struct PerfVizName {
@@ -450,7 +487,15 @@ template <class K> SOFA_HD void put_i64(K& k, int64_t v) {
 }
 
 template <class K>
-struct QuoteFilter { K* k; SOFA_HD void put(char ch) { if (ch != '"') k->put(ch); } };
+struct QuoteFilter {
+    static constexpr bool WORDS = K::WORDS;
+    K* k;
+    SOFA_HD void put(char ch) { if (ch != '"') k->put(ch); }
+    SOFA_HD void put_word(uint64_t w, int nb) {
+        if ((lanes_eq(w, '"') & lanes_first(nb)) == 0) k->put_word(w, nb);
+        else put_word_bytes(*this, w, nb);
+    }
+};
 template <typename S>
 struct GpuName {
     S line; GpuRow r; bool wide;
@@ -586,6 +631,7 @@ SOFA_HD void col_value(const RowVals& v, int c, uint32_t fmask, bool* isf, doubl
 
 // ============================================================================ CSV (QUOTE_MINIMAL)
 struct CsvCount {
+    static constexpr bool WORDS = true;
     int len; bool special;
     SOFA_HD CsvCount() : len(0), special(false) {}
     SOFA_HD void put(char ch) {
@@ -593,11 +639,27 @@ struct CsvCount {
         if (ch == '"') { len++; special = true; }
         else if (ch == ',' || ch == '\n' || ch == '\r') special = true;
     }
+    SOFA_HD void put_word(uint64_t w, int nb) {
+        uint64_t sp = (lanes_eq(w, '"') | lanes_eq(w, ',') | lanes_eq(w, '\n') | lanes_eq(w, '\r')) & lanes_first(nb);
+        if (sp == 0) len += nb; else put_word_bytes(*this, w, nb);
+    }
 };
 template <typename O>
 struct CsvWrite {
+    static constexpr bool WORDS = true;
     O out; int n;
     SOFA_HD void put(char ch) { if (ch == '"') out[n++] = '"'; out[n++] = ch; }
+    SOFA_HD void put_word(uint64_t w, int nb) {
+        if ((lanes_eq(w, '"') & lanes_first(nb)) == 0) {
+            if (nb == 8) {
+#pragma unroll
+                for (int b = 0; b < 8; b++) out[n + b] = (char)((w >> (8 * b)) & 0xff);
+            } else {
+                for (int b = 0; b < nb; b++) out[n + b] = (char)((w >> (8 * b)) & 0xff);
+            }
+            n += nb;
+        } else put_word_bytes(*this, w, nb);
+    }
 };
 
 // Float columns that can hold non-integral values (timestamp, event, duration, bandwidth) get
@@ -717,21 +779,34 @@ struct JsonEsc {
     }
 };
 SOFA_HD bool json_plain(unsigned char b) { return b >= 0x20 && b < 0x7f && b != '"' && b != '\\'; }
+// lanes that json.dump would escape: < 0x20, >= 0x7f, '"', '\\'
+SOFA_HD uint64_t json_special_lanes(uint64_t w) {
+    const uint64_t K7 = 0x7f7f7f7f7f7f7f7full, K8 = 0x8080808080808080ull;
+    uint64_t L = w & K7;
+    uint64_t lt20 = ~(L + 0x6060606060606060ull) & K8;           // low 7 bits < 0x20
+    uint64_t eq7f = (L + 0x0101010101010101ull) & K8;            // low 7 bits == 0x7f
+    return (lt20 | eq7f | (w & K8) | lanes_eq(w, '"') | lanes_eq(w, '\\')) & K8;
+}
 struct JsonCount {
+    static constexpr bool WORDS = false;
     JsonEsc e; int len;
     SOFA_HD JsonCount() : len(0) {}
     SOFA_HD void put(char ch) {
         if (e.need == 0 && json_plain((unsigned char)ch)) { len++; return; }
         char b[12]; len += e.feed((unsigned char)ch, b);
     }
+    // (a whole-word fast path measured slower here: short viz names, higher register pressure)
+    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
 };
 template <typename O>
 struct JsonWrite {
+    static constexpr bool WORDS = false;
     O out; int n; JsonEsc e;
     SOFA_HD void put(char ch) {
         if (e.need == 0 && json_plain((unsigned char)ch)) { out[n++] = ch; return; }
         char b[12]; int l = e.feed((unsigned char)ch, b); for (int i = 0; i < l; i++) out[n++] = b[i];
     }
+    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
 };
 
 // Record text: {"x": V, "event": V, "y": V, "deviceId": V, ... "name": "S", "category": V}
@@ -829,6 +904,7 @@ struct FilterTable {
     int packed;
 };
 struct MatchSink {
+    static constexpr bool WORDS = false;
     const FilterTable* t; uint32_t st[8]; uint32_t hit; uint64_t ps, phit;
     SOFA_HD MatchSink(const FilterTable* tt) : t(tt), hit(0), ps(0), phit(0) { for (int k = 0; k < 8; k++) st[k] = 0; }
     SOFA_HD void put(char ch) {
@@ -843,6 +919,7 @@ struct MatchSink {
             if (st[k] & t->final_bit[k]) hit |= 1u << k;
         }
     }
+    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
     SOFA_HD uint32_t hits() const {
         if (!t->packed) return hit;
         uint32_t h = 0;
@@ -872,15 +949,28 @@ inline void filter_table_build(FilterTable* ft, int nkw, const char* const* kws,
 
 // FNV-1a 64 over generated characters (name dictionary keys)
 struct HashSink {
+    static constexpr bool WORDS = false;
     uint64_t h; int len; char c0, c1;
     SOFA_HD HashSink() : h(1469598103934665603ull), len(0), c0(0), c1(0) {}
     SOFA_HD void put(char ch) {
         if (len == 0) c0 = ch; else if (len == 1) c1 = ch;
         h = (h ^ (unsigned char)ch) * 1099511628211ull; len++;
     }
+    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
 };
 template <typename O>
-struct RawWrite { O out; int n; SOFA_HD void put(char ch) { out[n++] = ch; } };
-struct LenSink { int len; SOFA_HD LenSink() : len(0) {} SOFA_HD void put(char) { len++; } };
+struct RawWrite {
+    static constexpr bool WORDS = false;
+    O out; int n;
+    SOFA_HD void put(char ch) { out[n++] = ch; }
+    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
+};
+struct LenSink {
+    static constexpr bool WORDS = true;
+    int len;
+    SOFA_HD LenSink() : len(0) {}
+    SOFA_HD void put(char) { len++; }
+    SOFA_HD void put_word(uint64_t, int nb) { len += nb; }
+};
 
 }  // namespace sofa

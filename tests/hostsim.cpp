@@ -2,6 +2,7 @@
 // sofa_b200/csrc/*.cuh with g++ so their exact arithmetic can be checked against
 // Python/numpy/pandas in the build container.  Never loaded by the product path.
 #include <string.h>
+#define SOFA_HOST_WIDE 1   // exercise the 8-byte-word sink paths (text is copied into a padded buffer)
 #include "../sofa_b200/csrc/num.cuh"
 using namespace sofa;
 extern "C" {
@@ -67,6 +68,9 @@ extern "C" {
 long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mode, int stride, unsigned fmask,
                 const char* kw, const HsDict* dict, char* out, long* outlen, unsigned* flags, long* nrec) {
     IngestCfg c = mk(h);
+    std::vector<char> padded((size_t)nbytes + 64, '\n');
+    memcpy(padded.data() + 16, text, (size_t)nbytes);
+    text = padded.data() + 16;
     long o = 0, row = 0, pos = 0, cnt = 0;
     unsigned fl = 0;
     FilterTable ft; memset(&ft, 0, sizeof(ft));
@@ -82,7 +86,7 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
             PerfRow r; err = parse_perf(line, (int)linelen, c, &r);
             if (!err) {
                 RowVals v = vals_perf(r);
-                PerfName<const char*> ng{line, r, false};
+                PerfName<const char*> ng{line, r, true};
                 if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
                 else if (sel) {
                     DictVizName vz{PerfVizName<const char*>{ng}, dict};
@@ -96,7 +100,7 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
             if (!err) {
                 if (sel) fl |= r.bw_is_float ? 1u : 0u;
                 RowVals v = vals_gpu(r, c.n_cudaproc);
-                GpuName<const char*> ng{line, r, false};
+                GpuName<const char*> ng{line, r, true};
                 if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
                 else {
                     bool take = (mode == 1) ? sel : true;
