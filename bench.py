@@ -36,6 +36,8 @@ MIX = (0.60, 0.35, 0.05)          # perf, gpu, net
 CPU_FILTERS = "idle:black,tensorflow:orange"
 GPU_KWS = ["CUDA_COPY_H2D", "CUDA_COPY_D2H", "CUDA_COPY_P2P", "_fw_", "_bw_", "AllReduceKernel"]
 CPU_KWS = ["idle", "tensorflow"]
+# dram__bytes_read+write / algorithmic bytes, measured by ncu --set full (profiles/r01_summary.md)
+NCU_TRAFFIC_RATIO = {"json_write": 1.83, "csv_write": 2.72, "parse": 1.66}
 TIME_BASE = 1600000000.0
 PERF_T_OFFSET = 1600000000.25 - 4999.5
 
@@ -47,8 +49,8 @@ def split_events(n):
 
 
 def env_rank():
-    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
-            int(os.environ.get("WORLD_SIZE", 1)))
+    from sofa_b200.multirank import rank_env
+    return rank_env()
 
 
 # --------------------------------------------------------------------------- clocks
@@ -287,6 +289,9 @@ def run_ours(args):
     barrier()
     nb = wl.out_bytes
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         eng.close()
         return
@@ -326,7 +331,9 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "frac": achieved / peak if peak else None,
+                     "traffic": NCU_TRAFFIC_RATIO.get(dname, 0) * dbytes / max(dl, 1) or None,
+                     "traffic_note": "dram read+write of this kernel = ratio x algorithmic bytes, ratio from the ncu --set full capture summarised in profiles/r01_summary.md",
                      "algorithmic_bytes_per_launch": dbytes / max(dl, 1), "launch_ms": dms / max(dl, 1),
                      "peak_source": peak_src,
                      "all_kernels_ms": {k: round(v[1], 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][1])},
