@@ -45,7 +45,7 @@ typedef struct {
     const double* mhz_fp;
     double ts_rescale, dt_rescale, payload_unit;
     int32_t idx[9];              /* Start, Duration, Size, Throughput, Context, Stream, Name, Src Ctx, Dst Ctx; -1 = absent */
-    int32_t reserved;
+    int32_t api_mode;            /* 1: gpu source holds `nvprof --print-api-trace` rows (cuda_api_trace_read) */
 } sofa_ingest_params_t;
 
 /* gpu_profile (sofa_analyze.py:343-377) + comm_profile (sofa_common.py:23-177) results */
@@ -97,6 +97,11 @@ int sofa_b200_row_flags(sofa_ctx*, int src, uint32_t stride, uint32_t* flags);
  * into output buffer 0.  Replaces DataFrame(...).to_csv(float_format='%.6f')
  * (:1204-1211, 1433-1444, 1800-1807). */
 int sofa_b200_emit_csv(sofa_ctx*, int src, uint32_t stride, uint64_t* nbytes);
+
+/* comm.csv body (no header): index, timestamp, pkt_src, pkt_dst, payload, bandwidth of every gpu
+ * row with pandas' default float text (repr of the gputrace.csv value), into output buffer 0.
+ * Replaces df_gpu.to_csv(columns=[...]) (sofa_common.py:160-167). */
+int sofa_b200_emit_comm_csv(sofa_ctx*, uint64_t* nbytes);
 
 /* Keyword filters, Series.str.contains(literal) (:1446-1452 gpu, full frame;
  * :1819-1827 cpu, down-sampled demangled viz frame).  counts[k] = matching rows. */

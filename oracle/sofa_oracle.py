@@ -141,6 +141,18 @@ def parse_gpu_record(record, absolute_timestamp, time_base, indices, n_cudaproc,
             n_cudaproc, tid, name, 0]
 
 
+def parse_api_record(record, absolute_timestamp, time_base, indices, n_cudaproc, ts_rescale, dt_rescale,
+                     t_offset):
+    """One `nvprof --csv --print-api-trace` row -> row.  sofa_preprocess.py:203-247."""
+    v = record.replace('"', '').split(',')
+    name = '[CUDA_API]' + v[indices.index('Name')]
+    t = float(v[indices.index('Start')]) / ts_rescale + t_offset
+    if not absolute_timestamp:
+        t = t - time_base
+    duration = float(v[indices.index('Duration')]) / dt_rescale
+    return [t, 0 * 100 + 17, duration, -1, 0, 0, 0, 0, 0, n_cudaproc, -1, name, 0]
+
+
 def gpu_units(unit_row):
     """Unit row -> (ts_rescale, dt_rescale, payload_unit).  sofa_preprocess.py:1392-1415."""
     u = unit_row.split(',')
@@ -224,6 +236,8 @@ class OracleConfig:
             if k == 'cpu_filters' and isinstance(v, str):
                 v = [tuple(p.split(':')) for p in v.split(',')]
             setattr(self, k, v)
+        if self.cuda_api_tracing and ("CUDA_API", "DarkSlateGray") not in self.gpu_filters:
+            self.gpu_filters.insert(3, ("CUDA_API", "DarkSlateGray"))            # bin/sofa:276-277
 
 
 def _pmap(fn, items, nprocs):
@@ -308,6 +322,29 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
             for kw, color in cfg.gpu_filters:                    # :1446-1452
                 filtered_gpu.append((kw, color, gpu_traces[gpu_traces['name'].str.contains(kw)]))
 
+    # ---- CUDA API trace  :1459-1543 (only with --cuda_api_tracing)
+    api_viz = []
+    if cfg.cuda_api_tracing and os.path.isfile(logdir + 'cuda_api_trace.tmp'):
+        with open(logdir + 'cuda_api_trace.tmp') as f:
+            records = f.readlines()
+        if len(records) > 0 and records[1].split(',')[0] == '"Start"':
+            indices = records[1].replace('"', '').replace('\n', '').split(',')
+            scale = {'ms': 1.0e3, 'us': 1.0e6}
+            ts_rescale = scale.get(records[2].split(',')[0], 1.0)
+            dt_rescale = scale.get(records[2].split(',')[1], 1.0)
+            records = records[3:]
+            t_base = float(records[0].split(',')[0])
+            if len(records[0].split(',')) == 4:                  # :1511-1517, first_corid = 1
+                for record in records:
+                    if int(record.split(',')[3]) == 1:
+                        t_base = float(record.split(',')[0])
+                        break
+            res = _pmap(partial(parse_api_record, absolute_timestamp=cfg.absolute_timestamp,
+                                time_base=time_base, indices=indices, n_cudaproc=1, ts_rescale=ts_rescale,
+                                dt_rescale=dt_rescale, t_offset=0 - t_base), records, cfg.nprocs)
+            write_trace_csv(frame(res), logdir + 'cuda_api_trace.csv')
+            api_viz = frame(downsample(res, cfg.plot_ratio))
+
     # ---- CPU  :1786-1838
     if os.path.isfile(logdir + 'perf.script'):
         with open(logdir + 'perf.script') as f:
@@ -353,6 +390,8 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
     series.append(Series('gpu_kernel_trace', 'GPU kernel', 'rgba(0,180,0,0.8)', gpu_viz))
     for kw, color, grp in filtered_gpu:
         series.append(Series(kw, '[keyword]' + kw, color, grp.copy()))
+    if cfg.cuda_api_tracing:
+        series.append(Series('cuda_api_trace', 'CUDA API', 'DarkSlateGray', api_viz))    # :2094-2102
     if emit_json:
         write_report_js(series, logdir + 'report.js')
     return series

@@ -16,7 +16,7 @@ EXPORTS = [
     "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
     "sofa_b200_synth", "sofa_b200_text_fetch", "sofa_b200_mark", "sofa_b200_elapsed_ms",
-    "sofa_b200_upload_async", "sofa_b200_fetch_async", "sofa_b200_wait_fetch", "sofa_b200_sync", "sofa_b200_set_output_arena",
+    "sofa_b200_upload_async", "sofa_b200_fetch_async", "sofa_b200_wait_fetch", "sofa_b200_sync", "sofa_b200_set_output_arena", "sofa_b200_emit_comm_csv",
 ]
 
 
@@ -27,7 +27,7 @@ class IngestParams(ctypes.Structure):
                 ("mhz_xp", ctypes.c_void_p), ("mhz_fp", ctypes.c_void_p),
                 ("ts_rescale", ctypes.c_double), ("dt_rescale", ctypes.c_double),
                 ("payload_unit", ctypes.c_double), ("idx", ctypes.c_int32 * 9),
-                ("reserved", ctypes.c_int32)]
+                ("api_mode", ctypes.c_int32)]
 
 
 class GpuProfile(ctypes.Structure):
@@ -77,6 +77,7 @@ def load_lib():
     lib.sofa_b200_parse.argtypes = [vp, ctypes.c_int, ctypes.POINTER(IngestParams), u64p]
     lib.sofa_b200_row_flags.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, u32p]
     lib.sofa_b200_emit_csv.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, u64p]
+    lib.sofa_b200_emit_comm_csv.argtypes = [vp, u64p]
     lib.sofa_b200_set_filters.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32,
                                           ctypes.POINTER(ctypes.c_char_p), u64p]
     lib.sofa_b200_viz_mangled.argtypes = [vp, ctypes.c_uint32, u64p, u32p]

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) k_nccl_hash(SrcView src, uint64_t n, uint
     uint64_t key = 0;
     if (src.c.g.kind[row] == 0) {
         GpuRow r = load_gpu(src, row);
-        GpuName<const char*> ng{src.text + src.c.g.line_start[row], r, true};
+        GpuName<const char*> ng{src.text + src.c.g.line_start[row], r, true, src.api_mode != 0};
         NcclHashSink s; ng.gen(s);
         if (s.hit) key = s.h.h ? s.h.h : 1;
         if (s.hit && keys) {

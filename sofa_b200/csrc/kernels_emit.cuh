@@ -19,6 +19,7 @@ struct SrcView {
     const int32_t* viz_id;      // per down-sampled perf candidate: -1 raw, else dictionary slot
     DictView dict;
     int32_t n_cudaproc;
+    int32_t api_mode;
 };
 
 template <typename S>
@@ -75,7 +76,7 @@ __device__ __forceinline__ void with_row(const SrcView& s, uint64_t row, uint64_
         GpuRow r = load_gpu(s, row);
         const char* line = s.text + s.c.g.line_start[row];
         RowVals v = vals_gpu(r, s.n_cudaproc);
-        GpuName<const char*> ng{line, r, true};
+        GpuName<const char*> ng{line, r, true, s.api_mode != 0};
         f(v, ng);
     } else {
         NetRow r = load_net(s, row);
@@ -85,7 +86,7 @@ __device__ __forceinline__ void with_row(const SrcView& s, uint64_t row, uint64_
     }
 }
 
-enum { FMT_CSV = 0, FMT_JSON = 1 };
+enum { FMT_CSV = 0, FMT_JSON = 1, FMT_COMM = 2 };
 
 struct EmitArgs {
     uint64_t ncand; uint32_t stride; uint32_t fmask;
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(256) k_mask_write(const uint8_t* __restrict__ 
 
 template <int FMT> struct RowPlanOf { typedef CsvRowPlan type; };
 template <> struct RowPlanOf<FMT_JSON> { typedef JsonRowPlan type; };
+template <> struct RowPlanOf<FMT_COMM> { typedef CommRowPlan type; };
 
 template <int KIND, int FMT>
 __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs a) {
@@ -346,6 +348,7 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
     if (sel) {
         with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
             if constexpr (FMT == FMT_CSV) plan = csv_row_plan(v, a.fmask, ng);
+            else if constexpr (FMT == FMT_COMM) plan = comm_row_plan(c, v, a.fmask);
             else plan = json_row_plan(v, a.fmask, ng);
         });
         if (plan.len < 0) { report_error(a.err, row, plan.len == -2 ? E_UTF8 : E_FORMAT); plan.len = 0; }
@@ -396,10 +399,12 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
             if (staged) {
                 SmemPtr dst{(uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)(base & 15) + ex};
                 if constexpr (FMT == FMT_CSV) csv_row_emit(v, a.fmask, ng, plan, dst);
+                else if constexpr (FMT == FMT_COMM) comm_row_emit(c, v, a.fmask, plan, dst);
                 else json_row_emit(v, a.fmask, ng, plan, dst);
             } else {
                 char* dst = a.out + base + ex;
                 if constexpr (FMT == FMT_CSV) csv_row_emit(v, a.fmask, ng, plan, dst);
+                else if constexpr (FMT == FMT_COMM) comm_row_emit(c, v, a.fmask, plan, dst);
                 else json_row_emit(v, a.fmask, ng, plan, dst);
             }
         });

@@ -380,6 +380,45 @@ SOFA_HD JPlan jp_fixed(bool neg, uint64_t I, uint64_t dg, int nd) {
     p.len = (uint8_t)(p.neg + ndigits_u64(I) + 1 + nd);
     return p;
 }
+// Python repr digits of y for 1e5 <= y < 1e16 (fixed notation): shortest decimal that rounds
+// back to y, found by an exact 128-bit test of the rounding interval; closest one on ties of length.
+SOFA_HD JPlan jp_shortest_ge1e5(bool neg, double y) {
+    JPlan bad; bad.I = 0; bad.dg = 0; bad.neg = 0; bad.nd = 0; bad.ex = 0; bad.len = 0; bad.kind = JP_BAD;
+    uint64_t yb = d_bits(y);
+    int e = (int)((yb >> 52) & 0x7ff) - 1075;
+    uint64_t m = (yb & 0xfffffffffffffull) | (1ull << 52);
+    if (e >= 0) return jp_fixed(neg, m << e, 0, 1);        // integer valued (< 1e16): digits + ".0"
+    int s = -e;                         // 1..36 because y >= 1e5 > 2^16
+    if (s > 36) return bad;
+    uint64_t I = m >> s;
+    uint64_t r0 = m & ((1ull << s) - 1);
+    if (r0 == 0) return jp_fixed(neg, I, 0, 1);
+    bool even = (m & 1) == 0;
+    bool pow2 = (m == (1ull << 52));    // lower neighbour is half as far
+    u128 one = ((u128)1) << s;
+    uint64_t p10 = 1;
+    for (int j = 1; j <= 12; j++) {
+        p10 *= 10;
+        u128 F = (u128)r0 * p10;
+        u128 fl = F >> s;
+        u128 rem = F - (fl << s);
+        u128 up = one - rem;
+        // candidate below y: distance rem / (2^s 10^j); half gap 2^-(s+1) (2^-(s+2) at a power of two)
+        u128 lo_lhs = pow2 ? rem * 4 : rem * 2;
+        bool lo_ok = (lo_lhs < (u128)p10) || (even && lo_lhs == (u128)p10);
+        u128 hi_lhs = up * 2;
+        bool hi_ok = (hi_lhs < (u128)p10) || (even && hi_lhs == (u128)p10);
+        if (!(lo_ok || hi_ok)) continue;
+        uint64_t dg = (uint64_t)fl;
+        bool take_hi;
+        if (lo_ok && hi_ok) take_hi = (up < rem) || (up == rem && (dg & 1));
+        else take_hi = hi_ok;
+        if (take_hi) dg++;
+        if (dg == p10) return jp_fixed(neg, I + 1, 0, 1);
+        return jp_fixed(neg, I, dg, j);
+    }
+    return bad;
+}
 SOFA_HD JPlan json_plan(double x) {
     JPlan p; p.I = 0; p.dg = 0; p.neg = 0; p.nd = 0; p.ex = 0; p.len = 0; p.kind = JP_BAD;
     uint64_t xb = d_bits(x);
@@ -414,39 +453,7 @@ SOFA_HD JPlan json_plan(double x) {
     // else y = (whole*1e10 + frac) / 1e10 (numerator < 2^53, one exact division)
     double y = v;
     if (whole < 524288ull) y = d_div((double)(whole * 10000000000ull + frac), 1e10);
-    uint64_t yb = d_bits(y);
-    int e = (int)((yb >> 52) & 0x7ff) - 1075;
-    uint64_t m = (yb & 0xfffffffffffffull) | (1ull << 52);
-    if (e >= 0) return jp_fixed(neg, m << e, 0, 1);        // integer valued (< 1e16): digits + ".0"
-    int s = -e;                         // 1..36 because y >= 1e5 > 2^16
-    uint64_t I = m >> s;
-    uint64_t r0 = m & ((1ull << s) - 1);
-    if (r0 == 0) return jp_fixed(neg, I, 0, 1);
-    bool even = (m & 1) == 0;
-    bool pow2 = (m == (1ull << 52));    // lower neighbour is half as far
-    u128 one = ((u128)1) << s;
-    uint64_t p10 = 1;
-    for (int j = 1; j <= 12; j++) {
-        p10 *= 10;
-        u128 F = (u128)r0 * p10;
-        u128 fl = F >> s;
-        u128 rem = F - (fl << s);
-        u128 up = one - rem;
-        // candidate below y: distance rem / (2^s 10^j); half gap 2^-(s+1) (2^-(s+2) at a power of two)
-        u128 lo_lhs = pow2 ? rem * 4 : rem * 2;
-        bool lo_ok = (lo_lhs < (u128)p10) || (even && lo_lhs == (u128)p10);
-        u128 hi_lhs = up * 2;
-        bool hi_ok = (hi_lhs < (u128)p10) || (even && hi_lhs == (u128)p10);
-        if (!(lo_ok || hi_ok)) continue;
-        uint64_t dg = (uint64_t)fl;
-        bool take_hi;
-        if (lo_ok && hi_ok) take_hi = (up < rem) || (up == rem && (dg & 1));
-        else take_hi = hi_ok;
-        if (take_hi) dg++;
-        if (dg == p10) return jp_fixed(neg, I + 1, 0, 1);
-        return jp_fixed(neg, I, dg, j);
-    }
-    return p;
+    return jp_shortest_ge1e5(neg, y);
 }
 template <typename O>
 SOFA_HD int json_emit(const JPlan& p, O out) {
@@ -472,6 +479,30 @@ SOFA_HD int json_double(double x, O out) {
     JPlan p = json_plan(x);
     if (p.kind == JP_BAD) return -1;
     return json_emit(p, out);
+}
+
+// repr(float("%.6f" % x)): what DataFrame.to_csv prints (no float_format) for a value that was
+// read back from a trace CSV - comm.csv (sofa_common.py:160-167).  |x| < 9e9.
+SOFA_HD JPlan repr6_plan(double x) {
+    JPlan p; p.I = 0; p.dg = 0; p.neg = 0; p.nd = 0; p.ex = 0; p.len = 0; p.kind = JP_BAD;
+    bool neg; uint64_t I; uint32_t F;
+    if (!fixed6_parts(x, &neg, &I, &F) || I >= 9000000000ull) return p;
+    if (I < 100000ull) {                       // <= 11 significant digits: the decimal itself
+        if (I > 0 || F >= 100u || F == 0u) {
+            if (F == 0u) return jp_fixed(neg, I, 0, 1);
+            int nd = 6; uint32_t f = F;
+            while (f % 10u == 0u) { f /= 10u; nd--; }
+            return jp_fixed(neg, I, f, nd);
+        }
+        int ex = 7 - ndigits_u32(F);           // 0 < y < 1e-4: "2e-06", "1.5e-05"
+        uint32_t f = F;
+        while (f % 10u == 0u) f /= 10u;
+        int L = ndigits_u32(f);
+        p.kind = JP_SCI; p.neg = neg ? 1 : 0; p.dg = f; p.nd = (uint8_t)L; p.ex = (uint8_t)ex;
+        p.len = (uint8_t)(p.neg + L + (L > 1 ? 1 : 0) + 4);
+        return p;
+    }
+    return jp_shortest_ge1e5(neg, d_div((double)(I * 1000000ull + F), 1e6));
 }
 
 // ----------------------------------------------------------------------------- double-double

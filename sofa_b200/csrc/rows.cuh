@@ -43,6 +43,7 @@ struct IngestCfg {
     double ts_rescale, dt_rescale, payload_unit;    // (:1392-1415)
     int n_cudaproc;                                   // pid column (:288)
     int idx_start, idx_dur, idx_size, idx_thr, idx_ctx, idx_stream, idx_name, idx_srcctx, idx_dstctx;
+    int api_mode;            // nvprof --print-api-trace rows (cuda_api_trace_read, :203-247)
 };
 
 struct Tok { int a, b; };
@@ -422,6 +423,11 @@ SOFA_HD int parse_gpu(S s, int n, const IngestCfg& c, GpuRow* r) {
     if (st) return num_status_to_err(st, true);
     r->ts = time;
     r->dur = d_div(dur, c.dt_rescale);
+    if (c.api_mode) {        // cuda_api_trace_read: constants besides time, duration and the name
+        r->payload = 0; r->bw = 0.0; r->bw_is_float = 0; r->dev = -1; r->tid = -1; r->src = 0; r->dst = 0; r->kind = 0;
+        r->name_off = (uint16_t)fa[6]; r->name_len = (uint16_t)(fb[6] - fa[6]);
+        return E_OK;
+    }
     int err = E_OK;
     double v; int64_t iv;
     r->payload = 0;
@@ -498,8 +504,9 @@ struct QuoteFilter {
 };
 template <typename S>
 struct GpuName {
-    S line; GpuRow r; bool wide;
+    S line; GpuRow r; bool wide; bool api;
     template <class K> SOFA_HD void gen(K& k) const {
+        if (api) put_lit(k, "[CUDA_API]");                                             // :213
         if (r.dev != -1) { put_lit(k, "[gpu"); put_i64(k, r.dev); k.put(']'); }        // :325-326
         if (r.kind == 0) {
             QuoteFilter<K> q{&k};
@@ -887,6 +894,34 @@ SOFA_HD int json_row_write(const RowVals& v, uint32_t fmask, const NG& ng, O out
 template <class NG>
 SOFA_HD int json_row_len(const RowVals& v, uint32_t fmask, const NG& ng) {
     return json_row_plan(v, fmask, ng).len;
+}
+
+// ============================================================================ comm.csv rows
+// df_gpu.to_csv(columns=[timestamp, pkt_src, pkt_dst, payload, bandwidth]) with the index and
+// pandas' default float text = repr of the value read back from gputrace.csv (sofa_common.py:160-167)
+struct CommRowPlan { int len; JPlan ts, bw; };
+SOFA_HD CommRowPlan comm_row_plan(uint64_t index, const RowVals& v, uint32_t fmask) {
+    CommRowPlan p;
+    p.ts = repr6_plan(v.ts);
+    bool bwf = ((fmask >> 6) & 1) != 0;
+    int n = len_i64((int64_t)index) + len_i64(v.src) + len_i64(v.dst) + len_i64(v.payload) + 6 + p.ts.len;
+    bool bad = p.ts.kind == JP_BAD;
+    if (bwf) { p.bw = repr6_plan(v.bw_is_f ? v.bw_f : 0.0); bad |= p.bw.kind == JP_BAD; n += p.bw.len; }
+    else n += len_i64(v.bw_i);
+    p.len = bad ? -1 : n;
+    return p;
+}
+template <typename O>
+SOFA_HD int comm_row_emit(uint64_t index, const RowVals& v, uint32_t fmask, const CommRowPlan& p, O out) {
+    int n = fmt_i64((int64_t)index, out);
+    out[n++] = ',';
+    n += json_emit(p.ts, out + n); out[n++] = ',';
+    n += fmt_i64(v.src, out + n); out[n++] = ',';
+    n += fmt_i64(v.dst, out + n); out[n++] = ',';
+    n += fmt_i64(v.payload, out + n); out[n++] = ',';
+    if ((fmask >> 6) & 1) n += json_emit(p.bw, out + n); else n += fmt_i64(v.bw_i, out + n);
+    out[n++] = '\n';
+    return n;
 }
 
 // ============================================================================ keyword filters

@@ -215,6 +215,7 @@ static SrcView make_view(sofa_ctx* c, int k, bool with_viz) {
     v.dict.n = s.dict_n; v.dict.hash = s.dict_hash.as<uint64_t>(); v.dict.off = s.dict_off.as<uint64_t>();
     v.dict.blob = s.dict_blob.as<char>();
     v.n_cudaproc = s.cfg.n_cudaproc;
+    v.api_mode = (k == SRC_GPU) ? s.cfg.api_mode : 0;
     return v;
 }
 
@@ -323,6 +324,7 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_GPU, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_NET, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_NET, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_GPU, FMT_COMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     *out = c;
     return 0;
 }
@@ -395,6 +397,7 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     cfg.idx_start = p->idx[0]; cfg.idx_dur = p->idx[1]; cfg.idx_size = p->idx[2]; cfg.idx_thr = p->idx[3];
     cfg.idx_ctx = p->idx[4]; cfg.idx_stream = p->idx[5]; cfg.idx_name = p->idx[6]; cfg.idx_srcctx = p->idx[7];
     cfg.idx_dstctx = p->idx[8];
+    cfg.api_mode = p->api_mode;
     if (k == SRC_GPU && (cfg.idx_start < 0 || cfg.idx_dur < 0 || cfg.idx_name < 0))
         FAIL(SOFA_ERR_ARG, "parse: gpu trace needs Start, Duration and Name columns");
     ENSURE(s.mhz, 16 * (size_t)cfg.n_mhz + 16);
@@ -572,7 +575,8 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
     uint64_t nblocks = cdiv(nitems, EMIT_TPB);
     ENSURE(c->tiles, (nblocks + 2) * 8);
     SrcView v = make_view(c, k, true);
-    uint64_t per_row = FMT == FMT_CSV ? 96 : 230;
+    uint64_t per_row = FMT == FMT_CSV ? 96 : (FMT == FMT_COMM ? 64 : 230);
+    if (FMT == FMT_COMM) text_share = 0;
     uint64_t cap = sel_hint * per_row + text_share + (1 << 16);
     uint32_t slot_bytes = 40 * 1024;
     for (int attempt = 0; attempt < 6; attempt++, cap *= 2) {
@@ -586,11 +590,16 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
         a.state = c->tiles.as<unsigned long long>(); a.ticket = c->d_flags + 4;
         a.err = c->d_err; a.count = c->d_err + 1; a.total = c->d_err + 11; a.overflow = c->d_flags + 2;
         a.slot_bytes = slot_bytes;
-        int kk = FMT == FMT_CSV ? K_CSV_WRITE : K_JSON_WRITE;
+        int kk = FMT == FMT_JSON ? K_JSON_WRITE : K_CSV_WRITE;
         unsigned g = (unsigned)nblocks;
-        if (k == SRC_PERF) LAUNCH(c, kk, (k_emit_fused<SRC_PERF, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
-        else if (k == SRC_GPU) LAUNCH(c, kk, (k_emit_fused<SRC_GPU, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
-        else LAUNCH(c, kk, (k_emit_fused<SRC_NET, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+        if constexpr (FMT == FMT_COMM) {
+            if (k != SRC_GPU) FAIL(SOFA_ERR_ARG, "comm.csv is a gpu-trace output");
+            LAUNCH(c, kk, (k_emit_fused<SRC_GPU, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+        } else {
+            if (k == SRC_PERF) LAUNCH(c, kk, (k_emit_fused<SRC_PERF, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+            else if (k == SRC_GPU) LAUNCH(c, kk, (k_emit_fused<SRC_GPU, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+            else LAUNCH(c, kk, (k_emit_fused<SRC_NET, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+        }
         unsigned long long total = 0, cnt = 0; unsigned int ovf = 0;
         CK_S(small_d2h(c, &total, c->d_err + 11, 8));
         CK_S(small_d2h(c, &cnt, c->d_err + 1, 8));
@@ -621,6 +630,13 @@ int sofa_b200_emit_csv(sofa_ctx* c, int k, uint32_t stride, uint64_t* nbytes) {
     r = fmask_for(c, k, stride, &fmask); if (r) return r;
     if (use_fused()) return emit_fused<FMT_CSV>(c, k, stride, nullptr, 0, fmask, 0, cdiv(c->src[k].n_rows, stride), nbytes, nullptr);
     return emit_common<FMT_CSV>(c, k, stride, nullptr, 0, fmask, 0, nbytes, nullptr);
+}
+
+int sofa_b200_emit_comm_csv(sofa_ctx* c, uint64_t* nbytes) {
+    int r = need_parsed(c, SRC_GPU); if (r) return r;
+    uint32_t fmask = 0;
+    r = fmask_for(c, SRC_GPU, 1, &fmask); if (r) return r;
+    return emit_fused<FMT_COMM>(c, SRC_GPU, 1, nullptr, 0, fmask, 0, c->src[SRC_GPU].n_rows, nbytes, nullptr);
 }
 
 int sofa_b200_emit_json(sofa_ctx* c, int k, uint32_t stride, int32_t filter_idx, uint64_t* nbytes, uint64_t* nrec) {

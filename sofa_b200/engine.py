@@ -108,6 +108,7 @@ class CudaEngine:
         ip.ts_rescale, ip.dt_rescale, ip.payload_unit = p['ts_rescale'], p['dt_rescale'], p['payload_unit']
         for i in range(9):
             ip.idx[i] = p['idx'][i]
+        ip.api_mode = p.get('api_mode', 0)
         return ip
 
     def parse(self, kind, params):
@@ -142,6 +143,12 @@ class CudaEngine:
 
     def csv(self, kind, stride, out=None):
         return self._fetch(0, self.csv_device(kind, stride), out)
+
+    def comm_csv(self, out=None):
+        """comm.csv body (sofa_common.py:160-167) of the parsed gpu rows."""
+        n = ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_emit_comm_csv(self.ctx, ctypes.byref(n)))
+        return self._fetch(0, n.value, out)
 
     def json_device(self, kind, stride, filt):
         n = ctypes.c_uint64()

@@ -59,7 +59,7 @@ def base_params(kind, time_base, absolute_timestamp, t_offset=0.0):
     return dict(kind=kind, time_base=float(time_base), t_offset=float(t_offset),
                 absolute_timestamp=1 if absolute_timestamp else 0, perf_has_cycles=1,
                 mhz_xp=[0.0], mhz_fp=[3000.0], ts_rescale=1.0, dt_rescale=1.0, payload_unit=1.0,
-                n_cudaproc=1, idx=[-1] * 9)
+                n_cudaproc=1, idx=[-1] * 9, api_mode=0)
 
 
 def gpu_header(head):
@@ -98,3 +98,45 @@ ROW_ERRORS = {1: "too few fields (IndexError in the reference)", 2: "float() Val
               7: "integer out of range", 8: "carriage return in trace text",
               9: "too many short lines in one tile", 10: "value outside the text codec's range",
               11: "invalid UTF-8 in a name"}
+
+
+def api_header(head):
+    """Header rows of `nvprof --csv --print-api-trace` (sofa_preprocess.py:1487-1506)."""
+    text = head.decode('utf-8', errors='replace')
+    rows = text.split('\n', 3)
+    if len(rows) < 3 or rows[1].split(',')[0] != '"Start"':
+        return None
+    indices = rows[1].replace('"', '').replace('\n', '').split(',')
+    units = rows[2].split(',')
+    scale = {'ms': 1.0e3, 'us': 1.0e6}
+    idx = [-1] * 9
+    for slot, col in ((0, 'Start'), (1, 'Duration'), (6, 'Name')):
+        if col not in indices:
+            raise PreprocessError("cuda_api_trace.tmp header lacks %s" % col)
+        idx[slot] = indices.index(col)
+    data_off = len(rows[0].encode()) + len(rows[1].encode()) + len(rows[2].encode()) + 3
+    return dict(ts_rescale=scale.get(units[0], 1.0), dt_rescale=scale.get(units[1], 1.0), idx=idx, api_mode=1), data_off
+
+
+def api_t_base(text, data_off, first_corid=1):
+    """t_base of the API trace (sofa_preprocess.py:1510-1518): Start of the first record, replaced
+    by the Start of the record whose 4th field equals first_corid when records have 4 fields."""
+    body = memoryview(text)[data_off:]
+    end = bytes(body[:4096]).find(b'\n')
+    first = bytes(body[:end if end >= 0 else len(body)]).decode()
+    if not first:
+        raise PreprocessError("cuda_api_trace.tmp has a header but no records")
+    t_base = float(first.split(',')[0])
+    if len(first.split(',')) == 4:
+        pos = 0
+        raw = bytes(body)
+        while pos < len(raw):
+            e = raw.find(b'\n', pos)
+            if e < 0:
+                e = len(raw)
+            rec = raw[pos:e + 1].decode()
+            if int(rec.split(',')[3]) == first_corid:
+                t_base = float(rec.split(',')[0])
+                break
+            pos = e + 1
+    return t_base

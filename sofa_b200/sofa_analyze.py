@@ -80,6 +80,9 @@ def gpu_profile(cfg, eng):
         raise TypeError("comm_profile: no GPU communication traces (deviceId never > 0); the "
                         "reference raises TypeError at sofa_common.py:59")
     feats += comm_profile_report(cfg, gp)
+    with open(cfg.logdir + '/' + 'comm.csv', 'wb') as f:          # sofa_common.py:160-167
+        f.write(b",timestamp,pkt_src,pkt_dst,payload,bandwidth\n")
+        f.write(memoryview(eng.comm_csv()))
     if cfg.verbose:                                   # get_top_k_events (sofa_analyze.py:34-44)
         print("Top %d Events: " % 10)
         for name, total in eng.top_k(SRC_GPU, 10):
@@ -164,7 +167,7 @@ def sofa_analyze(cfg, engine=None):
                 from .engine import CudaEngine
                 eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
                 own = True
-            if own or engine is not None and not getattr(engine, 'gpu_loaded', False):
+            if own or engine is not None or getattr(cfg, '_sofa_b200_gpu_slot_is_api', False):
                 if not load_gpu_source(cfg, eng):
                     raise IOError("gputrace.csv exists but gputrace.tmp (raw rows) is missing: "
                                   "CSV re-ingest is not implemented")

@@ -39,7 +39,7 @@ class SOFA_Config:
         self.net_filters = []
 
 
-def default_report_config(logdir, cpu_filters=None, gpu_filters=None):
+def default_report_config(logdir, cpu_filters=None, gpu_filters=None, cuda_api_tracing=False):
     """cfg as `sofa report` leaves it (bin/sofa:258-291 default filters)."""
     cfg = SOFA_Config()
     cfg.logdir = logdir if logdir.endswith('/') else logdir + '/'
@@ -49,6 +49,9 @@ def default_report_config(logdir, cpu_filters=None, gpu_filters=None):
     cfg.gpu_filters.append(Filter('CUDA_COPY_H2D', 'Red'))
     cfg.gpu_filters.append(Filter('CUDA_COPY_D2H', 'Peru'))
     cfg.gpu_filters.append(Filter('CUDA_COPY_P2P', 'Purple'))
+    cfg.cuda_api_tracing = cuda_api_tracing
+    if cuda_api_tracing:
+        cfg.gpu_filters.append(Filter('CUDA_API', 'DarkSlateGray'))            # bin/sofa:276-277
     for pair in (gpu_filters or '_fw_:royalblue,_bw_:darkviolet,AllReduceKernel:indigo').split(','):
         cfg.gpu_filters.append(Filter(pair.split(':')[0], pair.split(':')[1]))
     return cfg

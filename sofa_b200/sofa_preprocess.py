@@ -221,8 +221,30 @@ def _preprocess(cfg, eng):
                 rec, nrec = eng.json(SRC_GPU, 1, i)
                 gpu_filter_series.append(SeriesOut(flt.keyword, '[keyword]' + flt.keyword, flt.color, rec, nrec))
 
+    # ---------------- CUDA API trace (:1459-1543), only with --cuda_api_tracing.  The rows go through
+    # the gpu source slot of the engine in api_mode (the gpu trace above is finished by now).
+    api_series = None
     if getattr(cfg, 'cuda_api_tracing', False):
-        raise NotImplementedError("cuda_api_tracing (a4) is not implemented")
+        api_series = SeriesOut('cuda_api_trace', 'CUDA API', 'DarkSlateGray')
+        for nvvp in nvvps:
+            if not os.path.isfile(logdir + 'cuda_api_trace.tmp') or os.path.getsize(nvvp) > 0:
+                with open(logdir + "cuda_api_trace.tmp", "w") as f:
+                    subprocess.call(["nvprof", "--csv", "--print-api-trace", "-i", nvvp], stderr=f)
+            text = _read_bytes(logdir + 'cuda_api_trace.tmp')
+            hdr = hl.api_header(text[:1 << 16]) if len(text) > 0 else None
+            if hdr is None:
+                continue
+            upd, data_off = hdr
+            t_base = hl.api_t_base(text, data_off)            # first_corid = 1 (no sqlite RUNTIME table)
+            p = hl.base_params(SRC_GPU, cfg.time_base, cfg.absolute_timestamp, 0 - t_base)
+            p.update(upd)
+            n_rows, _ = eng.load(SRC_GPU, text, p, data_off)
+            print_info(cfg, "Length of cuda_api_traces = %d" % n_rows)
+            with open(logdir + 'cuda_api_trace.csv', 'wb') as f:
+                f.write(CSV_HEADER)
+                f.write(memoryview(eng.csv(SRC_GPU, 1)))
+            api_series.records, api_series.nrec = eng.json(SRC_GPU, ratio, -1)
+        cfg._sofa_b200_gpu_slot_is_api = True
 
     # ---------------- CPU (:1544-1551, 1766-1838)
     cfg.perf_events = hl.read_perf_events(logdir)
@@ -281,5 +303,7 @@ def _preprocess(cfg, eng):
     series.append(SeriesOut('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)'))
     series.append(gpu_series)
     series.extend(gpu_filter_series)
+    if api_series is not None:
+        series.append(api_series)
     write_report_js(series, logdir + 'report.js')
     print_progress(cfg, "Export Overhead Dynamics JSON File of CPU, Network and GPU traces -- end")

@@ -203,6 +203,30 @@ def net_line(seed, i, non_ip_pct=1):
         ts, src, sport, dst, dport, (r1 >> 44) % 65536)
 
 
+API_NAMES = ["cudaLaunchKernel", "cudaMemcpyAsync", "cudaStreamSynchronize", "cudaMalloc", "cudaFree",
+             "cudaEventRecord", "cuLaunchKernel", "cudaMemsetAsync"]
+STREAM_API = 4
+
+
+def api_header(with_corid=True):
+    cols = '"Start","Duration","Name"' + (',"Correlation_ID"' if with_corid else '')
+    units = "ms,us," + ("," if with_corid else "")
+    return "==4242== Profiling result:\n" + cols + "\n" + units + "\n"
+
+
+def api_line(seed, i, with_corid=True):
+    r0 = rnd(seed, STREAM_API, i, 0)
+    us = 349000 + i * 19 + (r0 >> 12) % 19
+    dur_ns = 500 + (r0 >> 20) % 90000
+    name = API_NAMES[(r0 >> 4) & 7]
+    row = '%d.%03d,%d.%03d,"%s"' % (us // 1000, us % 1000, dur_ns // 1000, dur_ns % 1000, name)
+    return row + (",%d\n" % (i + 1) if with_corid else "\n")
+
+
+def api_text(seed, n, with_corid=True):
+    return api_header(with_corid) + "".join(api_line(seed, i, with_corid) for i in range(n))
+
+
 def perf_text(seed, n, cpu_col=False):
     return "".join(perf_line(seed, i, cpu_col) for i in range(n))
 
@@ -240,7 +264,7 @@ def write_side_files(logdir, elapsed=12.5, perf_events="cycles", cpuinfo=None):
 
 def make_logdir(logdir, seed, n_perf=0, n_gpu=0, n_net=0, cpu_col=False,
                 units="s_ms", p2p_cols=False, non_ip_pct=1, perf_events="cycles",
-                cpuinfo=None):
+                cpuinfo=None, n_api=0, api_corid=True):
     """Write a complete synthetic logdir. GPU / net sources are written as the
     text dumps (`gputrace.tmp`, `net.tmp`) plus the marker files the reference
     globs for (`gputrace1.nvvp`, `sofa.pcap`)."""
@@ -251,6 +275,10 @@ def make_logdir(logdir, seed, n_perf=0, n_gpu=0, n_net=0, cpu_col=False,
     if n_gpu:
         with open(os.path.join(logdir, "gputrace.tmp"), "w") as f:
             f.write(gpu_text(seed, n_gpu, units, p2p_cols))
+        open(os.path.join(logdir, "gputrace1.nvvp"), "w").close()
+    if n_api:
+        with open(os.path.join(logdir, "cuda_api_trace.tmp"), "w") as f:
+            f.write(api_text(seed, n_api, api_corid))
         open(os.path.join(logdir, "gputrace1.nvvp"), "w").close()
     if n_net:
         with open(os.path.join(logdir, "net.tmp"), "w") as f:

@@ -45,6 +45,8 @@ CASES = {
     "net_nan": (dict(seed=83, n_net=300, non_ip_pct=3), dict(plot_ratio=2)),
     "mixed": (dict(seed=20260921 + 3, n_perf=600, n_gpu=350, n_net=100),
               dict(cpu_filters="idle:black,tensorflow:orange")),
+    "api_corid": (dict(seed=84, n_gpu=200, n_api=250), dict(cuda_api_tracing=True, plot_ratio=2)),
+    "api_nocorid": (dict(seed=85, n_gpu=150, n_api=200, api_corid=False), dict(cuda_api_tracing=True)),
 }
 
 
@@ -83,8 +85,9 @@ def install_shims(shimdir):
     os.makedirs(shimdir, exist_ok=True)
     nv = os.path.join(shimdir, "nvprof")
     with open(nv, "w") as f:
-        f.write('#!/bin/sh\n# args: --csv --print-gpu-trace -i <file.nvvp>\n'
-                'for a; do last="$a"; done\ncat "$(dirname "$last")/gputrace.src" >&2\n')
+        f.write('#!/bin/sh\n# args: --csv --print-gpu-trace|--print-api-trace -i <file.nvvp>\n'
+                'src=gputrace.src\nfor a; do last="$a"; [ "$a" = "--print-api-trace" ] && src=cuda_api_trace.src; done\n'
+                'cat "$(dirname "$last")/$src" >&2\n')
     td = os.path.join(shimdir, "tcpdump")
     with open(td, "w") as f:
         f.write('#!/bin/sh\n# args: -q -n -tt -r <file.pcap>\n'
@@ -116,6 +119,8 @@ def make_ref_cfg(logdir, overrides):
     cfg.gpu_filters.append(Filter("CUDA_COPY_H2D", "Red"))
     cfg.gpu_filters.append(Filter("CUDA_COPY_D2H", "Peru"))
     cfg.gpu_filters.append(Filter("CUDA_COPY_P2P", "Purple"))
+    if ov.get("cuda_api_tracing"):
+        cfg.gpu_filters.append(Filter("CUDA_API", "DarkSlateGray"))          # bin/sofa:276-277
     cfg.gpu_filters.append(Filter("_fw_", "royalblue"))
     cfg.gpu_filters.append(Filter("_bw_", "darkviolet"))
     cfg.gpu_filters.append(Filter("AllReduceKernel", "indigo"))
@@ -128,7 +133,8 @@ def run_reference(logdir, overrides, analyze=True):
     """Run reference sofa_preprocess (+ the analyze functions that work on this
     pandas) in `logdir`.  Returns dict of feature name -> value (or None)."""
     import sofa_preprocess as ref_pre
-    for src, dst in (("gputrace.tmp", "gputrace.src"), ("net.tmp", "net.src")):
+    for src, dst in (("gputrace.tmp", "gputrace.src"), ("net.tmp", "net.src"),
+                     ("cuda_api_trace.tmp", "cuda_api_trace.src")):
         if os.path.isfile(os.path.join(logdir, src)):
             shutil.copy(os.path.join(logdir, src), os.path.join(logdir, dst))
     cfg = make_ref_cfg(logdir, overrides)
@@ -169,7 +175,7 @@ def main():
         meta = {"make_logdir": mk, "cfg": ov, "features": feats}
         with open(os.path.join(out, "case.json"), "w") as f:
             json.dump(meta, f, indent=1, sort_keys=True)
-        for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "comm.csv"):
+        for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "comm.csv", "cuda_api_trace.csv"):
             p = os.path.join(logdir, fn)
             if os.path.isfile(p):
                 shutil.copy(p, os.path.join(out, fn))

@@ -40,6 +40,7 @@ struct HsCfg {
     const double* mhz_xp; const double* mhz_fp;
     double ts_rescale, dt_rescale, payload_unit; int n_cudaproc;
     int idx[9];
+    int api_mode;
 };
 static IngestCfg mk(const HsCfg* h) {
     IngestCfg c; c.time_base = h->time_base; c.t_offset = h->t_offset; c.absolute_timestamp = h->absolute_timestamp;
@@ -47,6 +48,7 @@ static IngestCfg mk(const HsCfg* h) {
     c.ts_rescale = h->ts_rescale; c.dt_rescale = h->dt_rescale; c.payload_unit = h->payload_unit; c.n_cudaproc = h->n_cudaproc;
     c.idx_start = h->idx[0]; c.idx_dur = h->idx[1]; c.idx_size = h->idx[2]; c.idx_thr = h->idx[3]; c.idx_ctx = h->idx[4];
     c.idx_stream = h->idx[5]; c.idx_name = h->idx[6]; c.idx_srcctx = h->idx[7]; c.idx_dstctx = h->idx[8];
+    c.api_mode = h->api_mode;
     return c;
 }
 // demangle table for viz names: sorted FNV hashes -> strings
@@ -100,7 +102,7 @@ long hs_process(int kind, const char* text, long nbytes, const HsCfg* h, int mod
             if (!err) {
                 if (sel) fl |= r.bw_is_float ? 1u : 0u;
                 RowVals v = vals_gpu(r, c.n_cudaproc);
-                GpuName<const char*> ng{line, r, true};
+                GpuName<const char*> ng{line, r, true, c.api_mode != 0};
                 if (mode == 0) { bool sp; int l = csv_row_len(v, fmask, ng, &sp); if (l < 0) err = E_FORMAT; else { len = csv_row_write(v, fmask, ng, sp, out + o); if (len != l) err = 99; } }
                 else {
                     bool take = (mode == 1) ? sel : true;
@@ -163,3 +165,5 @@ extern "C" int hs_tokenize(const char* s, int n, int* ab, int maxt) {
     for (int i = 0; i < k; i++) { ab[2 * i] = t[i].a; ab[2 * i + 1] = t[i].b; }
     return k;
 }
+
+extern "C" int hs_repr6(double x, char* out) { JPlan p = repr6_plan(x); if (p.kind == JP_BAD) return -1; int l = json_emit(p, out); return l == p.len ? l : -2; }

@@ -18,7 +18,7 @@ class HsCfg(ctypes.Structure):
                 ("n_mhz", ctypes.c_int), ("mhz_xp", ctypes.c_void_p), ("mhz_fp", ctypes.c_void_p),
                 ("ts_rescale", ctypes.c_double), ("dt_rescale", ctypes.c_double),
                 ("payload_unit", ctypes.c_double), ("n_cudaproc", ctypes.c_int),
-                ("idx", ctypes.c_int * 9)]
+                ("idx", ctypes.c_int * 9), ("api_mode", ctypes.c_int)]
 
 
 class HsDict(ctypes.Structure):
@@ -67,11 +67,12 @@ class HostSimEngine:
         c.n_cudaproc = p['n_cudaproc']
         for i in range(9):
             c.idx[i] = p['idx'][i]
+        c.api_mode = p.get('api_mode', 0)
         return c
 
     def _run(self, kind, mode, stride, fmask, kw=None):
         text, cfg = self.src[kind]
-        out = ctypes.create_string_buffer(len(text) * 6 + 4096)
+        out = ctypes.create_string_buffer(len(text) * 16 + 4096)
         outlen = ctypes.c_long()
         flags = ctypes.c_uint()
         nrec = ctypes.c_long()

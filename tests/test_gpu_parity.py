@@ -28,11 +28,12 @@ def _diff(name, fn, got, want):
 def test_cuda_path_reproduces_reference_files(name, tmp_path):
     case, logdir = build_case_logdir(name, tmp_path)
     ov = dict(case["cfg"])
-    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None))
+    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None),
+                                cuda_api_tracing=ov.pop("cuda_api_tracing", False))
     for k, v in ov.items():
         setattr(cfg, k, v)
     sofa_preprocess(cfg)
-    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "cuda_api_trace.csv"):
         want = golden_bytes(name, fn)
         if want is None:
             assert not os.path.isfile(logdir + fn)
@@ -120,7 +121,8 @@ def test_gpu_profile_features_match_reference(name, tmp_path, capsys):
     from sofa_b200.sofa_analyze import sofa_analyze
     case, logdir = build_case_logdir(name, tmp_path)
     ov = dict(case["cfg"])
-    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None))
+    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None),
+                                cuda_api_tracing=ov.pop("cuda_api_tracing", False))
     for k, v in ov.items():
         setattr(cfg, k, v)
     sofa_preprocess(cfg)
@@ -129,6 +131,8 @@ def test_gpu_profile_features_match_reference(name, tmp_path, capsys):
         if k not in ("elapsed_time", "__top10_names__"):
             assert float(feats[k]) == v, (k, feats[k], v)
     assert "Complete!!" in capsys.readouterr().out
+    with open(logdir + "comm.csv", "rb") as f:
+        _diff(name, "comm.csv", f.read(), golden_bytes(name, "comm.csv"))
 
 
 def test_gpu_profile_matches_oracle_on_larger_log(tmp_path):

@@ -277,3 +277,18 @@ def test_swar_tokenizer_matches_str_split(hs):
     b = b"ab\xc2\xa0cd \xe2\x80\x83ef"
     k = hs.hs_tokenize(b, len(b), ab, 8)
     assert [(ab[2 * i], ab[2 * i + 1]) for i in range(k)] == [(0, 6), (7, 12)]
+
+
+def test_repr6_is_python_repr_of_csv_value(hs):
+    hs.hs_repr6.argtypes = [ctypes.c_double, ctypes.c_char_p]
+    rng = random.Random(43)
+    xs = rand_doubles(rng, 40000) + [0.0, -0.0, 2e-6, 1.5e-5, 9.9e-5, 1e-4, 0.5, 99999.999999, 100000.0,
+                                      100000.000001, -1600000349.671978, 1599999999.999987, 8999999999.123456,
+                                      524288.0000005, 1e-7, 4.9e-7, 5e-7]
+    buf = ctypes.create_string_buffer(64)
+    for x in xs:
+        if abs(x) >= 8.9e9:
+            continue
+        n = hs.hs_repr6(x, buf)
+        assert n > 0, x
+        assert buf.raw[:n].decode() == repr(float("%.6f" % x)), (x, buf.raw[:n])

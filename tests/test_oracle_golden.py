@@ -14,7 +14,7 @@ def test_oracle_reproduces_reference_files(name, tmp_path):
     cfg = orc.OracleConfig(logdir, nprocs=1, **case["cfg"])
     orc.preprocess(cfg, demangle=demangle)
     checked = 0
-    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "cuda_api_trace.csv"):
         want = golden_bytes(name, fn)
         if want is None:
             assert not os.path.isfile(logdir + fn)

@@ -14,11 +14,12 @@ from sofa_b200.sofa_preprocess import sofa_preprocess
 def test_row_codecs_reproduce_reference_files(name, tmp_path):
     case, logdir = build_case_logdir(name, tmp_path)
     ov = dict(case["cfg"])
-    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None))
+    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None),
+                                cuda_api_tracing=ov.pop("cuda_api_tracing", False))
     for k, v in ov.items():
         setattr(cfg, k, v)
     sofa_preprocess(cfg, engine=HostSimEngine())
-    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "cuda_api_trace.csv"):
         want = golden_bytes(name, fn)
         if want is None:
             assert not os.path.isfile(logdir + fn)
