@@ -816,6 +816,53 @@ struct JsonWrite {
     SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
 };
 
+// Common-case name sinks: a name made only of printable ASCII plus the characters json.dump
+// writes as two-byte escapes (\" \\ \n \r \t \b \f) needs no UTF-8 / \uXXXX state machine.
+SOFA_HD uint64_t lanes_two_byte_escape(uint64_t w) {
+    return lanes_eq(w, '"') | lanes_eq(w, '\\') | lanes_eq(w, '\n') | lanes_eq(w, '\r') | lanes_eq(w, '\t') |
+           lanes_eq(w, '\b') | lanes_eq(w, '\f');
+}
+struct JsonScan {             // raw length, number of two-byte escapes, "needs the full encoder"
+    static constexpr bool WORDS = true;
+    int raw, two; bool complex;
+    SOFA_HD JsonScan() : raw(0), two(0), complex(false) {}
+    SOFA_HD void put(char ch) {
+        unsigned char b = (unsigned char)ch;
+        raw++;
+        if (json_plain(b)) return;
+        if (b == '"' || b == '\\' || b == '\n' || b == '\r' || b == '\t' || b == '\b' || b == '\f') two++;
+        else complex = true;
+    }
+    SOFA_HD void put_word(uint64_t w, int nb) {
+        uint64_t sp = json_special_lanes(w) & lanes_first(nb);
+        if (sp == 0) { raw += nb; return; }
+        for (int b = 0; b < nb; b++) { put((char)(w & 0xff)); w >>= 8; }
+    }
+};
+template <typename O>
+struct JsonSimpleWrite {      // valid only when JsonScan found complex == false
+    static constexpr bool WORDS = true;
+    O out; int n;
+    SOFA_HD void put(char ch) {
+        unsigned char b = (unsigned char)ch;
+        if (json_plain(b)) { out[n++] = ch; return; }
+        out[n++] = '\\';
+        char e = ch;
+        if (b == '\n') e = 'n'; else if (b == '\r') e = 'r'; else if (b == '\t') e = 't';
+        else if (b == '\b') e = 'b'; else if (b == '\f') e = 'f';
+        out[n++] = e;
+    }
+    SOFA_HD void put_word(uint64_t w, int nb) {
+        if ((json_special_lanes(w) & lanes_first(nb)) == 0 && nb == 8) {
+#pragma unroll
+            for (int b = 0; b < 8; b++) out[n + b] = (char)((w >> (8 * b)) & 0xff);
+            n += 8;
+            return;
+        }
+        for (int b = 0; b < nb; b++) { put((char)(w & 0xff)); w >>= 8; }
+    }
+};
+
 // Record text: {"x": V, "event": V, "y": V, "deviceId": V, ... "name": "S", "category": V}
 // (x=timestamp, y=duration renamed, :351-355).  Keys are written with fully unrolled
 // constant stores (one store per byte, no loads).  A record is emitted as ", " + {...}; the
@@ -830,20 +877,26 @@ struct JsonWrite {
 // total bytes of the 13 key texts + ", " + "{" ... "}" framing
 #define SOFA_JSON_FIXED (2 + 6 + 11 + 7 + 14 + 14 + 13 + 15 + 13 + 13 + 9 + 9 + 10 + 14 + 1)
 
-struct JsonRowPlan { int len; JPlan f[4]; };     // len: -1 unformattable number, -2 invalid UTF-8
+struct JsonRowPlan { int len; bool simple_name; JPlan f[4]; };     // len: -1 unformattable number, -2 invalid UTF-8
 
 template <class NG>
 SOFA_HD JsonRowPlan json_row_plan(const RowVals& v, uint32_t fmask, const NG& ng) {
     JsonRowPlan p;
+    p.simple_name = true;
     int n = SOFA_JSON_FIXED;
     if (!v.valid) { p.len = n + 13 * 4; return p; }
     int bad = 0;
 #pragma unroll
     for (int c = 0; c < 13; c++) {
         if (c == 11) {
-            JsonCount k; ng.gen(k);
-            if (k.e.bad || k.e.need) bad = -2;
-            n += k.len + 2;
+            JsonScan sc; ng.gen(sc);
+            p.simple_name = !sc.complex;
+            if (!sc.complex) n += sc.raw + sc.two + 2;
+            else {
+                JsonCount k; ng.gen(k);
+                if (k.e.bad || k.e.need) bad = -2;
+                n += k.len + 2;
+            }
         } else {
             bool isf; double f; int64_t i;
             col_value(v, c, fmask, &isf, &f, &i);
@@ -876,8 +929,8 @@ SOFA_HD int json_row_emit(const RowVals& v, uint32_t fmask, const NG& ng, const 
     if (!v.valid) { out[n] = 'n'; out[n + 1] = 'u'; out[n + 2] = 'l'; out[n + 3] = 'l'; n += 4; }
     else {
         out[n++] = '"';
-        JsonWrite<O> w{out + n, 0, JsonEsc()}; ng.gen(w);
-        n += w.n;
+        if (p.simple_name) { JsonSimpleWrite<O> w{out + n, 0}; ng.gen(w); n += w.n; }
+        else { JsonWrite<O> w{out + n, 0, JsonEsc()}; ng.gen(w); n += w.n; }
         out[n++] = '"';
     }
     SOFA_JKEY(", \"category\": "); SOFA_JNUM(12);
