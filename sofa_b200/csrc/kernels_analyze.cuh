@@ -75,6 +75,14 @@ __global__ void k_pairwise_combine(double* partial, int depth, double* out) {
         for (uint32_t i = 0; i < (1u << lev); i++) partial[i] = d_add(partial[2 * i], partial[2 * i + 1]);
     *out = d_add(0.0, partial[0]);
 }
+// one level of the combine sweep, ping-pong buffers: out[i] = in[2i] + in[2i+1]
+__global__ void __launch_bounds__(256) k_pairwise_level(const double* __restrict__ in, double* __restrict__ out, uint32_t n_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_out) out[i] = d_add(in[2 * i], in[2 * i + 1]);
+}
+__global__ void k_pairwise_finish(const double* in, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = d_add(0.0, in[0]);
+}
 // python-loop accumulation in row order (sofa_common.py:108-119 accum_bw)
 __global__ void k_seq_sum(const double* __restrict__ a, uint64_t n, double* out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;

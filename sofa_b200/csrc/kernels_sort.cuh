@@ -141,15 +141,41 @@ struct GatherR6 {
     __device__ __forceinline__ double operator[](uint64_t i) const { return round6_value(col[idx[i]]); }
     __device__ __forceinline__ GatherR6 operator+(uint64_t d) const { return GatherR6{col, idx + d}; }
 };
-// one thread per segment: numpy pairwise sum of the segment's values
+// numpy pairwise sum of every segment's values.  Small segments: one thread each.  Segments longer
+// than SEG_BIG are queued and summed by one block each (2^d sub-trees in parallel, tree-order combine).
+constexpr uint32_t SEG_BIG = 2048;
 __global__ void __launch_bounds__(128) k_seg_pairwise(const double* __restrict__ col, const uint32_t* __restrict__ vals,
                                                       const uint32_t* __restrict__ seg_start, uint32_t nseg, uint64_t n,
-                                                      double* __restrict__ sums) {
+                                                      double* __restrict__ sums, uint32_t* __restrict__ big_list,
+                                                      unsigned int* __restrict__ n_big) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseg) return;
     uint64_t a = seg_start[s], b = (s + 1 < nseg) ? seg_start[s + 1] : n;
+    if (b - a > SEG_BIG) { big_list[atomicAdd(n_big, 1u)] = s; return; }
     GatherR6 g{col, vals + a};
     sums[s] = pairwise_sum(g, b - a);
+}
+__global__ void __launch_bounds__(256) k_seg_pairwise_big(const double* __restrict__ col, const uint32_t* __restrict__ vals,
+                                                          const uint32_t* __restrict__ seg_start, uint32_t nseg, uint64_t n,
+                                                          double* __restrict__ sums, const uint32_t* __restrict__ big_list) {
+    __shared__ double part[256];
+    uint32_t s = big_list[blockIdx.x];
+    uint64_t a = seg_start[s], b = (s + 1 < nseg) ? seg_start[s + 1] : n;
+    uint64_t len = b - a;
+    int depth = 0;
+    while (depth < 8 && (len >> (depth + 1)) >= 256) depth++;
+    if (threadIdx.x < (1u << depth)) {
+        uint64_t st, l;
+        pairwise_subtree(len, depth, threadIdx.x, &st, &l);
+        GatherR6 g{col, vals + a + st};
+        part[threadIdx.x] = pairwise_sum(g, l);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int lev = depth - 1; lev >= 0; lev--)
+            for (uint32_t i = 0; i < (1u << lev); i++) part[i] = d_add(part[2 * i], part[2 * i + 1]);
+        sums[s] = d_add(0.0, part[0]);
+    }
 }
 // keys for ordering segments by their sum, descending; payload = segment index
 __global__ void __launch_bounds__(256) k_sum_keys_desc(const double* __restrict__ sums, uint32_t nseg, uint64_t* __restrict__ kout,
@@ -160,21 +186,25 @@ __global__ void __launch_bounds__(256) k_sum_keys_desc(const double* __restrict_
     vout[s] = s;
 }
 
-// names (full, '\0'-terminated) of a short list of rows, in list order; single block, serial.
+// names (full, '\0'-terminated) of a list of rows, in list order: lengths, then (after a prefix sum
+// on the host - the list is short) the bytes; one thread per row.
 template <int KIND>
-__global__ void k_rows_names(SrcView src, const uint32_t* __restrict__ rows, uint32_t nrows, char* out, uint64_t cap,
-                             uint64_t* __restrict__ name_off, unsigned long long* total) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t o = 0;
-    for (uint32_t i = 0; i < nrows; i++) {
-        uint64_t row = rows[i];
-        with_row<KIND, false>(src, row, row, [&](const RowVals&, const auto& ng) {
-            LenSink l; ng.gen(l);
-            if (out && o + l.len + 1 <= cap) { RawWrite<char*> w{out + o, 0}; ng.gen(w); out[o + l.len] = '\0'; name_off[i] = o; }
-            o += l.len + 1;
-        });
-    }
-    *total = o;
+__global__ void __launch_bounds__(128) k_rows_name_len(SrcView src, const uint32_t* __restrict__ rows, uint32_t nrows, uint32_t* lens) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    uint64_t row = rows[i];
+    with_row<KIND, false>(src, row, row, [&](const RowVals&, const auto& ng) { LenSink l; ng.gen(l); lens[i] = (uint32_t)l.len; });
+}
+template <int KIND>
+__global__ void __launch_bounds__(128) k_rows_name_write(SrcView src, const uint32_t* __restrict__ rows, uint32_t nrows,
+                                                         const uint64_t* __restrict__ name_off, char* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    uint64_t row = rows[i];
+    with_row<KIND, false>(src, row, row, [&](const RowVals&, const auto& ng) {
+        RawWrite<char*> w{out + name_off[i], 0}; ng.gen(w);
+        out[name_off[i] + w.n] = '\0';
+    });
 }
 // ts / duration (CSV values) of a short list of perf rows
 __global__ void k_rows_values(SrcView src, const uint32_t* __restrict__ rows, uint32_t nrows, double* ts, double* dur) {
