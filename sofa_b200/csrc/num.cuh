@@ -17,8 +17,10 @@
 
 #if defined(__CUDACC__)
 #define SOFA_HD __host__ __device__ __forceinline__
+#define SOFA_HD_COLD __host__ __device__ __noinline__
 #else
 #define SOFA_HD inline
+#define SOFA_HD_COLD __attribute__((noinline))
 #endif
 
 namespace sofa {

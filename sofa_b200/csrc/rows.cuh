@@ -487,9 +487,32 @@ SOFA_HD int parse_gpu(S s, int n, const IngestCfg& c, GpuRow* r) {
 }
 
 template <class K> SOFA_HD void put_lit(K& k, const char* lit) { for (int i = 0; lit[i]; i++) k.put(lit[i]); }
+// decimal digits of v straight into a sink: digits are produced least-significant first into
+// byte stacks held in registers (no local-memory buffer), then popped most-significant first
 template <class K> SOFA_HD void put_i64(K& k, int64_t v) {
-    char b[24]; int n = fmt_i64(v, (char*)b);
-    for (int i = 0; i < n; i++) k.put(b[i]);
+    uint64_t u = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    if (v < 0) k.put('-');
+    if ((u >> 32) == 0) {
+        uint32_t x = (uint32_t)u;
+        if (x < 10u) { k.put((char)('0' + x)); return; }
+        uint64_t r0 = 0, r1 = 0; int n = 0;
+        do { uint32_t q = x / 10u; uint64_t d = '0' + (x - q * 10u); if (n < 8) r0 = (r0 << 8) | d; else r1 = (r1 << 8) | d; x = q; n++; } while (x);
+        for (int i = 8; i < n; i++) { k.put((char)(r1 & 0xff)); r1 >>= 8; }
+        int m = n < 8 ? n : 8;
+        for (int i = 0; i < m; i++) { k.put((char)(r0 & 0xff)); r0 >>= 8; }
+        return;
+    }
+    uint64_t r0 = 0, r1 = 0, r2 = 0; int n = 0;
+    do {
+        uint64_t q = u / 10u; uint64_t d = '0' + (u - q * 10u);
+        if (n < 8) r0 = (r0 << 8) | d; else if (n < 16) r1 = (r1 << 8) | d; else r2 = (r2 << 8) | d;
+        u = q; n++;
+    } while (u);
+    for (int i = 16; i < n; i++) { k.put((char)(r2 & 0xff)); r2 >>= 8; }
+    int m1 = n < 16 ? n : 16;
+    for (int i = 8; i < m1; i++) { k.put((char)(r1 & 0xff)); r1 >>= 8; }
+    int m0 = n < 8 ? n : 8;
+    for (int i = 0; i < m0; i++) { k.put((char)(r0 & 0xff)); r0 >>= 8; }
 }
 
 template <class K>
@@ -877,6 +900,20 @@ struct JsonSimpleWrite {      // valid only when JsonScan found complex == false
 // total bytes of the 13 key texts + ", " + "{" ... "}" framing
 #define SOFA_JSON_FIXED (2 + 6 + 11 + 7 + 14 + 14 + 13 + 15 + 13 + 13 + 9 + 9 + 10 + 14 + 1)
 
+// rare path (control characters / non-ASCII in a name): full json.dump escaping, kept out of line
+// so that its state machine does not inflate the registers of the common path
+template <class NG>
+SOFA_HD_COLD int json_name_full_len(const NG& ng) {
+    JsonCount k; ng.gen(k);
+    if (k.e.bad || k.e.need) return -2;
+    return k.len;
+}
+template <class NG, typename O>
+SOFA_HD_COLD int json_name_full_write(const NG& ng, O out) {
+    JsonWrite<O> w{out, 0, JsonEsc()}; ng.gen(w);
+    return w.n;
+}
+
 struct JsonRowPlan { int len; bool simple_name; JPlan f[4]; };     // len: -1 unformattable number, -2 invalid UTF-8
 
 template <class NG>
@@ -893,9 +930,8 @@ SOFA_HD JsonRowPlan json_row_plan(const RowVals& v, uint32_t fmask, const NG& ng
             p.simple_name = !sc.complex;
             if (!sc.complex) n += sc.raw + sc.two + 2;
             else {
-                JsonCount k; ng.gen(k);
-                if (k.e.bad || k.e.need) bad = -2;
-                n += k.len + 2;
+                int l = json_name_full_len(ng);
+                if (l < 0) bad = -2; else n += l + 2;
             }
         } else {
             bool isf; double f; int64_t i;
@@ -930,7 +966,7 @@ SOFA_HD int json_row_emit(const RowVals& v, uint32_t fmask, const NG& ng, const 
     else {
         out[n++] = '"';
         if (p.simple_name) { JsonSimpleWrite<O> w{out + n, 0}; ng.gen(w); n += w.n; }
-        else { JsonWrite<O> w{out + n, 0, JsonEsc()}; ng.gen(w); n += w.n; }
+        else n += json_name_full_write(ng, out + n);
         out[n++] = '"';
     }
     SOFA_JKEY(", \"category\": "); SOFA_JNUM(12);
