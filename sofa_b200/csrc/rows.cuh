@@ -186,6 +186,10 @@ SOFA_HD int tokenize(S s, int n, Tok* t, int maxt) {
 // first position in [from, to) holding byte c (c < 128), or -1; 8 bytes per step
 SOFA_HD int find_char(const char* s, int n, int from, int to, unsigned char c) {
     if (from >= to) return -1;
+    if (to - from <= 10) {                         // short token: a byte loop beats the word setup
+        for (int i = from; i < to; i++) if ((unsigned char)s[i] == c) return i;
+        return -1;
+    }
     const int sh = line_misalign(s);
     int j0 = (from + sh) >> 3, j1 = (to - 1 + sh) >> 3;
     for (int j = j0; j <= j1; j++) {
