@@ -578,7 +578,9 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
     uint64_t per_row = FMT == FMT_CSV ? 96 : (FMT == FMT_COMM ? 64 : 230);
     if (FMT == FMT_COMM) text_share = 0;
     uint64_t cap = sel_hint * per_row + text_share + (1 << 16);
-    uint32_t slot_bytes = 40 * 1024;
+    // shared-memory image per block: sized for 128 typical rows of the format (larger ranges fall back
+    // to direct global writes); smaller images = more resident blocks per SM
+    uint32_t slot_bytes = FMT == FMT_COMM ? 16 * 1024 : 40 * 1024;      // (22 KB for CSV measured slower)
     for (int attempt = 0; attempt < 6; attempt++, cap *= 2) {
         char* outp = nullptr;
         { int ra = out_alloc(c, outslot, cap, &outp); if (ra) return ra; }
