@@ -28,7 +28,9 @@ extern "C" {
 #define SOFA_ERR_STATE (-4)  /* call order (e.g. emit before parse) */
 #define SOFA_ERR_CAP (-5)    /* caller buffer too small */
 
-enum { SOFA_SRC_PERF = 0, SOFA_SRC_GPU = 1, SOFA_SRC_NET = 2 };
+enum { SOFA_SRC_PERF = 0, SOFA_SRC_GPU = 1, SOFA_SRC_NET = 2,
+       /* 13-column trace CSV bodies read by concurrency_breakdown (upload + parse like a source) */
+       SOFA_SRC_MPSTAT_CSV = 3, SOFA_SRC_NVSMI_CSV = 4, SOFA_SRC_NETSTAT_CSV = 5 };
 
 typedef struct sofa_ctx sofa_ctx;
 
@@ -154,6 +156,20 @@ int sofa_b200_top_k(sofa_ctx*, int src, uint32_t k, double* sums, uint64_t* nbyt
  * cputrace.csv; their names '\0'-terminated into output buffer 2. */
 int sofa_b200_cpu_profile(sofa_ctx*, uint32_t k, double* total, uint64_t* rows, double* ts, double* dur,
                           uint64_t* names_nbytes, uint32_t* n_out);
+
+/* Per-window aggregates of concurrency_breakdown (sofa_analyze.py:75-243) over the parsed side
+ * tables: window k = (ends[k] - delta, ends[k]].  mpstat: row count, max usr/sys/idl/iow, sums of
+ * usr/sys/irq, max/min of usr+sys+irq (started at 0 / 100 as the reference does); nvsmi SM rows
+ * (event 0): count, max/min/sum duration, distinct deviceIds; netstat: tx (event 0) / rx (event 1)
+ * bandwidth sums (numpy pairwise, row order).  num_gpus = distinct deviceIds of the whole nvsmi table. */
+typedef struct {
+    uint32_t mp_count; int32_t usr_max, sys_max, idl_max, iow_max, cpu_max, cpu_min;
+    int64_t usr_sum, sys_sum, irq_sum;
+    uint32_t nv_count, nv_ndev; double nv_max, nv_min; int64_t nv_sum;
+    uint32_t tx_count, rx_count; double tx_sum, rx_sum;
+} sofa_window_t;
+int sofa_b200_window_reduce(sofa_ctx*, const double* ends, uint32_t n_windows, double delta, sofa_window_t* out,
+                            uint32_t* num_gpus);
 
 /* CUDA-event stopwatch on the ctx stream: mark(0) ... mark(1); elapsed = ms between them */
 int sofa_b200_mark(sofa_ctx*, int which);

@@ -519,3 +519,84 @@ def ujson_double_str(value, precision=10):
         whole += 1
     fs = ('%0*d' % (precision, frac)).rstrip('0') or '0'
     return ('-' if neg else '') + '%d.%s' % (whole, fs)
+
+
+# --------------------------------------------------------------------------- a14
+def window_ends(t_begin, t_end, sample_time):
+    """Window end times of concurrency_breakdown: repeated t = t + sample_time (sofa_analyze.py:89-99)."""
+    ends = []
+    t = t_begin
+    while t < t_end:
+        t = t + sample_time
+        ends.append(t)
+    return ends
+
+
+def concurrency_breakdown(df_mpstat, df_cpu, df_nvsmi, df_bandwidth, sys_mon_rate=10, is_idle_threshold=10,
+                          roi_begin=0, roi_end=0, spotlight_gpu=False):
+    """sofa_analyze.py:75-243 -> (feature list, performance table or None).  Windows (t-d, t];
+    per window: max usr/sys/idl/iow share of the mpstat rows, SM utilisation max/sum/min of the
+    nvsmi rows with event 0, tx/rx bandwidth sums; dominator classes; Pearson table."""
+    feats = []
+    if len(df_mpstat) == 0:
+        return feats, None
+    total = {'usr': 0, 'sys': 0, 'gpu': 0, 'iow': 0, 'idl': 0}
+    interval_vecs, perf_vecs = [], []
+    sample_time = (1 / float(sys_mon_rate))
+    t_begin = df_mpstat.iloc[0]['timestamp']
+    t_end = df_mpstat.iloc[-1]['timestamp']
+    num_gpus = len(list(set(df_nvsmi['deviceId'])))
+    for t in window_ends(t_begin, t_end, sample_time):
+        if roi_end > 0 and (t < roi_begin or t > roi_end):
+            continue
+        wb, we = t - sample_time, t
+        if len(df_cpu) > 0 and df_cpu.iloc[0].timestamp > we:
+            continue
+        nv = df_nvsmi[(df_nvsmi['timestamp'] > wb) & (df_nvsmi['timestamp'] <= we) & (df_nvsmi['event'] == int(0))]
+        mpi = df_mpstat[(df_mpstat['timestamp'] > wb) & (df_mpstat['timestamp'] <= we)]
+        inw = (df_bandwidth['timestamp'] > wb) & (df_bandwidth['timestamp'] <= we)
+        tx = df_bandwidth[inw & (df_bandwidth['event'] == float(0))]
+        rx = df_bandwidth[inw & (df_bandwidth['event'] == float(1))]
+        usr, sysv, idl, iow, irq = [], [], [], [], []
+        cpu_max, cpu_min = 0, 100
+        for i in range(len(mpi)):
+            r = mpi.iloc[i]['name'].split(':')[1].split('|')
+            usr.append(int(r[1])); sysv.append(int(r[2])); idl.append(int(r[3])); iow.append(int(r[4])); irq.append(int(r[5]))
+            c = int(r[1]) + int(r[2]) + int(r[5])
+            cpu_max = max(cpu_max, c)
+            cpu_min = min(cpu_min, c)
+        if len(mpi) == 0:
+            continue
+        mp = {k: np.asarray([sample_time * v / 100.0 for v in arr]) for k, arr in
+              (('usr', usr), ('sys', sysv), ('idl', idl), ('iow', iow))}
+        elapsed = {'usr': mp['usr'].max(), 'sys': mp['sys'].max(),
+                   'gpu': nv['duration'].max() * 0.01 * sample_time, 'iow': mp['iow'].max(), 'idl': 0}
+        dominator = max(elapsed, key=elapsed.get)
+        if elapsed[dominator] > sample_time * int(is_idle_threshold) / 100:
+            total[dominator] = total[dominator] + sample_time
+        else:
+            total['idl'] += sample_time
+        time_gpu_avg = nv['duration'].sum() * 0.01 * sample_time / num_gpus if num_gpus > 0 else 0
+        interval_vecs.append((mp['usr'].max(), mp['sys'].max(), mp['iow'].max(), mp['idl'].max(), time_gpu_avg,
+                              tx['bandwidth'].sum(), rx['bandwidth'].sum()))
+        sm_avg = nv['duration'].sum() / int(len(list(set(nv['deviceId'])))) if num_gpus > 0 else 0
+        perf_vecs.append((we, nv['duration'].max(), sm_avg, nv['duration'].min(),
+                          round((np.asarray(usr).mean() + np.asarray(sysv).mean() + np.asarray(irq).mean()), 0),
+                          cpu_max, cpu_min))
+    total_all = sum(total.values())
+    if total_all > 0:
+        ratio = {k: 100 * total[k] / total_all for k in total}
+        hotspot = roi_end - roi_begin if spotlight_gpu else 0
+        feats += [('elapsed_usr_time_ratio', ratio['usr']), ('elapsed_sys_time_ratio', ratio['sys']),
+                  ('elapsed_gpu_time_ratio', ratio['gpu']), ('elapsed_iow_time_ratio', ratio['iow']),
+                  ('elapsed_hotspot_time', hotspot)]
+    perf = None
+    if len(perf_vecs) > 0:
+        perf = pd.DataFrame(perf_vecs, columns=['time', 'max_gpu_util', 'avg_gpu_util', 'min_gpu_util', 'cpu_util',
+                                                'cpu_max', 'cpu_min'])
+        vt = pd.DataFrame(interval_vecs, columns=['usr', 'sys', 'iow', 'idl', 'gpu', 'net_tx', 'net_rx'])
+        pearson = vt.corr(method='pearson').round(2)
+        feats += [('corr_gpu_usr', pearson['gpu'].usr), ('corr_gpu_sys', pearson['gpu'].sys),
+                  ('corr_gpu_iow', pearson['gpu'].iow), ('corr_gpu_ntx', pearson['gpu'].net_tx),
+                  ('corr_gpu_nrx', pearson['gpu'].net_rx)]
+    return feats, perf

@@ -16,7 +16,7 @@ EXPORTS = [
     "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
     "sofa_b200_synth", "sofa_b200_text_fetch", "sofa_b200_mark", "sofa_b200_elapsed_ms",
-    "sofa_b200_upload_async", "sofa_b200_fetch_async", "sofa_b200_wait_fetch", "sofa_b200_sync", "sofa_b200_set_output_arena", "sofa_b200_emit_comm_csv",
+    "sofa_b200_upload_async", "sofa_b200_fetch_async", "sofa_b200_wait_fetch", "sofa_b200_sync", "sofa_b200_set_output_arena", "sofa_b200_emit_comm_csv", "sofa_b200_window_reduce",
 ]
 
 
@@ -37,6 +37,16 @@ class GpuProfile(ctypes.Structure):
                 ("bandwidth", ctypes.c_double * 4), ("duration", ctypes.c_double * 4),
                 ("accum", ctypes.c_double * 256), ("accum_count", ctypes.c_double * 256),
                 ("accum_bw", ctypes.c_double * 256), ("accum_bw_count", ctypes.c_double * 256)]
+
+
+class Window(ctypes.Structure):
+    _fields_ = [("mp_count", ctypes.c_uint32), ("usr_max", ctypes.c_int32), ("sys_max", ctypes.c_int32),
+                ("idl_max", ctypes.c_int32), ("iow_max", ctypes.c_int32), ("cpu_max", ctypes.c_int32),
+                ("cpu_min", ctypes.c_int32), ("usr_sum", ctypes.c_int64), ("sys_sum", ctypes.c_int64),
+                ("irq_sum", ctypes.c_int64), ("nv_count", ctypes.c_uint32), ("nv_ndev", ctypes.c_uint32),
+                ("nv_max", ctypes.c_double), ("nv_min", ctypes.c_double), ("nv_sum", ctypes.c_int64),
+                ("tx_count", ctypes.c_uint32), ("rx_count", ctypes.c_uint32), ("tx_sum", ctypes.c_double),
+                ("rx_sum", ctypes.c_double)]
 
 
 class Stats(ctypes.Structure):
@@ -96,6 +106,8 @@ def load_lib():
     lib.sofa_b200_set_output_arena.argtypes = [vp, ctypes.c_uint64]
     lib.sofa_b200_mark.argtypes = [vp, ctypes.c_int]
     lib.sofa_b200_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    lib.sofa_b200_window_reduce.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32, ctypes.c_double,
+                                            ctypes.POINTER(Window), u32p]
     lib.sofa_b200_set_profiling.argtypes = [vp, ctypes.c_int]
     lib.sofa_b200_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.sofa_b200_reset_stats.argtypes = [vp]

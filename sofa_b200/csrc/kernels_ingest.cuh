@@ -22,7 +22,9 @@ struct GpuCols {
 };
 struct NetCols { double* ts; int64_t *payload, *src, *dst; uint8_t* proto; };
 
-struct AllCols { PerfCols p; GpuCols g; NetCols n; };
+struct SideCols { double *ts, *event, *dur, *dev, *bw; int32_t* ratios; };      // ratios: 5 per row
+
+struct AllCols { PerfCols p; GpuCols g; NetCols n; SideCols s; };
 
 __device__ __forceinline__ uint32_t newline_mask4(uint32_t w) {       // 0xff in every byte equal to '\n'
     return __vcmpeq4(w, 0x0a0a0a0au);
@@ -182,6 +184,14 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
                     cols.g.dev[row] = r.dev; cols.g.tid[row] = r.tid; cols.g.src[row] = r.src; cols.g.dst[row] = r.dst;
                     cols.g.kind[row] = r.kind; cols.g.bwf[row] = r.bw_is_float;
                     cols.g.line_start[row] = s0 + ls; cols.g.noff[row] = r.name_off; cols.g.nlen[row] = r.name_len;
+                }
+            } else if (KIND == SRC_SIDE) {
+                SideRow r;
+                code = parse_side(line, n, cfg, &r);
+                if (code == E_OK) {
+                    cols.s.ts[row] = r.ts; cols.s.event[row] = r.event; cols.s.dur[row] = r.dur; cols.s.dev[row] = r.dev;
+                    cols.s.bw[row] = r.bw;
+                    for (int q = 0; q < 5; q++) cols.s.ratios[row * 5 + q] = r.r[q];
                 }
             } else {
                 NetRow r;

@@ -12,7 +12,7 @@
 
 namespace sofa {
 
-enum { SRC_PERF = 0, SRC_GPU = 1, SRC_NET = 2 };
+enum { SRC_PERF = 0, SRC_GPU = 1, SRC_NET = 2, SRC_SIDE = 3 };      // SIDE: a 13-column trace CSV row
 
 // row-level error codes (the reference raises for all of these; we fail loudly with the row)
 enum {
@@ -44,6 +44,7 @@ struct IngestCfg {
     int n_cudaproc;                                   // pid column (:288)
     int idx_start, idx_dur, idx_size, idx_thr, idx_ctx, idx_stream, idx_name, idx_srcctx, idx_dstctx;
     int api_mode;            // nvprof --print-api-trace rows (cuda_api_trace_read, :203-247)
+    int side_table;          // SRC_SIDE: 0 mpstat.csv (name carries usr|sys|idl|iow|irq), 1 nvsmi_trace.csv, 2 netstat.csv
 };
 
 struct Tok { int a, b; };
@@ -610,6 +611,63 @@ struct NetName {
         put_i64(k, r.src); put_lit(k, "_to_"); put_i64(k, r.dst); put_lit(k, "_with_"); put_i64(k, r.payload);
     }
 };
+
+// ============================================================================ side-table CSV rows
+// pd.read_csv row of mpstat.csv / nvsmi_trace.csv / netstat.csv as concurrency_breakdown uses it
+// (sofa_analyze.py:75-243): timestamp, event, duration, deviceId, bandwidth and, for mpstat, the five
+// integers of name.split(':')[1].split('|')[1:6] (:136-147).  Quoted fields are refused.
+struct SideRow { double ts, event, dur, dev, bw; int32_t r[5]; };
+
+template <typename S>
+SOFA_HD int parse_side(S s, int n, const IngestCfg& c, SideRow* r) {
+    if (n > 65535) return E_LINE_TOO_LONG;
+    int fa[13], fb[13];
+    int f = 0, a = 0;
+    {
+        const int sh = line_misalign(s);
+        const int nw = (n + sh + 7) >> 3;
+        for (int j = 0; j < nw; j++) {
+            uint64_t w = line_word(s, n, sh, j);
+            if (eq8(w, '"') & valid8(n, sh, j)) return E_UNSUPPORTED_NUM;
+            uint32_t m = eq8(w, ',') & valid8(n, sh, j);
+            while (m) {
+                int i = 8 * j - sh + ctz32(m);
+                m &= m - 1;
+                if (f < 13) { fa[f] = a; fb[f] = i; }
+                f++; a = i + 1;
+            }
+        }
+        if (f < 13) { fa[f] = a; fb[f] = n; }
+        f++;
+    }
+    if (f != 13) return E_FEW_TOKENS;
+    double* dst[5] = {&r->ts, &r->event, &r->dur, &r->dev, &r->bw};
+    const int col[5] = {0, 1, 2, 3, 6};
+    for (int k = 0; k < 5; k++) {
+        int st = parse_double(s + fa[col[k]], fb[col[k]] - fa[col[k]], dst[k]);
+        if (st) return num_status_to_err(st, true);
+    }
+    for (int k = 0; k < 5; k++) r->r[k] = 0;
+    if (c.side_table == 0) {
+        int p = find_char(s, n, fa[11], fb[11], ':');                 // .split(':')[1]
+        if (p < 0) return E_FEW_TOKENS;
+        int e2 = find_char(s, n, p + 1, fb[11], ':');
+        int end = e2 < 0 ? fb[11] : e2;
+        int q = find_char(s, n, p + 1, end, '|');                     // .split('|')[0] is dropped
+        for (int k = 0; k < 5; k++) {
+            if (q < 0) return E_FEW_TOKENS;
+            int q2 = find_char(s, n, q + 1, end, '|');
+            int stop = q2 < 0 ? end : q2;
+            int64_t v;
+            int st = parse_i64(s + q + 1, stop - q - 1, &v);
+            if (st) return num_status_to_err(st, false);
+            if (v < -1000000 || v > 1000000) return E_RANGE;
+            r->r[k] = (int32_t)v;
+            q = q2;
+        }
+    }
+    return E_OK;
+}
 
 // ============================================================================ 13-column row values
 struct RowVals {

@@ -12,6 +12,7 @@
 #include "kernels_emit.cuh"
 #include "kernels_analyze.cuh"
 #include "kernels_sort.cuh"
+#include "kernels_window.cuh"
 #include "synth.cuh"
 
 using namespace sofa;
@@ -61,7 +62,7 @@ struct TimedEvent { int kind; cudaEvent_t a, b; };
 struct sofa_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    Source src[3];
+    Source src[6];                       // 0 perf, 1 gpu, 2 net, 3..5 side tables (mpstat, nvsmi, netstat CSV)
     DevBuf out[3]; uint64_t out_n[3] = {0, 0, 0};
     // overlapped transfers: copy streams, the idle halves of the csv/json double buffers and the
     // D2H-complete event of each half
@@ -189,9 +190,18 @@ static int reset_err(sofa_ctx* c) {
 enum { PC_TS = 0, PC_EVENT, PC_DUR, PC_PID, PC_TID, PC_LS, PC_PIECES };
 enum { GC_TS = 0, GC_DUR, GC_BW, GC_PAYLOAD, GC_DEV, GC_TID, GC_SRC, GC_DST, GC_KIND, GC_BWF, GC_LS, GC_NOFF, GC_NLEN };
 enum { NC_TS = 0, NC_PAYLOAD, NC_SRC, NC_DST, NC_PROTO };
+enum { SC_TS = 0, SC_EVENT, SC_DUR, SC_DEV, SC_BW, SC_RATIOS };
 
-static AllCols all_cols(sofa_ctx* c) {
+static SideCols side_cols(sofa_ctx* c, int slot) {
+    Source& t = c->src[slot];
+    SideCols sc;
+    sc.ts = t.cols[SC_TS].as<double>(); sc.event = t.cols[SC_EVENT].as<double>(); sc.dur = t.cols[SC_DUR].as<double>();
+    sc.dev = t.cols[SC_DEV].as<double>(); sc.bw = t.cols[SC_BW].as<double>(); sc.ratios = t.cols[SC_RATIOS].as<int32_t>();
+    return sc;
+}
+static AllCols all_cols(sofa_ctx* c, int side_slot = 3) {
     AllCols a;
+    a.s = side_cols(c, side_slot);
     Source& p = c->src[0]; Source& g = c->src[1]; Source& n = c->src[2];
     a.p.ts = p.cols[PC_TS].as<double>(); a.p.event = p.cols[PC_EVENT].as<double>(); a.p.dur = p.cols[PC_DUR].as<double>();
     a.p.pid = p.cols[PC_PID].as<int32_t>(); a.p.tid = p.cols[PC_TID].as<int32_t>();
@@ -231,9 +241,12 @@ static int alloc_cols(sofa_ctx* c, int k, uint64_t n) {
         ENSURE(s.cols[GC_PAYLOAD], m * 8); ENSURE(s.cols[GC_DEV], m * 4); ENSURE(s.cols[GC_TID], m * 4);
         ENSURE(s.cols[GC_SRC], m * 4); ENSURE(s.cols[GC_DST], m * 4); ENSURE(s.cols[GC_KIND], m);
         ENSURE(s.cols[GC_BWF], m); ENSURE(s.cols[GC_LS], m * 8); ENSURE(s.cols[GC_NOFF], m * 2); ENSURE(s.cols[GC_NLEN], m * 2);
-    } else {
+    } else if (k == SRC_NET) {
         ENSURE(s.cols[NC_TS], m * 8); ENSURE(s.cols[NC_PAYLOAD], m * 8); ENSURE(s.cols[NC_SRC], m * 8);
         ENSURE(s.cols[NC_DST], m * 8); ENSURE(s.cols[NC_PROTO], m);
+    } else {
+        ENSURE(s.cols[SC_TS], m * 8); ENSURE(s.cols[SC_EVENT], m * 8); ENSURE(s.cols[SC_DUR], m * 8);
+        ENSURE(s.cols[SC_DEV], m * 8); ENSURE(s.cols[SC_BW], m * 8); ENSURE(s.cols[SC_RATIOS], m * 20);
     }
     return 0;
 }
@@ -318,6 +331,7 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaFuncSetAttribute(k_parse<SRC_PERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_parse<SRC_GPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_parse<SRC_NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_parse<SRC_SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_PERF, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_PERF, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_GPU, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -341,12 +355,12 @@ int sofa_b200_destroy(sofa_ctx* c) {
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& e : c->pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 6; k++) {
         Source& s = c->src[k];
         s.text.release(); s.mhz.release(); s.mask.release(); s.vizhash.release(); s.viz_id.release();
         s.dict_hash.release(); s.dict_off.release(); s.dict_blob.release();
         for (auto& b : s.cols) b.release();
-        c->out[k].release();
+        if (k < 3) c->out[k].release();
     }
     c->tiles.release(); c->rowlen.release(); c->blockoff.release(); c->scratch.release(); c->ftable.release();
     c->keys.release(); c->rows.release();
@@ -367,7 +381,7 @@ void* sofa_b200_host_alloc(uint64_t nbytes) {
 void sofa_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
-    if (!c || k < 0 || k > 2 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload: bad argument");
+    if (!c || k < 0 || k > 5 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload: bad argument");
     if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload: data_off beyond the text");
     CK(cudaSetDevice(c->device));
     Source& s = c->src[k];
@@ -381,10 +395,10 @@ int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint
     return 0;
 }
 
-static uint32_t pick_tile_bytes(int k) { return k == SRC_NET ? 16384u : 24576u; }
+static uint32_t pick_tile_bytes(int k) { return (k == SRC_NET || k >= 3) ? 16384u : 24576u; }
 
 int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t* n_rows) {
-    if (!c || k < 0 || k > 2 || !p) FAIL(SOFA_ERR_ARG, "parse: bad argument");
+    if (!c || k < 0 || k > 5 || !p) FAIL(SOFA_ERR_ARG, "parse: bad argument");
     Source& s = c->src[k];
     if (!s.uploaded) FAIL(SOFA_ERR_STATE, "parse: nothing uploaded for this source");
     CK(cudaSetDevice(c->device));
@@ -398,6 +412,7 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     cfg.idx_ctx = p->idx[4]; cfg.idx_stream = p->idx[5]; cfg.idx_name = p->idx[6]; cfg.idx_srcctx = p->idx[7];
     cfg.idx_dstctx = p->idx[8];
     cfg.api_mode = p->api_mode;
+    cfg.side_table = k >= 3 ? k - 3 : 0;
     if (k == SRC_GPU && (cfg.idx_start < 0 || cfg.idx_dur < 0 || cfg.idx_name < 0))
         FAIL(SOFA_ERR_ARG, "parse: gpu trace needs Start, Duration and Name columns");
     ENSURE(s.mhz, 16 * (size_t)cfg.n_mhz + 16);
@@ -435,8 +450,11 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     s.n_rows = total;
     uint32_t max_lines = tile / 8;
     size_t smem = (((size_t)tile + OVERLAP_BYTES + 48) & ~(size_t)15) + (size_t)max_lines * 4;
-    AllCols cols = all_cols(c);
-    if (k == SRC_PERF)
+    AllCols cols = all_cols(c, k >= 3 ? k : 3);
+    if (k >= 3)
+        LAUNCH(c, K_PARSE, (k_parse<SRC_SIDE><<<(unsigned)ntiles, PARSE_TPB, smem, c->stream>>>(
+            s.text.as<char>(), begin, end, tile, max_lines, c->tiles.as<uint64_t>(), cfg, cols, c->d_err)));
+    else if (k == SRC_PERF)
         LAUNCH(c, K_PARSE, (k_parse<SRC_PERF><<<(unsigned)ntiles, PARSE_TPB, smem, c->stream>>>(
             s.text.as<char>(), begin, end, tile, max_lines, c->tiles.as<uint64_t>(), cfg, cols, c->d_err)));
     else if (k == SRC_GPU)
@@ -948,6 +966,7 @@ int sofa_b200_text_fetch(sofa_ctx* c, int k, void* host_out, uint64_t cap) {
 }
 
 #include "capi_analyze.inc"
+#include "capi_window.inc"
 #include "capi_synth.inc"
 
 }  // extern "C"

@@ -225,6 +225,15 @@ class CudaEngine:
         names = self._fetch(2, nb.value).tobytes().decode().split('\x00')[:-1] if nb.value else []
         return total.value, [(rows[i], ts[i], dur[i], names[i]) for i in range(cnt.value)]
 
+    def window_reduce(self, ends, delta):
+        """Per-window aggregates of the parsed side tables (sources 3,4,5) -> (list of Window, num_gpus)."""
+        ends = np.ascontiguousarray(ends, dtype=np.float64)
+        out = (L.Window * len(ends))()
+        ng = ctypes.c_uint32()
+        self._check(self.lib.sofa_b200_window_reduce(self.ctx, ends.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                     len(ends), float(delta), out, ctypes.byref(ng)))
+        return out, ng.value
+
     # ---- stopwatch (CUDA events on the engine's stream)
     def mark(self, which):
         self._check(self.lib.sofa_b200_mark(self.ctx, which))

@@ -105,6 +105,115 @@ def cpu_profile(cfg, eng):
     return total, rows
 
 
+SRC_MPSTAT_CSV, SRC_NVSMI_CSV, SRC_NETSTAT_CSV = 3, 4, 5
+
+
+def _csv_body(path):
+    with open(path, 'rb') as f:
+        data = f.read()
+    nl = data.find(b'\n')
+    return data[nl + 1:] if nl >= 0 else b''
+
+
+def _first_last_timestamp(body):
+    first = body[:body.find(b',')]
+    tail = body.rstrip(b'\n')
+    last_line = tail[tail.rfind(b'\n') + 1:]
+    return float(first), float(last_line[:last_line.find(b',')])
+
+
+def concurrency_breakdown(logdir, cfg, eng, features):
+    """sofa_analyze.py:75-243.  The per-window masks over mpstat.csv / nvsmi_trace.csv / netstat.csv
+    (O(windows x rows) in the reference) are one device pass (`window_reduce`); the scalar logic per
+    window and the small tables (performance.csv, Pearson) stay on the host as in the reference."""
+    import numpy as np
+    import pandas as pd
+    from . import hostlogic as hl2
+    bodies = {}
+    for k, fn in ((SRC_MPSTAT_CSV, 'mpstat.csv'), (SRC_NVSMI_CSV, 'nvsmi_trace.csv'), (SRC_NETSTAT_CSV, 'netstat.csv')):
+        bodies[k] = _csv_body(logdir + fn) if os.path.isfile(logdir + fn) else b''
+    if len(bodies[SRC_MPSTAT_CSV]) == 0:
+        print_warning(cfg, 'no mpstat and perf traces!')
+        return features
+    for k in (SRC_MPSTAT_CSV, SRC_NVSMI_CSV, SRC_NETSTAT_CSV):
+        eng.upload(k, bodies[k])
+        eng.parse(k, hl2.base_params(k, 0.0, True))
+    t_begin, t_end = _first_last_timestamp(bodies[SRC_MPSTAT_CSV])
+    sample_time = (1 / float(cfg.sys_mon_rate))
+    first_cpu = None
+    if os.path.isfile(logdir + 'cputrace.csv'):
+        cb = _csv_body(logdir + 'cputrace.csv')
+        if cb:
+            first_cpu = float(cb[:cb.find(b',')])
+    ends = []
+    t = t_begin
+    while t < t_end:                                             # :89-99, repeated addition
+        t = t + sample_time
+        ends.append(t)
+    if not ends:
+        return features
+    wins, num_gpus = eng.window_reduce(ends, sample_time)
+    total = {'usr': 0, 'sys': 0, 'gpu': 0, 'iow': 0, 'idl': 0}
+    interval_vecs, perf_vecs = [], []
+    nan = float('nan')
+    for t, w in zip(ends, wins):
+        if cfg.roi_end > 0 and (t < cfg.roi_begin or t > cfg.roi_end):
+            continue
+        if first_cpu is not None and first_cpu > t:
+            continue
+        if w.mp_count == 0:
+            continue
+        usr_max = np.float64(sample_time * w.usr_max / 100.0)
+        sys_max = np.float64(sample_time * w.sys_max / 100.0)
+        idl_max = np.float64(sample_time * w.idl_max / 100.0)
+        iow_max = np.float64(sample_time * w.iow_max / 100.0)
+        nv_max = np.int64(int(w.nv_max)) if w.nv_count else nan
+        nv_min = np.int64(int(w.nv_min)) if w.nv_count else nan
+        nv_sum = np.int64(w.nv_sum)
+        elapsed = {'usr': usr_max, 'sys': sys_max, 'gpu': nv_max * 0.01 * sample_time, 'iow': iow_max, 'idl': 0}
+        dominator = max(elapsed, key=elapsed.get)
+        if elapsed[dominator] > sample_time * int(cfg.is_idle_threshold) / 100:
+            total[dominator] = total[dominator] + sample_time
+        else:
+            total['idl'] += sample_time
+        time_gpu_avg = nv_sum * 0.01 * sample_time / num_gpus if num_gpus > 0 else 0
+        interval_vecs.append((usr_max, sys_max, iow_max, idl_max, time_gpu_avg,
+                              w.tx_sum if w.tx_count else 0.0, w.rx_sum if w.rx_count else 0.0))
+        with np.errstate(all='ignore'):
+            sm_avg = nv_sum / int(w.nv_ndev) if num_gpus > 0 else 0
+        cpu_util = round((np.float64(w.usr_sum) / w.mp_count + np.float64(w.sys_sum) / w.mp_count +
+                          np.float64(w.irq_sum) / w.mp_count), 0)
+        perf_vecs.append((t, nv_max, sm_avg, nv_min, cpu_util, w.cpu_max, w.cpu_min))
+    total_all = sum(total.values())
+    if total_all > 0:
+        ratio = {k: 100 * total[k] / total_all for k in total}
+        if cfg.verbose:
+            print('Elapsed Time = %.1lf ' % total_all)
+            print('USR = %.1lf %%' % ratio['usr'])
+            print('SYS = %.1lf %%' % ratio['sys'])
+            if num_gpus > 0:
+                print('GPU = %.1lf %%' % ratio['gpu'])
+            print('IDL = %.1lf %%' % ratio['idl'])
+            print('IOW = %.1lf %%' % ratio['iow'])
+        hotspot = cfg.roi_end - cfg.roi_begin if cfg.spotlight_gpu else 0
+        features += [('elapsed_usr_time_ratio', ratio['usr']), ('elapsed_sys_time_ratio', ratio['sys']),
+                     ('elapsed_gpu_time_ratio', ratio['gpu']), ('elapsed_iow_time_ratio', ratio['iow']),
+                     ('elapsed_hotspot_time', hotspot)]
+    if len(perf_vecs) > 0:
+        perf = pd.DataFrame(perf_vecs, columns=['time', 'max_gpu_util', 'avg_gpu_util', 'min_gpu_util', 'cpu_util',
+                                                'cpu_max', 'cpu_min'])
+        perf.to_csv('%s/performance.csv' % logdir)
+        vt = pd.DataFrame(interval_vecs, columns=['usr', 'sys', 'iow', 'idl', 'gpu', 'net_tx', 'net_rx'])
+        pearson = vt.corr(method='pearson').round(2)
+        if cfg.verbose:
+            print('Correlation Table :')
+            print(pearson)
+        features += [('corr_gpu_usr', pearson['gpu'].usr), ('corr_gpu_sys', pearson['gpu'].sys),
+                     ('corr_gpu_iow', pearson['gpu'].iow), ('corr_gpu_ntx', pearson['gpu'].net_tx),
+                     ('corr_gpu_nrx', pearson['gpu'].net_rx)]
+    return features
+
+
 def load_perf_source(cfg, eng):
     """(Re-)ingest perf.script exactly as sofa_preprocess does (sofa_preprocess.py:1786-1807)."""
     logdir = cfg.logdir
@@ -174,6 +283,12 @@ def sofa_analyze(cfg, engine=None):
             features += gpu_profile(cfg, eng)
         else:
             print_warning(cfg, "%sgputrace.csv is not found. If there is no need to profile GPU, just ignore it." % logdir)
+        if os.path.isfile(logdir + "mpstat.csv") and os.path.getsize(logdir + "mpstat.csv") > 0:     # :979-984
+            if eng is None:
+                from .engine import CudaEngine
+                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
+                own = True
+            features = concurrency_breakdown(logdir, cfg, eng, features)
     finally:
         if own and eng is not None:
             eng.close()

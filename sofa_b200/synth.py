@@ -284,3 +284,54 @@ def make_logdir(logdir, seed, n_perf=0, n_gpu=0, n_net=0, cpu_col=False,
         with open(os.path.join(logdir, "net.tmp"), "w") as f:
             f.write(net_text(seed, n_net, non_ip_pct))
         open(os.path.join(logdir, "sofa.pcap"), "w").close()
+
+
+# ----------------------------------------------------------------------------- side sources
+# Raw side logs as the recorder writes them (sofa_record.py:62-135, 303-310), consumed by the
+# reference's preprocess (sofa_preprocess.py:482-546 mpstat, 1013-1098 nvsmi_query, 1235-1337
+# netstat).  Used to produce mpstat.csv / nvsmi_trace.csv / netstat.csv inputs for
+# concurrency_breakdown (sofa_analyze.py:75-243).
+def write_side_raw(logdir, seed, n_samples=60, n_cores=4, n_gpus=2, rate_hz=10):
+    import datetime
+    os.makedirs(logdir, exist_ok=True)
+    t0 = TIME_BASE + 0.5
+    dt = 1.0 / rate_hz
+    # mpstat.txt: header + cumulative jiffies per (sample, cpu); cpu -1 = all
+    cum = [[0] * 7 for _ in range(n_cores + 1)]
+    with open(os.path.join(logdir, "mpstat.txt"), "w") as f:
+        f.write("time,cpu,user,nice,system,idle,iowait,irq,softirq\n")
+        for s in range(n_samples):
+            t = t0 + s * dt
+            for ci, cpu in enumerate([-1] + list(range(n_cores))):
+                r = rnd(seed, 5, s * 64 + ci, 0)
+                phase = (s // 15) % 3                      # busy / gpu-bound / idle phases
+                usr = (r & 63) + (40 if phase == 0 else 3)
+                sysj = ((r >> 6) & 15) + (10 if phase == 0 else 1)
+                iow = ((r >> 10) & 7) if phase != 2 else 0
+                irq = (r >> 13) & 3
+                idl = 100 - min(99, usr + sysj + iow + irq) + ((r >> 15) & 7)
+                inc = [usr, 0, sysj, idl, iow, irq, (r >> 18) & 1]
+                for k in range(7):
+                    cum[ci][k] += inc[k]
+                f.write("%.6f,%d,%s\n" % (t, cpu, ",".join(str(v) for v in cum[ci])))
+    # nvsmi_query.txt: first line skipped, "timestamp, name, index, sm %, mem %"
+    with open(os.path.join(logdir, "nvsmi_query.txt"), "w") as f:
+        f.write("timestamp, name, index, utilization.gpu [%], utilization.memory [%]\n")
+        for s in range(n_samples):
+            t = t0 + 0.013 + s * dt
+            ts = datetime.datetime.fromtimestamp(t).strftime('%Y/%m/%d %H:%M:%S.%f')[:-3]
+            for g in range(n_gpus):
+                r = rnd(seed, 6, s * 16 + g, 0)
+                phase = (s // 15) % 3
+                sm = (r % 30) + (65 if phase == 1 else (20 if phase == 0 else 0))
+                mem = (r >> 8) % 60
+                f.write("%s, Tesla V100-SXM2-16GB, %d, %d %%, %d %%\n" % (ts, g, sm, mem))
+    # netstat.txt: time,tx_bytes,rx_bytes (cumulative)
+    tx = rx = 0
+    with open(os.path.join(logdir, "netstat.txt"), "w") as f:
+        for s in range(n_samples + 1):
+            t = t0 - dt + 0.031 + s * dt
+            r = rnd(seed, 7, s, 0)
+            tx += r % 1000000
+            rx += (r >> 20) % 3000000
+            f.write("%.6f,%d,%d\n" % (t, tx, rx))

@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Golden fixtures for concurrency_breakdown (a14): the UNMODIFIED reference preprocess turns
+synthetic mpstat / nvsmi_query / netstat raw logs into mpstat.csv, nvsmi_trace.csv, netstat.csv
+(+ cputrace.csv); the UNMODIFIED reference concurrency_breakdown (called directly: the analyze
+driver line :981 fails on pandas 3) produces performance.csv and the feature rows.  Build
+container only (needs /root/reference)."""
+import contextlib
+import io
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, HERE)
+import make_golden as mg  # noqa: E402
+from sofa_b200 import synth  # noqa: E402
+
+CASES = {
+    "side_small": (dict(seed=91, n_samples=60, n_cores=4, n_gpus=2), dict()),
+    "side_thresh": (dict(seed=92, n_samples=45, n_cores=2, n_gpus=1), dict(is_idle_threshold=25, sys_mon_rate=5)),
+}
+
+
+def main():
+    mg.install_stubs()
+    sys.path.insert(0, mg.REF_BIN)
+    shimdir = tempfile.mkdtemp(prefix="sofa_shims_")
+    mg.install_shims(shimdir)
+    import pandas as pd
+    for name, (mk, ov) in CASES.items():
+        work = tempfile.mkdtemp(prefix="sofa_golden_")
+        logdir = os.path.join(work, "sofalog") + "/"
+        synth.make_logdir(logdir, seed=mk["seed"], n_perf=120)
+        synth.write_side_raw(logdir, **mk)
+        cfg = mg.make_ref_cfg(logdir, ov)
+        import sofa_preprocess as ref_pre
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_pre.sofa_preprocess(cfg)
+        import sofa_analyze as ref_an
+        df_mpstat = pd.read_csv(logdir + "mpstat.csv")
+        df_cpu = pd.read_csv(logdir + "cputrace.csv")
+        df_nvsmi = pd.read_csv(logdir + "nvsmi_trace.csv")
+        df_bw = pd.read_csv(logdir + "netstat.csv")
+        feats = pd.DataFrame({'name': ['elapsed_time'], 'value': [12.5]}, columns=['name', 'value'])
+        with contextlib.redirect_stdout(io.StringIO()):
+            feats = ref_an.concurrency_breakdown(logdir, cfg, df_mpstat, df_cpu, pd.DataFrame([], columns=cfg.columns),
+                                                 df_nvsmi, df_bw, feats)
+        out = os.path.join(HERE, name)
+        shutil.rmtree(out, ignore_errors=True)
+        os.makedirs(out)
+        for fn in ("mpstat.csv", "nvsmi_trace.csv", "netstat.csv", "cputrace.csv", "performance.csv", "misc.txt"):
+            shutil.copy(logdir + fn, os.path.join(out, fn))
+        meta = {"make": mk, "cfg": ov,
+                "features": [[str(n), (None if v != v else float(v))] for n, v in zip(feats['name'], feats['value'])]}
+        with open(os.path.join(out, "case.json"), "w") as f:
+            json.dump(meta, f, indent=1, sort_keys=True)
+        print(name, sorted(os.listdir(out)), meta["features"])
+        shutil.rmtree(work, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

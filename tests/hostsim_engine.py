@@ -117,6 +117,44 @@ class HostSimEngine:
             out, _, n = self._run(kind, 2, stride, self._fmask(kind, stride), kws[filt])
         return out[2:], n
 
+    # ---- side tables: numpy stand-in for the device window reduction (test infrastructure only)
+    def upload(self, kind, text, data_off=0):
+        self.src[kind] = (bytes(text)[data_off:], None)
+
+    def parse(self, kind, params):
+        return self.src[kind][0].count(b"\n")
+
+    def window_reduce(self, ends, delta):
+        import io
+        import types
+        import pandas as pd
+        cols = ["timestamp", "event", "duration", "deviceId", "copyKind", "payload", "bandwidth", "pkt_src",
+                "pkt_dst", "pid", "tid", "name", "category"]
+        df = {k: (pd.read_csv(io.BytesIO(self.src[k][0]), names=cols) if self.src[k][0] else pd.DataFrame([], columns=cols))
+              for k in (3, 4, 5)}
+        out = []
+        for t in ends:
+            wb, we = t - delta, t
+            mp = df[3][(df[3].timestamp > wb) & (df[3].timestamp <= we)]
+            nv = df[4][(df[4].timestamp > wb) & (df[4].timestamp <= we) & (df[4].event == 0)]
+            ns = df[5][(df[5].timestamp > wb) & (df[5].timestamp <= we)]
+            r = [[int(x) for x in nm.split(':')[1].split('|')[1:6]] for nm in mp.name]
+            w = types.SimpleNamespace()
+            w.mp_count = len(mp)
+            for i, nm in enumerate(('usr', 'sys', 'idl', 'iow')):
+                setattr(w, nm + '_max', max([x[i] for x in r]) if r else 0)
+            w.usr_sum = sum(x[0] for x in r); w.sys_sum = sum(x[1] for x in r); w.irq_sum = sum(x[4] for x in r)
+            cpu = [x[0] + x[1] + x[4] for x in r]
+            w.cpu_max = max([0] + cpu); w.cpu_min = min([100] + cpu)
+            w.nv_count = len(nv); w.nv_max = float(nv.duration.max()) if len(nv) else 0.0
+            w.nv_min = float(nv.duration.min()) if len(nv) else 0.0
+            w.nv_sum = int(nv.duration.sum()); w.nv_ndev = len(set(nv.deviceId))
+            tx, rx = ns[ns.event == 0], ns[ns.event == 1]
+            w.tx_count, w.rx_count = len(tx), len(rx)
+            w.tx_sum, w.rx_sum = float(tx.bandwidth.sum()), float(rx.bandwidth.sum())
+            out.append(w)
+        return out, len(set(df[4].deviceId))
+
     def viz_mangled(self, stride):
         text, _ = self.src[0]
         names = set()

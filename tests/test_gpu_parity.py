@@ -251,3 +251,72 @@ def test_async_transfers_give_identical_outputs(tmp_path):
                 assert np.array_equal(o.array[:len(w)], w)
     finally:
         eng.close()
+
+
+def _side_csvs(logdir, seed, n_samples, n_cores, n_gpus, rate=10):
+    """Side CSVs in the format the reference's preprocess writes (see tests/golden/side_small)."""
+    import random
+    rng = random.Random(seed)
+    hdr = "timestamp,event,duration,deviceId,copyKind,payload,bandwidth,pkt_src,pkt_dst,pid,tid,name,category\n"
+    dt = 1.0 / rate
+    with open(logdir + "mpstat.csv", "w") as f:
+        f.write(hdr)
+        for s in range(n_samples):
+            for c in range(n_cores):
+                r = [rng.randint(0, 60), rng.randint(0, 25), rng.randint(0, 99), rng.randint(0, 9), rng.randint(0, 3)]
+                f.write("%.6f,-1,%.6f,%.6f,-1,-1,-1,-1,-1,-1,-1,mpstat_core%d (usr|sys|idl|iow|irq): |%3d|%3d|%3d|%3d|%3d|,0\n"
+                        % (0.6 + s * dt, rng.random(), c, c, *r))
+    with open(logdir + "nvsmi_trace.csv", "w") as f:
+        f.write(hdr)
+        for ev in (0, 1):
+            for s in range(n_samples):
+                for g in range(n_gpus):
+                    v = rng.randint(0, 100)
+                    f.write("%.6f,%d,%d,%d,-1,-1,-1,-1,-1,-1,-1,GPUID_%s=%d_%d,%d\n"
+                            % (0.513 + s * dt, ev, v, g, "sm" if ev == 0 else "mem", g, v, g))
+    with open(logdir + "netstat.csv", "w") as f:
+        f.write(hdr)
+        for ev in (0, 1):
+            for s in range(n_samples):
+                bw = rng.random() * 1e7
+                f.write("%.6f,%d,-1,-1,-1,-1,%.6f,-1,-1,-1,-1,network_bandwidth_%s(bytes):%d,0\n"
+                        % (0.531 + s * dt * (1 + 0.3 * (s % 3 == 0)), ev, bw, "tx" if ev == 0 else "rx", int(bw)))
+    with open(logdir + "cputrace.csv", "w") as f:
+        f.write(hdr + "0.750014,14.624498,0.000178,-1,-1,0,0,-1,-1,4242,4255,x,0\n")
+    with open(logdir + "misc.txt", "w") as f:
+        f.write("elapsed_time 12.5\ncores 4\nvcores 4\npid 1\n")
+
+
+@pytest.mark.parametrize("name", sorted(d for d in os.listdir(os.path.join(os.path.dirname(__file__), "golden")) if d.startswith("side_")))
+def test_concurrency_breakdown_device_matches_reference(name, tmp_path):
+    from test_side_host import run_case
+    from sofa_b200.engine import CudaEngine
+    eng = CudaEngine(0)
+    try:
+        run_case(name, tmp_path, eng)
+    finally:
+        eng.close()
+
+
+def test_concurrency_breakdown_device_matches_oracle_larger(tmp_path):
+    import pandas as pd
+    from sofa_b200.engine import CudaEngine
+    from sofa_b200 import sofa_analyze as an
+    logdir = str(tmp_path) + "/"
+    _side_csvs(logdir, seed=5, n_samples=4000, n_cores=16, n_gpus=8)
+    cfg = default_report_config(logdir)
+    cfg.is_idle_threshold = 30
+    eng = CudaEngine(0)
+    try:
+        feats = an.concurrency_breakdown(logdir, cfg, eng, [])
+    finally:
+        eng.close()
+    got_perf = open(logdir + "performance.csv", "rb").read()
+    ofeats, operf = orc.concurrency_breakdown(pd.read_csv(logdir + "mpstat.csv"), pd.read_csv(logdir + "cputrace.csv"),
+                                              pd.read_csv(logdir + "nvsmi_trace.csv"), pd.read_csv(logdir + "netstat.csv"),
+                                              is_idle_threshold=30)
+    import io
+    buf = io.StringIO()
+    operf.to_csv(buf)
+    assert got_perf == buf.getvalue().encode()
+    assert [(n, float(v)) for n, v in feats] == [(n, float(v)) for n, v in ofeats]

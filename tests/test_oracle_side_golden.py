@@ -1,0 +1,26 @@
+"""Pin the oracle's concurrency_breakdown against the unmodified reference (tests/golden/side_*)."""
+import io
+import json
+import os
+
+import pandas as pd
+import pytest
+
+from helpers import GOLDEN
+from oracle import sofa_oracle as orc
+
+SIDE = sorted(d for d in os.listdir(GOLDEN) if d.startswith("side_"))
+
+
+@pytest.mark.parametrize("name", SIDE)
+def test_oracle_concurrency_breakdown_matches_reference(name):
+    d = os.path.join(GOLDEN, name)
+    case = json.load(open(os.path.join(d, "case.json")))
+    feats, perf = orc.concurrency_breakdown(pd.read_csv(d + "/mpstat.csv"), pd.read_csv(d + "/cputrace.csv"),
+                                            pd.read_csv(d + "/nvsmi_trace.csv"), pd.read_csv(d + "/netstat.csv"),
+                                            **{k: v for k, v in case["cfg"].items()})
+    want = [tuple(x) for x in case["features"][1:]]
+    assert [(n, float(v)) for n, v in feats] == [(n, v) for n, v in want]
+    buf = io.StringIO()
+    perf.to_csv(buf)
+    assert buf.getvalue().encode() == open(d + "/performance.csv", "rb").read()
