@@ -6,7 +6,8 @@ Workload (BASELINE.json configs[2]): 100 M-event mixed synthetic trace - 60 M pe
 cpu_filters=idle,tensorflow and the default gpu_filters.  One step = one full pass:
 line index + parse of the three sources, cputrace/gputrace/nettrace CSV bodies, viz-name
 dictionary + demangle, keyword filters, every report.js series (cpu_trace, 2 cpu filters,
-net_trace, gpu_kernel_trace, 6 gpu filters) and gpu_profile/comm_profile.
+net_trace, gpu_kernel_trace, 6 gpu filters), gpu_profile/comm_profile, and the window reduction of
+concurrency_breakdown over 10 Hz mpstat/nvsmi/netstat tables (64 cores x 8 GPUs).
 
   value : events/s with the raw text already resident in HBM (device-timed, CUDA events)
   e2e   : same pass through the public engine API from PINNED HOST text, with H2D of the
@@ -37,7 +38,7 @@ CPU_FILTERS = "idle:black,tensorflow:orange"
 GPU_KWS = ["CUDA_COPY_H2D", "CUDA_COPY_D2H", "CUDA_COPY_P2P", "_fw_", "_bw_", "AllReduceKernel"]
 CPU_KWS = ["idle", "tensorflow"]
 # dram__bytes_read+write / algorithmic bytes, measured by ncu --set full (profiles/r01_summary.md)
-NCU_TRAFFIC_RATIO = {"json_write": 1.83, "csv_write": 2.72, "parse": 1.66}
+NCU_TRAFFIC_RATIO = {"json_emit": 1.86, "csv_emit": 2.71, "parse": 1.66}
 TIME_BASE = 1600000000.0
 PERF_T_OFFSET = 1600000000.25 - 4999.5
 
@@ -116,6 +117,8 @@ class Workload:
         self.host_text = {}
         self.out_bytes = {"csv": 0, "json": 0}
         self.demangled = {}
+        self.side = None
+        self.side_resident = False
 
     def generate(self):
         hl, eng = self.hl, self.eng
@@ -140,6 +143,28 @@ class Workload:
         p.update(upd)
         self.params[hl.SRC_GPU] = eng.make_params(p); self._keep.append(eng._keep)
         self.data_off[hl.SRC_GPU] = off
+
+    def make_side(self):
+        """10 Hz mpstat / nvsmi / netstat CSV tables for 64 cores x 8 GPUs over the trace's duration
+         -> pinned host buffers + the window end times of concurrency_breakdown."""
+        from sofa_b200 import synth
+        eng = self.eng
+        n_samples = max(8, int(self.n[0] * 17e-6 * 10))
+        bodies = synth.side_csv_bodies(self.seed, n_samples, 64, 8)
+        self.side = []
+        for b in bodies:
+            pb = eng.pinned(len(b))
+            pb.array[:] = memoryview(b)
+            self.side.append(pb)
+        self.side_rows = sum(b.count(b"\n") for b in bodies)
+        t_begin, t_end = 0.6, 0.6 + (n_samples - 1) * 0.1
+        ends, t = [], t_begin
+        while t < t_end:
+            t = t + 0.1
+            ends.append(t)
+        self.win_ends = ends
+        self.side_params = eng.make_params(self.hl.base_params(3, 0.0, True))
+        self._keep.append(eng._keep)
 
     def _demangle_all(self, names):
         from sofa_b200.sofa_preprocess import demangle
@@ -205,6 +230,16 @@ class Workload:
                 for i in range(len(CPU_KWS)):
                     js(kind, 1, i)
         gp = eng.gpu_profile() if analyze else None
+        if analyze and self.side is not None:                       # concurrency_breakdown, device part
+            for i, pb in enumerate(self.side):
+                if e2e:
+                    eng.upload_async(3 + i, pb.array, 0)
+                    nb["h2d"] += pb.nbytes
+                elif not self.side_resident:
+                    eng.upload(3 + i, pb.array, 0)
+                eng.parse(3 + i, self.side_params)
+            self.side_resident = True
+            eng.window_reduce(self.win_ends, 0.1)
         if e2e:
             eng.sync()
         self.out_bytes = nb
@@ -227,6 +262,7 @@ def run_ours(args):
     wl = Workload(eng, args.events, SEED + 1000 * rank)
     wl.generate()
     wl.fetch_host_text()
+    wl.make_side()
     total_events = sum(wl.n)
     text_total = sum(wl.text_bytes.values())
 
@@ -306,8 +342,7 @@ def run_ours(args):
     # algorithmic bytes per kernel kind for ONE step: text in for the ingest
     # kernels, text out for the emit kernels
     algo = {"count_lines": text_total, "parse": text_total,
-            "csv_size": out_bytes["csv"], "csv_write": out_bytes["csv"],
-            "json_size": out_bytes["json"], "json_write": out_bytes["json"]}
+            "csv_emit": out_bytes["csv"], "json_emit": out_bytes["json"]}
     dom = max(kstats.items(), key=lambda kv: kv[1][1])
     dname, (dl, dms) = dom
     dbytes = algo.get(dname, 0)

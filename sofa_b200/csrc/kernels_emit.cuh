@@ -1,10 +1,10 @@
 // Emit: columns (+ name spans in the resident text) -> CSV rows / report.js records,
 // keyword filters, dtype flags, viz-name dictionary.
 //
-// Text emission is a size pass, a scan of per-block byte totals and a write pass.  The
-// write pass formats each row into a shared-memory image of the block's output range
-// (same 16-byte phase as the global destination) and flushes it with 128-bit coalesced
-// stores; blocks whose range exceeds the staging buffer write straight to global memory.
+// Text emission is one kernel per output (k_emit_fused, below): digit plans + exact row length,
+// decoupled look-back for the block's byte offset, rows printed into a packed shared-memory
+// image (same 16-byte phase as the global destination), 128-bit coalesced flush; blocks whose
+// range exceeds the image write straight to global memory.
 #pragma once
 #include "kernels_ingest.cuh"
 
@@ -87,66 +87,6 @@ __device__ __forceinline__ void with_row(const SrcView& s, uint64_t row, uint64_
 }
 
 enum { FMT_CSV = 0, FMT_JSON = 1, FMT_COMM = 2 };
-
-struct EmitArgs {
-    uint64_t ncand; uint32_t stride; uint32_t fmask;
-    const uint8_t* mask; int bit;          // optional row filter (mask[cand] >> bit) & 1
-    uint32_t* rowlen;                      // len | special << 31
-    uint64_t* blockoff;                    // per block byte total -> (after scan) byte offset
-    char* out;
-    unsigned long long* err;
-    unsigned long long* count;             // selected rows
-};
-
-template <int KIND, int FMT>
-__global__ void __launch_bounds__(EMIT_TPB) k_emit_size(SrcView src, EmitArgs a) {
-    __shared__ uint32_t sm[33];
-    uint64_t c = (uint64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
-    bool sel = c < a.ncand && (a.mask == nullptr || ((a.mask[c] >> a.bit) & 1));
-    uint32_t len = 0, special = 0;
-    if (sel) {
-        uint64_t row = c * a.stride;
-        int l = 0;
-        with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
-            if constexpr (FMT == FMT_CSV) { bool sp; l = csv_row_len(v, a.fmask, ng, &sp); special = sp ? 1u : 0u; }
-            else l = json_row_len(v, a.fmask, ng);
-        });
-        if (l < 0) { report_error(a.err, row, l == -2 ? E_UTF8 : E_FORMAT); l = 0; }
-        len = (uint32_t)l;
-    }
-    if (c < a.ncand) a.rowlen[c] = len | (special << 31);
-    uint32_t total, cnt_total;
-    block_excl_scan(len, &total, sm);
-    block_excl_scan(sel ? 1u : 0u, &cnt_total, sm);
-    if (threadIdx.x == 0) {
-        a.blockoff[blockIdx.x] = total;
-        if (cnt_total) atomicAdd(a.count, (unsigned long long)cnt_total);
-    }
-}
-
-template <int KIND, int FMT>
-__global__ void __launch_bounds__(EMIT_TPB) k_emit_write(SrcView src, EmitArgs a) {
-    __shared__ __align__(16) unsigned char stage[EMIT_STAGE_BYTES + 32];
-    __shared__ uint32_t sm[33];
-    uint64_t c = (uint64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
-    uint32_t rl = c < a.ncand ? a.rowlen[c] : 0;
-    uint32_t len = rl & 0x7fffffffu;
-    bool special = (rl >> 31) != 0;
-    uint32_t total;
-    uint32_t ex = block_excl_scan(len, &total, sm);
-    uint64_t tile_off = a.blockoff[blockIdx.x];
-    bool staged = total <= EMIT_STAGE_BYTES;
-    if (len) {
-        char* dst = staged ? reinterpret_cast<char*>(stage) + (tile_off & 15) + ex : a.out + tile_off + ex;
-        uint64_t row = c * a.stride;
-        with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
-            if constexpr (FMT == FMT_CSV) csv_row_write(v, a.fmask, ng, special, dst);
-            else json_row_write(v, a.fmask, ng, dst);
-        });
-    }
-    __syncthreads();
-    if (staged && total) flush_staged(stage, a.out, tile_off, total);
-}
 
 // ---------------------------------------------------------------------------- dtype flags
 template <int KIND>

@@ -20,11 +20,11 @@ using namespace sofa;
 static thread_local std::string g_last_error;
 
 enum {
-    K_COUNT = 0, K_SCAN, K_PARSE, K_FLAGS, K_CSV_SIZE, K_CSV_WRITE, K_JSON_SIZE, K_JSON_WRITE, K_FILTER,
+    K_COUNT = 0, K_SCAN, K_PARSE, K_FLAGS, K_CSV_WRITE, K_JSON_WRITE, K_FILTER,
     K_VIZ, K_ANALYZE, K_SORT, K_SYNTH, K_NKINDS
 };
 static const char* KERNEL_NAMES[K_NKINDS] = {
-    "count_lines", "scan", "parse", "row_flags", "csv_size", "csv_write", "json_size", "json_write", "filter",
+    "count_lines", "scan", "parse", "row_flags", "csv_emit", "json_emit", "filter",
     "viz_dict", "analyze", "sort", "synth"};
 
 struct DevBuf {
@@ -70,8 +70,8 @@ struct sofa_ctx {
     DevBuf out_alt[2];
     cudaEvent_t out_ev[2] = {nullptr, nullptr}, out_alt_ev[2] = {nullptr, nullptr};
     bool out_busy[2] = {false, false}, out_alt_busy[2] = {false, false};
-    cudaEvent_t up_ev[3] = {nullptr, nullptr, nullptr};
-    bool up_pending[3] = {false, false, false};
+    cudaEvent_t up_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool up_pending[6] = {false, false, false, false, false, false};
     cudaEvent_t fetch_ev[16]; bool fetch_used[16]; int fetch_next = 0;
     DevBuf arena; uint64_t arena_cur = 0; bool arena_on = false;
     // small host<->device traffic goes through mapped pinned memory + a copy kernel, never the
@@ -319,7 +319,7 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->out_ev[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_alt_ev[i], cudaEventDisableTiming)); }
-    for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 6; i++) CK(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 16; i++) { CK(cudaEventCreateWithFlags(&c->fetch_ev[i], cudaEventDisableTiming)); c->fetch_used[i] = false; }
     CK(cudaHostAlloc((void**)&c->stage_h, c->stage_cap, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&c->stage_d, c->stage_h, 0));
@@ -350,7 +350,7 @@ int sofa_b200_destroy(sofa_ctx* c) {
     if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
     if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
     for (int i = 0; i < 2; i++) { if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); if (c->out_alt_ev[i]) cudaEventDestroy(c->out_alt_ev[i]); c->out_alt[i].release(); }
-    for (int i = 0; i < 3; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
+    for (int i = 0; i < 6; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
     for (int i = 0; i < 16; i++) cudaEventDestroy(c->fetch_ev[i]);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& e : c->pool) cudaEventDestroy(e);
@@ -512,51 +512,6 @@ static int fmask_for(sofa_ctx* c, int k, uint32_t stride, uint32_t* fmask) {
 
 }  // extern "C"
 
-template <int FMT>
-static int emit_common(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, int bit, uint32_t fmask,
-                       int outslot, uint64_t* nbytes, uint64_t* nrec) {
-    Source& s = c->src[k];
-    uint64_t ncand = cdiv(s.n_rows, stride);
-    c->out_n[outslot] = 0;
-    if (nbytes) *nbytes = 0;
-    if (nrec) *nrec = 0;
-    if (flip_output(c, outslot)) return SOFA_ERR_CUDA;
-    if (ncand == 0) return 0;
-    uint64_t nblocks = cdiv(ncand, EMIT_TPB);
-    ENSURE(c->rowlen, ncand * 4);
-    ENSURE(c->blockoff, (nblocks + 2) * 8);
-    if (reset_err(c)) return SOFA_ERR_CUDA;
-    SrcView v = make_view(c, k, true);
-    EmitArgs a;
-    a.ncand = ncand; a.stride = stride; a.fmask = fmask; a.mask = mask; a.bit = bit;
-    a.rowlen = c->rowlen.as<uint32_t>(); a.blockoff = c->blockoff.as<uint64_t>(); a.out = nullptr;
-    a.err = c->d_err; a.count = c->d_err + 1;
-    int ks = FMT == FMT_CSV ? K_CSV_SIZE : K_JSON_SIZE, kw = FMT == FMT_CSV ? K_CSV_WRITE : K_JSON_WRITE;
-    unsigned g = (unsigned)nblocks;
-    if (k == SRC_PERF) LAUNCH(c, ks, (k_emit_size<SRC_PERF, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
-    else if (k == SRC_GPU) LAUNCH(c, ks, (k_emit_size<SRC_GPU, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
-    else LAUNCH(c, ks, (k_emit_size<SRC_NET, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
-    LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(c->blockoff.as<uint64_t>(), nblocks)));
-    uint64_t total = 0; unsigned long long cnt = 0;
-    CK_S(small_d2h(c, &total, c->blockoff.as<uint64_t>() + nblocks, 8));
-    CK_S(small_d2h(c, &cnt, c->d_err + 1, 8));
-    int r = check_kernel_error(c, FMT == FMT_CSV ? "emit_csv" : "emit_json");
-    if (r) return r;
-    { int ra = out_alloc(c, outslot, total, &a.out); if (ra) return ra; }
-    if (total) {
-        if (k == SRC_PERF) LAUNCH(c, kw, (k_emit_write<SRC_PERF, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
-        else if (k == SRC_GPU) LAUNCH(c, kw, (k_emit_write<SRC_GPU, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
-        else LAUNCH(c, kw, (k_emit_write<SRC_NET, FMT><<<g, EMIT_TPB, 0, c->stream>>>(v, a)));
-        CK_S(stream_sync(c));
-        CK(cudaGetLastError());
-    }
-    out_commit(c, outslot, total);
-    if (nbytes) *nbytes = total;
-    if (nrec) *nrec = cnt;
-    return 0;
-}
-
-
 constexpr uint32_t FUSED_SLOT_BYTES = 64 * 1024;
 
 template <int FMT>
@@ -635,12 +590,6 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
     FAIL(SOFA_ERR_CAP, "emit: output capacity estimate failed repeatedly");
 }
 
-static bool use_fused() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SOFA_B200_EMIT"); v = (e && strcmp(e, "twopass") == 0) ? 0 : 1; }
-    return v == 1;
-}
-
 extern "C" {
 
 int sofa_b200_emit_csv(sofa_ctx* c, int k, uint32_t stride, uint64_t* nbytes) {
@@ -648,8 +597,7 @@ int sofa_b200_emit_csv(sofa_ctx* c, int k, uint32_t stride, uint64_t* nbytes) {
     if (stride == 0) FAIL(SOFA_ERR_ARG, "emit_csv: stride must be >= 1");
     uint32_t fmask = 0;
     r = fmask_for(c, k, stride, &fmask); if (r) return r;
-    if (use_fused()) return emit_fused<FMT_CSV>(c, k, stride, nullptr, 0, fmask, 0, cdiv(c->src[k].n_rows, stride), nbytes, nullptr);
-    return emit_common<FMT_CSV>(c, k, stride, nullptr, 0, fmask, 0, nbytes, nullptr);
+    return emit_fused<FMT_CSV>(c, k, stride, nullptr, 0, fmask, 0, cdiv(c->src[k].n_rows, stride), nbytes, nullptr);
 }
 
 int sofa_b200_emit_comm_csv(sofa_ctx* c, uint64_t* nbytes) {
@@ -673,11 +621,8 @@ int sofa_b200_emit_json(sofa_ctx* c, int k, uint32_t stride, int32_t filter_idx,
     uint32_t fmask = 0;
     r = fmask_for(c, k, stride, &fmask); if (r) return r;
     uint64_t nb = 0, nr = 0;
-    if (use_fused()) {
-        uint64_t hint = filter_idx >= 0 ? s.filter_counts[filter_idx] : cdiv(s.n_rows, stride);
-        r = emit_fused<FMT_JSON>(c, k, stride, mask, filter_idx >= 0 ? filter_idx : 0, fmask, 1, hint, &nb, &nr);
-    } else
-        r = emit_common<FMT_JSON>(c, k, stride, mask, filter_idx >= 0 ? filter_idx : 0, fmask, 1, &nb, &nr);
+    uint64_t hint = filter_idx >= 0 ? s.filter_counts[filter_idx] : cdiv(s.n_rows, stride);
+    r = emit_fused<FMT_JSON>(c, k, stride, mask, filter_idx >= 0 ? filter_idx : 0, fmask, 1, hint, &nb, &nr);
     if (r) return r;
     if (nbytes) *nbytes = nb >= 2 ? nb - 2 : 0;       // the leading ", " is dropped by fetch
     if (nrec) *nrec = nr;
@@ -700,7 +645,7 @@ int sofa_b200_fetch(sofa_ctx* c, int which, void* host_out, uint64_t cap) {
 }
 
 int sofa_b200_upload_async(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
-    if (!c || k < 0 || k > 2 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
+    if (!c || k < 0 || k > 5 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
     if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload_async: data_off beyond the text");
     CK(cudaSetDevice(c->device));
     Source& s = c->src[k];

@@ -335,3 +335,26 @@ def write_side_raw(logdir, seed, n_samples=60, n_cores=4, n_gpus=2, rate_hz=10):
             tx += r % 1000000
             rx += (r >> 20) % 3000000
             f.write("%.6f,%d,%d\n" % (t, tx, rx))
+
+
+def side_csv_bodies(seed, n_samples, n_cores, n_gpus, rate_hz=10):
+    """Header-less bodies of mpstat.csv, nvsmi_trace.csv, netstat.csv in the format the reference's
+    preprocess writes them (tests/golden/side_small), for concurrency_breakdown at scale."""
+    dt = 1.0 / rate_hz
+    mp, nv, ns = [], [], []
+    for s_ in range(n_samples):
+        t = 0.6 + s_ * dt
+        for c in range(n_cores):
+            r = rnd(seed, 8, s_ * 256 + c, 0)
+            mp.append("%.6f,-1,%.6f,%.6f,-1,-1,-1,-1,-1,-1,-1,mpstat_core%d (usr|sys|idl|iow|irq): |%3d|%3d|%3d|%3d|%3d|,0\n"
+                      % (t, ((r >> 40) % 1000000) / 1e6, c, c, r % 61, (r >> 6) % 26, (r >> 12) % 100, (r >> 20) % 10, (r >> 24) % 4))
+    for ev, tag in ((0, "sm"), (1, "mem")):
+        for s_ in range(n_samples):
+            for g in range(n_gpus):
+                v = rnd(seed, 9, (s_ * 16 + g) * 2 + ev, 0) % 101
+                nv.append("%.6f,%d,%d,%d,-1,-1,-1,-1,-1,-1,-1,GPUID_%s=%d_%d,%d\n" % (0.513 + s_ * dt, ev, v, g, tag, g, v, g))
+    for ev, tag in ((0, "tx"), (1, "rx")):
+        for s_ in range(n_samples):
+            bw = (rnd(seed, 10, s_ * 2 + ev, 0) % 10**13) / 1e6
+            ns.append("%.6f,%d,-1,-1,-1,-1,%.6f,-1,-1,-1,-1,network_bandwidth_%s(bytes):%d,0\n" % (0.531 + s_ * dt, ev, bw, tag, int(bw)))
+    return "".join(mp).encode(), "".join(nv).encode(), "".join(ns).encode()

@@ -12,6 +12,7 @@ eng = CudaEngine(0)
 wl = bench.Workload(eng, events, bench.SEED)
 wl.generate()
 wl.fetch_host_text()
+wl.make_side()
 kinds = [int(x) for x in os.environ.get('SOFA_KINDS', '0,1,2').split(',')]
 analyze = os.environ.get('SOFA_ANALYZE', '1') == '1' and 1 in kinds
 for _ in range(steps):
