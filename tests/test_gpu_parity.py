@@ -320,3 +320,59 @@ def test_concurrency_breakdown_device_matches_oracle_larger(tmp_path):
     operf.to_csv(buf)
     assert got_perf == buf.getvalue().encode()
     assert [(n, float(v)) for n, v in feats] == [(n, float(v)) for n, v in ofeats]
+
+
+def test_tile_boundaries_with_ragged_line_lengths(tmp_path):
+    """Lines from 20 bytes to ~6 KB (long kernel / symbol names) so that tile edges, the overlap
+    window, unstaged emit blocks and multi-word spans are all exercised; byte-compare with the oracle."""
+    import random
+    rng = random.Random(99)
+    a = os.path.join(str(tmp_path), "gpu") + "/"
+    b = os.path.join(str(tmp_path), "cpu") + "/"
+    for d in (a, b):
+        synth.write_side_files(d)
+    hdr = synth.gpu_header()
+    glines, plines = [], []
+    for i in range(6000):
+        base = synth.gpu_line(7, i)
+        if i % 3 == 0 and '"[' not in base:
+            L = rng.choice([1, 7, 8, 9, 63, 64, 65, 500, 3000, 6000])
+            nm = "".join(rng.choice("abcdefgh_<>():,") for _ in range(L))
+            base = base[:base.rindex(',"') + 2] + nm + '"\n'
+        glines.append(base)
+        pl = synth.perf_line(7, i)
+        if i % 5 == 0:
+            L = rng.choice([1, 15, 16, 17, 200, 2500])
+            tok = pl.split()
+            tok[5] = "S" * L + "+0x1f"
+            pl = " ".join(tok) + "\n"
+        plines.append(pl)
+    for d in (a, b):
+        with open(d + "gputrace.tmp", "w") as f:
+            f.write(hdr + "".join(glines))
+        open(d + "gputrace1.nvvp", "w").close()
+        with open(d + "perf.script", "w") as f:
+            f.write("".join(plines))
+    cfg = default_report_config(a)
+    cfg.plot_ratio = 3
+    sofa_preprocess(cfg)
+    orc.preprocess(orc.OracleConfig(b, plot_ratio=3, nprocs=1), demangle=demangle)
+    for fn in ("cputrace.csv", "gputrace.csv", "report.js"):
+        with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
+            _diff("ragged", fn, f.read(), g.read())
+
+
+def test_line_longer_than_overlap_window_fails_loudly(tmp_path):
+    from sofa_b200._lib import SofaB200Error
+    logdir = os.path.join(str(tmp_path), "l") + "/"
+    synth.make_logdir(logdir, seed=4, n_perf=3000)
+    with open(logdir + "perf.script") as f:
+        lines = f.readlines()
+    tok = lines[1500].split()
+    tok[5] = "S" * 20000 + "+0x1"
+    lines[1500] = " ".join(tok) + "\n"
+    with open(logdir + "perf.script", "w") as f:
+        f.write("".join(lines))
+    with pytest.raises(SofaB200Error) as ei:
+        sofa_preprocess(default_report_config(logdir))
+    assert ei.value.row_code in (6,) and ei.value.row == 1500
