@@ -20,6 +20,7 @@ Multi-GPU: one process per GPU (torchrun); every rank processes its own 100 M-ev
 `--impl reference` times the reference-path CPU port (oracle/) on the host cores.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -145,12 +146,35 @@ class Workload:
         self.data_off[hl.SRC_GPU] = off
 
     def make_side(self):
-        """10 Hz mpstat / nvsmi / netstat CSV tables for 64 cores x 8 GPUs over the trace's duration
-         -> pinned host buffers + the window end times of concurrency_breakdown."""
+        """10 Hz mpstat.txt / nvsmi_query.txt / netstat.txt for 64 cores x 8 GPUs over the trace's duration
+         in pinned host buffers.  One untimed device pass turns them into mpstat.csv /
+        nvsmi_trace.csv / netstat.csv bodies: those are what the analyze half of every step re-reads (the
+        reference's sofa_analyze reads the files sofa_preprocess wrote), plus the window end times of
+        concurrency_breakdown."""
+        import tempfile
+        import shutil
         from sofa_b200 import synth
         eng = self.eng
         n_samples = max(8, int(self.n[0] * 17e-6 * 10))
-        bodies = synth.side_csv_bodies(self.seed, n_samples, 64, 8)
+        tmp = tempfile.mkdtemp(prefix="sofa_bench_side_") + "/"
+        try:
+            synth.write_side_raw(tmp, self.seed, n_samples=n_samples, n_cores=64, n_gpus=8)
+            raw = [open(tmp + fn, "rb").read() for fn in ("mpstat.txt", "nvsmi_query.txt", "netstat.txt")]
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        self.side_raw = []
+        for b in raw:
+            pb = eng.pinned(len(b))
+            pb.array[:] = memoryview(b)
+            self.side_raw.append(pb)
+        self.side_raw_off = [0, raw[1].find(b"\n") + 1, 0]
+        self.side_tz = self.hl.nvsmi_local_offset(raw[1], self.side_raw_off[1])
+        self.side_raw_lines = sum(b.count(b"\n") for b in raw)
+        bodies = []
+        for i in range(3):
+            eng.side_preprocess(6 + i, self.side_raw[i].array, TIME_BASE, False, self.side_tz, 0.0, self.side_raw_off[i])
+            parts = [eng.side_csv(6 + i, lst)[0].tobytes() for lst in ((0,) if i == 0 else (0, 1))]
+            bodies.append(b"".join(parts))
         self.side = []
         for b in bodies:
             pb = eng.pinned(len(b))
@@ -207,7 +231,35 @@ class Workload:
                 fetch(1, n)
             return nrec
 
+        def side_source(i):
+            """mpstat.txt / nvsmi_query.txt / netstat.txt -> CSV rows, aux table, report.js series"""
+            raw = 6 + i
+            if e2e:
+                eng.upload_async(raw, self.side_raw[i].array, self.side_raw_off[i])
+                nb["h2d"] += self.side_raw[i].nbytes
+            eng.side_preprocess(raw, None, TIME_BASE, False, self.side_tz, 0.0)      # text resident (make_side / upload above)
+            lists = (0,) if i == 0 else (0, 1)
+            n64 = ctypes.c_uint64()
+            if i != 1:
+                eng._check(eng.lib.sofa_b200_side_emit_aux(eng.ctx, raw, ctypes.byref(n64), None))
+                nb["csv"] += n64.value
+                if e2e and n64.value:
+                    fetch(0, n64.value)
+            for lst in lists:
+                eng._check(eng.lib.sofa_b200_side_emit_csv(eng.ctx, raw, lst, ctypes.byref(n64), None))
+                nb["csv"] += n64.value
+                if e2e and n64.value:
+                    fetch(0, n64.value)
+            for lst in lists:
+                eng._check(eng.lib.sofa_b200_side_emit_json(eng.ctx, raw, lst, ctypes.byref(n64), None))
+                nb["json"] += n64.value
+                if e2e and n64.value:
+                    fetch(1, n64.value)
+
         order = [k for k in (hl.SRC_NET, hl.SRC_GPU, hl.SRC_PERF) if kinds is None or k in kinds]
+        if kinds is None and self.side is not None:
+            for i in range(3):
+                side_source(i)
         if e2e:
             for kind in order:                                      # all uploads queued up front
                 eng.upload_async(kind, self.host_text[kind].array, self.data_off[kind])
@@ -386,6 +438,7 @@ def write_sample_logdir(logdir, n_events, seed, wl=None):
     from sofa_b200 import synth
     n_perf, n_gpu, n_net = split_events(n_events)
     synth.write_side_files(logdir)
+    synth.write_side_raw(logdir, seed, n_samples=max(8, int(n_perf * 17e-6 * 10)), n_cores=64, n_gpus=8)   # same 10 Hz side files, pro rata
     if wl is not None:                      # slice the device-generated text at a line boundary
         import numpy as np
         for kind, fn, n in ((0, "perf.script", n_perf), (1, "gputrace.tmp", n_gpu), (2, "net.tmp", n_net)):
@@ -409,7 +462,7 @@ def write_sample_logdir(logdir, n_events, seed, wl=None):
 
 
 def oracle_pass(logdir, nprocs):
-    """preprocess + gpu_profile of the CPU oracle (reference-path port) on `logdir`."""
+    """preprocess (trace + side files) + gpu_profile + concurrency_breakdown of the CPU oracle (reference-path port)."""
     import pandas as pd
     from oracle import sofa_oracle as orc
     from sofa_b200.sofa_preprocess import demangle
@@ -417,6 +470,9 @@ def oracle_pass(logdir, nprocs):
     orc.preprocess(cfg, demangle=demangle)
     df = pd.read_csv(logdir + "/gputrace.csv")
     orc.gpu_profile(df, logdir)
+    if os.path.isfile(logdir + "/mpstat.csv"):
+        orc.concurrency_breakdown(pd.read_csv(logdir + "/mpstat.csv"), pd.read_csv(logdir + "/cputrace.csv"),
+                                  pd.read_csv(logdir + "/nvsmi_trace.csv"), pd.read_csv(logdir + "/netstat.csv"))
 
 
 def cpu_baseline_sample(args, wl):

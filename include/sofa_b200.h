@@ -30,7 +30,9 @@ extern "C" {
 
 enum { SOFA_SRC_PERF = 0, SOFA_SRC_GPU = 1, SOFA_SRC_NET = 2,
        /* 13-column trace CSV bodies read by concurrency_breakdown (upload + parse like a source) */
-       SOFA_SRC_MPSTAT_CSV = 3, SOFA_SRC_NVSMI_CSV = 4, SOFA_SRC_NETSTAT_CSV = 5 };
+       SOFA_SRC_MPSTAT_CSV = 3, SOFA_SRC_NVSMI_CSV = 4, SOFA_SRC_NETSTAT_CSV = 5,
+       /* recorder side files as written by `sofa record` (upload, then sofa_b200_side_preprocess) */
+       SOFA_RAW_MPSTAT = 6, SOFA_RAW_NVSMI_QUERY = 7, SOFA_RAW_NETSTAT = 8 };
 
 typedef struct sofa_ctx sofa_ctx;
 
@@ -171,6 +173,28 @@ typedef struct {
 int sofa_b200_window_reduce(sofa_ctx*, const double* ends, uint32_t n_windows, double delta, sofa_window_t* out,
                             uint32_t* num_gpus);
 
+/* Recorder side files -> rows of mpstat.csv + usr_sys.csv (sofa_preprocess.py:482-546),
+ * nvsmi_trace.csv (:1013-1084) and netstat.csv + netbandwidth.csv (:1235-1337), and the records
+ * of their report.js series (mpstat_usr; nvsmi_sm / nvsmi_mem; tx_bandwidth / rx_bandwidth).
+ * Upload the file with sofa_b200_upload (nvsmi_query.txt: data_off = after its first line, which
+ * the reference skips), then call sofa_b200_side_preprocess once and the emitters as needed.
+ *   n_lines : lines parsed;  n_cand : candidate rows per list (mpstat: rows of mpstat[1:], some of
+ *   which are dropped or go to usr_sys.csv; nvsmi: one sm + one mem row per line; netstat: one tx +
+ *   one rx row per line after the first);  no_data : nvidia-smi reported a failure (:1017-1021).
+ * list: 0 = sm / tx (and mpstat), 1 = mem / rx.  CSV and aux bodies go to output buffer 0, JSON
+ * records to output buffer 1 (fetch as usual).  aux = usr_sys.csv / netbandwidth.csv body. */
+typedef struct {
+    double time_base;            /* cfg.time_base */
+    int32_t absolute_timestamp;  /* cfg.absolute_timestamp */
+    int32_t reserved;
+    int64_t local_utc_offset;    /* seconds the host's local zone is ahead of UTC (naive datetime.timestamp()) */
+    double nvsmi_tz_add;         /* cfg.nvsmi_time_zone * 3600 */
+} sofa_side_params_t;
+int sofa_b200_side_preprocess(sofa_ctx*, int raw_src, const sofa_side_params_t*, uint64_t* n_lines, uint64_t* n_cand,
+                              int32_t* no_data);
+int sofa_b200_side_emit_csv(sofa_ctx*, int raw_src, int list, uint64_t* nbytes, uint64_t* n_rows);
+int sofa_b200_side_emit_json(sofa_ctx*, int raw_src, int list, uint64_t* nbytes, uint64_t* n_records);
+int sofa_b200_side_emit_aux(sofa_ctx*, int raw_src, uint64_t* nbytes, uint64_t* n_rows);
 /* CUDA-event stopwatch on the ctx stream: mark(0) ... mark(1); elapsed = ms between them */
 int sofa_b200_mark(sofa_ctx*, int which);
 int sofa_b200_elapsed_ms(sofa_ctx*, double* ms);

@@ -213,6 +213,99 @@ def write_report_js(series, path):
         f.write(" ]")
 
 
+# --------------------------------------------------------------------------- N1: recorder side files
+def _to_csv_list(rows, path, mode):
+    """list_to_csv_and_traces (sofa_preprocess.py:89-102) on an already sliced list."""
+    if len(rows) == 0:
+        return []
+    df = frame(rows)
+    df.to_csv(path, mode=mode, header=(mode == 'w'), index=False, float_format='%.6f')
+    return df
+
+
+def preprocess_mpstat(logdir, absolute_timestamp, time_base):
+    """mpstat.txt -> usr_sys.csv + mpstat.csv.  sofa_preprocess.py:482-546."""
+    mpstat = np.genfromtxt(logdir + 'mpstat.txt', delimiter=',', invalid_raise=False)      # :484
+    mpstat = mpstat[1:]                                                                    # header row (all nan)
+    n_cores = int(mpstat[:, 1].max() + 1)                                                  # :489
+    stride = n_cores + 1
+    rows, usr_sys = [], []
+    for i in range(len(mpstat)):
+        if i <= stride:                                                                    # :495
+            continue
+        core = mpstat[i, 1]
+        d = mpstat[i, :] - mpstat[i - stride, :]
+        total = d[2] + d[4] + d[5] + d[6] + d[7]
+        if total == 0:
+            continue
+        usr = d[2] * 100 / float(total)
+        sys_ = d[4] * 100 / float(total)
+        idl = d[5] * 100 / float(total)
+        iow = d[6] * 100 / float(total)
+        irq = d[7] * 100 / float(total)
+        cpu_time = (total - d[5]) * 0.01
+        t_begin = mpstat[i, 0]
+        if not absolute_timestamp:
+            t_begin = t_begin - time_base
+        if mpstat[i, 1] != -1:
+            name = 'mpstat_core%d (usr|sys|idl|iow|irq): |%3d|%3d|%3d|%3d|%3d|' % (core, usr, sys_, idl, iow, irq)
+            rows.append([t_begin, -1, cpu_time, core, -1, -1, -1, -1, -1, -1, -1, name, 0])
+        else:
+            usr_sys.append((t_begin, usr, sys_))
+    pd.DataFrame(usr_sys, columns=['time', 'usr', 'sys']).to_csv(logdir + 'usr_sys.csv', index=False)   # :544-545
+    return _to_csv_list(rows, logdir + 'mpstat.csv', 'w')
+
+
+def preprocess_nvsmi_query(logdir, absolute_timestamp, time_base, nvsmi_time_zone=0):
+    """nvsmi_query.txt -> nvsmi_trace.csv (sm rows, then mem rows).  sofa_preprocess.py:1013-1084."""
+    import datetime
+    with open(logdir + 'nvsmi_query.txt') as f:
+        next(f)
+        lines = f.readlines()
+    for line in lines:
+        if line.find('failed') != -1 or line.find('Failed') != -1:
+            return [], []
+    sm, mem = [], []
+    for line in lines:
+        fields = line.split(',')
+        nv_time = datetime.datetime.strptime(fields[0], '%Y/%m/%d %H:%M:%S.%f').timestamp() + nvsmi_time_zone * 3600
+        gid, v_sm, v_mem = int(fields[2]), int(fields[3][:-2]), int(fields[4][:-2])
+        t_begin = nv_time if absolute_timestamp else nv_time - time_base
+        sm.append([t_begin, 0, v_sm, gid, -1, -1, -1, -1, -1, -1, -1, "GPUID_sm=%d_%d" % (gid, v_sm), gid])
+        mem.append([t_begin, 1, v_mem, gid, -1, -1, -1, -1, -1, -1, -1, "GPUID_mem=%d_%d" % (gid, v_mem), gid])
+    if not sm:
+        return [], []
+    return _to_csv_list(sm, logdir + 'nvsmi_trace.csv', 'w'), _to_csv_list(mem, logdir + 'nvsmi_trace.csv', 'a')
+
+
+def preprocess_netstat(logdir, absolute_timestamp, time_base):
+    """netstat.txt -> netbandwidth.csv + netstat.csv (tx rows, then rx rows).  sofa_preprocess.py:1235-1337."""
+    with open(logdir + 'netstat.txt') as f:
+        lines = f.readlines()
+    if not lines:
+        return [], []
+    tmp_time = float(lines[0].split(',')[0])
+    tmp_tx, tmp_rx = int(lines[0].split(',')[1]), int(lines[0].split(',')[2])
+    tx_list, rx_list, bw = [], [], []
+    for line in lines[1:]:
+        time = float(line.split(',')[0])
+        tx, rx = int(line.split(',')[1]), int(line.split(',')[2])
+        tx_bw = (tx - tmp_tx) / (time - tmp_time)
+        rx_bw = (rx - tmp_rx) / (time - tmp_time)
+        t_begin = time if absolute_timestamp else time - time_base
+        tx_list.append([t_begin, 0, -1, -1, -1, -1, tx_bw, -1, -1, -1, -1, "network_bandwidth_tx(bytes):%d" % tx_bw, 0])
+        rx_list.append([t_begin, 1, -1, -1, -1, -1, rx_bw, -1, -1, -1, -1, "network_bandwidth_rx(bytes):%d" % rx_bw, 0])
+        bw.append([t_begin, tx_bw, rx_bw])
+        tmp_time, tmp_tx, tmp_rx = time, tx, rx
+    # the reference grows this frame by pd.concat one row at a time (:1315-1316); the bytes are those of one frame
+    pd.DataFrame(bw, columns=['time', 'tx_bandwidth', 'rx_bandwidth']).to_csv(logdir + 'netbandwidth.csv', header=True, index=False)
+    tx_traces = pd.DataFrame(tx_list, columns=FIELDNAMES)
+    tx_traces.to_csv(logdir + 'netstat.csv', mode='w', header=True, index=False, float_format='%.6f')
+    rx_traces = pd.DataFrame(rx_list, columns=FIELDNAMES)
+    rx_traces.to_csv(logdir + 'netstat.csv', mode='a', header=False, index=False, float_format='%.6f')
+    return tx_traces, rx_traces
+
+
 # --------------------------------------------------------------------------- driver
 class OracleConfig:
     """The cfg attributes the hot path reads (bin/sofa:159-312 defaults)."""
@@ -232,6 +325,7 @@ class OracleConfig:
         self.cuda_api_tracing = False
         self.verbose = False
         self.nprocs = None
+        self.nvsmi_time_zone = 0
         for k, v in kw.items():
             if k == 'cpu_filters' and isinstance(v, str):
                 v = [tuple(p.split(':')) for p in v.split(',')]
@@ -291,6 +385,15 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
     filtered_cpu = []
     gpu_viz = []
     filtered_gpu = []
+
+    # ---- recorder side files  :482-546, :1013-1084, :1235-1337
+    mpstat_traces, nvsmi_sm, nvsmi_mem, tx_traces, rx_traces = [], [], [], [], []
+    if os.path.isfile(logdir + 'mpstat.txt'):
+        mpstat_traces = preprocess_mpstat(logdir, cfg.absolute_timestamp, time_base)
+    if os.path.isfile(logdir + 'nvsmi_query.txt'):
+        nvsmi_sm, nvsmi_mem = preprocess_nvsmi_query(logdir, cfg.absolute_timestamp, time_base, cfg.nvsmi_time_zone)
+    if os.path.isfile(logdir + 'netstat.txt'):
+        tx_traces, rx_traces = preprocess_netstat(logdir, cfg.absolute_timestamp, time_base)
 
     # ---- network  :1187-1232  (nettrace.csv holds the DOWN-SAMPLED rows)
     if os.path.isfile(logdir + 'sofa.pcap') and os.path.isfile(logdir + 'net.tmp'):
@@ -373,20 +476,22 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
                              ('vmstat_bo', 'VMSTAT_BO', 'DarkOrchid')):
         series.append(Series(nm, title, color, []))
     if cfg.enable_mpstat:
-        series.append(Series('mpstat_usr', 'MPSTAT_USR', 'Cyan', []))
+        series.append(Series('mpstat_usr', 'MPSTAT_USR', 'Cyan', mpstat_traces))
     if cfg.enable_diskstat:
         series.append(Series('diskstat', 'DISKSTAT', 'GreenYellow', [], y_field='bandwidth'))
     if cfg.enable_vmstat:
         for nm in ('vmstat_usr', 'vmstat_sys', 'vmstat_in', 'vmstat_cs'):
             series.append(Series(nm, nm.upper(), '', []))
-    for nm in ('strace', 'pystacks', 'nvsmi_mem', 'nvsmi_sm'):
+    for nm in ('strace', 'pystacks'):
         series.append(Series(nm, nm, '', []))
+    series.append(Series('nvsmi_mem', 'GPU_MEM_Util.', 'lightblue', nvsmi_mem))
+    series.append(Series('nvsmi_sm', 'GPU_SM_Util.', 'red', nvsmi_sm))
     if cfg.enable_encode_decode:
         series.append(Series('nvsmi_enc', '', '', []))
         series.append(Series('nvsmi_dec', '', '', []))
     series.append(Series('net_trace', 'NET', 'blue', net_traces))
-    series.append(Series('tx_bandwidth', 'tx Bandwidth', 'rgba(135,206,250,0.8)', [], y_field='bandwidth'))
-    series.append(Series('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)', [], y_field='bandwidth'))
+    series.append(Series('tx_bandwidth', 'tx Bandwidth', 'rgba(135,206,250,0.8)', tx_traces, y_field='bandwidth'))
+    series.append(Series('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)', rx_traces, y_field='bandwidth'))
     series.append(Series('gpu_kernel_trace', 'GPU kernel', 'rgba(0,180,0,0.8)', gpu_viz))
     for kw, color, grp in filtered_gpu:
         series.append(Series(kw, '[keyword]' + kw, color, grp.copy()))

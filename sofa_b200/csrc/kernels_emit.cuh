@@ -7,12 +7,18 @@
 // range exceeds the image write straight to global memory.
 #pragma once
 #include "kernels_ingest.cuh"
+#include "kernels_side.cuh"
 
 namespace sofa {
 
 struct DictView { int n; const uint64_t* hash; const uint64_t* off; const char* blob; };
 
+// rows derived from a recorder side file: candidate c + base addresses row (c + base) % n_half of
+// list (c + base) / n_half (nvsmi: sm, mem; netstat: tx, rx; mpstat: one list)
+struct SideView { int table; uint64_t n_half, base; SideOutCols o; };
+
 struct SrcView {
+    SideView side;
     const char* text;
     uint64_t n_rows;
     AllCols c;
@@ -78,6 +84,12 @@ __device__ __forceinline__ void with_row(const SrcView& s, uint64_t row, uint64_
         RowVals v = vals_gpu(r, s.n_cudaproc);
         GpuName<const char*> ng{line, r, true, s.api_mode != 0};
         f(v, ng);
+    } else if constexpr (KIND == SRC_SIDEOUT) {
+        const uint64_t cc = cand + s.side.base;
+        const int half = cc >= s.side.n_half ? 1 : 0;
+        SideName ng{s.side.table, half, load_sideout(s.side.o, half ? cc - s.side.n_half : cc)};
+        RowVals v = vals_side(s.side.table, half, ng.r);
+        f(v, ng);
     } else {
         NetRow r = load_net(s, row);
         RowVals v = vals_net(r);
@@ -86,7 +98,7 @@ __device__ __forceinline__ void with_row(const SrcView& s, uint64_t row, uint64_
     }
 }
 
-enum { FMT_CSV = 0, FMT_JSON = 1, FMT_COMM = 2 };
+enum { FMT_CSV = 0, FMT_JSON = 1, FMT_COMM = 2, FMT_AUX = 3 };     // AUX: usr_sys.csv / netbandwidth.csv rows
 
 // ---------------------------------------------------------------------------- dtype flags
 template <int KIND>
@@ -267,6 +279,7 @@ __global__ void __launch_bounds__(256) k_mask_write(const uint8_t* __restrict__ 
 template <int FMT> struct RowPlanOf { typedef CsvRowPlan type; };
 template <> struct RowPlanOf<FMT_JSON> { typedef JsonRowPlan type; };
 template <> struct RowPlanOf<FMT_COMM> { typedef CommRowPlan type; };
+template <> struct RowPlanOf<FMT_AUX> { typedef AuxRowPlan type; };
 
 template <int KIND, int FMT>
 __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs a) {
@@ -289,6 +302,7 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
         with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
             if constexpr (FMT == FMT_CSV) plan = csv_row_plan(v, a.fmask, ng);
             else if constexpr (FMT == FMT_COMM) plan = comm_row_plan(c, v, a.fmask);
+            else if constexpr (FMT == FMT_AUX) plan = aux_row_plan(ng.r.ts, ng.r.f1, ng.r.f2);
             else plan = json_row_plan(v, a.fmask, ng);
         });
         if (plan.len < 0) { report_error(a.err, row, plan.len == -2 ? E_UTF8 : E_FORMAT); plan.len = 0; }
@@ -340,11 +354,13 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
                 SmemPtr dst{(uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)(base & 15) + ex};
                 if constexpr (FMT == FMT_CSV) csv_row_emit(v, a.fmask, ng, plan, dst);
                 else if constexpr (FMT == FMT_COMM) comm_row_emit(c, v, a.fmask, plan, dst);
+                else if constexpr (FMT == FMT_AUX) aux_row_emit(plan, dst);
                 else json_row_emit(v, a.fmask, ng, plan, dst);
             } else {
                 char* dst = a.out + base + ex;
                 if constexpr (FMT == FMT_CSV) csv_row_emit(v, a.fmask, ng, plan, dst);
                 else if constexpr (FMT == FMT_COMM) comm_row_emit(c, v, a.fmask, plan, dst);
+                else if constexpr (FMT == FMT_AUX) aux_row_emit(plan, dst);
                 else json_row_emit(v, a.fmask, ng, plan, dst);
             }
         });

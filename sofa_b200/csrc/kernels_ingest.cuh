@@ -9,6 +9,7 @@
 // with coalesced stores (row i of the tile -> thread i).
 #pragma once
 #include "rows.cuh"
+#include "side.cuh"
 #include "devutil.cuh"
 
 namespace sofa {
@@ -24,7 +25,11 @@ struct NetCols { double* ts; int64_t *payload, *src, *dst; uint8_t* proto; };
 
 struct SideCols { double *ts, *event, *dur, *dev, *bw; int32_t* ratios; };      // ratios: 5 per row
 
-struct AllCols { PerfCols p; GpuCols g; NetCols n; SideCols s; };
+// raw recorder side files (side.cuh): f = 9 doubles per line, i = 4 int64 per line, nf = field count
+// (-1: the line says "failed" - nvidia-smi query error)
+struct RawCols { double* f; int64_t* i; int32_t* nf; };
+
+struct AllCols { PerfCols p; GpuCols g; NetCols n; SideCols s; RawCols r; };
 
 __device__ __forceinline__ uint32_t newline_mask4(uint32_t w) {       // 0xff in every byte equal to '\n'
     return __vcmpeq4(w, 0x0a0a0a0au);
@@ -184,6 +189,16 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
                     cols.g.dev[row] = r.dev; cols.g.tid[row] = r.tid; cols.g.src[row] = r.src; cols.g.dst[row] = r.dst;
                     cols.g.kind[row] = r.kind; cols.g.bwf[row] = r.bw_is_float;
                     cols.g.line_start[row] = s0 + ls; cols.g.noff[row] = r.name_off; cols.g.nlen[row] = r.name_len;
+                }
+            } else if (KIND == SRC_RAW) {
+                RawRow r = RawRow();
+                if (cfg.side_table == RAW_MPSTAT) code = parse_raw_mpstat(line, n, &r);
+                else if (cfg.side_table == RAW_NVSMI) code = parse_raw_nvsmi(line, n, has_nl, &r);
+                else code = parse_raw_netstat(line, n, &r);
+                if (code == E_OK) {
+                    for (int q = 0; q < 9; q++) cols.r.f[row * 9 + q] = r.f[q];
+                    for (int q = 0; q < 4; q++) cols.r.i[row * 4 + q] = r.i[q];
+                    cols.r.nf[row] = r.flag ? -1 : r.nf;
                 }
             } else if (KIND == SRC_SIDE) {
                 SideRow r;

@@ -507,6 +507,81 @@ SOFA_HD JPlan repr6_plan(double x) {
     return jp_shortest_ge1e5(neg, d_div((double)(I * 1000000ull + F), 1e6));
 }
 
+// repr(x) of an arbitrary double - what DataFrame.to_csv prints without float_format
+// (usr_sys.csv, netbandwidth.csv: sofa_preprocess.py:545, 1323).  Shortest decimal that rounds
+// back to x (closest one, even digit on a tie), found by an exact 128-bit test of the rounding
+// interval.  Covers 0, integers below 1e16 and 1e-6 <= |x| < 1e16; anything else is JP_BAD.
+// kind JP_SCI here carries up to 17 digits: print with repr_emit, not json_emit.
+SOFA_HD JPlan repr_plan(double x) {
+    JPlan bad; bad.I = 0; bad.dg = 0; bad.neg = 0; bad.nd = 0; bad.ex = 0; bad.len = 0; bad.kind = JP_BAD;
+    uint64_t xb = d_bits(x);
+    bool neg = (xb >> 63) != 0;
+    int be = (int)((xb >> 52) & 0x7ff);
+    if (be == 0x7ff) return bad;
+    uint64_t frac = xb & 0xfffffffffffffull;
+    if (be == 0) return frac == 0 ? jp_fixed(neg, 0, 0, 1) : bad;          // "0.0" / "-0.0"; subnormals unsupported
+    uint64_t m = frac | (1ull << 52);
+    int e = be - 1075;
+    if (e >= 0) {
+        if (e > 1 || (m << e) >= 10000000000000000ull) return bad;         // repr switches to 1e+16 there
+        return jp_fixed(neg, m << e, 0, 1);
+    }
+    int s = -e;
+    if (s > 74) return bad;                       // |x| < 2^-22
+    uint64_t I = s >= 64 ? 0 : (m >> s);
+    uint64_t r0 = s >= 64 ? m : (m & ((1ull << s) - 1));
+    if (I >= 10000000000000000ull) return bad;
+    if (r0 == 0) return jp_fixed(neg, I, 0, 1);
+    bool even = (m & 1) == 0;
+    bool pow2 = (frac == 0);                      // lower neighbour is half as far
+    u128 one = ((u128)1) << s;
+    u128 p10 = 1;
+    for (int j = 1; j <= 22; j++) {
+        p10 *= 10;
+        u128 F = (u128)r0 * p10;                  // < 2^53 * 10^22 < 2^127
+        u128 fl = F >> s;
+        u128 rem = F - (fl << s);
+        u128 up = one - rem;
+        u128 lo_lhs = pow2 ? rem * 4 : rem * 2;
+        bool lo_ok = (lo_lhs < p10) || (even && lo_lhs == p10);
+        u128 hi_lhs = up * 2;
+        bool hi_ok = (hi_lhs < p10) || (even && hi_lhs == p10);
+        if (!(lo_ok || hi_ok)) continue;
+        u128 dg = fl;
+        bool take_hi;
+        if (lo_ok && hi_ok) take_hi = (up < rem) || (up == rem && ((uint64_t)dg & 1));
+        else take_hi = hi_ok;
+        if (take_hi) dg++;
+        if (dg == p10) return jp_fixed(neg, I + 1, 0, 1);
+        if (dg >> 63) return bad;
+        uint64_t d = (uint64_t)dg;
+        if (I > 0 || j <= 4 || d >= (uint64_t)(p10 / 10000)) {            // |x| >= 1e-4: fixed notation
+            while (d % 10 == 0) { d /= 10; j--; }                          // (cannot happen for the shortest j; kept for safety)
+            return jp_fixed(neg, I, d, j);
+        }
+        // 0 < |x| < 1e-4: "d.ddde-XX"
+        int L = ndigits_u64(d);
+        JPlan p; p.kind = JP_SCI; p.neg = neg ? 1 : 0; p.I = 0; p.dg = d; p.nd = (uint8_t)L;
+        p.ex = (uint8_t)(j - L + 1);
+        p.len = (uint8_t)(p.neg + L + (L > 1 ? 1 : 0) + 4);
+        return p;
+    }
+    return bad;
+}
+template <typename O>
+SOFA_HD int repr_emit(const JPlan& p, O out) {
+    if (p.kind != JP_SCI) return json_emit(p, out);
+    int n = 0;
+    if (p.neg) out[n++] = '-';
+    char ds[20];
+    fmt_u64_pad(p.dg, p.nd, ds);
+    out[n++] = ds[0];
+    if (p.nd > 1) { out[n++] = '.'; for (int k = 1; k < p.nd; k++) out[n++] = ds[k]; }
+    out[n++] = 'e'; out[n++] = '-';
+    out[n++] = (char)('0' + p.ex / 10); out[n++] = (char)('0' + p.ex % 10);
+    return n;
+}
+
 // ----------------------------------------------------------------------------- double-double
 struct dd { double hi, lo; };
 SOFA_HD dd two_sum(double a, double b) {

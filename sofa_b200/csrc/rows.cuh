@@ -12,7 +12,8 @@
 
 namespace sofa {
 
-enum { SRC_PERF = 0, SRC_GPU = 1, SRC_NET = 2, SRC_SIDE = 3 };      // SIDE: a 13-column trace CSV row
+enum { SRC_PERF = 0, SRC_GPU = 1, SRC_NET = 2, SRC_SIDE = 3,         // SIDE: a 13-column trace CSV row
+       SRC_RAW = 4, SRC_SIDEOUT = 5 };                               // RAW: a recorder side-file line; SIDEOUT: the rows derived from them
 
 // row-level error codes (the reference raises for all of these; we fail loudly with the row)
 enum {
@@ -44,7 +45,8 @@ struct IngestCfg {
     int n_cudaproc;                                   // pid column (:288)
     int idx_start, idx_dur, idx_size, idx_thr, idx_ctx, idx_stream, idx_name, idx_srcctx, idx_dstctx;
     int api_mode;            // nvprof --print-api-trace rows (cuda_api_trace_read, :203-247)
-    int side_table;          // SRC_SIDE: 0 mpstat.csv (name carries usr|sys|idl|iow|irq), 1 nvsmi_trace.csv, 2 netstat.csv
+    int side_table;          // SRC_SIDE: 0 mpstat.csv (name carries usr|sys|idl|iow|irq), 1 nvsmi_trace.csv, 2 netstat.csv;
+                             // SRC_RAW: 0 mpstat.txt, 1 nvsmi_query.txt, 2 netstat.txt
 };
 
 struct Tok { int a, b; };
@@ -672,7 +674,9 @@ SOFA_HD int parse_side(S s, int n, const IngestCfg& c, SideRow* r) {
 // ============================================================================ 13-column row values
 struct RowVals {
     bool valid;              // false: the all-NaN row a `[]` record becomes
-    double ts, dur;          // columns 0, 2 (always float)
+    double ts, dur;          // columns 0, 2 (float; the recorder side tables print an int duration: dur_i)
+    bool dur_is_f; int64_t dur_i;
+    int64_t cat;             // column 12 (0 for the trace sources)
     bool ev_is_f; double ev_f; int64_t ev_i;       // column 1
     int64_t dev, kind, payload;                     // 3, 4, 5
     bool bw_is_f; double bw_f; int64_t bw_i;        // 6
@@ -680,18 +684,18 @@ struct RowVals {
     // 11 = name (generator), 12 = category (always 0)
 };
 SOFA_HD RowVals vals_perf(const PerfRow& r) {
-    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.ev_is_f = true; v.ev_f = r.event; v.ev_i = 0;
+    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.dur_is_f = true; v.dur_i = 0; v.cat = 0; v.ev_is_f = true; v.ev_f = r.event; v.ev_i = 0;
     v.dev = -1; v.kind = -1; v.payload = 0; v.bw_is_f = false; v.bw_f = 0; v.bw_i = 0;
     v.src = -1; v.dst = -1; v.pid = r.pid; v.tid = r.tid; return v;
 }
 SOFA_HD RowVals vals_gpu(const GpuRow& r, int n_cudaproc) {
-    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.ev_is_f = false; v.ev_f = 0;
+    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.dur_is_f = true; v.dur_i = 0; v.cat = 0; v.ev_is_f = false; v.ev_f = 0;
     v.ev_i = r.payload * 100 + 17;                                   // :329
     v.dev = r.dev; v.kind = r.kind; v.payload = r.payload; v.bw_is_f = r.bw_is_float != 0; v.bw_f = r.bw; v.bw_i = 0;
     v.src = r.src; v.dst = r.dst; v.pid = n_cudaproc; v.tid = r.tid; return v;
 }
 SOFA_HD RowVals vals_net(const NetRow& r) {
-    RowVals v; v.valid = r.proto != 0; v.ts = r.ts;
+    RowVals v; v.valid = r.proto != 0; v.ts = r.ts; v.dur_is_f = true; v.dur_i = 0; v.cat = 0;
     v.dur = d_div((double)r.payload, 128.0e6);                       // :178
     v.ev_is_f = false; v.ev_f = 0; v.ev_i = r.payload * 100 + 17;
     v.dev = -1; v.kind = -1; v.payload = r.payload; v.bw_is_f = true; v.bw_f = 128.0e6; v.bw_i = 0;
@@ -704,7 +708,7 @@ SOFA_HD void col_value(const RowVals& v, int c, uint32_t fmask, bool* isf, doubl
     switch (c) {
         case 0: nat_f = true; nf = v.ts; break;
         case 1: nat_f = v.ev_is_f; nf = v.ev_f; ni = v.ev_i; break;
-        case 2: nat_f = true; nf = v.dur; break;
+        case 2: nat_f = v.dur_is_f; nf = v.dur; ni = v.dur_i; break;
         case 3: ni = v.dev; break;
         case 4: ni = v.kind; break;
         case 5: ni = v.payload; break;
@@ -713,7 +717,7 @@ SOFA_HD void col_value(const RowVals& v, int c, uint32_t fmask, bool* isf, doubl
         case 8: ni = v.dst; break;
         case 9: ni = v.pid; break;
         case 10: ni = v.tid; break;
-        default: ni = 0; break;        // 12: category
+        default: ni = v.cat; break;    // 12: category
     }
     bool colf = ((fmask >> c) & 1) != 0 || nat_f;
     *isf = colf;
@@ -978,11 +982,16 @@ SOFA_HD_COLD int json_name_full_write(const NG& ng, O out) {
 
 struct JsonRowPlan { int len; bool simple_name; JPlan f[4]; };     // len: -1 unformattable number, -2 invalid UTF-8
 
+// Series whose y_field is 'bandwidth' (tx_bandwidth / rx_bandwidth, sofa_preprocess.py:2051-2067):
+// the record keeps the key "duration" and renames "bandwidth" to "y".  Only the side-table name
+// generator specialises this; for the trace sources it folds to false at compile time.
+template <class NG> struct JsonYIsBw { static SOFA_HD bool get(const NG&) { return false; } };
+
 template <class NG>
 SOFA_HD JsonRowPlan json_row_plan(const RowVals& v, uint32_t fmask, const NG& ng) {
     JsonRowPlan p;
     p.simple_name = true;
-    int n = SOFA_JSON_FIXED;
+    int n = SOFA_JSON_FIXED - (JsonYIsBw<NG>::get(ng) ? 1 : 0);
     if (!v.valid) { p.len = n + 13 * 4; return p; }
     int bad = 0;
 #pragma unroll
@@ -1014,11 +1023,14 @@ SOFA_HD int json_row_emit(const RowVals& v, uint32_t fmask, const NG& ng, const 
     int n = 0;
     SOFA_JKEY(", {\"x\": "); SOFA_JNUM(0);
     SOFA_JKEY(", \"event\": "); SOFA_JNUM(1);
-    SOFA_JKEY(", \"y\": "); SOFA_JNUM(2);
+    const bool ybw = JsonYIsBw<NG>::get(ng);
+    if (ybw) SOFA_JKEY(", \"duration\": "); else SOFA_JKEY(", \"y\": ");
+    SOFA_JNUM(2);
     SOFA_JKEY(", \"deviceId\": "); SOFA_JNUM(3);
     SOFA_JKEY(", \"copyKind\": "); SOFA_JNUM(4);
     SOFA_JKEY(", \"payload\": "); SOFA_JNUM(5);
-    SOFA_JKEY(", \"bandwidth\": "); SOFA_JNUM(6);
+    if (ybw) SOFA_JKEY(", \"y\": "); else SOFA_JKEY(", \"bandwidth\": ");
+    SOFA_JNUM(6);
     SOFA_JKEY(", \"pkt_src\": "); SOFA_JNUM(7);
     SOFA_JKEY(", \"pkt_dst\": "); SOFA_JNUM(8);
     SOFA_JKEY(", \"pid\": "); SOFA_JNUM(9);

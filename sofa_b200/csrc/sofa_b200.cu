@@ -55,6 +55,7 @@ struct Source {
     uint32_t flags_stride[2] = {0, 0}, flags_val[2] = {0, 0};      // cached sofa_b200_row_flags results
     DevBuf vizhash, viz_id; uint32_t viz_stride = 0; bool viz_ready = false;
     DevBuf dict_hash, dict_off, dict_blob; int dict_n = 0;
+    bool side_ready = false; uint64_t side_ncand = 0;          // raw side source: rows per list after sofa_b200_side_preprocess
 };
 
 struct TimedEvent { int kind; cudaEvent_t a, b; };
@@ -62,7 +63,7 @@ struct TimedEvent { int kind; cudaEvent_t a, b; };
 struct sofa_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    Source src[6];                       // 0 perf, 1 gpu, 2 net, 3..5 side tables (mpstat, nvsmi, netstat CSV)
+    Source src[9];                       // 0 perf, 1 gpu, 2 net, 3..5 side tables (mpstat, nvsmi, netstat CSV), 6..8 raw recorder side files
     DevBuf out[3]; uint64_t out_n[3] = {0, 0, 0};
     // overlapped transfers: copy streams, the idle halves of the csv/json double buffers and the
     // D2H-complete event of each half
@@ -70,8 +71,8 @@ struct sofa_ctx {
     DevBuf out_alt[2];
     cudaEvent_t out_ev[2] = {nullptr, nullptr}, out_alt_ev[2] = {nullptr, nullptr};
     bool out_busy[2] = {false, false}, out_alt_busy[2] = {false, false};
-    cudaEvent_t up_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool up_pending[6] = {false, false, false, false, false, false};
+    cudaEvent_t up_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool up_pending[9] = {false, false, false, false, false, false, false, false, false};
     cudaEvent_t fetch_ev[16]; bool fetch_used[16]; int fetch_next = 0;
     DevBuf arena; uint64_t arena_cur = 0; bool arena_on = false;
     // small host<->device traffic goes through mapped pinned memory + a copy kernel, never the
@@ -199,9 +200,11 @@ static SideCols side_cols(sofa_ctx* c, int slot) {
     sc.dev = t.cols[SC_DEV].as<double>(); sc.bw = t.cols[SC_BW].as<double>(); sc.ratios = t.cols[SC_RATIOS].as<int32_t>();
     return sc;
 }
-static AllCols all_cols(sofa_ctx* c, int side_slot = 3) {
+static AllCols all_cols(sofa_ctx* c, int side_slot = 3, int raw_slot = 6) {
     AllCols a;
     a.s = side_cols(c, side_slot);
+    a.r.f = c->src[raw_slot].cols[0].as<double>(); a.r.i = c->src[raw_slot].cols[1].as<int64_t>();
+    a.r.nf = c->src[raw_slot].cols[2].as<int32_t>();
     Source& p = c->src[0]; Source& g = c->src[1]; Source& n = c->src[2];
     a.p.ts = p.cols[PC_TS].as<double>(); a.p.event = p.cols[PC_EVENT].as<double>(); a.p.dur = p.cols[PC_DUR].as<double>();
     a.p.pid = p.cols[PC_PID].as<int32_t>(); a.p.tid = p.cols[PC_TID].as<int32_t>();
@@ -218,6 +221,7 @@ static AllCols all_cols(sofa_ctx* c, int side_slot = 3) {
 static SrcView make_view(sofa_ctx* c, int k, bool with_viz) {
     SrcView v;
     Source& s = c->src[k];
+    memset(&v.side, 0, sizeof v.side);
     v.text = s.text.as<char>();
     v.n_rows = s.n_rows;
     v.c = all_cols(c);
@@ -244,6 +248,8 @@ static int alloc_cols(sofa_ctx* c, int k, uint64_t n) {
     } else if (k == SRC_NET) {
         ENSURE(s.cols[NC_TS], m * 8); ENSURE(s.cols[NC_PAYLOAD], m * 8); ENSURE(s.cols[NC_SRC], m * 8);
         ENSURE(s.cols[NC_DST], m * 8); ENSURE(s.cols[NC_PROTO], m);
+    } else if (k >= 6) {
+        ENSURE(s.cols[0], m * 72); ENSURE(s.cols[1], m * 32); ENSURE(s.cols[2], m * 4);
     } else {
         ENSURE(s.cols[SC_TS], m * 8); ENSURE(s.cols[SC_EVENT], m * 8); ENSURE(s.cols[SC_DUR], m * 8);
         ENSURE(s.cols[SC_DEV], m * 8); ENSURE(s.cols[SC_BW], m * 8); ENSURE(s.cols[SC_RATIOS], m * 20);
@@ -319,7 +325,7 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->out_ev[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_alt_ev[i], cudaEventDisableTiming)); }
-    for (int i = 0; i < 6; i++) CK(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 9; i++) CK(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 16; i++) { CK(cudaEventCreateWithFlags(&c->fetch_ev[i], cudaEventDisableTiming)); c->fetch_used[i] = false; }
     CK(cudaHostAlloc((void**)&c->stage_h, c->stage_cap, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&c->stage_d, c->stage_h, 0));
@@ -332,6 +338,7 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaFuncSetAttribute(k_parse<SRC_GPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_parse<SRC_NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_parse<SRC_SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_parse<SRC_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_PERF, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_PERF, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_GPU, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -339,6 +346,9 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_NET, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_NET, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_emit_fused<SRC_GPU, FMT_COMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_SIDEOUT, FMT_CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_SIDEOUT, FMT_JSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_emit_fused<SRC_SIDEOUT, FMT_AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     *out = c;
     return 0;
 }
@@ -350,12 +360,12 @@ int sofa_b200_destroy(sofa_ctx* c) {
     if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
     if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
     for (int i = 0; i < 2; i++) { if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); if (c->out_alt_ev[i]) cudaEventDestroy(c->out_alt_ev[i]); c->out_alt[i].release(); }
-    for (int i = 0; i < 6; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
+    for (int i = 0; i < 9; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
     for (int i = 0; i < 16; i++) cudaEventDestroy(c->fetch_ev[i]);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& e : c->pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 9; k++) {
         Source& s = c->src[k];
         s.text.release(); s.mhz.release(); s.mask.release(); s.vizhash.release(); s.viz_id.release();
         s.dict_hash.release(); s.dict_off.release(); s.dict_blob.release();
@@ -381,7 +391,7 @@ void* sofa_b200_host_alloc(uint64_t nbytes) {
 void sofa_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
-    if (!c || k < 0 || k > 5 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload: bad argument");
+    if (!c || k < 0 || k > 8 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload: bad argument");
     if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload: data_off beyond the text");
     CK(cudaSetDevice(c->device));
     Source& s = c->src[k];
@@ -396,9 +406,10 @@ int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint
 }
 
 static uint32_t pick_tile_bytes(int k) { return (k == SRC_NET || k >= 3) ? 16384u : 24576u; }
+enum { RC_F = 0, RC_I, RC_NF, RC_IDX, RC_TS, RC_F1, RC_F2, RC_I6, RC_CLS, RC_MASK };      // column slots of a raw side source
 
 int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t* n_rows) {
-    if (!c || k < 0 || k > 5 || !p) FAIL(SOFA_ERR_ARG, "parse: bad argument");
+    if (!c || k < 0 || k > 8 || !p) FAIL(SOFA_ERR_ARG, "parse: bad argument");
     Source& s = c->src[k];
     if (!s.uploaded) FAIL(SOFA_ERR_STATE, "parse: nothing uploaded for this source");
     CK(cudaSetDevice(c->device));
@@ -412,7 +423,7 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     cfg.idx_ctx = p->idx[4]; cfg.idx_stream = p->idx[5]; cfg.idx_name = p->idx[6]; cfg.idx_srcctx = p->idx[7];
     cfg.idx_dstctx = p->idx[8];
     cfg.api_mode = p->api_mode;
-    cfg.side_table = k >= 3 ? k - 3 : 0;
+    cfg.side_table = k >= 6 ? k - 6 : (k >= 3 ? k - 3 : 0);
     if (k == SRC_GPU && (cfg.idx_start < 0 || cfg.idx_dur < 0 || cfg.idx_name < 0))
         FAIL(SOFA_ERR_ARG, "parse: gpu trace needs Start, Duration and Name columns");
     ENSURE(s.mhz, 16 * (size_t)cfg.n_mhz + 16);
@@ -447,11 +458,15 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     CK(cudaGetLastError());
     if (cr) { c->err_row = 0; c->err_code = E_CR; FAIL(SOFA_ERR_ROW, "parse: carriage return in trace text (not supported)"); }
     if (alloc_cols(c, k, total)) return SOFA_ERR_CUDA;
+    if (k >= 6 && total) CK(cudaMemsetAsync(s.cols[RC_NF].p, 0, total * 4, c->stream));
     s.n_rows = total;
     uint32_t max_lines = tile / 8;
     size_t smem = (((size_t)tile + OVERLAP_BYTES + 48) & ~(size_t)15) + (size_t)max_lines * 4;
-    AllCols cols = all_cols(c, k >= 3 ? k : 3);
-    if (k >= 3)
+    AllCols cols = all_cols(c, (k >= 3 && k < 6) ? k : 3, k >= 6 ? k : 6);
+    if (k >= 6)
+        LAUNCH(c, K_PARSE, (k_parse<SRC_RAW><<<(unsigned)ntiles, PARSE_TPB, smem, c->stream>>>(
+            s.text.as<char>(), begin, end, tile, max_lines, c->tiles.as<uint64_t>(), cfg, cols, c->d_err)));
+    else if (k >= 3)
         LAUNCH(c, K_PARSE, (k_parse<SRC_SIDE><<<(unsigned)ntiles, PARSE_TPB, smem, c->stream>>>(
             s.text.as<char>(), begin, end, tile, max_lines, c->tiles.as<uint64_t>(), cfg, cols, c->d_err)));
     else if (k == SRC_PERF)
@@ -514,11 +529,13 @@ static int fmask_for(sofa_ctx* c, int k, uint32_t stride, uint32_t* fmask) {
 
 constexpr uint32_t FUSED_SLOT_BYTES = 64 * 1024;
 
+struct SideEmit { SideView v; uint64_t ncand; };
+
 template <int FMT>
 static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, int bit, uint32_t fmask,
-                      int outslot, uint64_t sel_hint, uint64_t* nbytes, uint64_t* nrec) {
+                      int outslot, uint64_t sel_hint, uint64_t* nbytes, uint64_t* nrec, const SideEmit* se = nullptr) {
     Source& s = c->src[k];
-    uint64_t ncand = cdiv(s.n_rows, stride);
+    uint64_t ncand = se ? se->ncand : cdiv(s.n_rows, stride);
     c->out_n[outslot] = 0;
     if (nbytes) *nbytes = 0;
     if (nrec) *nrec = 0;
@@ -526,6 +543,7 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
     if (ncand == 0) return 0;
     if (ncand >= 0xffffffffull) FAIL(SOFA_ERR_ARG, "emit: too many rows for one call");
     uint64_t text_share = s.nbytes > s.data_off ? s.nbytes - s.data_off : 0;
+    if (se) text_share = 0;                      // names are generated, not copied from the text
     const uint32_t* index = nullptr;
     uint64_t nitems = ncand;
     if (mask) {
@@ -548,7 +566,8 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
     uint64_t nblocks = cdiv(nitems, EMIT_TPB);
     ENSURE(c->tiles, (nblocks + 2) * 8);
     SrcView v = make_view(c, k, true);
-    uint64_t per_row = FMT == FMT_CSV ? 96 : (FMT == FMT_COMM ? 64 : 230);
+    if (se) v.side = se->v;
+    uint64_t per_row = FMT == FMT_CSV ? 96 : ((FMT == FMT_COMM || FMT == FMT_AUX) ? 64 : 230);
     if (FMT == FMT_COMM) text_share = 0;
     uint64_t cap = sel_hint * per_row + text_share + (1 << 16);
     // shared-memory image per block: sized for 128 typical rows of the format (larger ranges fall back
@@ -570,8 +589,12 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
         if constexpr (FMT == FMT_COMM) {
             if (k != SRC_GPU) FAIL(SOFA_ERR_ARG, "comm.csv is a gpu-trace output");
             LAUNCH(c, kk, (k_emit_fused<SRC_GPU, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+        } else if constexpr (FMT == FMT_AUX) {
+            if (!se) FAIL(SOFA_ERR_ARG, "aux rows are a side-source output");
+            LAUNCH(c, kk, (k_emit_fused<SRC_SIDEOUT, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
         } else {
-            if (k == SRC_PERF) LAUNCH(c, kk, (k_emit_fused<SRC_PERF, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+            if (se) LAUNCH(c, kk, (k_emit_fused<SRC_SIDEOUT, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
+            else if (k == SRC_PERF) LAUNCH(c, kk, (k_emit_fused<SRC_PERF, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
             else if (k == SRC_GPU) LAUNCH(c, kk, (k_emit_fused<SRC_GPU, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
             else LAUNCH(c, kk, (k_emit_fused<SRC_NET, FMT><<<g, EMIT_TPB, slot_bytes + 32, c->stream>>>(v, a)));
         }
@@ -645,7 +668,7 @@ int sofa_b200_fetch(sofa_ctx* c, int which, void* host_out, uint64_t cap) {
 }
 
 int sofa_b200_upload_async(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
-    if (!c || k < 0 || k > 5 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
+    if (!c || k < 0 || k > 8 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
     if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload_async: data_off beyond the text");
     CK(cudaSetDevice(c->device));
     Source& s = c->src[k];
@@ -912,6 +935,7 @@ int sofa_b200_text_fetch(sofa_ctx* c, int k, void* host_out, uint64_t cap) {
 
 #include "capi_analyze.inc"
 #include "capi_window.inc"
+#include "capi_side.inc"
 #include "capi_synth.inc"
 
 }  // extern "C"

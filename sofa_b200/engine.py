@@ -234,6 +234,37 @@ class CudaEngine:
                                                      len(ends), float(delta), out, ctypes.byref(ng)))
         return out, ng.value
 
+    # ---- recorder side files (mpstat.txt 6, nvsmi_query.txt 7, netstat.txt 8)
+    def side_preprocess(self, raw_src, text, time_base, absolute_timestamp, local_utc_offset=0, nvsmi_tz_add=0.0,
+                        data_off=0):
+        """-> (lines parsed, candidate rows per list, no_data flag); text=None: already uploaded"""
+        if text is not None:
+            self.upload(raw_src, text, data_off)
+        sp = L.SideParams()
+        sp.time_base, sp.absolute_timestamp = float(time_base), 1 if absolute_timestamp else 0
+        sp.local_utc_offset, sp.nvsmi_tz_add = int(local_utc_offset), float(nvsmi_tz_add)
+        nl, nc, nd = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int32()
+        self._check(self.lib.sofa_b200_side_preprocess(self.ctx, raw_src, ctypes.byref(sp), ctypes.byref(nl),
+                                                       ctypes.byref(nc), ctypes.byref(nd)))
+        return nl.value, nc.value, bool(nd.value)
+
+    def side_csv(self, raw_src, lst=0):
+        """(CSV body of one list, number of rows)"""
+        n, nr = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_side_emit_csv(self.ctx, raw_src, lst, ctypes.byref(n), ctypes.byref(nr)))
+        return self._fetch(0, n.value), nr.value
+
+    def side_json(self, raw_src, lst=0):
+        n, nr = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_side_emit_json(self.ctx, raw_src, lst, ctypes.byref(n), ctypes.byref(nr)))
+        return self._fetch(1, n.value), nr.value
+
+    def side_aux(self, raw_src):
+        """usr_sys.csv / netbandwidth.csv body (default float repr) and its row count"""
+        n, nr = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_side_emit_aux(self.ctx, raw_src, ctypes.byref(n), ctypes.byref(nr)))
+        return self._fetch(0, n.value), nr.value
+
     # ---- stopwatch (CUDA events on the engine's stream)
     def mark(self, which):
         self._check(self.lib.sofa_b200_mark(self.ctx, which))

@@ -92,6 +92,29 @@ def gpu_header(head):
                 payload_unit=pu[units[11]], idx=idx, t_base=t_base), data_off
 
 
+def nvsmi_local_offset(text, data_off):
+    """Seconds the host's local zone is ahead of UTC for the stamps of nvsmi_query.txt.  The reference
+    calls datetime.strptime(...).timestamp() on the naive stamps (sofa_preprocess.py:1032), i.e. reads
+    them as local time; the device computes the civil-to-epoch part as UTC and subtracts this.  Looked
+    up for the first and the last record; a change in between (DST switch) is refused."""
+    import calendar
+    import datetime
+    body = bytes(memoryview(text)[data_off:])
+    first = body[:body.find(b'\n')] if b'\n' in body else body
+    tail = body.rstrip(b'\n')
+    last = tail[tail.rfind(b'\n') + 1:]
+    offs = set()
+    for ln in (first, last):
+        try:
+            dt = datetime.datetime.strptime(ln.split(b',')[0].decode(), '%Y/%m/%d %H:%M:%S.%f')
+        except (ValueError, UnicodeDecodeError):
+            continue                                    # the device reports the malformed record
+        offs.add(int(calendar.timegm(dt.timetuple()) - dt.replace(microsecond=0).timestamp()))
+    if len(offs) > 1:
+        raise PreprocessError("the local UTC offset changes within nvsmi_query.txt (DST switch): not supported")
+    return offs.pop() if offs else 0
+
+
 ROW_ERRORS = {1: "too few fields (IndexError in the reference)", 2: "float() ValueError",
               3: "int() ValueError", 4: "number spelling not supported by the device codec",
               5: "int('0x01'+ip, 16) ValueError", 6: "line longer than 65535 bytes / tile overlap",

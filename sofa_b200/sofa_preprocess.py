@@ -8,10 +8,11 @@ reading side files, the nvprof header rows, demangling the unique mangled symbol
 writing the series wrappers of report.js.  There is no CPU fallback: without the CUDA
 library this module raises.
 
-Hot-path sources handled: perf.script (a1), nvprof gpu trace (a2), tcpdump text (a3).
-Sources SURVEY.md §8(f) ranks "next" (mpstat, vmstat, diskstat, nvsmi, netstat, strace,
-blktrace, pystacks) raise NotImplementedError when their input files are present, rather
-than silently producing a report.js that differs from the reference's.
+Sources handled: perf.script (a1), nvprof gpu trace (a2) and API trace (a4), tcpdump text (a3),
+and of SURVEY.md §8(f) N1 the recorder side files mpstat.txt, nvsmi_query.txt and netstat.txt.
+The remaining N1 sources (vmstat, diskstat, nvsmi.txt enc/dec, strace, blktrace, pystacks) raise
+NotImplementedError when their input files are present, rather than silently producing a
+report.js that differs from the reference's.
 """
 import ctypes
 import glob
@@ -26,8 +27,8 @@ sofa_fieldnames = ["timestamp", "event", "duration", "deviceId", "copyKind", "pa
                    "bandwidth", "pkt_src", "pkt_dst", "pid", "tid", "name", "category"]
 CSV_HEADER = (",".join(sofa_fieldnames) + "\n").encode()
 
-NOT_YET = ['mpstat.txt', 'vmstat.txt', 'diskstat.txt', 'nvsmi_query.txt', 'nvsmi.txt',
-           'netstat.txt', 'strace.txt', 'blktrace.txt', 'pystacks.txt']
+NOT_YET = ['vmstat.txt', 'diskstat.txt', 'nvsmi.txt', 'strace.txt', 'blktrace.txt', 'pystacks.txt']
+RAW_MPSTAT, RAW_NVSMI, RAW_NETSTAT = 6, 7, 8
 
 _libstdcxx = None
 
@@ -115,6 +116,59 @@ def gpu_first_timestamp(nvvp):
     return sorted(bases)[0] * 1.0 / 1e+9 if bases else 0
 
 
+def _write(path, *parts):
+    with open(path, 'wb') as f:
+        for p in parts:
+            f.write(memoryview(p))
+
+
+def _side_sources(cfg, eng, logdir):
+    """mpstat.txt (:482-546), nvsmi_query.txt (:1013-1084), netstat.txt (:1235-1337): rows, CSV text and
+    report.js records are produced on the device; this function only names the files."""
+    out = {}
+    if os.path.isfile(logdir + 'mpstat.txt'):
+        eng.side_preprocess(RAW_MPSTAT, _read_bytes(logdir + 'mpstat.txt'), cfg.time_base, cfg.absolute_timestamp)
+        aux, _ = eng.side_aux(RAW_MPSTAT)
+        _write(logdir + 'usr_sys.csv', b"time,usr,sys\n", aux)
+        body, nrows = eng.side_csv(RAW_MPSTAT)
+        if nrows > 0:
+            _write(logdir + 'mpstat.csv', CSV_HEADER, body)
+            out['mpstat_usr'] = eng.side_json(RAW_MPSTAT)
+        else:
+            print_warning(cfg, 'Empty list cannot be exported to mpstat.csv!')
+    if os.path.isfile(logdir + 'nvsmi_query.txt'):
+        text = _read_bytes(logdir + 'nvsmi_query.txt')
+        if len(text) == 0:
+            raise PreprocessError("nvsmi_query.txt is empty (next(f) raises StopIteration in the reference)")
+        nl = text.find(b'\n')
+        data_off = nl + 1 if nl >= 0 else len(text)                       # next(f): the header line
+        n_lines, ncand, no_data = eng.side_preprocess(
+            RAW_NVSMI, text, cfg.time_base, cfg.absolute_timestamp, hl.nvsmi_local_offset(text, data_off),
+            cfg.nvsmi_time_zone * 3600, data_off)
+        if no_data:
+            print_warning(cfg, 'No nvsmi query data.')
+        else:
+            print_info(cfg, "Length of nvsmi_query_traces = %d" % n_lines)
+            if ncand > 0:
+                sm, _ = eng.side_csv(RAW_NVSMI, 0)
+                mem, _ = eng.side_csv(RAW_NVSMI, 1)
+                _write(logdir + 'nvsmi_trace.csv', CSV_HEADER, sm, mem)
+                out['nvsmi_sm'] = eng.side_json(RAW_NVSMI, 0)
+                out['nvsmi_mem'] = eng.side_json(RAW_NVSMI, 1)
+    if os.path.isfile(logdir + 'netstat.txt'):
+        text = _read_bytes(logdir + 'netstat.txt')
+        if len(text) > 0:
+            eng.side_preprocess(RAW_NETSTAT, text, cfg.time_base, cfg.absolute_timestamp)
+            aux, _ = eng.side_aux(RAW_NETSTAT)
+            _write(logdir + 'netbandwidth.csv', b"time,tx_bandwidth,rx_bandwidth\n", aux)
+            tx, _ = eng.side_csv(RAW_NETSTAT, 0)
+            rx, _ = eng.side_csv(RAW_NETSTAT, 1)
+            _write(logdir + 'netstat.csv', CSV_HEADER, tx, rx)
+            out['tx_bandwidth'] = eng.side_json(RAW_NETSTAT, 0)
+            out['rx_bandwidth'] = eng.side_json(RAW_NETSTAT, 1)
+    return out
+
+
 def sofa_preprocess(cfg, engine=None):
     print_main_progress('SOFA preprocessing...')
     own_engine = engine is None
@@ -157,6 +211,7 @@ def _preprocess(cfg, eng):
     if ratio < 1:
         raise PreprocessError("plot_ratio must be >= 1")
 
+    side = _side_sources(cfg, eng, logdir)
     net_series = SeriesOut('net_trace', 'NET', 'blue')
     gpu_series = SeriesOut('gpu_kernel_trace', 'GPU kernel', 'rgba(0,180,0,0.8)')
     gpu_filter_series = []
@@ -287,20 +342,22 @@ def _preprocess(cfg, eng):
     for nm in ('blktrace_starting_block', 'blktrace_time', 'vmstat_cs', 'vmstat_bi', 'vmstat_bo'):
         series.append(SeriesOut(nm, nm, ''))
     if cfg.enable_mpstat:
-        series.append(SeriesOut('mpstat_usr', 'MPSTAT_USR', 'Cyan'))
+        series.append(SeriesOut('mpstat_usr', 'MPSTAT_USR', 'Cyan', *side.get('mpstat_usr', (None, 0))))
     if cfg.enable_diskstat:
         series.append(SeriesOut('diskstat', 'DISKSTAT', 'GreenYellow'))
     if cfg.enable_vmstat:
         for nm in ('vmstat_usr', 'vmstat_sys', 'vmstat_in', 'vmstat_cs'):
             series.append(SeriesOut(nm, nm, ''))
-    for nm in ('strace', 'pystacks', 'nvsmi_mem', 'nvsmi_sm'):
+    for nm in ('strace', 'pystacks'):
         series.append(SeriesOut(nm, nm, ''))
+    series.append(SeriesOut('nvsmi_mem', 'GPU_MEM_Util.', 'lightblue', *side.get('nvsmi_mem', (None, 0))))
+    series.append(SeriesOut('nvsmi_sm', 'GPU_SM_Util.', 'red', *side.get('nvsmi_sm', (None, 0))))
     if getattr(cfg, 'enable_encode_decode', False):
         series.append(SeriesOut('nvsmi_enc', '', ''))
         series.append(SeriesOut('nvsmi_dec', '', ''))
     series.append(net_series)
-    series.append(SeriesOut('tx_bandwidth', 'tx Bandwidth', 'rgba(135,206,250,0.8)'))
-    series.append(SeriesOut('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)'))
+    series.append(SeriesOut('tx_bandwidth', 'tx Bandwidth', 'rgba(135,206,250,0.8)', *side.get('tx_bandwidth', (None, 0))))
+    series.append(SeriesOut('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)', *side.get('rx_bandwidth', (None, 0))))
     series.append(gpu_series)
     series.extend(gpu_filter_series)
     if api_series is not None:

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Golden fixtures for concurrency_breakdown (a14): the UNMODIFIED reference preprocess turns
 synthetic mpstat / nvsmi_query / netstat raw logs into mpstat.csv, nvsmi_trace.csv, netstat.csv
-(+ cputrace.csv); the UNMODIFIED reference concurrency_breakdown (called directly: the analyze
+(+ cputrace.csv, usr_sys.csv, netbandwidth.csv and the side series of report.js, the N1 preprocess
+fixtures; raw inputs are stored next to them, time zone pinned to UTC because the reference reads
+the naive nvidia-smi stamps as local time); the UNMODIFIED reference concurrency_breakdown (called directly: the analyze
 driver line :981 fails on pandas 3) produces performance.csv and the feature rows.  Build
 container only (needs /root/reference)."""
 import contextlib
@@ -26,6 +28,9 @@ CASES = {
 
 
 def main():
+    import time
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
     mg.install_stubs()
     sys.path.insert(0, mg.REF_BIN)
     shimdir = tempfile.mkdtemp(prefix="sofa_shims_")
@@ -52,7 +57,10 @@ def main():
         out = os.path.join(HERE, name)
         shutil.rmtree(out, ignore_errors=True)
         os.makedirs(out)
-        for fn in ("mpstat.csv", "nvsmi_trace.csv", "netstat.csv", "cputrace.csv", "performance.csv", "misc.txt"):
+        for fn in ("mpstat.csv", "nvsmi_trace.csv", "netstat.csv", "cputrace.csv", "performance.csv", "misc.txt",
+                   "usr_sys.csv", "netbandwidth.csv", "report.js",
+                   "mpstat.txt", "nvsmi_query.txt", "netstat.txt", "perf.script", "sofa_time.txt",
+                   "perf_events_used.txt", "perf_timebase.txt"):
             shutil.copy(logdir + fn, os.path.join(out, fn))
         meta = {"make": mk, "cfg": ov,
                 "features": [[str(n), (None if v != v else float(v))] for n, v in zip(feats['name'], feats['value'])]}

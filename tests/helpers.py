@@ -57,3 +57,27 @@ def build_case_logdir(name, tmpdir):
     logdir = os.path.join(str(tmpdir), "sofalog") + "/"
     synth.make_logdir(logdir, **case["make_logdir"])
     return case, logdir
+
+
+SIDE_INPUTS = ("mpstat.txt", "nvsmi_query.txt", "netstat.txt", "perf.script", "sofa_time.txt", "perf_events_used.txt",
+               "perf_timebase.txt", "misc.txt")
+SIDE_OUTPUTS = ("mpstat.csv", "usr_sys.csv", "nvsmi_trace.csv", "netstat.csv", "netbandwidth.csv", "cputrace.csv",
+                "report.js")
+
+
+def side_cases():
+    return sorted(d for d in os.listdir(GOLDEN) if d.startswith("side_"))
+
+
+def build_side_logdir(name, tmpdir):
+    """Copy the stored raw inputs of a side_* golden case into a fresh logdir; pin the time zone the
+    fixtures were generated under (the reference reads nvidia-smi stamps as local time)."""
+    import shutil
+    import time
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
+    logdir = os.path.join(str(tmpdir), "sofalog") + "/"
+    os.makedirs(logdir)
+    for fn in SIDE_INPUTS:
+        shutil.copy(os.path.join(GOLDEN, name, fn), logdir + fn)
+    return load_case(name), logdir

@@ -33,6 +33,7 @@ void hs_fixed6_many(const double* x, long n, char* out, long* off) {
 
 // ---------------------------------------------------------------- row-level harness
 #include "../sofa_b200/csrc/rows.cuh"
+#include "../sofa_b200/csrc/side.cuh"
 #include <vector>
 #include <string>
 struct HsCfg {
@@ -167,3 +168,92 @@ extern "C" int hs_tokenize(const char* s, int n, int* ab, int maxt) {
 }
 
 extern "C" int hs_repr6(double x, char* out) { JPlan p = repr6_plan(x); if (p.kind == JP_BAD) return -1; int l = json_emit(p, out); return l == p.len ? l : -2; }
+
+// ---------------------------------------------------------------- recorder side files (side.cuh)
+// CPU mirror of sofa_b200_side_preprocess + the side emitters: same row functions, the indexing
+// (which line a row is differenced against, which rows survive) restated sequentially.
+// mode: 0/1 CSV of list 0/1, 2/3 JSON records of list 0/1, 4 aux rows (usr_sys.csv / netbandwidth.csv).
+// Returns -1, or row*1000+err; *nodata = 1 when nvidia-smi reported a failure.
+extern "C" long hs_side(int table, const char* text, long nbytes, int absolute, double time_base, long long local_off,
+                        double tz_add, int mode, char* out, long* outlen, long* nrec, long* nlines, long* ncand_out, int* nodata) {
+    std::vector<char> padded((size_t)nbytes + 64, '\n');
+    memcpy(padded.data() + 16, text, (size_t)nbytes);
+    text = padded.data() + 16;
+    std::vector<RawRow> raw;
+    long pos = 0, row = 0, first_err = -1;
+    bool failed = false;
+    while (pos < nbytes) {
+        long e = pos; while (e < nbytes && text[e] != '\n') e++;
+        bool has_nl = e < nbytes;
+        RawRow r = RawRow();
+        int err;
+        if (table == RAW_MPSTAT) err = parse_raw_mpstat(text + pos, (int)(e - pos), &r);
+        else if (table == RAW_NVSMI) err = parse_raw_nvsmi(text + pos, (int)(e - pos), has_nl, &r);
+        else err = parse_raw_netstat(text + pos, (int)(e - pos), &r);
+        if (err && first_err < 0) first_err = row * 1000 + err;
+        if (r.flag) failed = true;
+        raw.push_back(r);
+        row++; pos = e + 1;
+    }
+    *nlines = row; *nodata = 0; *outlen = 0; *nrec = 0; *ncand_out = 0;
+    if (table == RAW_NVSMI && failed) { *nodata = 1; return -1; }
+    if (first_err >= 0) return first_err;
+    std::vector<SideOutRow> rows;
+    if (table == RAW_MPSTAT) {
+        std::vector<long> idx;
+        long first = -1;
+        for (long i = 0; i < (long)raw.size(); i++) if (raw[i].nf > 0) { first = i; break; }
+        for (long i = 0; i < (long)raw.size(); i++) if (first >= 0 && raw[i].nf == raw[first].nf) idx.push_back(i);
+        if (idx.size() < 2) return 0 * 1000 + E_FEW_TOKENS;
+        double mx = -1e300; bool nan = false;
+        for (size_t j = 1; j < idx.size(); j++) { double v = raw[idx[j]].f[1]; if (d_isnan(v)) nan = true; else if (v > mx) mx = v; }
+        if (nan) return 1 * 1000 + E_FORMAT;
+        double nc = mx + 1.0;
+        if (!(nc >= 0.0 && nc < 1e9)) return 1 * 1000 + E_RANGE;
+        long stride = (long)nc + 1;
+        for (long i = 0; i + 1 < (long)idx.size(); i++) {
+            SideOutRow q; q.cls = 0;
+            if (i > stride) {
+                int e = side_mpstat_row(raw[idx[i + 1]].f, raw[idx[i + 1 - stride]].f, absolute, time_base, &q);
+                if (e) return idx[i + 1] * 1000 + e;
+            }
+            rows.push_back(q);
+        }
+    } else if (table == RAW_NVSMI) {
+        for (auto& r : raw) { SideOutRow q; side_nvsmi_row(r, local_off, tz_add, absolute, time_base, &q); rows.push_back(q); }
+    } else {
+        for (long i = 0; i + 1 < (long)raw.size(); i++) {
+            SideOutRow q;
+            int e = side_netstat_row(raw[i + 1], raw[i], absolute, time_base, &q);
+            if (e) return (i + 1) * 1000 + e;
+            rows.push_back(q);
+        }
+    }
+    *ncand_out = (long)rows.size();
+    long o = 0, cnt = 0;
+    const int half = (mode == 1 || mode == 3) ? 1 : 0;
+    const uint32_t fmask = side_fmask(table);
+    for (size_t i = 0; i < rows.size(); i++) {
+        const SideOutRow& q = rows[i];
+        if (mode == 4) {
+            if (table == RAW_MPSTAT && q.cls != 2) continue;
+            AuxRowPlan p = aux_row_plan(q.ts, q.f1, q.f2);
+            if (p.len < 0) return (long)i * 1000 + E_FORMAT;
+            int l = aux_row_emit(p, out + o);
+            if (l != p.len) return (long)i * 1000 + 99;
+            o += l; cnt++;
+            continue;
+        }
+        if (q.cls != 1) continue;
+        SideName ng{table, half, q};
+        RowVals v = vals_side(table, half, q);
+        int l, len;
+        if (mode <= 1) { bool sp; l = csv_row_len(v, fmask, ng, &sp); if (l < 0) return (long)i * 1000 + E_FORMAT; len = csv_row_write(v, fmask, ng, sp, out + o); }
+        else { l = json_row_len(v, fmask, ng); if (l < 0) return (long)i * 1000 + E_FORMAT; len = json_row_write(v, fmask, ng, out + o); }
+        if (len != l) return (long)i * 1000 + 99;
+        o += len; cnt++;
+    }
+    *outlen = o; *nrec = cnt;
+    return -1;
+}
+extern "C" int hs_repr(double x, char* out) { JPlan p = repr_plan(x); if (p.kind == JP_BAD) return -1; int l = repr_emit(p, out); return l == p.len ? l : -2; }

@@ -30,13 +30,14 @@ def build_hostsim():
     so = os.path.join(HERE, "_build", "libhostsim.so")
     src = os.path.join(HERE, "hostsim.cpp")
     os.makedirs(os.path.dirname(so), exist_ok=True)
-    deps = [src] + [os.path.join(HERE, "..", "sofa_b200", "csrc", f) for f in ("num.cuh", "rows.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "sofa_b200", "csrc", f) for f in ("num.cuh", "rows.cuh", "side.cuh")]
     if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                                "-o", so, src])
     lib = ctypes.CDLL(so)
     lib.hs_process.restype = ctypes.c_long
     lib.hs_fnv.restype = ctypes.c_ulonglong
+    lib.hs_side.restype = ctypes.c_long
     return lib
 
 
@@ -116,6 +117,38 @@ class HostSimEngine:
             assert fstride == stride
             out, _, n = self._run(kind, 2, stride, self._fmask(kind, stride), kws[filt])
         return out[2:], n
+
+    # ---- recorder side files: CPU build of side.cuh (hs_side)
+    def _side(self, raw_src, mode):
+        text, absolute, time_base, local_off, tz_add = self.side[raw_src]
+        out = ctypes.create_string_buffer(len(text) * 24 + 4096)
+        outlen, nrec, nlines, ncand = ctypes.c_long(), ctypes.c_long(), ctypes.c_long(), ctypes.c_long()
+        nodata = ctypes.c_int()
+        r = self.lib.hs_side(raw_src - 6, text, ctypes.c_long(len(text)), int(absolute), ctypes.c_double(time_base),
+                             ctypes.c_longlong(local_off), ctypes.c_double(tz_add), mode, out, ctypes.byref(outlen),
+                             ctypes.byref(nrec), ctypes.byref(nlines), ctypes.byref(ncand), ctypes.byref(nodata))
+        if r != -1:
+            raise HostSimError("row %d: error %d" % (r // 1000, r % 1000))
+        return np.frombuffer(out.raw[:outlen.value], dtype=np.uint8), nrec.value, nlines.value, ncand.value, bool(nodata.value)
+
+    def side_preprocess(self, raw_src, text, time_base, absolute_timestamp, local_utc_offset=0, nvsmi_tz_add=0.0,
+                        data_off=0):
+        if not hasattr(self, 'side'):
+            self.side = {}
+        self.side[raw_src] = (bytes(text)[data_off:], 1 if absolute_timestamp else 0, float(time_base),
+                              int(local_utc_offset), float(nvsmi_tz_add))
+        _, _, nlines, ncand, nodata = self._side(raw_src, 0)
+        return nlines, ncand, nodata
+
+    def side_csv(self, raw_src, lst=0):
+        return self._side(raw_src, lst)[:2]
+
+    def side_json(self, raw_src, lst=0):
+        out, n = self._side(raw_src, 2 + lst)[:2]
+        return out[2:], n
+
+    def side_aux(self, raw_src):
+        return self._side(raw_src, 4)[:2]
 
     # ---- side tables: numpy stand-in for the device window reduction (test infrastructure only)
     def upload(self, kind, text, data_off=0):

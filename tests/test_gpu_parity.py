@@ -376,3 +376,62 @@ def test_line_longer_than_overlap_window_fails_loudly(tmp_path):
     with pytest.raises(SofaB200Error) as ei:
         sofa_preprocess(default_report_config(logdir))
     assert ei.value.row_code in (6,) and ei.value.row == 1500
+
+
+# ---------------------------------------------------------------- N1: recorder side files on the device
+def test_side_sources_device_reproduce_reference_files(tmp_path):
+    from helpers import side_cases, build_side_logdir, SIDE_OUTPUTS
+    for name in side_cases():
+        case, logdir = build_side_logdir(name, tmp_path / name)
+        sofa_preprocess(default_report_config(logdir))
+        for fn in SIDE_OUTPUTS:
+            with open(logdir + fn, "rb") as f:
+                _diff(name, fn, f.read(), golden_bytes(name, fn))
+
+
+def test_side_sources_device_match_oracle_larger_and_edge_cases(tmp_path):
+    """40 k mpstat lines (64 cores), 20 k nvidia-smi lines, 5 k netstat lines - several tiles and emit
+    blocks per file - plus malformed mpstat lines and a time-zone shift; byte-compare with the oracle."""
+    import shutil
+    import time
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
+    a = os.path.join(str(tmp_path), "gpu") + "/"
+    synth.make_logdir(a, seed=11, n_perf=500)
+    synth.write_side_raw(a, seed=12, n_samples=620, n_cores=64, n_gpus=8)
+    with open(a + "nvsmi_query.txt", "a") as f:             # more nvidia-smi lines than samples x gpus
+        body = open(a + "nvsmi_query.txt").read().split("\n")[1:-1]
+        for rep in range(3):
+            f.write("\n".join(body) + "\n")
+    lines = open(a + "mpstat.txt").read().split("\n")
+    lines.insert(1000, "1600000004.1,2,77")
+    lines.insert(2000, "")
+    lines[3000] += ",1"
+    open(a + "mpstat.txt", "w").write("\n".join(lines))
+    b = os.path.join(str(tmp_path), "cpu") + "/"
+    shutil.copytree(a, b)
+    cfg = default_report_config(a)
+    cfg.nvsmi_time_zone = -5
+    sofa_preprocess(cfg)
+    orc.preprocess(orc.OracleConfig(b, nprocs=1, nvsmi_time_zone=-5), demangle=demangle)
+    for fn in ("mpstat.csv", "usr_sys.csv", "nvsmi_trace.csv", "netstat.csv", "netbandwidth.csv", "report.js"):
+        with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
+            _diff("side_large", fn, f.read(), g.read())
+
+
+def test_side_sources_device_errors_and_no_data(tmp_path):
+    from helpers import build_side_logdir
+    from sofa_b200._lib import SofaB200Error
+    _, d = build_side_logdir("side_small", tmp_path / "dup")
+    lines = open(d + "netstat.txt").read().split("\n")
+    lines[3] = lines[2]                                      # ZeroDivisionError in the reference
+    open(d + "netstat.txt", "w").write("\n".join(lines))
+    with pytest.raises(SofaB200Error):
+        sofa_preprocess(default_report_config(d))
+    _, d = build_side_logdir("side_small", tmp_path / "failed")
+    with open(d + "nvsmi_query.txt", "a") as f:
+        f.write("Unable to determine the device handle for GPU 0000:3B:00.0: Unknown Error (Failed)\n")
+    sofa_preprocess(default_report_config(d))
+    assert not os.path.isfile(d + "nvsmi_trace.csv")
+    js = open(d + "report.js").read()
+    assert "nvsmi_sm =" not in js and "mpstat_usr =" in js and "tx_bandwidth =" in js

@@ -24,3 +24,13 @@ def test_oracle_concurrency_breakdown_matches_reference(name):
     buf = io.StringIO()
     perf.to_csv(buf)
     assert buf.getvalue().encode() == open(d + "/performance.csv", "rb").read()
+
+
+@pytest.mark.parametrize("name", SIDE)
+def test_oracle_side_preprocess_matches_reference(name, tmp_path):
+    """N1: mpstat.txt / nvsmi_query.txt / netstat.txt -> CSVs + report.js series, byte for byte."""
+    from helpers import build_side_logdir, SIDE_OUTPUTS, golden_bytes, demangle
+    case, logdir = build_side_logdir(name, tmp_path)
+    orc.preprocess(orc.OracleConfig(logdir, nprocs=1), demangle=demangle)
+    for fn in SIDE_OUTPUTS:
+        assert open(logdir + fn, "rb").read() == golden_bytes(name, fn), fn

@@ -1,0 +1,147 @@
+"""N1: mpstat.txt / nvsmi_query.txt / netstat.txt through the product host logic
+(sofa_b200.sofa_preprocess) and the CPU build of the device row functions (side.cuh), byte for byte
+against the unmodified reference's files (tests/golden/side_*); edge cases against the oracle."""
+import ctypes
+import math
+import os
+import random
+import struct
+
+import pytest
+
+from helpers import side_cases, build_side_logdir, golden_bytes, SIDE_OUTPUTS, demangle
+from hostsim_engine import HostSimEngine, HostSimError, build_hostsim
+from oracle import sofa_oracle as orc
+from sofa_b200.sofa_config import default_report_config
+from sofa_b200.sofa_preprocess import sofa_preprocess
+
+
+def run_product(logdir, engine, **over):
+    cfg = default_report_config(logdir)
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    sofa_preprocess(cfg, engine=engine)
+    return cfg
+
+
+def assert_same(got, want, what):
+    if got != want:
+        i = next((k for k in range(min(len(got), len(want))) if got[k] != want[k]), min(len(got), len(want)))
+        raise AssertionError("%s differs at byte %d: got %r want %r" % (what, i, got[max(0, i - 80):i + 60], want[max(0, i - 80):i + 60]))
+
+
+@pytest.mark.parametrize("name", side_cases())
+def test_side_sources_reproduce_reference_files(name, tmp_path):
+    case, logdir = build_side_logdir(name, tmp_path)
+    run_product(logdir, HostSimEngine())
+    for fn in SIDE_OUTPUTS:
+        assert_same(open(logdir + fn, "rb").read(), golden_bytes(name, fn), "%s/%s" % (name, fn))
+
+
+def oracle_vs_product(tmp_path, mutate, **over):
+    """Same mutated logdir through the oracle and the product; compare every side output."""
+    import shutil
+    _, a = build_side_logdir("side_small", tmp_path / "a")
+    mutate(a)
+    b = str(tmp_path / "b") + "/"
+    shutil.copytree(a, b)
+    run_product(a, HostSimEngine(), **over)
+    orc.preprocess(orc.OracleConfig(b, nprocs=1, **over), demangle=demangle)
+    for fn in SIDE_OUTPUTS:
+        ea, eb = os.path.isfile(a + fn), os.path.isfile(b + fn)
+        assert ea == eb, fn
+        if ea:
+            assert_same(open(a + fn, "rb").read(), open(b + fn, "rb").read(), fn)
+
+
+def test_mpstat_bad_lines_and_absolute_timestamps(tmp_path):
+    def mutate(d):
+        lines = open(d + "mpstat.txt").read().split("\n")
+        lines.insert(40, "1600000004.1,2,77")                # wrong field count: genfromtxt drops it
+        lines.insert(90, "")                                 # blank line
+        lines[120] = lines[120] + ",9"                       # one field too many
+        lines[-2] = lines[-2].rsplit(",", 3)[0]              # truncated last record
+        open(d + "mpstat.txt", "w").write("\n".join(lines))
+    oracle_vs_product(tmp_path, mutate, absolute_timestamp=True)
+
+
+def test_mpstat_idle_interval_and_no_increase(tmp_path):
+    def mutate(d):
+        lines = open(d + "mpstat.txt").read().split("\n")
+        # repeat one sample verbatim: every delta is 0 -> "No increases in mpstat values" rows are skipped
+        block = lines[1 + 5 * 20: 1 + 5 * 21]
+        lines[1 + 5 * 21: 1 + 5 * 22] = [b.replace(b.split(",")[0], l.split(",")[0], 1) for b, l in zip(block, lines[1 + 5 * 21: 1 + 5 * 22])]
+        open(d + "mpstat.txt", "w").write("\n".join(lines))
+    oracle_vs_product(tmp_path, mutate)
+
+
+def test_nvsmi_time_zone_failed_and_short_fraction(tmp_path):
+    def mutate(d):
+        lines = open(d + "nvsmi_query.txt").read().split("\n")
+        lines[7] = lines[7][:20] + "5" + lines[7][23:]                    # 1-digit fraction ".5"
+        open(d + "nvsmi_query.txt", "w").write("\n".join(lines))
+    oracle_vs_product(tmp_path, mutate, nvsmi_time_zone=8)
+
+    def failed(d):
+        with open(d + "nvsmi_query.txt", "a") as f:
+            f.write("Unable to determine the device handle: Failed\n")
+    oracle_vs_product(tmp_path / "f", failed)
+
+
+def test_netstat_single_line_and_no_trailing_newline(tmp_path):
+    def one(d):
+        open(d + "netstat.txt", "w").write("1600000000.5,100,200\n")
+    oracle_vs_product(tmp_path / "one", one)
+
+    def nonl(d):
+        t = open(d + "netstat.txt").read().rstrip("\n")
+        open(d + "netstat.txt", "w").write(t)
+    oracle_vs_product(tmp_path / "nonl", nonl)
+
+    def neg(d):                                              # counter wrap: negative bandwidth, '%d' truncates toward zero
+        lines = open(d + "netstat.txt").read().split("\n")
+        lines[10] = lines[10].split(",")[0] + ",5,7"
+        open(d + "netstat.txt", "w").write("\n".join(lines))
+    oracle_vs_product(tmp_path / "neg", neg)
+
+
+def test_side_errors_are_loud(tmp_path):
+    _, d = build_side_logdir("side_small", tmp_path)
+    lines = open(d + "netstat.txt").read().split("\n")
+    lines[3] = lines[2]                                       # same timestamp twice: ZeroDivisionError in the reference
+    open(d + "netstat.txt", "w").write("\n".join(lines))
+    with pytest.raises(HostSimError):
+        run_product(d, HostSimEngine())
+
+
+def test_repr_matches_python():
+    lib = build_hostsim()
+    lib.hs_repr.argtypes = [ctypes.c_double, ctypes.c_char_p]
+    buf = ctypes.create_string_buffer(64)
+    rng = random.Random(20260921)
+    vals = [0.0, -0.0, 1.0, -1.5, 0.1, 0.2 + 0.1, 1e-4, 9.999e-5, 1.2345e-5, 1e-6, 123456.789, 1e15, 9007199254740993.0,
+            9999999999999998.0, 0.7000000476837158, 68.14159292035399, 8157367.779472141, 5e-324 * 0 + 2.5e-5,
+            4503599627370496.0, 4503599627370497.0, 0.3, 2.0 / 3.0, 1.0 / 3.0, 100.0, 1e5, 99999.99999999999]
+    for _ in range(20000):
+        kind = rng.random()
+        if kind < 0.4:
+            vals.append(struct.unpack('<d', struct.pack('<Q', rng.getrandbits(64)))[0])
+        elif kind < 0.7:
+            vals.append(rng.uniform(-1e7, 1e7))
+        elif kind < 0.85:
+            vals.append(rng.randrange(0, 10**7) / rng.choice([1, 3, 7, 100, 1000, 12345]))
+        else:
+            vals.append(10 ** rng.uniform(-6, 16) * rng.choice([-1, 1]))
+    n_ok = 0
+    for v in vals:
+        if math.isnan(v) or math.isinf(v):
+            continue
+        r = lib.hs_repr(v, buf)
+        a = abs(v)
+        if v == 0 or (1e-6 <= a < 1e16):
+            assert r > 0, v
+            assert buf.raw[:r].decode() == repr(v), (v, buf.raw[:r], repr(v))
+            n_ok += 1
+        elif r > 0:                                          # outside the guaranteed range: never wrong, may refuse
+            assert buf.raw[:r].decode() == repr(v), (v, buf.raw[:r], repr(v))
+    assert n_ok > 10000
