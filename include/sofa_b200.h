@@ -173,6 +173,20 @@ typedef struct {
 int sofa_b200_window_reduce(sofa_ctx*, const double* ends, uint32_t n_windows, double delta, sofa_window_t* out,
                             uint32_t* num_gpus);
 
+/* nvsmi_profile (sofa_analyze.py:259-341) over the parsed nvsmi_trace.csv body (source 4), optionally
+ * restricted to roi_begin < timestamp <= roi_end (--spotlight_gpu).  One entry per (deviceId, event)
+ * present: row count, duration sum (means = sum / count), and for q = 0.25, 0.5, 0.75 the two order
+ * statistics numpy's linear quantile interpolates between (q_lo at floor((count-1)q), q_hi at ceil).
+ * dev_order: device ids in order of first appearance (the reference iterates a Python set of them);
+ * ts_first / ts_last: timestamps of the first / last row used (df.iloc[0] / df.iloc[-1]). */
+typedef struct {
+    int32_t dev, event;
+    uint64_t count; int64_t sum;
+    double q_lo[3], q_hi[3];
+} sofa_nvsmi_group_t;
+int sofa_b200_nvsmi_profile(sofa_ctx*, int use_roi, double roi_begin, double roi_end, sofa_nvsmi_group_t* groups,
+                            uint32_t cap, uint32_t* n_groups, int32_t* dev_order, uint32_t* n_dev, double* ts_first,
+                            double* ts_last, uint64_t* n_used);
 /* Recorder side files -> rows of mpstat.csv + usr_sys.csv (sofa_preprocess.py:482-546),
  * nvsmi_trace.csv (:1013-1084) and netstat.csv + netbandwidth.csv (:1235-1337), and the records
  * of their report.js series (mpstat_usr; nvsmi_sm / nvsmi_mem; tx_bandwidth / rx_bandwidth).

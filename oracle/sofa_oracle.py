@@ -599,6 +599,25 @@ def cpu_profile(df):
 
 
 # --------------------------------------------------------------------------- ujson double
+def nvsmi_profile(df_nvsmi, nvsmi_data=False, spotlight_gpu=False, roi_begin=0, roi_end=0):
+    """sofa_analyze.py:259-341 -> the six feature rows (verbose tables are print-only)."""
+    if spotlight_gpu and roi_end != 0:
+        df_nvsmi = df_nvsmi[(df_nvsmi['timestamp'] > roi_begin) & (df_nvsmi['timestamp'] <= roi_end)]
+    df_nvsmi.iloc[0].timestamp                                           # :271 raises on an empty frame
+    gpu_sm_util = df_nvsmi.groupby(['event'])['duration'].mean()[0]
+    gpu_mem_util = df_nvsmi.groupby(['event'])['duration'].mean()[1]
+    sm = df_nvsmi['event'] == int(0)
+    mem = df_nvsmi['event'] == int(1)
+    gpunum = list(set(df_nvsmi['deviceId']))
+    gpuid = df_nvsmi['deviceId'] == int(gpunum[-1])                      # the loop variable leaks (:295, :330)
+    return [('gpu_sm_util_q2', df_nvsmi[sm & gpuid]['duration'].quantile(0.5)),
+            ('gpu_sm_util_q3', df_nvsmi[sm & gpuid]['duration'].quantile(0.75)),
+            ('gpu_sm_util', int(gpu_sm_util)),
+            ('gpu_mem_util_q2', df_nvsmi[mem & gpuid]['duration'].quantile(0.5)),
+            ('gpu_mem_util_q3', df_nvsmi[mem & gpuid]['duration'].quantile(0.75)),
+            ('gpu_mem_util', int(gpu_mem_util))]
+
+
 def ujson_double_str(value, precision=10):
     """pandas' vendored ultrajson Buffer_AppendDoubleUnchecked (what `to_json` prints for a
     float64, double_precision=10) restated for the fixed-notation range; used to pin the

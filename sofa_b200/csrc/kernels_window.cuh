@@ -107,4 +107,40 @@ __global__ void __launch_bounds__(256) k_win_net_scatter(const uint64_t* __restr
     if (key != ~0ull) txrx[key] = sums[s];
 }
 
+// ---------------------------------------------------------------------------- nvsmi_profile (sofa_analyze.py:259-341)
+// Sort key of an nvsmi_trace.csv row: (deviceId * 4 + event) << 32 | (duration + 2^31), so that every
+// (deviceId, event) group is contiguous and ordered by duration; rows outside the region of interest
+// get ~0.  tab[g] = {count, sum}; first[dev] = first row of that device (set() insertion order);
+// span[0] / span[1] = first / last kept row.
+__global__ void __launch_bounds__(256) k_nvsmi_keys(SideCols v, uint64_t n, int use_roi, double roi_begin, double roi_end,
+                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                    unsigned long long* tab, unsigned long long* first, unsigned long long* span,
+                                                    unsigned int* bad) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = ~0ull;
+    double ts = v.ts[i];
+    if (!use_roi || (ts > roi_begin && ts <= roi_end)) {
+        double dev = v.dev[i], ev = v.event[i], d = v.dur[i];
+        long long di = (long long)dev, ei = (long long)ev, dl = (long long)d;
+        if ((double)di != dev || di < 0 || di > 63) { atomicOr(bad, 1u); }
+        else if ((double)ei != ev || ei < 0 || ei > 3) { atomicOr(bad, 8u); }
+        else if ((double)dl != d || dl <= -2147483648ll || dl >= 2147483648ll) { atomicOr(bad, 2u); }
+        else {
+            unsigned g = (unsigned)(di * 4 + ei);
+            key = ((uint64_t)g << 32) | (uint64_t)(uint32_t)(dl + 2147483648ll);
+            atomicAdd(&tab[2 * g], 1ull);
+            atomicAdd(&tab[2 * g + 1], (unsigned long long)dl);
+            atomicMin(&first[di], (unsigned long long)i);
+            atomicMin(&span[0], (unsigned long long)i);
+            atomicMax(&span[1], (unsigned long long)i);
+        }
+    }
+    keys[i] = key; vals[i] = (uint32_t)i;
+}
+__global__ void k_gather_u64(const uint64_t* __restrict__ src, const uint64_t* __restrict__ pos, uint32_t n, uint64_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[pos[i]];
+}
+
 }  // namespace sofa

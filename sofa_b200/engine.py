@@ -234,6 +234,22 @@ class CudaEngine:
                                                      len(ends), float(delta), out, ctypes.byref(ng)))
         return out, ng.value
 
+    def nvsmi_profile(self, roi=None):
+        """Per (deviceId, event) group of the parsed nvsmi_trace.csv (source 4): {(dev, event): (count, sum,
+        [(lo, hi)] for q = .25, .5, .75)}, device ids in order of first appearance, first / last timestamp."""
+        groups = (L.NvsmiGroup * 256)()
+        ng, nd = ctypes.c_uint32(), ctypes.c_uint32()
+        order = (ctypes.c_int32 * 64)()
+        t0, t1, used = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_nvsmi_profile(self.ctx, 1 if roi else 0, float(roi[0]) if roi else 0.0,
+                                                     float(roi[1]) if roi else 0.0, groups, 256, ctypes.byref(ng), order,
+                                                     ctypes.byref(nd), ctypes.byref(t0), ctypes.byref(t1), ctypes.byref(used)))
+        out = {}
+        for i in range(ng.value):
+            g = groups[i]
+            out[(g.dev, g.event)] = (int(g.count), int(g.sum), [(g.q_lo[q], g.q_hi[q]) for q in range(3)])
+        return out, [order[i] for i in range(nd.value)], t0.value, t1.value, used.value
+
     # ---- recorder side files (mpstat.txt 6, nvsmi_query.txt 7, netstat.txt 8)
     def side_preprocess(self, raw_src, text, time_base, absolute_timestamp, local_utc_offset=0, nvsmi_tz_add=0.0,
                         data_off=0):

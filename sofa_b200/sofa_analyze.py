@@ -122,6 +122,82 @@ def _first_last_timestamp(body):
     return float(first), float(last_line[:last_line.find(b',')])
 
 
+def _lerp(lo, hi, count, q):
+    """numpy's linear quantile between the two order statistics around (count-1)*q."""
+    vi = (count - 1) * q
+    gamma = vi - int(vi)
+    return lo + (hi - lo) * gamma
+
+
+def nvsmi_profile(logdir, cfg, eng, features):
+    """sofa_analyze.py:259-341.  Group counts, duration sums and the order statistics behind the
+    quartiles come from one device pass over nvsmi_trace.csv (key build + radix sort); the handful of
+    divisions and the verbose tables stay on the host."""
+    from . import hostlogic as hl2
+    body = _csv_body(logdir + 'nvsmi_trace.csv')
+    eng.upload(SRC_NVSMI_CSV, body)
+    eng.parse(SRC_NVSMI_CSV, hl2.base_params(SRC_NVSMI_CSV, 0.0, True))
+    if not cfg.cluster_ip and cfg.verbose:
+        print_title('SM & MEM & ENCODE/DECODE Profiling')
+    roi = None
+    if cfg.spotlight_gpu:
+        if cfg.roi_end == 0:
+            print_warning(cfg, 'spotlight_gpu has no effects.')
+        else:
+            roi = (cfg.roi_begin, cfg.roi_end)
+    groups, dev_order, ts_first, ts_last, used = eng.nvsmi_profile(roi)
+    if used == 0:
+        raise IndexError("single positional indexer is out-of-bounds")          # df_nvsmi.iloc[0] on an empty frame
+
+    def ev_mean(ev):                                             # groupby(['event'])['duration'].mean()[ev]
+        cnt = sum(g[0] for (d, e), g in groups.items() if e == ev)
+        if cnt == 0:
+            raise KeyError(ev)
+        return sum(g[1] for (d, e), g in groups.items() if e == ev) / cnt
+    gpu_sm_util, gpu_mem_util = ev_mean(0), ev_mean(1)
+    gpu_enc_util, gpu_dec_util = (ev_mean(2), ev_mean(3)) if cfg.nvsmi_data else (0, 0)
+    nan = float('nan')
+
+    import numpy as np
+
+    def mean(dev, ev):
+        g = groups.get((dev, ev))
+        return np.float64(g[1] / g[0] if g else nan)
+
+    def quant(dev, ev, qi):
+        g = groups.get((dev, ev))
+        return np.float64(_lerp(g[2][qi][0], g[2][qi][1], g[0], 0.25 * (qi + 1)) if g else nan)
+    gpunum = list(set(dev_order))                                # iteration order of the reference's set
+    if not cfg.cluster_ip and cfg.verbose:
+        import pandas as pd
+        res = pd.DataFrame([], columns=['sm', 'mem', 'enc', 'dec'])
+        sm_q = pd.DataFrame([], columns=['Q1', 'Q2', 'Q3', 'Avg'])
+        mem_q = pd.DataFrame([], columns=['Q1', 'Q2', 'Q3', 'Avg'])
+        for i in gpunum:                                         # frames grown row by row as in :293-318 (their dtypes shape the print)
+            res = pd.concat([res, pd.DataFrame([[round(mean(i, e), 2) for e in range(4)]], columns=['sm', 'mem', 'enc', 'dec'], index=[i])])
+            sm_q = pd.concat([sm_q, pd.DataFrame([[round(quant(i, 0, 0), 2), round(quant(i, 0, 1), 2), round(quant(i, 0, 2), 2),
+                                                   round(mean(i, 0), 2)]], columns=['Q1', 'Q2', 'Q3', 'Avg'], index=[i])])
+            mem_q = pd.concat([mem_q, pd.DataFrame([[round(quant(i, 1, 0), 2), round(quant(i, 1, 1), 2), round(quant(i, 1, 2), 2),
+                                                     round(mean(i, 1), 2)]], columns=['Q1', 'Q2', 'Q3', 'Avg'], index=[i])])
+        for d in (res, sm_q, mem_q):
+            d.index.name = 'gpu_id'
+        print('GPU Utilization (%):')
+        print(res)
+        print('\nGPU SM Quartile (%):')
+        print(sm_q)
+        print('\nGPU MEM Quartile (%):')
+        print(mem_q)
+        print('Overall Average SM Utilization (%): ', int(gpu_sm_util))
+        print('Overall Average MEM Utilization (%): ', int(gpu_mem_util))
+        print('Overall Average ENC Utilization (%): ', int(gpu_enc_util))
+        print('Overall Average DEC Utilization (%): ', int(gpu_dec_util))
+        print('Overall Active GPU Time (s): %.3lf' % ((ts_last - ts_first) * gpu_sm_util / 100.0))
+    last = gpunum[-1]                                            # `gpuid` leaks out of the reference's loop (:330-336)
+    return features + [('gpu_sm_util_q2', quant(last, 0, 1)), ('gpu_sm_util_q3', quant(last, 0, 2)),
+                       ('gpu_sm_util', int(gpu_sm_util)), ('gpu_mem_util_q2', quant(last, 1, 1)),
+                       ('gpu_mem_util_q3', quant(last, 1, 2)), ('gpu_mem_util', int(gpu_mem_util))]
+
+
 def concurrency_breakdown(logdir, cfg, eng, features):
     """sofa_analyze.py:75-243.  The per-window masks over mpstat.csv / nvsmi_trace.csv / netstat.csv
     (O(windows x rows) in the reference) are one device pass (`window_reduce`); the scalar logic per
@@ -271,6 +347,14 @@ def sofa_analyze(cfg, engine=None):
             if own or engine is not None:
                 load_perf_source(cfg, eng)
             cpu_profile(cfg, eng)
+        if os.path.isfile(logdir + "nvsmi_trace.csv"):                     # :957-961
+            if eng is None:
+                from .engine import CudaEngine
+                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
+                own = True
+            features = nvsmi_profile(logdir, cfg, eng, features)
+        else:
+            print_warning(cfg, "nvsmi_trace.csv is not found")
         if os.path.isfile(logdir + "gputrace.csv"):
             if eng is None:
                 from .engine import CudaEngine

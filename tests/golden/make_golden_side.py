@@ -54,15 +54,25 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             feats = ref_an.concurrency_breakdown(logdir, cfg, df_mpstat, df_cpu, pd.DataFrame([], columns=cfg.columns),
                                                  df_nvsmi, df_bw, feats)
+        # a17 nvsmi_profile (sofa_analyze.py:259-341), called directly; verbose output kept as a fixture
+        nv_feats = pd.DataFrame({'name': ['elapsed_time'], 'value': [12.5]}, columns=['name', 'value'])
+        cfg.verbose = True
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            nv_feats = ref_an.nvsmi_profile(logdir, cfg, df_nvsmi, nv_feats)
+        cfg.verbose = False
+        with open(logdir + "nvsmi_profile_verbose.txt", "w") as f:
+            f.write(buf.getvalue())
         out = os.path.join(HERE, name)
         shutil.rmtree(out, ignore_errors=True)
         os.makedirs(out)
         for fn in ("mpstat.csv", "nvsmi_trace.csv", "netstat.csv", "cputrace.csv", "performance.csv", "misc.txt",
                    "usr_sys.csv", "netbandwidth.csv", "report.js",
                    "mpstat.txt", "nvsmi_query.txt", "netstat.txt", "perf.script", "sofa_time.txt",
-                   "perf_events_used.txt", "perf_timebase.txt"):
+                   "perf_events_used.txt", "perf_timebase.txt", "nvsmi_profile_verbose.txt"):
             shutil.copy(logdir + fn, os.path.join(out, fn))
         meta = {"make": mk, "cfg": ov,
+                "nvsmi_features": [[str(n), float(v)] for n, v in zip(nv_feats['name'], nv_feats['value'])],
                 "features": [[str(n), (None if v != v else float(v))] for n, v in zip(feats['name'], feats['value'])]}
         with open(os.path.join(out, "case.json"), "w") as f:
             json.dump(meta, f, indent=1, sort_keys=True)

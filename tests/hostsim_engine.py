@@ -157,6 +157,31 @@ class HostSimEngine:
     def parse(self, kind, params):
         return self.src[kind][0].count(b"\n")
 
+    def nvsmi_profile(self, roi=None):
+        """numpy stand-in for sofa_b200_nvsmi_profile (test infrastructure only)."""
+        import io
+        import pandas as pd
+        cols = ["timestamp", "event", "duration", "deviceId", "copyKind", "payload", "bandwidth", "pkt_src",
+                "pkt_dst", "pid", "tid", "name", "category"]
+        df = pd.read_csv(io.BytesIO(self.src[4][0]), names=cols)
+        if roi:
+            df = df[(df.timestamp > roi[0]) & (df.timestamp <= roi[1])]
+        groups, order = {}, []
+        for d in df.deviceId:
+            if int(d) not in order:
+                order.append(int(d))
+        for (d, e), g in df.groupby(['deviceId', 'event']):
+            v = sorted(int(x) for x in g.duration)
+            qs = []
+            for q in (1, 2, 3):
+                num = (len(v) - 1) * q
+                lo = num // 4
+                qs.append((float(v[lo]), float(v[lo + 1 if num % 4 else lo])))
+            groups[(int(d), int(e))] = (len(v), sum(v), qs)
+        if len(df) == 0:
+            return groups, order, 0.0, 0.0, 0
+        return groups, order, float(df.timestamp.iloc[0]), float(df.timestamp.iloc[-1]), len(df)
+
     def window_reduce(self, ends, delta):
         import io
         import types

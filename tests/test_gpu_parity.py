@@ -435,3 +435,45 @@ def test_side_sources_device_errors_and_no_data(tmp_path):
     assert not os.path.isfile(d + "nvsmi_trace.csv")
     js = open(d + "report.js").read()
     assert "nvsmi_sm =" not in js and "mpstat_usr =" in js and "tx_bandwidth =" in js
+
+
+@pytest.mark.parametrize("name", sorted(d for d in os.listdir(os.path.join(os.path.dirname(__file__), "golden")) if d.startswith("side_")))
+def test_nvsmi_profile_device_matches_reference(name, tmp_path, capsys):
+    from test_side_host import run_nvsmi_case
+    from sofa_b200.engine import CudaEngine
+    eng = CudaEngine(0)
+    try:
+        run_nvsmi_case(name, tmp_path, eng, capsys)
+    finally:
+        eng.close()
+
+
+def test_nvsmi_profile_device_matches_oracle_larger_and_roi(tmp_path):
+    """200 k rows, 8 devices whose first appearance is not in id order, negative and large durations,
+    with and without the spotlight region of interest."""
+    import random
+    import pandas as pd
+    from sofa_b200.engine import CudaEngine
+    from sofa_b200 import sofa_analyze as an
+    rng = random.Random(7)
+    logdir = str(tmp_path) + "/"
+    devs = [5, 1, 9, 0, 12, 3, 8, 2]
+    with open(logdir + "nvsmi_trace.csv", "w") as f:
+        f.write("timestamp,event,duration,deviceId,copyKind,payload,bandwidth,pkt_src,pkt_dst,pid,tid,name,category\n")
+        for ev in (0, 1):
+            for s_ in range(12500):
+                for d in devs:
+                    v = rng.choice([rng.randrange(0, 101), rng.randrange(-5, 3), rng.randrange(0, 1000000)])
+                    f.write("%.6f,%d,%d,%d,-1,-1,-1,-1,-1,-1,-1,GPUID_x=%d_%d,%d\n" % (0.5 + s_ * 0.1, ev, v, d, d, v, d))
+    df = pd.read_csv(logdir + "nvsmi_trace.csv")
+    eng = CudaEngine(0)
+    try:
+        for roi in (None, (100.0, 733.3)):
+            cfg = default_report_config(logdir)
+            if roi:
+                cfg.spotlight_gpu, cfg.roi_begin, cfg.roi_end = True, roi[0], roi[1]
+            got = an.nvsmi_profile(logdir, cfg, eng, [])
+            want = orc.nvsmi_profile(df, spotlight_gpu=bool(roi), roi_begin=roi[0] if roi else 0, roi_end=roi[1] if roi else 0)
+            assert [(n, float(v)) for n, v in got] == [(n, float(v)) for n, v in want]
+    finally:
+        eng.close()

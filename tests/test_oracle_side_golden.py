@@ -34,3 +34,11 @@ def test_oracle_side_preprocess_matches_reference(name, tmp_path):
     orc.preprocess(orc.OracleConfig(logdir, nprocs=1), demangle=demangle)
     for fn in SIDE_OUTPUTS:
         assert open(logdir + fn, "rb").read() == golden_bytes(name, fn), fn
+
+
+@pytest.mark.parametrize("name", SIDE)
+def test_oracle_nvsmi_profile_matches_reference(name):
+    d = os.path.join(GOLDEN, name)
+    case = json.load(open(os.path.join(d, "case.json")))
+    feats = orc.nvsmi_profile(pd.read_csv(d + "/nvsmi_trace.csv"))
+    assert [(n, float(v)) for n, v in feats] == [tuple(x) for x in case["nvsmi_features"][1:]]

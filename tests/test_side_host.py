@@ -33,3 +33,23 @@ def run_case(name, tmp_path, engine):
 @pytest.mark.parametrize("name", SIDE)
 def test_concurrency_breakdown_host_logic(name, tmp_path):
     run_case(name, tmp_path, HostSimEngine())
+
+
+def run_nvsmi_case(name, tmp_path, engine, capsys):
+    """nvsmi_profile (a17) host logic: features and the verbose tables against the reference's."""
+    d = os.path.join(GOLDEN, name)
+    case = json.load(open(os.path.join(d, "case.json")))
+    logdir = str(tmp_path) + "/"
+    shutil.copy(os.path.join(d, "nvsmi_trace.csv"), logdir + "nvsmi_trace.csv")
+    cfg = default_report_config(logdir)
+    cfg.verbose = True
+    capsys.readouterr()
+    feats = an.nvsmi_profile(logdir, cfg, engine, [('elapsed_time', 12.5)])
+    out = capsys.readouterr().out
+    assert [(n, float(v)) for n, v in feats] == [tuple(x) for x in case["nvsmi_features"]]
+    assert out == open(os.path.join(d, "nvsmi_profile_verbose.txt")).read()
+
+
+@pytest.mark.parametrize("name", SIDE)
+def test_nvsmi_profile_host_logic(name, tmp_path, capsys):
+    run_nvsmi_case(name, tmp_path, HostSimEngine(), capsys)
