@@ -32,7 +32,7 @@ enum { SOFA_SRC_PERF = 0, SOFA_SRC_GPU = 1, SOFA_SRC_NET = 2,
        /* 13-column trace CSV bodies read by concurrency_breakdown (upload + parse like a source) */
        SOFA_SRC_MPSTAT_CSV = 3, SOFA_SRC_NVSMI_CSV = 4, SOFA_SRC_NETSTAT_CSV = 5,
        /* recorder side files as written by `sofa record` (upload, then sofa_b200_side_preprocess) */
-       SOFA_RAW_MPSTAT = 6, SOFA_RAW_NVSMI_QUERY = 7, SOFA_RAW_NETSTAT = 8 };
+       SOFA_RAW_MPSTAT = 6, SOFA_RAW_NVSMI_QUERY = 7, SOFA_RAW_NETSTAT = 8, SOFA_RAW_VMSTAT = 9, SOFA_RAW_NVSMI_DMON = 10 };
 
 typedef struct sofa_ctx sofa_ctx;
 
@@ -187,15 +187,18 @@ typedef struct {
 int sofa_b200_nvsmi_profile(sofa_ctx*, int use_roi, double roi_begin, double roi_end, sofa_nvsmi_group_t* groups,
                             uint32_t cap, uint32_t* n_groups, int32_t* dev_order, uint32_t* n_dev, double* ts_first,
                             double* ts_last, uint64_t* n_used);
-/* Recorder side files -> rows of mpstat.csv + usr_sys.csv (sofa_preprocess.py:482-546),
- * nvsmi_trace.csv (:1013-1084) and netstat.csv + netbandwidth.csv (:1235-1337), and the records
- * of their report.js series (mpstat_usr; nvsmi_sm / nvsmi_mem; tx_bandwidth / rx_bandwidth).
+/* Recorder side files -> rows of mpstat.csv + usr_sys.csv (sofa_preprocess.py:482-546), vmstat.csv
+ * (:787-1008), nvsmi_trace.csv (nvsmi_query.txt :1013-1084; nvsmi.txt enc/dec rows :1092-1183) and
+ * netstat.csv + netbandwidth.csv (:1235-1337), and the records of their report.js series (mpstat_usr;
+ * vmstat_*; nvsmi_sm / nvsmi_mem / nvsmi_enc / nvsmi_dec; tx_bandwidth / rx_bandwidth).
  * Upload the file with sofa_b200_upload (nvsmi_query.txt: data_off = after its first line, which
  * the reference skips), then call sofa_b200_side_preprocess once and the emitters as needed.
  *   n_lines : lines parsed;  n_cand : candidate rows per list (mpstat: rows of mpstat[1:], some of
- *   which are dropped or go to usr_sys.csv; nvsmi: one sm + one mem row per line; netstat: one tx +
- *   one rx row per line after the first);  no_data : nvidia-smi reported a failure (:1017-1021).
- * list: 0 = sm / tx (and mpstat), 1 = mem / rx.  CSV and aux bodies go to output buffer 0, JSON
+ *   which are dropped or go to usr_sys.csv; nvsmi_query: one sm + one mem row per line; netstat: one tx +
+ *   one rx row per line after the first; vmstat: eight rows per accepted line; nvsmi.txt: one enc + one
+ *   dec row per accepted line, those of the first seconds dropped);  no_data : nvidia-smi reported a
+ *   failure (:1017-1021, :1095-1099).
+ * list: 0 = sm / tx / enc (and mpstat), 1 = mem / rx / dec; vmstat 0..7 = bi, bo, in, cs, wa, st, usr, sys.  CSV and aux bodies go to output buffer 0, JSON
  * records to output buffer 1 (fetch as usual).  aux = usr_sys.csv / netbandwidth.csv body. */
 typedef struct {
     double time_base;            /* cfg.time_base */

@@ -306,6 +306,58 @@ def preprocess_netstat(logdir, absolute_timestamp, time_base):
     return tx_traces, rx_traces
 
 
+def preprocess_vmstat(logdir, absolute_timestamp, time_base):
+    """vmstat.txt -> vmstat.csv (bi, bo, in, cs, wa, st, usr, sys lists).  sofa_preprocess.py:787-1008.
+    Returns the eight frames in that order."""
+    with open(logdir + 'vmstat.txt') as f:
+        lines = f.readlines()
+    lists = [[] for _ in range(8)]
+    cols = (8, 9, 10, 11, 15, 16, 12, 13)
+    keys = ('r', 'b', 'sw', 'fr', 'bu', 'ca', 'si', 'so', 'bi', 'bo', 'in', 'cs', 'usr', 'sys', 'idl', 'wa', 'st')
+    t = 0
+    for line in lines:
+        if line.find('procs') == -1 and line.find('swpd') == -1:
+            fields = line.split()
+            if len(fields) < 17:
+                continue
+            vm = [float(fields[k]) + 1e-5 for k in range(17)]
+            t_begin = t + time_base if absolute_timestamp else t
+            info = '|'.join('%s=%s' % (k, str(int(v))) for k, v in zip(keys, vm))
+            for lst, c in zip(lists, cols):
+                lst.append([t_begin, -1, vm[c], -1, -1, -1, -1, -1, -1, -1, -1, info, -1])
+            t = t + 1
+    return [_to_csv_list(lst, logdir + 'vmstat.csv', 'w' if i == 0 else 'a') for i, lst in enumerate(lists)]
+
+
+def preprocess_nvsmi_dmon(logdir, absolute_timestamp, time_base):
+    """nvsmi.txt (`nvidia-smi dmon -s u`) -> enc / dec rows appended to nvsmi_trace.csv.
+    sofa_preprocess.py:1092-1183.  Returns (enc frame, dec frame, nvsmi_data flag)."""
+    with open(logdir + 'nvsmi.txt') as f:
+        lines = f.readlines()
+    for line in lines:
+        if line.find('failed') != -1 or line.find('Failed') != -1:
+            return [], [], False
+    enc_list, dec_list = [], []
+    t = 0
+    for line in lines:
+        if line.find('gpu') == -1 and line.find('Idx') == -1:
+            fields = line.split()
+            if len(fields) < 5:
+                continue
+            gid = int(fields[0])
+            enc = int(0) if fields[3] == '-' else int(fields[3])
+            dec = int(0) if fields[4] == '-' else int(fields[4])
+            t_begin = t + time_base if absolute_timestamp else t
+            if t > 3:
+                enc_list.append([t_begin, 2, enc, gid, -1, -1, -1, -1, -1, -1, -1, "GPUID_enc=%d_%d" % (gid, enc), gid])
+                dec_list.append([t_begin, 3, dec, gid, -1, -1, -1, -1, -1, -1, -1, "GPUID_dec=%d_%d" % (gid, dec), gid])
+            if gid == 0:
+                t = t + 1
+    if not enc_list:
+        return [], [], False
+    return _to_csv_list(enc_list, logdir + 'nvsmi_trace.csv', 'a'), _to_csv_list(dec_list, logdir + 'nvsmi_trace.csv', 'a'), True
+
+
 # --------------------------------------------------------------------------- driver
 class OracleConfig:
     """The cfg attributes the hot path reads (bin/sofa:159-312 defaults)."""
@@ -390,8 +442,16 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
     mpstat_traces, nvsmi_sm, nvsmi_mem, tx_traces, rx_traces = [], [], [], [], []
     if os.path.isfile(logdir + 'mpstat.txt'):
         mpstat_traces = preprocess_mpstat(logdir, cfg.absolute_timestamp, time_base)
+    vm = [[] for _ in range(8)]
+    nvsmi_enc, nvsmi_dec = [], []
+    if os.path.isfile(logdir + 'vmstat.txt'):
+        with open(logdir + 'vmstat.txt') as f:
+            if len(f.readlines()) > 0:                                    # :791
+                vm = preprocess_vmstat(logdir, cfg.absolute_timestamp, time_base)
     if os.path.isfile(logdir + 'nvsmi_query.txt'):
         nvsmi_sm, nvsmi_mem = preprocess_nvsmi_query(logdir, cfg.absolute_timestamp, time_base, cfg.nvsmi_time_zone)
+    if os.path.isfile(logdir + 'nvsmi.txt'):
+        nvsmi_enc, nvsmi_dec, cfg.nvsmi_data = preprocess_nvsmi_dmon(logdir, cfg.absolute_timestamp, time_base)
     if os.path.isfile(logdir + 'netstat.txt'):
         tx_traces, rx_traces = preprocess_netstat(logdir, cfg.absolute_timestamp, time_base)
 
@@ -469,26 +529,29 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
         series.append(Series('cpu_trace', 'CPU', 'DarkGray', cpu_viz))
         for kw, color, grp in filtered_cpu:
             series.append(Series(kw, '[keyword]' + kw, color, grp.copy()))
-    for nm, title, color in (('blktrace_starting_block', 'BLKTRACE_STARTING_BLOCK', 'Green'),
-                             ('blktrace_time', 'BLKTRACE_TIME', 'DodgerBlue'),
-                             ('vmstat_cs', 'VMSTAT_CS', 'Pink'),
-                             ('vmstat_bi', 'VMSTAT_BI', 'DarkOrange'),
-                             ('vmstat_bo', 'VMSTAT_BO', 'DarkOrchid')):
-        series.append(Series(nm, title, color, []))
+    vm_bi, vm_bo, vm_in, vm_cs, vm_wa, vm_st, vm_usr, vm_sys = vm
+    for nm, title, color, data in (('blktrace_starting_block', 'BLKTRACE_STARTING_BLOCK', 'Green', []),
+                                   ('blktrace_time', 'BLKTRACE_TIME', 'DodgerBlue', []),
+                                   ('vmstat_cs', 'VMSTAT_CS', 'Pink', vm_cs),
+                                   ('vmstat_bi', 'VMSTAT_BI', 'DarkOrange', vm_bi),
+                                   ('vmstat_bo', 'VMSTAT_BO', 'DarkOrchid', vm_bo)):
+        series.append(Series(nm, title, color, data))
     if cfg.enable_mpstat:
         series.append(Series('mpstat_usr', 'MPSTAT_USR', 'Cyan', mpstat_traces))
     if cfg.enable_diskstat:
         series.append(Series('diskstat', 'DISKSTAT', 'GreenYellow', [], y_field='bandwidth'))
-    if cfg.enable_vmstat:
-        for nm in ('vmstat_usr', 'vmstat_sys', 'vmstat_in', 'vmstat_cs'):
-            series.append(Series(nm, nm.upper(), '', []))
+    if cfg.enable_vmstat:                                                   # :1964-1999
+        series.append(Series('vmstat_usr', 'CPU_USAGE_USR', 'Magenta', vm_usr))
+        series.append(Series('vmstat_sys', 'CPU_USAGE_SYS', 'LightBlue', vm_sys))
+        series.append(Series('vmstat_in', 'VMSTAT_IN', 'DarkMagenta', vm_in))
+        series.append(Series('vmstat_cs', 'VMSTAT_CS', 'DarkOliveGreen', vm_cs))
     for nm in ('strace', 'pystacks'):
         series.append(Series(nm, nm, '', []))
     series.append(Series('nvsmi_mem', 'GPU_MEM_Util.', 'lightblue', nvsmi_mem))
     series.append(Series('nvsmi_sm', 'GPU_SM_Util.', 'red', nvsmi_sm))
-    if cfg.enable_encode_decode:
-        series.append(Series('nvsmi_enc', '', '', []))
-        series.append(Series('nvsmi_dec', '', '', []))
+    if cfg.enable_encode_decode:                                            # :2033-2050
+        series.append(Series('nvsmi_enc', 'GPU_ENC_Util.', 'rgba(255, 215, 0, 0.8)', nvsmi_enc))
+        series.append(Series('nvsmi_dec', 'GPU_DEC_Util.', 'rgba(218, 165, 32, 0.8)', nvsmi_dec))
     series.append(Series('net_trace', 'NET', 'blue', net_traces))
     series.append(Series('tx_bandwidth', 'tx Bandwidth', 'rgba(135,206,250,0.8)', tx_traces, y_field='bandwidth'))
     series.append(Series('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)', rx_traces, y_field='bandwidth'))

@@ -15,7 +15,7 @@ struct DictView { int n; const uint64_t* hash; const uint64_t* off; const char* 
 
 // rows derived from a recorder side file: candidate c + base addresses row (c + base) % n_half of
 // list (c + base) / n_half (nvsmi: sm, mem; netstat: tx, rx; mpstat: one list)
-struct SideView { int table; uint64_t n_half, base; SideOutCols o; };
+struct SideView { int table, absolute; uint64_t n_half, base; SideOutCols o; };
 
 struct SrcView {
     SideView side;
@@ -86,9 +86,9 @@ __device__ __forceinline__ void with_row(const SrcView& s, uint64_t row, uint64_
         f(v, ng);
     } else if constexpr (KIND == SRC_SIDEOUT) {
         const uint64_t cc = cand + s.side.base;
-        const int half = cc >= s.side.n_half ? 1 : 0;
-        SideName ng{s.side.table, half, load_sideout(s.side.o, half ? cc - s.side.n_half : cc)};
-        RowVals v = vals_side(s.side.table, half, ng.r);
+        const int list = (int)(cc / s.side.n_half);
+        SideName ng{s.side.table, list, load_sideout(s.side.o, cc - (uint64_t)list * s.side.n_half)};
+        RowVals v = vals_side(s.side.table, list, s.side.absolute, ng.r);
         f(v, ng);
     } else {
         NetRow r = load_net(s, row);

@@ -25,7 +25,7 @@ struct NetCols { double* ts; int64_t *payload, *src, *dst; uint8_t* proto; };
 
 struct SideCols { double *ts, *event, *dur, *dev, *bw; int32_t* ratios; };      // ratios: 5 per row
 
-// raw recorder side files (side.cuh): f = 9 doubles per line, i = 4 int64 per line, nf = field count
+// raw recorder side files (side.cuh): f = RAW_NF doubles per line, i = 4 int64 per line, nf = field count
 // (-1: the line says "failed" - nvidia-smi query error)
 struct RawCols { double* f; int64_t* i; int32_t* nf; };
 
@@ -194,9 +194,11 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
                 RawRow r = RawRow();
                 if (cfg.side_table == RAW_MPSTAT) code = parse_raw_mpstat(line, n, &r);
                 else if (cfg.side_table == RAW_NVSMI) code = parse_raw_nvsmi(line, n, has_nl, &r);
-                else code = parse_raw_netstat(line, n, &r);
+                else if (cfg.side_table == RAW_NETSTAT) code = parse_raw_netstat(line, n, &r);
+                else if (cfg.side_table == RAW_VMSTAT) code = parse_raw_vmstat(line, n, &r);
+                else code = parse_raw_dmon(line, n, &r);
                 if (code == E_OK) {
-                    for (int q = 0; q < 9; q++) cols.r.f[row * 9 + q] = r.f[q];
+                    for (int q = 0; q < RAW_NF; q++) cols.r.f[row * RAW_NF + q] = r.f[q];
                     for (int q = 0; q < 4; q++) cols.r.i[row * 4 + q] = r.i[q];
                     cols.r.nf[row] = r.flag ? -1 : r.nf;
                 }

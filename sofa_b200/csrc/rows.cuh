@@ -676,6 +676,7 @@ struct RowVals {
     bool valid;              // false: the all-NaN row a `[]` record becomes
     double ts, dur;          // columns 0, 2 (float; the recorder side tables print an int duration: dur_i)
     bool dur_is_f; int64_t dur_i;
+    bool ts_is_f; int64_t ts_i;          // vmstat / nvidia-smi dmon rows count seconds: an int column unless absolute
     int64_t cat;             // column 12 (0 for the trace sources)
     bool ev_is_f; double ev_f; int64_t ev_i;       // column 1
     int64_t dev, kind, payload;                     // 3, 4, 5
@@ -684,18 +685,18 @@ struct RowVals {
     // 11 = name (generator), 12 = category (always 0)
 };
 SOFA_HD RowVals vals_perf(const PerfRow& r) {
-    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.dur_is_f = true; v.dur_i = 0; v.cat = 0; v.ev_is_f = true; v.ev_f = r.event; v.ev_i = 0;
+    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.dur_is_f = true; v.dur_i = 0; v.ts_is_f = true; v.ts_i = 0; v.cat = 0; v.ev_is_f = true; v.ev_f = r.event; v.ev_i = 0;
     v.dev = -1; v.kind = -1; v.payload = 0; v.bw_is_f = false; v.bw_f = 0; v.bw_i = 0;
     v.src = -1; v.dst = -1; v.pid = r.pid; v.tid = r.tid; return v;
 }
 SOFA_HD RowVals vals_gpu(const GpuRow& r, int n_cudaproc) {
-    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.dur_is_f = true; v.dur_i = 0; v.cat = 0; v.ev_is_f = false; v.ev_f = 0;
+    RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.dur_is_f = true; v.dur_i = 0; v.ts_is_f = true; v.ts_i = 0; v.cat = 0; v.ev_is_f = false; v.ev_f = 0;
     v.ev_i = r.payload * 100 + 17;                                   // :329
     v.dev = r.dev; v.kind = r.kind; v.payload = r.payload; v.bw_is_f = r.bw_is_float != 0; v.bw_f = r.bw; v.bw_i = 0;
     v.src = r.src; v.dst = r.dst; v.pid = n_cudaproc; v.tid = r.tid; return v;
 }
 SOFA_HD RowVals vals_net(const NetRow& r) {
-    RowVals v; v.valid = r.proto != 0; v.ts = r.ts; v.dur_is_f = true; v.dur_i = 0; v.cat = 0;
+    RowVals v; v.valid = r.proto != 0; v.ts = r.ts; v.dur_is_f = true; v.dur_i = 0; v.ts_is_f = true; v.ts_i = 0; v.cat = 0;
     v.dur = d_div((double)r.payload, 128.0e6);                       // :178
     v.ev_is_f = false; v.ev_f = 0; v.ev_i = r.payload * 100 + 17;
     v.dev = -1; v.kind = -1; v.payload = r.payload; v.bw_is_f = true; v.bw_f = 128.0e6; v.bw_i = 0;
@@ -706,7 +707,7 @@ SOFA_HD RowVals vals_net(const NetRow& r) {
 SOFA_HD void col_value(const RowVals& v, int c, uint32_t fmask, bool* isf, double* f, int64_t* i) {
     bool nat_f = false; double nf = 0; int64_t ni = 0;
     switch (c) {
-        case 0: nat_f = true; nf = v.ts; break;
+        case 0: nat_f = v.ts_is_f; nf = v.ts; ni = v.ts_i; break;
         case 1: nat_f = v.ev_is_f; nf = v.ev_f; ni = v.ev_i; break;
         case 2: nat_f = v.dur_is_f; nf = v.dur; ni = v.dur_i; break;
         case 3: ni = v.dev; break;

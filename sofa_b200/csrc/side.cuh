@@ -10,14 +10,17 @@
 
 namespace sofa {
 
-enum { RAW_MPSTAT = 0, RAW_NVSMI = 1, RAW_NETSTAT = 2 };
+enum { RAW_MPSTAT = 0, RAW_NVSMI = 1, RAW_NETSTAT = 2, RAW_VMSTAT = 3, RAW_DMON = 4 };
+constexpr int RAW_NF = 17;           // doubles kept per parsed line (vmstat has 17 columns)
 
 // One parsed line of a side file.
 //   mpstat : f[0..8] = the nine float fields, nf = number of ',' separated fields (0: blank line)
 //   nvsmi  : i[0] = seconds since 1970-01-01 of the naive stamp read as UTC, i[1] = microseconds,
-//            i[2] = index | sm << 16 | mem << 40 is NOT used - see fields below
+//            i[2] = gpu index, i[3] = sm %, f[0] = mem %
 //   netstat: f[0] = time, i[0] = tx bytes, i[1] = rx bytes
-struct RawRow { double f[9]; int64_t i[4]; int32_t nf; int32_t flag; };
+//   vmstat : f[0..16] = the 17 columns of `vmstat -w 1`, nf = 17 (0: header or short line, skipped)
+//   dmon   : i[0] = gpu index, i[1] = enc %, i[2] = dec % of `nvidia-smi dmon -s u`, nf = 5 (0: skipped)
+struct RawRow { double f[RAW_NF]; int64_t i[4]; int32_t nf; int32_t flag; };
 
 // ---------------------------------------------------------------------------- mpstat.txt
 // np.genfromtxt(delimiter=',', invalid_raise=False) (:484): comments ('#') are cut, the line is
@@ -74,6 +77,7 @@ SOFA_HD int parse_raw_mpstat(S s, int n, RawRow* r) {
 }
 
 struct SideOutRow {
+    const double* ext;       // vmstat: the line's 17 parsed columns (durations and name ints are derived on the fly)
     double ts, f1, f2;       // mpstat: f1 = cpu_time (trace row) or usr (usr_sys row), f2 = sys; netstat: tx, rx bandwidth
     int64_t i[6];            // mpstat: core, usr, sys, idl, iow, irq (the %3d ints); nvsmi: id, sm, mem; netstat: int(tx), int(rx)
     int cls;                 // 0 dropped, 1 trace row, 2 usr_sys.csv row
@@ -95,7 +99,7 @@ SOFA_HD int side_mpstat_row(const double* cur, const double* prev, int absolute,
     for (int k = 0; k < 9; k++) d[k] = d_sub(cur[k], prev[k]);
     if (d_isnan(d[2]) || d_isnan(d[4]) || d_isnan(d[5]) || d_isnan(d[6]) || d_isnan(d[7])) return E_FORMAT;   // '%3d' % nan raises
     double total = d_add(d_add(d_add(d_add(d[2], d[4]), d[5]), d[6]), d[7]);
-    o->cls = 0;
+    o->cls = 0; o->ext = nullptr;
     if (total == 0.0) return E_OK;                                           // "No increases in mpstat values"
     double usr = d_div(d_mul(d[2], 100.0), total), sys = d_div(d_mul(d[4], 100.0), total);
     double idl = d_div(d_mul(d[5], 100.0), total), iow = d_div(d_mul(d[6], 100.0), total);
@@ -192,7 +196,7 @@ SOFA_HD void side_nvsmi_row(const RawRow& r, int64_t local_off, double tz_add, i
     double t = d_add((double)(r.i[0] - local_off), d_div((double)r.i[1], 1e6));
     t = d_add(t, tz_add);
     o->ts = absolute ? t : d_sub(t, time_base);
-    o->f1 = 0; o->f2 = 0;
+    o->ext = nullptr; o->f1 = 0; o->f2 = 0;
     o->i[0] = r.i[2]; o->i[1] = r.i[3]; o->i[2] = (int64_t)r.f[0];
     o->i[3] = o->i[4] = o->i[5] = 0;
     o->cls = 1;
@@ -228,24 +232,95 @@ SOFA_HD int side_netstat_row(const RawRow& cur, const RawRow& prev, int absolute
     e = trunc_i64(o->f2, &o->i[1]); if (e) return e;
     o->i[2] = o->i[3] = o->i[4] = o->i[5] = 0;
     o->ts = absolute ? cur.f[0] : d_sub(cur.f[0], time_base);
-    o->cls = 1;
+    o->ext = nullptr; o->cls = 1;
     return E_OK;
 }
 
+// ---------------------------------------------------------------------------- vmstat.txt (:787-1008)
+template <typename S>
+SOFA_HD bool line_contains(S s, int n, const char* w) {
+    int L = 0; while (w[L]) L++;
+    for (int i = 0; i + L <= n; i++) {
+        bool eq = true;
+        for (int k = 0; k < L; k++) if (s[i + k] != w[k]) { eq = false; break; }
+        if (eq) return true;
+    }
+    return false;
+}
+SOFA_HD int parse_raw_vmstat(const char* s, int n, RawRow* r) {
+    r->nf = 0; r->flag = 0;
+    if (line_contains(s, n, "procs") || line_contains(s, n, "swpd")) return E_OK;       // header lines (:810)
+    Tok t[17];
+    if (tokenize(s, n, t, 17) < 17) return E_OK;                                       // :813
+    for (int q = 0; q < 17; q++) {
+        int st = parse_double(s + t[q].a, t[q].b - t[q].a, &r->f[q]);
+        if (st) return num_status_to_err(st, true);
+    }
+    r->nf = 17;
+    return E_OK;
+}
+// accepted line number j (the reference's counter t); validates every value the name prints
+SOFA_HD int side_vmstat_row(int64_t j, const double* ext, int absolute, double time_base, SideOutRow* o) {
+    for (int q = 0; q < 17; q++) { int64_t v; int e = trunc_i64(d_add(ext[q], 1e-5), &v); if (e) return e; }
+    o->ext = ext; o->f1 = 0; o->f2 = 0; o->cls = 1;
+    o->i[0] = j; o->i[1] = o->i[2] = o->i[3] = o->i[4] = o->i[5] = 0;
+    o->ts = absolute ? d_add((double)j, time_base) : (double)j;
+    return E_OK;
+}
+// list order of vmstat.csv (bi, bo, in, cs, wa, st, usr, sys: :994-1008) -> column of `vmstat -w`
+SOFA_HD int vmstat_list_col(int list) { const int c[8] = {8, 9, 10, 11, 15, 16, 12, 13}; return c[list & 7]; }
+
+// ---------------------------------------------------------------------------- nvsmi.txt, `nvidia-smi dmon -s u` (:1092-1183)
+SOFA_HD int parse_raw_dmon(const char* s, int n, RawRow* r) {
+    r->nf = 0; r->flag = 0;
+    if (line_contains(s, n, "failed") || line_contains(s, n, "Failed")) r->flag = 1;
+    if (line_contains(s, n, "gpu") || line_contains(s, n, "Idx")) return E_OK;            // header lines (:1108)
+    Tok t[5];
+    if (tokenize(s, n, t, 5) < 5) return E_OK;
+    int st = parse_i64(s + t[0].a, t[0].b - t[0].a, &r->i[0]);
+    if (st) return num_status_to_err(st, false);
+    for (int q = 0; q < 2; q++) {
+        const Tok& k = t[3 + q];
+        if (k.b - k.a == 1 && s[k.a] == '-') { r->i[1 + q] = 0; continue; }
+        st = parse_i64(s + k.a, k.b - k.a, &r->i[1 + q]);
+        if (st) return num_status_to_err(st, false);
+    }
+    if (r->i[0] < -2147483647 || r->i[0] > 2147483647) return E_RANGE;
+    r->nf = 5;
+    return E_OK;
+}
+// t = number of earlier accepted lines whose gpu index is 0 (the reference's counter, :1172-1173)
+SOFA_HD void side_dmon_row(int64_t t, const RawRow& r, int absolute, double time_base, SideOutRow* o) {
+    o->ext = nullptr; o->f1 = 0; o->f2 = 0; o->cls = t > 3 ? 1 : 0;                      // rows of the first seconds are dropped
+    o->i[0] = r.i[0]; o->i[1] = r.i[1]; o->i[2] = r.i[2]; o->i[3] = t; o->i[4] = o->i[5] = 0;
+    o->ts = absolute ? d_add((double)t, time_base) : (double)t;
+}
+
 // ---------------------------------------------------------------------------- 13-column view
-// half: nvsmi 0 = sm list, 1 = mem list; netstat 0 = tx list, 1 = rx list
-SOFA_HD RowVals vals_side(int table, int half, const SideOutRow& r) {
-    RowVals v; v.valid = true; v.ts = r.ts; v.dur = 0; v.dur_is_f = false; v.dur_i = -1; v.cat = 0;
+// list: nvsmi 0 = sm, 1 = mem; netstat 0 = tx, 1 = rx; vmstat 0..7 = bi, bo, in, cs, wa, st, usr, sys; dmon 0 = enc, 1 = dec
+SOFA_HD RowVals vals_side(int table, int list, int absolute, const SideOutRow& r) {
+    RowVals v; v.valid = true; v.ts = r.ts; v.ts_is_f = true; v.ts_i = 0; v.dur = 0; v.dur_is_f = false; v.dur_i = -1; v.cat = 0;
     v.ev_is_f = false; v.ev_f = 0; v.ev_i = -1;
     v.dev = -1; v.kind = -1; v.payload = -1; v.bw_is_f = false; v.bw_f = 0; v.bw_i = -1;
     v.src = -1; v.dst = -1; v.pid = -1; v.tid = -1;
     if (table == RAW_MPSTAT) { v.dur_is_f = true; v.dur = r.f1; v.dev = r.i[0]; }
-    else if (table == RAW_NVSMI) { v.ev_i = half; v.dur_i = half ? r.i[2] : r.i[1]; v.dev = r.i[0]; v.cat = r.i[0]; }
-    else { v.ev_i = half; v.bw_is_f = true; v.bw_f = half ? r.f2 : r.f1; }
+    else if (table == RAW_NVSMI) { v.ev_i = list; v.dur_i = list ? r.i[2] : r.i[1]; v.dev = r.i[0]; v.cat = r.i[0]; }
+    else if (table == RAW_NETSTAT) { v.ev_i = list; v.bw_is_f = true; v.bw_f = list ? r.f2 : r.f1; }
+    else if (table == RAW_VMSTAT) {
+        v.ts_is_f = absolute != 0; v.ts_i = r.i[0]; v.dur_is_f = true; v.dur = d_add(r.ext[vmstat_list_col(list)], 1e-5); v.cat = -1;
+    } else {
+        v.ts_is_f = absolute != 0; v.ts_i = r.i[3]; v.ev_i = 2 + list; v.dur_i = list ? r.i[2] : r.i[1]; v.dev = r.i[0]; v.cat = r.i[0];
+    }
     return v;
 }
 // float-column mask of the file (pandas dtype of each DataFrame column)
-SOFA_HD uint32_t side_fmask(int table) { return table == RAW_MPSTAT ? 0xDu : (table == RAW_NVSMI ? 0x1u : 0x41u); }
+SOFA_HD uint32_t side_fmask(int table, int absolute) {
+    if (table == RAW_MPSTAT) return 0xDu;
+    if (table == RAW_NVSMI) return 0x1u;
+    if (table == RAW_NETSTAT) return 0x41u;
+    if (table == RAW_VMSTAT) return 0x4u | (absolute ? 1u : 0u);
+    return absolute ? 1u : 0u;
+}
 
 template <class K> SOFA_HD void put_pad3(K& k, int64_t v) {                   // '%3d'
     int l = len_i64(v);
@@ -260,8 +335,14 @@ struct SideName {
             for (int q = 1; q <= 5; q++) { put_pad3(k, r.i[q]); k.put('|'); }
         } else if (table == RAW_NVSMI) {                                       // :1046-1047
             put_lit(k, half ? "GPUID_mem=" : "GPUID_sm="); put_i64(k, r.i[0]); k.put('_'); put_i64(k, half ? r.i[2] : r.i[1]);
-        } else {                                                               // :1287, 1304
+        } else if (table == RAW_NETSTAT) {                                     // :1287, 1304
             put_lit(k, half ? "network_bandwidth_rx(bytes):" : "network_bandwidth_tx(bytes):"); put_i64(k, half ? r.i[1] : r.i[0]);
+        } else if (table == RAW_VMSTAT) {                                      // :850-866
+            const char* keys[17] = {"r=", "|b=", "|sw=", "|fr=", "|bu=", "|ca=", "|si=", "|so=", "|bi=", "|bo=", "|in=", "|cs=",
+                                    "|usr=", "|sys=", "|idl=", "|wa=", "|st="};
+            for (int q = 0; q < 17; q++) { put_lit(k, keys[q]); put_i64(k, (int64_t)d_add(r.ext[q], 1e-5)); }
+        } else {                                                               // :1132-1133
+            put_lit(k, half ? "GPUID_dec=" : "GPUID_enc="); put_i64(k, r.i[0]); k.put('_'); put_i64(k, half ? r.i[2] : r.i[1]);
         }
     }
 };

@@ -55,7 +55,7 @@ struct Source {
     uint32_t flags_stride[2] = {0, 0}, flags_val[2] = {0, 0};      // cached sofa_b200_row_flags results
     DevBuf vizhash, viz_id; uint32_t viz_stride = 0; bool viz_ready = false;
     DevBuf dict_hash, dict_off, dict_blob; int dict_n = 0;
-    bool side_ready = false; uint64_t side_ncand = 0;          // raw side source: rows per list after sofa_b200_side_preprocess
+    bool side_ready = false; int side_absolute = 0; uint64_t side_ncand = 0;          // raw side source: rows per list after sofa_b200_side_preprocess
 };
 
 struct TimedEvent { int kind; cudaEvent_t a, b; };
@@ -63,7 +63,7 @@ struct TimedEvent { int kind; cudaEvent_t a, b; };
 struct sofa_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    Source src[9];                       // 0 perf, 1 gpu, 2 net, 3..5 side tables (mpstat, nvsmi, netstat CSV), 6..8 raw recorder side files
+    Source src[11];                      // 0 perf, 1 gpu, 2 net, 3..5 side tables (mpstat, nvsmi, netstat CSV), 6..10 raw recorder side files
     DevBuf out[3]; uint64_t out_n[3] = {0, 0, 0};
     // overlapped transfers: copy streams, the idle halves of the csv/json double buffers and the
     // D2H-complete event of each half
@@ -71,8 +71,8 @@ struct sofa_ctx {
     DevBuf out_alt[2];
     cudaEvent_t out_ev[2] = {nullptr, nullptr}, out_alt_ev[2] = {nullptr, nullptr};
     bool out_busy[2] = {false, false}, out_alt_busy[2] = {false, false};
-    cudaEvent_t up_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool up_pending[9] = {false, false, false, false, false, false, false, false, false};
+    cudaEvent_t up_ev[11] = {};
+    bool up_pending[11] = {};
     cudaEvent_t fetch_ev[16]; bool fetch_used[16]; int fetch_next = 0;
     DevBuf arena; uint64_t arena_cur = 0; bool arena_on = false;
     // small host<->device traffic goes through mapped pinned memory + a copy kernel, never the
@@ -249,7 +249,7 @@ static int alloc_cols(sofa_ctx* c, int k, uint64_t n) {
         ENSURE(s.cols[NC_TS], m * 8); ENSURE(s.cols[NC_PAYLOAD], m * 8); ENSURE(s.cols[NC_SRC], m * 8);
         ENSURE(s.cols[NC_DST], m * 8); ENSURE(s.cols[NC_PROTO], m);
     } else if (k >= 6) {
-        ENSURE(s.cols[0], m * 72); ENSURE(s.cols[1], m * 32); ENSURE(s.cols[2], m * 4);
+        ENSURE(s.cols[0], m * 8 * RAW_NF); ENSURE(s.cols[1], m * 32); ENSURE(s.cols[2], m * 4);
     } else {
         ENSURE(s.cols[SC_TS], m * 8); ENSURE(s.cols[SC_EVENT], m * 8); ENSURE(s.cols[SC_DUR], m * 8);
         ENSURE(s.cols[SC_DEV], m * 8); ENSURE(s.cols[SC_BW], m * 8); ENSURE(s.cols[SC_RATIOS], m * 20);
@@ -325,7 +325,7 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->out_ev[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_alt_ev[i], cudaEventDisableTiming)); }
-    for (int i = 0; i < 9; i++) CK(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 11; i++) CK(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 16; i++) { CK(cudaEventCreateWithFlags(&c->fetch_ev[i], cudaEventDisableTiming)); c->fetch_used[i] = false; }
     CK(cudaHostAlloc((void**)&c->stage_h, c->stage_cap, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&c->stage_d, c->stage_h, 0));
@@ -360,12 +360,12 @@ int sofa_b200_destroy(sofa_ctx* c) {
     if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
     if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
     for (int i = 0; i < 2; i++) { if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); if (c->out_alt_ev[i]) cudaEventDestroy(c->out_alt_ev[i]); c->out_alt[i].release(); }
-    for (int i = 0; i < 9; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
+    for (int i = 0; i < 11; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
     for (int i = 0; i < 16; i++) cudaEventDestroy(c->fetch_ev[i]);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& e : c->pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
-    for (int k = 0; k < 9; k++) {
+    for (int k = 0; k < 11; k++) {
         Source& s = c->src[k];
         s.text.release(); s.mhz.release(); s.mask.release(); s.vizhash.release(); s.viz_id.release();
         s.dict_hash.release(); s.dict_off.release(); s.dict_blob.release();
@@ -391,7 +391,7 @@ void* sofa_b200_host_alloc(uint64_t nbytes) {
 void sofa_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
-    if (!c || k < 0 || k > 8 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload: bad argument");
+    if (!c || k < 0 || k > 10 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload: bad argument");
     if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload: data_off beyond the text");
     CK(cudaSetDevice(c->device));
     Source& s = c->src[k];
@@ -406,10 +406,10 @@ int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint
 }
 
 static uint32_t pick_tile_bytes(int k) { return (k == SRC_NET || k >= 3) ? 16384u : 24576u; }
-enum { RC_F = 0, RC_I, RC_NF, RC_IDX, RC_TS, RC_F1, RC_F2, RC_I6, RC_CLS, RC_MASK };      // column slots of a raw side source
+enum { RC_F = 0, RC_I, RC_NF, RC_IDX, RC_TS, RC_F1, RC_F2, RC_I6, RC_CLS, RC_MASK, RC_TCLOCK };      // column slots of a raw side source
 
 int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t* n_rows) {
-    if (!c || k < 0 || k > 8 || !p) FAIL(SOFA_ERR_ARG, "parse: bad argument");
+    if (!c || k < 0 || k > 10 || !p) FAIL(SOFA_ERR_ARG, "parse: bad argument");
     Source& s = c->src[k];
     if (!s.uploaded) FAIL(SOFA_ERR_STATE, "parse: nothing uploaded for this source");
     CK(cudaSetDevice(c->device));
@@ -668,7 +668,7 @@ int sofa_b200_fetch(sofa_ctx* c, int which, void* host_out, uint64_t cap) {
 }
 
 int sofa_b200_upload_async(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
-    if (!c || k < 0 || k > 8 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
+    if (!c || k < 0 || k > 10 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
     if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload_async: data_off beyond the text");
     CK(cudaSetDevice(c->device));
     Source& s = c->src[k];

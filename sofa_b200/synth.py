@@ -337,6 +337,34 @@ def write_side_raw(logdir, seed, n_samples=60, n_cores=4, n_gpus=2, rate_hz=10):
             f.write("%.6f,%d,%d\n" % (t, tx, rx))
 
 
+def write_side_raw_1hz(logdir, seed, n_seconds=30, n_gpus=2):
+    """vmstat.txt (`vmstat -w 1`) and nvsmi.txt (`nvidia-smi dmon -s u`) as the recorder captures them
+    (sofa_record.py:249-251, 300-302): one sample per second, headers repeated every 20 samples."""
+    os.makedirs(logdir, exist_ok=True)
+    with open(os.path.join(logdir, "vmstat.txt"), "w") as f:
+        for s in range(n_seconds):
+            if s % 20 == 0:
+                f.write("procs -----------------------memory---------------------- ---swap-- -----io---- -system-- --------cpu--------\n")
+                f.write(" r  b         swpd         free         buff        cache   si   so    bi    bo   in   cs  us  sy  id  wa  st\n")
+            r = rnd(seed, 10, s, 0)
+            us, sy = r % 60, (r >> 6) % 20
+            wa = (r >> 11) % 5
+            f.write("%2d %2d %12d %12d %12d %12d %4d %4d %5d %5d %4d %4d %3d %3d %3d %3d %3d\n" % (
+                (r >> 14) % 9, (r >> 18) % 3, 0, 100000000 + (r >> 20) % 5000000, 1234567, 23456789 + s * 1000,
+                0, 0, (r >> 24) % 5000, (r >> 36) % 90000, 100 + (r >> 44) % 9000, 200 + (r >> 50) % 9000,
+                us, sy, 100 - us - sy - wa, wa, 0))
+        f.write("  3  0\n")                                 # a truncated last line (recorder killed mid-write)
+    with open(os.path.join(logdir, "nvsmi.txt"), "w") as f:
+        for s in range(n_seconds):
+            if s % 20 == 0:
+                f.write("# gpu    sm   mem   enc   dec\n# Idx     %     %     %     %\n")
+            for g in range(n_gpus):
+                r = rnd(seed, 11, s * 16 + g, 0)
+                enc = "-" if (r >> 20) % 7 == 0 else str(r % 40)
+                dec = "-" if (r >> 24) % 5 == 0 else str((r >> 8) % 30)
+                f.write("%5d %5d %5d %5s %5s\n" % (g, (r >> 12) % 100, (r >> 30) % 100, enc, dec))
+
+
 def side_csv_bodies(seed, n_samples, n_cores, n_gpus, rate_hz=10):
     """Header-less bodies of mpstat.csv, nvsmi_trace.csv, netstat.csv in the format the reference's
     preprocess writes them (tests/golden/side_small), for concurrency_breakdown at scale."""

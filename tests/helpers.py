@@ -60,9 +60,14 @@ def build_case_logdir(name, tmpdir):
 
 
 SIDE_INPUTS = ("mpstat.txt", "nvsmi_query.txt", "netstat.txt", "perf.script", "sofa_time.txt", "perf_events_used.txt",
-               "perf_timebase.txt", "misc.txt")
+               "perf_timebase.txt", "misc.txt", "vmstat.txt", "nvsmi.txt")          # the last two only in some cases
 SIDE_OUTPUTS = ("mpstat.csv", "usr_sys.csv", "nvsmi_trace.csv", "netstat.csv", "netbandwidth.csv", "cputrace.csv",
-                "report.js")
+                "report.js", "vmstat.csv")
+PREPROCESS_CFG_KEYS = ("absolute_timestamp", "enable_vmstat", "enable_encode_decode", "nvsmi_time_zone")
+
+
+def preprocess_overrides(case):
+    return {k: v for k, v in case["cfg"].items() if k in PREPROCESS_CFG_KEYS}
 
 
 def side_cases():
@@ -79,5 +84,6 @@ def build_side_logdir(name, tmpdir):
     logdir = os.path.join(str(tmpdir), "sofalog") + "/"
     os.makedirs(logdir)
     for fn in SIDE_INPUTS:
-        shutil.copy(os.path.join(GOLDEN, name, fn), logdir + fn)
+        if os.path.isfile(os.path.join(GOLDEN, name, fn)):
+            shutil.copy(os.path.join(GOLDEN, name, fn), logdir + fn)
     return load_case(name), logdir

@@ -172,7 +172,7 @@ extern "C" int hs_repr6(double x, char* out) { JPlan p = repr6_plan(x); if (p.ki
 // ---------------------------------------------------------------- recorder side files (side.cuh)
 // CPU mirror of sofa_b200_side_preprocess + the side emitters: same row functions, the indexing
 // (which line a row is differenced against, which rows survive) restated sequentially.
-// mode: 0/1 CSV of list 0/1, 2/3 JSON records of list 0/1, 4 aux rows (usr_sys.csv / netbandwidth.csv).
+// mode = 16 * fmt + list; fmt 0 CSV, 1 JSON records, 2 aux rows (usr_sys.csv / netbandwidth.csv).
 // Returns -1, or row*1000+err; *nodata = 1 when nvidia-smi reported a failure.
 extern "C" long hs_side(int table, const char* text, long nbytes, int absolute, double time_base, long long local_off,
                         double tz_add, int mode, char* out, long* outlen, long* nrec, long* nlines, long* ncand_out, int* nodata) {
@@ -189,14 +189,16 @@ extern "C" long hs_side(int table, const char* text, long nbytes, int absolute, 
         int err;
         if (table == RAW_MPSTAT) err = parse_raw_mpstat(text + pos, (int)(e - pos), &r);
         else if (table == RAW_NVSMI) err = parse_raw_nvsmi(text + pos, (int)(e - pos), has_nl, &r);
-        else err = parse_raw_netstat(text + pos, (int)(e - pos), &r);
+        else if (table == RAW_NETSTAT) err = parse_raw_netstat(text + pos, (int)(e - pos), &r);
+        else if (table == RAW_VMSTAT) err = parse_raw_vmstat(text + pos, (int)(e - pos), &r);
+        else err = parse_raw_dmon(text + pos, (int)(e - pos), &r);
         if (err && first_err < 0) first_err = row * 1000 + err;
         if (r.flag) failed = true;
         raw.push_back(r);
         row++; pos = e + 1;
     }
     *nlines = row; *nodata = 0; *outlen = 0; *nrec = 0; *ncand_out = 0;
-    if (table == RAW_NVSMI && failed) { *nodata = 1; return -1; }
+    if ((table == RAW_NVSMI || table == RAW_DMON) && failed) { *nodata = 1; return -1; }
     if (first_err >= 0) return first_err;
     std::vector<SideOutRow> rows;
     if (table == RAW_MPSTAT) {
@@ -221,6 +223,24 @@ extern "C" long hs_side(int table, const char* text, long nbytes, int absolute, 
         }
     } else if (table == RAW_NVSMI) {
         for (auto& r : raw) { SideOutRow q; side_nvsmi_row(r, local_off, tz_add, absolute, time_base, &q); rows.push_back(q); }
+    } else if (table == RAW_VMSTAT) {
+        long j = 0;
+        for (long i = 0; i < (long)raw.size(); i++) {
+            if (raw[i].nf <= 0) continue;
+            SideOutRow q;
+            int e = side_vmstat_row(j++, raw[i].f, absolute, time_base, &q);
+            if (e) return i * 1000 + e;
+            rows.push_back(q);
+        }
+    } else if (table == RAW_DMON) {
+        long t = 0;
+        for (long i = 0; i < (long)raw.size(); i++) {
+            if (raw[i].nf <= 0) continue;
+            SideOutRow q;
+            side_dmon_row(t, raw[i], absolute, time_base, &q);
+            rows.push_back(q);
+            if (raw[i].i[0] == 0) t++;
+        }
     } else {
         for (long i = 0; i + 1 < (long)raw.size(); i++) {
             SideOutRow q;
@@ -231,11 +251,11 @@ extern "C" long hs_side(int table, const char* text, long nbytes, int absolute, 
     }
     *ncand_out = (long)rows.size();
     long o = 0, cnt = 0;
-    const int half = (mode == 1 || mode == 3) ? 1 : 0;
-    const uint32_t fmask = side_fmask(table);
+    const int fmt = mode >> 4, half = mode & 15;
+    const uint32_t fmask = side_fmask(table, absolute);
     for (size_t i = 0; i < rows.size(); i++) {
         const SideOutRow& q = rows[i];
-        if (mode == 4) {
+        if (fmt == 2) {
             if (table == RAW_MPSTAT && q.cls != 2) continue;
             AuxRowPlan p = aux_row_plan(q.ts, q.f1, q.f2);
             if (p.len < 0) return (long)i * 1000 + E_FORMAT;
@@ -246,9 +266,9 @@ extern "C" long hs_side(int table, const char* text, long nbytes, int absolute, 
         }
         if (q.cls != 1) continue;
         SideName ng{table, half, q};
-        RowVals v = vals_side(table, half, q);
+        RowVals v = vals_side(table, half, absolute, q);
         int l, len;
-        if (mode <= 1) { bool sp; l = csv_row_len(v, fmask, ng, &sp); if (l < 0) return (long)i * 1000 + E_FORMAT; len = csv_row_write(v, fmask, ng, sp, out + o); }
+        if (fmt == 0) { bool sp; l = csv_row_len(v, fmask, ng, &sp); if (l < 0) return (long)i * 1000 + E_FORMAT; len = csv_row_write(v, fmask, ng, sp, out + o); }
         else { l = json_row_len(v, fmask, ng); if (l < 0) return (long)i * 1000 + E_FORMAT; len = json_row_write(v, fmask, ng, out + o); }
         if (len != l) return (long)i * 1000 + 99;
         o += len; cnt++;

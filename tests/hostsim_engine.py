@@ -121,7 +121,7 @@ class HostSimEngine:
     # ---- recorder side files: CPU build of side.cuh (hs_side)
     def _side(self, raw_src, mode):
         text, absolute, time_base, local_off, tz_add = self.side[raw_src]
-        out = ctypes.create_string_buffer(len(text) * 24 + 4096)
+        out = ctypes.create_string_buffer(len(text) * 40 + 4096)
         outlen, nrec, nlines, ncand = ctypes.c_long(), ctypes.c_long(), ctypes.c_long(), ctypes.c_long()
         nodata = ctypes.c_int()
         r = self.lib.hs_side(raw_src - 6, text, ctypes.c_long(len(text)), int(absolute), ctypes.c_double(time_base),
@@ -141,14 +141,14 @@ class HostSimEngine:
         return nlines, ncand, nodata
 
     def side_csv(self, raw_src, lst=0):
-        return self._side(raw_src, lst)[:2]
+        return self._side(raw_src, lst)[:2]                 # mode = 16 * fmt + list
 
     def side_json(self, raw_src, lst=0):
-        out, n = self._side(raw_src, 2 + lst)[:2]
+        out, n = self._side(raw_src, 16 + lst)[:2]
         return out[2:], n
 
     def side_aux(self, raw_src):
-        return self._side(raw_src, 4)[:2]
+        return self._side(raw_src, 32)[:2]
 
     # ---- side tables: numpy stand-in for the device window reduction (test infrastructure only)
     def upload(self, kind, text, data_off=0):

@@ -380,13 +380,20 @@ def test_line_longer_than_overlap_window_fails_loudly(tmp_path):
 
 # ---------------------------------------------------------------- N1: recorder side files on the device
 def test_side_sources_device_reproduce_reference_files(tmp_path):
-    from helpers import side_cases, build_side_logdir, SIDE_OUTPUTS
+    from helpers import side_cases, build_side_logdir, SIDE_OUTPUTS, preprocess_overrides
     for name in side_cases():
         case, logdir = build_side_logdir(name, tmp_path / name)
-        sofa_preprocess(default_report_config(logdir))
+        cfg = default_report_config(logdir)
+        for k, v in preprocess_overrides(case).items():
+            setattr(cfg, k, v)
+        sofa_preprocess(cfg)
         for fn in SIDE_OUTPUTS:
+            want = golden_bytes(name, fn)
+            if want is None:
+                assert not os.path.isfile(logdir + fn), fn
+                continue
             with open(logdir + fn, "rb") as f:
-                _diff(name, fn, f.read(), golden_bytes(name, fn))
+                _diff(name, fn, f.read(), want)
 
 
 def test_side_sources_device_match_oracle_larger_and_edge_cases(tmp_path):
@@ -399,6 +406,7 @@ def test_side_sources_device_match_oracle_larger_and_edge_cases(tmp_path):
     a = os.path.join(str(tmp_path), "gpu") + "/"
     synth.make_logdir(a, seed=11, n_perf=500)
     synth.write_side_raw(a, seed=12, n_samples=620, n_cores=64, n_gpus=8)
+    synth.write_side_raw_1hz(a, seed=13, n_seconds=3000, n_gpus=8)
     with open(a + "nvsmi_query.txt", "a") as f:             # more nvidia-smi lines than samples x gpus
         body = open(a + "nvsmi_query.txt").read().split("\n")[1:-1]
         for rep in range(3):
@@ -412,9 +420,10 @@ def test_side_sources_device_match_oracle_larger_and_edge_cases(tmp_path):
     shutil.copytree(a, b)
     cfg = default_report_config(a)
     cfg.nvsmi_time_zone = -5
+    cfg.enable_vmstat = cfg.enable_encode_decode = True
     sofa_preprocess(cfg)
-    orc.preprocess(orc.OracleConfig(b, nprocs=1, nvsmi_time_zone=-5), demangle=demangle)
-    for fn in ("mpstat.csv", "usr_sys.csv", "nvsmi_trace.csv", "netstat.csv", "netbandwidth.csv", "report.js"):
+    orc.preprocess(orc.OracleConfig(b, nprocs=1, nvsmi_time_zone=-5, enable_vmstat=True, enable_encode_decode=True), demangle=demangle)
+    for fn in ("mpstat.csv", "usr_sys.csv", "nvsmi_trace.csv", "netstat.csv", "netbandwidth.csv", "vmstat.csv", "report.js"):
         with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
             _diff("side_large", fn, f.read(), g.read())
 

@@ -18,7 +18,7 @@ def test_oracle_concurrency_breakdown_matches_reference(name):
     case = json.load(open(os.path.join(d, "case.json")))
     feats, perf = orc.concurrency_breakdown(pd.read_csv(d + "/mpstat.csv"), pd.read_csv(d + "/cputrace.csv"),
                                             pd.read_csv(d + "/nvsmi_trace.csv"), pd.read_csv(d + "/netstat.csv"),
-                                            **{k: v for k, v in case["cfg"].items()})
+                                            **{k: v for k, v in case["cfg"].items() if k in ("is_idle_threshold", "sys_mon_rate")})
     want = [tuple(x) for x in case["features"][1:]]
     assert [(n, float(v)) for n, v in feats] == [(n, v) for n, v in want]
     buf = io.StringIO()
@@ -29,16 +29,20 @@ def test_oracle_concurrency_breakdown_matches_reference(name):
 @pytest.mark.parametrize("name", SIDE)
 def test_oracle_side_preprocess_matches_reference(name, tmp_path):
     """N1: mpstat.txt / nvsmi_query.txt / netstat.txt -> CSVs + report.js series, byte for byte."""
-    from helpers import build_side_logdir, SIDE_OUTPUTS, golden_bytes, demangle
+    from helpers import build_side_logdir, SIDE_OUTPUTS, golden_bytes, demangle, preprocess_overrides
     case, logdir = build_side_logdir(name, tmp_path)
-    orc.preprocess(orc.OracleConfig(logdir, nprocs=1), demangle=demangle)
+    orc.preprocess(orc.OracleConfig(logdir, nprocs=1, **preprocess_overrides(case)), demangle=demangle)
     for fn in SIDE_OUTPUTS:
-        assert open(logdir + fn, "rb").read() == golden_bytes(name, fn), fn
+        want = golden_bytes(name, fn)
+        if want is None:
+            assert not os.path.isfile(logdir + fn), fn
+        else:
+            assert open(logdir + fn, "rb").read() == want, fn
 
 
 @pytest.mark.parametrize("name", SIDE)
 def test_oracle_nvsmi_profile_matches_reference(name):
     d = os.path.join(GOLDEN, name)
     case = json.load(open(os.path.join(d, "case.json")))
-    feats = orc.nvsmi_profile(pd.read_csv(d + "/nvsmi_trace.csv"))
+    feats = orc.nvsmi_profile(pd.read_csv(d + "/nvsmi_trace.csv"), nvsmi_data=os.path.isfile(d + "/nvsmi.txt"))
     assert [(n, float(v)) for n, v in feats] == [tuple(x) for x in case["nvsmi_features"][1:]]

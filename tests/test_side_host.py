@@ -23,7 +23,8 @@ def run_case(name, tmp_path, engine):
         shutil.copy(os.path.join(d, fn), logdir + fn)
     cfg = default_report_config(logdir)
     for k, v in case["cfg"].items():
-        setattr(cfg, k, v)
+        if k in ("is_idle_threshold", "sys_mon_rate"):
+            setattr(cfg, k, v)
     feats = an.concurrency_breakdown(logdir, cfg, engine, [('elapsed_time', 12.5)])
     want = [(n, v) for n, v in case["features"]]
     assert [(n, float(v)) for n, v in feats] == want
@@ -43,6 +44,7 @@ def run_nvsmi_case(name, tmp_path, engine, capsys):
     shutil.copy(os.path.join(d, "nvsmi_trace.csv"), logdir + "nvsmi_trace.csv")
     cfg = default_report_config(logdir)
     cfg.verbose = True
+    cfg.nvsmi_data = os.path.isfile(os.path.join(d, "nvsmi.txt"))     # set by sofa_preprocess when enc/dec rows exist
     capsys.readouterr()
     feats = an.nvsmi_profile(logdir, cfg, engine, [('elapsed_time', 12.5)])
     out = capsys.readouterr().out

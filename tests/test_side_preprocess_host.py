@@ -9,7 +9,7 @@ import struct
 
 import pytest
 
-from helpers import side_cases, build_side_logdir, golden_bytes, SIDE_OUTPUTS, demangle
+from helpers import side_cases, build_side_logdir, golden_bytes, SIDE_OUTPUTS, demangle, preprocess_overrides
 from hostsim_engine import HostSimEngine, HostSimError, build_hostsim
 from oracle import sofa_oracle as orc
 from sofa_b200.sofa_config import default_report_config
@@ -33,15 +33,19 @@ def assert_same(got, want, what):
 @pytest.mark.parametrize("name", side_cases())
 def test_side_sources_reproduce_reference_files(name, tmp_path):
     case, logdir = build_side_logdir(name, tmp_path)
-    run_product(logdir, HostSimEngine())
+    run_product(logdir, HostSimEngine(), **preprocess_overrides(case))
     for fn in SIDE_OUTPUTS:
-        assert_same(open(logdir + fn, "rb").read(), golden_bytes(name, fn), "%s/%s" % (name, fn))
+        want = golden_bytes(name, fn)
+        if want is None:
+            assert not os.path.isfile(logdir + fn), fn
+        else:
+            assert_same(open(logdir + fn, "rb").read(), want, "%s/%s" % (name, fn))
 
 
-def oracle_vs_product(tmp_path, mutate, **over):
+def oracle_vs_product(tmp_path, mutate, base="side_small", **over):
     """Same mutated logdir through the oracle and the product; compare every side output."""
     import shutil
-    _, a = build_side_logdir("side_small", tmp_path / "a")
+    _, a = build_side_logdir(base, tmp_path / "a")
     mutate(a)
     b = str(tmp_path / "b") + "/"
     shutil.copytree(a, b)
@@ -103,6 +107,31 @@ def test_netstat_single_line_and_no_trailing_newline(tmp_path):
         lines[10] = lines[10].split(",")[0] + ",5,7"
         open(d + "netstat.txt", "w").write("\n".join(lines))
     oracle_vs_product(tmp_path / "neg", neg)
+
+
+def test_vmstat_and_dmon_edge_cases(tmp_path):
+    def short_run(d):                                        # fewer than 4 seconds: no enc/dec rows, nvsmi_data stays False
+        lines = open(d + "nvsmi.txt").read().split("\n")
+        open(d + "nvsmi.txt", "w").write("\n".join(lines[:8]) + "\n")
+    oracle_vs_product(tmp_path / "short", short_run, base="side_full", enable_vmstat=True, enable_encode_decode=True)
+
+    def failed(d):
+        with open(d + "nvsmi.txt", "a") as f:
+            f.write("\nFailed\n")
+    oracle_vs_product(tmp_path / "failed", failed, base="side_full", enable_encode_decode=True)
+
+    def headers_only(d):
+        lines = [l for l in open(d + "vmstat.txt").read().split("\n") if "procs" in l or "swpd" in l]
+        open(d + "vmstat.txt", "w").write("\n".join(lines) + "\n")
+    oracle_vs_product(tmp_path / "hdr", headers_only, base="side_full", enable_vmstat=True)
+
+    def decimals(d):                                         # float() accepts "1.5" and "2e3"; int() truncates after + 1e-5
+        lines = open(d + "vmstat.txt").read().split("\n")
+        f = lines[5].split()
+        f[8], f[9], f[12] = "1.99999", "2e3", "7.5"
+        lines[5] = " ".join(f)
+        open(d + "vmstat.txt", "w").write("\n".join(lines))
+    oracle_vs_product(tmp_path / "dec", decimals, base="side_full", enable_vmstat=True, absolute_timestamp=True)
 
 
 def test_side_errors_are_loud(tmp_path):
