@@ -32,8 +32,15 @@ template <typename S>
 struct DevVizName {
     PerfVizName<S> raw; int id; DictView d;
     template <class K> __device__ __forceinline__ void gen(K& k) const {
-        if (id >= 0) put_span(k, d.blob + d.off[id], (int)(d.off[id + 1] - d.off[id]), true);
-        else raw.gen(k);
+        const PerfRow& r = raw.full.r;
+        if (id < 0 && r.va_len == 0xffff) { raw.gen(k); return; }        // rare: the slice was not cached at parse
+        // one code path for demangled (dictionary) and raw names - two spans, the second empty for a
+        // dictionary entry - so that the lanes of a warp stay together
+        const char* p0 = raw.full.line + r.sym_off;
+        int l0 = r.va_len, l1 = r.vb_len;
+        if (id >= 0) { p0 = d.blob + d.off[id]; l0 = (int)(d.off[id + 1] - d.off[id]); l1 = 0; }
+        put_span(k, p0, l0, true);
+        put_span(k, raw.full.line + r.dso_off, l1, true);
     }
 };
 

@@ -309,13 +309,22 @@ SOFA_HD int parse_perf(S s, int n, const IngestCfg& c, PerfRow* r) {
     return E_OK;
 }
 
+// evt.replace('-', '_') on the fly
+template <class K>
+struct DashFilter {
+    static constexpr bool WORDS = K::WORDS;
+    K* k;
+    SOFA_HD void put(char ch) { k->put(ch == '-' ? '_' : ch); }
+    SOFA_HD void put_word(uint64_t w, int nb) { k->put_word(w ^ ((lanes_eq(w, '-') >> 7) * 0x72ull), nb); }      // '-' ^ '_' = 0x72
+};
+
 // name = '[%s]' % evt.replace('-','_') + sym + dso   (:116,121)
 template <typename S>
 struct PerfName {
     S line; PerfRow r; bool wide;
     template <class K> SOFA_HD void gen(K& k) const {
         k.put('[');
-        for (int i = 0; i < r.evt_len; i++) { char ch = line[r.evt_off + i]; k.put(ch == '-' ? '_' : ch); }
+        { DashFilter<K> df{&k}; put_span(df, line + r.evt_off, r.evt_len, wide); }
         k.put(']');
         put_span(k, line + r.sym_off, r.sym_len, wide);
         put_span(k, line + r.dso_off, r.dso_len, wide);
@@ -493,7 +502,24 @@ SOFA_HD int parse_gpu(S s, int n, const IngestCfg& c, GpuRow* r) {
     return E_OK;
 }
 
-template <class K> SOFA_HD void put_lit(K& k, const char* lit) { for (int i = 0; lit[i]; i++) k.put(lit[i]); }
+template <class K> SOFA_HD void put_cstr(K& k, const char* lit) { for (int i = 0; lit[i]; i++) k.put(lit[i]); }
+// string literal: sinks with word paths get it as compile-time constant 8-byte words (a per-byte feed
+// costs a class test per character and, in a warp whose lanes print different kinds of names, runs with
+// a handful of lanes active)
+template <class K, int N> SOFA_HD void put_lit(K& k, const char (&lit)[N]) {
+    if constexpr (K::WORDS) {
+#pragma unroll
+        for (int o = 0; o < N - 1; o += 8) {
+            uint64_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) if (o + b < N - 1) w |= (uint64_t)(unsigned char)lit[o + b] << (8 * b);
+            k.put_word(w, (N - 1 - o) < 8 ? (N - 1 - o) : 8);
+        }
+    } else {
+        for (int i = 0; i < N - 1; i++) k.put(lit[i]);
+    }
+}
+
 // decimal digits of v straight into a sink: digits are produced least-significant first into
 // byte stacks held in registers (no local-memory buffer), then popped most-significant first
 template <class K> SOFA_HD void put_i64(K& k, int64_t v) {
@@ -504,9 +530,8 @@ template <class K> SOFA_HD void put_i64(K& k, int64_t v) {
         if (x < 10u) { k.put((char)('0' + x)); return; }
         uint64_t r0 = 0, r1 = 0; int n = 0;
         do { uint32_t q = x / 10u; uint64_t d = '0' + (x - q * 10u); if (n < 8) r0 = (r0 << 8) | d; else r1 = (r1 << 8) | d; x = q; n++; } while (x);
-        for (int i = 8; i < n; i++) { k.put((char)(r1 & 0xff)); r1 >>= 8; }
-        int m = n < 8 ? n : 8;
-        for (int i = 0; i < m; i++) { k.put((char)(r0 & 0xff)); r0 >>= 8; }
+        if (n > 8) k.put_word(r1, n - 8);               // the stacks already hold the digits in output order
+        k.put_word(r0, n < 8 ? n : 8);
         return;
     }
     uint64_t r0 = 0, r1 = 0, r2 = 0; int n = 0;
@@ -515,11 +540,9 @@ template <class K> SOFA_HD void put_i64(K& k, int64_t v) {
         if (n < 8) r0 = (r0 << 8) | d; else if (n < 16) r1 = (r1 << 8) | d; else r2 = (r2 << 8) | d;
         u = q; n++;
     } while (u);
-    for (int i = 16; i < n; i++) { k.put((char)(r2 & 0xff)); r2 >>= 8; }
-    int m1 = n < 16 ? n : 16;
-    for (int i = 8; i < m1; i++) { k.put((char)(r1 & 0xff)); r1 >>= 8; }
-    int m0 = n < 8 ? n : 8;
-    for (int i = 0; i < m0; i++) { k.put((char)(r0 & 0xff)); r0 >>= 8; }
+    if (n > 16) k.put_word(r2, n - 16);
+    if (n > 8) k.put_word(r1, n < 16 ? n - 8 : 8);
+    k.put_word(r0, n < 8 ? n : 8);
 }
 
 template <class K>
@@ -528,8 +551,18 @@ struct QuoteFilter {
     K* k;
     SOFA_HD void put(char ch) { if (ch != '"') k->put(ch); }
     SOFA_HD void put_word(uint64_t w, int nb) {
-        if ((lanes_eq(w, '"') & lanes_first(nb)) == 0) k->put_word(w, nb);
-        else put_word_bytes(*this, w, nb);
+        uint64_t q = lanes_eq(w, '"') & lanes_first(nb);
+        while (q) {                                     // squeeze the quote bytes out of the word (usually one, at an end)
+            int p = 0;
+            { uint64_t t = q; while (!(t & 0xff)) { t >>= 8; p++; } }
+            uint64_t lo = p ? (w & ((1ull << (8 * p)) - 1ull)) : 0ull;
+            uint64_t hi = p < 7 ? ((w >> (8 * p + 8)) << (8 * p)) : 0ull;
+            w = lo | hi; nb--;
+            uint64_t ql = p ? (q & ((1ull << (8 * p)) - 1ull)) : 0ull;
+            uint64_t qh = p < 7 ? ((q >> (8 * p + 8)) << (8 * p)) : 0ull;
+            q = ql | qh;
+        }
+        if (nb > 0) k->put_word(w, nb);
     }
 };
 template <typename S>
@@ -545,7 +578,8 @@ struct GpuName {
             put_lit(k, "[CUDA_COPY_P2P]from_gpu"); put_i64(k, r.src); put_lit(k, "_to_gpu"); put_i64(k, r.dst);
             k.put('_'); put_i64(k, r.payload); k.put('B');
         } else {
-            put_lit(k, r.kind == 1 ? "CUDA_COPY_H2D_" : (r.kind == 2 ? "CUDA_COPY_D2H_" : "CUDA_COPY_D2D_"));
+            put_lit(k, "CUDA_COPY_");
+            k.put_word(r.kind == 1 ? 0x5f443248ull : (r.kind == 2 ? 0x5f483244ull : 0x5f443244ull), 4);      // "H2D_" / "D2H_" / "D2D_"
             put_i64(k, r.payload); k.put('B');
         }
     }
@@ -609,7 +643,7 @@ SOFA_HD int parse_net(S s, int n, const IngestCfg& c, NetRow* r) {
 struct NetName {
     NetRow r;
     template <class K> SOFA_HD void gen(K& k) const {     // "network:%s:%d_to_%d_with_%d" (:198)
-        put_lit(k, r.proto == 1 ? "network:UDP,:" : "network:tcp:");
+        if (r.proto == 1) put_lit(k, "network:UDP,:"); else put_lit(k, "network:tcp:");
         put_i64(k, r.src); put_lit(k, "_to_"); put_i64(k, r.dst); put_lit(k, "_with_"); put_i64(k, r.payload);
     }
 };
@@ -748,12 +782,10 @@ struct CsvWrite {
     SOFA_HD void put(char ch) { if (ch == '"') out[n++] = '"'; out[n++] = ch; }
     SOFA_HD void put_word(uint64_t w, int nb) {
         if ((lanes_eq(w, '"') & lanes_first(nb)) == 0) {
-            if (nb == 8) {
+            // eight predicated stores whatever nb is: lanes of a warp sit at different word boundaries of
+            // their names, and a separate loop for partial words serialises them (measured 4-7 of 32 lanes)
 #pragma unroll
-                for (int b = 0; b < 8; b++) out[n + b] = (char)((w >> (8 * b)) & 0xff);
-            } else {
-                for (int b = 0; b < nb; b++) out[n + b] = (char)((w >> (8 * b)) & 0xff);
-            }
+            for (int b = 0; b < 8; b++) if (b < nb) out[n + b] = (char)((w >> (8 * b)) & 0xff);
             n += nb;
         } else put_word_bytes(*this, w, nb);
     }
@@ -943,10 +975,10 @@ struct JsonSimpleWrite {      // valid only when JsonScan found complex == false
         out[n++] = e;
     }
     SOFA_HD void put_word(uint64_t w, int nb) {
-        if ((json_special_lanes(w) & lanes_first(nb)) == 0 && nb == 8) {
+        if ((json_special_lanes(w) & lanes_first(nb)) == 0) {
 #pragma unroll
-            for (int b = 0; b < 8; b++) out[n + b] = (char)((w >> (8 * b)) & 0xff);
-            n += 8;
+            for (int b = 0; b < 8; b++) if (b < nb) out[n + b] = (char)((w >> (8 * b)) & 0xff);     // predicated, see CsvWrite
+            n += nb;
             return;
         }
         for (int b = 0; b < nb; b++) { put((char)(w & 0xff)); w >>= 8; }

@@ -334,15 +334,15 @@ struct SideName {
             put_lit(k, "mpstat_core"); put_i64(k, r.i[0]); put_lit(k, " (usr|sys|idl|iow|irq): |");
             for (int q = 1; q <= 5; q++) { put_pad3(k, r.i[q]); k.put('|'); }
         } else if (table == RAW_NVSMI) {                                       // :1046-1047
-            put_lit(k, half ? "GPUID_mem=" : "GPUID_sm="); put_i64(k, r.i[0]); k.put('_'); put_i64(k, half ? r.i[2] : r.i[1]);
+            put_cstr(k, half ? "GPUID_mem=" : "GPUID_sm="); put_i64(k, r.i[0]); k.put('_'); put_i64(k, half ? r.i[2] : r.i[1]);
         } else if (table == RAW_NETSTAT) {                                     // :1287, 1304
-            put_lit(k, half ? "network_bandwidth_rx(bytes):" : "network_bandwidth_tx(bytes):"); put_i64(k, half ? r.i[1] : r.i[0]);
+            put_cstr(k, half ? "network_bandwidth_rx(bytes):" : "network_bandwidth_tx(bytes):"); put_i64(k, half ? r.i[1] : r.i[0]);
         } else if (table == RAW_VMSTAT) {                                      // :850-866
             const char* keys[17] = {"r=", "|b=", "|sw=", "|fr=", "|bu=", "|ca=", "|si=", "|so=", "|bi=", "|bo=", "|in=", "|cs=",
                                     "|usr=", "|sys=", "|idl=", "|wa=", "|st="};
-            for (int q = 0; q < 17; q++) { put_lit(k, keys[q]); put_i64(k, (int64_t)d_add(r.ext[q], 1e-5)); }
+            for (int q = 0; q < 17; q++) { put_cstr(k, keys[q]); put_i64(k, (int64_t)d_add(r.ext[q], 1e-5)); }
         } else {                                                               // :1132-1133
-            put_lit(k, half ? "GPUID_dec=" : "GPUID_enc="); put_i64(k, r.i[0]); k.put('_'); put_i64(k, half ? r.i[2] : r.i[1]);
+            put_cstr(k, half ? "GPUID_dec=" : "GPUID_enc="); put_i64(k, r.i[0]); k.put('_'); put_i64(k, half ? r.i[2] : r.i[1]);
         }
     }
 };
