@@ -162,6 +162,21 @@ SOFA_HD int ctz32(uint32_t x) {
 #endif
 }
 
+SOFA_HD int ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+SOFA_HD int popc_lanes(uint64_t m) {                       // number of lanes flagged (bit 7 set)
+#if defined(__CUDA_ARCH__)
+    return __popcll(m & 0x8080808080808080ull);
+#else
+    return __builtin_popcountll(m & 0x8080808080808080ull);
+#endif
+}
+
 // str.split() with no argument (ASCII whitespace); returns number of tokens, capped at maxt.
 template <typename S>
 SOFA_HD int tokenize(S s, int n, Tok* t, int maxt) {
@@ -553,8 +568,7 @@ struct QuoteFilter {
     SOFA_HD void put_word(uint64_t w, int nb) {
         uint64_t q = lanes_eq(w, '"') & lanes_first(nb);
         while (q) {                                     // squeeze the quote bytes out of the word (usually one, at an end)
-            int p = 0;
-            { uint64_t t = q; while (!(t & 0xff)) { t >>= 8; p++; } }
+            const int p = ctz64(q) >> 3;
             uint64_t lo = p ? (w & ((1ull << (8 * p)) - 1ull)) : 0ull;
             uint64_t hi = p < 7 ? ((w >> (8 * p + 8)) << (8 * p)) : 0ull;
             w = lo | hi; nb--;
@@ -770,9 +784,12 @@ struct CsvCount {
         if (ch == '"') { len++; special = true; }
         else if (ch == ',' || ch == '\n' || ch == '\r') special = true;
     }
-    SOFA_HD void put_word(uint64_t w, int nb) {
-        uint64_t sp = (lanes_eq(w, '"') | lanes_eq(w, ',') | lanes_eq(w, '\n') | lanes_eq(w, '\r')) & lanes_first(nb);
-        if (sp == 0) len += nb; else put_word_bytes(*this, w, nb);
+    SOFA_HD void put_word(uint64_t w, int nb) {               // no per-byte loop: quotes are counted with a popcount
+        const uint64_t first = lanes_first(nb);
+        const uint64_t qt = lanes_eq(w, '"') & first;
+        const uint64_t sp = (qt | lanes_eq(w, ',') | lanes_eq(w, '\n') | lanes_eq(w, '\r')) & first;
+        len += nb + popc_lanes(qt);
+        special |= (sp != 0);
     }
 };
 template <typename O>
@@ -955,10 +972,14 @@ struct JsonScan {             // raw length, number of two-byte escapes, "needs 
         if (b == '"' || b == '\\' || b == '\n' || b == '\r' || b == '\t' || b == '\b' || b == '\f') two++;
         else complex = true;
     }
-    SOFA_HD void put_word(uint64_t w, int nb) {
-        uint64_t sp = json_special_lanes(w) & lanes_first(nb);
-        if (sp == 0) { raw += nb; return; }
-        for (int b = 0; b < nb; b++) { put((char)(w & 0xff)); w >>= 8; }
+    SOFA_HD void put_word(uint64_t w, int nb) {               // mask arithmetic only, no per-byte loop
+        const uint64_t first = lanes_first(nb);
+        const uint64_t sp = json_special_lanes(w) & first;
+        raw += nb;
+        if (sp == 0) return;
+        const uint64_t tw = lanes_two_byte_escape(w) & first;
+        two += popc_lanes(tw);
+        complex |= ((sp & ~tw) != 0);
     }
 };
 template <typename O>
@@ -981,7 +1002,20 @@ struct JsonSimpleWrite {      // valid only when JsonScan found complex == false
             n += nb;
             return;
         }
-        for (int b = 0; b < nb; b++) { put((char)(w & 0xff)); w >>= 8; }
+        // a word holding a character that needs a two-byte escape (every nvprof kernel name ends in '\n'):
+        // straight-line code, no loop, so lanes that reach it at different times spend little on it
+        const uint64_t sp = json_special_lanes(w);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            if (b < nb) {
+                char ch = (char)((w >> (8 * b)) & 0xff);
+                if ((sp >> (8 * b + 7)) & 1) {
+                    out[n++] = '\\';
+                    ch = ch == '\n' ? 'n' : (ch == '\r' ? 'r' : (ch == '\t' ? 't' : (ch == '\b' ? 'b' : (ch == '\f' ? 'f' : ch))));
+                }
+                out[n++] = ch;
+            }
+        }
     }
 };
 
