@@ -95,6 +95,31 @@ __global__ void __launch_bounds__(1024) k_scan_u64(uint64_t* a, uint64_t n) {
     if (threadIdx.x == 0) a[n] = carry;
 }
 
+// Large scans in three launches: every block scans 8192 elements in place and leaves its total in
+// part[block]; k_scan_u64 scans the totals; k_scan_add adds them back (and stores a[n] = grand total).
+constexpr uint32_t SCAN_BLOCK_ELEMS = 8192;
+__global__ void __launch_bounds__(1024) k_scan_part(uint64_t* a, uint64_t n, uint64_t* part) {
+    __shared__ uint64_t sm[33];
+    constexpr int PER = 8;
+    uint64_t v[PER];
+    uint64_t i0 = (uint64_t)blockIdx.x * SCAN_BLOCK_ELEMS + (uint64_t)threadIdx.x * PER;
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { v[k] = (i0 + k < n) ? a[i0 + k] : 0; s += v[k]; }
+    uint64_t total;
+    uint64_t ex = block_excl_scan64(s, &total, sm);
+#pragma unroll
+    for (int k = 0; k < PER; k++) { if (i0 + k < n) a[i0 + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) k_scan_add(uint64_t* a, uint64_t n, const uint64_t* __restrict__ part, uint32_t nparts) {
+    uint64_t off = part[blockIdx.x];
+    uint64_t i0 = (uint64_t)blockIdx.x * SCAN_BLOCK_ELEMS + (uint64_t)threadIdx.x * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (i0 + k < n) a[i0 + k] += off;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a[n] = part[nparts];
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(PARSE_TPB)
 k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t tile_bytes, uint32_t max_lines,

@@ -399,6 +399,13 @@ struct GpuRow {
 // parse a numeric field whose '"' characters have been removed (record.replace('"',''))
 template <typename S>
 SOFA_HD int parse_double_q(S s, int a, int b, double* out) {
+    {   // common case: the field is a bare or a fully quoted number - parse it in place (a quote anywhere
+        // else makes parse_double fail, and the buffer path below then decides)
+        int a2 = a, b2 = b;
+        if (a2 < b2 && s[a2] == '"') a2++;
+        if (b2 > a2 && s[b2 - 1] == '"') b2--;
+        if (parse_double(s + a2, b2 - a2, out) == P_OK) return P_OK;
+    }
     char buf[48];
     int m = 0;
     for (int i = a; i < b; i++) { char ch = s[i]; if (ch != '"') { if (m >= 47) return P_UNSUPPORTED; buf[m++] = ch; } }
@@ -428,7 +435,8 @@ SOFA_HD int parse_gpu(S s, int n, const IngestCfg& c, GpuRow* r) {
     int fa[9], fb[9];
     int want[9] = {c.idx_start, c.idx_dur, c.idx_size, c.idx_thr, c.idx_ctx, c.idx_stream,
                    c.idx_name, c.idx_srcctx, c.idx_dstctx};
-    for (int k = 0; k < 9; k++) { fa[k] = -1; fb[k] = -1; }
+    uint32_t wantmask = 0;
+    for (int k = 0; k < 9; k++) { fa[k] = -1; fb[k] = -1; if (want[k] >= 0 && want[k] < 32) wantmask |= 1u << want[k]; }
     int f = 0, a = 0;
     {
         const int sh = line_misalign(s);
@@ -438,7 +446,9 @@ SOFA_HD int parse_gpu(S s, int n, const IngestCfg& c, GpuRow* r) {
             while (m) {
                 int i = 8 * j - sh + ctz32(m);
                 m &= m - 1;
-                for (int k = 0; k < 9; k++) if (want[k] == f) { fa[k] = a; fb[k] = i; }
+                if (f >= 32 || ((wantmask >> f) & 1u)) {            // most columns are not wanted: skip the slot search
+                    for (int k = 0; k < 9; k++) if (want[k] == f) { fa[k] = a; fb[k] = i; }
+                }
                 f++; a = i + 1;
             }
         }
@@ -486,18 +496,53 @@ SOFA_HD int parse_gpu(S s, int n, const IngestCfg& c, GpuRow* r) {
     }
     if (err) return err;
     if (dev < -2147483647 || dev > 2147483647 || tid < -2147483647 || tid > 2147483647) return E_RANGE;
-    // substring tags on the quote-free name (:293-323)
+    // substring tags on the quote-free name (:293-323).  Word pass: every tag is [HDP] 't' 'o' [HDP], so only
+    // the positions where a 't' is directly followed by an 'o' are looked at (one or two per name at most);
+    // a quote anywhere but at the ends of the field falls back to the byte loop over the quote-free text.
     bool h2d = false, d2h = false, d2d = false, p2p = false;
     {
-        uint32_t w = 0;
-        for (int i = fa[6]; i < fb[6]; i++) {
-            char ch = s[i];
-            if (ch == '"') continue;
-            w = (w << 8) | (unsigned char)ch;
-            h2d |= (w == 0x48746f44u);   // "HtoD"
-            d2h |= (w == 0x44746f48u);   // "DtoH"
-            d2d |= (w == 0x44746f44u);   // "DtoD"
-            p2p |= (w == 0x50746f50u);   // "PtoP"
+        const int na = fa[6], nb_ = fb[6];
+        if (nb_ > na) {
+            const uint64_t K8 = 0x8080808080808080ull;
+            const int sh = line_misalign(s);
+            const int j0 = (na + sh) >> 3, j1 = (nb_ - 1 + sh) >> 3;
+            uint64_t prev_t = 0;
+            int quotes = 0;
+            for (int j = j0; j <= j1; j++) {
+                const uint64_t w = line_word(s, n, sh, j);
+                const int base = 8 * j - sh;
+                const int lo = na > base ? na - base : 0, hi = nb_ - base < 8 ? nb_ - base : 8;
+                const uint64_t vm = (hi >= 8 ? ~0ull : ((1ull << (8 * hi)) - 1ull)) & ~((1ull << (8 * lo)) - 1ull) & K8;
+                const uint64_t t = lanes_eq(w, 't') & vm, o = lanes_eq(w, 'o') & vm;
+                uint64_t hit = ((t << 8) & o) | (prev_t & o);          // flagged lane = the 'o'
+                prev_t = t >> 56;
+                quotes += popc_lanes(lanes_eq(w, '"') & vm);
+                while (hit) {
+                    const int po = base + (ctz64(hit) >> 3);           // position of the 'o'
+                    hit &= hit - 1;
+                    if (po - 2 >= na && po + 1 < nb_) {
+                        const char x = s[po - 2], y = s[po + 1];
+                        h2d |= (x == 'H' && y == 'D'); d2h |= (x == 'D' && y == 'H');
+                        d2d |= (x == 'D' && y == 'D'); p2p |= (x == 'P' && y == 'P');
+                    }
+                }
+            }
+            quotes -= (s[na] == '"') ? 1 : 0;
+            if (nb_ - 1 > na) quotes -= (s[nb_ - 1] == '"') ? 1 : 0;
+            if (nb_ - 2 > na) quotes -= (s[nb_ - 2] == '"') ? 1 : 0;
+            if (quotes != 0) {                                         // quotes inside the name: exact scan of the quote-free text
+                h2d = d2h = d2d = p2p = false;
+                uint32_t w = 0;
+                for (int i = na; i < nb_; i++) {
+                    char ch = s[i];
+                    if (ch == '"') continue;
+                    w = (w << 8) | (unsigned char)ch;
+                    h2d |= (w == 0x48746f44u);   // "HtoD"
+                    d2h |= (w == 0x44746f48u);   // "DtoH"
+                    d2d |= (w == 0x44746f44u);   // "DtoD"
+                    p2p |= (w == 0x50746f50u);   // "PtoP"
+                }
+            }
         }
     }
     int64_t src = 0, dst = 0;
@@ -1169,7 +1214,7 @@ struct FilterTable {
     int packed;
 };
 struct MatchSink {
-    static constexpr bool WORDS = false;
+    static constexpr bool WORDS = true;
     const FilterTable* t; uint32_t st[8]; uint32_t hit; uint64_t ps, phit;
     SOFA_HD MatchSink(const FilterTable* tt) : t(tt), hit(0), ps(0), phit(0) { for (int k = 0; k < 8; k++) st[k] = 0; }
     SOFA_HD void put(char ch) {
@@ -1184,7 +1229,16 @@ struct MatchSink {
             if (st[k] & t->final_bit[k]) hit |= 1u << k;
         }
     }
-    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
+    SOFA_HD void put_word(uint64_t w, int nb) {
+        if (!t->packed) { put_word_bytes(*this, w, nb); return; }
+#pragma unroll
+        for (int b = 0; b < 8; b++) {                    // straight-line shift-and steps, predicated on the byte count
+            if (b < nb) {
+                ps = ((ps << 1) | t->pstart) & t->pmask[(w >> (8 * b)) & 0xff];
+                phit |= ps & t->pfinal;
+            }
+        }
+    }
     SOFA_HD uint32_t hits() const {
         if (!t->packed) return hit;
         uint32_t h = 0;
@@ -1214,14 +1268,20 @@ inline void filter_table_build(FilterTable* ft, int nkw, const char* const* kws,
 
 // FNV-1a 64 over generated characters (name dictionary keys)
 struct HashSink {
-    static constexpr bool WORDS = false;
+    static constexpr bool WORDS = true;
     uint64_t h; int len; char c0, c1;
     SOFA_HD HashSink() : h(1469598103934665603ull), len(0), c0(0), c1(0) {}
     SOFA_HD void put(char ch) {
         if (len == 0) c0 = ch; else if (len == 1) c1 = ch;
         h = (h ^ (unsigned char)ch) * 1099511628211ull; len++;
     }
-    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
+    SOFA_HD void put_word(uint64_t w, int nb) {                // FNV-1a steps, straight-line
+        if (len == 0) { c0 = (char)(w & 0xff); if (nb > 1) c1 = (char)((w >> 8) & 0xff); }
+        else if (len == 1) c1 = (char)(w & 0xff);
+#pragma unroll
+        for (int b = 0; b < 8; b++) if (b < nb) h = (h ^ ((w >> (8 * b)) & 0xff)) * 1099511628211ull;
+        len += nb;
+    }
 };
 template <typename O>
 struct RawWrite {

@@ -82,7 +82,7 @@ struct sofa_ctx {
     std::vector<SmallXfer> pending;
     char* out_ptr[3] = {nullptr, nullptr, nullptr};
     DevBuf tiles, rowlen, blockoff, scratch, ftable, keys, rows;
-    DevBuf sk0, sv0, sk1, sv1, hist, segs, sums, small;
+    DevBuf sk0, sv0, sk1, sv1, hist, segs, sums, small, scanpart;
     unsigned long long* d_err = nullptr;        // [0] error slot, [1] counter, [2..9] filter counts, [10] misc
     unsigned int* d_flags = nullptr;            // [0] cr flag, [1] row flags, [2] overflow, [3] count
     uint64_t err_row = 0; int err_code = 0;
@@ -259,6 +259,22 @@ static int alloc_cols(sofa_ctx* c, int k, uint64_t n) {
 
 static inline uint64_t cdiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
+// In-place exclusive scan of a[0..n), a[n] = total: one block for short arrays, three launches otherwise.
+static int launch_scan(sofa_ctx* c, uint64_t* a, uint64_t n) {
+    if (n <= 4 * (uint64_t)SCAN_BLOCK_ELEMS) {
+        LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(a, n)));
+        return 0;
+    }
+    uint64_t nparts = cdiv(n, SCAN_BLOCK_ELEMS);
+    if (nparts > 0x7fffffffull) FAIL(SOFA_ERR_ARG, "scan: array too long");
+    ENSURE(c->scanpart, (nparts + 2) * 8);
+    uint64_t* part = c->scanpart.as<uint64_t>();
+    LAUNCH(c, K_SCAN, (k_scan_part<<<(unsigned)nparts, 1024, 0, c->stream>>>(a, n, part)));
+    LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(part, nparts)));
+    LAUNCH(c, K_SCAN, (k_scan_add<<<(unsigned)nparts, 1024, 0, c->stream>>>(a, n, part, (uint32_t)nparts)));
+    return 0;
+}
+
 // Flip the double buffer of output slot `s` (0 csv, 1 json) before an emit overwrites it: the
 // emit goes into the half whose last asynchronous fetch is oldest, after that fetch completed.
 static int flip_output(sofa_ctx* c, int s) {
@@ -375,7 +391,7 @@ int sofa_b200_destroy(sofa_ctx* c) {
     c->tiles.release(); c->rowlen.release(); c->blockoff.release(); c->scratch.release(); c->ftable.release();
     c->keys.release(); c->rows.release();
     c->sk0.release(); c->sv0.release(); c->sk1.release(); c->sv1.release(); c->hist.release(); c->segs.release();
-    c->sums.release(); c->small.release(); c->arena.release();
+    c->sums.release(); c->small.release(); c->arena.release(); c->scanpart.release();
     cudaFree(c->d_err); cudaFree(c->d_flags);
     if (c->stage_h) cudaFreeHost(c->stage_h);
     cudaStreamDestroy(c->stream);
@@ -450,7 +466,7 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     if (reset_err(c)) return SOFA_ERR_CUDA;
     LAUNCH(c, K_COUNT, (k_count_lines<<<(unsigned)ntiles, PARSE_TPB, 0, c->stream>>>(
         s.text.as<char>(), begin, end, tile, c->tiles.as<uint64_t>(), c->d_flags)));
-    LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(c->tiles.as<uint64_t>(), ntiles)));
+    CK_S(launch_scan(c, c->tiles.as<uint64_t>(), ntiles));
     uint64_t total = 0; unsigned int cr = 0;
     CK_S(small_d2h(c, &total, c->tiles.as<uint64_t>() + ntiles, 8));
     CK_S(small_d2h(c, &cr, c->d_flags, 4));
@@ -551,7 +567,7 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
         uint64_t nb = cdiv(ncand, 256);
         ENSURE(c->blockoff, (nb + 2) * 8);
         LAUNCH(c, K_FILTER, (k_mask_count<<<(unsigned)nb, 256, 0, c->stream>>>(mask, bit, ncand, c->blockoff.as<uint64_t>())));
-        LAUNCH(c, K_SCAN, (k_scan_u64<<<1, 1024, 0, c->stream>>>(c->blockoff.as<uint64_t>(), nb)));
+        CK_S(launch_scan(c, c->blockoff.as<uint64_t>(), nb));
         uint64_t cnt = 0;
         CK_S(small_d2h(c, &cnt, c->blockoff.as<uint64_t>() + nb, 8));
         CK_S(stream_sync(c));

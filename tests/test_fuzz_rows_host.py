@@ -130,3 +130,33 @@ def test_gpu_line_fuzz(seed):
     lines = [mut(synth.gpu_line(700 + seed, i, "ms_us_KB", True)) for i in range(1500)]
     _check(hl.SRC_GPU, lines, p,
            lambda ln: orc.parse_gpu_record(ln, False, TIME_BASE, indices, 1, 1e3, 1e6, 1024, -350.0))
+
+
+def test_gpu_copy_tags_anywhere_in_the_name():
+    """The reference tags a row by substring search on the quote-free Name (HtoD / DtoH / DtoD / PtoP anywhere,
+    first match in that order wins); the device looks only at 't''o' pairs.  Exercise tags at every alignment,
+    split by quotes, at the ends of the field, overlapping, and near-misses."""
+    rng = random.Random(11)
+    hdr = synth.gpu_header("ms_us_KB", True)
+    upd, off = hl.gpu_header(hdr.encode() + synth.gpu_line(700, 0, "ms_us_KB", True).encode())
+    p = hl.base_params(hl.SRC_GPU, TIME_BASE, False, -350.0)
+    upd.pop("t_base")
+    p.update(upd)
+    indices = hdr.split("\n")[1].replace('"', '').split(',')
+    units = hdr.split("\n")[2]
+    ts_rescale, dt_rescale, payload_unit = orc.gpu_units(units)
+    base = synth.gpu_line(701, 3, "ms_us_KB", True).rstrip("\n").split(",")
+    pieces = ["HtoD", "DtoH", "DtoD", "PtoP", "Hto", "toD", "HtoX", "PtoD", "to", "otot", "HHtoDD", "DtoDtoH", "t", "o", "Ht\"oD",
+              "H\"toD", "\"HtoD\"", "kernel_", "volta_sgemm", "operator()", "iterator", "x" * 7, "y" * 8, "z" * 9, ""]
+    lines = []
+    for i in range(600):
+        name = "".join(rng.choice(pieces) for _ in range(rng.randint(1, 6)))
+        quoted = rng.random() < 0.7
+        f = list(base)
+        f[-1] = ('"%s"' % name) if quoted else name
+        lines.append(",".join(f) + ("\n" if rng.random() < 0.9 or i < 599 else ""))
+    lines = [ln for ln in lines if "," not in ln.split(",", 18)[-1].replace('"', '') or True]
+
+    def parse_one(ln):
+        return orc.parse_gpu_record(ln, False, TIME_BASE, indices, 1, ts_rescale, dt_rescale, payload_unit, -350.0)
+    _check(hl.SRC_GPU, lines, p, parse_one)
