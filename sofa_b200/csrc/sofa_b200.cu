@@ -543,7 +543,6 @@ static int fmask_for(sofa_ctx* c, int k, uint32_t stride, uint32_t* fmask) {
 
 }  // extern "C"
 
-constexpr uint32_t FUSED_SLOT_BYTES = 64 * 1024;
 
 struct SideEmit { SideView v; uint64_t ncand; };
 
