@@ -410,6 +410,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": "100 M-event mixed perf+CUPTI+tcpdump trace with cpu_filters/gpu_filters tagging (BASELINE configs[2])",
                    "events_per_gpu": total_events, "perf": wl.n[0], "gpu": wl.n[1], "net": wl.n[2],
+                   "side_files": "10 Hz mpstat.txt / nvsmi_query.txt / netstat.txt, 64 cores x 8 GPUs: %d lines preprocessed, %d CSV rows window-reduced per step" % (wl.side_raw_lines, wl.side_rows),
                    "cpu_filters": CPU_FILTERS, "gpu_filters": GPU_KWS, "plot_ratio": 1,
                    "cache": "inputs_larger_than_L2 (%.1f GB text per step)" % (text_total / 1e9),
                    "parallelism": "one trace per GPU, no data-path collective"},

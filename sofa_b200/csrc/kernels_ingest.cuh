@@ -50,22 +50,32 @@ k_count_lines(const char* __restrict__ text, uint64_t begin, uint64_t end, uint3
     bool cr = false;
     uint64_t a0 = qlo & ~15ull;
     const uint4* t4 = reinterpret_cast<const uint4*>(text);
-    for (uint64_t p = a0 + 16ull * threadIdx.x; p < qhi; p += 16ull * blockDim.x) {
-        uint4 v = t4[p >> 4];
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // two 128-bit loads in flight per thread and iteration (the text buffer is padded past `end`)
+    const uint64_t step = 16ull * blockDim.x;
+    for (uint64_t p0 = a0 + 16ull * threadIdx.x; p0 < qhi; p0 += 2 * step) {
+        const uint64_t pp[2] = {p0, p0 + step};
+        uint4 vv[2];
+        vv[0] = t4[pp[0] >> 4];
+        vv[1] = pp[1] < qhi ? t4[pp[1] >> 4] : make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t m = newline_mask4(w[k]);
-            uint32_t c = __vcmpeq4(w[k], 0x0d0d0d0du);
-            uint64_t q = p + 4 * k;
-            if (q < qlo || q + 4 > qhi) {            // partial word: drop bytes outside [qlo, qhi)
-                uint32_t keep = 0;
+        for (int u = 0; u < 2; u++) {
+            const uint64_t p = pp[u];
+            if (p >= qhi) continue;
+            uint32_t w[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
 #pragma unroll
-                for (int j = 0; j < 4; j++) if (q + j >= qlo && q + j < qhi) keep |= 0xffu << (8 * j);
-                m &= keep; c &= keep;
+            for (int k = 0; k < 4; k++) {
+                uint32_t m = newline_mask4(w[k]);
+                uint32_t c = __vcmpeq4(w[k], 0x0d0d0d0du);
+                uint64_t q = p + 4 * k;
+                if (q < qlo || q + 4 > qhi) {            // partial word: drop bytes outside [qlo, qhi)
+                    uint32_t keep = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (q + j >= qlo && q + j < qhi) keep |= 0xffu << (8 * j);
+                    m &= keep; c &= keep;
+                }
+                cnt += __popc(m) >> 3;
+                cr |= (c != 0);
             }
-            cnt += __popc(m) >> 3;
-            cr |= (c != 0);
         }
     }
     if (threadIdx.x == 0 && b0 == begin && begin < end) cnt += 1;
