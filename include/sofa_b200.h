@@ -173,6 +173,12 @@ typedef struct {
 int sofa_b200_window_reduce(sofa_ctx*, const double* ends, uint32_t n_windows, double delta, sofa_window_t* out,
                             uint32_t* num_gpus);
 
+/* net_profile (sofa_analyze.py:385-493) over the packets of nettrace.csv = rows i % stride == 0 of the parsed
+ * net source: net_time (summed duration of the "network:tcp:" names, group by group in sorted-name order) and
+ * the payload summed per (pkt_src, pkt_dst) pair (unordered; the host ranks them into netrank.csv). */
+typedef struct { int64_t src, dst, payload_sum, count; } sofa_net_pair_t;
+int sofa_b200_net_profile(sofa_ctx*, uint32_t stride, double* net_time, int64_t* payload_total, sofa_net_pair_t* pairs,
+                          uint32_t cap, uint32_t* n_pairs);
 /* nvsmi_profile (sofa_analyze.py:259-341) over the parsed nvsmi_trace.csv body (source 4), optionally
  * restricted to roi_begin < timestamp <= roi_end (--spotlight_gpu).  One entry per (deviceId, event)
  * present: row count, duration sum (means = sum / count), and for q = 0.25, 0.5, 0.75 the two order

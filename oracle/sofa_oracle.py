@@ -662,6 +662,54 @@ def cpu_profile(df):
 
 
 # --------------------------------------------------------------------------- ujson double
+def _convertbyte(B):
+    """sofa_analyze.py:495-511."""
+    B = int(B)
+    KB = float(1024)
+    MB = float(KB ** 2)
+    GB = float(KB ** 3)
+    TB = float(KB ** 4)
+    if B < KB:
+        return '{} Bytes'.format(B)
+    elif KB <= B < MB:
+        return '{0:.2f} KB'.format(B / KB)
+    elif MB <= B < GB:
+        return '{0:.2f} MB'.format(B / MB)
+    elif GB <= B < TB:
+        return '{0:.2f} GB'.format(B / GB)
+    return '{0:.2f} TB'.format(B / TB)
+
+
+def net_profile(df, logdir):
+    """sofa_analyze.py:385-493 without the verbose tables: net_time feature and netrank.csv."""
+    grouped_df = df.groupby("name")["duration"]
+    net_time = 0
+    for key, item in grouped_df:
+        if key.find("network:tcp:") != -1:
+            net_time = net_time + grouped_df.get_group(key).sum()
+    packet_sum_matrix = df.groupby(['pkt_src', 'pkt_dst'])["payload"].sum().unstack(level=1, fill_value=0)
+
+    def zero(s):
+        if s[0:2] == '00':
+            s = s[2]
+        elif (s[0] == '0') and (s[1] != '0'):
+            s = s[1:3]
+        return s
+
+    def ip_text(j):
+        j = str(int(j))
+        return j[:-9] + '.' + zero(j[-9:-6]) + '.' + zero(j[-6:-3]) + '.' + zero(j[-3:])
+    record = []
+    for index in packet_sum_matrix.index:
+        for column in packet_sum_matrix.columns:
+            record.append((ip_text(index), ip_text(column), packet_sum_matrix[column][index]))
+    record.sort(key=lambda tup: tup[2], reverse=True)
+    final = [[s_, d_, _convertbyte(v), round(v / df['payload'].sum(), 2)] for s_, d_, v in record if v != 0]
+    pd.DataFrame(final, columns=['Source', 'Destination', 'Amount', 'Percentage of a Node']).to_csv(
+        logdir + 'netrank.csv', mode='w', header=True, index=False)
+    return [('net_time', net_time)]
+
+
 def nvsmi_profile(df_nvsmi, nvsmi_data=False, spotlight_gpu=False, roi_begin=0, roi_end=0):
     """sofa_analyze.py:259-341 -> the six feature rows (verbose tables are print-only)."""
     if spotlight_gpu and roi_end != 0:

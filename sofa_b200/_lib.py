@@ -17,7 +17,7 @@ EXPORTS = [
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
     "sofa_b200_synth", "sofa_b200_text_fetch", "sofa_b200_mark", "sofa_b200_elapsed_ms",
     "sofa_b200_upload_async", "sofa_b200_fetch_async", "sofa_b200_wait_fetch", "sofa_b200_sync", "sofa_b200_set_output_arena", "sofa_b200_emit_comm_csv", "sofa_b200_window_reduce",
-    "sofa_b200_side_preprocess", "sofa_b200_side_emit_csv", "sofa_b200_side_emit_json", "sofa_b200_side_emit_aux", "sofa_b200_nvsmi_profile",
+    "sofa_b200_side_preprocess", "sofa_b200_side_emit_csv", "sofa_b200_side_emit_json", "sofa_b200_side_emit_aux", "sofa_b200_nvsmi_profile", "sofa_b200_net_profile",
 ]
 
 
@@ -48,6 +48,10 @@ class Window(ctypes.Structure):
                 ("nv_max", ctypes.c_double), ("nv_min", ctypes.c_double), ("nv_sum", ctypes.c_int64),
                 ("tx_count", ctypes.c_uint32), ("rx_count", ctypes.c_uint32), ("tx_sum", ctypes.c_double),
                 ("rx_sum", ctypes.c_double)]
+
+
+class NetPair(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_int64), ("dst", ctypes.c_int64), ("payload_sum", ctypes.c_int64), ("count", ctypes.c_int64)]
 
 
 class NvsmiGroup(ctypes.Structure):
@@ -119,6 +123,8 @@ def load_lib():
     lib.sofa_b200_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.sofa_b200_window_reduce.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32, ctypes.c_double,
                                             ctypes.POINTER(Window), u32p]
+    lib.sofa_b200_net_profile.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                                          ctypes.POINTER(NetPair), ctypes.c_uint32, u32p]
     lib.sofa_b200_nvsmi_profile.argtypes = [vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.POINTER(NvsmiGroup),
                                             ctypes.c_uint32, u32p, ctypes.POINTER(ctypes.c_int32), u32p,
                                             ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), u64p]

@@ -196,6 +196,59 @@ __global__ void __launch_bounds__(256) k_nccl_hash(SrcView src, uint64_t n, uint
     }
     namehash[row] = key;
 }
+// ---------------------------------------------------------------------------- net_profile (sofa_analyze.py:385-493)
+// Rows of nettrace.csv are the packets i % stride == 0.  namehash[row] = FNV-1a of the name for tcp packets
+// (the names that contain "network:tcp:"), 0 otherwise; dur[row] = payload / 128e6 as the CSV holds it.
+__global__ void __launch_bounds__(256) k_net_tcp_hash(SrcView src, uint64_t n, uint32_t stride, uint64_t* __restrict__ namehash,
+                                                      double* __restrict__ dur) {
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    uint64_t key = 0;
+    NetRow r = load_net(src, row);
+    if (row % stride == 0 && r.proto == 2) {
+        NetName ng{r};
+        HashSink h; ng.gen(h);
+        key = h.h ? h.h : 1;
+    }
+    namehash[row] = key;
+    dur[row] = d_div((double)r.payload, 128.0e6);
+}
+// payload summed per (pkt_src, pkt_dst): open addressing on a 64-bit tag of the pair; every slot also keeps
+// min / max of src and dst so that the host can prove that no two pairs shared a tag (exact, or a loud error).
+struct NetPairSlot { unsigned long long tag; long long sum, src_min, src_max, dst_min, dst_max; unsigned long long count; };
+__global__ void __launch_bounds__(256) k_net_pairs(SrcView src, uint64_t n, uint32_t stride, NetPairSlot* tab, uint64_t cap_mask,
+                                                   unsigned long long* total, unsigned int* overflow) {
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n || row % stride) return;
+    NetRow r = load_net(src, row);
+    if (r.proto == 0) return;                                  // the all-NaN row of a non-IP line
+    uint64_t h = 1469598103934665603ull;
+    h = (h ^ (uint64_t)r.src) * 1099511628211ull; h ^= h >> 29;
+    h = (h ^ (uint64_t)r.dst) * 1099511628211ull; h ^= h >> 32;
+    unsigned long long tag = h | 1ull;
+    uint64_t slot = (h >> 7) & cap_mask;
+    for (uint64_t probe = 0; probe <= cap_mask && probe < 65536; probe++) {
+        unsigned long long prev = atomicCAS(&tab[slot].tag, 0ull, tag);
+        if (prev == 0ull || prev == tag) {
+            atomicAdd((unsigned long long*)&tab[slot].sum, (unsigned long long)r.payload);
+            atomicAdd(&tab[slot].count, 1ull);
+            atomicMin(&tab[slot].src_min, (long long)r.src); atomicMax(&tab[slot].src_max, (long long)r.src);
+            atomicMin(&tab[slot].dst_min, (long long)r.dst); atomicMax(&tab[slot].dst_max, (long long)r.dst);
+            atomicAdd(total, (unsigned long long)r.payload);
+            return;
+        }
+        slot = (slot + 1) & cap_mask;
+    }
+    atomicOr(overflow, 1u);
+}
+__global__ void k_net_pairs_init(NetPairSlot* tab, uint64_t cap) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    NetPairSlot s; s.tag = 0; s.sum = 0; s.count = 0;
+    s.src_min = s.dst_min = 0x7fffffffffffffffll; s.src_max = s.dst_max = -0x7fffffffffffffffll - 1;
+    tab[i] = s;
+}
+
 // names of the table's representative rows, each followed by '\0' (gpu names may hold '\n');
 // order[] receives the slot of every exported name in output order.
 template <int KIND>

@@ -352,19 +352,13 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
     __syncthreads();
     const unsigned long long base = s_base;
     if (base + total > a.cap) { if (threadIdx.x == 0) atomicOr(a.overflow, 1u); return; }
-    // ---- phase 3: print the row at its final position in a shared-memory image of the block's output range
-    // and flush the image with 128-bit stores.  A range larger than the image goes through it in rounds of
-    // S bytes (S a multiple of 16, so every round has the phase of the global destination); only a row that
-    // straddles a round boundary is written straight to global memory, after the last flush.
-    const uint32_t phase = (uint32_t)(base & 15);
-    const uint32_t S = (a.slot_bytes - 16) & ~15u;
-    const uint32_t rounds = total ? (total + S - 1) / S : 0;
-    const uint32_t my_round = ex / S;
-    const bool straddle = len && ((ex + len - 1) / S != my_round);
-    auto print_row = [&](bool to_image) {
+    // ---- phase 3: print the row at its final position (shared-memory image, or global when the
+    // block's range does not fit)
+    const bool staged = total + 16 <= a.slot_bytes;
+    if (len) {
         with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
-            if (to_image) {
-                SmemPtr dst{(uint32_t)__cvta_generic_to_shared(stage) + phase + (ex - my_round * S)};
+            if (staged) {
+                SmemPtr dst{(uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)(base & 15) + ex};
                 if constexpr (FMT == FMT_CSV) csv_row_emit(v, a.fmask, ng, plan, dst);
                 else if constexpr (FMT == FMT_COMM) comm_row_emit(c, v, a.fmask, plan, dst);
                 else if constexpr (FMT == FMT_AUX) aux_row_emit(plan, dst);
@@ -377,18 +371,10 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
                 else json_row_emit(v, a.fmask, ng, plan, dst);
             }
         });
-    };
-    for (uint32_t r = 0; r < rounds; r++) {
-        if (len && !straddle && my_round == r) print_row(true);
-        __syncthreads();
-        const uint32_t lo = r * S, hi = (r + 1) * S < total ? (r + 1) * S : total;
-        flush_staged(stage, a.out, base + lo, hi - lo);
-        if (r + 1 < rounds) __syncthreads();
     }
-    if (rounds > 1) {
-        __syncthreads();
-        if (straddle) print_row(false);
-    }
+    __syncthreads();
+    // ---- phase 4: 128-bit coalesced flush
+    if (staged && total) flush_staged(stage, a.out, base, total);
 }
 
 }  // namespace sofa

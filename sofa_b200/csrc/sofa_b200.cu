@@ -190,7 +190,7 @@ static int reset_err(sofa_ctx* c) {
 // column slots
 enum { PC_TS = 0, PC_EVENT, PC_DUR, PC_PID, PC_TID, PC_LS, PC_PIECES };
 enum { GC_TS = 0, GC_DUR, GC_BW, GC_PAYLOAD, GC_DEV, GC_TID, GC_SRC, GC_DST, GC_KIND, GC_BWF, GC_LS, GC_NOFF, GC_NLEN };
-enum { NC_TS = 0, NC_PAYLOAD, NC_SRC, NC_DST, NC_PROTO };
+enum { NC_TS = 0, NC_PAYLOAD, NC_SRC, NC_DST, NC_PROTO, NC_DUR };
 enum { SC_TS = 0, SC_EVENT, SC_DUR, SC_DEV, SC_BW, SC_RATIOS };
 
 static SideCols side_cols(sofa_ctx* c, int slot) {
@@ -592,6 +592,14 @@ static int emit_fused(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, 
     static const uint32_t slot_csv = getenv("SOFA_B200_SLOT_CSV") ? (uint32_t)atoi(getenv("SOFA_B200_SLOT_CSV")) : 32u * 1024u;
     static const uint32_t slot_json = getenv("SOFA_B200_SLOT_JSON") ? (uint32_t)atoi(getenv("SOFA_B200_SLOT_JSON")) : 40u * 1024u;
     uint32_t slot_bytes = (FMT == FMT_COMM || FMT == FMT_AUX) ? 16 * 1024 : (FMT == FMT_JSON ? slot_json : slot_csv);
+    if (!se && nitems) {
+        // traces with long names (C++ symbols of several hundred bytes): grow the image with the average line
+        // length so that a block's 128 rows still fit - the direct-to-global fallback is several times slower
+        double avg_line = (double)(s.nbytes > s.data_off ? s.nbytes - s.data_off : 0) / (double)(s.n_rows ? s.n_rows : 1);
+        double est_row = (FMT == FMT_JSON ? 200.0 : 70.0) + avg_line;
+        uint32_t want = (uint32_t)(est_row * EMIT_TPB * 1.1);
+        if (FMT != FMT_COMM && want > slot_bytes + slot_bytes / 8) slot_bytes = (want + 1023u) & ~1023u;     // only when clearly needed
+    }
     if (slot_bytes < 4096u) slot_bytes = 4096u;
     if (slot_bytes > 63u * 1024u) slot_bytes = 63u * 1024u;
     for (int attempt = 0; attempt < 6; attempt++, cap *= 2) {

@@ -234,6 +234,14 @@ class CudaEngine:
                                                      len(ends), float(delta), out, ctypes.byref(ng)))
         return out, ng.value
 
+    def net_profile(self, stride, cap=1 << 20):
+        """(net_time, total payload, {(pkt_src, pkt_dst): summed payload}) of the packets i % stride == 0."""
+        t, total, n = ctypes.c_double(), ctypes.c_int64(), ctypes.c_uint32()
+        pairs = (L.NetPair * cap)()
+        self._check(self.lib.sofa_b200_net_profile(self.ctx, int(stride), ctypes.byref(t), ctypes.byref(total), pairs, cap,
+                                                   ctypes.byref(n)))
+        return t.value, total.value, {(pairs[i].src, pairs[i].dst): pairs[i].payload_sum for i in range(n.value)}
+
     def nvsmi_profile(self, roi=None):
         """Per (deviceId, event) group of the parsed nvsmi_trace.csv (source 4): {(dev, event): (count, sum,
         [(lo, hi)] for q = .25, .5, .75)}, device ids in order of first appearance, first / last timestamp."""

@@ -122,6 +122,73 @@ def _first_last_timestamp(body):
     return float(first), float(last_line[:last_line.find(b',')])
 
 
+def _convertbyte(B):
+    """sofa_analyze.py:495-511."""
+    B = int(B)
+    KB = float(1024)
+    MB = float(KB ** 2)
+    GB = float(KB ** 3)
+    TB = float(KB ** 4)
+    if B < KB:
+        return '{} Bytes'.format(B)
+    elif KB <= B < MB:
+        return '{0:.2f} KB'.format(B / KB)
+    elif MB <= B < GB:
+        return '{0:.2f} MB'.format(B / MB)
+    elif GB <= B < TB:
+        return '{0:.2f} GB'.format(B / GB)
+    return '{0:.2f} TB'.format(B / TB)
+
+
+def _ip_text(j):
+    """check_str / zero of net_profile (:406-426): the 3-digit groups of the packed address, as the reference prints them."""
+    def zero(s):
+        if s[0:2] == '00':
+            s = s[2]
+        elif (s[0] == '0') and (s[1] != '0'):
+            s = s[1:3]
+        return s
+    j = str(int(j))
+    return j[:-9] + '.' + zero(j[-9:-6]) + '.' + zero(j[-6:-3]) + '.' + zero(j[-3:])
+
+
+def load_net_source(cfg, eng):
+    """Re-ingest net.tmp (for a stand-alone `sofa analyze`); returns False when it is absent."""
+    logdir = cfg.logdir
+    if not os.path.isfile(logdir + 'net.tmp'):
+        return False
+    with open(logdir + 'net.tmp', 'rb') as f:
+        text = f.read()
+    cfg.time_base = hl.read_time_base(logdir, cfg.cpu_time_offset)
+    eng.load(hl.SRC_NET, text, hl.base_params(hl.SRC_NET, cfg.time_base, cfg.absolute_timestamp, 0.0))
+    return True
+
+
+def net_profile(logdir, cfg, eng, features):
+    """sofa_analyze.py:385-493.  The group-by-name duration sums and the payload sums per (pkt_src, pkt_dst) come
+    from the device (rows i % plot_ratio == 0 of the parsed packets = the rows of nettrace.csv); ranking and the
+    text of netrank.csv are a few hundred cells on the host."""
+    import numpy as np
+    if not cfg.cluster_ip:
+        print_title("Network Profiling:")
+    ratio = int(cfg.plot_ratio)
+    net_time, total, pairs = eng.net_profile(ratio)
+    as_float = bool(eng.row_flags(hl.SRC_NET, ratio) & 2)            # a [] packet row makes the payload column float64
+    cast = (lambda x: np.float64(x)) if as_float else (lambda x: np.int64(x))
+    total = cast(total)
+    if cfg.verbose:
+        raise NotImplementedError("net_profile --verbose tables are not implemented")
+    record = [(s, d, cast(v)) for (s, d), v in sorted(pairs.items())]          # index-major, ascending, as the unstacked frame
+    record.sort(key=lambda tup: tup[2], reverse=True)
+    with open(logdir + 'netrank.csv', 'w') as f:
+        f.write('Source,Destination,Amount,Percentage of a Node\n')
+        for s, d, value in record:
+            if value == 0:
+                continue
+            f.write('%s,%s,%s,%s\n' % (_ip_text(s), _ip_text(d), _convertbyte(value), repr(float(round(value / total, 2)))))
+    return features + [('net_time', net_time)]
+
+
 def _lerp(lo, hi, count, q):
     """numpy's linear quantile between the two order statistics around (count-1)*q."""
     vi = (count - 1) * q
@@ -347,6 +414,15 @@ def sofa_analyze(cfg, engine=None):
             if own or engine is not None:
                 load_perf_source(cfg, eng)
             cpu_profile(cfg, eng)
+        if os.path.isfile(logdir + "nettrace.csv") and os.path.getsize(logdir + "nettrace.csv") > len(",".join(['x'] * 13)):   # :917-923
+            if eng is None:
+                from .engine import CudaEngine
+                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
+                own = True
+            if own or engine is not None:
+                if not load_net_source(cfg, eng):
+                    raise IOError("nettrace.csv exists but net.tmp (raw packets) is missing: CSV re-ingest is not implemented")
+            features = net_profile(logdir, cfg, eng, features)
         if os.path.isfile(logdir + "nvsmi_trace.csv"):                     # :957-961
             if eng is None:
                 from .engine import CudaEngine

@@ -129,6 +129,22 @@ def make_ref_cfg(logdir, overrides):
     return cfg
 
 
+def install_pandas_shim():
+    """net_profile (sofa_analyze.py:458) calls MultiIndex.set_levels(..., inplace=True), a keyword pandas 2 removed.
+    The shim accepts it again (the frame it touches is only printed with --verbose), so that the UNMODIFIED
+    function runs to its outputs (netrank.csv, net_time) on this container's pandas."""
+    import pandas as pd
+    if getattr(pd.MultiIndex.set_levels, "_sofa_shim", False):
+        return
+    orig = pd.MultiIndex.set_levels
+
+    def set_levels(self, levels, *, level=None, inplace=None, verify_integrity=True):
+        res = orig(self, levels, level=level, verify_integrity=verify_integrity)
+        return None if inplace else res
+    set_levels._sofa_shim = True
+    pd.MultiIndex.set_levels = set_levels
+
+
 def run_reference(logdir, overrides, analyze=True):
     """Run reference sofa_preprocess (+ the analyze functions that work on this
     pandas) in `logdir`.  Returns dict of feature name -> value (or None)."""
@@ -151,6 +167,16 @@ def run_reference(logdir, overrides, analyze=True):
         feats = {str(n): float(v) for n, v in zip(features['name'], features['value'])}
         with contextlib.redirect_stdout(io.StringIO()):
             feats['__top10_names__'] = ref_an.get_top_k_events(cfg, df_gpu, 10)
+    if analyze and os.path.isfile(os.path.join(logdir, "nettrace.csv")):
+        import pandas as pd
+        import sofa_analyze as ref_an
+        install_pandas_shim()
+        df_net = pd.read_csv(os.path.join(logdir, "nettrace.csv"))
+        nf = pd.DataFrame({'name': ['elapsed_time'], 'value': [12.5]}, columns=['name', 'value'])
+        with contextlib.redirect_stdout(io.StringIO()):
+            nf = ref_an.net_profile(logdir, cfg, df_net, nf)
+        feats = feats if feats is not None else {}
+        feats['__net_features__'] = [[str(n), float(v)] for n, v in zip(nf['name'], nf['value'])]
     return feats
 
 
@@ -175,7 +201,7 @@ def main():
         meta = {"make_logdir": mk, "cfg": ov, "features": feats}
         with open(os.path.join(out, "case.json"), "w") as f:
             json.dump(meta, f, indent=1, sort_keys=True)
-        for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "comm.csv", "cuda_api_trace.csv"):
+        for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "comm.csv", "cuda_api_trace.csv", "netrank.csv"):
             p = os.path.join(logdir, fn)
             if os.path.isfile(p):
                 shutil.copy(p, os.path.join(out, fn))

@@ -157,6 +157,25 @@ class HostSimEngine:
     def parse(self, kind, params):
         return self.src[kind][0].count(b"\n")
 
+    def net_profile(self, stride, cap=0):
+        """pandas stand-in for sofa_b200_net_profile (test infrastructure only)."""
+        import io
+        import pandas as pd
+        cols = ["timestamp", "event", "duration", "deviceId", "copyKind", "payload", "bandwidth", "pkt_src",
+                "pkt_dst", "pid", "tid", "name", "category"]
+        df = pd.read_csv(io.BytesIO(self.csv(2, stride).tobytes()), names=cols)
+        g = df.groupby("name")["duration"]
+        t = 0
+        for key, _ in g:
+            if key.find("network:tcp:") != -1:
+                t = t + g.get_group(key).sum()
+        ok = df.dropna(subset=["payload"])
+        pairs = {(int(a), int(b)): int(v) for (a, b), v in ok.groupby(["pkt_src", "pkt_dst"])["payload"].sum().items()}
+        return float(t), int(ok.payload.sum()), pairs
+
+    def row_flags(self, kind, stride):
+        return self._run(kind, 0 if kind == 2 else 1, stride, 0x1fff)[1]
+
     def nvsmi_profile(self, roi=None):
         """numpy stand-in for sofa_b200_nvsmi_profile (test infrastructure only)."""
         import io

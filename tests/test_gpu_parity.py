@@ -128,7 +128,11 @@ def test_gpu_profile_features_match_reference(name, tmp_path, capsys):
     sofa_preprocess(cfg)
     feats = dict(sofa_analyze(cfg))
     for k, v in case["features"].items():
-        if k not in ("elapsed_time", "__top10_names__"):
+        if k == "__net_features__":
+            assert float(feats["net_time"]) == v[1][1]
+            with open(logdir + "netrank.csv", "rb") as f:
+                _diff(name, "netrank.csv", f.read(), golden_bytes(name, "netrank.csv"))
+        elif k not in ("elapsed_time", "__top10_names__"):
             assert float(feats[k]) == v, (k, feats[k], v)
     assert "Complete!!" in capsys.readouterr().out
     with open(logdir + "comm.csv", "rb") as f:
@@ -486,3 +490,34 @@ def test_nvsmi_profile_device_matches_oracle_larger_and_roi(tmp_path):
             assert [(n, float(v)) for n, v in got] == [(n, float(v)) for n, v in want]
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("name", ["net_small", "net_nan"])
+def test_net_profile_device_matches_reference(name, tmp_path):
+    from helpers import load_case
+    from sofa_b200.sofa_analyze import sofa_analyze
+    case, logdir = build_case_logdir(name, tmp_path)
+    cfg = default_report_config(logdir)
+    for k, v in case["cfg"].items():
+        setattr(cfg, k, v)
+    sofa_preprocess(cfg)
+    feats = dict(sofa_analyze(cfg))
+    assert float(feats["net_time"]) == case["features"]["__net_features__"][1][1]
+    with open(logdir + "netrank.csv", "rb") as f:
+        _diff(name, "netrank.csv", f.read(), golden_bytes(name, "netrank.csv"))
+
+
+def test_net_profile_device_matches_oracle_larger(tmp_path):
+    import pandas as pd
+    from sofa_b200.sofa_analyze import sofa_analyze
+    for ratio, pct in ((1, 0), (3, 2)):
+        a = os.path.join(str(tmp_path), "r%d" % ratio) + "/"
+        synth.make_logdir(a, seed=300 + ratio, n_net=120000, non_ip_pct=pct)
+        cfg = default_report_config(a)
+        cfg.plot_ratio = ratio
+        sofa_preprocess(cfg)
+        feats = dict(sofa_analyze(cfg))
+        got = open(a + "netrank.csv", "rb").read()
+        want = orc.net_profile(pd.read_csv(a + "nettrace.csv"), a)
+        assert float(feats["net_time"]) == float(dict(want)["net_time"])
+        assert got == open(a + "netrank.csv", "rb").read()

@@ -35,7 +35,7 @@ def test_oracle_gpu_profile_matches_reference(name, tmp_path):
     feats = dict(orc.gpu_profile(df, logdir))
     want = case["features"]
     for k, v in want.items():
-        if k == "elapsed_time":
+        if k in ("elapsed_time", "__net_features__"):
             continue
         if k == "__top10_names__":
             top = orc.top_k_events(df, 10)
@@ -47,3 +47,15 @@ def test_oracle_gpu_profile_matches_reference(name, tmp_path):
         assert float(feats[k]) == v, k
     with open(logdir + "comm.csv", "rb") as f:
         assert f.read() == golden_bytes(name, "comm.csv")
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if golden_bytes(n, "netrank.csv")])
+def test_oracle_net_profile_matches_reference(name, tmp_path):
+    """a15: net_time and netrank.csv against the unmodified reference (run with the pandas shim of make_golden.py)."""
+    case, logdir = build_case_logdir(name, tmp_path)
+    cfg = orc.OracleConfig(logdir, nprocs=1, **case["cfg"])
+    orc.preprocess(cfg, demangle=demangle, emit_json=False)
+    feats = orc.net_profile(pd.read_csv(logdir + "nettrace.csv"), logdir)
+    assert [(n, float(v)) for n, v in feats] == [tuple(x) for x in case["features"]["__net_features__"][1:]]
+    with open(logdir + "netrank.csv", "rb") as f:
+        assert f.read() == golden_bytes(name, "netrank.csv")

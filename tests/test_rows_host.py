@@ -29,3 +29,19 @@ def test_row_codecs_reproduce_reference_files(name, tmp_path):
         if got != want:
             i = next(k for k in range(min(len(got), len(want))) if got[k] != want[k]) if got[:len(want)] != want[:len(got)] else min(len(got), len(want))
             raise AssertionError("%s/%s differs at byte %d: got %r want %r" % (name, fn, i, got[max(0, i - 80):i + 40], want[max(0, i - 80):i + 40]))
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if golden_bytes(n, "netrank.csv")])
+def test_net_profile_host_logic(name, tmp_path):
+    """a15 host logic (ranking, address text, netrank.csv) against the reference's file."""
+    from sofa_b200 import sofa_analyze as an
+    case, logdir = build_case_logdir(name, tmp_path)
+    ov = dict(case["cfg"])
+    cfg = default_report_config(logdir, cpu_filters=ov.pop("cpu_filters", None))
+    for k, v in ov.items():
+        setattr(cfg, k, v)
+    eng = HostSimEngine()
+    sofa_preprocess(cfg, engine=eng)
+    feats = an.net_profile(logdir, cfg, eng, [])
+    assert float(dict(feats)["net_time"]) == case["features"]["__net_features__"][1][1]
+    assert open(logdir + "netrank.csv", "rb").read() == golden_bytes(name, "netrank.csv")
