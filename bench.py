@@ -6,8 +6,9 @@ Workload (BASELINE.json configs[2]): 100 M-event mixed synthetic trace - 60 M pe
 cpu_filters=idle,tensorflow and the default gpu_filters.  One step = one full pass:
 line index + parse of the three sources, cputrace/gputrace/nettrace CSV bodies, viz-name
 dictionary + demangle, keyword filters, every report.js series (cpu_trace, 2 cpu filters,
-net_trace, gpu_kernel_trace, 6 gpu filters), gpu_profile/comm_profile, and the window reduction of
-concurrency_breakdown over 10 Hz mpstat/nvsmi/netstat tables (64 cores x 8 GPUs).
+net_trace, gpu_kernel_trace, 6 gpu filters), the 10 Hz side files (mpstat.txt / nvsmi_query.txt / netstat.txt of
+64 cores x 8 GPUs -> their CSVs and series), gpu_profile/comm_profile, net_profile, nvsmi_profile and the window
+reduction of concurrency_breakdown over the side tables.
 
   value : events/s with the raw text already resident in HBM (device-timed, CUDA events)
   e2e   : same pass through the public engine API from PINNED HOST text, with H2D of the
@@ -282,6 +283,8 @@ class Workload:
                 for i in range(len(CPU_KWS)):
                     js(kind, 1, i)
         gp = eng.gpu_profile() if analyze else None
+        if analyze and (kinds is None or hl.SRC_NET in kinds):
+            eng.net_profile(1)                                      # net_time + payload per (src, dst)
         if analyze and self.side is not None:                       # concurrency_breakdown, device part
             for i, pb in enumerate(self.side):
                 if e2e:
@@ -291,6 +294,7 @@ class Workload:
                     eng.upload(3 + i, pb.array, 0)
                 eng.parse(3 + i, self.side_params)
             self.side_resident = True
+            eng.nvsmi_profile()                                     # group sums + quartile order statistics
             eng.window_reduce(self.win_ends, 0.1)
         if e2e:
             eng.sync()
@@ -463,7 +467,7 @@ def write_sample_logdir(logdir, n_events, seed, wl=None):
 
 
 def oracle_pass(logdir, nprocs):
-    """preprocess (trace + side files) + gpu_profile + concurrency_breakdown of the CPU oracle (reference-path port)."""
+    """preprocess (trace + side files) + gpu_profile + net_profile + nvsmi_profile + concurrency_breakdown of the CPU oracle."""
     import pandas as pd
     from oracle import sofa_oracle as orc
     from sofa_b200.sofa_preprocess import demangle
@@ -471,6 +475,10 @@ def oracle_pass(logdir, nprocs):
     orc.preprocess(cfg, demangle=demangle)
     df = pd.read_csv(logdir + "/gputrace.csv")
     orc.gpu_profile(df, logdir)
+    if os.path.isfile(logdir + "/nettrace.csv"):
+        orc.net_profile(pd.read_csv(logdir + "/nettrace.csv"), logdir + "/")
+    if os.path.isfile(logdir + "/nvsmi_trace.csv"):
+        orc.nvsmi_profile(pd.read_csv(logdir + "/nvsmi_trace.csv"))
     if os.path.isfile(logdir + "/mpstat.csv"):
         orc.concurrency_breakdown(pd.read_csv(logdir + "/mpstat.csv"), pd.read_csv(logdir + "/cputrace.csv"),
                                   pd.read_csv(logdir + "/nvsmi_trace.csv"), pd.read_csv(logdir + "/netstat.csv"))

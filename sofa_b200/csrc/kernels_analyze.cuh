@@ -213,6 +213,57 @@ __global__ void __launch_bounds__(256) k_net_tcp_hash(SrcView src, uint64_t n, u
     namehash[row] = key;
     dur[row] = d_div((double)r.payload, 128.0e6);
 }
+// Order of the names "network:tcp:%d_to_%d_with_%d" as strings: compare src, dst, payload as decimal STRINGS.
+// Inside the name a number is followed by '_' (greater than every digit), so a shorter number that is a prefix
+// of a longer one sorts after it; the payload ends the string, so there the shorter one sorts first.
+// strkey = the decimal digits left-aligned in 13 base-11 places, pad = 10 (inner numbers) or 0 with digits
+// shifted to 1..10 (last number): integer order of the key = string order of the number.
+__device__ __forceinline__ uint64_t net_strkey(int64_t v, bool last) {
+    uint64_t u = v < 0 ? 0 : (uint64_t)v;                // (addresses and payloads of tcp rows are never negative)
+    int nd = ndigits_u64(u);
+    uint64_t key = 0;
+    uint64_t p = 1;
+    for (int i = 1; i < nd; i++) p *= 10;
+    for (int i = 0; i < 13; i++) {
+        uint64_t d;
+        if (i < nd) { uint64_t q = u / p; d = (last ? 1 : 0) + q; u -= q * p; p /= 10; }
+        else d = last ? 0 : 10;
+        key = key * 11 + d;
+    }
+    return key;
+}
+// keys[i] = string-order key of one name component of packet rows[i]: which = 0 payload, 1 dst, 2 src
+__global__ void __launch_bounds__(256) k_net_key(SrcView src, const uint32_t* __restrict__ rows, uint64_t m, int which,
+                                                 uint64_t* __restrict__ keys) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint64_t row = rows[i];
+    int64_t v = which == 0 ? src.c.n.payload[row] : (which == 1 ? src.c.n.dst[row] : src.c.n.src[row]);
+    keys[i] = net_strkey(v, which == 0);
+}
+// segment heads of the packets sorted by name: (src, dst, payload) differs from the previous packet's
+__device__ __forceinline__ bool net_new_group(const SrcView& s, const uint32_t* rows, uint64_t i) {
+    if (i == 0) return true;
+    uint64_t a = rows[i], b = rows[i - 1];
+    return s.c.n.src[a] != s.c.n.src[b] || s.c.n.dst[a] != s.c.n.dst[b] || s.c.n.payload[a] != s.c.n.payload[b];
+}
+__global__ void __launch_bounds__(256) k_net_seg_count(SrcView src, const uint32_t* __restrict__ rows, uint64_t m, uint64_t* blockoff) {
+    __shared__ uint32_t sm[33];
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t total;
+    block_excl_scan((i < m && net_new_group(src, rows, i)) ? 1u : 0u, &total, sm);
+    if (threadIdx.x == 0) blockoff[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) k_net_seg_write(SrcView src, const uint32_t* __restrict__ rows, uint64_t m, const uint64_t* blockoff,
+                                                       uint32_t* __restrict__ seg_start) {
+    __shared__ uint32_t sm[33];
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    bool f = i < m && net_new_group(src, rows, i);
+    uint32_t total;
+    uint32_t ex = block_excl_scan(f ? 1u : 0u, &total, sm);
+    if (f) seg_start[blockoff[blockIdx.x] + ex] = (uint32_t)i;
+}
+
 // payload summed per (pkt_src, pkt_dst): open addressing on a 64-bit tag of the pair; every slot also keeps
 // min / max of src and dst so that the host can prove that no two pairs shared a tag (exact, or a loud error).
 struct NetPairSlot { unsigned long long tag; long long sum, src_min, src_max, dst_min, dst_max; unsigned long long count; };

@@ -83,6 +83,7 @@ struct sofa_ctx {
     char* out_ptr[3] = {nullptr, nullptr, nullptr};
     DevBuf tiles, rowlen, blockoff, scratch, ftable, keys, rows;
     DevBuf sk0, sv0, sk1, sv1, hist, segs, sums, small, scanpart;
+    void* pin_h = nullptr; size_t pin_cap = 0;  // pinned host scratch for larger read-backs (grown on demand)
     unsigned long long* d_err = nullptr;        // [0] error slot, [1] counter, [2..9] filter counts, [10] misc
     unsigned int* d_flags = nullptr;            // [0] cr flag, [1] row flags, [2] overflow, [3] count
     uint64_t err_row = 0; int err_code = 0;
@@ -259,6 +260,15 @@ static int alloc_cols(sofa_ctx* c, int k, uint64_t n) {
 
 static inline uint64_t cdiv(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
+static int ensure_pinned(sofa_ctx* c, size_t n) {
+    if (n <= c->pin_cap) return 0;
+    if (c->pin_h) { cudaFreeHost(c->pin_h); c->pin_h = nullptr; c->pin_cap = 0; }
+    size_t want = n + n / 4 + 4096;
+    CK(cudaHostAlloc(&c->pin_h, want, cudaHostAllocDefault));
+    c->pin_cap = want;
+    return 0;
+}
+
 // In-place exclusive scan of a[0..n), a[n] = total: one block for short arrays, three launches otherwise.
 static int launch_scan(sofa_ctx* c, uint64_t* a, uint64_t n) {
     if (n <= 4 * (uint64_t)SCAN_BLOCK_ELEMS) {
@@ -394,6 +404,7 @@ int sofa_b200_destroy(sofa_ctx* c) {
     c->sums.release(); c->small.release(); c->arena.release(); c->scanpart.release();
     cudaFree(c->d_err); cudaFree(c->d_flags);
     if (c->stage_h) cudaFreeHost(c->stage_h);
+    if (c->pin_h) cudaFreeHost(c->pin_h);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;

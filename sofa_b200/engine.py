@@ -234,12 +234,22 @@ class CudaEngine:
                                                      len(ends), float(delta), out, ctypes.byref(ng)))
         return out, ng.value
 
-    def net_profile(self, stride, cap=1 << 20):
+    def net_profile(self, stride):
         """(net_time, total payload, {(pkt_src, pkt_dst): summed payload}) of the packets i % stride == 0."""
         t, total, n = ctypes.c_double(), ctypes.c_int64(), ctypes.c_uint32()
-        pairs = (L.NetPair * cap)()
-        self._check(self.lib.sofa_b200_net_profile(self.ctx, int(stride), ctypes.byref(t), ctypes.byref(total), pairs, cap,
-                                                   ctypes.byref(n)))
+        cap = getattr(self, '_net_pair_cap', 1 << 14)
+        while True:
+            if getattr(self, '_net_pairs', None) is None or len(self._net_pairs) < cap:
+                self._net_pairs = (L.NetPair * cap)()
+            rc = self.lib.sofa_b200_net_profile(self.ctx, int(stride), ctypes.byref(t), ctypes.byref(total), self._net_pairs, cap,
+                                                ctypes.byref(n))
+            if rc == L.SOFA_ERR_CAP and cap < (1 << 24):
+                cap *= 8                                        # more address pairs than the buffer holds: grow and repeat
+                continue
+            self._check(rc)
+            break
+        self._net_pair_cap = cap
+        pairs = self._net_pairs
         return t.value, total.value, {(pairs[i].src, pairs[i].dst): pairs[i].payload_sum for i in range(n.value)}
 
     def nvsmi_profile(self, roi=None):

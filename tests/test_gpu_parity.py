@@ -521,3 +521,29 @@ def test_net_profile_device_matches_oracle_larger(tmp_path):
         want = orc.net_profile(pd.read_csv(a + "nettrace.csv"), a)
         assert float(feats["net_time"]) == float(dict(want)["net_time"])
         assert got == open(a + "netrank.csv", "rb").read()
+
+
+def test_net_profile_name_order_with_mixed_address_lengths(tmp_path):
+    """net_time accumulates the group sums in sorted-NAME order; the device sorts by string-order keys of
+    (src, dst, payload).  Addresses and payloads of different digit counts make numeric and string order differ."""
+    import random
+    import pandas as pd
+    from sofa_b200.sofa_analyze import sofa_analyze
+    rng = random.Random(5)
+    a = str(tmp_path) + "/"
+    synth.make_logdir(a, seed=9, n_net=10)
+    hosts = ["1.2.3.4", "10.0.0.1", "9.255.1.77", "100.1.2.3", "2.0.0.200", "192.168.1.1", "19.216.81.1", "1.0.0.9"]
+    t = 1600000000.5
+    with open(a + "net.tmp", "w") as f:
+        for i in range(60000):
+            t += 0.00001
+            s_, d_ = rng.choice(hosts), rng.choice(hosts)
+            f.write("%.6f IP %s.%d > %s.%d: tcp %d\n" % (t, s_, rng.randrange(1, 65535), d_, rng.randrange(1, 65535),
+                                                        rng.choice([0, 7, 64, 640, 1448, 14480, 65000, rng.randrange(1, 99999)])))
+    cfg = default_report_config(a)
+    sofa_preprocess(cfg)
+    feats = dict(sofa_analyze(cfg))
+    got = open(a + "netrank.csv", "rb").read()
+    want = dict(orc.net_profile(pd.read_csv(a + "nettrace.csv"), a))
+    assert float(feats["net_time"]) == float(want["net_time"])
+    assert got == open(a + "netrank.csv", "rb").read()
