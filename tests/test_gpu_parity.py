@@ -547,3 +547,46 @@ def test_net_profile_name_order_with_mixed_address_lengths(tmp_path):
     want = dict(orc.net_profile(pd.read_csv(a + "nettrace.csv"), a))
     assert float(feats["net_time"]) == float(want["net_time"])
     assert got == open(a + "netrank.csv", "rb").read()
+
+
+def test_cli_report_then_standalone_analyze(tmp_path):
+    """`bin/sofa report` on a logdir with the trace sources and all five side files, then `bin/sofa analyze` on its
+    own (re-ingesting the dumped text): same feature table both times, files identical to the oracle's."""
+    import subprocess
+    import sys
+    import time
+    import pandas as pd
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = os.path.join(str(tmp_path), "gpu") + "/"
+    synth.make_logdir(a, seed=41, n_perf=3000, n_gpu=2000, n_net=1500, non_ip_pct=1)
+    synth.write_side_raw(a, seed=42, n_samples=80, n_cores=4, n_gpus=2)
+    synth.write_side_raw_1hz(a, seed=43, n_seconds=20, n_gpus=2)
+    b = os.path.join(str(tmp_path), "cpu") + "/"
+    import shutil
+    shutil.copytree(a, b)
+    env = dict(os.environ, TZ='UTC')
+    out1 = subprocess.run([sys.executable, os.path.join(repo, "bin", "sofa"), "report", "--logdir", a, "--enable_vmstat",
+                           "--enable_encode_decode"], capture_output=True, text=True, env=env, timeout=600)
+    assert out1.returncode == 0, out1.stderr[-2000:]
+    assert "Complete!!" in out1.stdout
+    out2 = subprocess.run([sys.executable, os.path.join(repo, "bin", "sofa"), "analyze", "--logdir", a], capture_output=True,
+                          text=True, env=env, timeout=600)
+    assert out2.returncode == 0, out2.stderr[-2000:]
+    table = lambda s_: [ln for ln in s_.split("\n") if ln[:1].isdigit()]
+    assert table(out1.stdout) == table(out2.stdout) and len(table(out1.stdout)) > 20
+    orc.preprocess(orc.OracleConfig(b, nprocs=1, enable_vmstat=True, enable_encode_decode=True), demangle=demangle)
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "mpstat.csv", "vmstat.csv", "nvsmi_trace.csv", "netstat.csv",
+               "usr_sys.csv", "netbandwidth.csv", "report.js"):
+        with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
+            _diff("cli", fn, f.read(), g.read())
+    want = dict(orc.gpu_profile(pd.read_csv(b + "gputrace.csv"), b))
+    want.update(dict(orc.net_profile(pd.read_csv(b + "nettrace.csv"), b)))
+    want.update(dict(orc.nvsmi_profile(pd.read_csv(b + "nvsmi_trace.csv"), nvsmi_data=True)))
+    got = {}
+    for ln in table(out1.stdout):
+        f = ln.split()
+        got[f[1]] = float(f[2])
+    for k, v in want.items():
+        assert abs(got[k] - float(v)) <= 0.0005 + 1e-9 * abs(float(v)), (k, got[k], v)       # the table prints %.3lf
