@@ -207,7 +207,7 @@ class Workload:
         output fetched into its own region of a pinned host arena (`ring`) on the D2H copy
         stream; both overlap the kernels.  The step ends when every copy has landed."""
         hl, eng = self.hl, self.eng
-        nb = {"csv": 0, "json": 0, "h2d": 0}
+        nb = {"csv": 0, "json": 0, "h2d": 0, "max_single": 0}
         counts = {}
         cursor = [0]
 
@@ -222,12 +222,14 @@ class Workload:
         def csv(kind, stride):
             n = eng.csv_device(kind, stride)
             nb["csv"] += n
+            nb["max_single"] = max(nb["max_single"], n)
             if e2e:
                 fetch(0, n)
 
         def js(kind, stride, filt):
             n, nrec = eng.json_device(kind, stride, filt)
             nb["json"] += n
+            nb["max_single"] = max(nb["max_single"], n)
             if e2e and n:
                 fetch(1, n)
             return nrec
@@ -368,7 +370,26 @@ def run_ours(args):
     eng.set_profiling(False)
 
     # ---- end-to-end arm: pinned host text in, every output fetched to pinned host memory
-    ring = eng.pinned(int((out_bytes["csv"] + out_bytes["json"]) * 1.02) + (64 << 20))
+    ring_bytes = int((out_bytes["csv"] + out_bytes["json"]) * 1.02) + (64 << 20)
+    try:                                     # every rank pins its text + this arena: stay within the node's free memory
+        with open("/proc/meminfo") as f:
+            avail = [int(ln.split()[1]) * 1024 for ln in f if ln.startswith("MemAvailable:")][0]
+        share = int(0.7 * avail / max(1, world))
+        if ring_bytes > share:
+            ring_bytes = max(int(out_bytes.get("max_single", 0) * 1.02) + (64 << 20), share)   # a smaller arena is drained and reused within the step
+    except Exception:
+        pass
+    if os.environ.get("SOFA_BENCH_RING_BYTES"):      # test hook: force a small arena to exercise the drain-and-reuse path
+        ring_bytes = max(int(out_bytes.get("max_single", 0) * 1.02) + (64 << 20), int(os.environ["SOFA_BENCH_RING_BYTES"]))
+    ring = None
+    while ring is None:
+        try:
+            ring = eng.pinned(ring_bytes)
+        except MemoryError:
+            floor = int(out_bytes.get("max_single", 0) * 1.02) + (64 << 20)
+            if ring_bytes <= floor:
+                raise
+            ring_bytes = max(floor, ring_bytes // 2)
     eng.set_output_arena(int((out_bytes["csv"] + out_bytes["json"]) * 1.25) + (1 << 30))
     for _ in range(max(1, min(args.warmup, 2))):
         wl.step(True, ring)
