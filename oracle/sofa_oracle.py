@@ -306,6 +306,70 @@ def preprocess_netstat(logdir, absolute_timestamp, time_base):
     return tx_traces, rx_traces
 
 
+def preprocess_diskstat(logdir, absolute_timestamp, time_base, diskstat_filters=None):
+    """diskstat.txt -> diskstat.csv, diskstat_vector.csv, diskstat_vector_ui.csv.  sofa_preprocess.py:548-673.
+    (Not on the device path yet: the product refuses diskstat.txt; this restatement is pinned against the
+    reference so that the device version can be checked against it.)"""
+    with open(logdir + 'diskstat.txt') as f:
+        diskstats = f.readlines()
+    tmp_list = [d[:-1].split(',') for d in diskstats]
+    devs = list(set(map(lambda x: x[1], tmp_list)))
+    n_dev = len(devs)
+    rows, vectors = [], []
+    for i in range(len(diskstats)):
+        if i < n_dev:
+            continue
+        m = diskstats[i][:-1].split(',')
+        dev = m[1]
+        m_last = diskstats[i - n_dev][:-1].split(',')
+        secsize = 512
+        try:
+            with open('/sys/block/' + dev + '/queue/hw_sector_size') as f:
+                secsize = int(re.match(r"\d+", f.readline()).group())
+        except Exception:
+            pass
+        d_read = (int(m[2]) - int(m_last[2])) * secsize
+        d_write = (int(m[3]) - int(m_last[3])) * secsize
+        d_disk_total = d_read + d_write
+        t_begin = float(m[0])
+        if not absolute_timestamp:
+            t_begin = t_begin - time_base
+        d_duration = float(m[0]) - float(m_last[0])
+        d_throughput = round((d_disk_total / d_duration) / float(1024 ** 2), 2)
+        read_bandwidth = d_read / d_duration
+        write_bandwidth = d_write / d_duration
+        total_bandwidth = d_disk_total / d_duration
+        r_io = int(m[4]) - int(m_last[4])
+        w_io = int(m[5]) - int(m_last[5])
+        r_iops = int(r_io / d_duration)
+        w_iops = int(w_io / d_duration)
+        iops = int((r_io + w_io) / d_duration)
+        r_time, w_time, await_time = 0, 0, 0
+        if r_io > 0:
+            r_time = (int(m[6]) - int(m_last[6])) / r_io
+        if w_io > 0:
+            w_time = (int(m[7]) - int(m_last[7])) / w_io
+        if (r_io + w_io) > 0:
+            await_time = ((int(m[6]) - int(m_last[6])) + (int(m[7]) - int(m_last[7]))) / (r_io + w_io)
+        vectors.append((t_begin, m[1], r_iops, w_iops, iops, r_time, w_time, await_time, read_bandwidth, write_bandwidth,
+                        total_bandwidth))
+        info = 'diskstat_dev:%s (read|write): |%3d|%3d| bytes' % (m[1], d_read, d_write)
+        rows.append([t_begin, -1, d_duration, m[1], -1, d_disk_total, d_throughput, -1, -1, -1, -1, info, 0])
+    traces = pd.DataFrame(rows, columns=FIELDNAMES)
+    table = pd.DataFrame(vectors, columns=['time', 'dev', 'r_iops', 'w_iops', 'iops', 'r_time', 'w_time', 'await_time',
+                                           'd_read', 'd_write', 'd_disk_total'])
+    for dev in devs:
+        if table[table['dev'] == dev]['d_disk_total'].max() == 0:
+            table = table[table.dev != dev]
+            traces = traces[traces.deviceId != dev]
+    traces.to_csv(logdir + 'diskstat.csv', index=False)
+    table.to_csv(logdir + 'diskstat_vector.csv', index=False)
+    if diskstat_filters:
+        table = table[table['dev'] == diskstat_filters]
+    table.to_csv(logdir + 'diskstat_vector_ui.csv', index=False)
+    return traces
+
+
 def preprocess_vmstat(logdir, absolute_timestamp, time_base):
     """vmstat.txt -> vmstat.csv (bi, bo, in, cs, wa, st, usr, sys lists).  sofa_preprocess.py:787-1008.
     Returns the eight frames in that order."""
@@ -444,6 +508,9 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
         mpstat_traces = preprocess_mpstat(logdir, cfg.absolute_timestamp, time_base)
     vm = [[] for _ in range(8)]
     nvsmi_enc, nvsmi_dec = [], []
+    diskstat_traces = []
+    if os.path.isfile(logdir + 'diskstat.txt'):
+        diskstat_traces = preprocess_diskstat(logdir, cfg.absolute_timestamp, time_base, getattr(cfg, 'diskstat_filters', None))
     if os.path.isfile(logdir + 'vmstat.txt'):
         with open(logdir + 'vmstat.txt') as f:
             if len(f.readlines()) > 0:                                    # :791
@@ -539,7 +606,7 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
     if cfg.enable_mpstat:
         series.append(Series('mpstat_usr', 'MPSTAT_USR', 'Cyan', mpstat_traces))
     if cfg.enable_diskstat:
-        series.append(Series('diskstat', 'DISKSTAT', 'GreenYellow', [], y_field='bandwidth'))
+        series.append(Series('diskstat', 'DISK_USAGE (MB/s)', 'GreenYellow', diskstat_traces, y_field='bandwidth'))
     if cfg.enable_vmstat:                                                   # :1964-1999
         series.append(Series('vmstat_usr', 'CPU_USAGE_USR', 'Magenta', vm_usr))
         series.append(Series('vmstat_sys', 'CPU_USAGE_SYS', 'LightBlue', vm_sys))

@@ -10,7 +10,7 @@ library this module raises.
 
 Sources handled: perf.script (a1), nvprof gpu trace (a2) and API trace (a4), tcpdump text (a3),
 and of SURVEY.md §8(f) N1 the recorder side files mpstat.txt, nvsmi_query.txt and netstat.txt.
-The remaining N1 sources (vmstat, diskstat, nvsmi.txt enc/dec, strace, blktrace, pystacks) raise
+and of SURVEY.md §8(f) N1 also vmstat.txt and nvsmi.txt.  The remaining N1 sources (diskstat, strace, blktrace, pystacks) raise
 NotImplementedError when their input files are present, rather than silently producing a
 report.js that differs from the reference's.
 """
@@ -384,7 +384,7 @@ def _preprocess(cfg, eng):
     if cfg.enable_mpstat:
         series.append(SeriesOut('mpstat_usr', 'MPSTAT_USR', 'Cyan', *side.get('mpstat_usr', (None, 0))))
     if cfg.enable_diskstat:
-        series.append(SeriesOut('diskstat', 'DISKSTAT', 'GreenYellow'))
+        series.append(SeriesOut('diskstat', 'DISK_USAGE (MB/s)', 'GreenYellow'))
     if cfg.enable_vmstat:
         series.append(SeriesOut('vmstat_usr', 'CPU_USAGE_USR', 'Magenta', *side.get('vmstat_usr', (None, 0))))
         series.append(SeriesOut('vmstat_sys', 'CPU_USAGE_SYS', 'LightBlue', *side.get('vmstat_sys', (None, 0))))

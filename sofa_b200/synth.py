@@ -365,6 +365,29 @@ def write_side_raw_1hz(logdir, seed, n_seconds=30, n_gpus=2):
                 f.write("%5d %5d %5d %5s %5s\n" % (g, (r >> 12) % 100, (r >> 30) % 100, enc, dec))
 
 
+def write_diskstat(logdir, seed, n_samples=40, devs=("sda", "sda1", "nvme0n1", "loop0", "dm-0"), rate_hz=10):
+    """diskstat.txt as the recorder appends it (sofa_record.py:96-121): one line per block device and sample,
+    `time,dev,sectors_read,sectors_written,reads,writes,ms_reading,ms_writing` with cumulative counters.
+    loop0 never moves (the reference drops devices whose traffic stays zero)."""
+    os.makedirs(logdir, exist_ok=True)
+    t0 = TIME_BASE + 0.5
+    cum = {d: [1000 * (i + 1), 2000 * (i + 1), 10 * (i + 1), 20 * (i + 1), 5 * (i + 1), 7 * (i + 1)] for i, d in enumerate(devs)}
+    with open(os.path.join(logdir, "diskstat.txt"), "w") as f:
+        for s_ in range(n_samples):
+            t = t0 + s_ / rate_hz + 0.0007 * (s_ % 3)
+            for i, d in enumerate(devs):
+                r = rnd(seed, 12, s_ * 16 + i, 0)
+                if d != "loop0":
+                    busy = (s_ // 10 + i) % 3
+                    rd = (r % 4000) * (busy != 2)
+                    wr = ((r >> 12) % 9000) * (busy != 0)
+                    rio, wio = (rd + 7) // 8 if rd else 0, (wr + 15) // 16 if wr else 0
+                    inc = [rd, wr, rio, wio, ((r >> 24) % 50) if rio else 0, ((r >> 30) % 120) if wio else 0]
+                    for k in range(6):
+                        cum[d][k] += inc[k]
+                f.write("%.6f,%s,%s\n" % (t, d, ",".join(str(v) for v in cum[d])))
+
+
 def side_csv_bodies(seed, n_samples, n_cores, n_gpus, rate_hz=10):
     """Header-less bodies of mpstat.csv, nvsmi_trace.csv, netstat.csv in the format the reference's
     preprocess writes them (tests/golden/side_small), for concurrency_breakdown at scale."""

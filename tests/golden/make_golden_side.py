@@ -27,6 +27,8 @@ CASES = {
     # + vmstat.txt and nvsmi.txt (1 Hz), every optional series switched on
     "side_full": (dict(seed=93, n_samples=50, n_cores=3, n_gpus=2, hz1=dict(n_seconds=30, n_gpus=2)),
                   dict(enable_vmstat=True, enable_encode_decode=True)),
+    # diskstat.txt (oracle-only fixture: the device path does not cover diskstat yet)
+    "disk_small": (dict(seed=95, n_samples=30, n_cores=2, n_gpus=1, disk=dict(n_samples=40)), dict()),
     "side_abs": (dict(seed=94, n_samples=40, n_cores=2, n_gpus=3, hz1=dict(n_seconds=12, n_gpus=3)),
                  dict(absolute_timestamp=True, enable_vmstat=True, enable_encode_decode=True)),
 }
@@ -47,9 +49,12 @@ def main():
         synth.make_logdir(logdir, seed=mk["seed"], n_perf=120)
         mk = dict(mk)
         hz1 = mk.pop("hz1", None)
+        disk = mk.pop("disk", None)
         synth.write_side_raw(logdir, **mk)
         if hz1:
             synth.write_side_raw_1hz(logdir, mk["seed"], **hz1)
+        if disk:
+            synth.write_diskstat(logdir, mk["seed"], **disk)
         cfg = mg.make_ref_cfg(logdir, ov)
         import sofa_preprocess as ref_pre
         with contextlib.redirect_stdout(io.StringIO()):
@@ -78,12 +83,15 @@ def main():
         if hz1:
             for fn in ("vmstat.txt", "nvsmi.txt", "vmstat.csv"):
                 shutil.copy(logdir + fn, os.path.join(out, fn))
+        if disk:
+            for fn in ("diskstat.txt", "diskstat.csv", "diskstat_vector.csv", "diskstat_vector_ui.csv"):
+                shutil.copy(logdir + fn, os.path.join(out, fn))
         for fn in ("mpstat.csv", "nvsmi_trace.csv", "netstat.csv", "cputrace.csv", "performance.csv", "misc.txt",
                    "usr_sys.csv", "netbandwidth.csv", "report.js",
                    "mpstat.txt", "nvsmi_query.txt", "netstat.txt", "perf.script", "sofa_time.txt",
                    "perf_events_used.txt", "perf_timebase.txt", "nvsmi_profile_verbose.txt"):
             shutil.copy(logdir + fn, os.path.join(out, fn))
-        meta = {"make": dict(mk, **({"hz1": hz1} if hz1 else {})), "cfg": ov,
+        meta = {"make": dict(mk, **({"hz1": hz1} if hz1 else {}), **({"disk": disk} if disk else {})), "cfg": ov,
                 "nvsmi_features": [[str(n), float(v)] for n, v in zip(nv_feats['name'], nv_feats['value'])],
                 "features": [[str(n), (None if v != v else float(v))] for n, v in zip(feats['name'], feats['value'])]}
         with open(os.path.join(out, "case.json"), "w") as f:

@@ -17,7 +17,7 @@ def golden_cases():
     out = []
     for name in sorted(os.listdir(GOLDEN)):
         p = os.path.join(GOLDEN, name, "case.json")
-        if os.path.isfile(p) and not name.startswith("side_"):      # side_* are concurrency_breakdown fixtures
+        if os.path.isfile(p) and not name.startswith(("side_", "disk_")):      # side_* / disk_* are side-file fixtures
             out.append(name)
     return out
 

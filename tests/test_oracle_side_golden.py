@@ -46,3 +46,21 @@ def test_oracle_nvsmi_profile_matches_reference(name):
     case = json.load(open(os.path.join(d, "case.json")))
     feats = orc.nvsmi_profile(pd.read_csv(d + "/nvsmi_trace.csv"), nvsmi_data=os.path.isfile(d + "/nvsmi.txt"))
     assert [(n, float(v)) for n, v in feats] == [tuple(x) for x in case["nvsmi_features"][1:]]
+
+
+def test_oracle_diskstat_matches_reference(tmp_path):
+    """diskstat.txt (N1, oracle only so far): diskstat.csv, both vector tables and the report.js series."""
+    import shutil
+    from helpers import demangle
+    name = "disk_small"
+    d = os.path.join(GOLDEN, name)
+    logdir = str(tmp_path) + "/"
+    os.environ['TZ'] = 'UTC'
+    import time
+    time.tzset()
+    for fn in ("mpstat.txt", "nvsmi_query.txt", "netstat.txt", "diskstat.txt", "perf.script", "sofa_time.txt",
+               "perf_events_used.txt", "perf_timebase.txt", "misc.txt"):
+        shutil.copy(os.path.join(d, fn), logdir + fn)
+    orc.preprocess(orc.OracleConfig(logdir, nprocs=1), demangle=demangle)
+    for fn in ("diskstat.csv", "diskstat_vector.csv", "diskstat_vector_ui.csv", "report.js"):
+        assert open(logdir + fn, "rb").read() == open(os.path.join(d, fn), "rb").read(), fn
