@@ -521,7 +521,7 @@ def cpu_baseline_sample(args, wl):
     import shutil
     shutil.rmtree(work, ignore_errors=True)
     return {"value": n / dt, "unit": "events/s", "cores": cores, "kind": "port",
-            "sample": "first %d events of the same mixed trace (60/35/5), oracle preprocess + gpu_profile, %.1f s" % (n, dt)}
+            "sample": "first %d events of the same mixed trace (60/35/5), oracle preprocess (trace + side files) + gpu/net/nvsmi profiles + concurrency_breakdown, %.1f s" % (n, dt)}
 
 
 def run_reference(args):

@@ -370,6 +370,76 @@ def preprocess_diskstat(logdir, absolute_timestamp, time_base, diskstat_filters=
     return traces
 
 
+def preprocess_blktrace(logdir):
+    """blktrace.txt -> blktrace.csv (D rows, then completion latencies).  sofa_preprocess.py:688-781.
+    Returns (starting-block frame, latency frame, cpuid left behind for later sections).  Oracle only so far."""
+    with open(logdir + 'blktrace.txt') as f:
+        lines = f.readlines()
+    d_dict, d_list, c_list = {}, [], []
+    cpuid = None
+    for line in lines:
+        if len(line) > 50 and "Read" not in line and "CPU" not in line and "IO unplugs" not in line:
+            fields = line.split()
+            cpu = fields[1]
+            ts = float(fields[3])
+            pid = fields[4]
+            event = fields[5]
+            try:
+                start_block = int(fields[7])
+            except Exception:
+                start_block = 0
+            cpuid = cpu
+            trace = [ts, event, start_block, cpu, -1, -1, -1, -1, -1, pid, pid, 'starting_block=' + str(start_block), cpu]
+            if event == 'D':                       # the reference writes `'D' is event` (interned one-character strings)
+                d_list.append(trace)
+                d_dict[start_block] = trace
+            if event == 'C':
+                if start_block not in d_dict:
+                    continue
+                d_event = d_dict[start_block]
+                lat = float(ts - d_event[0])
+                c_list.append([d_event[0], event, float(lat), cpu, -1, -1, -1, -1, -1, pid, pid, 'latency=%0.6f' % float(lat), cpu])
+    return _to_csv_list(d_list, logdir + 'blktrace.csv', 'w'), _to_csv_list(c_list, logdir + 'blktrace.csv', 'a'), cpuid
+
+
+STRACE_FILTER_KEYS = ('resume', 'nanosleep', 'clock_gettime', 'brk', 'stat', 'close', 'exited', 'access', 'lseek', 'getrusage', 'exited')
+
+
+def preprocess_strace(logdir, absolute_timestamp, time_base, plot_ratio, pid, strace_min_time, cpuid):
+    """strace.txt -> strace.csv.  sofa_preprocess.py:1618-1704.  `cpuid` is whatever an earlier section left in
+    that variable (the reference never sets it here).  Oracle only so far."""
+    with open(logdir + 'strace.txt') as f:
+        lines = f.readlines()
+    rows = []
+    if len(lines) > 1:
+        for i in range(len(lines)):
+            if i % plot_ratio > 0:
+                continue
+            if any(lines[i].find(key) != -1 for key in STRACE_FILTER_KEYS):
+                continue
+            fields = lines[i].split()
+            if fields[0].find('pid') != -1:
+                tid = int(fields[1].split(']')[0])
+                t_begin = float(fields[2])
+                info = ''.join(fields[3:-3])
+            else:
+                tid = pid
+                t_begin = float(fields[1])
+                info = ''.join(fields[1:-3])
+            if not absolute_timestamp:
+                t_begin = t_begin - time_base
+            try:
+                duration = float(fields[-1].split('<')[1].split('>')[0])
+            except Exception:
+                duration = 0
+            if duration < strace_min_time:
+                continue
+            if cpuid is None:
+                raise NameError("name 'cpuid' is not defined")
+            rows.append([t_begin, -1, duration, -1, -1, -1, -1, -1, -1, pid, tid, info, cpuid])
+    return _to_csv_list(rows, logdir + 'strace.csv', 'w')
+
+
 def preprocess_vmstat(logdir, absolute_timestamp, time_base):
     """vmstat.txt -> vmstat.csv (bi, bo, in, cs, wa, st, usr, sys lists).  sofa_preprocess.py:787-1008.
     Returns the eight frames in that order."""
@@ -509,16 +579,32 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
     vm = [[] for _ in range(8)]
     nvsmi_enc, nvsmi_dec = [], []
     diskstat_traces = []
+    blk_d_traces, blk_traces, strace_traces = [], [], []
+    cpuid = None                                    # a local of the reference that leaks from section to section
+    if os.path.isfile(logdir + 'blktrace.txt'):
+        with open(logdir + 'blktrace.txt') as f:
+            if len(f.readlines()) > 0:
+                blk_d_traces, blk_traces, c_ = preprocess_blktrace(logdir)
+                cpuid = c_ if c_ is not None else cpuid
     if os.path.isfile(logdir + 'diskstat.txt'):
         diskstat_traces = preprocess_diskstat(logdir, cfg.absolute_timestamp, time_base, getattr(cfg, 'diskstat_filters', None))
     if os.path.isfile(logdir + 'vmstat.txt'):
         with open(logdir + 'vmstat.txt') as f:
             if len(f.readlines()) > 0:                                    # :791
                 vm = preprocess_vmstat(logdir, cfg.absolute_timestamp, time_base)
+                if len(vm[0]) > 0:
+                    cpuid = -1
     if os.path.isfile(logdir + 'nvsmi_query.txt'):
         nvsmi_sm, nvsmi_mem = preprocess_nvsmi_query(logdir, cfg.absolute_timestamp, time_base, cfg.nvsmi_time_zone)
+        if len(nvsmi_sm) > 0:
+            cpuid = int(nvsmi_sm['deviceId'].iloc[-1])
     if os.path.isfile(logdir + 'nvsmi.txt'):
         nvsmi_enc, nvsmi_dec, cfg.nvsmi_data = preprocess_nvsmi_dmon(logdir, cfg.absolute_timestamp, time_base)
+        with open(logdir + 'nvsmi.txt') as f:
+            dm = [ln.split() for ln in f.readlines() if ln.find('gpu') == -1 and ln.find('Idx') == -1]
+        dm = [x for x in dm if len(x) >= 5]
+        if dm and not any(('failed' in ' '.join(x) or 'Failed' in ' '.join(x)) for x in dm):
+            cpuid = int(dm[-1][0])
     if os.path.isfile(logdir + 'netstat.txt'):
         tx_traces, rx_traces = preprocess_netstat(logdir, cfg.absolute_timestamp, time_base)
 
@@ -590,6 +676,16 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
             for kw, color in cfg.cpu_filters:                    # :1819-1827
                 filtered_cpu.append((kw, color, cpu_viz[cpu_viz['name'].str.contains(kw)]))
 
+    # ---- strace  :1618-1704 (after the trace sources in the reference; it only needs `cpuid` from above)
+    if os.path.isfile(logdir + 'strace.txt'):
+        pid = 0
+        with open(logdir + 'misc.txt') as f:
+            ml = f.readlines()
+            if len(ml) == 4:
+                pid = int(ml[3].split()[1])
+        strace_traces = preprocess_strace(logdir, cfg.absolute_timestamp, time_base, cfg.plot_ratio, pid,
+                                          getattr(cfg, 'strace_min_time', 1e-6), cpuid)
+
     # ---- series list  :1849-2102 (sources outside the hot path are empty placeholders)
     series = []
     if len(cpu_viz) > 0:
@@ -597,8 +693,8 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
         for kw, color, grp in filtered_cpu:
             series.append(Series(kw, '[keyword]' + kw, color, grp.copy()))
     vm_bi, vm_bo, vm_in, vm_cs, vm_wa, vm_st, vm_usr, vm_sys = vm
-    for nm, title, color, data in (('blktrace_starting_block', 'BLKTRACE_STARTING_BLOCK', 'Green', []),
-                                   ('blktrace_time', 'BLKTRACE_TIME', 'DodgerBlue', []),
+    for nm, title, color, data in (('blktrace_starting_block', 'BLKTRACE_STARTING_BLOCK', 'Green', blk_d_traces),
+                                   ('blktrace_time', 'BLKTRACE_TIME', 'DodgerBlue', blk_traces),
                                    ('vmstat_cs', 'VMSTAT_CS', 'Pink', vm_cs),
                                    ('vmstat_bi', 'VMSTAT_BI', 'DarkOrange', vm_bi),
                                    ('vmstat_bo', 'VMSTAT_BO', 'DarkOrchid', vm_bo)):
@@ -612,8 +708,8 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
         series.append(Series('vmstat_sys', 'CPU_USAGE_SYS', 'LightBlue', vm_sys))
         series.append(Series('vmstat_in', 'VMSTAT_IN', 'DarkMagenta', vm_in))
         series.append(Series('vmstat_cs', 'VMSTAT_CS', 'DarkOliveGreen', vm_cs))
-    for nm in ('strace', 'pystacks'):
-        series.append(Series(nm, nm, '', []))
+    series.append(Series('strace', 'STRACE.', 'DarkSlateGray', strace_traces))
+    series.append(Series('pystacks', 'Python-stacks.', 'Tomato', []))
     series.append(Series('nvsmi_mem', 'GPU_MEM_Util.', 'lightblue', nvsmi_mem))
     series.append(Series('nvsmi_sm', 'GPU_SM_Util.', 'red', nvsmi_sm))
     if cfg.enable_encode_decode:                                            # :2033-2050

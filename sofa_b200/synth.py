@@ -388,6 +388,51 @@ def write_diskstat(logdir, seed, n_samples=40, devs=("sda", "sda1", "nvme0n1", "
                 f.write("%.6f,%s,%s\n" % (t, d, ",".join(str(v) for v in cum[d])))
 
 
+def write_strace_blktrace(logdir, seed, n_strace=300, n_blk=200):
+    """strace.txt as `strace -q -T -tt(t) -f -o` writes it (pid prefix, epoch stamps, `<duration>` suffix) and
+    blktrace.txt as `blkparse` prints it (sofa_record.py:337, 444); both opt-in recorder outputs."""
+    os.makedirs(logdir, exist_ok=True)
+    calls = ["read(3, \"abc\\n\", 4096) = 4", "write(1, \"x, y\", 4) = 4", "mmap(NULL, 262144, PROT_READ|PROT_WRITE, MAP_PRIVATE|MAP_ANONYMOUS, -1, 0) = 0x7f501f910000",
+             "futex(0x7f50, FUTEX_WAIT_PRIVATE, 2, NULL) = 0", "openat(AT_FDCWD, \"/etc/ld.so.cache\", O_RDONLY|O_CLOEXEC) = 3", "ioctl(4, TCGETS, 0x7ffd) = -1 ENOTTY (Inappropriate ioctl for device)",
+             "close(3) = 0", "nanosleep({tv_sec=0, tv_nsec=1000}, NULL) = 0", "poll([{fd=5, events=POLLIN}], 1, 100) = 1 ([{fd=5, revents=POLLIN}])"]
+    t = TIME_BASE + 0.4
+    with open(os.path.join(logdir, "strace.txt"), "w") as f:
+        for i in range(n_strace):
+            r = rnd(seed, 13, i, 0)
+            t += (r % 5000) / 1e6
+            pid = 4242 + (r >> 13) % 3
+            call = calls[(r >> 16) % len(calls)]
+            dur = ((r >> 24) % 200000) / 1e6
+            if (r >> 50) % 23 == 0:
+                f.write("%d %.6f +++ exited with 0 +++\n" % (pid, t))
+            elif (r >> 45) % 17 == 0:
+                f.write("[pid %5d] %.6f %s <%.6f>\n" % (pid, t, call, dur))
+            elif (r >> 40) % 19 == 0:
+                f.write("%d %.6f %s <unfinished ...>\n" % (pid, t, call.split(" = ")[0]))
+            else:
+                f.write("%d %.6f %s <%.6f>\n" % (pid, t, call, dur))
+    with open(os.path.join(logdir, "blktrace.txt"), "w") as f:
+        tb = 0.0
+        seq = 0
+        pending = []
+        for i in range(n_blk):
+            r = rnd(seed, 14, i, 0)
+            tb += (r % 3000) / 1e6
+            seq += 1
+            cpu = (r >> 12) % 8
+            blk = 691248304 + 1024 * ((r >> 16) % 40)
+            if pending and (r >> 30) % 3 == 0:
+                b0 = pending.pop(0)
+                f.write("  8,0  %3d %8d %14.9f %5d  C   W %d + 1024 [0]\n" % (cpu, seq, tb, 0, b0))
+            else:
+                ev = "QGID"[(r >> 34) % 4]
+                f.write("  8,0  %3d %8d %14.9f %5d  %s   W %d + 1024 [dd]\n" % (cpu, seq, tb, 31479, ev, blk))
+                if ev == "D":
+                    pending.append(blk)
+        f.write("CPU0 (8,0):\n Reads Queued:           0,        0KiB\t Writes Queued:         100,    51200KiB\n")
+        f.write("Total (8,0):\n IO unplugs:             5        \t Timer unplugs:           0\n")
+
+
 def side_csv_bodies(seed, n_samples, n_cores, n_gpus, rate_hz=10):
     """Header-less bodies of mpstat.csv, nvsmi_trace.csv, netstat.csv in the format the reference's
     preprocess writes them (tests/golden/side_small), for concurrency_breakdown at scale."""

@@ -29,6 +29,9 @@ CASES = {
                   dict(enable_vmstat=True, enable_encode_decode=True)),
     # diskstat.txt (oracle-only fixture: the device path does not cover diskstat yet)
     "disk_small": (dict(seed=95, n_samples=30, n_cores=2, n_gpus=1, disk=dict(n_samples=40)), dict()),
+    # strace.txt + blktrace.txt (oracle-only fixture, opt-in recorder outputs; vmstat / nvsmi give `cpuid` its value)
+    "oracle_strace_blk": (dict(seed=96, n_samples=30, n_cores=2, n_gpus=2, hz1=dict(n_seconds=10, n_gpus=2),
+                               strace=dict(n_strace=300, n_blk=200)), dict(plot_ratio=2)),
     "side_abs": (dict(seed=94, n_samples=40, n_cores=2, n_gpus=3, hz1=dict(n_seconds=12, n_gpus=3)),
                  dict(absolute_timestamp=True, enable_vmstat=True, enable_encode_decode=True)),
 }
@@ -50,11 +53,14 @@ def main():
         mk = dict(mk)
         hz1 = mk.pop("hz1", None)
         disk = mk.pop("disk", None)
+        strace = mk.pop("strace", None)
         synth.write_side_raw(logdir, **mk)
         if hz1:
             synth.write_side_raw_1hz(logdir, mk["seed"], **hz1)
         if disk:
             synth.write_diskstat(logdir, mk["seed"], **disk)
+        if strace:
+            synth.write_strace_blktrace(logdir, mk["seed"], **strace)
         cfg = mg.make_ref_cfg(logdir, ov)
         import sofa_preprocess as ref_pre
         with contextlib.redirect_stdout(io.StringIO()):
@@ -86,12 +92,16 @@ def main():
         if disk:
             for fn in ("diskstat.txt", "diskstat.csv", "diskstat_vector.csv", "diskstat_vector_ui.csv"):
                 shutil.copy(logdir + fn, os.path.join(out, fn))
+        if strace:
+            for fn in ("strace.txt", "blktrace.txt", "strace.csv", "blktrace.csv"):
+                shutil.copy(logdir + fn, os.path.join(out, fn))
         for fn in ("mpstat.csv", "nvsmi_trace.csv", "netstat.csv", "cputrace.csv", "performance.csv", "misc.txt",
                    "usr_sys.csv", "netbandwidth.csv", "report.js",
                    "mpstat.txt", "nvsmi_query.txt", "netstat.txt", "perf.script", "sofa_time.txt",
                    "perf_events_used.txt", "perf_timebase.txt", "nvsmi_profile_verbose.txt"):
             shutil.copy(logdir + fn, os.path.join(out, fn))
-        meta = {"make": dict(mk, **({"hz1": hz1} if hz1 else {}), **({"disk": disk} if disk else {})), "cfg": ov,
+        meta = {"make": dict(mk, **({"hz1": hz1} if hz1 else {}), **({"disk": disk} if disk else {}),
+                             **({"strace": strace} if strace else {})), "cfg": ov,
                 "nvsmi_features": [[str(n), float(v)] for n, v in zip(nv_feats['name'], nv_feats['value'])],
                 "features": [[str(n), (None if v != v else float(v))] for n, v in zip(feats['name'], feats['value'])]}
         with open(os.path.join(out, "case.json"), "w") as f:

@@ -64,3 +64,21 @@ def test_oracle_diskstat_matches_reference(tmp_path):
     orc.preprocess(orc.OracleConfig(logdir, nprocs=1), demangle=demangle)
     for fn in ("diskstat.csv", "diskstat_vector.csv", "diskstat_vector_ui.csv", "report.js"):
         assert open(logdir + fn, "rb").read() == open(os.path.join(d, fn), "rb").read(), fn
+
+
+def test_oracle_strace_blktrace_match_reference(tmp_path):
+    """strace.txt / blktrace.txt (N1, oracle only so far): strace.csv, blktrace.csv and their report.js series."""
+    import shutil
+    import time
+    from helpers import demangle
+    d = os.path.join(GOLDEN, "oracle_strace_blk")
+    case = json.load(open(os.path.join(d, "case.json")))
+    logdir = str(tmp_path) + "/"
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
+    for fn in ("mpstat.txt", "nvsmi_query.txt", "netstat.txt", "vmstat.txt", "nvsmi.txt", "strace.txt", "blktrace.txt", "perf.script",
+               "sofa_time.txt", "perf_events_used.txt", "perf_timebase.txt", "misc.txt"):
+        shutil.copy(os.path.join(d, fn), logdir + fn)
+    orc.preprocess(orc.OracleConfig(logdir, nprocs=1, **case["cfg"]), demangle=demangle)
+    for fn in ("strace.csv", "blktrace.csv", "vmstat.csv", "nvsmi_trace.csv", "report.js"):
+        assert open(logdir + fn, "rb").read() == open(os.path.join(d, fn), "rb").read(), fn
