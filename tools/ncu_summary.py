@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Summaries of ncu exports (how profiles/r01_summary.md's tables were produced).
+
+  launches  FILE.csv[.gz]            aggregate a `--metrics gpu__time_duration.sum --csv` launch list per kernel
+  source    RAW.csv SRC.csv[.gz] [N] key metrics of `ncu -i rep --page raw --csv` plus the N hottest source lines of
+                                     `ncu -i rep --page source --csv --print-source cuda,sass`: share of executed
+                                     warp instructions, share of stall samples, average active lanes per line
+
+Typical capture on the GPU box (one kernel, one launch; keep the exports, drop the 40 MB report):
+  SOFA_KINDS=1 SOFA_ANALYZE=0 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \\
+      -k regex:"k_emit_fused<\\(int\\)1, \\(int\\)1>" --launch-count 1 -o /tmp/p -f python tools/profile_step.py 4000000 1
+  ncu -i /tmp/p.ncu-rep --page raw --csv > gpurun_out/raw.csv
+  ncu -i /tmp/p.ncu-rep --page source --csv --print-source cuda,sass | gzip > gpurun_out/src.csv.gz
+"""
+import collections
+import csv
+import gzip
+import io
+import re
+import sys
+
+
+def _open(path):
+    return io.TextIOWrapper(gzip.open(path)) if path.endswith(".gz") else open(path)
+
+
+def launches(path):
+    rows = list(csv.reader(_open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in data:
+        if len(r) <= vi:
+            continue
+        name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("sofa::", "")
+        v = float(r[vi].replace(",", ""))
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[ui], 1.0)
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    print("kernel,launches,total_ms,share_pct,avg_ms   # %d launches, %.1f ms" % (sum(v[0] for v in agg.values()), tot))
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%s,%d,%.3f,%.1f,%.4f" % (k, v[0], v[1], 100 * v[1] / tot, v[1] / v[0]))
+
+
+RAW_KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+            "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+
+
+def source(raw_path, src_path, top=24):
+    raw = list(csv.reader(_open(raw_path)))
+    h = raw[0]
+    for r in raw[2:]:
+        print({w: r[h.index(w)][:48] for w in RAW_KEYS if w in h})
+    rows = list(csv.reader(_open(src_path)))
+    cur = hdr = None
+    inst, tinst, stall, text = collections.Counter(), collections.Counter(), collections.Counter(), {}
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur, hdr = r[1].split("/")[-1], None
+            continue
+        if r[0] == "Function Name":
+            continue
+        if r[0] == "Line No":
+            hdr = r
+            ii, ti = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+            si = hdr.index("Warp Stall Sampling (All Samples)")
+            continue
+        if hdr and cur and len(r) > ti:
+            try:
+                ln, a, b, c = int(r[0]), int(r[ii] or 0), int(r[ti] or 0), int(r[si] or 0)
+            except ValueError:
+                continue
+            inst[(cur, ln)] += a
+            tinst[(cur, ln)] += b
+            stall[(cur, ln)] += c
+            text[(cur, ln)] = r[1].strip()[:90]
+    tot, ts = sum(inst.values()), max(1, sum(stall.values()))
+    print("warp instructions %d, average active lanes %.1f" % (tot, sum(tinst.values()) / max(1, tot)))
+    for kk, v in inst.most_common(top):
+        print("  inst %4.1f%%  stall %4.1f%%  lanes %4.1f  %s:%d  %s" % (100 * v / tot, 100 * stall[kk] / ts, tinst[kk] / max(v, 1),
+                                                                       kk[0], kk[1], text[kk]))
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    elif len(sys.argv) >= 4 and sys.argv[1] == "source":
+        source(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 24)
+    else:
+        sys.exit(__doc__)
