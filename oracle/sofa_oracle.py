@@ -402,6 +402,36 @@ def preprocess_blktrace(logdir):
     return _to_csv_list(d_list, logdir + 'blktrace.csv', 'w'), _to_csv_list(c_list, logdir + 'blktrace.csv', 'a'), cpuid
 
 
+def preprocess_pystacks(logdir, absolute_timestamp, time_base, cpuid):
+    """pystacks.txt -> pystacks.csv.  sofa_preprocess.py:1706-1761.  list_to_csv_and_traces drops the first element
+    of the list it is given; this list has no placeholder row, so the first stack is lost - as in the reference.
+    Oracle only so far."""
+    import itertools
+    ret = {}
+    with open(logdir + 'pystacks.txt', 'r') as f:
+        for ts, fs in itertools.zip_longest(*[f] * 2):
+            fs = fs.replace('\n', '').replace(';', '<br>')
+            if fs.find('idle') != -1:
+                continue
+            ret[int(ts) / 10 ** 6] = fs
+    duration = {}
+    prev = None
+    for k in ret:
+        if prev is None:
+            prev = k
+            continue
+        duration[prev] = k - prev
+        prev = k
+    del ret[max(ret.keys())]
+    rows = []
+    for key, info in ret.items():
+        if cpuid is None:
+            raise NameError("name 'cpuid' is not defined")
+        t_begin = key if absolute_timestamp else key - time_base
+        rows.append([t_begin, -1, float(duration[key]), -1, -1, -1, -1, -1, -1, -1, -1, info, cpuid])
+    return _to_csv_list(rows[1:], logdir + 'pystacks.csv', 'w') if rows else []
+
+
 STRACE_FILTER_KEYS = ('resume', 'nanosleep', 'clock_gettime', 'brk', 'stat', 'close', 'exited', 'access', 'lseek', 'getrusage', 'exited')
 
 
@@ -686,6 +716,10 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
         strace_traces = preprocess_strace(logdir, cfg.absolute_timestamp, time_base, cfg.plot_ratio, pid,
                                           getattr(cfg, 'strace_min_time', 1e-6), cpuid)
 
+    pystacks_traces = []
+    if os.path.isfile(logdir + 'pystacks.txt'):                              # :1730-1761
+        pystacks_traces = preprocess_pystacks(logdir, cfg.absolute_timestamp, time_base, cpuid)
+
     # ---- series list  :1849-2102 (sources outside the hot path are empty placeholders)
     series = []
     if len(cpu_viz) > 0:
@@ -709,7 +743,7 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
         series.append(Series('vmstat_in', 'VMSTAT_IN', 'DarkMagenta', vm_in))
         series.append(Series('vmstat_cs', 'VMSTAT_CS', 'DarkOliveGreen', vm_cs))
     series.append(Series('strace', 'STRACE.', 'DarkSlateGray', strace_traces))
-    series.append(Series('pystacks', 'Python-stacks.', 'Tomato', []))
+    series.append(Series('pystacks', 'Python-stacks.', 'Tomato', pystacks_traces))
     series.append(Series('nvsmi_mem', 'GPU_MEM_Util.', 'lightblue', nvsmi_mem))
     series.append(Series('nvsmi_sm', 'GPU_SM_Util.', 'red', nvsmi_sm))
     if cfg.enable_encode_decode:                                            # :2033-2050

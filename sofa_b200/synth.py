@@ -433,6 +433,19 @@ def write_strace_blktrace(logdir, seed, n_strace=300, n_blk=200):
         f.write("Total (8,0):\n IO unplugs:             5        \t Timer unplugs:           0\n")
 
 
+def write_pystacks(logdir, seed, n=60):
+    """pystacks.txt as `pyflame --flamechart -t` writes it: a microsecond time stamp line, then the stack line."""
+    frames = ["train.py:main:10", "model.py:forward:55", "ops.py:conv2d:120", "data.py:next_batch:33", "(idle)", "optim.py:step:77"]
+    t = int((TIME_BASE + 0.45) * 1e6)
+    with open(os.path.join(logdir, "pystacks.txt"), "w") as f:
+        for i in range(n):
+            r = rnd(seed, 15, i, 0)
+            t += 1000 + r % 50000
+            depth = 1 + (r >> 16) % 4
+            stack = ";".join(frames[(r >> (20 + 3 * k)) % len(frames)] for k in range(depth))
+            f.write("%d\n%s\n" % (t, stack))
+
+
 def side_csv_bodies(seed, n_samples, n_cores, n_gpus, rate_hz=10):
     """Header-less bodies of mpstat.csv, nvsmi_trace.csv, netstat.csv in the format the reference's
     preprocess writes them (tests/golden/side_small), for concurrency_breakdown at scale."""

@@ -61,6 +61,7 @@ def main():
             synth.write_diskstat(logdir, mk["seed"], **disk)
         if strace:
             synth.write_strace_blktrace(logdir, mk["seed"], **strace)
+            synth.write_pystacks(logdir, mk["seed"])
         cfg = mg.make_ref_cfg(logdir, ov)
         import sofa_preprocess as ref_pre
         with contextlib.redirect_stdout(io.StringIO()):
@@ -93,7 +94,7 @@ def main():
             for fn in ("diskstat.txt", "diskstat.csv", "diskstat_vector.csv", "diskstat_vector_ui.csv"):
                 shutil.copy(logdir + fn, os.path.join(out, fn))
         if strace:
-            for fn in ("strace.txt", "blktrace.txt", "strace.csv", "blktrace.csv"):
+            for fn in ("strace.txt", "blktrace.txt", "strace.csv", "blktrace.csv", "pystacks.txt", "pystacks.csv"):
                 shutil.copy(logdir + fn, os.path.join(out, fn))
         for fn in ("mpstat.csv", "nvsmi_trace.csv", "netstat.csv", "cputrace.csv", "performance.csv", "misc.txt",
                    "usr_sys.csv", "netbandwidth.csv", "report.js",

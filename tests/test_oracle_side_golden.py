@@ -67,7 +67,7 @@ def test_oracle_diskstat_matches_reference(tmp_path):
 
 
 def test_oracle_strace_blktrace_match_reference(tmp_path):
-    """strace.txt / blktrace.txt (N1, oracle only so far): strace.csv, blktrace.csv and their report.js series."""
+    """strace.txt / blktrace.txt / pystacks.txt (N1, oracle only so far): their CSVs and report.js series."""
     import shutil
     import time
     from helpers import demangle
@@ -76,9 +76,9 @@ def test_oracle_strace_blktrace_match_reference(tmp_path):
     logdir = str(tmp_path) + "/"
     os.environ['TZ'] = 'UTC'
     time.tzset()
-    for fn in ("mpstat.txt", "nvsmi_query.txt", "netstat.txt", "vmstat.txt", "nvsmi.txt", "strace.txt", "blktrace.txt", "perf.script",
+    for fn in ("mpstat.txt", "nvsmi_query.txt", "netstat.txt", "vmstat.txt", "nvsmi.txt", "strace.txt", "blktrace.txt", "pystacks.txt", "perf.script",
                "sofa_time.txt", "perf_events_used.txt", "perf_timebase.txt", "misc.txt"):
         shutil.copy(os.path.join(d, fn), logdir + fn)
     orc.preprocess(orc.OracleConfig(logdir, nprocs=1, **case["cfg"]), demangle=demangle)
-    for fn in ("strace.csv", "blktrace.csv", "vmstat.csv", "nvsmi_trace.csv", "report.js"):
+    for fn in ("strace.csv", "blktrace.csv", "pystacks.csv", "vmstat.csv", "nvsmi_trace.csv", "report.js"):
         assert open(logdir + fn, "rb").read() == open(os.path.join(d, fn), "rb").read(), fn
