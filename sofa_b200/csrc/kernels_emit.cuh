@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) k_filter(SrcView src, uint64_t ncand, uin
     }
 }
 
+#ifdef SOFA_K_VIZ
 // ---------------------------------------------------------------------------- viz-name dictionary
 // Hash every down-sampled perf row's raw viz name; mangled ones (_Z...) go into an
 // open-addressing table (key = FNV-1a 64, value = smallest row) for host demangling.
@@ -218,6 +219,8 @@ __global__ void __launch_bounds__(256) k_viz_resolve(const uint64_t* __restrict_
     viz_id[c] = id;
 }
 
+#endif  // SOFA_K_VIZ
+
 }  // namespace sofa
 
 // ============================================================================ single-pass emit
@@ -266,14 +269,14 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 }
 
 // candidate indices whose filter bit is set, ascending (two-pass compaction)
-__global__ void __launch_bounds__(256) k_mask_count(const uint8_t* __restrict__ mask, int bit, uint64_t n, uint64_t* blockoff) {
+static __global__ void __launch_bounds__(256) k_mask_count(const uint8_t* __restrict__ mask, int bit, uint64_t n, uint64_t* blockoff) {
     __shared__ uint32_t sm[33];
     uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     uint32_t total;
     block_excl_scan((i < n && ((mask[i] >> bit) & 1)) ? 1u : 0u, &total, sm);
     if (threadIdx.x == 0) blockoff[blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(256) k_mask_write(const uint8_t* __restrict__ mask, int bit, uint64_t n, const uint64_t* blockoff,
+static __global__ void __launch_bounds__(256) k_mask_write(const uint8_t* __restrict__ mask, int bit, uint64_t n, const uint64_t* blockoff,
                                                     uint32_t* __restrict__ index) {
     __shared__ uint32_t sm[33];
     uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;

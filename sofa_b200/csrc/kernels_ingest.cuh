@@ -35,6 +35,7 @@ __device__ __forceinline__ uint32_t newline_mask4(uint32_t w) {       // 0xff in
     return __vcmpeq4(w, 0x0a0a0a0au);
 }
 
+#ifdef SOFA_K_COUNT
 // Line starts owned by tile t: `begin` itself (first tile) and q+1 for every newline at
 // q in [max(b0-1,begin), min(b1-1,end-1)).
 __global__ void __launch_bounds__(PARSE_TPB)
@@ -85,8 +86,10 @@ k_count_lines(const char* __restrict__ text, uint64_t begin, uint64_t end, uint3
     if (cr) atomicOr(cr_flag, 1u);
 }
 
-// In-place exclusive scan of a[0..n) (single block); a[n] = total.
-__global__ void __launch_bounds__(1024) k_scan_u64(uint64_t* a, uint64_t n) {
+#endif  // SOFA_K_COUNT
+
+// In-place exclusive scan of a[0..n) (single block); a[n] = total.  (static: every translation unit that scans gets its own copy)
+static __global__ void __launch_bounds__(1024) k_scan_u64(uint64_t* a, uint64_t n) {
     __shared__ uint64_t sm[33];
     constexpr int PER = 8;
     uint64_t carry = 0;
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(1024) k_scan_u64(uint64_t* a, uint64_t n) {
 // Large scans in three launches: every block scans 8192 elements in place and leaves its total in
 // part[block]; k_scan_u64 scans the totals; k_scan_add adds them back (and stores a[n] = grand total).
 constexpr uint32_t SCAN_BLOCK_ELEMS = 8192;
-__global__ void __launch_bounds__(1024) k_scan_part(uint64_t* a, uint64_t n, uint64_t* part) {
+static __global__ void __launch_bounds__(1024) k_scan_part(uint64_t* a, uint64_t n, uint64_t* part) {
     __shared__ uint64_t sm[33];
     constexpr int PER = 8;
     uint64_t v[PER];
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(1024) k_scan_part(uint64_t* a, uint64_t n, uin
     for (int k = 0; k < PER; k++) { if (i0 + k < n) a[i0 + k] = ex; ex += v[k]; }
     if (threadIdx.x == 0) part[blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(1024) k_scan_add(uint64_t* a, uint64_t n, const uint64_t* __restrict__ part, uint32_t nparts) {
+static __global__ void __launch_bounds__(1024) k_scan_add(uint64_t* a, uint64_t n, const uint64_t* __restrict__ part, uint32_t nparts) {
     uint64_t off = part[blockIdx.x];
     uint64_t i0 = (uint64_t)blockIdx.x * SCAN_BLOCK_ELEMS + (uint64_t)threadIdx.x * 8;
 #pragma unroll

@@ -9,6 +9,7 @@ namespace sofa {
 struct SideOutCols { double *ts, *f1, *f2; int64_t* i; uint8_t* cls; const double* ext; const uint32_t* ext_idx; };
 // i: 6 per row; cls: 0 dropped, 1 trace row, 2 usr_sys row; ext: the raw RAW_NF doubles of line ext_idx[row] (vmstat)
 
+#ifdef SOFA_K_SIDE
 // what[0] = first line with nf > 0 (min), what[1] |= 1 when some line is flagged "failed"
 __global__ void __launch_bounds__(256) k_side_first(RawCols r, uint64_t n, unsigned long long* what) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,6 +118,8 @@ __global__ void __launch_bounds__(128) k_side_dmon(RawCols r, const uint32_t* __
     o.cls[j] = (uint8_t)q.cls; o.ts[j] = q.ts; o.f1[j] = 0; o.f2[j] = 0;
     for (int k = 0; k < 6; k++) o.i[j * 6 + k] = q.i[k];
 }
+
+#endif  // SOFA_K_SIDE
 
 __device__ __forceinline__ SideOutRow load_sideout(const SideOutCols& o, uint64_t i) {
     SideOutRow q;

@@ -1,0 +1,13 @@
+// libsofa_b200.so, translation unit: analyze half (gpu_profile, comm_profile, top-k, cpu_profile, net_profile,
+// nvsmi_profile, window reduction of concurrency_breakdown).
+#include "ctx.cuh"
+#include "kernels_analyze.cuh"
+#include "kernels_sort.cuh"
+#include "kernels_window.cuh"
+
+extern "C" {
+
+#include "capi_analyze.inc"
+#include "capi_window.inc"
+
+}  // extern "C"

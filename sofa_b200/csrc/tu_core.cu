@@ -1,0 +1,358 @@
+// libsofa_b200.so, translation unit 1: context lifecycle, transfers, line index + parse driver, dtype flags,
+// statistics.  The kernels live in inst/*.cu (one instantiation per file, compiled in parallel).
+#include "ctx.cuh"
+
+thread_local std::string g_last_error;
+static const char* KERNEL_NAMES[K_NKINDS] = {
+    "count_lines", "scan", "parse", "row_flags", "csv_emit", "json_emit", "filter",
+    "viz_dict", "analyze", "sort", "synth"};
+
+int need_parsed(sofa_ctx* c, int k) {
+    if (!c || k < 0 || k > 2) FAIL(SOFA_ERR_ARG, "bad source");
+    if (!c->src[k].parsed) FAIL(SOFA_ERR_STATE, "source not parsed");
+    CK(cudaSetDevice(c->device));
+    c->pending.clear(); c->stage_cur = 0;          // drop read-backs orphaned by an earlier failed call
+    return 0;
+}
+
+extern "C" {
+
+int sofa_b200_abi_version(void) { return SOFA_B200_ABI_VERSION; }
+const char* sofa_b200_last_error(void) { return g_last_error.c_str(); }
+const char* sofa_b200_kernel_name(int kind) { return (kind >= 0 && kind < K_NKINDS) ? KERNEL_NAMES[kind] : ""; }
+
+int sofa_b200_error_row(sofa_ctx* c, uint64_t* row, int32_t* code) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    if (row) *row = c->err_row;
+    if (code) *code = c->err_code;
+    return 0;
+}
+
+int sofa_b200_create(sofa_ctx** out, int device) {
+    if (!out) FAIL(SOFA_ERR_ARG, "null out");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) FAIL(SOFA_ERR_CUDA, "no CUDA device: libsofa_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) FAIL(SOFA_ERR_ARG, "bad device index");
+    CK(cudaSetDevice(device));
+    sofa_ctx* c = new sofa_ctx();
+    c->device = device;
+    memset(&c->stats, 0, sizeof c->stats);
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->out_ev[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_alt_ev[i], cudaEventDisableTiming)); }
+    for (int i = 0; i < 11; i++) CK(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 16; i++) { CK(cudaEventCreateWithFlags(&c->fetch_ev[i], cudaEventDisableTiming)); c->fetch_used[i] = false; }
+    CK(cudaHostAlloc((void**)&c->stage_h, c->stage_cap, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&c->stage_d, c->stage_h, 0));
+    CK(cudaMalloc(&c->d_err, 8 * 16));
+    CK(cudaMalloc(&c->d_flags, 4 * 8));
+    { int e_attr = set_kernel_attrs(); if (e_attr) { g_last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)e_attr); return SOFA_ERR_CUDA; } }
+    *out = c;
+    return 0;
+}
+
+int sofa_b200_destroy(sofa_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
+    if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
+    for (int i = 0; i < 2; i++) { if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); if (c->out_alt_ev[i]) cudaEventDestroy(c->out_alt_ev[i]); c->out_alt[i].release(); }
+    for (int i = 0; i < 11; i++) if (c->up_ev[i]) cudaEventDestroy(c->up_ev[i]);
+    for (int i = 0; i < 16; i++) cudaEventDestroy(c->fetch_ev[i]);
+    for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto& e : c->pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
+    for (int k = 0; k < 11; k++) {
+        Source& s = c->src[k];
+        s.text.release(); s.mhz.release(); s.mask.release(); s.vizhash.release(); s.viz_id.release();
+        s.dict_hash.release(); s.dict_off.release(); s.dict_blob.release();
+        for (auto& b : s.cols) b.release();
+        if (k < 3) c->out[k].release();
+    }
+    c->tiles.release(); c->rowlen.release(); c->blockoff.release(); c->scratch.release(); c->ftable.release();
+    c->keys.release(); c->rows.release();
+    c->sk0.release(); c->sv0.release(); c->sk1.release(); c->sv1.release(); c->hist.release(); c->segs.release();
+    c->sums.release(); c->small.release(); c->arena.release(); c->scanpart.release();
+    cudaFree(c->d_err); cudaFree(c->d_flags);
+    if (c->stage_h) cudaFreeHost(c->stage_h);
+    if (c->pin_h) cudaFreeHost(c->pin_h);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+void* sofa_b200_host_alloc(uint64_t nbytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void sofa_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
+    if (!c || k < 0 || k > 10 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload: bad argument");
+    if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload: data_off beyond the text");
+    CK(cudaSetDevice(c->device));
+    Source& s = c->src[k];
+    ENSURE(s.text, nbytes + 64);
+    if (nbytes) CK(cudaMemcpyAsync(s.text.p, text, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(s.text.as<char>() + nbytes, '\n', 64, c->stream));
+    CK_S(stream_sync(c));
+    c->stats.h2d_bytes += nbytes;
+    s.nbytes = nbytes; s.data_off = data_off; s.uploaded = true; s.parsed = false; s.viz_ready = false; s.n_rows = 0;
+    s.mask_stride = 0; s.nkw = 0;
+    return 0;
+}
+
+static uint32_t pick_tile_bytes(int k) { return (k == SRC_NET || k >= 3) ? 16384u : 24576u; }
+
+int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t* n_rows) {
+    if (!c || k < 0 || k > 10 || !p) FAIL(SOFA_ERR_ARG, "parse: bad argument");
+    Source& s = c->src[k];
+    if (!s.uploaded) FAIL(SOFA_ERR_STATE, "parse: nothing uploaded for this source");
+    CK(cudaSetDevice(c->device));
+    c->pending.clear(); c->stage_cur = 0;
+    IngestCfg cfg;
+    cfg.time_base = p->time_base; cfg.t_offset = p->t_offset; cfg.absolute_timestamp = p->absolute_timestamp;
+    cfg.perf_has_cycles = p->perf_has_cycles; cfg.n_mhz = p->n_mhz > 0 ? p->n_mhz : 1;
+    cfg.ts_rescale = p->ts_rescale; cfg.dt_rescale = p->dt_rescale; cfg.payload_unit = p->payload_unit;
+    cfg.n_cudaproc = p->n_cudaproc;
+    cfg.idx_start = p->idx[0]; cfg.idx_dur = p->idx[1]; cfg.idx_size = p->idx[2]; cfg.idx_thr = p->idx[3];
+    cfg.idx_ctx = p->idx[4]; cfg.idx_stream = p->idx[5]; cfg.idx_name = p->idx[6]; cfg.idx_srcctx = p->idx[7];
+    cfg.idx_dstctx = p->idx[8];
+    cfg.api_mode = p->api_mode;
+    cfg.side_table = k >= 6 ? k - 6 : (k >= 3 ? k - 3 : 0);
+    if (k == SRC_GPU && (cfg.idx_start < 0 || cfg.idx_dur < 0 || cfg.idx_name < 0))
+        FAIL(SOFA_ERR_ARG, "parse: gpu trace needs Start, Duration and Name columns");
+    ENSURE(s.mhz, 16 * (size_t)cfg.n_mhz + 16);
+    if (p->n_mhz > 0 && p->mhz_xp && p->mhz_fp) {
+        CK_S(small_h2d(c, s.mhz.p, p->mhz_xp, 8 * (size_t)cfg.n_mhz));
+        CK_S(small_h2d(c, s.mhz.as<double>() + cfg.n_mhz, p->mhz_fp, 8 * (size_t)cfg.n_mhz));
+    } else {
+        double d[2] = {0.0, 3000.0};
+        CK_S(small_h2d(c, s.mhz.p, &d[0], 8));
+        CK_S(small_h2d(c, s.mhz.as<double>() + 1, &d[1], 8));
+        CK_S(stream_sync(c));
+    }
+    cfg.mhz_xp = s.mhz.as<double>(); cfg.mhz_fp = s.mhz.as<double>() + cfg.n_mhz;
+    s.cfg = cfg;
+    s.parsed = false; s.viz_ready = false; s.mask_stride = 0;
+    s.flags_stride[0] = s.flags_stride[1] = 0;
+    if (wait_upload(c, k)) return SOFA_ERR_CUDA;
+    uint64_t begin = s.data_off, end = s.nbytes;
+    if (end <= begin) { s.n_rows = 0; s.parsed = true; if (n_rows) *n_rows = 0; return 0; }
+    uint32_t tile = pick_tile_bytes(k);
+    uint64_t ntiles = cdiv(end - begin, tile);
+    if (ntiles > 0x7fffffffull) FAIL(SOFA_ERR_ARG, "parse: source too large for one call");
+    ENSURE(c->tiles, (ntiles + 2) * 8);
+    if (reset_err(c)) return SOFA_ERR_CUDA;
+    LAUNCH(c, K_COUNT, launch_count_lines((unsigned)ntiles, c->stream, s.text.as<char>(), begin, end, tile, c->tiles.as<uint64_t>(), c->d_flags));
+    CK_S(launch_scan(c, c->tiles.as<uint64_t>(), ntiles));
+    uint64_t total = 0; unsigned int cr = 0;
+    CK_S(small_d2h(c, &total, c->tiles.as<uint64_t>() + ntiles, 8));
+    CK_S(small_d2h(c, &cr, c->d_flags, 4));
+    CK_S(stream_sync(c));
+    CK(cudaGetLastError());
+    if (cr) { c->err_row = 0; c->err_code = E_CR; FAIL(SOFA_ERR_ROW, "parse: carriage return in trace text (not supported)"); }
+    if (alloc_cols(c, k, total)) return SOFA_ERR_CUDA;
+    if (k >= 6 && total) CK(cudaMemsetAsync(s.cols[RC_NF].p, 0, total * 4, c->stream));
+    s.n_rows = total;
+    uint32_t max_lines = tile / 8;
+    size_t smem = (((size_t)tile + OVERLAP_BYTES + 48) & ~(size_t)15) + (size_t)max_lines * 4;
+    AllCols cols = all_cols(c, (k >= 3 && k < 6) ? k : 3, k >= 6 ? k : 6);
+    const int tpl = k >= 6 ? SRC_RAW : (k >= 3 ? SRC_SIDE : k);
+    LAUNCH(c, K_PARSE, launch_parse(tpl, (unsigned)ntiles, smem, c->stream, s.text.as<char>(), begin, end, tile, max_lines,
+                                    c->tiles.as<uint64_t>(), cfg, cols, c->d_err));
+    int r = check_kernel_error(c, "parse");
+    if (r) return r;
+    s.parsed = true;
+    if (n_rows) *n_rows = total;
+    return 0;
+}
+
+
+int sofa_b200_row_flags(sofa_ctx* c, int k, uint32_t stride, uint32_t* flags) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (stride == 0 || !flags) FAIL(SOFA_ERR_ARG, "row_flags: bad argument");
+    Source& s = c->src[k];
+    *flags = 0;
+    if (k == SRC_PERF || s.n_rows == 0) return 0;
+    for (int i = 0; i < 2; i++) if (s.flags_stride[i] == stride) { *flags = s.flags_val[i]; return 0; }
+    uint64_t ncand = cdiv(s.n_rows, stride);
+    CK(cudaMemsetAsync(c->d_flags + 1, 0, 4, c->stream));
+    SrcView v = make_view(c, k, false);
+    if (k == SRC_GPU) LAUNCH(c, K_FLAGS, (k_row_flags<SRC_GPU><<<(unsigned)cdiv(ncand, 256), 256, 0, c->stream>>>(v, ncand, stride, c->d_flags + 1)));
+    else LAUNCH(c, K_FLAGS, (k_row_flags<SRC_NET><<<(unsigned)cdiv(ncand, 256), 256, 0, c->stream>>>(v, ncand, stride, c->d_flags + 1)));
+    CK_S(small_d2h(c, flags, c->d_flags + 1, 4));
+    CK_S(stream_sync(c));
+    CK(cudaGetLastError());
+    { int slot = s.flags_stride[0] == 0 ? 0 : 1; s.flags_stride[slot] = stride; s.flags_val[slot] = *flags; }
+    return 0;
+}
+
+
+int sofa_b200_fetch(sofa_ctx* c, int which, void* host_out, uint64_t cap) {
+    if (!c || which < 0 || which > 2 || !host_out) FAIL(SOFA_ERR_ARG, "fetch: bad argument");
+    CK(cudaSetDevice(c->device));
+    uint64_t n = c->out_n[which], skip = 0;
+    if (which == 1) { skip = n >= 2 ? 2 : n; n -= skip; }
+    if (cap < n) FAIL(SOFA_ERR_CAP, "fetch: buffer too small");
+    if (n) {
+        const char* srcp = which < 2 ? c->out_ptr[which] : c->out[which].as<char>();
+        CK(cudaMemcpyAsync(host_out, srcp + skip, n, cudaMemcpyDeviceToHost, c->stream));
+        CK_S(stream_sync(c));
+        c->stats.d2h_bytes += n;
+    }
+    return 0;
+}
+
+int sofa_b200_upload_async(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
+    if (!c || k < 0 || k > 10 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
+    if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload_async: data_off beyond the text");
+    CK(cudaSetDevice(c->device));
+    Source& s = c->src[k];
+    if (nbytes + 64 > s.text.cap) { CK_S(stream_sync(c)); CK(cudaStreamSynchronize(c->h2d)); ENSURE(s.text, nbytes + 64); }
+    // the copy must not overtake kernels of an earlier pass that still read this buffer
+    CK(cudaEventRecord(c->up_ev[k], c->stream));
+    CK(cudaStreamWaitEvent(c->h2d, c->up_ev[k], 0));
+    if (nbytes) CK(cudaMemcpyAsync(s.text.p, text, nbytes, cudaMemcpyHostToDevice, c->h2d));
+    CK(cudaMemsetAsync(s.text.as<char>() + nbytes, '\n', 64, c->h2d));
+    CK(cudaEventRecord(c->up_ev[k], c->h2d));
+    c->up_pending[k] = true;
+    c->stats.h2d_bytes += nbytes;
+    s.nbytes = nbytes; s.data_off = data_off; s.uploaded = true; s.parsed = false; s.viz_ready = false; s.n_rows = 0;
+    s.mask_stride = 0; s.nkw = 0;
+    return 0;
+}
+
+int sofa_b200_fetch_async(sofa_ctx* c, int which, void* host_out, uint64_t cap, int32_t* ticket) {
+    if (!c || which < 0 || which > 1 || !host_out) FAIL(SOFA_ERR_ARG, "fetch_async: output buffer 0 or 1");
+    CK(cudaSetDevice(c->device));
+    uint64_t n = c->out_n[which], skip = 0;
+    if (which == 1) { skip = n >= 2 ? 2 : n; n -= skip; }
+    if (cap < n) FAIL(SOFA_ERR_CAP, "fetch_async: buffer too small");
+    int t = c->fetch_next;
+    c->fetch_next = (c->fetch_next + 1) & 15;
+    if (c->fetch_used[t]) CK(cudaEventSynchronize(c->fetch_ev[t]));
+    if (n) CK(cudaMemcpyAsync(host_out, c->out_ptr[which] + skip, n, cudaMemcpyDeviceToHost, c->d2h));
+    CK(cudaEventRecord(c->out_ev[which], c->d2h));
+    CK(cudaEventRecord(c->fetch_ev[t], c->d2h));
+    c->out_busy[which] = true;
+    c->fetch_used[t] = true;
+    c->stats.d2h_bytes += n;
+    if (ticket) *ticket = t;
+    return 0;
+}
+int sofa_b200_wait_fetch(sofa_ctx* c, int32_t ticket) {
+    if (!c || ticket < 0 || ticket > 15) FAIL(SOFA_ERR_ARG, "wait_fetch: bad ticket");
+    CK(cudaSetDevice(c->device));
+    if (c->fetch_used[ticket]) CK(cudaEventSynchronize(c->fetch_ev[ticket]));
+    return 0;
+}
+int sofa_b200_sync(sofa_ctx* c) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->h2d));
+    CK_S(stream_sync(c));
+    CK(cudaStreamSynchronize(c->d2h));
+    c->arena_cur = 0;
+    return 0;
+}
+int sofa_b200_set_output_arena(sofa_ctx* c, uint64_t nbytes) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK_S(stream_sync(c));
+    CK(cudaStreamSynchronize(c->d2h));
+    if (nbytes == 0) { c->arena.release(); c->arena_on = false; c->arena_cur = 0; return 0; }
+    ENSURE(c->arena, nbytes);
+    c->arena_on = true; c->arena_cur = 0;
+    return 0;
+}
+
+int sofa_b200_get_column(sofa_ctx* c, int k, int col, void* host_out, uint64_t cap_bytes) {
+    int r = need_parsed(c, k); if (r) return r;
+    Source& s = c->src[k];
+    int slot = -1; size_t w = 0;
+    if (k == SRC_PERF) {
+        switch (col) { case 0: slot = PC_TS; w = 8; break; case 1: slot = PC_EVENT; w = 8; break; case 2: slot = PC_DUR; w = 8; break;
+                       case 9: slot = PC_PID; w = 4; break; case 10: slot = PC_TID; w = 4; break; }
+    } else if (k == SRC_GPU) {
+        switch (col) { case 0: slot = GC_TS; w = 8; break; case 2: slot = GC_DUR; w = 8; break; case 6: slot = GC_BW; w = 8; break;
+                       case 5: slot = GC_PAYLOAD; w = 8; break; case 3: slot = GC_DEV; w = 4; break; case 10: slot = GC_TID; w = 4; break;
+                       case 7: slot = GC_SRC; w = 4; break; case 8: slot = GC_DST; w = 4; break; case 4: slot = GC_KIND; w = 1; break; }
+    } else {
+        switch (col) { case 0: slot = NC_TS; w = 8; break; case 5: slot = NC_PAYLOAD; w = 8; break; case 7: slot = NC_SRC; w = 8; break;
+                       case 8: slot = NC_DST; w = 8; break; case 4: slot = NC_PROTO; w = 1; break; }
+    }
+    if (slot < 0) FAIL(SOFA_ERR_ARG, "get_column: no such stored column for this source");
+    uint64_t nb = s.n_rows * w;
+    if (cap_bytes < nb) FAIL(SOFA_ERR_CAP, "get_column: buffer too small");
+    if (nb) { CK(cudaMemcpyAsync(host_out, s.cols[slot].p, nb, cudaMemcpyDeviceToHost, c->stream)); CK_S(stream_sync(c)); }
+    return 0;
+}
+
+int sofa_b200_mark(sofa_ctx* c, int which) {
+    if (!c || which < 0 || which > 1) FAIL(SOFA_ERR_ARG, "mark: bad argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->mark[which]) CK(cudaEventCreate(&c->mark[which]));
+    CK(cudaEventRecord(c->mark[which], c->stream));
+    return 0;
+}
+int sofa_b200_elapsed_ms(sofa_ctx* c, double* ms) {
+    if (!c || !ms || !c->mark[0] || !c->mark[1]) FAIL(SOFA_ERR_ARG, "elapsed_ms: marks not set");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->mark[1]));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->mark[0], c->mark[1]));
+    *ms = f;
+    return 0;
+}
+
+int sofa_b200_set_profiling(sofa_ctx* c, int on) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (drain_events(c)) return SOFA_ERR_CUDA;
+    c->profiling = on != 0;
+    return 0;
+}
+int sofa_b200_get_stats(sofa_ctx* c, sofa_stats_t* out) {
+    if (!c || !out) FAIL(SOFA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    if (drain_events(c)) return SOFA_ERR_CUDA;
+    *out = c->stats;
+    return 0;
+}
+int sofa_b200_reset_stats(sofa_ctx* c) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (drain_events(c)) return SOFA_ERR_CUDA;
+    memset(&c->stats, 0, sizeof c->stats);
+    return 0;
+}
+
+int sofa_b200_text_fetch(sofa_ctx* c, int k, void* host_out, uint64_t cap) {
+    if (!c || k < 0 || k > 2 || !host_out) FAIL(SOFA_ERR_ARG, "text_fetch: bad argument");
+    Source& s = c->src[k];
+    if (!s.uploaded) FAIL(SOFA_ERR_STATE, "text_fetch: no text");
+    if (cap < s.nbytes) FAIL(SOFA_ERR_CAP, "text_fetch: buffer too small");
+    CK(cudaSetDevice(c->device));
+    if (s.nbytes) { CK(cudaMemcpyAsync(host_out, s.text.p, s.nbytes, cudaMemcpyDeviceToHost, c->stream)); CK_S(stream_sync(c)); }
+    return 0;
+}
+
+}  // extern "C"
+
+int fmask_for(sofa_ctx* c, int k, uint32_t stride, uint32_t* fmask) {
+    if (k == SRC_PERF) { *fmask = 0x7; return 0; }
+    uint32_t fl = 0;
+    int r = sofa_b200_row_flags(c, k, stride, &fl);
+    if (r) return r;
+    if (k == SRC_GPU) { *fmask = 0x5u | ((fl & 1) ? 0x40u : 0u); return 0; }
+    if (fl & 2) {
+        if (!(fl & 4)) FAIL(SOFA_ERR_ROW, "every selected packet row is empty: the reference raises (0 columns)");
+        *fmask = 0x17ff;
+    } else *fmask = 0x45;
+    return 0;
+}
