@@ -121,6 +121,7 @@ class Workload:
         self.demangled = {}
         self.side = None
         self.side_resident = False
+        self.eng_device = 0
 
     def generate(self):
         hl, eng = self.hl, self.eng
@@ -234,6 +235,15 @@ class Workload:
                 fetch(1, n)
             return nrec
 
+        def js_series(kind, stride, kws):
+            """main series; the keyword filters are matched in the same pass (as sofa_preprocess does)"""
+            n, nrec, _ = eng.json_series_device(kind, stride, kws)
+            nb["json"] += n
+            nb["max_single"] = max(nb["max_single"], n)
+            if e2e and n:
+                fetch(1, n)
+            return nrec
+
         def side_source(i):
             """mpstat.txt / nvsmi_query.txt / netstat.txt -> CSV rows, aux table, report.js series"""
             raw = 6 + i
@@ -273,15 +283,13 @@ class Workload:
             if kind == hl.SRC_NET:
                 csv(kind, 1); js(kind, 1, -1)
             elif kind == hl.SRC_GPU:
-                csv(kind, 1); js(kind, 1, -1)
-                eng.set_filters(kind, 1, GPU_KWS)
+                csv(kind, 1); js_series(kind, 1, GPU_KWS)
                 for i in range(len(GPU_KWS)):
                     js(kind, 1, i)
             else:
                 csv(kind, 1)
                 eng.set_demangled(self._demangle_all(eng.viz_mangled(1)))
-                js(kind, 1, -1)
-                eng.set_filters(kind, 1, CPU_KWS)
+                js_series(kind, 1, CPU_KWS)
                 for i in range(len(CPU_KWS)):
                     js(kind, 1, i)
         gp = eng.gpu_profile() if analyze else None
@@ -315,9 +323,12 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from sofa_b200 import multirank
+    numa = multirank.bind_to_gpu_numa(local_rank, world) if args.numa_bind else {"node": None}
     from sofa_b200.engine import CudaEngine
     eng = CudaEngine(local_rank)
     wl = Workload(eng, args.events, SEED + 1000 * rank)
+    wl.eng_device = local_rank
     wl.generate()
     wl.fetch_host_text()
     wl.make_side()
@@ -428,6 +439,7 @@ def run_ours(args):
     value = world * total_events / (ms_step * 1e-3)
     e2e_value = world * total_events / (e2e_ms / args.steps * 1e-3)
     cpu = cpu_baseline_sample(args, wl)
+    windows = verify_windows(wl) if args.verify_windows else None
     line = {
         "metric": "trace events/s (preprocess+analyze)", "value": value, "unit": "events/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -440,7 +452,9 @@ def run_ours(args):
                    "cache": "inputs_larger_than_L2 (%.1f GB text per step)" % (text_total / 1e9),
                    "parallelism": "one trace per GPU, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": nb["h2d"],
-                "d2h_bytes_per_step": nb["csv"] + nb["json"], "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": nb["csv"] + nb["json"], "ms_per_step": e2e_ms / args.steps,
+                "pcie_GBps_per_rank": (nb["h2d"] + nb["csv"] + nb["json"]) / (e2e_ms / args.steps * 1e-3) / 1e9,
+                "numa": numa},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -452,10 +466,136 @@ def run_ours(args):
                      "all_kernels_ms": {k: round(v[1], 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][1])},
                      "whole_step_algorithmic_GBps": (text_total + out_bytes["csv"] + out_bytes["json"]) / (ms_step * 1e-3) / 1e9},
         "cpu_baseline": cpu,
+        "parity_sample": (cpu or {}).get("parity_sample"),
+        "parity_windows": ({"result": "identical", "windows": windows} if windows is not None else None),
         "wall_ms_per_step": wall_ms / args.steps,
     }
     print(json.dumps(line))
     eng.close()
+
+
+# --------------------------------------------------------------------------- output windows vs the oracle at full size
+class LineIndex:
+    """Byte offsets of rows of a resident host text (newline counts per 32 MiB chunk, refined on demand)."""
+    CH = 32 << 20
+
+    def __init__(self, arr, data_off):
+        import numpy as np
+        self.np, self.arr, self.off = np, arr, data_off
+        n = len(arr)
+        self.counts = [int(np.count_nonzero(arr[s:min(n, s + self.CH)] == 10)) for s in range(data_off, n, self.CH)]
+
+    def row_start(self, r):
+        """byte offset of the first byte of row r (r may equal the row count: end of text)"""
+        np = self.np
+        if r == 0:
+            return self.off
+        need, s = r, self.off                     # the r-th newline ends row r-1
+        for c in self.counts:
+            if need <= c:
+                pos = np.flatnonzero(self.arr[s:s + self.CH] == 10)
+                return s + int(pos[need - 1]) + 1
+            need -= c
+            s += self.CH
+        return len(self.arr)
+
+    def lines(self, r0, r1):
+        a, z = self.row_start(r0), self.row_start(r1)
+        return self.arr[a:z].tobytes().decode().splitlines(keepends=True)
+
+
+def _oracle_window(kind, lines, ctx, fmt):
+    """Oracle text of a window of input lines: CSV rows (to_csv '%.6f') or report.js records, with the FILE's column
+    dtypes (a carrier row that has the file-level property is appended and its output dropped)."""
+    import io
+    import json as js
+    from oracle import sofa_oracle as orc
+    from sofa_b200.sofa_preprocess import demangle
+    carrier = ctx.get("carrier")
+    src = lines + ([carrier] if carrier else [])
+    if kind == 0:
+        rows = [orc.parse_perf_sample(s, False, TIME_BASE, PERF_T_OFFSET, [0.0], [3000.0], "cycles") for s in src]
+    elif kind == 1:
+        rows = [orc.parse_gpu_record(s, False, TIME_BASE, ctx["indices"], 1, ctx["ts_rescale"], ctx["dt_rescale"],
+                                     ctx["payload_unit"], ctx["t_offset"]) for s in src]
+    else:
+        rows = [orc.parse_net_packet(s, False, TIME_BASE, 0) for s in src]
+    df = orc.frame(rows)
+    ncar = 1 if carrier else 0
+    if fmt == "csv":
+        buf = io.StringIO()
+        df.to_csv(buf, header=False, index=False, float_format='%.6f')
+        text = buf.getvalue()
+        if ncar:
+            text = text[:text.rstrip("\n").rfind("\n") + 1]        # the carriers used here print as one line
+        return text.encode()
+    if kind == 0:
+        df['name'] = df['name'].apply(lambda x: orc.viz_name(x, demangle))
+    d = df.rename(columns={'timestamp': 'x', 'duration': 'y'})
+    recs = js.loads(d.to_json(orient='records'))
+    if ncar:
+        recs = recs[:-1]
+    return ", ".join(js.dumps(r) for r in recs).encode()
+
+
+def verify_windows(wl, blocks=6):
+    """Parity at the full bench size: for every source, three windows of the CSV body and of the main report.js
+    series - the first rows, the rows whose output straddles the 4 GiB offset (when the output is that large) and the
+    last rows - are fetched from the device and byte-compared with the oracle run on the same input lines."""
+    import numpy as np
+    hl, eng = wl.hl, wl.eng
+    G4 = 1 << 32
+    out = {}
+    head = wl.host_text[hl.SRC_GPU].array[:1 << 16].tobytes().decode()
+    hrows = head.split("\n", 4)
+    from oracle import sofa_oracle as orc
+    tsr, dtr, pu = orc.gpu_units(hrows[2])
+    gctx = {"indices": hrows[1].replace('"', '').split(','), "ts_rescale": tsr, "dt_rescale": dtr, "payload_unit": pu,
+            "t_offset": 0 - float(hrows[3].split(',')[0])}
+    first_gpu = wl.host_text[hl.SRC_GPU].array[wl.data_off[hl.SRC_GPU]:wl.data_off[hl.SRC_GPU] + (4 << 20)].tobytes().decode().splitlines(keepends=True)
+    gctx["carrier"] = next(l for l in first_gpu[:-1] if "[CUDA memcpy" in l)       # a row with a Throughput: bandwidth is a float column
+    first_net = wl.host_text[hl.SRC_NET].array[:4 << 20].tobytes().decode().splitlines(keepends=True)
+    nctx = {"carrier": next(l for l in first_net[:-1] if l.split()[1] != "IP")}     # a [] row: every numeric column is float
+    ctxs = {hl.SRC_PERF: {}, hl.SRC_GPU: gctx, hl.SRC_NET: nctx}
+    kws = {hl.SRC_PERF: CPU_KWS, hl.SRC_GPU: GPU_KWS, hl.SRC_NET: []}
+    for kind in (hl.SRC_NET, hl.SRC_GPU, hl.SRC_PERF):
+        rows = eng.parse(kind, wl.params[kind])
+        li = LineIndex(wl.host_text[kind].array, wl.data_off[kind])
+        nblk = (rows + 127) // 128
+        for fmt in ("csv", "json"):
+            if fmt == "csv":
+                total = eng.csv_device(kind, 1)
+                skip = 0
+            else:
+                if kind == hl.SRC_PERF:
+                    eng.set_demangled(wl._demangle_all(eng.viz_mangled(1)))
+                total = (eng.json_series_device(kind, 1, kws[kind])[0] if kws[kind] else eng.json_device(kind, 1, -1)[0]) + 2
+                skip = 2                                  # device records are ", {...}": the first two bytes are dropped by fetch
+            wins = [("first", 0, min(blocks, nblk)), ("last", max(0, nblk - blocks), nblk)]
+            if total > G4:
+                lo, hi = 0, nblk - 1                       # first block that ends beyond 4 GiB
+                while lo < hi:
+                    mid = (lo + hi) // 2
+                    if eng.emit_block_end(mid) > G4:
+                        hi = mid
+                    else:
+                        lo = mid + 1
+                wins.append(("across_4GiB", max(0, lo - blocks // 2), min(nblk, lo + blocks // 2)))
+            for name, b0, b1 in wins:
+                start = eng.emit_block_end(b0 - 1) if b0 else 0
+                end = eng.emit_block_end(b1 - 1)
+                got = eng.fetch_range(0 if fmt == "csv" else 1, start, end - start).tobytes()
+                want = _oracle_window(kind, li.lines(b0 * 128, min(b1 * 128, rows)), ctxs[kind], fmt)
+                if fmt == "json":
+                    got = got[2:]                          # ", " in front of the window's first record
+                if got != want:
+                    n = min(len(got), len(want))
+                    i = next((i for i in range(n) if got[i] != want[i]), n)
+                    raise AssertionError("window %s of %s source %d differs from the oracle at byte %d (+%d in the output): %r vs %r"
+                                         % (name, fmt, kind, i, start, got[max(0, i - 40):i + 40], want[max(0, i - 40):i + 40]))
+                out["%s_%s_%s" % (("perf", "gpu", "net")[kind], fmt, name)] = {"rows": [b0 * 128, min(b1 * 128, rows)], "out_bytes": [start, end]}
+            del skip
+    return out
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -488,21 +628,66 @@ def write_sample_logdir(logdir, n_events, seed, wl=None):
 
 
 def oracle_pass(logdir, nprocs):
-    """preprocess (trace + side files) + gpu_profile + net_profile + nvsmi_profile + concurrency_breakdown of the CPU oracle."""
+    """preprocess (trace + side files) + gpu_profile + net_profile + nvsmi_profile + concurrency_breakdown of the CPU oracle.
+    Leaves every output file the reference would write (trace CSVs, report.js, side CSVs, comm.csv, netrank.csv,
+    performance.csv) in logdir."""
     import pandas as pd
     from oracle import sofa_oracle as orc
     from sofa_b200.sofa_preprocess import demangle
     cfg = orc.OracleConfig(logdir, cpu_filters=CPU_FILTERS, nprocs=nprocs)
     orc.preprocess(cfg, demangle=demangle)
-    df = pd.read_csv(logdir + "/gputrace.csv")
-    orc.gpu_profile(df, logdir)
+    if os.path.isfile(logdir + "/gputrace.csv"):
+        orc.gpu_profile(pd.read_csv(logdir + "/gputrace.csv"), logdir)
     if os.path.isfile(logdir + "/nettrace.csv"):
         orc.net_profile(pd.read_csv(logdir + "/nettrace.csv"), logdir + "/")
     if os.path.isfile(logdir + "/nvsmi_trace.csv"):
         orc.nvsmi_profile(pd.read_csv(logdir + "/nvsmi_trace.csv"))
     if os.path.isfile(logdir + "/mpstat.csv"):
-        orc.concurrency_breakdown(pd.read_csv(logdir + "/mpstat.csv"), pd.read_csv(logdir + "/cputrace.csv"),
-                                  pd.read_csv(logdir + "/nvsmi_trace.csv"), pd.read_csv(logdir + "/netstat.csv"))
+        _, perf = orc.concurrency_breakdown(pd.read_csv(logdir + "/mpstat.csv"), pd.read_csv(logdir + "/cputrace.csv"),
+                                            pd.read_csv(logdir + "/nvsmi_trace.csv"), pd.read_csv(logdir + "/netstat.csv"))
+        if perf is not None:
+            perf.to_csv(logdir + "/performance.csv")
+
+
+PARITY_FILES = ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "mpstat.csv", "usr_sys.csv", "nvsmi_trace.csv",
+                "netstat.csv", "netbandwidth.csv", "comm.csv", "netrank.csv", "performance.csv")
+
+
+def product_pass(logdir, device):
+    """The drop-in entry points themselves - sofa_preprocess(cfg) + sofa_analyze(cfg) - on a logdir; returns their wall time."""
+    import contextlib
+    import io
+    from sofa_b200.sofa_config import default_report_config
+    from sofa_b200.sofa_preprocess import sofa_preprocess
+    from sofa_b200.sofa_analyze import sofa_analyze
+    os.environ["SOFA_B200_DEVICE"] = str(device)
+    cfg = default_report_config(logdir, cpu_filters=CPU_FILTERS)
+    cfg.keep_engine = True
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        sofa_preprocess(cfg)
+        sofa_analyze(cfg)
+    return time.perf_counter() - t0
+
+
+def parity_sample(oracle_dir, product_dir):
+    """Byte comparison of every output file of the two passes; raises on the first difference."""
+    compared = []
+    for fn in PARITY_FILES:
+        a, b = os.path.join(oracle_dir, fn), os.path.join(product_dir, fn)
+        if not os.path.isfile(a):
+            continue
+        if not os.path.isfile(b):
+            raise AssertionError("parity sample: %s written by the oracle but not by the CUDA path" % fn)
+        with open(a, "rb") as f, open(b, "rb") as g:
+            x, y = f.read(), g.read()
+        if x != y:
+            n = min(len(x), len(y))
+            i = next((i for i in range(n) if x[i] != y[i]), n)
+            raise AssertionError("parity sample: %s differs at byte %d (oracle %d bytes, CUDA %d bytes): %r vs %r" %
+                                 (fn, i, len(x), len(y), x[max(0, i - 40):i + 40], y[max(0, i - 40):i + 40]))
+        compared.append(fn)
+    return compared
 
 
 def cpu_baseline_sample(args, wl):
@@ -514,14 +699,21 @@ def cpu_baseline_sample(args, wl):
     logdir = os.path.join(work, "sofalog") + "/"
     os.makedirs(logdir)
     write_sample_logdir(logdir, n, SEED, wl)
+    import shutil
+    pdir = os.path.join(work, "product") + "/"
+    shutil.copytree(logdir, pdir)
     cores = mp.cpu_count()
     t0 = time.perf_counter()
     oracle_pass(logdir, cores)
     dt = time.perf_counter() - t0
-    import shutil
+    # the same logdir through the CUDA path's public entry points: every output file must be byte-identical
+    pdt = product_pass(pdir, wl.eng_device)
+    files = parity_sample(logdir, pdir)
     shutil.rmtree(work, ignore_errors=True)
     return {"value": n / dt, "unit": "events/s", "cores": cores, "kind": "port",
-            "sample": "first %d events of the same mixed trace (60/35/5), oracle preprocess (trace + side files) + gpu/net/nvsmi profiles + concurrency_breakdown, %.1f s" % (n, dt)}
+            "sample": "first %d events of the same mixed trace (60/35/5), oracle preprocess (trace + side files) + gpu/net/nvsmi profiles + concurrency_breakdown, %.1f s" % (n, dt),
+            "parity_sample": "identical", "parity_files": files,
+            "entrypoints_s_on_sample": round(pdt, 3)}
 
 
 def run_reference(args):
@@ -564,6 +756,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=100000000, help="events per GPU (default: BASELINE configs[2])")
     ap.add_argument("--cpu-sample", type=int, default=150000, help="events in the CPU baseline sample")
+    ap.add_argument("--numa-bind", type=int, default=1, help="1: bind every rank (CPUs + pinned arenas) to its GPU's NUMA node")
+    ap.add_argument("--verify-windows", type=int, default=1,
+                    help="1: byte-compare first / 4 GiB-straddling / last windows of every CSV and main JSON output with the oracle")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -124,6 +124,16 @@ int sofa_b200_set_demangled(sofa_ctx*, uint32_t n, const char* mangled, const ui
 int sofa_b200_emit_json(sofa_ctx*, int src, uint32_t stride, int32_t filter_idx, uint64_t* nbytes,
                         uint64_t* n_records);
 
+/* Main series of a source plus its keyword filters in ONE formatting pass: the keywords are matched on each name
+ * while the record is sized (same semantics as sofa_b200_set_filters: counts[k] = matching rows, masks kept for
+ * sofa_b200_emit_json(filter_idx)), the records go to output buffer 1, and the byte offset of every record is
+ * kept with the output so that the following sofa_b200_emit_json(src, stride, k) calls GATHER series k from this
+ * output instead of formatting the rows again (a filter series holds the very same record bytes,
+ * sofa_preprocess.py:1446-1452, 1819-1827).  Valid when the filters run on the frame of the main series: always
+ * for the cpu filters, for the gpu filters when plot_ratio == 1. */
+int sofa_b200_emit_json_series(sofa_ctx*, int src, uint32_t stride, int32_t nkw, const char* const* keywords,
+                               uint64_t* counts, uint64_t* nbytes, uint64_t* n_records);
+
 /* D2H of an output buffer (0 csv, 1 json, 2 names) */
 int sofa_b200_fetch(sofa_ctx*, int which, void* host_out, uint64_t cap);
 
@@ -221,6 +231,19 @@ int sofa_b200_side_emit_aux(sofa_ctx*, int raw_src, uint64_t* nbytes, uint64_t* 
 /* CUDA-event stopwatch on the ctx stream: mark(0) ... mark(1); elapsed = ms between them */
 int sofa_b200_mark(sofa_ctx*, int which);
 int sofa_b200_elapsed_ms(sofa_ctx*, double* ms);
+
+/* Verification helpers (bench.py checks windows of the > 4 GiB outputs against the CPU oracle): a byte range of
+ * output buffer 0 / 1 as it is on the device (buffer 1 still carries the leading ", " of the first record), and
+ * the inclusive byte offset at which block `block` (128 consecutive selected rows) of the LAST emit ends, read
+ * from that emit's look-back state. */
+int sofa_b200_fetch_range(sofa_ctx*, int which, uint64_t off, uint64_t nbytes, void* host_out);
+int sofa_b200_emit_block_end(sofa_ctx*, uint64_t block, uint64_t* end_bytes);
+
+/* Test hooks.  SOFA_DEBUG_NAME_HASH_MASK: the 64-bit name hashes that key get_top_k_events / nccl_time groups
+ * (sofa_analyze.py:34-44, 363-368) are ANDed with `value`; a narrow mask forces collisions, which the group
+ * verification pass must then report (SOFA_ERR_ROW) instead of merging two names. */
+#define SOFA_DEBUG_NAME_HASH_MASK 1
+int sofa_b200_set_debug(sofa_ctx*, int key, uint64_t value);
 
 int sofa_b200_set_profiling(sofa_ctx*, int on);
 int sofa_b200_get_stats(sofa_ctx*, sofa_stats_t* out);

@@ -8,11 +8,13 @@ LIB_PATH = os.path.join(HERE, "libsofa_b200.so")
 
 SOFA_OK, SOFA_ERR_CUDA, SOFA_ERR_ARG, SOFA_ERR_ROW, SOFA_ERR_STATE, SOFA_ERR_CAP = 0, -1, -2, -3, -4, -5
 
+SOFA_DEBUG_NAME_HASH_MASK = 1
+
 EXPORTS = [
     "sofa_b200_abi_version", "sofa_b200_last_error", "sofa_b200_error_row", "sofa_b200_create",
     "sofa_b200_destroy", "sofa_b200_host_alloc", "sofa_b200_host_free", "sofa_b200_upload",
     "sofa_b200_parse", "sofa_b200_row_flags", "sofa_b200_emit_csv", "sofa_b200_set_filters",
-    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_fetch",
+    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_emit_json_series", "sofa_b200_set_debug", "sofa_b200_fetch_range", "sofa_b200_emit_block_end", "sofa_b200_fetch",
     "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
     "sofa_b200_synth", "sofa_b200_text_fetch", "sofa_b200_mark", "sofa_b200_elapsed_ms",
@@ -108,7 +110,11 @@ def load_lib():
     lib.sofa_b200_viz_mangled.argtypes = [vp, ctypes.c_uint32, u64p, u32p]
     lib.sofa_b200_set_demangled.argtypes = [vp, ctypes.c_uint32, ctypes.c_char_p, u64p, ctypes.c_char_p, u64p]
     lib.sofa_b200_emit_json.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32, u64p, u64p]
+    lib.sofa_b200_emit_json_series.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), u64p, u64p, u64p]
     lib.sofa_b200_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
+    lib.sofa_b200_set_debug.argtypes = [vp, ctypes.c_int, ctypes.c_uint64]
+    lib.sofa_b200_fetch_range.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp]
+    lib.sofa_b200_emit_block_end.argtypes = [vp, ctypes.c_uint64, u64p]
     lib.sofa_b200_get_column.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64]
     lib.sofa_b200_gpu_profile.argtypes = [vp, ctypes.POINTER(GpuProfile), ctypes.c_int]
     lib.sofa_b200_top_k.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), u64p, u32p]

@@ -49,6 +49,9 @@ struct Source {
     uint32_t flags_stride[2] = {0, 0}, flags_val[2] = {0, 0};      // cached sofa_b200_row_flags results
     DevBuf vizhash, viz_id; uint32_t viz_stride = 0; bool viz_ready = false;
     DevBuf dict_hash, dict_off, dict_blob; int dict_n = 0;
+    // report.js main series kept resident for gathering the filter series (sofa_b200_emit_json_series)
+    DevBuf json_main, rec_off; const char* gather_ptr = nullptr; uint64_t gather_gen = 0; bool gather_ok = false;
+    uint32_t gather_stride = 0; double gather_total = 0;
     bool side_ready = false; int side_absolute = 0; uint64_t side_ncand = 0;          // raw side source: rows per list after sofa_b200_side_preprocess
 };
 
@@ -69,6 +72,8 @@ struct sofa_ctx {
     bool up_pending[11] = {};
     cudaEvent_t fetch_ev[16]; bool fetch_used[16]; int fetch_next = 0;
     DevBuf arena; uint64_t arena_cur = 0; bool arena_on = false;
+    uint64_t arena_gen = 1;              // bumped whenever the arena wraps or is re-created (older pointers into it are dead)
+    uint64_t async_fetches = 0;          // asynchronous fetches issued since the D2H stream was last drained
     // small host<->device traffic goes through mapped pinned memory + a copy kernel, never the
     // DMA engines (a tiny read-back queued behind a multi-GB transfer would stall the host)
     unsigned char* stage_h = nullptr; unsigned char* stage_d = nullptr; size_t stage_cap = 8u << 20, stage_cur = 0;
@@ -81,6 +86,7 @@ struct sofa_ctx {
     unsigned long long* d_err = nullptr;        // [0] error slot, [1] counter, [2..9] filter counts, [10] misc
     unsigned int* d_flags = nullptr;            // [0] cr flag, [1] row flags, [2] overflow, [3] count
     uint64_t err_row = 0; int err_code = 0;
+    uint64_t debug_hash_mask = ~0ull;    // name-group hashes are ANDed with this (tests force collisions with a narrow mask)
     bool profiling = false;
     cudaEvent_t mark[2] = {nullptr, nullptr};
     std::vector<TimedEvent> events;
@@ -297,7 +303,7 @@ static int out_alloc(sofa_ctx* c, int s, uint64_t cap, char** p) {
         uint64_t need = (cap + 64 + 255) & ~255ull;
         if (c->arena_cur + need > c->arena.cap) {
             CK(cudaStreamSynchronize(c->d2h));
-            c->arena_cur = 0;
+            c->arena_cur = 0; c->arena_gen++; c->async_fetches = 0;
             if (need > c->arena.cap) { CK_S(stream_sync(c)); ENSURE(c->arena, need); }
         }
         *p = c->arena.as<char>() + c->arena_cur;
@@ -333,4 +339,5 @@ void launch_parse(int tpl_kind, unsigned grid, size_t smem, cudaStream_t st, con
 void launch_count_lines(unsigned grid, cudaStream_t st, const char* text, uint64_t begin, uint64_t end, uint32_t tile_bytes,
                         uint64_t* tile_counts, unsigned int* cr_flag);
 void launch_emit(int kind, int fmt, unsigned grid, size_t smem, cudaStream_t st, const sofa::SrcView& v, const sofa::FusedArgs& a);
+int set_gather_attr(void);
 int set_kernel_attrs(void);       // dynamic shared memory opt-in of every instantiation; 0 or a cudaError_t

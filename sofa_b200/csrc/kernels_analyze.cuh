@@ -174,7 +174,7 @@ struct NcclHashSink {
 // go into an open-addressing table (value = smallest row).
 __global__ void __launch_bounds__(256) k_nccl_hash(SrcView src, uint64_t n, uint64_t* __restrict__ namehash,
                                                    unsigned long long* keys, unsigned long long* rows, uint64_t cap_mask,
-                                                   unsigned int* overflow) {
+                                                   unsigned int* overflow, uint64_t hash_mask) {
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     uint64_t key = 0;
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) k_nccl_hash(SrcView src, uint64_t n, uint
         GpuRow r = load_gpu(src, row);
         GpuName<const char*> ng{src.text + src.c.g.line_start[row], r, true, src.api_mode != 0};
         NcclHashSink s; ng.gen(s);
+        s.h.h &= hash_mask;
         if (s.hit) key = s.h.h ? s.h.h : 1;
         if (s.hit && keys) {
             uint64_t slot = key & cap_mask;

@@ -99,15 +99,53 @@ __global__ void __launch_bounds__(256) k_pairs_write(const uint64_t* __restrict_
 }
 // FNV-1a of every row's full name (all kinds) + identity payload
 template <int KIND>
-__global__ void __launch_bounds__(256) k_name_hash_all(SrcView src, uint64_t n, uint64_t* __restrict__ kout, uint32_t* __restrict__ vout) {
+__global__ void __launch_bounds__(256) k_name_hash_all(SrcView src, uint64_t n, uint64_t* __restrict__ kout, uint32_t* __restrict__ vout,
+                                                        uint64_t hash_mask) {
     uint64_t row = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (row >= n) return;
     with_row<KIND, false>(src, row, row, [&](const RowVals&, const auto& ng) {
         HashSink h; ng.gen(h);
+        h.h &= hash_mask;                    // all ones, except in the collision test (sofa_b200_set_debug)
         kout[row] = h.h ? h.h : 1;
         vout[row] = (uint32_t)row;
     });
 }
+// Groups are keyed by a 64-bit hash of the name; this pass makes them exact: in the hash-sorted order every row whose
+// key equals its predecessor's must have the same name bytes (equality is transitive along the segment).  A
+// mismatch (two names with one hash) sets *collision: the host raises instead of merging two groups.
+struct WinWrite {           // bytes [lo, lo + W) of the generated name -> buf
+    static constexpr bool WORDS = false;
+    char* buf; int lo, n;
+    __device__ __forceinline__ void put(char ch) { int d = n - lo; if (d >= 0 && d < 128) buf[d] = ch; n++; }
+    __device__ __forceinline__ void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
+};
+struct WinCompare {
+    static constexpr bool WORDS = false;
+    const char* buf; int lo, n; bool diff;
+    __device__ __forceinline__ void put(char ch) { int d = n - lo; if (d >= 0 && d < 128 && buf[d] != ch) diff = true; n++; }
+    __device__ __forceinline__ void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
+};
+template <int KIND>
+__global__ void __launch_bounds__(128) k_verify_groups(SrcView src, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                       uint64_t m, unsigned int* collision) {
+    uint64_t i = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i == 0 || i >= m || keys[i] != keys[i - 1]) return;
+    const uint64_t ra = vals[i - 1], rb = vals[i];
+    char buf[128];
+    bool diff = false;
+    with_row<KIND, false>(src, ra, ra, [&](const RowVals&, const auto& na) {
+        with_row<KIND, false>(src, rb, rb, [&](const RowVals&, const auto& nb) {
+            for (int lo = 0;; lo += 128) {
+                WinWrite w{buf, lo, 0}; na.gen(w);
+                WinCompare cmp{buf, lo, 0, false}; nb.gen(cmp);
+                if (cmp.diff || cmp.n != w.n) { diff = true; break; }
+                if (lo + 128 >= w.n) break;
+            }
+        });
+    });
+    if (diff) atomicOr(collision, 1u);
+}
+
 // keys for sort_values(by='duration', ascending=False): descending order of the CSV value
 __global__ void __launch_bounds__(256) k_dur_keys_desc(const double* __restrict__ dur, uint64_t n, uint64_t* __restrict__ kout,
                                                        uint32_t* __restrict__ vout) {

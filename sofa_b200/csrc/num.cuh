@@ -18,7 +18,16 @@
 #if defined(__CUDACC__)
 #define SOFA_HD __host__ __device__ __forceinline__
 #define SOFA_HD_COLD __host__ __device__ __noinline__
+// number formatters: out of line in translation units that define SOFA_OUTLINE_NUM.  Measured on B200 (round 2): the
+// fully inlined JSON emit kernels are 0.8-2.1 MB of SASS, but calling the formatters (plans through local memory)
+// made json_emit 59 -> 63 ms and csv_emit 28 -> 33 ms per 100 M events, so nothing defines it
+#ifdef SOFA_OUTLINE_NUM
+#define SOFA_HD_FN static __host__ __device__ __noinline__
 #else
+#define SOFA_HD_FN __host__ __device__ __forceinline__
+#endif
+#else
+#define SOFA_HD_FN inline
 #define SOFA_HD inline
 #define SOFA_HD_COLD __attribute__((noinline))
 #endif
@@ -300,7 +309,7 @@ SOFA_HD int fmt_u64(uint64_t v, O out) {
     return n;
 }
 template <typename O>
-SOFA_HD int fmt_i64(int64_t v, O out) {
+SOFA_HD_FN int fmt_i64(int64_t v, O out) {
     if (v < 0) { out[0] = '-'; return 1 + fmt_u64((uint64_t)0 - (uint64_t)v, out + 1); }
     return fmt_u64((uint64_t)v, out);
 }
@@ -342,7 +351,7 @@ SOFA_HD bool fixed6_parts(double x, bool* neg, uint64_t* ip, uint32_t* fp) {
 // "%.6f" split into a plan (sign, integer part, 6 fraction digits, exact length) and an emit
 // step, so kernels can size a row first and print its digits exactly once afterwards.
 struct F6Plan { uint64_t I; uint32_t F; uint8_t neg, ok, len; };
-SOFA_HD F6Plan fixed6_plan(double x) {
+SOFA_HD_FN F6Plan fixed6_plan(double x) {
     F6Plan p; bool neg;
     p.ok = fixed6_parts(x, &neg, &p.I, &p.F) ? 1 : 0;
     p.neg = neg ? 1 : 0;
@@ -350,7 +359,7 @@ SOFA_HD F6Plan fixed6_plan(double x) {
     return p;
 }
 template <typename O>
-SOFA_HD int fixed6_emit(const F6Plan& p, O out) {
+SOFA_HD_FN int fixed6_emit(const F6Plan& p, O out) {
     int n = 0;
     if (p.neg) out[n++] = '-';
     n += fmt_u64(p.I, out + n);
@@ -384,7 +393,7 @@ SOFA_HD JPlan jp_fixed(bool neg, uint64_t I, uint64_t dg, int nd) {
 }
 // Python repr digits of y for 1e5 <= y < 1e16 (fixed notation): shortest decimal that rounds
 // back to y, found by an exact 128-bit test of the rounding interval; closest one on ties of length.
-SOFA_HD JPlan jp_shortest_ge1e5(bool neg, double y) {
+SOFA_HD_FN JPlan jp_shortest_ge1e5(bool neg, double y) {
     JPlan bad; bad.I = 0; bad.dg = 0; bad.neg = 0; bad.nd = 0; bad.ex = 0; bad.len = 0; bad.kind = JP_BAD;
     uint64_t yb = d_bits(y);
     int e = (int)((yb >> 52) & 0x7ff) - 1075;
@@ -421,7 +430,7 @@ SOFA_HD JPlan jp_shortest_ge1e5(bool neg, double y) {
     }
     return bad;
 }
-SOFA_HD JPlan json_plan(double x) {
+SOFA_HD_FN JPlan json_plan(double x) {
     JPlan p; p.I = 0; p.dg = 0; p.neg = 0; p.nd = 0; p.ex = 0; p.len = 0; p.kind = JP_BAD;
     uint64_t xb = d_bits(x);
     if (((xb >> 52) & 0x7ff) == 0x7ff) { p.kind = JP_NULL; p.len = 4; return p; }
@@ -458,7 +467,7 @@ SOFA_HD JPlan json_plan(double x) {
     return jp_shortest_ge1e5(neg, y);
 }
 template <typename O>
-SOFA_HD int json_emit(const JPlan& p, O out) {
+SOFA_HD_FN int json_emit(const JPlan& p, O out) {
     if (p.kind == JP_NULL) { out[0] = 'n'; out[1] = 'u'; out[2] = 'l'; out[3] = 'l'; return 4; }
     int n = 0;
     if (p.neg) out[n++] = '-';
@@ -485,7 +494,7 @@ SOFA_HD int json_double(double x, O out) {
 
 // repr(float("%.6f" % x)): what DataFrame.to_csv prints (no float_format) for a value that was
 // read back from a trace CSV - comm.csv (sofa_common.py:160-167).  |x| < 9e9.
-SOFA_HD JPlan repr6_plan(double x) {
+SOFA_HD_FN JPlan repr6_plan(double x) {
     JPlan p; p.I = 0; p.dg = 0; p.neg = 0; p.nd = 0; p.ex = 0; p.len = 0; p.kind = JP_BAD;
     bool neg; uint64_t I; uint32_t F;
     if (!fixed6_parts(x, &neg, &I, &F) || I >= 9000000000ull) return p;

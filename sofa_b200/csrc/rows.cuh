@@ -1266,6 +1266,46 @@ inline void filter_table_build(FilterTable* ft, int nkw, const char* const* kws,
     }
 }
 
+// the packed variant alone (2 KB instead of 10): what the report.js main-series kernel stages in shared memory to
+// match the keywords while it sizes the name
+struct PackedFilter {
+    uint64_t pmask[256];
+    uint64_t pstart, pfinal;
+    uint8_t pfinal_pos[8];
+    int nk, pad;
+};
+struct PackedMatchSink {
+    static constexpr bool WORDS = true;
+    const PackedFilter* t; uint64_t ps, phit;
+    SOFA_HD PackedMatchSink(const PackedFilter* tt) : t(tt), ps(0), phit(0) {}
+    SOFA_HD void put(char ch) {
+        ps = ((ps << 1) | t->pstart) & t->pmask[(unsigned char)ch];
+        phit |= ps & t->pfinal;
+    }
+    SOFA_HD void put_word(uint64_t w, int nb) {
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            if (b < nb) {
+                ps = ((ps << 1) | t->pstart) & t->pmask[(w >> (8 * b)) & 0xff];
+                phit |= ps & t->pfinal;
+            }
+        }
+    }
+    SOFA_HD uint32_t hits() const {
+        uint32_t h = 0;
+        for (int k = 0; k < t->nk; k++) if ((phit >> t->pfinal_pos[k]) & 1) h |= 1u << k;
+        return h;
+    }
+};
+inline bool packed_filter_from(const FilterTable& ft, PackedFilter* pf) {
+    if (!ft.packed) return false;
+    for (int c = 0; c < 256; c++) pf->pmask[c] = ft.pmask[c];
+    pf->pstart = ft.pstart; pf->pfinal = ft.pfinal;
+    for (int i = 0; i < 8; i++) pf->pfinal_pos[i] = ft.pfinal_pos[i];
+    pf->nk = ft.nk; pf->pad = 0;
+    return true;
+}
+
 // FNV-1a 64 over generated characters (name dictionary keys)
 struct HashSink {
     static constexpr bool WORDS = true;

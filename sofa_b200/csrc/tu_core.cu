@@ -69,6 +69,7 @@ int sofa_b200_destroy(sofa_ctx* c) {
         Source& s = c->src[k];
         s.text.release(); s.mhz.release(); s.mask.release(); s.vizhash.release(); s.viz_id.release();
         s.dict_hash.release(); s.dict_off.release(); s.dict_blob.release();
+        s.json_main.release(); s.rec_off.release();
         for (auto& b : s.cols) b.release();
         if (k < 3) c->out[k].release();
     }
@@ -208,6 +209,30 @@ int sofa_b200_fetch(sofa_ctx* c, int which, void* host_out, uint64_t cap) {
     return 0;
 }
 
+int sofa_b200_fetch_range(sofa_ctx* c, int which, uint64_t off, uint64_t n, void* host_out) {
+    if (!c || which < 0 || which > 1 || (!host_out && n)) FAIL(SOFA_ERR_ARG, "fetch_range: bad argument");
+    CK(cudaSetDevice(c->device));
+    if (off + n > c->out_n[which]) FAIL(SOFA_ERR_CAP, "fetch_range: beyond the output");
+    if (n) {
+        CK(cudaMemcpyAsync(host_out, c->out_ptr[which] + off, n, cudaMemcpyDeviceToHost, c->stream));
+        CK_S(stream_sync(c));
+        c->stats.d2h_bytes += n;
+    }
+    return 0;
+}
+
+int sofa_b200_emit_block_end(sofa_ctx* c, uint64_t block, uint64_t* end_bytes) {
+    if (!c || !end_bytes) FAIL(SOFA_ERR_ARG, "emit_block_end: bad argument");
+    CK(cudaSetDevice(c->device));
+    if ((block + 1) * 8 > c->tiles.cap) FAIL(SOFA_ERR_ARG, "emit_block_end: no such block");
+    unsigned long long v = 0;
+    CK_S(small_d2h(c, &v, c->tiles.as<unsigned long long>() + block, 8));
+    CK_S(stream_sync(c));
+    if ((v >> 62) != 2) FAIL(SOFA_ERR_STATE, "emit_block_end: the look-back state of the last emit is gone");
+    *end_bytes = v & ((1ull << 62) - 1);
+    return 0;
+}
+
 int sofa_b200_upload_async(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint64_t data_off) {
     if (!c || k < 0 || k > 10 || (!text && nbytes)) FAIL(SOFA_ERR_ARG, "upload_async: bad argument");
     if (data_off > nbytes) FAIL(SOFA_ERR_ARG, "upload_async: data_off beyond the text");
@@ -241,6 +266,7 @@ int sofa_b200_fetch_async(sofa_ctx* c, int which, void* host_out, uint64_t cap, 
     CK(cudaEventRecord(c->fetch_ev[t], c->d2h));
     c->out_busy[which] = true;
     c->fetch_used[t] = true;
+    c->async_fetches++;
     c->stats.d2h_bytes += n;
     if (ticket) *ticket = t;
     return 0;
@@ -257,7 +283,7 @@ int sofa_b200_sync(sofa_ctx* c) {
     CK(cudaStreamSynchronize(c->h2d));
     CK_S(stream_sync(c));
     CK(cudaStreamSynchronize(c->d2h));
-    c->arena_cur = 0;
+    c->arena_cur = 0; c->arena_gen++; c->async_fetches = 0;
     return 0;
 }
 int sofa_b200_set_output_arena(sofa_ctx* c, uint64_t nbytes) {
@@ -265,6 +291,7 @@ int sofa_b200_set_output_arena(sofa_ctx* c, uint64_t nbytes) {
     CK(cudaSetDevice(c->device));
     CK_S(stream_sync(c));
     CK(cudaStreamSynchronize(c->d2h));
+    c->arena_gen++;
     if (nbytes == 0) { c->arena.release(); c->arena_on = false; c->arena_cur = 0; return 0; }
     ENSURE(c->arena, nbytes);
     c->arena_on = true; c->arena_cur = 0;
@@ -308,6 +335,12 @@ int sofa_b200_elapsed_ms(sofa_ctx* c, double* ms) {
     CK(cudaEventElapsedTime(&f, c->mark[0], c->mark[1]));
     *ms = f;
     return 0;
+}
+
+int sofa_b200_set_debug(sofa_ctx* c, int key, uint64_t value) {
+    if (!c) FAIL(SOFA_ERR_ARG, "null ctx");
+    if (key == SOFA_DEBUG_NAME_HASH_MASK) { c->debug_hash_mask = value; return 0; }
+    FAIL(SOFA_ERR_ARG, "set_debug: unknown key");
 }
 
 int sofa_b200_set_profiling(sofa_ctx* c, int on) {

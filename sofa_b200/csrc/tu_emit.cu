@@ -1,10 +1,15 @@
 // libsofa_b200.so, translation unit: text emission driver (output buffers, capacity retry, look-back state) over
 // k_emit_fused<KIND, FMT> (instantiated in inst/emit_*.cu).
 #include "ctx.cuh"
+#include "kernels_gather.cuh"
+
+// report.js main series with fused keyword matching / record offsets (see FusedArgs)
+struct JsonFuse { const PackedFilter* pf; uint8_t* mask_out; unsigned long long* rec_off; bool keep_output; };
 
 template <int FMT>
 static int emit_fused_t(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, int bit, uint32_t fmask,
-                      int outslot, uint64_t sel_hint, uint64_t* nbytes, uint64_t* nrec, const SideEmit* se = nullptr) {
+                      int outslot, uint64_t sel_hint, uint64_t* nbytes, uint64_t* nrec, const SideEmit* se = nullptr,
+                      const JsonFuse* jf = nullptr) {
     Source& s = c->src[k];
     uint64_t ncand = se ? se->ncand : cdiv(s.n_rows, stride);
     c->out_n[outslot] = 0;
@@ -60,7 +65,13 @@ static int emit_fused_t(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask
     if (slot_bytes > 63u * 1024u) slot_bytes = 63u * 1024u;
     for (int attempt = 0; attempt < 6; attempt++, cap *= 2) {
         char* outp = nullptr;
-        { int ra = out_alloc(c, outslot, cap, &outp); if (ra) return ra; }
+        if (jf && jf->keep_output && !c->arena_on) {
+            // the main series stays resident in its own buffer so that the filter series can be gathered from it
+            if (c->async_fetches) { CK(cudaStreamSynchronize(c->d2h)); c->async_fetches = 0; }
+            ENSURE(s.json_main, cap + 64);
+            outp = s.json_main.as<char>();
+            c->out_ptr[outslot] = outp;
+        } else { int ra = out_alloc(c, outslot, cap, &outp); if (ra) return ra; }
         if (reset_err(c)) return SOFA_ERR_CUDA;
         CK(cudaMemsetAsync(c->tiles.p, 0, (nblocks + 1) * 8, c->stream));
         FusedArgs a;
@@ -69,6 +80,8 @@ static int emit_fused_t(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask
         a.state = c->tiles.as<unsigned long long>(); a.ticket = c->d_flags + 4;
         a.err = c->d_err; a.count = c->d_err + 1; a.total = c->d_err + 11; a.overflow = c->d_flags + 2;
         a.slot_bytes = slot_bytes;
+        a.pf = jf ? jf->pf : nullptr; a.mask_out = jf ? jf->mask_out : nullptr; a.kwcounts = c->d_err + 2;
+        a.rec_off = jf ? jf->rec_off : nullptr;
         int kk = FMT == FMT_JSON ? K_JSON_WRITE : K_CSV_WRITE;
         unsigned g = (unsigned)nblocks;
         if (FMT == FMT_COMM && k != SRC_GPU) FAIL(SOFA_ERR_ARG, "comm.csv is a gpu-trace output");
@@ -82,6 +95,9 @@ static int emit_fused_t(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask
         int r = check_kernel_error(c, FMT == FMT_CSV ? "emit_csv" : "emit_json");
         if (r) return r;
         if (ovf) { if (total + 64 > cap * 2) cap = total / 2 + 64; continue; }
+        if (jf && jf->keep_output) {
+            s.gather_ptr = outp; s.gather_gen = c->arena_on ? c->arena_gen : ~0ull;
+        }
         out_commit(c, outslot, total);
         if (nbytes) *nbytes = total;
         if (nrec) *nrec = cnt;
@@ -100,7 +116,111 @@ int sofa_emit_fused(sofa_ctx* c, int fmt, int k, uint32_t stride, const uint8_t*
     }
 }
 
+// filter series `bit` of source k gathered from the resident main series (k_gather_records)
+static int gather_series(sofa_ctx* c, int k, int bit, uint64_t* nbytes, uint64_t* nrec) {
+    Source& s = c->src[k];
+    const int outslot = 1;
+    uint64_t ncand = cdiv(s.n_rows, s.gather_stride);
+    c->out_n[outslot] = 0;
+    if (nbytes) *nbytes = 0;
+    if (nrec) *nrec = 0;
+    if (flip_output(c, outslot)) return SOFA_ERR_CUDA;
+    if (ncand == 0) return 0;
+    const uint8_t* mask = s.mask.as<uint8_t>();
+    uint64_t nb = cdiv(ncand, 256);
+    ENSURE(c->blockoff, (nb + 2) * 8);
+    LAUNCH(c, K_FILTER, (k_mask_count<<<(unsigned)nb, 256, 0, c->stream>>>(mask, bit, ncand, c->blockoff.as<uint64_t>())));
+    CK_S(launch_scan(c, c->blockoff.as<uint64_t>(), nb));
+    uint64_t cnt = 0;
+    CK_S(small_d2h(c, &cnt, c->blockoff.as<uint64_t>() + nb, 8));
+    CK_S(stream_sync(c));
+    if (cnt == 0) return 0;
+    ENSURE(c->rowlen, cnt * 4 + 16);
+    LAUNCH(c, K_FILTER, (k_mask_write<<<(unsigned)nb, 256, 0, c->stream>>>(mask, bit, ncand, c->blockoff.as<uint64_t>(), c->rowlen.as<uint32_t>())));
+    uint64_t nblocks = cdiv(cnt, EMIT_TPB);
+    ENSURE(c->tiles, (nblocks + 2) * 8);
+    double avg = s.gather_total / (double)(ncand ? ncand : 1);
+    uint64_t cap = (uint64_t)(cnt * (avg * 1.15 + 16.0)) + (1 << 16);
+    const uint32_t slot_bytes = 48u * 1024u;
+    for (int attempt = 0; attempt < 6; attempt++, cap *= 2) {
+        uint64_t gen0 = c->arena_gen;
+        char* outp = nullptr;
+        { int ra = out_alloc(c, outslot, cap, &outp); if (ra) return ra; }
+        if (c->arena_on && c->arena_gen != gen0) return 1;           // the arena wrapped: the main series is gone, format instead
+        if (reset_err(c)) return SOFA_ERR_CUDA;
+        CK(cudaMemsetAsync(c->tiles.p, 0, (nblocks + 1) * 8, c->stream));
+        GatherArgs a;
+        a.main_out = s.gather_ptr; a.rec_off = s.rec_off.as<unsigned long long>();
+        a.index = c->rowlen.as<uint32_t>(); a.nsel = cnt; a.out = outp; a.cap = cap;
+        a.state = c->tiles.as<unsigned long long>(); a.ticket = c->d_flags + 4;
+        a.total = c->d_err + 11; a.overflow = c->d_flags + 2; a.slot_bytes = slot_bytes;
+        LAUNCH(c, K_JSON_WRITE, (k_gather_records<<<(unsigned)nblocks, EMIT_TPB, slot_bytes + 32, c->stream>>>(a)));
+        unsigned long long total = 0; unsigned int ovf = 0;
+        CK_S(small_d2h(c, &total, c->d_err + 11, 8));
+        CK_S(small_d2h(c, &ovf, c->d_flags + 2, 4));
+        int r = check_kernel_error(c, "emit_json (gather)");
+        if (r) return r;
+        if (ovf) { if (total + 64 > cap * 2) cap = total / 2 + 64; continue; }
+        out_commit(c, outslot, total);
+        if (nbytes) *nbytes = total;
+        if (nrec) *nrec = cnt;
+        return 0;
+    }
+    FAIL(SOFA_ERR_CAP, "emit_json (gather): output capacity estimate failed repeatedly");
+}
+
+int set_gather_attr(void) {
+    return (int)cudaFuncSetAttribute(k_gather_records, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+}
+
 extern "C" {
+
+int sofa_b200_emit_json_series(sofa_ctx* c, int k, uint32_t stride, int32_t nkw, const char* const* kws, uint64_t* counts,
+                               uint64_t* nbytes, uint64_t* nrec) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (stride == 0 || nkw < 0 || nkw > 8 || (nkw && !kws)) FAIL(SOFA_ERR_ARG, "emit_json_series: stride >= 1, 0..8 keywords");
+    Source& s = c->src[k];
+    if (k == SRC_PERF && !(s.viz_ready && s.viz_stride == stride))
+        FAIL(SOFA_ERR_STATE, "emit_json_series(perf): call viz_mangled + set_demangled for this stride first");
+    s.gather_ok = false;
+    FilterTable ft;
+    memset(&ft, 0, sizeof ft);
+    size_t lens[8] = {0};
+    for (int i = 0; i < nkw; i++) {
+        lens[i] = strlen(kws[i]);
+        if (lens[i] == 0 || lens[i] > 32) FAIL(SOFA_ERR_ARG, "emit_json_series: keyword length must be 1..32 bytes");
+    }
+    filter_table_build(&ft, nkw, kws, lens);
+    PackedFilter pf;
+    if (nkw == 0 || !packed_filter_from(ft, &pf)) {
+        // keywords longer than 64 bytes in total: unfused path (main series, then set_filters + formatted filter series)
+        r = sofa_b200_emit_json(c, k, stride, -1, nbytes, nrec);
+        if (r || nkw == 0) return r;
+        return sofa_b200_set_filters(c, k, stride, nkw, kws, counts);
+    }
+    uint64_t ncand = cdiv(s.n_rows, stride);
+    ENSURE(c->ftable, sizeof(FilterTable));
+    ENSURE(s.mask, ncand + 16);
+    ENSURE(s.rec_off, (ncand + 2) * 8);
+    CK_S(small_h2d(c, c->ftable.p, &pf, sizeof pf));
+    CK_S(stream_sync(c));
+    uint32_t fmask = 0;
+    r = fmask_for(c, k, stride, &fmask); if (r) return r;
+    JsonFuse jf{c->ftable.as<PackedFilter>(), s.mask.as<uint8_t>(), s.rec_off.as<unsigned long long>(), true};
+    uint64_t nb = 0, nr = 0;
+    unsigned long long cn[8] = {0};
+    r = emit_fused_t<FMT_JSON>(c, k, stride, nullptr, 0, fmask, 1, ncand, &nb, &nr, nullptr, &jf);
+    if (r) return r;
+    CK_S(small_d2h(c, cn, c->d_err + 2, 64));
+    CK_S(stream_sync(c));
+    if (counts) for (int i = 0; i < nkw; i++) counts[i] = cn[i];
+    for (int i = 0; i < 8; i++) s.filter_counts[i] = i < nkw ? cn[i] : 0;
+    s.mask_stride = stride; s.nkw = nkw;
+    s.gather_ok = nr > 0; s.gather_stride = stride; s.gather_total = (double)nb;
+    if (nbytes) *nbytes = nb >= 2 ? nb - 2 : 0;
+    if (nrec) *nrec = nr;
+    return 0;
+}
 
 int sofa_b200_emit_csv(sofa_ctx* c, int k, uint32_t stride, uint64_t* nbytes) {
     int r = need_parsed(c, k); if (r) return r;
@@ -127,6 +247,19 @@ int sofa_b200_emit_json(sofa_ctx* c, int k, uint32_t stride, int32_t filter_idx,
     if (filter_idx >= 0) {
         if (filter_idx >= s.nkw || s.mask_stride != stride) FAIL(SOFA_ERR_STATE, "emit_json: filter not set for this stride");
         mask = s.mask.as<uint8_t>();
+    }
+    if (filter_idx < 0) s.gather_ok = false;              // a plain main-series emit replaces the resident one
+    if (filter_idx >= 0 && s.gather_ok && s.gather_stride == stride &&
+        (s.gather_gen == ~0ull || (c->arena_on && s.gather_gen == c->arena_gen))) {
+        uint64_t gb = 0, gr = 0;
+        r = gather_series(c, k, filter_idx, &gb, &gr);
+        if (r == 0) {
+            if (nbytes) *nbytes = gb >= 2 ? gb - 2 : 0;
+            if (nrec) *nrec = gr;
+            return 0;
+        }
+        if (r < 0) return r;
+        s.gather_ok = false;                                 // r == 1: main series no longer resident
     }
     uint32_t fmask = 0;
     r = fmask_for(c, k, stride, &fmask); if (r) return r;

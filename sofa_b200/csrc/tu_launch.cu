@@ -82,5 +82,6 @@ int set_kernel_attrs(void) {
     if ((e = inst_emit_attr_sideout_csv())) return e;
     if ((e = inst_emit_attr_sideout_json())) return e;
     if ((e = inst_emit_attr_sideout_aux())) return e;
+    if ((e = set_gather_attr())) return e;
     return 0;
 }

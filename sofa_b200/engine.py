@@ -160,6 +160,30 @@ class CudaEngine:
         n, nrec = self.json_device(kind, stride, filt)
         return self._fetch(1, n, out), nrec
 
+    def json_series_device(self, kind, stride, kws):
+        """Main series with the keyword filters matched in the same pass -> (bytes, records, [hits per keyword]);
+        the filter series are then gathered by json_device(kind, stride, k)."""
+        arr = (ctypes.c_char_p * max(1, len(kws)))(*[k.encode() if isinstance(k, str) else k for k in kws])
+        counts = (ctypes.c_uint64 * 8)()
+        n, nrec = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_emit_json_series(self.ctx, kind, stride, len(kws), arr, counts,
+                                                        ctypes.byref(n), ctypes.byref(nrec)))
+        return n.value, nrec.value, [counts[i] for i in range(len(kws))]
+
+    def json_series(self, kind, stride, kws, out=None):
+        n, nrec, counts = self.json_series_device(kind, stride, kws)
+        return self._fetch(1, n, out), nrec, counts
+
+    def fetch_range(self, which, off, n):
+        out = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.sofa_b200_fetch_range(self.ctx, which, int(off), int(n), ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def emit_block_end(self, block):
+        v = ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_emit_block_end(self.ctx, int(block), ctypes.byref(v)))
+        return v.value
+
     def set_filters(self, kind, stride, kws):
         arr = (ctypes.c_char_p * max(1, len(kws)))(*[k.encode() if isinstance(k, str) else k for k in kws])
         counts = (ctypes.c_uint64 * 8)()

@@ -303,12 +303,18 @@ def _preprocess(cfg, eng):
         with open(logdir + 'gputrace.csv', 'wb') as f:
             f.write(CSV_HEADER)
             f.write(memoryview(body))
-        gpu_series.records, gpu_series.nrec = eng.json(SRC_GPU, ratio, -1)
         kws = [flt.keyword for flt in cfg.gpu_filters]
         for kw in kws:
             _check_keyword(kw)
+        if kws and ratio == 1:
+            # the filters run on the frame of the main series: one formatting pass matches them too, and the
+            # filter series below are gathered from its records
+            gpu_series.records, gpu_series.nrec, _ = eng.json_series(SRC_GPU, 1, kws)
+        else:
+            gpu_series.records, gpu_series.nrec = eng.json(SRC_GPU, ratio, -1)
+            if kws:
+                eng.set_filters(SRC_GPU, 1, kws)               # on the FULL frame (:1446-1452)
         if kws:
-            eng.set_filters(SRC_GPU, 1, kws)                   # on the FULL frame (:1446-1452)
             for i, flt in enumerate(cfg.gpu_filters):
                 rec, nrec = eng.json(SRC_GPU, 1, i)
                 gpu_filter_series.append(SeriesOut(flt.keyword, '[keyword]' + flt.keyword, flt.color, rec, nrec))
@@ -360,13 +366,15 @@ def _preprocess(cfg, eng):
                 f.write(memoryview(body))
             mangled = eng.viz_mangled(ratio)                  # unique _Z... viz names
             eng.set_demangled([(m, demangle(m)) for m in mangled])
-            rec, nrec = eng.json(SRC_PERF, ratio, -1)
-            cpu_series.append(SeriesOut('cpu_trace', 'CPU', 'DarkGray', rec, nrec))
             kws = [flt.keyword for flt in cfg.cpu_filters]
             for kw in kws:
                 _check_keyword(kw)
+            if kws:                                           # filters on the viz frame (:1819-1827): matched in the same pass
+                rec, nrec, _ = eng.json_series(SRC_PERF, ratio, kws)
+            else:
+                rec, nrec = eng.json(SRC_PERF, ratio, -1)
+            cpu_series.append(SeriesOut('cpu_trace', 'CPU', 'DarkGray', rec, nrec))
             if kws:
-                eng.set_filters(SRC_PERF, ratio, kws)         # on the viz frame (:1819-1827)
                 for i, flt in enumerate(cfg.cpu_filters):
                     rec, nrec = eng.json(SRC_PERF, ratio, i)
                     cpu_series.append(SeriesOut(flt.keyword, '[keyword]' + flt.keyword, flt.color, rec, nrec))

@@ -109,6 +109,12 @@ class HostSimEngine:
     def set_filters(self, kind, stride, kws):
         self.filters[kind] = (stride, list(kws))
 
+    def json_series(self, kind, stride, kws):
+        """main series + keyword filters set for the following json(kind, stride, k) calls"""
+        rec, n = self.json(kind, stride, -1)
+        self.set_filters(kind, stride, kws)
+        return rec, n, None
+
     def json(self, kind, stride, filt):
         if filt < 0:
             out, _, n = self._run(kind, 1, stride, self._fmask(kind, stride))

@@ -207,6 +207,35 @@ def test_top_k_and_cpu_profile_match_oracle(tmp_path):
         eng.close()
 
 
+def test_name_group_hash_collisions_fail_loudly(tmp_path):
+    """get_top_k_events / nccl_time group rows by a 64-bit hash of the name; the verification pass over the sorted
+    rows must refuse to merge two different names that share a hash.  Collisions are forced by narrowing the hash
+    (test hook), the same run with the full hash passes."""
+    import ctypes
+    from sofa_b200.engine import CudaEngine
+    from sofa_b200 import hostlogic as hl, _lib as L
+    from sofa_b200.sofa_analyze import load_gpu_source, load_perf_source
+    a = os.path.join(str(tmp_path), "l") + "/"
+    synth.make_logdir(a, seed=77, n_perf=5000, n_gpu=20000)
+    cfg = default_report_config(a)
+    sofa_preprocess(cfg)
+    eng = CudaEngine(0)
+    try:
+        assert load_gpu_source(cfg, eng) and load_perf_source(cfg, eng)
+        ok = eng.top_k(hl.SRC_GPU, 5)
+        gp = eng.gpu_profile()
+        eng._check(eng.lib.sofa_b200_set_debug(eng.ctx, L.SOFA_DEBUG_NAME_HASH_MASK, ctypes.c_uint64(0xF)))
+        for call in (lambda: eng.top_k(hl.SRC_GPU, 5), lambda: eng.top_k(hl.SRC_PERF, 5), eng.gpu_profile):
+            with pytest.raises(L.SofaB200Error) as ei:
+                call()
+            assert "share one 64-bit hash" in str(ei.value)
+        eng._check(eng.lib.sofa_b200_set_debug(eng.ctx, L.SOFA_DEBUG_NAME_HASH_MASK, ctypes.c_uint64(0xFFFFFFFFFFFFFFFF)))
+        assert eng.top_k(hl.SRC_GPU, 5) == ok
+        assert eng.gpu_profile().nccl_time == gp.nccl_time
+    finally:
+        eng.close()
+
+
 def test_verbose_analyze_runs(tmp_path, capsys):
     from sofa_b200.sofa_analyze import sofa_analyze
     a = os.path.join(str(tmp_path), "l") + "/"
@@ -590,3 +619,36 @@ def test_cli_report_then_standalone_analyze(tmp_path):
         got[f[1]] = float(f[2])
     for k, v in want.items():
         assert abs(got[k] - float(v)) <= 0.0005 + 1e-9 * abs(float(v)), (k, got[k], v)       # the table prints %.3lf
+
+
+# ---------------------------------------------------------------------------- BASELINE config sizes (slow)
+def _full_pass_parity(tmp_path, **kw):
+    """One logdir through the oracle (all host cores) and through sofa_preprocess + sofa_analyze; every output file the
+    reference would write must be byte-identical (bench.py's parity_sample helpers)."""
+    import shutil
+    import multiprocessing as mp
+    import bench
+    a = os.path.join(str(tmp_path), "oracle") + "/"
+    b = os.path.join(str(tmp_path), "cuda") + "/"
+    os.makedirs(a)
+    synth.make_logdir(a, **kw)
+    synth.write_side_raw(a, kw["seed"], n_samples=200, n_cores=16, n_gpus=4)
+    shutil.copytree(a, b)
+    bench.oracle_pass(a, mp.cpu_count())
+    bench.product_pass(b, 0)
+    files = bench.parity_sample(a, b)
+    assert "report.js" in files
+    return files
+
+
+def test_config1_one_million_perf_events(tmp_path):
+    """BASELINE configs[0]: 1 M-event perf-only trace, full preprocess + analyze, byte-exact."""
+    files = _full_pass_parity(tmp_path, seed=20260921 + 1, n_perf=1000000)
+    assert "cputrace.csv" in files and "performance.csv" in files
+
+
+def test_config2_slice_two_million_gpu_events(tmp_path):
+    """A 2 M-row nvprof slice of BASELINE configs[1] (+ 100 k perf and packets so every analyze function runs)."""
+    files = _full_pass_parity(tmp_path, seed=20260921 + 2, n_perf=100000, n_gpu=2000000, n_net=100000)
+    for fn in ("gputrace.csv", "comm.csv", "nettrace.csv", "netrank.csv"):
+        assert fn in files
