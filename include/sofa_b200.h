@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define SOFA_B200_ABI_VERSION 1
+#define SOFA_B200_ABI_VERSION 2
 
 #define SOFA_OK 0
 #define SOFA_ERR_CUDA (-1)   /* CUDA runtime error */
@@ -62,6 +62,8 @@ typedef struct {
     double duration[4];          /* summed duration */
     /* (1+n) x (1+n) row-major matrices, n = min(n_gpus_max, 15): payload sum, count, bw sum, bw count */
     double accum[256], accum_count[256], accum_bw[256], accum_bw_count[256];
+    /* the "[id]: time" lines of --verbose (:349-354): the first 64 deviceIds in ascending order and their summed durations */
+    int64_t per_gpu_id[64]; double per_gpu_time[64];
 } sofa_gpu_profile_t;
 
 typedef struct {
@@ -189,6 +191,31 @@ int sofa_b200_window_reduce(sofa_ctx*, const double* ends, uint32_t n_windows, d
 typedef struct { int64_t src, dst, payload_sum, count; } sofa_net_pair_t;
 int sofa_b200_net_profile(sofa_ctx*, uint32_t stride, double* net_time, int64_t* payload_total, sofa_net_pair_t* pairs,
                           uint32_t cap, uint32_t* n_pairs);
+/* net_profile --verbose (:398): df.groupby(['pkt_src','pkt_dst','payload']).size() over the same packets, unordered. */
+typedef struct { int64_t src, dst, payload, count; } sofa_net_triple_t;
+int sofa_b200_net_triples(sofa_ctx*, uint32_t stride, sofa_net_triple_t* out, uint32_t cap, uint32_t* n_out);
+/* --network_filters (sofa_preprocess.py:1214-1231) on the packets i % stride == 0: mask bit k (k < n_others) = payload > 0
+ * and pkt_src == base and pkt_dst == others[k] (series "to_<others[k]>"), bit 4 + k = payload > 0 and pkt_dst == base and
+ * pkt_src == others[k] ("from_<others[k]>"); counts[8] = rows per bit.  The series are then emitted with
+ * sofa_b200_emit_json(SRC_NET, stride, bit).  At most 4 peers per call. */
+int sofa_b200_set_net_filters(sofa_ctx*, uint32_t stride, int64_t base, int32_t n_others, const int64_t* others, uint64_t* counts);
+/* mpstat_profile (sofa_analyze.py:735-790) over the parsed mpstat.csv body (source 3): n_cores = int(max(deviceId) + 1),
+ * sums[core * 5 + q] = sum over the core's rows, in row order with numpy's pairwise tree, of t_USR, t_SYS, t_IDL, t_IOW,
+ * t_IRQ (q = 0..4) with dt_all = 0.1 where IDL == 100 else duration / ((100 - IDL) / 100) and t_X = dt_all * X / 100. */
+int sofa_b200_mpstat_profile(sofa_ctx*, double* sums, uint32_t cap_cores, uint32_t* n_cores);
+/* Column statistics of a parsed side table (source 3..5) over the rows with event == `event` (all rows when use_event
+ * is 0): row count, numpy-pairwise sum in row order (mean = sum / count) and, for q = 0.25, 0.5, 0.75, the two order
+ * statistics numpy's linear quantile interpolates between.  value_col: 0 timestamp, 2 duration, 3 deviceId, 6 bandwidth.
+ * Used by netbandwidth_profile (sofa_analyze.py:531-594). */
+int sofa_b200_side_quantiles(sofa_ctx*, int slot, int value_col, int use_event, double event, double* sum, uint64_t* count,
+                             double* q_lo, double* q_hi);
+/* Sums of the five integers parsed out of the name column of a side table (mpstat.csv: usr sys idl iow irq; vmstat.csv
+ * parsed with api_mode = 2: bi bo in cs, vmstat_profile :712-733) and the row count. */
+int sofa_b200_side_int_sums(sofa_ctx*, int slot, int64_t* sums, uint64_t* n_rows);
+/* --spotlight_gpu region of interest (sofa_analyze.py:872-895): the saturating-counter state machine over the
+ * event == 0, deviceId == 0 rows of the parsed nvsmi_trace.csv body (source 4), in row order.  roi_begin / roi_end are
+ * in/out (cfg.roi_begin / cfg.roi_end); both are reset to 0 when end < begin. */
+int sofa_b200_nvsmi_roi(sofa_ctx*, double* roi_begin, double* roi_end);
 /* nvsmi_profile (sofa_analyze.py:259-341) over the parsed nvsmi_trace.csv body (source 4), optionally
  * restricted to roi_begin < timestamp <= roi_end (--spotlight_gpu).  One entry per (deviceId, event)
  * present: row count, duration sum (means = sum / count), and for q = 0.25, 0.5, 0.75 the two order

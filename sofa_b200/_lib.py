@@ -14,7 +14,8 @@ EXPORTS = [
     "sofa_b200_abi_version", "sofa_b200_last_error", "sofa_b200_error_row", "sofa_b200_create",
     "sofa_b200_destroy", "sofa_b200_host_alloc", "sofa_b200_host_free", "sofa_b200_upload",
     "sofa_b200_parse", "sofa_b200_row_flags", "sofa_b200_emit_csv", "sofa_b200_set_filters",
-    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_emit_json_series", "sofa_b200_set_debug", "sofa_b200_fetch_range", "sofa_b200_emit_block_end", "sofa_b200_fetch",
+    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_emit_json_series", "sofa_b200_set_debug", "sofa_b200_net_triples", "sofa_b200_set_net_filters", "sofa_b200_mpstat_profile",
+    "sofa_b200_side_quantiles", "sofa_b200_side_int_sums", "sofa_b200_nvsmi_roi", "sofa_b200_fetch_range", "sofa_b200_emit_block_end", "sofa_b200_fetch",
     "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
     "sofa_b200_synth", "sofa_b200_text_fetch", "sofa_b200_mark", "sofa_b200_elapsed_ms",
@@ -39,7 +40,8 @@ class GpuProfile(ctypes.Structure):
                 ("n_gpus_max", ctypes.c_int64), ("payload", ctypes.c_double * 4),
                 ("bandwidth", ctypes.c_double * 4), ("duration", ctypes.c_double * 4),
                 ("accum", ctypes.c_double * 256), ("accum_count", ctypes.c_double * 256),
-                ("accum_bw", ctypes.c_double * 256), ("accum_bw_count", ctypes.c_double * 256)]
+                ("accum_bw", ctypes.c_double * 256), ("accum_bw_count", ctypes.c_double * 256),
+                ("per_gpu_id", ctypes.c_int64 * 64), ("per_gpu_time", ctypes.c_double * 64)]
 
 
 class Window(ctypes.Structure):
@@ -54,6 +56,10 @@ class Window(ctypes.Structure):
 
 class NetPair(ctypes.Structure):
     _fields_ = [("src", ctypes.c_int64), ("dst", ctypes.c_int64), ("payload_sum", ctypes.c_int64), ("count", ctypes.c_int64)]
+
+
+class NetTriple(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_int64), ("dst", ctypes.c_int64), ("payload", ctypes.c_int64), ("count", ctypes.c_int64)]
 
 
 class NvsmiGroup(ctypes.Structure):
@@ -113,6 +119,14 @@ def load_lib():
     lib.sofa_b200_emit_json_series.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), u64p, u64p, u64p]
     lib.sofa_b200_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
     lib.sofa_b200_set_debug.argtypes = [vp, ctypes.c_int, ctypes.c_uint64]
+    dp = ctypes.POINTER(ctypes.c_double)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    lib.sofa_b200_net_triples.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(NetTriple), ctypes.c_uint32, u32p]
+    lib.sofa_b200_set_net_filters.argtypes = [vp, ctypes.c_uint32, ctypes.c_int64, ctypes.c_int32, i64p, u64p]
+    lib.sofa_b200_mpstat_profile.argtypes = [vp, dp, ctypes.c_uint32, u32p]
+    lib.sofa_b200_side_quantiles.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, u64p, dp, dp]
+    lib.sofa_b200_side_int_sums.argtypes = [vp, ctypes.c_int, i64p, u64p]
+    lib.sofa_b200_nvsmi_roi.argtypes = [vp, dp, dp]
     lib.sofa_b200_fetch_range.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp]
     lib.sofa_b200_emit_block_end.argtypes = [vp, ctypes.c_uint64, u64p]
     lib.sofa_b200_get_column.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64]
@@ -144,7 +158,7 @@ def load_lib():
     lib.sofa_b200_reset_stats.argtypes = [vp]
     lib.sofa_b200_synth.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, u64p]
     lib.sofa_b200_text_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
-    if lib.sofa_b200_abi_version() != 1:
+    if lib.sofa_b200_abi_version() != 2:
         raise ImportError("libsofa_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -18,7 +18,7 @@ extern thread_local std::string g_last_error;
 
 enum {
     K_COUNT = 0, K_SCAN, K_PARSE, K_FLAGS, K_CSV_WRITE, K_JSON_WRITE, K_FILTER,
-    K_VIZ, K_ANALYZE, K_SORT, K_SYNTH, K_NKINDS
+    K_VIZ, K_ANALYZE, K_SORT, K_SYNTH, K_GATHER, K_NKINDS
 };
 
 struct DevBuf {

@@ -760,6 +760,25 @@ SOFA_HD int parse_side(S s, int n, const IngestCfg& c, SideRow* r) {
             r->r[k] = (int32_t)v;
             q = q2;
         }
+    } else if (c.side_table == 3) {
+        // vmstat.csv (vmstat_profile, sofa_analyze.py:712-733): name = 'r=..|b=..|...|si=..|so=..|bi=..|bo=..|in=..|cs=..|...';
+        // pieces 8..11 of name.split('|') with their first three characters dropped: bi, bo, in, cs
+        int q = fa[11] - 1;                                            // "separator" in front of piece 0
+        for (int piece = 0; piece < 12; piece++) {
+            int q2 = find_char(s, n, q + 1, fb[11], '|');
+            int stop = q2 < 0 ? fb[11] : q2;
+            if (piece >= 8) {
+                int a0 = q + 1 + 3;
+                if (a0 > stop) return E_BAD_FLOAT;
+                int64_t v;
+                int st = parse_i64(s + a0, stop - a0, &v);
+                if (st) return num_status_to_err(st, true);
+                if (v < -2000000000 || v > 2000000000) return E_RANGE;
+                r->r[piece - 8] = (int32_t)v;
+            }
+            if (q2 < 0 && piece < 11) return E_FEW_TOKENS;
+            q = q2;
+        }
     }
     return E_OK;
 }

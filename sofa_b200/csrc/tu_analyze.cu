@@ -4,10 +4,12 @@
 #include "kernels_analyze.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_window.cuh"
+#include "kernels_profiles.cuh"
 
 extern "C" {
 
 #include "capi_analyze.inc"
 #include "capi_window.inc"
+#include "capi_profiles.inc"
 
 }  // extern "C"

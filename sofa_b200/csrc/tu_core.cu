@@ -5,7 +5,7 @@
 thread_local std::string g_last_error;
 static const char* KERNEL_NAMES[K_NKINDS] = {
     "count_lines", "scan", "parse", "row_flags", "csv_emit", "json_emit", "filter",
-    "viz_dict", "analyze", "sort", "synth"};
+    "viz_dict", "analyze", "sort", "synth", "json_gather"};
 
 int need_parsed(sofa_ctx* c, int k) {
     if (!c || k < 0 || k > 2) FAIL(SOFA_ERR_ARG, "bad source");
@@ -125,6 +125,7 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     cfg.idx_dstctx = p->idx[8];
     cfg.api_mode = p->api_mode;
     cfg.side_table = k >= 6 ? k - 6 : (k >= 3 ? k - 3 : 0);
+    if (k >= 3 && k < 6 && p->api_mode == 2) cfg.side_table = 3;          // vmstat.csv: bi / bo / in / cs out of the name column
     if (k == SRC_GPU && (cfg.idx_start < 0 || cfg.idx_dur < 0 || cfg.idx_name < 0))
         FAIL(SOFA_ERR_ARG, "parse: gpu trace needs Start, Duration and Name columns");
     ENSURE(s.mhz, 16 * (size_t)cfg.n_mhz + 16);

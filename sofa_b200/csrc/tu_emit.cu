@@ -154,7 +154,7 @@ static int gather_series(sofa_ctx* c, int k, int bit, uint64_t* nbytes, uint64_t
         a.index = c->rowlen.as<uint32_t>(); a.nsel = cnt; a.out = outp; a.cap = cap;
         a.state = c->tiles.as<unsigned long long>(); a.ticket = c->d_flags + 4;
         a.total = c->d_err + 11; a.overflow = c->d_flags + 2; a.slot_bytes = slot_bytes;
-        LAUNCH(c, K_JSON_WRITE, (k_gather_records<<<(unsigned)nblocks, EMIT_TPB, slot_bytes + 32, c->stream>>>(a)));
+        LAUNCH(c, K_GATHER, (k_gather_records<<<(unsigned)nblocks, EMIT_TPB, slot_bytes + 32, c->stream>>>(a)));
         unsigned long long total = 0; unsigned int ovf = 0;
         CK_S(small_d2h(c, &total, c->d_err + 11, 8));
         CK_S(small_d2h(c, &ovf, c->d_flags + 2, 4));

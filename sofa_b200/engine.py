@@ -276,6 +276,54 @@ class CudaEngine:
         pairs = self._net_pairs
         return t.value, total.value, {(pairs[i].src, pairs[i].dst): pairs[i].payload_sum for i in range(n.value)}
 
+    def net_triples(self, stride):
+        """{(pkt_src, pkt_dst, payload): packets} of the packets i % stride == 0 (net_profile --verbose)."""
+        cap = 1 << 16
+        n = ctypes.c_uint32()
+        while True:
+            buf = (L.NetTriple * cap)()
+            rc = self.lib.sofa_b200_net_triples(self.ctx, int(stride), buf, cap, ctypes.byref(n))
+            if rc == L.SOFA_ERR_CAP and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            self._check(rc)
+            break
+        return {(buf[i].src, buf[i].dst, buf[i].payload): buf[i].count for i in range(n.value)}
+
+    def set_net_filters(self, stride, base, others):
+        """--network_filters masks for up to 4 peers: bit k = to_<others[k]>, bit 4 + k = from_<others[k]> -> hit counts [8]"""
+        arr = (ctypes.c_int64 * 4)(*(list(others) + [0] * (4 - len(others))))
+        counts = (ctypes.c_uint64 * 8)()
+        self._check(self.lib.sofa_b200_set_net_filters(self.ctx, int(stride), int(base), len(others), arr, counts))
+        return [counts[i] for i in range(8)]
+
+    def mpstat_profile(self):
+        """[[t_USR, t_SYS, t_IDL, t_IOW, t_IRQ] per core] summed over the parsed mpstat.csv (source 3)"""
+        cap = 4096
+        sums = (ctypes.c_double * (cap * 5))()
+        n = ctypes.c_uint32()
+        self._check(self.lib.sofa_b200_mpstat_profile(self.ctx, sums, cap, ctypes.byref(n)))
+        return [[sums[c * 5 + q] for q in range(5)] for c in range(n.value)]
+
+    def side_quantiles(self, slot, value_col, event=None):
+        """(count, pairwise sum, [(lo, hi)] for q = .25, .5, .75) of one column of a parsed side table"""
+        s, n = ctypes.c_double(), ctypes.c_uint64()
+        lo, hi = (ctypes.c_double * 3)(), (ctypes.c_double * 3)()
+        self._check(self.lib.sofa_b200_side_quantiles(self.ctx, slot, value_col, 0 if event is None else 1,
+                                                      0.0 if event is None else float(event), ctypes.byref(s), ctypes.byref(n), lo, hi))
+        return n.value, s.value, [(lo[i], hi[i]) for i in range(3)]
+
+    def side_int_sums(self, slot):
+        sums = (ctypes.c_int64 * 5)()
+        n = ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_side_int_sums(self.ctx, slot, sums, ctypes.byref(n)))
+        return [sums[i] for i in range(5)], n.value
+
+    def nvsmi_roi(self, roi_begin, roi_end):
+        a, b = ctypes.c_double(float(roi_begin)), ctypes.c_double(float(roi_end))
+        self._check(self.lib.sofa_b200_nvsmi_roi(self.ctx, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def nvsmi_profile(self, roi=None):
         """Per (deviceId, event) group of the parsed nvsmi_trace.csv (source 4): {(dev, event): (count, sum,
         [(lo, hi)] for q = .25, .5, .75)}, device ids in order of first appearance, first / last timestamp."""

@@ -1,15 +1,22 @@
 """Drop-in `sofa_analyze(cfg)` (reference: bin/sofa_analyze.py:793-1055).
 
-Round-1 scope: gpu_profile + comm_profile features and the
-"Final Performance Features" table, computed by device kernels on the parsed columns
-(values read through the "%.6f" round trip the reference's pd.read_csv sees; float sums
-follow numpy's pairwise tree exactly).  Profiles of sources that are not on the hot path
-yet (mpstat / nvsmi / netstat / vmstat / diskstat / strace, concurrency_breakdown, aisi,
-potato) are absent; their input files make sofa_preprocess raise, so no silent gaps.
+Same driver order, same stdout (feature table, verbose tables) and the same files (comm.csv, netrank.csv,
+performance.csv) as the reference; pinned byte for byte against the unmodified reference driver on
+tests/golden/driver_* (tests/golden/make_golden_driver.py).  Every per-row reduction runs in device kernels
+behind libsofa_b200.so: group sums in numpy's pairwise order, radix sorts for top-k / quartiles, hash tables
+for the (pkt_src, pkt_dst[, payload]) groups, window reductions, the --spotlight_gpu state machine.  The host
+keeps the scalar logic and the printing of the small result tables (a few hundred cells) with pandas, as the
+reference does.
 
-The reference re-reads <src>trace.csv; here the rows are re-ingested from the raw logs in
-`cfg.logdir` (same bytes -> same columns), or taken from the engine sofa_preprocess left
-resident when `cfg.keep_engine` is set (`sofa report`).
+Profile functions: cpu_profile, strace_profile (a title), net_profile (+ --verbose matrices), netbandwidth_profile,
+vmstat_profile, mpstat_profile, nvsmi_profile, gpu_profile (+ comm_profile, get_top_k_events), concurrency_breakdown.
+Not built: blktrace_latency_profile / diskstat_profile (their inputs come from `btt` and diskstat_vector.csv), the PDF
+charts (no matplotlib), nvlink ring search, POTATO, AISI driver hook.
+
+The reference re-reads <src>trace.csv; here the trace rows are re-ingested from the raw logs in `cfg.logdir`
+(same bytes -> same columns), or taken from the engine sofa_preprocess left resident when `cfg.keep_engine` is
+set (`sofa report`); the small side tables (mpstat.csv, nvsmi_trace.csv, netstat.csv, vmstat.csv) are parsed from
+the CSV files themselves.
 """
 import glob
 import os
@@ -73,6 +80,8 @@ def gpu_profile(cfg, eng):
     if cfg.verbose:
         print_title('GPU Profiling')
         print('Per-GPU time (s):')
+        for i in range(min(int(gp.num_gpus), 64)):                # :349-354
+            print("[%d]: %lf" % (gp.per_gpu_id[i], gp.per_gpu_time[i]))
     feats = []
     if gp.n_gpus_max == 0:
         # sofa_common.py:58-60 calls print_warning with one argument: the reference dies with
@@ -84,9 +93,10 @@ def gpu_profile(cfg, eng):
         f.write(b",timestamp,pkt_src,pkt_dst,payload,bandwidth\n")
         f.write(memoryview(eng.comm_csv()))
     if cfg.verbose:                                   # get_top_k_events (sofa_analyze.py:34-44)
+        import pandas as pd
+        top = eng.top_k(SRC_GPU, 10)
         print("Top %d Events: " % 10)
-        for name, total in eng.top_k(SRC_GPU, 10):
-            print("%-60s %.6f" % (name.rstrip('\n')[:60], total))
+        print(pd.DataFrame({'duration': [t for _, t in top]}, index=pd.Index([n for n, _ in top], name='name')))
     feats += [('gpu_time', gp.gpu_time), ('num_gpus', gp.num_gpus), ('kernel_time', gp.kernel_time),
               ('nccl_time', gp.nccl_time)]
     return feats
@@ -99,9 +109,13 @@ def cpu_profile(cfg, eng):
     print('elapsed_time (s) = %.6lf' % cfg.elapsed_time)
     print("[%d]: %lf" % (-1, total))
     print("total execution time (s) = %.3lf" % total)
-    print("%12s %10s %10s  %s" % ('timestamp', 'ratio(%)', 'duration', 'name'))
-    for _, ts, dur, name in rows:
-        print("%12.6f %10.6f %10.6f  %s" % (ts, dur / total * 100 if total else 0.0, dur, name))
+    import numpy as np
+    import pandas as pd
+    df = pd.DataFrame({'timestamp': [r[1] for r in rows], 'duration': [r[2] for r in rows], 'name': [r[3] for r in rows]},
+                      columns=['timestamp', 'duration', 'name'])
+    with np.errstate(all='ignore'):
+        df['ratio(%)'] = df['duration'] / total * 100
+    print(df[['timestamp', 'ratio(%)', 'duration', 'name']].to_string(index=False))
     return total, rows
 
 
@@ -177,7 +191,7 @@ def net_profile(logdir, cfg, eng, features):
     cast = (lambda x: np.float64(x)) if as_float else (lambda x: np.int64(x))
     total = cast(total)
     if cfg.verbose:
-        raise NotImplementedError("net_profile --verbose tables are not implemented")
+        _net_verbose(eng, ratio, pairs, total, as_float)
     record = [(s, d, cast(v)) for (s, d), v in sorted(pairs.items())]          # index-major, ascending, as the unstacked frame
     record.sort(key=lambda tup: tup[2], reverse=True)
     with open(logdir + 'netrank.csv', 'w') as f:
@@ -187,6 +201,154 @@ def net_profile(logdir, cfg, eng, features):
                 continue
             f.write('%s,%s,%s,%s\n' % (_ip_text(s), _ip_text(d), _convertbyte(value), repr(float(round(value / total, 2)))))
     return features + [('net_time', net_time)]
+
+
+def _net_verbose(eng, ratio, pairs, total, as_float):
+    """The two matrices of sofa_analyze.py:398-461: payload summed per (pkt_src, pkt_dst) and packets per
+    (pkt_src, pkt_dst, payload), both from device hash tables, laid out and printed with pandas as the reference does."""
+    import numpy as np
+    import pandas as pd
+    kt = np.float64 if as_float else np.int64
+
+    def frame(d, names, dtype):
+        keys = sorted(d)
+        idx = pd.MultiIndex.from_arrays([np.asarray([k[i] for k in keys], dtype=kt) for i in range(len(names))], names=names)
+        return pd.Series(np.asarray([d[k] for k in keys], dtype=dtype), index=idx).unstack(level=1, fill_value=0)
+    psum = frame(pairs, ['pkt_src', 'pkt_dst'], kt)
+    pnum = frame(eng.net_triples(ratio), ['pkt_src', 'pkt_dst', 'payload'], np.int64)
+    psum = psum.rename(columns={c: _ip_text(c) for c in psum.columns.tolist()})
+    pnum = pnum.rename(columns={c: _ip_text(c) for c in pnum.columns.tolist()})
+    psum = psum.rename(index={i: _ip_text(i) for i in psum.index.tolist()})
+    # (:458 renames level 0 of the packet-count index with set_levels(inplace=True), which current pandas cannot do in
+    #  place: the golden stdout of the reference on this stack keeps the numeric level, and so does this)
+    print("total amount of network traffic : ", _convertbyte(total), '\n', psum.to_string(), "\n")
+    print("total amount of network packets = %d\n" % pnum.sum().sum(), pnum.to_string(), "\n")
+
+
+def _convertbytes(B):
+    """sofa_analyze.py:513-529."""
+    B = float(B)
+    KB = float(1024)
+    MB = float(KB ** 2)
+    GB = float(KB ** 3)
+    TB = float(KB ** 4)
+    if B < KB:
+        return '{0:.2f} B/s'.format(B)
+    elif KB <= B < MB:
+        return '{0:.2f} KB/s'.format(B / KB)
+    elif MB <= B < GB:
+        return '{0:.2f} MB/s'.format(B / MB)
+    elif GB <= B < TB:
+        return '{0:.2f} GB/s'.format(B / GB)
+    return '{0:.2f} TB/s'.format(B / TB)
+
+
+def _np_quantile(lo, hi, count, q):
+    """numpy's linear quantile between the order statistics at floor / ceil of (count - 1) * q (its _lerp, both branches)."""
+    import numpy as np
+    vi = np.float64(q) * (count - 1)
+    t = vi - np.floor(vi)
+    a, b = np.float64(lo), np.float64(hi)
+    d = b - a
+    return b - d * (1 - t) if t >= 0.5 else a + d * t
+
+
+def _upload_side_csv(eng, logdir, slot, fn, api_mode=0):
+    """Body of a 13-column side CSV (mpstat / nvsmi_trace / netstat / vmstat) -> parsed columns of a side-table slot."""
+    p = hl.base_params(slot, 0.0, True)
+    p['api_mode'] = api_mode
+    body = _csv_body(logdir + fn)
+    eng.upload(slot, body)
+    eng.parse(slot, p)
+    return body
+
+
+def netbandwidth_profile(logdir, cfg, eng, features):
+    """sofa_analyze.py:531-594 (the PDF chart needs matplotlib and is not drawn)."""
+    if not cfg.cluster_ip and cfg.verbose:
+        print_title('Network Bandwidth Profiling:')
+    _upload_side_csv(eng, logdir, SRC_NETSTAT_CSV, 'netstat.csv')
+    st = {}
+    for key, ev in (('tx', 0.0), ('rx', 1.0)):
+        cnt, total, qs = eng.side_quantiles(SRC_NETSTAT_CSV, 6, ev)
+        if cnt == 0:
+            raise ValueError("cannot convert float NaN to integer")          # int(nan mean) in the reference
+        st[key] = [_np_quantile(lo, hi, cnt, 0.25 * (i + 1)) for i, (lo, hi) in enumerate(qs)] + [int(total / cnt)]
+    with open('%s/netstat.txt' % logdir) as f:
+        lines = f.readlines()
+    first_line, last_line = lines[0], lines[-1]
+    tx_amount = int(last_line.split(',')[1]) - int(first_line.split(',')[1])
+    rx_amount = int(last_line.split(',')[2]) - int(first_line.split(',')[2])
+    if not cfg.cluster_ip and cfg.verbose:
+        print('Amount of Network Traffic : %s' % (_convertbyte(tx_amount + rx_amount)))
+        print('Amount of tx : %s' % _convertbyte(tx_amount))
+        print('Amount of rx : %s' % _convertbyte(rx_amount))
+        print('Bandwidth Quartile :')
+        for i, nm in enumerate(('Q1 ', 'Q2 ', 'Q3 ')):
+            print('%s tx : %s, rx : %s' % (nm, _convertbytes(st['tx'][i]), _convertbytes(st['rx'][i])))
+        print('Avg tx : %s, rx : %s' % (_convertbytes(st['tx'][3]), _convertbytes(st['rx'][3])))
+        print('Network Bandwidth Chart is saved at %s/network_report.pdf' % logdir)
+        features = features + [('bw_tx_q2', st['tx'][1]), ('bw_tx_q3', st['tx'][2]), ('bw_rx_q2', st['rx'][1]), ('bw_rx_q3', st['rx'][2])]
+    return features
+
+
+def vmstat_profile(logdir, cfg, eng, features):
+    """sofa_analyze.py:712-733: means of bi / bo / in / cs parsed out of the name column of vmstat.csv."""
+    _upload_side_csv(eng, logdir, SRC_MPSTAT_CSV, 'vmstat.csv', api_mode=2)
+    (bi, bo, in_, cs, _), n = eng.side_int_sums(SRC_MPSTAT_CSV)
+    import numpy as np
+    vm_bi, vm_bo, vm_in, vm_cs = (np.float64(v) / n for v in (bi, bo, in_, cs))
+    if cfg.verbose:
+        print_title('VMSTAT Profiling:')
+        print('average bi/s: %d' % int(vm_cs))            # (labels as swapped as in the reference)
+        print('average bo/s: %d' % int(vm_in))
+        print('average cs/s: %d' % int(vm_bi))
+        print('average in/s: %d' % int(vm_bo))
+    return features + [('vm_bi', vm_bi), ('vm_bo', vm_bo), ('vm_cs', vm_cs), ('vm_in', vm_in)]
+
+
+def mpstat_profile(logdir, cfg, eng, features):
+    """sofa_analyze.py:735-790.  Per-core sums of t_USR .. t_IRQ on the device (stable sort by core + numpy-pairwise
+    segment sums); the per-core table is a few dozen cells and is reduced and printed with pandas as in the reference
+    (with :752-756's chained assignments taking effect, as on the pandas versions the reference was written for)."""
+    import pandas as pd
+    if not cfg.cluster_ip and cfg.verbose:
+        print_title('MPSTAT Profiling:')
+    _upload_side_csv(eng, logdir, SRC_MPSTAT_CSV, 'mpstat.csv')
+    sums = eng.mpstat_profile()
+    num_cores = len(sums)
+    df_summary = pd.DataFrame(sums, columns=['USR', 'SYS', 'IDL', 'IOW', 'IRQ'], dtype='float64')
+    verbose = not cfg.cluster_ip and cfg.verbose
+    if verbose:
+        print('CPU Utilization (%):')
+        print('core\tUSR\tSYS\tIDL\tIOW\tIRQ')
+    for i in range(len(df_summary)):
+        t_sum = df_summary.iloc[i].sum()
+        if verbose:
+            print('%3d\t%3d\t%3d\t%3d\t%3d\t%3d' % (i, int(100.0 * df_summary.iloc[i]['USR'] / t_sum),
+                                                      int(100.0 * df_summary.iloc[i]['SYS'] / t_sum),
+                                                      int(100.0 * df_summary.iloc[i]['IDL'] / t_sum),
+                                                      int(100.0 * df_summary.iloc[i]['IOW'] / t_sum),
+                                                      int(100.0 * df_summary.iloc[i]['IRQ'] / t_sum)))
+    if verbose:
+        print('CPU Time (s):')
+        print('core\tUSR\tSYS\tIDL\tIOW\tIRQ')
+        for i in range(len(df_summary)):
+            print('%3d\t%.2lf\t%.2lf\t%.2lf\t%.2lf\t%.2lf' % (i, df_summary.iloc[i]['USR'], df_summary.iloc[i]['SYS'],
+                                                                df_summary.iloc[i]['IDL'], df_summary.iloc[i]['IOW'],
+                                                                df_summary.iloc[i]['IRQ']))
+    total_cpu_time = df_summary[['USR', 'SYS', 'IRQ']].sum().sum()
+    cpu_util = int(100 * total_cpu_time / (num_cores * cfg.elapsed_time))
+    if verbose:
+        print('Active CPU Time (s): %.3lf' % total_cpu_time)
+        print('Active CPU ratio (%%): %3d' % cpu_util)
+    return features + [('num_cores', num_cores), ('cpu_util', cpu_util)]
+
+
+def spotlight_roi(logdir, cfg, eng):
+    """sofa_analyze.py:872-895: cfg.roi_begin / cfg.roi_end from the SM utilisation of GPU 0 (device state machine)."""
+    _upload_side_csv(eng, logdir, SRC_NVSMI_CSV, 'nvsmi_trace.csv')
+    cfg.roi_begin, cfg.roi_end = eng.nvsmi_roi(cfg.roi_begin, cfg.roi_end)
 
 
 def _lerp(lo, hi, count, q):
@@ -272,6 +434,8 @@ def concurrency_breakdown(logdir, cfg, eng, features):
     import numpy as np
     import pandas as pd
     from . import hostlogic as hl2
+    if cfg.verbose:
+        print_title('Concurrency Breakdown Analysis')
     bodies = {}
     for k, fn in ((SRC_MPSTAT_CSV, 'mpstat.csv'), (SRC_NVSMI_CSV, 'nvsmi_trace.csv'), (SRC_NETSTAT_CSV, 'netstat.csv')):
         bodies[k] = _csv_body(logdir + fn) if os.path.isfile(logdir + fn) else b''
@@ -396,6 +560,16 @@ def load_gpu_source(cfg, eng):
     return True
 
 
+def _has_rows(path):
+    """the file exists and pd.read_csv would give a non-empty frame (more than the header line)"""
+    if not os.path.isfile(path):
+        return False
+    with open(path, 'rb') as f:
+        head = f.read(1 << 16)
+    nl = head.find(b'\n')
+    return nl >= 0 and (len(head) > nl + 1 or os.path.getsize(path) > nl + 1)
+
+
 def sofa_analyze(cfg, engine=None):
     print_main_progress('SOFA analyzing...')
     logdir = cfg.logdir
@@ -403,54 +577,86 @@ def sofa_analyze(cfg, engine=None):
         lines = f.readlines()
         cfg.elapsed_time = float(lines[0].split()[1])
     features = [('elapsed_time', cfg.elapsed_time)]
-    own = False
+    resident = engine is None and getattr(cfg, '_sofa_b200_engine', None) is not None      # `sofa report`: parsed trace rows still on the device
     eng = engine or getattr(cfg, '_sofa_b200_engine', None)
+    own = False
+    if eng is None:
+        from .engine import CudaEngine
+        eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
+        own = True
     try:
-        if cfg.verbose and os.path.isfile(logdir + "cputrace.csv"):
-            if eng is None:
-                from .engine import CudaEngine
-                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
-                own = True
-            if own or engine is not None:
-                load_perf_source(cfg, eng)
-            cpu_profile(cfg, eng)
-        if os.path.isfile(logdir + "nettrace.csv") and os.path.getsize(logdir + "nettrace.csv") > len(",".join(['x'] * 13)):   # :917-923
-            if eng is None:
-                from .engine import CudaEngine
-                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
-                own = True
-            if own or engine is not None:
-                if not load_net_source(cfg, eng):
+        # ---- --spotlight_gpu region of interest (:872-897)
+        if os.path.isfile(logdir + "nvsmi_trace.csv"):
+            if _has_rows(logdir + "nvsmi_trace.csv") and cfg.spotlight_gpu:
+                spotlight_roi(logdir, cfg, eng)
+        else:
+            print_warning(cfg, "nvsmi_trace.csv is not found")
+        # ---- cpu (:899-907)
+        if os.path.isfile(logdir + "cputrace.csv"):
+            if cfg.verbose and _has_rows(logdir + "cputrace.csv"):
+                if not resident:
+                    load_perf_source(cfg, eng)
+                cpu_profile(cfg, eng)
+        else:
+            print_warning(cfg, "%s is not found" % (logdir + "cputrace.csv"))
+        # ---- strace (:909-915)
+        if os.path.isfile(logdir + "strace.csv"):
+            if _has_rows(logdir + "strace.csv"):
+                print_title('STRACE Profiling:')                         # strace_profile (:379-382)
+        else:
+            print_warning(cfg, "%s is not found" % (logdir + "strace.csv"))
+        # ---- net (:917-923)
+        if os.path.isfile(logdir + "nettrace.csv"):
+            if _has_rows(logdir + "nettrace.csv"):
+                if not resident and not load_net_source(cfg, eng):
                     raise IOError("nettrace.csv exists but net.tmp (raw packets) is missing: CSV re-ingest is not implemented")
-            features = net_profile(logdir, cfg, eng, features)
-        if os.path.isfile(logdir + "nvsmi_trace.csv"):                     # :957-961
-            if eng is None:
-                from .engine import CudaEngine
-                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
-                own = True
+                features = net_profile(logdir, cfg, eng, features)
+        else:
+            print_warning(cfg, "%s is not found" % (logdir + "nettrace.csv"))
+        # ---- netstat.csv (:925-931)
+        if os.path.isfile(logdir + "netstat.csv"):
+            if _has_rows(logdir + "netstat.csv"):
+                features = netbandwidth_profile(logdir, cfg, eng, features)
+        else:
+            print_warning(cfg, "%s is not found" % (logdir + "netstat.csv"))
+        # ---- blktrace / diskstat (:933-947): their profile functions are not built; the files make that explicit
+        for fn, what in (("blktrace.csv", "blktrace_latency_profile"), ("diskstat_vector.csv", "diskstat_profile")):
+            if os.path.isfile(logdir + fn):
+                if _has_rows(logdir + fn):
+                    print_warning(cfg, "%s: %s is not implemented; its features are missing from the table" % (fn, what))
+            else:
+                print_warning(cfg, "%s is not found" % (logdir + fn))
+        # ---- vmstat (:949-955), mpstat (:957-963)
+        if os.path.isfile(logdir + "vmstat.csv"):
+            if _has_rows(logdir + "vmstat.csv"):
+                features = vmstat_profile(logdir, cfg, eng, features)
+        else:
+            print_warning(cfg, "%s is not found" % (logdir + "vmstat.csv"))
+        have_mpstat = False
+        if os.path.isfile(logdir + "mpstat.csv"):
+            if _has_rows(logdir + "mpstat.csv"):
+                have_mpstat = True
+                features = mpstat_profile(logdir, cfg, eng, features)
+        else:
+            print_warning(cfg, "%s is not found" % (logdir + "mpstat.csv"))
+        # ---- nvsmi (:965-969), gpu (:971-977)
+        if os.path.isfile(logdir + "nvsmi_trace.csv"):
             features = nvsmi_profile(logdir, cfg, eng, features)
         else:
             print_warning(cfg, "nvsmi_trace.csv is not found")
         if os.path.isfile(logdir + "gputrace.csv"):
-            if eng is None:
-                from .engine import CudaEngine
-                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
-                own = True
-            if own or engine is not None or getattr(cfg, '_sofa_b200_gpu_slot_is_api', False):
-                if not load_gpu_source(cfg, eng):
+            if _has_rows(logdir + "gputrace.csv"):
+                if (not resident or getattr(cfg, '_sofa_b200_gpu_slot_is_api', False)) and not load_gpu_source(cfg, eng):
                     raise IOError("gputrace.csv exists but gputrace.tmp (raw rows) is missing: "
                                   "CSV re-ingest is not implemented")
-            features += gpu_profile(cfg, eng)
+                features += gpu_profile(cfg, eng)
         else:
             print_warning(cfg, "%sgputrace.csv is not found. If there is no need to profile GPU, just ignore it." % logdir)
-        if os.path.isfile(logdir + "mpstat.csv") and os.path.getsize(logdir + "mpstat.csv") > 0:     # :979-984
-            if eng is None:
-                from .engine import CudaEngine
-                eng = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
-                own = True
+        # ---- concurrency_breakdown (:979-984)
+        if have_mpstat:
             features = concurrency_breakdown(logdir, cfg, eng, features)
     finally:
-        if own and eng is not None:
+        if own:
             eng.close()
         if getattr(cfg, '_sofa_b200_engine', None) is not None and engine is None:
             cfg._sofa_b200_engine.close()

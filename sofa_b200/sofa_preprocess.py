@@ -123,6 +123,31 @@ def _write(path, *parts):
             f.write(memoryview(p))
 
 
+def _net_filter_series(cfg, eng, ratio):
+    """--network_filters (:1214-1231): cfg.net_filters[0] is the node of interest; one series "to_<f>" (payload > 0,
+    pkt_src == node, pkt_dst == f) per other address, then one "from_<f>" each.  Equality tests run on the device over
+    the packed addresses; the colours are random in the reference too."""
+    import random
+
+    def packed(s):
+        v = float(s)
+        return int(v) if v == int(v) else None
+    base = packed(cfg.net_filters[0])
+    others = list(cfg.net_filters[1:])
+    out = []
+    for direction, bit0 in (('to_', 0), ('from_', 4)):
+        for c0 in range(0, len(others), 4):
+            chunk = others[c0:c0 + 4]
+            vals = [packed(f) for f in chunk]
+            if base is not None:
+                eng.set_net_filters(ratio, base, [v if v is not None else -(1 << 62) for v in vals])
+            for k, f in enumerate(chunk):
+                color = 'rgba(%s,%s,%s,0.8)' % (random.randint(0, 255), random.randint(0, 255), random.randint(0, 255))
+                rec, nrec = (eng.json(SRC_NET, ratio, bit0 + k) if base is not None and vals[k] is not None else (None, 0))
+                out.append(SeriesOut('%s%s' % (direction, f), '[keyword]%s%s' % (direction, f), color, rec, nrec))
+    return out
+
+
 def _side_sources(cfg, eng, logdir):
     """mpstat.txt (:482-546), nvsmi_query.txt (:1013-1084), netstat.txt (:1235-1337): rows, CSV text and
     report.js records are produced on the device; this function only names the files."""
@@ -250,6 +275,7 @@ def _preprocess(cfg, eng):
 
     side = _side_sources(cfg, eng, logdir)
     net_series = SeriesOut('net_trace', 'NET', 'blue')
+    net_filter_series = []
     gpu_series = SeriesOut('gpu_kernel_trace', 'GPU kernel', 'rgba(0,180,0,0.8)')
     gpu_filter_series = []
     cpu_series = []
@@ -263,8 +289,6 @@ def _preprocess(cfg, eng):
         text = _read_bytes(logdir + 'net.tmp')
         print_info(cfg, "Length of net_traces = %d" % text.count(b'\n'))
         if len(text) > 0:
-            if getattr(cfg, 'net_filters', None):
-                raise NotImplementedError("network_filters series are not implemented")
             p = hl.base_params(SRC_NET, cfg.time_base, cfg.absolute_timestamp, 0.0)
             eng.load(SRC_NET, text, p)
             body = eng.csv(SRC_NET, ratio)
@@ -272,6 +296,8 @@ def _preprocess(cfg, eng):
                 f.write(CSV_HEADER)
                 f.write(memoryview(body))
             net_series.records, net_series.nrec = eng.json(SRC_NET, ratio, -1)
+            if getattr(cfg, 'net_filters', None):
+                net_filter_series = _net_filter_series(cfg, eng, ratio)
     else:
         print_warning(cfg, "no network traces were recorded.")
 
@@ -406,6 +432,7 @@ def _preprocess(cfg, eng):
         series.append(SeriesOut('nvsmi_enc', 'GPU_ENC_Util.', 'rgba(255, 215, 0, 0.8)', *side.get('nvsmi_enc', (None, 0))))
         series.append(SeriesOut('nvsmi_dec', 'GPU_DEC_Util.', 'rgba(218, 165, 32, 0.8)', *side.get('nvsmi_dec', (None, 0))))
     series.append(net_series)
+    series.extend(net_filter_series)                             # :2046-2055
     series.append(SeriesOut('tx_bandwidth', 'tx Bandwidth', 'rgba(135,206,250,0.8)', *side.get('tx_bandwidth', (None, 0))))
     series.append(SeriesOut('rx_bandwidth', 'rx Bandwidth', 'rgba(25,25,112,0.8)', *side.get('rx_bandwidth', (None, 0))))
     series.append(gpu_series)

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load_lib()
     missing = [n for n in declared_functions() if not hasattr(lib, n)]
     assert missing == []
-    assert lib.sofa_b200_abi_version() == 1
+    assert lib.sofa_b200_abi_version() == 2
 
 
 def test_ctypes_binding_covers_the_header():

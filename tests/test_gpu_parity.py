@@ -652,3 +652,87 @@ def test_config2_slice_two_million_gpu_events(tmp_path):
     files = _full_pass_parity(tmp_path, seed=20260921 + 2, n_perf=100000, n_gpu=2000000, n_net=100000)
     for fn in ("gputrace.csv", "comm.csv", "nettrace.csv", "netrank.csv"):
         assert fn in files
+
+
+# ---------------------------------------------------------------------------- the whole analyze driver vs the reference
+DRIVER_CASES = sorted(d for d in os.listdir(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")) if d.startswith("driver_"))
+
+
+@pytest.mark.parametrize("name", DRIVER_CASES)
+@pytest.mark.parametrize("variant", ["plain", "verbose"])
+def test_analyze_driver_stdout_matches_reference(name, variant, tmp_path, capsys):
+    """sofa_preprocess + sofa_analyze on the inputs of tests/golden/driver_*: the whole stdout of the analyze driver
+    (feature table; with --verbose every profile function's tables) and netrank.csv / performance.csv / comm.csv equal
+    the unmodified reference driver's (tests/golden/make_golden_driver.py), byte for byte."""
+    import json
+    import shutil
+    from sofa_b200.sofa_analyze import sofa_analyze
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    meta = json.load(open(os.path.join(gdir, "case.json")))
+    a = os.path.join(str(tmp_path), "sofalog") + "/"
+    os.makedirs(a)
+    for fn in os.listdir(gdir):
+        if fn.endswith(".txt") and not fn.startswith("analyze_") or fn.endswith((".tmp", ".script")):
+            shutil.copy(os.path.join(gdir, fn), a + fn)
+    if os.path.isfile(a + "gputrace.tmp"):
+        open(a + "gputrace1.nvvp", "w").close()
+    if os.path.isfile(a + "net.tmp"):
+        open(a + "sofa.pcap", "w").close()
+    ov = dict(meta["cfg"])
+    cfg = default_report_config(a, cpu_filters=ov.pop("cpu_filters", None))
+    for k, v in ov.items():
+        setattr(cfg, k, v)
+    sofa_preprocess(cfg)
+    capsys.readouterr()
+    cfg.verbose = variant == "verbose"
+    sofa_analyze(cfg)
+    got = capsys.readouterr().out.replace(a, "LOGDIR/").replace(a.rstrip("/"), "LOGDIR")
+    want = open(os.path.join(gdir, "analyze_%s.txt" % variant)).read()
+    assert cfg.roi_begin == meta["variants"][variant]["roi_begin"] and cfg.roi_end == meta["variants"][variant]["roi_end"]
+    if got != want:
+        gl, wl = got.split("\n"), want.split("\n")
+        for i, (x, y) in enumerate(zip(gl, wl)):
+            assert x == y, "line %d:\n got %r\nwant %r" % (i + 1, x[:300], y[:300])
+        assert len(gl) == len(wl), (len(gl), len(wl), gl[-3:], wl[-3:])
+    for fn in ("netrank.csv", "performance.csv", "comm.csv"):
+        if os.path.isfile(os.path.join(gdir, fn)):
+            _diff(name, fn, open(a + fn, "rb").read(), open(os.path.join(gdir, fn), "rb").read())
+
+
+def test_network_filters_series(tmp_path):
+    """--network_filters (sofa_preprocess.py:1214-1231): to_/from_ series of the node of interest vs the oracle's frame
+    selection; the colours are random in the reference and are not compared."""
+    import json
+    import re
+    import pandas as pd
+    a = os.path.join(str(tmp_path), "l") + "/"
+    synth.make_logdir(a, seed=909, n_net=4000, non_ip_pct=2)
+    cfg = default_report_config(a)
+    cfg.plot_ratio = 2
+    df0 = None
+    cfg.net_filters = []
+    sofa_preprocess(cfg)
+    df = pd.read_csv(a + "nettrace.csv")
+    top = df.groupby(['pkt_src', 'pkt_dst']).size().sort_values(ascending=False).index[:6].tolist()
+    node = int(top[0][0])
+    peers = [int(d) for s, d in top if int(s) == node][:2] + [int(s) for s, d in top if int(d) == node][:2] + [123456789012]
+    peers = list(dict.fromkeys(peers))
+    cfg.net_filters = [str(node)] + [str(p) for p in peers]
+    sofa_preprocess(cfg)
+    js = open(a + "report.js").read()
+    names = re.findall(r"^(\w+) = ", js, flags=re.M)
+    for direction in ("to_", "from_"):
+        for p in peers:
+            nm = "%s%d" % (direction, p)
+            sel = df[(df['payload'] > 0) & ((df['pkt_src'] == float(node)) & (df['pkt_dst'] == float(p)) if direction == "to_"
+                                            else (df['pkt_dst'] == float(node)) & (df['pkt_src'] == float(p)))]
+            if len(sel) == 0:
+                assert nm not in names
+                continue
+            m = re.search(r"^%s = (\{.*\})$" % nm, js, flags=re.M)
+            assert m, nm
+            data = json.loads(m.group(1))
+            assert data["name"] == "[keyword]" + nm
+            want = json.loads(sel.rename(columns={'timestamp': 'x', 'duration': 'y'}).to_json(orient='records'))
+            assert data["data"] == want, nm
+    assert js.rstrip().endswith("]") and ("to_%d," % peers[0]) in js.split("sofa_traces = [ ")[1]
