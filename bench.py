@@ -415,6 +415,9 @@ def run_ours(args):
     barrier()
     nb = wl.out_bytes
 
+    strong = None
+    if dist is not None and args.strong:
+        strong = run_strong(args, eng, dist, rank, world, local_rank, dev_ms / args.steps, barrier, max_over_ranks)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -469,6 +472,7 @@ def run_ours(args):
                      "peak_source": peak_src,
                      "all_kernels_ms": {k: round(v[1], 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][1])},
                      "whole_step_algorithmic_GBps": (text_total + out_bytes["csv"] + out_bytes["json"]) / (ms_step * 1e-3) / 1e9},
+        "strong": strong,
         "cpu_baseline": cpu,
         "parity_sample": (cpu or {}).get("parity_sample"),
         "parity_windows": ({"result": "identical", "windows": windows} if windows is not None else None),
@@ -476,6 +480,113 @@ def run_ours(args):
     }
     print(json.dumps(line))
     eng.close()
+
+
+# --------------------------------------------------------------------------- strong scaling: one trace over all ranks
+def run_strong(args, eng, dist, rank, world, local_rank, weak_ms, barrier, max_over_ranks):
+    """ONE logical trace of --events events (BASELINE configs[2] mix; configs[3] is the same at 500 M) split over the
+    ranks as newline-aligned row ranges of every source.  Per step and rank: parse + CSV + every report.js series of its
+    shard; dtype flags all-reduced (NCCL) before formatting; then the parsed gpu and packet shards are gathered on rank 0
+    over NCCL (send/recv of text + columns straight into place) where gpu_profile / comm_profile / net_profile run over
+    the whole columns (their sums follow numpy's pairwise order over ALL rows).  Side files and their analysis stay on
+    rank 0.  Reported: ms per step (max over ranks), events/s, time inside the collectives, speed-up over the same
+    trace on one GPU (the weak arm's per-GPU step)."""
+    import torch
+    from sofa_b200 import hostlogic as hl
+    from sofa_b200 import sharded
+    from sofa_b200.sofa_preprocess import demangle
+    device = torch.device("cuda", local_rank)
+    n = split_events(args.events)
+    io = sharded.ShardIO(rank, world, dist, device)
+    params, cache = {}, {}
+    eng.set_output_arena(0)
+    # header parameters of the nvprof text: every rank needs the first record's Start
+    eng.synth_range(hl.SRC_GPU, SEED, 0, 1, 0, True)
+    head = eng.text_fetch(hl.SRC_GPU, 4096)[:4096].tobytes()
+    upd, off = hl.gpu_header(head + b"\n")
+    p = hl.base_params(hl.SRC_GPU, TIME_BASE, False, 0 - upd.pop('t_base'))
+    p.update(upd)
+    keep = []
+    params[hl.SRC_GPU] = eng.make_params(p); keep.append(eng._keep)
+    params[hl.SRC_PERF] = eng.make_params(hl.base_params(hl.SRC_PERF, TIME_BASE, False, PERF_T_OFFSET)); keep.append(eng._keep)
+    params[hl.SRC_NET] = eng.make_params(hl.base_params(hl.SRC_NET, TIME_BASE, False, 0.0)); keep.append(eng._keep)
+    shard_rows = {}
+    for kind, total, variant in ((hl.SRC_PERF, n[0], 0), (hl.SRC_GPU, n[1], 0), (hl.SRC_NET, n[2], 1)):
+        r0, r1 = total * rank // world, total * (rank + 1) // world
+        shard_rows[kind] = (r0, r1)
+
+    def regen(kind):
+        r0, r1 = shard_rows[kind]
+        eng.synth_range(kind, SEED, r0, r1 - r0, 0 if kind != hl.SRC_NET else 1, rank == 0)
+
+    def dm(names):
+        out = []
+        for m in names:
+            d = cache.get(m)
+            if d is None:
+                d = cache[m] = demangle(m)
+            out.append((m, d))
+        return out
+    coll = {"ms": 0.0, "bytes": 0}
+
+    def timed(fn):
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize(device)
+        coll["ms"] += (time.perf_counter() - t0) * 1e3
+        return r
+
+    def step():
+        for kind in (hl.SRC_NET, hl.SRC_GPU, hl.SRC_PERF):
+            eng.parse(kind, params[kind])
+            if kind != hl.SRC_PERF:
+                timed(lambda: io.sync_flags(eng, kind, 1))
+            eng.csv_device(kind, 1)
+            if kind == hl.SRC_NET:
+                eng.json_device(kind, 1, -1)
+            else:
+                if kind == hl.SRC_PERF:
+                    eng.set_demangled(dm(eng.viz_mangled(1)))
+                kws = GPU_KWS if kind == hl.SRC_GPU else CPU_KWS
+                eng.json_series_device(kind, 1, kws)
+                for i in range(len(kws)):
+                    eng.json_device(kind, 1, i)
+        for kind in (hl.SRC_GPU, hl.SRC_NET):
+            coll["bytes"] += timed(lambda: sharded.gather_source(eng, kind, dist, device, 0))
+        if rank == 0:
+            eng.gpu_profile()
+            eng.net_profile(1)
+
+    def restore():          # (untimed) the gathered state replaced rank 0's shard: put the shard's text back for the next step
+        if rank == 0:
+            for kind in (hl.SRC_GPU, hl.SRC_NET):
+                regen(kind)
+
+    for kind in (hl.SRC_PERF, hl.SRC_GPU, hl.SRC_NET):
+        regen(kind)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+        restore()
+    coll["ms"], coll["bytes"] = 0.0, 0
+    total_ms = 0.0
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        step()
+        torch.cuda.synchronize(device)
+        total_ms += max_over_ranks((time.perf_counter() - t0) * 1e3)
+        restore()
+    ms = total_ms / args.steps
+    cms = max_over_ranks(coll["ms"]) / args.steps
+    barrier()
+    return {"n_gpus": world, "events": sum(n), "ms_per_step": ms, "value": sum(n) / (ms * 1e-3), "unit": "events/s",
+            "scaling": "strong", "collective_ms_per_step": cms, "collective_share": cms / ms if ms else None,
+            "nccl_bytes_per_step_this_rank": coll["bytes"] / args.steps,
+            "one_gpu_ms_per_step": weak_ms, "speedup_vs_one_gpu": weak_ms / ms if ms else None,
+            "efficiency": weak_ms / ms / world if ms else None,
+            "note": "wall clock between device synchronisations, max over ranks, per step; side files and concurrency_breakdown are not part of this arm",
+            "collectives": "all-reduce of dtype flags (per source), all-gather of shard sizes, send/recv of parsed gpu + packet shards to rank 0"}
 
 
 # --------------------------------------------------------------------------- output windows vs the oracle at full size
@@ -760,6 +871,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=100000000, help="events per GPU (default: BASELINE configs[2])")
     ap.add_argument("--cpu-sample", type=int, default=150000, help="events in the CPU baseline sample")
+    ap.add_argument("--strong", type=int, default=1,
+                    help="1 (with --gpus > 1): also time ONE trace of --events events sharded over all GPUs (strong scaling, NCCL on the data path)")
     ap.add_argument("--numa-bind", type=int, default=1, help="1: bind every rank (CPUs + pinned arenas) to its GPU's NUMA node")
     ap.add_argument("--verify-windows", type=int, default=1,
                     help="1: byte-compare first / 4 GiB-straddling / last windows of every CSV and main JSON output with the oracle")

@@ -266,6 +266,29 @@ int sofa_b200_elapsed_ms(sofa_ctx*, double* ms);
 int sofa_b200_fetch_range(sofa_ctx*, int which, uint64_t off, uint64_t nbytes, void* host_out);
 int sofa_b200_emit_block_end(sofa_ctx*, uint64_t block, uint64_t* end_bytes);
 
+/* One logical trace sharded over several contexts / GPUs (newline-aligned byte ranges, one per rank): a column's dtype
+ * (int or float text, pandas' per-file inference) is a property of the WHOLE file, so after sofa_b200_parse every rank
+ * all-reduces (bitwise OR, NCCL) the value of sofa_b200_row_flags and hands the result back with this call; all later
+ * emits of the shard format with it. */
+int sofa_b200_set_global_flags(sofa_ctx*, int src, uint32_t stride, uint32_t flags);
+
+/* Gathering the parsed shards of one source on one rank (sofa_analyze runs there): device pointers and sizes of a
+ * shard's text and columns (export), fresh buffers for the whole source (reserve), and the switch to them once every
+ * shard's bytes are in place (commit; the caller moves the bytes: device copies and NCCL send/recv between ranks).
+ * cols[] order - perf: timestamp event duration pid tid line_start pieces; gpu: timestamp duration bandwidth payload
+ * deviceId tid pkt_src pkt_dst copyKind bw_is_float line_start name_off name_len; net: timestamp payload pkt_src
+ * pkt_dst proto. */
+typedef struct {
+    uint64_t n_rows, text_bytes, data_off;
+    void* text;
+    void* cols[16];
+    uint32_t col_elem[16];
+    int32_t n_cols, pad;
+} sofa_shard_t;
+int sofa_b200_shard_export(sofa_ctx*, int src, sofa_shard_t* out);
+int sofa_b200_shard_reserve(sofa_ctx*, int src, uint64_t total_rows, uint64_t total_text, sofa_shard_t* out);
+int sofa_b200_shard_commit(sofa_ctx*, int src, int32_t nshards, const uint64_t* shard_rows, const uint64_t* shard_text);
+
 /* Test hooks.  SOFA_DEBUG_NAME_HASH_MASK: the 64-bit name hashes that key get_top_k_events / nccl_time groups
  * (sofa_analyze.py:34-44, 363-368) are ANDed with `value`; a narrow mask forces collisions, which the group
  * verification pass must then report (SOFA_ERR_ROW) instead of merging two names. */
@@ -281,6 +304,9 @@ const char* sofa_b200_kernel_name(int kind);
  * sofa_b200/synth.py).  variant: perf 0/1 = without/with [cpu] column; gpu 0 = s/ms/MB,
  * 1 = ms/us/KB + P2P columns; net = percent of non-IP lines. */
 int sofa_b200_synth(sofa_ctx*, int src, uint64_t seed, uint64_t n_rows, int variant, uint64_t* nbytes);
+/* rows [row0, row0 + n_rows) of the same trace (one shard of it); the nvprof header rows only when with_header */
+int sofa_b200_synth_range(sofa_ctx*, int src, uint64_t seed, uint64_t row0, uint64_t n_rows, int variant, int with_header,
+                          uint64_t* nbytes);
 int sofa_b200_text_fetch(sofa_ctx*, int src, void* host_out, uint64_t cap);
 
 #ifdef __cplusplus

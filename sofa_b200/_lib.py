@@ -14,7 +14,7 @@ EXPORTS = [
     "sofa_b200_abi_version", "sofa_b200_last_error", "sofa_b200_error_row", "sofa_b200_create",
     "sofa_b200_destroy", "sofa_b200_host_alloc", "sofa_b200_host_free", "sofa_b200_upload",
     "sofa_b200_parse", "sofa_b200_row_flags", "sofa_b200_emit_csv", "sofa_b200_set_filters",
-    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_emit_json_series", "sofa_b200_set_debug", "sofa_b200_net_triples", "sofa_b200_set_net_filters", "sofa_b200_mpstat_profile",
+    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_emit_json_series", "sofa_b200_set_debug", "sofa_b200_synth_range", "sofa_b200_shard_export", "sofa_b200_shard_reserve", "sofa_b200_shard_commit", "sofa_b200_set_global_flags", "sofa_b200_net_triples", "sofa_b200_set_net_filters", "sofa_b200_mpstat_profile",
     "sofa_b200_side_quantiles", "sofa_b200_side_int_sums", "sofa_b200_nvsmi_roi", "sofa_b200_fetch_range", "sofa_b200_emit_block_end", "sofa_b200_fetch",
     "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
@@ -60,6 +60,12 @@ class NetPair(ctypes.Structure):
 
 class NetTriple(ctypes.Structure):
     _fields_ = [("src", ctypes.c_int64), ("dst", ctypes.c_int64), ("payload", ctypes.c_int64), ("count", ctypes.c_int64)]
+
+
+class ShardDesc(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_uint64), ("text_bytes", ctypes.c_uint64), ("data_off", ctypes.c_uint64),
+                ("text", ctypes.c_void_p), ("cols", ctypes.c_void_p * 16), ("col_elem", ctypes.c_uint32 * 16),
+                ("n_cols", ctypes.c_int32), ("pad", ctypes.c_int32)]
 
 
 class NvsmiGroup(ctypes.Structure):
@@ -119,6 +125,10 @@ def load_lib():
     lib.sofa_b200_emit_json_series.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), u64p, u64p, u64p]
     lib.sofa_b200_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
     lib.sofa_b200_set_debug.argtypes = [vp, ctypes.c_int, ctypes.c_uint64]
+    lib.sofa_b200_shard_export.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ShardDesc)]
+    lib.sofa_b200_shard_reserve.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ShardDesc)]
+    lib.sofa_b200_shard_commit.argtypes = [vp, ctypes.c_int, ctypes.c_int32, u64p, u64p]
+    lib.sofa_b200_set_global_flags.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]
     dp = ctypes.POINTER(ctypes.c_double)
     i64p = ctypes.POINTER(ctypes.c_int64)
     lib.sofa_b200_net_triples.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(NetTriple), ctypes.c_uint32, u32p]
@@ -157,6 +167,7 @@ def load_lib():
     lib.sofa_b200_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.sofa_b200_reset_stats.argtypes = [vp]
     lib.sofa_b200_synth.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, u64p]
+    lib.sofa_b200_synth_range.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, u64p]
     lib.sofa_b200_text_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
     if lib.sofa_b200_abi_version() != 2:
         raise ImportError("libsofa_b200.so ABI version mismatch")

@@ -81,11 +81,13 @@ struct sofa_ctx {
     std::vector<SmallXfer> pending;
     char* out_ptr[3] = {nullptr, nullptr, nullptr};
     DevBuf tiles, rowlen, blockoff, scratch, ftable, keys, rows;
+    DevBuf gather[17];                   // rank 0 of a sharded trace: text + columns being gathered (sofa_b200_shard_reserve)
     DevBuf sk0, sv0, sk1, sv1, hist, segs, sums, small, scanpart;
     void* pin_h = nullptr; size_t pin_cap = 0;  // pinned host scratch for larger read-backs (grown on demand)
     unsigned long long* d_err = nullptr;        // [0] error slot, [1] counter, [2..9] filter counts, [10] misc
     unsigned int* d_flags = nullptr;            // [0] cr flag, [1] row flags, [2] overflow, [3] count
     uint64_t err_row = 0; int err_code = 0;
+    int sm_count = 148;                  // multiprocessors of the device (persistent grids)
     uint64_t debug_hash_mask = ~0ull;    // name-group hashes are ANDed with this (tests force collisions with a narrow mask)
     bool profiling = false;
     cudaEvent_t mark[2] = {nullptr, nullptr};
@@ -336,6 +338,10 @@ int sofa_emit_fused(sofa_ctx* c, int fmt, int k, uint32_t stride, const uint8_t*
 void launch_parse(int tpl_kind, unsigned grid, size_t smem, cudaStream_t st, const char* text, uint64_t begin, uint64_t end,
                   uint32_t tile_bytes, uint32_t max_lines, const uint64_t* tile_row_base, const sofa::IngestCfg& cfg,
                   const sofa::AllCols& cols, unsigned long long* err);
+int parse_tma_occupancy(int kind, size_t smem);
+void launch_parse_tma(int kind, unsigned grid, size_t smem, cudaStream_t st, const char* text, uint64_t begin, uint64_t end,
+                      uint32_t tile_bytes, uint32_t max_lines, uint64_t ntiles, const uint64_t* tile_row_base, const sofa::IngestCfg& cfg,
+                      const sofa::AllCols& cols, unsigned long long* err);
 void launch_count_lines(unsigned grid, cudaStream_t st, const char* text, uint64_t begin, uint64_t end, uint32_t tile_bytes,
                         uint64_t* tile_counts, unsigned int* cr_flag);
 void launch_emit(int kind, int fmt, unsigned grid, size_t smem, cudaStream_t st, const sofa::SrcView& v, const sofa::FusedArgs& a);

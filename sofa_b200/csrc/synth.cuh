@@ -199,17 +199,17 @@ template <class K> SOFA_HD void synth_line(K& k, int src, uint64_t seed, uint64_
 }
 
 #if defined(__CUDACC__)
-__global__ void __launch_bounds__(EMIT_TPB) k_synth_size(int src, uint64_t seed, uint64_t n, int variant, uint32_t* rowlen,
+__global__ void __launch_bounds__(EMIT_TPB) k_synth_size(int src, uint64_t seed, uint64_t row0, uint64_t n, int variant, uint32_t* rowlen,
                                                          uint64_t* blockoff) {
     __shared__ uint32_t sm[33];
     uint64_t i = (uint64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
     uint32_t len = 0;
-    if (i < n) { LenSink l; synth_line(l, src, seed, i, variant); len = (uint32_t)l.len; rowlen[i] = len; }
+    if (i < n) { LenSink l; synth_line(l, src, seed, row0 + i, variant); len = (uint32_t)l.len; rowlen[i] = len; }
     uint32_t total;
     block_excl_scan(len, &total, sm);
     if (threadIdx.x == 0) blockoff[blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(EMIT_TPB) k_synth_write(int src, uint64_t seed, uint64_t n, int variant, const uint32_t* rowlen,
+__global__ void __launch_bounds__(EMIT_TPB) k_synth_write(int src, uint64_t seed, uint64_t row0, uint64_t n, int variant, const uint32_t* rowlen,
                                                           const uint64_t* blockoff, char* out, uint64_t base) {
     __shared__ __align__(16) unsigned char stage[EMIT_STAGE_BYTES + 32];
     __shared__ uint32_t sm[33];
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(EMIT_TPB) k_synth_write(int src, uint64_t seed
     if (len) {
         char* dst = staged ? reinterpret_cast<char*>(stage) + (tile_off & 15) + ex : out + tile_off + ex;
         RawWrite<char*> w{dst, 0};
-        synth_line(w, src, seed, i, variant);
+        synth_line(w, src, seed, row0 + i, variant);
     }
     __syncthreads();
     if (staged && total) flush_staged(stage, out, tile_off, total);

@@ -1,6 +1,7 @@
 // libsofa_b200.so, translation unit 1: context lifecycle, transfers, line index + parse driver, dtype flags,
 // statistics.  The kernels live in inst/*.cu (one instantiation per file, compiled in parallel).
 #include "ctx.cuh"
+#include "kernels_ingest_tma.cuh"
 
 thread_local std::string g_last_error;
 static const char* KERNEL_NAMES[K_NKINDS] = {
@@ -48,6 +49,7 @@ int sofa_b200_create(sofa_ctx** out, int device) {
     CK(cudaHostGetDevicePointer((void**)&c->stage_d, c->stage_h, 0));
     CK(cudaMalloc(&c->d_err, 8 * 16));
     CK(cudaMalloc(&c->d_flags, 4 * 8));
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     { int e_attr = set_kernel_attrs(); if (e_attr) { g_last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)e_attr); return SOFA_ERR_CUDA; } }
     *out = c;
     return 0;
@@ -70,6 +72,7 @@ int sofa_b200_destroy(sofa_ctx* c) {
         s.text.release(); s.mhz.release(); s.mask.release(); s.vizhash.release(); s.viz_id.release();
         s.dict_hash.release(); s.dict_off.release(); s.dict_blob.release();
         s.json_main.release(); s.rec_off.release();
+        for (auto& g : c->gather) g.release();
         for (auto& b : s.cols) b.release();
         if (k < 3) c->out[k].release();
     }
@@ -165,8 +168,20 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     size_t smem = (((size_t)tile + OVERLAP_BYTES + 48) & ~(size_t)15) + (size_t)max_lines * 4;
     AllCols cols = all_cols(c, (k >= 3 && k < 6) ? k : 3, k >= 6 ? k : 6);
     const int tpl = k >= 6 ? SRC_RAW : (k >= 3 ? SRC_SIDE : k);
-    LAUNCH(c, K_PARSE, launch_parse(tpl, (unsigned)ntiles, smem, c->stream, s.text.as<char>(), begin, end, tile, max_lines,
-                                    c->tiles.as<uint64_t>(), cfg, cols, c->d_err));
+    static const bool use_tma = !(getenv("SOFA_B200_PARSE_TMA") && atoi(getenv("SOFA_B200_PARSE_TMA")) == 0);
+    if (k <= 2 && use_tma) {
+        // trace sources: persistent blocks, two tile buffers filled by cp.async.bulk (kernels_ingest_tma.cuh)
+        const size_t buf = ((size_t)tile + TMA_OVERLAP_STAGED + TMA_STAGE_PAD + 127) & ~(size_t)127;
+        const size_t smem_tma = 2 * buf + (size_t)max_lines * 2 + 16;
+        const int occ = parse_tma_occupancy(k, smem_tma);
+        const uint64_t resident = (uint64_t)c->sm_count * (uint64_t)occ;
+        const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);
+        LAUNCH(c, K_PARSE, launch_parse_tma(k, grid, smem_tma, c->stream, s.text.as<char>(), begin, end, tile, max_lines, ntiles,
+                                            c->tiles.as<uint64_t>(), cfg, cols, c->d_err));
+    } else {
+        LAUNCH(c, K_PARSE, launch_parse(tpl, (unsigned)ntiles, smem, c->stream, s.text.as<char>(), begin, end, tile, max_lines,
+                                        c->tiles.as<uint64_t>(), cfg, cols, c->d_err));
+    }
     int r = check_kernel_error(c, "parse");
     if (r) return r;
     s.parsed = true;
@@ -180,8 +195,9 @@ int sofa_b200_row_flags(sofa_ctx* c, int k, uint32_t stride, uint32_t* flags) {
     if (stride == 0 || !flags) FAIL(SOFA_ERR_ARG, "row_flags: bad argument");
     Source& s = c->src[k];
     *flags = 0;
-    if (k == SRC_PERF || s.n_rows == 0) return 0;
+    if (k == SRC_PERF) return 0;
     for (int i = 0; i < 2; i++) if (s.flags_stride[i] == stride) { *flags = s.flags_val[i]; return 0; }
+    if (s.n_rows == 0) return 0;
     uint64_t ncand = cdiv(s.n_rows, stride);
     CK(cudaMemsetAsync(c->d_flags + 1, 0, 4, c->stream));
     SrcView v = make_view(c, k, false);
@@ -373,6 +389,102 @@ int sofa_b200_text_fetch(sofa_ctx* c, int k, void* host_out, uint64_t cap) {
     if (cap < s.nbytes) FAIL(SOFA_ERR_CAP, "text_fetch: buffer too small");
     CK(cudaSetDevice(c->device));
     if (s.nbytes) { CK(cudaMemcpyAsync(host_out, s.text.p, s.nbytes, cudaMemcpyDeviceToHost, c->stream)); CK_S(stream_sync(c)); }
+    return 0;
+}
+
+static __global__ void k_add_u64(uint64_t* a, uint64_t n, uint64_t delta) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += delta;
+}
+// (slot, element bytes) of the parsed columns of a trace source, in a fixed order
+static int shard_layout(int k, int* slots, uint32_t* elem) {
+    if (k == SRC_PERF) {
+        const int s[] = {PC_TS, PC_EVENT, PC_DUR, PC_PID, PC_TID, PC_LS, PC_PIECES}; const uint32_t e[] = {8, 8, 8, 4, 4, 8, 16};
+        for (int i = 0; i < 7; i++) { slots[i] = s[i]; elem[i] = e[i]; }
+        return 7;
+    }
+    if (k == SRC_GPU) {
+        const int s[] = {GC_TS, GC_DUR, GC_BW, GC_PAYLOAD, GC_DEV, GC_TID, GC_SRC, GC_DST, GC_KIND, GC_BWF, GC_LS, GC_NOFF, GC_NLEN};
+        const uint32_t e[] = {8, 8, 8, 8, 4, 4, 4, 4, 1, 1, 8, 2, 2};
+        for (int i = 0; i < 13; i++) { slots[i] = s[i]; elem[i] = e[i]; }
+        return 13;
+    }
+    const int s[] = {NC_TS, NC_PAYLOAD, NC_SRC, NC_DST, NC_PROTO}; const uint32_t e[] = {8, 8, 8, 8, 1};
+    for (int i = 0; i < 5; i++) { slots[i] = s[i]; elem[i] = e[i]; }
+    return 5;
+}
+
+int sofa_b200_shard_export(sofa_ctx* c, int k, sofa_shard_t* out) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (!out) FAIL(SOFA_ERR_ARG, "shard_export: null out");
+    CK_S(stream_sync(c));
+    Source& s = c->src[k];
+    memset(out, 0, sizeof *out);
+    int slots[16]; uint32_t elem[16];
+    out->n_cols = shard_layout(k, slots, elem);
+    out->n_rows = s.n_rows; out->text_bytes = s.nbytes; out->data_off = s.data_off; out->text = s.text.p;
+    for (int i = 0; i < out->n_cols; i++) { out->cols[i] = s.cols[slots[i]].p; out->col_elem[i] = elem[i]; }
+    return 0;
+}
+
+/* rank 0 of a sharded trace: fresh buffers for `total_rows` rows and `total_text` text bytes of source k (the shard it
+ * parsed itself stays valid until sofa_b200_shard_commit); the caller fills them shard by shard (its own shard with a
+ * device copy, the others with NCCL receives straight into place) and commits. */
+int sofa_b200_shard_reserve(sofa_ctx* c, int k, uint64_t total_rows, uint64_t total_text, sofa_shard_t* out) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (!out) FAIL(SOFA_ERR_ARG, "shard_reserve: null out");
+    CK_S(stream_sync(c));
+    memset(out, 0, sizeof *out);
+    int slots[16]; uint32_t elem[16];
+    out->n_cols = shard_layout(k, slots, elem);
+    for (int i = 0; i <= out->n_cols; i++) c->gather[i].release();
+    uint64_t m = total_rows ? total_rows : 1;
+    ENSURE(c->gather[0], total_text + 64);
+    for (int i = 0; i < out->n_cols; i++) ENSURE(c->gather[1 + i], m * elem[i] + 64);
+    out->n_rows = total_rows; out->text_bytes = total_text; out->text = c->gather[0].p;
+    for (int i = 0; i < out->n_cols; i++) { out->cols[i] = c->gather[1 + i].p; out->col_elem[i] = elem[i]; }
+    return 0;
+}
+
+/* shard_rows[i] / shard_text[i]: rows and text bytes of shard i as laid out in the reserved buffers, in rank order.
+ * The row -> line offsets of shard i are rebased onto its position in the gathered text; the gathered buffers become
+ * the source's parsed state (as if one context had parsed the whole file). */
+int sofa_b200_shard_commit(sofa_ctx* c, int k, int32_t nshards, const uint64_t* shard_rows, const uint64_t* shard_text) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (nshards < 1 || !shard_rows || !shard_text) FAIL(SOFA_ERR_ARG, "shard_commit: bad argument");
+    Source& s = c->src[k];
+    int slots[16]; uint32_t elem[16];
+    int nc = shard_layout(k, slots, elem);
+    uint64_t rows = 0, text = 0;
+    int ls_slot = k == SRC_PERF ? PC_LS : (k == SRC_GPU ? GC_LS : -1);
+    for (int i = 0; i < nshards; i++) {
+        if (ls_slot >= 0 && text && shard_rows[i]) {
+            int gi = 0;
+            for (int q = 0; q < nc; q++) if (slots[q] == ls_slot) gi = 1 + q;
+            uint64_t* ls = c->gather[gi].as<uint64_t>() + rows;
+            k_add_u64<<<(unsigned)cdiv(shard_rows[i], 256), 256, 0, c->stream>>>(ls, shard_rows[i], text);
+        }
+        rows += shard_rows[i]; text += shard_text[i];
+    }
+    CK(cudaMemsetAsync(c->gather[0].as<char>() + text, '\n', 64, c->stream));
+    CK_S(stream_sync(c));
+    CK(cudaGetLastError());
+    std::swap(s.text, c->gather[0]);
+    for (int q = 0; q < nc; q++) std::swap(s.cols[slots[q]], c->gather[1 + q]);
+    for (int i = 0; i <= nc; i++) c->gather[i].release();
+    s.n_rows = rows; s.nbytes = text; s.data_off = 0; s.parsed = true; s.viz_ready = false; s.mask_stride = 0; s.nkw = 0; s.gather_ok = false;
+    return 0;
+}
+
+/* one logical trace split over several contexts (ranks): the dtype flags of a column are a property of the whole
+ * file, so every shard formats with the OR of all shards' flags */
+int sofa_b200_set_global_flags(sofa_ctx* c, int k, uint32_t stride, uint32_t flags) {
+    int r = need_parsed(c, k); if (r) return r;
+    if (stride == 0) FAIL(SOFA_ERR_ARG, "set_global_flags: stride must be >= 1");
+    Source& s = c->src[k];
+    int slot = (s.flags_stride[0] == stride || s.flags_stride[0] == 0) ? 0 : 1;
+    s.flags_stride[slot] = stride; s.flags_val[slot] = flags;
+    if (s.n_rows == 0) { s.flags_stride[slot] = stride; }
     return 0;
 }
 

@@ -127,6 +127,27 @@ class CudaEngine:
         self._check(self.lib.sofa_b200_row_flags(self.ctx, kind, stride, ctypes.byref(f)))
         return f.value
 
+    # ---- sharded traces: the parsed state of a source as raw device memory
+    def shard_export(self, kind):
+        d = L.ShardDesc()
+        self._check(self.lib.sofa_b200_shard_export(self.ctx, kind, ctypes.byref(d)))
+        return d
+
+    def shard_reserve(self, kind, total_rows, total_text):
+        d = L.ShardDesc()
+        self._check(self.lib.sofa_b200_shard_reserve(self.ctx, kind, int(total_rows), int(total_text), ctypes.byref(d)))
+        return d
+
+    def shard_commit(self, kind, rows, text_bytes):
+        n = len(rows)
+        a = (ctypes.c_uint64 * n)(*rows)
+        b = (ctypes.c_uint64 * n)(*text_bytes)
+        self._check(self.lib.sofa_b200_shard_commit(self.ctx, kind, n, a, b))
+
+    def set_global_flags(self, kind, stride, flags):
+        """sharded traces: the OR over all shards of row_flags (column dtypes are a property of the whole file)"""
+        self._check(self.lib.sofa_b200_set_global_flags(self.ctx, kind, stride, int(flags)))
+
     # ---- outputs
     def _fetch(self, which, n, out=None):
         if out is None:
@@ -400,6 +421,12 @@ class CudaEngine:
     def synth(self, kind, seed, n_rows, variant=0):
         n = ctypes.c_uint64()
         self._check(self.lib.sofa_b200_synth(self.ctx, kind, seed, n_rows, variant, ctypes.byref(n)))
+        return n.value
+
+    def synth_range(self, kind, seed, row0, n_rows, variant=0, with_header=True):
+        n = ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_synth_range(self.ctx, kind, seed, int(row0), int(n_rows), variant, 1 if with_header else 0,
+                                                   ctypes.byref(n)))
         return n.value
 
     def text_fetch(self, kind, nbytes, out=None):

@@ -227,14 +227,45 @@ def _side_sources(cfg, eng, logdir):
     return out
 
 
-def sofa_preprocess(cfg, engine=None):
+class PlainIO:
+    """File access of an unsharded run.  sofa_b200.sharded.ShardIO has the same interface for one logical trace split
+    over several ranks (byte ranges in, part files out, dtype flags all-reduced)."""
+    rank, world = 0, 1
+
+    def head(self, path, n):
+        with open(path, 'rb') as f:
+            return f.read(n)
+
+    def read(self, path, data_off=0):
+        """(text of this rank's rows incl. the header on rank 0, offset of the first row in it)"""
+        return _read_bytes(path), data_off
+
+    def size(self, path):
+        return os.path.getsize(path)
+
+    def sync_flags(self, eng, kind, stride):
+        pass
+
+    def write_csv(self, path, header, body):
+        with open(path, 'wb') as f:
+            f.write(header)
+            f.write(memoryview(body))
+
+    def series(self, s):
+        return s
+
+    def finish(self, series, path):
+        write_report_js(series, path)
+
+
+def sofa_preprocess(cfg, engine=None, io=None):
     print_main_progress('SOFA preprocessing...')
     own_engine = engine is None
     if own_engine:
         from .engine import CudaEngine
         engine = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
     try:
-        return _preprocess(cfg, engine)
+        return _preprocess(cfg, engine, io or PlainIO())
     finally:
         if own_engine:
             if getattr(cfg, 'keep_engine', False):
@@ -243,7 +274,7 @@ def sofa_preprocess(cfg, engine=None):
                 engine.close()
 
 
-def _preprocess(cfg, eng):
+def _preprocess(cfg, eng, io):
     cfg.time_base = 0
     logdir = cfg.logdir
     with open(logdir + 'misc.txt', 'r') as f:
@@ -273,7 +304,9 @@ def _preprocess(cfg, eng):
     if ratio < 1:
         raise PreprocessError("plot_ratio must be >= 1")
 
-    side = _side_sources(cfg, eng, logdir)
+    if io.world > 1 and ratio != 1:
+        raise NotImplementedError("a trace sharded over several GPUs needs plot_ratio 1 (the down-sampling phase of a shard is not carried yet)")
+    side = _side_sources(cfg, eng, logdir) if io.rank == 0 else {}
     net_series = SeriesOut('net_trace', 'NET', 'blue')
     net_filter_series = []
     gpu_series = SeriesOut('gpu_kernel_trace', 'GPU kernel', 'rgba(0,180,0,0.8)')
@@ -286,15 +319,14 @@ def _preprocess(cfg, eng):
             with open(logdir + 'net.tmp', 'w') as f:
                 subprocess.check_call(["tcpdump", "-q", "-n", "-tt", "-r", "%s/sofa.pcap" % logdir],
                                       stdout=f, stderr=subprocess.DEVNULL)
-        text = _read_bytes(logdir + 'net.tmp')
+        text, _ = io.read(logdir + 'net.tmp')
         print_info(cfg, "Length of net_traces = %d" % text.count(b'\n'))
-        if len(text) > 0:
+        if io.size(logdir + 'net.tmp') > 0:
             p = hl.base_params(SRC_NET, cfg.time_base, cfg.absolute_timestamp, 0.0)
             eng.load(SRC_NET, text, p)
+            io.sync_flags(eng, SRC_NET, ratio)
             body = eng.csv(SRC_NET, ratio)
-            with open(logdir + 'nettrace.csv', 'wb') as f:
-                f.write(CSV_HEADER)
-                f.write(memoryview(body))
+            io.write_csv(logdir + 'nettrace.csv', CSV_HEADER, body)
             net_series.records, net_series.nrec = eng.json(SRC_NET, ratio, -1)
             if getattr(cfg, 'net_filters', None):
                 net_filter_series = _net_filter_series(cfg, eng, ratio)
@@ -314,21 +346,21 @@ def _preprocess(cfg, eng):
         t_glb_gpu_base = gpu_first_timestamp(nvvp)
         print_info(cfg, "Timestamp of the first GPU trace = " + str(t_glb_gpu_base))
         print_progress(cfg, "Read " + nvvp + " by nvprof -- end")
-        text = _read_bytes(logdir + 'gputrace.tmp')
-        hdr = hl.gpu_header(text[:1 << 16]) if len(text) > 0 else None
+        head = io.head(logdir + 'gputrace.tmp', 1 << 16)
+        hdr = hl.gpu_header(head) if len(head) > 0 else None
         if hdr is None:
             print_warning(cfg, "gputrace existed, but no kernel traces were recorded.")
             continue
         upd, data_off = hdr
+        text, data_off = io.read(logdir + 'gputrace.tmp', data_off)
         p = hl.base_params(SRC_GPU, cfg.time_base, cfg.absolute_timestamp, t_glb_gpu_base - upd.pop('t_base'))
         p.update(upd)
         p['n_cudaproc'] = 1
         n_rows, _ = eng.load(SRC_GPU, text, p, data_off)
         print_info(cfg, "Length of gpu_traces = %d" % n_rows)
+        io.sync_flags(eng, SRC_GPU, 1)
         body = eng.csv(SRC_GPU, 1)
-        with open(logdir + 'gputrace.csv', 'wb') as f:
-            f.write(CSV_HEADER)
-            f.write(memoryview(body))
+        io.write_csv(logdir + 'gputrace.csv', CSV_HEADER, body)
         kws = [flt.keyword for flt in cfg.gpu_filters]
         for kw in kws:
             _check_keyword(kw)
@@ -379,17 +411,15 @@ def _preprocess(cfg, eng):
     try:
         if not os.path.isfile(logdir + 'perf.script'):
             raise IOError('perf.script')
-        text = _read_bytes(logdir + 'perf.script')
+        text, _ = io.read(logdir + 'perf.script')
         print_info(cfg, "Length of cpu_traces = %d" % text.count(b'\n'))
-        if len(text) > 0:
+        if io.size(logdir + 'perf.script') > 0:
             p = hl.base_params(SRC_PERF, cfg.time_base, cfg.absolute_timestamp, t_offset)
             p['perf_has_cycles'] = 1 if cfg.perf_events.find('cycles') != -1 else 0
             p['mhz_xp'], p['mhz_fp'] = mhz_xp, mhz_fp
             eng.load(SRC_PERF, text, p)
             body = eng.csv(SRC_PERF, 1)
-            with open(logdir + 'cputrace.csv', 'wb') as f:
-                f.write(CSV_HEADER)
-                f.write(memoryview(body))
+            io.write_csv(logdir + 'cputrace.csv', CSV_HEADER, body)
             mangled = eng.viz_mangled(ratio)                  # unique _Z... viz names
             eng.set_demangled([(m, demangle(m)) for m in mangled])
             kws = [flt.keyword for flt in cfg.cpu_filters]
@@ -439,5 +469,5 @@ def _preprocess(cfg, eng):
     series.extend(gpu_filter_series)
     if api_series is not None:
         series.append(api_series)
-    write_report_js(series, logdir + 'report.js')
+    io.finish(series, logdir + 'report.js')
     print_progress(cfg, "Export Overhead Dynamics JSON File of CPU, Network and GPU traces -- end")

@@ -88,11 +88,20 @@ class HostSimEngine:
     def load(self, kind, text, params, data_off=0):
         text = bytes(text)[data_off:]
         self.src[kind] = (text, self._cfg(params))
+        for key in [k for k in getattr(self, 'gflags', {}) if k[0] == kind]:
+            del self.gflags[key]
         _, flags, n = self._run(kind, 0, 1, 0x1fff)
         return n, flags
 
+    def set_global_flags(self, kind, stride, flags):
+        if not hasattr(self, 'gflags'):
+            self.gflags = {}
+        self.gflags[(kind, stride)] = flags
+
     def _fmask(self, kind, stride):
-        _, flags, _ = self._run(kind, 0 if kind == 2 else 1, stride, 0x1fff)
+        flags = getattr(self, 'gflags', {}).get((kind, stride))
+        if flags is None:
+            _, flags, _ = self._run(kind, 0 if kind == 2 else 1, stride, 0x1fff)
         if kind == 0:
             return 0b111
         if kind == 1:

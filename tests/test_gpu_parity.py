@@ -759,3 +759,38 @@ def test_network_filters_series(tmp_path):
             assert [r["payload"] for r in data["data"]] == sel["payload"].tolist(), nm
             assert [round(r["x"], 6) for r in data["data"]] == sel["timestamp"].tolist(), nm
     assert js.rstrip().endswith("]") and ("to_%d," % peers[0]) in js.split("sofa_traces = [ ")[1]
+
+
+def test_sharded_trace_two_gpus(tmp_path):
+    """One logdir preprocessed by two ranks on two GPUs (sofa_b200.sharded: byte-range shards, NCCL all-reduce of the dtype
+    flags, ordered concat) and analysed on rank 0 after the parsed gpu / packet shards were gathered there over NCCL:
+    every file equals the single-GPU run's, and so do the analyze features.  Needs 2 GPUs (skipped otherwise)."""
+    import subprocess
+    import sys
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import shutil
+    a = os.path.join(str(tmp_path), "single") + "/"
+    b = os.path.join(str(tmp_path), "sharded") + "/"
+    synth.make_logdir(a, seed=606, n_perf=30000, n_gpu=24000, n_net=9000, non_ip_pct=1)
+    synth.write_side_raw(a, 606, n_samples=40, n_cores=4, n_gpus=2)
+    shutil.copytree(a, b)
+    from sofa_b200.sofa_analyze import sofa_analyze
+    cfg = default_report_config(a, cpu_filters="idle:black,tensorflow:orange")
+    sofa_preprocess(cfg)
+    feats = sofa_analyze(cfg)
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(str(tmp_path), "feats.json")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29600 + os.getpid() % 300), os.path.join(repo, "tests", "sharded_worker.py"), b, out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "comm.csv", "netrank.csv", "performance.csv",
+               "mpstat.csv", "nvsmi_trace.csv", "netstat.csv"):
+        _diff("sharded", fn, open(b + fn, "rb").read(), open(a + fn, "rb").read())
+    got = json.load(open(out))
+    assert [n for n, _ in feats] == [n for n, _ in got]
+    for (n, v), (_, w) in zip(feats, got):
+        assert float(v) == float(w) or (v != v and w != w), (n, v, w)

@@ -64,3 +64,78 @@ def test_two_ranks_gloo():
     port = 29500 + (os.getpid() % 400)
     with tempfile.TemporaryDirectory() as workdir:
         mp.spawn(_worker, args=(world, port, workdir), nprocs=world, join=True)
+
+
+# ---------------------------------------------------------------------------- one logical trace over two ranks
+def _shard_worker(rank, world, port, workdir):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hostsim_engine import HostSimEngine
+        from sofa_b200.sofa_config import default_report_config
+        from sofa_b200 import sharded
+        import sofa_b200.sofa_preprocess as pre
+        from helpers import demangle
+        pre.demangle = demangle
+        for case in ("mixed", "gpu_only_kernels", "net_nan_late"):
+            cfg = default_report_config(os.path.join(workdir, case, "sharded"), cpu_filters="idle:black,tensorflow:orange")
+            io = sharded.ShardIO(rank, world, dist)
+            lo, hi = io.byte_range(cfg.logdir + "perf.script") if os.path.isfile(cfg.logdir + "perf.script") else (0, 0)
+            eng = HostSimEngine()
+            pre.sofa_preprocess(cfg, engine=eng, io=io)
+            if os.path.isfile(cfg.logdir + "perf.script"):
+                off, total = io.row_offsets(open(cfg.logdir + "perf.script", "rb").read()[lo:hi].count(b"\n"))
+                assert total == open(cfg.logdir + "perf.script", "rb").read().count(b"\n")
+                assert (off == 0) == (rank == 0)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_shards_equal_one_shard_gloo():
+    """sofa_preprocess of ONE logdir by two ranks (newline-aligned byte ranges, dtype flags all-reduced, ordered concat)
+    writes byte-for-byte the files a single rank writes - including when only ONE shard holds the row that decides a
+    column's dtype (a Throughput value / a non-IP packet)."""
+    import shutil
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, HERE)
+    from hostsim_engine import HostSimEngine
+    from helpers import demangle
+    from sofa_b200 import synth
+    from sofa_b200.sofa_config import default_report_config
+    import sofa_b200.sofa_preprocess as pre
+    pre.demangle = demangle
+    world = 2
+    port = 29900 + (os.getpid() % 90)
+    with tempfile.TemporaryDirectory() as workdir:
+        for case, kw in (("mixed", dict(seed=41, n_perf=700, n_gpu=500, n_net=300, non_ip_pct=2)),
+                         ("gpu_only_kernels", dict(seed=42, n_gpu=400)),
+                         ("net_nan_late", dict(seed=43, n_net=400, non_ip_pct=0))):
+            a = os.path.join(workdir, case, "single") + "/"
+            synth.make_logdir(a, **kw)
+            if case == "gpu_only_kernels":
+                # keep exactly one memcpy row (with a Throughput) and put it into the LAST quarter: only rank 1 sees it
+                lines = open(a + "gputrace.tmp").read().splitlines(keepends=True)
+                head, rows = lines[:3], lines[3:]
+                mem = [r for r in rows if "[CUDA memcpy" in r]
+                ker = [r for r in rows if "[CUDA memcpy" not in r]
+                rows = ker[:len(ker) * 3 // 4] + mem[:1] + ker[len(ker) * 3 // 4:]
+                open(a + "gputrace.tmp", "w").write("".join(head + rows))
+            if case == "net_nan_late":
+                lines = open(a + "net.tmp").read().splitlines(keepends=True)
+                lines.insert(len(lines) - 5, "1600000001.500000 ARP, Request who-has 10.0.0.1 tell 10.0.0.2, length 28\n")
+                open(a + "net.tmp", "w").write("".join(lines))
+            shutil.copytree(a, os.path.join(workdir, case, "sharded"))
+            cfg = default_report_config(a, cpu_filters="idle:black,tensorflow:orange")
+            pre.sofa_preprocess(cfg, engine=HostSimEngine())
+        mp.spawn(_shard_worker, args=(world, port, workdir), nprocs=world, join=True)
+        for case in ("mixed", "gpu_only_kernels", "net_nan_late"):
+            a, b = os.path.join(workdir, case, "single") + "/", os.path.join(workdir, case, "sharded") + "/"
+            for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+                if os.path.isfile(a + fn):
+                    with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
+                        assert f.read() == g.read(), (case, fn)
+            assert not [f for f in os.listdir(b) if ".shard" in f]
