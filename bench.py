@@ -447,6 +447,7 @@ def run_ours(args):
     e2e_value = world * total_events / (e2e_ms / args.steps * 1e-3)
     cpu = cpu_baseline_sample(args, wl)
     windows = verify_windows(wl) if args.verify_windows else None
+    entry = entrypoints_run(wl, min(args.entry_events, total_events), local_rank) if args.entry_events > 0 else None
     line = {
         "metric": "trace events/s (preprocess+analyze)", "value": value, "unit": "events/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -472,6 +473,7 @@ def run_ours(args):
                      "peak_source": peak_src,
                      "all_kernels_ms": {k: round(v[1], 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][1])},
                      "whole_step_algorithmic_GBps": (text_total + out_bytes["csv"] + out_bytes["json"]) / (ms_step * 1e-3) / 1e9},
+        "e2e_entrypoints": entry,
         "strong": strong,
         "cpu_baseline": cpu,
         "parity_sample": (cpu or {}).get("parity_sample"),
@@ -785,6 +787,26 @@ def product_pass(logdir, device):
     return time.perf_counter() - t0
 
 
+def entrypoints_run(wl, n_events, device):
+    """Wall clock of the drop-in entry points themselves - sofa_preprocess(cfg) + sofa_analyze(cfg), files in, files out -
+    on a logdir of n_events events (the head of the same synthetic trace + its side files) in /dev/shm."""
+    import shutil
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    work = tempfile.mkdtemp(prefix="sofa_entry_", dir=base)
+    try:
+        logdir = os.path.join(work, "sofalog") + "/"
+        os.makedirs(logdir)
+        write_sample_logdir(logdir, n_events, SEED, wl)
+        in_bytes = sum(os.path.getsize(logdir + f) for f in os.listdir(logdir))
+        dt = product_pass(logdir, device)
+        out_bytes = sum(os.path.getsize(logdir + f) for f in os.listdir(logdir)) - in_bytes
+        return {"events": n_events, "seconds": round(dt, 3), "events_per_s": n_events / dt, "input_bytes": in_bytes,
+                "output_bytes": out_bytes, "where": base,
+                "what": "sofa_preprocess(cfg) + sofa_analyze(cfg): file reads, H2D, kernels, D2H, file writes, demangling, Python"}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def parity_sample(oracle_dir, product_dir):
     """Byte comparison of every output file of the two passes; raises on the first difference."""
     compared = []
@@ -871,6 +893,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=100000000, help="events per GPU (default: BASELINE configs[2])")
     ap.add_argument("--cpu-sample", type=int, default=150000, help="events in the CPU baseline sample")
+    ap.add_argument("--entry-events", type=int, default=10000000,
+                    help="events of the logdir that goes through sofa_preprocess + sofa_analyze themselves (e2e_entrypoints; 0 = skip)")
     ap.add_argument("--strong", type=int, default=1,
                     help="1 (with --gpus > 1): also time ONE trace of --events events sharded over all GPUs (strong scaling, NCCL on the data path)")
     ap.add_argument("--numa-bind", type=int, default=1, help="1: bind every rank (CPUs + pinned arenas) to its GPU's NUMA node")

@@ -49,7 +49,10 @@ typedef struct {
     const double* mhz_fp;
     double ts_rescale, dt_rescale, payload_unit;
     int32_t idx[9];              /* Start, Duration, Size, Throughput, Context, Stream, Name, Src Ctx, Dst Ctx; -1 = absent */
-    int32_t api_mode;            /* 1: gpu source holds `nvprof --print-api-trace` rows (cuda_api_trace_read) */
+    int32_t api_mode;            /* 1: gpu source holds `nvprof --print-api-trace` rows (cuda_api_trace_read);
+                                  * 2 (side CSV sources 3..5): vmstat.csv name fields;
+                                  * 3 (trace sources 0..2): the text is <src>trace.csv itself, header line skipped by data_off -
+                                  *   the rows pd.read_csv would give (stand-alone `sofa analyze`, sofa_analyze.py:898-977) */
 } sofa_ingest_params_t;
 
 /* gpu_profile (sofa_analyze.py:343-377) + comm_profile (sofa_common.py:23-177) results */

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) k_row_flags(SrcView src, uint64_t ncand, 
     unsigned int f = 0;
     if (c < ncand) {
         uint64_t row = c * stride;
-        if (KIND == SRC_GPU) f = src.c.g.bwf[row] ? 1u : 0u;
+        if (KIND == SRC_GPU) f = (src.c.g.bwf[row] & 1) ? 1u : 0u;
         else if (KIND == SRC_NET) f = src.c.n.proto[row] == 0 ? 2u : 4u;
     }
     f = __reduce_or_sync(0xffffffffu, f);

@@ -31,6 +31,8 @@ struct RawCols { double* f; int64_t* i; int32_t* nf; };
 
 struct AllCols { PerfCols p; GpuCols g; NetCols n; SideCols s; RawCols r; };
 
+constexpr uint32_t CSVFIX_CHUNK = 4096;      // bytes per warp of the trace-CSV quote-parity pre-pass (below)
+
 __device__ __forceinline__ uint32_t newline_mask4(uint32_t w) {       // 0xff in every byte equal to '\n'
     return __vcmpeq4(w, 0x0a0a0a0au);
 }
@@ -86,6 +88,36 @@ k_count_lines(const char* __restrict__ text, uint64_t begin, uint64_t end, uint3
     if (cr) atomicOr(cr_flag, 1u);
 }
 
+// ---- trace CSV re-ingest: newlines inside quoted name fields (nvprof kernel names keep their '\n') become 0x1f, so
+// that rows are lines for the tile machinery above.  Quote parity of a byte = number of '"' before it, mod 2:
+// counted per chunk, prefix-summed over the chunks, then resolved inside every chunk by one warp with ballots.
+__global__ void __launch_bounds__(256) k_csv_quote_count(const char* __restrict__ text, uint64_t begin, uint64_t end, uint64_t* counts) {
+    const uint64_t chunk = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t a = begin + chunk * CSVFIX_CHUNK;
+    if (a >= end) return;
+    const uint64_t b = a + CSVFIX_CHUNK < end ? a + CSVFIX_CHUNK : end;
+    uint32_t c = 0;
+    for (uint64_t p = a + (threadIdx.x & 31); p < b; p += 32) c += text[p] == '"';
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) counts[chunk] = c;
+}
+__global__ void __launch_bounds__(256) k_csv_mask_newlines(char* text, uint64_t begin, uint64_t end, const uint64_t* prefix) {
+    const uint64_t chunk = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t a = begin + chunk * CSVFIX_CHUNK;
+    if (a >= end) return;
+    const uint64_t b = a + CSVFIX_CHUNK < end ? a + CSVFIX_CHUNK : end;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t inq = (uint32_t)(prefix[chunk] & 1);
+    for (uint64_t p0 = a; p0 < b; p0 += 32) {
+        const uint64_t p = p0 + lane;
+        const char ch = p < b ? text[p] : 0;
+        const unsigned qb = __ballot_sync(0xffffffffu, ch == '"');
+        const uint32_t mine = inq ^ (__popc(qb & ((1u << lane) - 1u)) & 1u);
+        if (ch == '\n' && mine) text[p] = 0x1f;
+        inq ^= __popc(qb) & 1u;
+    }
+}
 #endif  // SOFA_K_COUNT
 
 // In-place exclusive scan of a[0..n) (single block); a[n] = total.  (static: every translation unit that scans gets its own copy)
@@ -209,7 +241,7 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
         if (code == E_OK) {
             if (KIND == SRC_PERF) {
                 PerfRow r;
-                code = parse_perf(line, n, cfg, &r);
+                code = cfg.csv_mode ? parse_csv_perf(line, n, &r) : parse_perf(line, n, cfg, &r);
                 if (code == E_OK) {
                     cols.p.ts[row] = r.ts; cols.p.event[row] = r.event; cols.p.dur[row] = r.dur;
                     cols.p.pid[row] = r.pid; cols.p.tid[row] = r.tid;
@@ -221,7 +253,7 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
                 }
             } else if (KIND == SRC_GPU) {
                 GpuRow r;
-                code = parse_gpu(line, n + (has_nl ? 1 : 0), cfg, &r);
+                code = cfg.csv_mode ? parse_csv_gpu(line, n, &r) : parse_gpu(line, n + (has_nl ? 1 : 0), cfg, &r);
                 if (code == E_OK) {
                     cols.g.ts[row] = r.ts; cols.g.dur[row] = r.dur; cols.g.bw[row] = r.bw; cols.g.payload[row] = r.payload;
                     cols.g.dev[row] = r.dev; cols.g.tid[row] = r.tid; cols.g.src[row] = r.src; cols.g.dst[row] = r.dst;
@@ -250,7 +282,7 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
                 }
             } else {
                 NetRow r;
-                code = parse_net(line, n, cfg, &r);
+                code = cfg.csv_mode ? parse_csv_net(line, n, &r) : parse_net(line, n, cfg, &r);
                 if (code == E_OK) {
                     cols.n.ts[row] = r.ts; cols.n.payload[row] = r.payload; cols.n.src[row] = r.src; cols.n.dst[row] = r.dst;
                     cols.n.proto[row] = r.proto;

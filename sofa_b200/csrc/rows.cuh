@@ -45,6 +45,7 @@ struct IngestCfg {
     int n_cudaproc;                                   // pid column (:288)
     int idx_start, idx_dur, idx_size, idx_thr, idx_ctx, idx_stream, idx_name, idx_srcctx, idx_dstctx;
     int api_mode;            // nvprof --print-api-trace rows (cuda_api_trace_read, :203-247)
+    int csv_mode;            // trace sources: the text is <src>trace.csv itself (stand-alone `sofa analyze`, :898-977)
     int side_table;          // SRC_SIDE: 0 mpstat.csv (name carries usr|sys|idl|iow|irq), 1 nvsmi_trace.csv, 2 netstat.csv;
                              // SRC_RAW: 0 mpstat.txt, 1 nvsmi_query.txt, 2 netstat.txt
 };
@@ -333,11 +334,32 @@ struct DashFilter {
     SOFA_HD void put_word(uint64_t w, int nb) { k->put_word(w ^ ((lanes_eq(w, '-') >> 7) * 0x72ull), nb); }      // '-' ^ '_' = 0x72
 };
 
+// A name taken verbatim from the name field of a trace CSV (csv_mode): the field without its enclosing quotes; inside,
+// a doubled quote is one quote (csv QUOTE_MINIMAL) and 0x1f stands for a newline that the pre-pass took out of the
+// quoted field so that rows are lines (k_csv_mask_newlines).
+template <class K>
+struct CsvLiteralFilter {
+    static constexpr bool WORDS = false;
+    K* k; bool q;
+    SOFA_HD void put(char ch) {
+        if (ch == '"') { if (q) { k->put('"'); q = false; } else q = true; return; }
+        q = false;
+        k->put(ch == 0x1f ? '\n' : ch);
+    }
+    SOFA_HD void put_word(uint64_t w, int nb) { put_word_bytes(*this, w, nb); }
+};
+constexpr uint16_t PERF_LITERAL = 0xffff;       // PerfRow.evt_len of a CSV-ingested row: name = the sym span, verbatim
+
 // name = '[%s]' % evt.replace('-','_') + sym + dso   (:116,121)
 template <typename S>
 struct PerfName {
     S line; PerfRow r; bool wide;
     template <class K> SOFA_HD void gen(K& k) const {
+        if (r.evt_len == PERF_LITERAL) {
+            CsvLiteralFilter<K> lf{&k, false};
+            put_span(lf, line + r.sym_off, r.sym_len, wide);
+            return;
+        }
         k.put('[');
         { DashFilter<K> df{&k}; put_span(df, line + r.evt_off, r.evt_len, wide); }
         k.put(']');
@@ -628,6 +650,11 @@ template <typename S>
 struct GpuName {
     S line; GpuRow r; bool wide; bool api;
     template <class K> SOFA_HD void gen(K& k) const {
+        if (r.bw_is_float & 2) {                                                       // CSV-ingested row: the name field, verbatim
+            CsvLiteralFilter<K> lf{&k, false};
+            put_span(lf, line + r.name_off, r.name_len, wide);
+            return;
+        }
         if (api) put_lit(k, "[CUDA_API]");                                             // :213
         if (r.dev != -1) { put_lit(k, "[gpu"); put_i64(k, r.dev); k.put(']'); }        // :325-326
         if (r.kind == 0) {
@@ -783,6 +810,89 @@ SOFA_HD int parse_side(S s, int n, const IngestCfg& c, SideRow* r) {
     return E_OK;
 }
 
+// ============================================================================ trace CSV rows (re-ingest)
+// One row of cputrace.csv / gputrace.csv / nettrace.csv as pd.read_csv sees it (sofa_analyze.py:898-977 works on these
+// files).  The first eleven fields are numeric, the last one (category) too; the name is everything between the 11th
+// comma and the last one, quoted iff it holds ',' '"' or a newline (newlines inside quotes were replaced by 0x1f).
+template <typename S>
+SOFA_HD int csv_row_fields(S s, int n, int* fa, int* fb) {       // 13 spans; returns E_OK / E_FEW_TOKENS
+    if (n > 65535) return E_LINE_TOO_LONG;
+    int f = 0, a = 0;
+    for (int i = 0; i < n && f < 11; i++) if (s[i] == ',') { fa[f] = a; fb[f] = i; f++; a = i + 1; }
+    if (f < 11) return E_FEW_TOKENS;
+    int last = -1;
+    for (int i = n - 1; i >= a; i--) if (s[i] == ',') { last = i; break; }
+    if (last < 0) return E_FEW_TOKENS;
+    fa[11] = a; fb[11] = last; fa[12] = last + 1; fb[12] = n;
+    if (fb[11] - fa[11] >= 2 && s[fa[11]] == '"' && s[fb[11] - 1] == '"') { fa[11]++; fb[11]--; }
+    return E_OK;
+}
+template <typename S>
+SOFA_HD int csv_num(S s, int a, int b, double* out, bool* is_float) {   // empty field = NaN (the [] packet rows)
+    if (b <= a) { *out = bits_d(0x7ff8000000000000ull); *is_float = true; return E_OK; }
+    *is_float = false;
+    for (int i = a; i < b; i++) if (s[i] == '.' || s[i] == 'e' || s[i] == 'n' || s[i] == 'i') *is_float = true;
+    int st = parse_double(s + a, b - a, out);
+    return st ? num_status_to_err(st, true) : E_OK;
+}
+SOFA_HD bool csv_to_i64(double v, int64_t* out) {
+    if (!(v >= -9.2e18 && v <= 9.2e18)) return false;
+    *out = (int64_t)v;
+    return (double)*out == v;
+}
+template <typename S>
+SOFA_HD int parse_csv_perf(S s, int n, PerfRow* r) {
+    int fa[13], fb[13];
+    int e = csv_row_fields(s, n, fa, fb); if (e) return e;
+    double v[11]; bool fl;
+    const int need[5] = {0, 1, 2, 9, 10};
+    for (int q = 0; q < 5; q++) { e = csv_num(s, fa[need[q]], fb[need[q]], &v[need[q]], &fl); if (e) return e; }
+    int64_t pid, tid;
+    if (!csv_to_i64(v[9], &pid) || !csv_to_i64(v[10], &tid) || pid < -2147483647 || pid > 2147483647 || tid < -2147483647 || tid > 2147483647)
+        return E_RANGE;
+    r->ts = v[0]; r->event = v[1]; r->dur = v[2]; r->pid = (int32_t)pid; r->tid = (int32_t)tid;
+    r->evt_off = 0; r->evt_len = PERF_LITERAL;
+    r->sym_off = (uint16_t)fa[11]; r->sym_len = (uint16_t)(fb[11] - fa[11]);
+    r->dso_off = 0; r->dso_len = 0; r->va_len = PERF_LITERAL; r->vb_len = 0;
+    return E_OK;
+}
+template <typename S>
+SOFA_HD int parse_csv_gpu(S s, int n, GpuRow* r) {
+    int fa[13], fb[13];
+    int e = csv_row_fields(s, n, fa, fb); if (e) return e;
+    double v[11]; bool fl[11];
+    for (int q = 0; q < 11; q++) { if (q == 1 || q == 9) continue; e = csv_num(s, fa[q], fb[q], &v[q], &fl[q]); if (e) return e; }
+    int64_t dev, kind, payload, src, dst, tid;
+    if (!csv_to_i64(v[3], &dev) || !csv_to_i64(v[4], &kind) || !csv_to_i64(v[5], &payload) || !csv_to_i64(v[7], &src) ||
+        !csv_to_i64(v[8], &dst) || !csv_to_i64(v[10], &tid)) return E_BAD_INT;
+    if (dev < -2147483647 || dev > 2147483647 || tid < -2147483647 || tid > 2147483647 || src < -2147483647 || src > 2147483647 ||
+        dst < -2147483647 || dst > 2147483647 || kind < 0 || kind > 255) return E_RANGE;
+    r->ts = v[0]; r->dur = v[2]; r->bw = v[6]; r->payload = payload;
+    r->dev = (int32_t)dev; r->tid = (int32_t)tid; r->src = (int32_t)src; r->dst = (int32_t)dst;
+    r->kind = (uint8_t)kind; r->bw_is_float = (uint8_t)((fl[6] ? 1 : 0) | 2);
+    r->name_off = (uint16_t)fa[11]; r->name_len = (uint16_t)(fb[11] - fa[11]);
+    return E_OK;
+}
+template <typename S>
+SOFA_HD int parse_csv_net(S s, int n, NetRow* r) {
+    int fa[13], fb[13];
+    int e = csv_row_fields(s, n, fa, fb); if (e) return e;
+    double ts, pl, src, dst; bool fl;
+    e = csv_num(s, fa[0], fb[0], &ts, &fl); if (e) return e;
+    r->ts = ts; r->proto = 0; r->payload = 0; r->src = 0; r->dst = 0;
+    if (fb[5] <= fa[5]) return E_OK;                                  // the all-NaN row of a non-IP packet
+    e = csv_num(s, fa[5], fb[5], &pl, &fl); if (e) return e;
+    e = csv_num(s, fa[7], fb[7], &src, &fl); if (e) return e;
+    e = csv_num(s, fa[8], fb[8], &dst, &fl); if (e) return e;
+    if (!csv_to_i64(pl, &r->payload) || !csv_to_i64(src, &r->src) || !csv_to_i64(dst, &r->dst)) return E_BAD_INT;
+    // 'network:tcp:...' or 'network:UDP,:...' (:198)
+    const int a = fa[11], l = fb[11] - fa[11];
+    if (l >= 12 && s[a + 8] == 't' && s[a + 9] == 'c' && s[a + 10] == 'p') r->proto = 2;
+    else if (l >= 13 && s[a + 8] == 'U' && s[a + 9] == 'D' && s[a + 10] == 'P') r->proto = 1;
+    else return E_FORMAT;
+    return E_OK;
+}
+
 // ============================================================================ 13-column row values
 struct RowVals {
     bool valid;              // false: the all-NaN row a `[]` record becomes
@@ -804,7 +914,7 @@ SOFA_HD RowVals vals_perf(const PerfRow& r) {
 SOFA_HD RowVals vals_gpu(const GpuRow& r, int n_cudaproc) {
     RowVals v; v.valid = true; v.ts = r.ts; v.dur = r.dur; v.dur_is_f = true; v.dur_i = 0; v.ts_is_f = true; v.ts_i = 0; v.cat = 0; v.ev_is_f = false; v.ev_f = 0;
     v.ev_i = r.payload * 100 + 17;                                   // :329
-    v.dev = r.dev; v.kind = r.kind; v.payload = r.payload; v.bw_is_f = r.bw_is_float != 0; v.bw_f = r.bw; v.bw_i = 0;
+    v.dev = r.dev; v.kind = r.kind; v.payload = r.payload; v.bw_is_f = (r.bw_is_float & 1) != 0; v.bw_f = r.bw; v.bw_i = 0;
     v.src = r.src; v.dst = r.dst; v.pid = n_cudaproc; v.tid = r.tid; return v;
 }
 SOFA_HD RowVals vals_net(const NetRow& r) {

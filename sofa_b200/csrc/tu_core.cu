@@ -126,10 +126,11 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     cfg.idx_start = p->idx[0]; cfg.idx_dur = p->idx[1]; cfg.idx_size = p->idx[2]; cfg.idx_thr = p->idx[3];
     cfg.idx_ctx = p->idx[4]; cfg.idx_stream = p->idx[5]; cfg.idx_name = p->idx[6]; cfg.idx_srcctx = p->idx[7];
     cfg.idx_dstctx = p->idx[8];
-    cfg.api_mode = p->api_mode;
+    cfg.api_mode = p->api_mode == 1 ? 1 : 0;
+    cfg.csv_mode = (k <= 2 && p->api_mode == 3) ? 1 : 0;
     cfg.side_table = k >= 6 ? k - 6 : (k >= 3 ? k - 3 : 0);
     if (k >= 3 && k < 6 && p->api_mode == 2) cfg.side_table = 3;          // vmstat.csv: bi / bo / in / cs out of the name column
-    if (k == SRC_GPU && (cfg.idx_start < 0 || cfg.idx_dur < 0 || cfg.idx_name < 0))
+    if (k == SRC_GPU && !cfg.csv_mode && (cfg.idx_start < 0 || cfg.idx_dur < 0 || cfg.idx_name < 0))
         FAIL(SOFA_ERR_ARG, "parse: gpu trace needs Start, Duration and Name columns");
     ENSURE(s.mhz, 16 * (size_t)cfg.n_mhz + 16);
     if (p->n_mhz > 0 && p->mhz_xp && p->mhz_fp) {
@@ -153,6 +154,12 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     if (ntiles > 0x7fffffffull) FAIL(SOFA_ERR_ARG, "parse: source too large for one call");
     ENSURE(c->tiles, (ntiles + 2) * 8);
     if (reset_err(c)) return SOFA_ERR_CUDA;
+    if (cfg.csv_mode) {
+        // rows of a trace CSV are lines once the newlines inside quoted names are masked (in place, on the device copy)
+        uint64_t nchunks = cdiv(end - begin, CSVFIX_CHUNK);
+        ENSURE(c->blockoff, (nchunks + 2) * 8);
+        CK_S(csv_mask_newlines(c, s.text.as<char>(), begin, end, c->blockoff.as<uint64_t>(), nchunks, launch_scan));
+    }
     LAUNCH(c, K_COUNT, launch_count_lines((unsigned)ntiles, c->stream, s.text.as<char>(), begin, end, tile, c->tiles.as<uint64_t>(), c->d_flags));
     CK_S(launch_scan(c, c->tiles.as<uint64_t>(), ntiles));
     uint64_t total = 0; unsigned int cr = 0;
@@ -169,7 +176,7 @@ int sofa_b200_parse(sofa_ctx* c, int k, const sofa_ingest_params_t* p, uint64_t*
     AllCols cols = all_cols(c, (k >= 3 && k < 6) ? k : 3, k >= 6 ? k : 6);
     const int tpl = k >= 6 ? SRC_RAW : (k >= 3 ? SRC_SIDE : k);
     static const bool use_tma = !(getenv("SOFA_B200_PARSE_TMA") && atoi(getenv("SOFA_B200_PARSE_TMA")) == 0);
-    if (k <= 2 && use_tma) {
+    if (k <= 2 && use_tma && !cfg.csv_mode) {
         // trace sources: persistent blocks, two tile buffers filled by cp.async.bulk (kernels_ingest_tma.cuh)
         const size_t buf = ((size_t)tile + TMA_OVERLAP_STAGED + TMA_STAGE_PAD + 127) & ~(size_t)127;
         const size_t smem_tma = 2 * buf + (size_t)max_lines * 2 + 16;

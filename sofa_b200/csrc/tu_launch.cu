@@ -70,6 +70,16 @@ void launch_count_lines(unsigned grid, cudaStream_t st, const char* text, uint64
                         uint64_t* tile_counts, unsigned int* cr_flag) {
     k_count_lines<<<grid, PARSE_TPB, 0, st>>>(text, begin, end, tile_bytes, tile_counts, cr_flag);
 }
+// quote-parity pre-pass of a trace CSV (see kernels_ingest.cuh); `counts` has room for nchunks + 2 values
+int csv_mask_newlines(sofa_ctx* c, char* text, uint64_t begin, uint64_t end, uint64_t* counts, uint64_t nchunks, int (*scan)(sofa_ctx*, uint64_t*, uint64_t)) {
+    if (nchunks == 0) return 0;
+    unsigned g = (unsigned)((nchunks + 7) / 8);
+    k_csv_quote_count<<<g, 256, 0, c->stream>>>(text, begin, end, counts);
+    int r = scan(c, counts, nchunks); if (r) return r;
+    k_csv_mask_newlines<<<g, 256, 0, c->stream>>>(text, begin, end, counts);
+    return 0;
+}
+
 void launch_emit(int kind, int fmt, unsigned grid, size_t smem, cudaStream_t st, const SrcView& v, const FusedArgs& a) {
     if (fmt == FMT_COMM) { inst_emit_gpu_comm(grid, smem, st, v, a); return; }
     if (fmt == FMT_AUX) { inst_emit_sideout_aux(grid, smem, st, v, a); return; }

@@ -213,12 +213,13 @@ def gather_source(eng, kind, dist, device, dst=0):
                 if r == rank:
                     _view(dptr, nb, device).copy_(_view(sptr, nb, device))
                 else:
-                    reqs.append(dist.irecv(_view(dptr, nb, device), src=r))
+                    reqs.append(dist.P2POp(dist.irecv, _view(dptr, nb, device), r))
                     moved += nb
             row0 += rows[r]
             text0 += texts[r]
-        for q in reqs:
-            q.wait()
+        if reqs:
+            for q in dist.batch_isend_irecv(reqs):           # one NCCL group: the transfers of all shards and columns overlap
+                q.wait()
         torch.cuda.synchronize(device)
         eng.shard_commit(kind, rows, texts)
     else:
@@ -226,9 +227,10 @@ def gather_source(eng, kind, dist, device, dst=0):
         reqs = []
         for sptr, nb in parts:
             if nb:
-                reqs.append(dist.isend(_view(sptr, nb, device), dst=dst))
+                reqs.append(dist.P2POp(dist.isend, _view(sptr, nb, device), dst))
                 moved += nb
-        for q in reqs:
-            q.wait()
+        if reqs:
+            for q in dist.batch_isend_irecv(reqs):
+                q.wait()
         torch.cuda.synchronize(device)
     return moved

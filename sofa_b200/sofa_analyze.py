@@ -13,10 +13,11 @@ vmstat_profile, mpstat_profile, nvsmi_profile, gpu_profile (+ comm_profile, get_
 Not built: blktrace_latency_profile / diskstat_profile (their inputs come from `btt` and diskstat_vector.csv), the PDF
 charts (no matplotlib), nvlink ring search, POTATO, AISI driver hook.
 
-The reference re-reads <src>trace.csv; here the trace rows are re-ingested from the raw logs in `cfg.logdir`
-(same bytes -> same columns), or taken from the engine sofa_preprocess left resident when `cfg.keep_engine` is
-set (`sofa report`); the small side tables (mpstat.csv, nvsmi_trace.csv, netstat.csv, vmstat.csv) are parsed from
-the CSV files themselves.
+Like the reference, a stand-alone `sofa analyze` (or `sofa report --skip_preprocess`) reads only the CSV files of the
+logdir: cputrace.csv / gputrace.csv / nettrace.csv are parsed on the device as pd.read_csv would see them (quoted,
+multi-line name fields included), and so are the small side tables (mpstat.csv, nvsmi_trace.csv, netstat.csv,
+vmstat.csv).  After `sofa report` the rows sofa_preprocess left resident on the device are analysed directly
+(`cfg.keep_engine`): same values, since every reduction reads them through the "%.6f" round trip.
 """
 import glob
 import os
@@ -166,9 +167,26 @@ def _ip_text(j):
     return j[:-9] + '.' + zero(j[-9:-6]) + '.' + zero(j[-6:-3]) + '.' + zero(j[-3:])
 
 
+def _load_trace_csv(eng, logdir, kind, fn):
+    """<src>trace.csv -> the engine's parsed rows of source `kind`, as pd.read_csv would give them (the reference's
+    sofa_analyze works on these files, :898-977; they are the resume format of `sofa report --skip_preprocess`)."""
+    with open(logdir + fn, 'rb') as f:
+        data = f.read()
+    nl = data.find(b'\n')
+    p = hl.base_params(kind, 0.0, True)
+    p['api_mode'] = 3
+    eng.load(kind, data, p, nl + 1 if nl >= 0 else len(data))
+    return True
+
+
 def load_net_source(cfg, eng):
-    """Re-ingest net.tmp (for a stand-alone `sofa analyze`); returns False when it is absent."""
+    """The packets for a stand-alone `sofa analyze`: nettrace.csv (already down-sampled by plot_ratio at preprocess
+    time), else the raw net.tmp; returns False when neither is there."""
     logdir = cfg.logdir
+    eng._net_rows_are_csv = False
+    if os.path.isfile(logdir + 'nettrace.csv'):
+        eng._net_rows_are_csv = True
+        return _load_trace_csv(eng, logdir, hl.SRC_NET, 'nettrace.csv')
     if not os.path.isfile(logdir + 'net.tmp'):
         return False
     with open(logdir + 'net.tmp', 'rb') as f:
@@ -185,7 +203,7 @@ def net_profile(logdir, cfg, eng, features):
     import numpy as np
     if not cfg.cluster_ip:
         print_title("Network Profiling:")
-    ratio = int(cfg.plot_ratio)
+    ratio = 1 if getattr(eng, '_net_rows_are_csv', False) else int(cfg.plot_ratio)     # nettrace.csv rows are the down-sampled ones
     net_time, total, pairs = eng.net_profile(ratio)
     as_float = bool(eng.row_flags(hl.SRC_NET, ratio) & 2)            # a [] packet row makes the payload column float64
     cast = (lambda x: np.float64(x)) if as_float else (lambda x: np.int64(x))
@@ -524,6 +542,8 @@ def concurrency_breakdown(logdir, cfg, eng, features):
 def load_perf_source(cfg, eng):
     """(Re-)ingest perf.script exactly as sofa_preprocess does (sofa_preprocess.py:1786-1807)."""
     logdir = cfg.logdir
+    if os.path.isfile(logdir + 'cputrace.csv'):
+        return _load_trace_csv(eng, logdir, hl.SRC_PERF, 'cputrace.csv')
     if not os.path.isfile(logdir + 'perf.script'):
         return False
     with open(logdir + 'perf.script', 'rb') as f:
@@ -542,6 +562,8 @@ def load_perf_source(cfg, eng):
 def load_gpu_source(cfg, eng):
     """(Re-)ingest gputrace.tmp exactly as sofa_preprocess does (sofa_preprocess.py:1343-1444)."""
     logdir = cfg.logdir
+    if os.path.isfile(logdir + 'gputrace.csv'):
+        return _load_trace_csv(eng, logdir, SRC_GPU, 'gputrace.csv')
     if not os.path.isfile(logdir + 'gputrace.tmp'):
         return False
     with open(logdir + 'gputrace.tmp', 'rb') as f:
@@ -609,7 +631,7 @@ def sofa_analyze(cfg, engine=None):
         if os.path.isfile(logdir + "nettrace.csv"):
             if _has_rows(logdir + "nettrace.csv"):
                 if not resident and not load_net_source(cfg, eng):
-                    raise IOError("nettrace.csv exists but net.tmp (raw packets) is missing: CSV re-ingest is not implemented")
+                    raise IOError("nettrace.csv could not be loaded")
                 features = net_profile(logdir, cfg, eng, features)
         else:
             print_warning(cfg, "%s is not found" % (logdir + "nettrace.csv"))
@@ -647,8 +669,7 @@ def sofa_analyze(cfg, engine=None):
         if os.path.isfile(logdir + "gputrace.csv"):
             if _has_rows(logdir + "gputrace.csv"):
                 if (not resident or getattr(cfg, '_sofa_b200_gpu_slot_is_api', False)) and not load_gpu_source(cfg, eng):
-                    raise IOError("gputrace.csv exists but gputrace.tmp (raw rows) is missing: "
-                                  "CSV re-ingest is not implemented")
+                    raise IOError("gputrace.csv could not be loaded")
                 features += gpu_profile(cfg, eng)
         else:
             print_warning(cfg, "%sgputrace.csv is not found. If there is no need to profile GPU, just ignore it." % logdir)

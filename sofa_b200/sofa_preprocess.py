@@ -285,12 +285,15 @@ def _preprocess(cfg, eng, io):
             print_warning(cfg, 'Incorrect misc.txt content. Some profiling information may not be available.')
     for fn in NOT_YET:
         if os.path.isfile(logdir + fn) and os.path.getsize(logdir + fn) > 0:
-            if os.environ.get('SOFA_B200_SKIP_UNSUPPORTED', '0') not in ('', '0'):
-                print_warning(cfg, "%s is skipped (SOFA_B200_SKIP_UNSUPPORTED): its series and CSV will be missing "
-                                   "compared with the reference's report" % fn)
-                continue
-            raise NotImplementedError("%s: this source is not on the accelerated hot path yet (SURVEY.md §8f N1); remove "
-                                      "it, use the reference, or set SOFA_B200_SKIP_UNSUPPORTED=1 to skip it knowingly" % fn)
+            # the recorder writes diskstat.txt on every Linux run (sofa_record.py:271-276): a drop-in must not die on
+            # it.  Default: say so, skip the source (its series stays empty, its CSV is not written) and go on;
+            # SOFA_B200_STRICT=1 turns the gap into an error for runs that must match the reference file for file.
+            msg = ("%s: this source is not on the accelerated path (SURVEY.md §8f N1): its report.js series stays empty "
+                   "and its CSV is not written" % fn)
+            if os.environ.get('SOFA_B200_STRICT', '0') not in ('', '0'):
+                raise NotImplementedError(msg + " (SOFA_B200_STRICT is set)")
+            import sys
+            sys.stderr.write("[WARNING] " + msg + "\n")
     if int(os.system('command -v perf 1> /dev/null')) == 0 and os.path.isfile(logdir + 'perf.data'):
         with open(logdir + 'perf.script', 'w') as logfile:
             subprocess.call('perf script -F time,pid,tid,event,ip,sym,dso,symoff,period,brstack,brstacksym '

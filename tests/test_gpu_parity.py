@@ -659,7 +659,7 @@ DRIVER_CASES = sorted(d for d in os.listdir(os.path.join(os.path.dirname(os.path
 
 
 @pytest.mark.parametrize("name", DRIVER_CASES)
-@pytest.mark.parametrize("variant", ["plain", "verbose"])
+@pytest.mark.parametrize("variant", ["plain", "verbose", "verbose_from_csv", "plain_resident"])
 def test_analyze_driver_stdout_matches_reference(name, variant, tmp_path, capsys):
     """sofa_preprocess + sofa_analyze on the inputs of tests/golden/driver_*: the whole stdout of the analyze driver
     (feature table; with --verbose every profile function's tables) and netrank.csv / performance.csv / comm.csv equal
@@ -682,10 +682,18 @@ def test_analyze_driver_stdout_matches_reference(name, variant, tmp_path, capsys
     cfg = default_report_config(a, cpu_filters=ov.pop("cpu_filters", None))
     for k, v in ov.items():
         setattr(cfg, k, v)
+    if variant == "plain_resident":
+        cfg.keep_engine = True        # `sofa report`: analyze the rows preprocess left on the device
     sofa_preprocess(cfg)
     capsys.readouterr()
-    cfg.verbose = variant == "verbose"
+    cfg.verbose = variant.startswith("verbose")
     cfg.nvsmi_data = False            # the golden driver run starts from a fresh cfg (as a stand-alone `sofa analyze` does)
+    if variant == "verbose_from_csv":
+        # the CSV resume contract (`sofa report --skip_preprocess`, bin/sofa:90,369-371): nothing but the CSVs is left
+        for fn in ("perf.script", "gputrace.tmp", "net.tmp"):
+            if os.path.isfile(a + fn):
+                os.remove(a + fn)
+    variant = "verbose" if variant.startswith("verbose") else "plain"
     sofa_analyze(cfg)
     got = capsys.readouterr().out.replace(a, "LOGDIR/").replace(a.rstrip("/"), "LOGDIR")
     want = open(os.path.join(gdir, "analyze_%s.txt" % variant)).read()
