@@ -215,6 +215,19 @@ int sofa_b200_side_quantiles(sofa_ctx*, int slot, int value_col, int use_event, 
 /* Sums of the five integers parsed out of the name column of a side table (mpstat.csv: usr sys idl iow irq; vmstat.csv
  * parsed with api_mode = 2: bi bo in cs, vmstat_profile :712-733) and the row count. */
 int sofa_b200_side_int_sums(sofa_ctx*, int slot, int64_t* sums, uint64_t* n_rows);
+/* AISI per-iteration profile (sofa_aisi.py:21-59 iter_profile over the slices of :429-453): the gpu rows of device
+ * `device_id` (df_gpu[df_gpu.deviceId == 1] in the reference) with times[i] <= timestamp < times[i+1] form iteration i
+ * (n_times - 1 iterations; the boundaries come from the host-side iteration detection).  Per iteration: row count,
+ * timestamps of its first / last row (frame order), numpy-pairwise sums of duration over all its rows and over the
+ * rows whose name contains "_fw", "_bw", "gemm", "CUDA_COPY", "nccl", payload sum, number of distinct streams (tid). */
+typedef struct {
+    uint64_t n_rows;
+    double first_ts, last_ts;
+    double gpu_time, fw_time, bw_time, gemm_time, copy_name_time, allreduce_time;
+    int64_t payload;
+    uint32_t streams, pad;
+} sofa_iter_t;
+int sofa_b200_iter_profile(sofa_ctx*, int32_t device_id, const double* times, uint32_t n_times, sofa_iter_t* out);
 /* --spotlight_gpu region of interest (sofa_analyze.py:872-895): the saturating-counter state machine over the
  * event == 0, deviceId == 0 rows of the parsed nvsmi_trace.csv body (source 4), in row order.  roi_begin / roi_end are
  * in/out (cfg.roi_begin / cfg.roi_end); both are reset to 0 when end < begin. */

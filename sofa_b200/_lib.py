@@ -14,7 +14,7 @@ EXPORTS = [
     "sofa_b200_abi_version", "sofa_b200_last_error", "sofa_b200_error_row", "sofa_b200_create",
     "sofa_b200_destroy", "sofa_b200_host_alloc", "sofa_b200_host_free", "sofa_b200_upload",
     "sofa_b200_parse", "sofa_b200_row_flags", "sofa_b200_emit_csv", "sofa_b200_set_filters",
-    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_emit_json_series", "sofa_b200_set_debug", "sofa_b200_synth_range", "sofa_b200_shard_export", "sofa_b200_shard_reserve", "sofa_b200_shard_commit", "sofa_b200_set_global_flags", "sofa_b200_net_triples", "sofa_b200_set_net_filters", "sofa_b200_mpstat_profile",
+    "sofa_b200_viz_mangled", "sofa_b200_set_demangled", "sofa_b200_emit_json", "sofa_b200_emit_json_series", "sofa_b200_set_debug", "sofa_b200_iter_profile", "sofa_b200_synth_range", "sofa_b200_shard_export", "sofa_b200_shard_reserve", "sofa_b200_shard_commit", "sofa_b200_set_global_flags", "sofa_b200_net_triples", "sofa_b200_set_net_filters", "sofa_b200_mpstat_profile",
     "sofa_b200_side_quantiles", "sofa_b200_side_int_sums", "sofa_b200_nvsmi_roi", "sofa_b200_fetch_range", "sofa_b200_emit_block_end", "sofa_b200_fetch",
     "sofa_b200_get_column", "sofa_b200_gpu_profile", "sofa_b200_top_k", "sofa_b200_cpu_profile",
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
@@ -66,6 +66,13 @@ class ShardDesc(ctypes.Structure):
     _fields_ = [("n_rows", ctypes.c_uint64), ("text_bytes", ctypes.c_uint64), ("data_off", ctypes.c_uint64),
                 ("text", ctypes.c_void_p), ("cols", ctypes.c_void_p * 16), ("col_elem", ctypes.c_uint32 * 16),
                 ("n_cols", ctypes.c_int32), ("pad", ctypes.c_int32)]
+
+
+class IterStats(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_uint64), ("first_ts", ctypes.c_double), ("last_ts", ctypes.c_double),
+                ("gpu_time", ctypes.c_double), ("fw_time", ctypes.c_double), ("bw_time", ctypes.c_double),
+                ("gemm_time", ctypes.c_double), ("copy_name_time", ctypes.c_double), ("allreduce_time", ctypes.c_double),
+                ("payload", ctypes.c_int64), ("streams", ctypes.c_uint32), ("pad", ctypes.c_uint32)]
 
 
 class NvsmiGroup(ctypes.Structure):
@@ -125,6 +132,7 @@ def load_lib():
     lib.sofa_b200_emit_json_series.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), u64p, u64p, u64p]
     lib.sofa_b200_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
     lib.sofa_b200_set_debug.argtypes = [vp, ctypes.c_int, ctypes.c_uint64]
+    lib.sofa_b200_iter_profile.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32, ctypes.POINTER(IterStats)]
     lib.sofa_b200_shard_export.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ShardDesc)]
     lib.sofa_b200_shard_reserve.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ShardDesc)]
     lib.sofa_b200_shard_commit.argtypes = [vp, ctypes.c_int, ctypes.c_int32, u64p, u64p]

@@ -192,3 +192,57 @@ __global__ void __launch_bounds__(256) k_seg_pairwise_big_raw(const double* __re
     }
 }
 }  // namespace sofa
+
+namespace sofa {
+// ---------------------------------------------------------------------------- AISI iter_profile (sofa_aisi.py:21-59, 429-453)
+// Rows of one GPU (df_gpu[df_gpu.deviceId == dev]) falling into iteration i: times[i] <= timestamp < times[i+1] (CSV
+// values).  Per row: iteration index + which of the five keywords ("_fw", "_bw", "gemm", "CUDA_COPY", "nccl") its name
+// contains (one packed shift-and pass).  Per iteration, exact integer / index reductions with atomics: row count,
+// first and last row (row order = frame order), payload sum.
+struct IterAcc { unsigned long long count, first_row, last_row; long long payload; };
+__global__ void __launch_bounds__(256) k_iter_rows(SrcView src, uint64_t n, int32_t dev, const double* __restrict__ times, uint32_t nt,
+                                                   const PackedFilter* __restrict__ pf, uint32_t* __restrict__ iter_of, uint8_t* __restrict__ bits,
+                                                   IterAcc* acc) {
+    __shared__ PackedFilter spf;
+    {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(pf);
+        uint32_t* sp = reinterpret_cast<uint32_t*>(&spf);
+        for (uint32_t i = threadIdx.x; i < sizeof(PackedFilter) / 4; i += blockDim.x) sp[i] = g[i];
+    }
+    __syncthreads();
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    uint32_t it = 0xffffffffu; uint32_t hit = 0;
+    if (src.c.g.dev[row] == dev) {
+        const double ts = round6_value(src.c.g.ts[row]);
+        if (ts >= times[0] && ts < times[nt - 1]) {
+            uint32_t lo = 0, hi = nt - 1;                       // largest lo with times[lo] <= ts
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (times[mid] <= ts) lo = mid; else hi = mid; }
+            it = lo;
+            GpuRow r = load_gpu(src, row);
+            GpuName<const char*> ng{src.text + src.c.g.line_start[row], r, true, src.api_mode != 0};
+            PackedMatchSink ms(&spf); ng.gen(ms); hit = ms.hits();
+            atomicAdd(&acc[it].count, 1ull);
+            atomicMin(&acc[it].first_row, (unsigned long long)row);
+            atomicMax(&acc[it].last_row, (unsigned long long)row);
+            atomicAdd((unsigned long long*)&acc[it].payload, (unsigned long long)r.payload);
+        }
+    }
+    iter_of[row] = it; bits[row] = (uint8_t)hit;
+}
+// selection `sel` (0: every row of an iteration, 1 + k: rows whose name holds keyword k): key = iteration + 1, else 0;
+// sel == 6: key = (iteration + 1) << 32 | tid (distinct streams per iteration)
+__global__ void __launch_bounds__(256) k_iter_selkey(const uint32_t* __restrict__ iter_of, const uint8_t* __restrict__ bits,
+                                                     const int32_t* __restrict__ tid, uint64_t n, int sel, uint64_t* __restrict__ key) {
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const uint32_t it = iter_of[row];
+    uint64_t k = 0;
+    if (it != 0xffffffffu) {
+        if (sel == 0) k = (uint64_t)it + 1;
+        else if (sel == 6) k = (((uint64_t)it + 1) << 32) | (uint32_t)tid[row];
+        else if ((bits[row] >> (sel - 1)) & 1) k = (uint64_t)it + 1;
+    }
+    key[row] = k;
+}
+}  // namespace sofa

@@ -345,6 +345,14 @@ class CudaEngine:
         self._check(self.lib.sofa_b200_nvsmi_roi(self.ctx, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def iter_profile(self, times, device_id=1):
+        """per-iteration sums of the parsed gpu rows of one device between consecutive boundaries -> list of L.IterStats"""
+        t = np.ascontiguousarray(times, dtype=np.float64)
+        out = (L.IterStats * max(1, len(t) - 1))()
+        self._check(self.lib.sofa_b200_iter_profile(self.ctx, int(device_id), t.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                    len(t), out))
+        return [out[i] for i in range(len(t) - 1)]
+
     def nvsmi_profile(self, roi=None):
         """Per (deviceId, event) group of the parsed nvsmi_trace.csv (source 4): {(dev, event): (count, sum,
         [(lo, hi)] for q = .25, .5, .75)}, device ids in order of first appearance, first / last timestamp."""

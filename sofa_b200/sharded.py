@@ -101,28 +101,34 @@ class ShardIO:
             f.write(memoryview(body))
         self.csv_parts.append((path, header))
 
-    def finish(self, series, path):
-        counts = self.all_gather_counts([s.nrec for s in series])
+    def _write_series_parts(self, series, path):
         for i, s in enumerate(series):
             if s.nrec > 0:
                 with open('%s.s%d.shard%d' % (path, i, self.rank), 'wb') as f:
                     f.write(memoryview(s.records))
+
+    def _assemble(self, series, counts, path):
+        for p, header in self.csv_parts:
+            with open(p, 'wb') as out:
+                out.write(header)
+                for r in range(self.world):
+                    part = '%s.shard%d' % (p, r)
+                    with open(part, 'rb') as f:
+                        while True:
+                            chunk = f.read(1 << 24)
+                            if not chunk:
+                                break
+                            out.write(chunk)
+                    os.remove(part)
+        if len(series):
+            self._write_report(series, counts, path)
+
+    def finish(self, series, path):
+        counts = self.all_gather_counts([s.nrec for s in series])
+        self._write_series_parts(series, path)
         self.dist.barrier()
         if self.rank == 0:
-            for p, header in self.csv_parts:
-                with open(p, 'wb') as out:
-                    out.write(header)
-                    for r in range(self.world):
-                        part = '%s.shard%d' % (p, r)
-                        with open(part, 'rb') as f:
-                            while True:
-                                chunk = f.read(1 << 24)
-                                if not chunk:
-                                    break
-                                out.write(chunk)
-                        os.remove(part)
-            if len(series):
-                self._write_report(series, counts, path)
+            self._assemble(series, counts, path)
         self.dist.barrier()
 
     def _write_report(self, series, counts, path):
@@ -234,3 +240,69 @@ def gather_source(eng, kind, dist, device, dst=0):
                 q.wait()
         torch.cuda.synchronize(device)
     return moved
+
+
+# ----------------------------------------------------------------------------- one GPU, bounded device memory
+class SegmentIO(ShardIO):
+    """The same byte-range splitting walked SEQUENTIALLY by one process: segment i of K plays rank i of K.  Device
+    memory then holds one segment of a source at a time instead of the whole file (text + columns + outputs are ~5x
+    the text: a 100 GB perf.script does not fit 180 GB of HBM in one piece), and the logdir's outputs are assembled
+    from the segments' part files exactly as a sharded run assembles its ranks'.  The file-level dtype flags are
+    collected by a parse-only pass over the gpu / packet segments first (state['flags'])."""
+
+    def __init__(self, index, count, state):
+        ShardIO.__init__(self, index, count, None)
+        self.state = state
+
+    def sync_flags(self, eng, kind, stride):
+        eng.set_global_flags(kind, stride, self.state['flags'].get(kind, 0))
+
+    def finish(self, series, path):
+        self.state['counts'].append([s.nrec for s in series])
+        self.state['csv_parts'] = self.csv_parts
+        self._write_series_parts(series, path)
+        if self.rank == 0:
+            self.state['series0'] = series
+        if self.rank + 1 == self.world:
+            self._assemble(self.state['series0'], self.state['counts'], path)
+
+
+def sofa_preprocess_segmented(cfg, engine, segment_bytes):
+    """sofa_preprocess(cfg) with at most ~segment_bytes of any source resident on the device at a time."""
+    import glob
+    from . import hostlogic as hl
+    from .sofa_preprocess import sofa_preprocess
+    logdir = cfg.logdir
+    if int(cfg.plot_ratio) != 1 or getattr(cfg, 'cuda_api_tracing', False):
+        raise NotImplementedError("segmented preprocess needs plot_ratio 1 and no --cuda_api_tracing")
+    files = {hl.SRC_PERF: logdir + 'perf.script', hl.SRC_GPU: logdir + 'gputrace.tmp', hl.SRC_NET: logdir + 'net.tmp'}
+    sizes = [os.path.getsize(p) for p in files.values() if os.path.isfile(p)]
+    K = max(1, max([-(-sz // int(segment_bytes)) for sz in sizes] or [1]))
+    if K == 1:
+        return sofa_preprocess(cfg, engine=engine)
+    state = {'flags': {}, 'counts': []}
+    # ---- pass 1: file-level dtype flags of the gpu and packet sources (parse only)
+    time_base = hl.read_time_base(logdir, cfg.cpu_time_offset)
+    for kind in (hl.SRC_NET, hl.SRC_GPU):
+        path = files[kind]
+        if not os.path.isfile(path) or os.path.getsize(path) == 0:
+            continue
+        if kind == hl.SRC_GPU and not glob.glob(logdir + "gputrace*[0-9].nvvp"):
+            continue
+        data_off, p = 0, hl.base_params(kind, time_base, cfg.absolute_timestamp, 0.0)
+        if kind == hl.SRC_GPU:
+            with open(path, 'rb') as f:
+                hdr = hl.gpu_header(f.read(1 << 16))
+            if hdr is None:
+                continue
+            upd, data_off = hdr
+            upd.pop('t_base')
+            p.update(upd)
+        fl = 0
+        for i in range(K):
+            text, off = SegmentIO(i, K, state).read(path, data_off)
+            fl |= engine.load(kind, text, p, off)[1]
+        state['flags'][kind] = fl
+    # ---- pass 2: every segment through the ordinary preprocess
+    for i in range(K):
+        sofa_preprocess(cfg, engine=engine, io=SegmentIO(i, K, state))

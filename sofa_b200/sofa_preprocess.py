@@ -265,6 +265,15 @@ def sofa_preprocess(cfg, engine=None, io=None):
         from .engine import CudaEngine
         engine = CudaEngine(int(os.environ.get('SOFA_B200_DEVICE', os.environ.get('LOCAL_RANK', 0))))
     try:
+        if io is None:
+            # bounded device memory: a source larger than the segment budget is walked in newline-aligned segments
+            # (sofa_b200.sharded.sofa_preprocess_segmented); text + columns + outputs of a segment are ~5x its text
+            budget = int(os.environ.get('SOFA_B200_SEGMENT_BYTES', 16 << 30))
+            big = [fn for fn in ('perf.script', 'gputrace.tmp', 'net.tmp')
+                   if os.path.isfile(cfg.logdir + fn) and os.path.getsize(cfg.logdir + fn) > budget]
+            if big and int(cfg.plot_ratio) == 1 and not getattr(cfg, 'cuda_api_tracing', False):
+                from .sharded import sofa_preprocess_segmented
+                return sofa_preprocess_segmented(cfg, engine, budget)
         return _preprocess(cfg, engine, io or PlainIO())
     finally:
         if own_engine:

@@ -802,3 +802,56 @@ def test_sharded_trace_two_gpus(tmp_path):
     assert [n for n, _ in feats] == [n for n, _ in got]
     for (n, v), (_, w) in zip(feats, got):
         assert float(v) == float(w) or (v != v and w != w), (n, v, w)
+
+
+def test_segmented_preprocess_on_device(tmp_path, monkeypatch):
+    """SOFA_B200_SEGMENT_BYTES smaller than the sources: sofa_preprocess walks them in segments (bounded device memory)
+    and writes the same bytes as the one-piece run."""
+    import shutil
+    a = os.path.join(str(tmp_path), "whole") + "/"
+    b = os.path.join(str(tmp_path), "segmented") + "/"
+    synth.make_logdir(a, seed=717, n_perf=40000, n_gpu=30000, n_net=12000, non_ip_pct=1)
+    synth.write_side_raw(a, 717, n_samples=30, n_cores=2, n_gpus=2)
+    shutil.copytree(a, b)
+    sofa_preprocess(default_report_config(a, cpu_filters="idle:black,tensorflow:orange"))
+    monkeypatch.setenv("SOFA_B200_SEGMENT_BYTES", str(700000))
+    sofa_preprocess(default_report_config(b, cpu_filters="idle:black,tensorflow:orange"))
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "mpstat.csv", "nvsmi_trace.csv", "netstat.csv"):
+        _diff("segmented", fn, open(b + fn, "rb").read(), open(a + fn, "rb").read())
+    assert not [f for f in os.listdir(b) if ".shard" in f]
+
+
+@pytest.mark.parametrize("name", ["aisi_iters", "aisi_units"])
+def test_iter_profile_matches_reference(name, tmp_path):
+    """AISI per-iteration sums (sofa_aisi.py:21-59) on the device vs the unmodified reference's iter_profile on the same
+    slices (tests/golden/make_golden_aisi.py): every field equal as floats; from the raw rows and from gputrace.csv."""
+    import json
+    import shutil
+    from sofa_b200.engine import CudaEngine
+    from sofa_b200.sofa_analyze import load_gpu_source
+    from sofa_b200.sofa_aisi import iter_profile
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    meta = json.load(open(os.path.join(gdir, "case.json")))
+    a = os.path.join(str(tmp_path), "l") + "/"
+    os.makedirs(a)
+    for fn in os.listdir(gdir):
+        if fn != "case.json":
+            shutil.copy(os.path.join(gdir, fn), a + fn)
+    open(a + "gputrace1.nvvp", "w").close()
+    cfg = default_report_config(a)
+    sofa_preprocess(cfg)
+    for from_csv in (True, False):
+        if not from_csv:
+            os.remove(a + "gputrace.csv")
+        eng = CudaEngine(0)
+        try:
+            assert load_gpu_source(cfg, eng)
+            got = iter_profile(cfg, eng, meta["times"])
+        finally:
+            eng.close()
+        assert len(got) == len(meta["iterations"])
+        for i, (g, w) in enumerate(zip(got, meta["iterations"])):
+            assert (g is None) == (w is None), i
+            if w is not None:
+                for k in w:
+                    assert g[k] == w[k], (from_csv, i, k, g[k], w[k])

@@ -139,3 +139,29 @@ def test_two_shards_equal_one_shard_gloo():
                     with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
                         assert f.read() == g.read(), (case, fn)
             assert not [f for f in os.listdir(b) if ".shard" in f]
+
+
+def test_segmented_preprocess_equals_whole(tmp_path):
+    """sofa_preprocess_segmented (bounded device memory: the sources walked in K newline-aligned segments, outputs assembled
+    from part files) writes the same bytes as the one-piece run."""
+    import shutil
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, HERE)
+    from hostsim_engine import HostSimEngine
+    from helpers import demangle
+    from sofa_b200 import synth, sharded
+    from sofa_b200.sofa_config import default_report_config
+    import sofa_b200.sofa_preprocess as pre
+    pre.demangle = demangle
+    a = os.path.join(str(tmp_path), "whole") + "/"
+    b = os.path.join(str(tmp_path), "segmented") + "/"
+    synth.make_logdir(a, seed=51, n_perf=900, n_gpu=700, n_net=300, non_ip_pct=1)
+    synth.write_side_raw(a, 51, n_samples=20, n_cores=2, n_gpus=2)
+    shutil.copytree(a, b)
+    pre.sofa_preprocess(default_report_config(a, cpu_filters="idle:black,tensorflow:orange"), engine=HostSimEngine())
+    eng = HostSimEngine()
+    sharded.sofa_preprocess_segmented(default_report_config(b, cpu_filters="idle:black,tensorflow:orange"), eng, 20000)
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "mpstat.csv", "nvsmi_trace.csv", "netstat.csv"):
+        with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
+            assert f.read() == g.read(), fn
+    assert not [f for f in os.listdir(b) if ".shard" in f]
