@@ -39,8 +39,30 @@ MIX = (0.60, 0.35, 0.05)          # perf, gpu, net
 CPU_FILTERS = "idle:black,tensorflow:orange"
 GPU_KWS = ["CUDA_COPY_H2D", "CUDA_COPY_D2H", "CUDA_COPY_P2P", "_fw_", "_bw_", "AllReduceKernel"]
 CPU_KWS = ["idle", "tensorflow"]
-# dram__bytes_read+write / algorithmic bytes, measured by ncu --set full (profiles/r01_summary.md)
-NCU_TRAFFIC_RATIO = {"json_emit": 1.86, "csv_emit": 2.71, "parse": 1.66}
+# DRAM traffic of the hot kernels: bytes per row from this round's `ncu --set full` capture, committed as
+# profiles/r02_ncu_traffic.json (tools/ncu_summary.py traffic); no constants live here.
+NCU_TRAFFIC_FILE = os.path.join(REPO, "profiles", "r02_ncu_traffic.json")
+KIND_KERNELS = {"json_emit": "k_emit_fused<%d,1>", "csv_emit": "k_emit_fused<%d,0>", "parse": "k_parse_tma<%d>"}
+
+
+def ncu_traffic(kind, rows_per_source):
+    """dram read+write bytes of one step's launches of `kind` (main series / whole sources), from the committed capture:
+    sum over the three sources of (measured bytes per row) x rows.  None when there is no capture for this kind."""
+    try:
+        with open(NCU_TRAFFIC_FILE) as f:
+            cap = json.load(f)["kernels"]
+    except Exception:
+        return None
+    pat = KIND_KERNELS.get(kind)
+    if pat is None:
+        return None
+    total = 0.0
+    for src, rows in enumerate(rows_per_source):
+        k = cap.get(pat % src) or (cap.get("k_parse<%d>" % src) if kind == "parse" else None)
+        if k is None:
+            return None
+        total += k["dram_bytes_per_row"] * rows
+    return total
 TIME_BASE = 1600000000.0
 PERF_T_OFFSET = 1600000000.25 - 4999.5
 
@@ -467,8 +489,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None,
-                     "traffic": NCU_TRAFFIC_RATIO.get(dname, 0) * dbytes / max(dl, 1) or None,
-                     "traffic_note": "dram read+write of this kernel = ratio x algorithmic bytes, ratio from the ncu --set full capture summarised in profiles/r01_summary.md",
+                     "traffic": (ncu_traffic(dname, wl.n) / max(dl, 1)) if ncu_traffic(dname, wl.n) else None,
+                     "traffic_note": "dram read+write per launch: bytes per row of each source measured by this round's ncu --set full capture (profiles/r02_ncu_traffic.json) x rows of this run / launches",
                      "algorithmic_bytes_per_launch": dbytes / max(dl, 1), "launch_ms": dms / max(dl, 1),
                      "peak_source": peak_src,
                      "all_kernels_ms": {k: round(v[1], 3) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][1])},
@@ -860,25 +882,36 @@ def run_reference(args):
         return
     cores = mp.cpu_count()
     n = args.cpu_sample
-    work = tempfile.mkdtemp(prefix="sofa_ref_")
-    logdir = os.path.join(work, "sofalog") + "/"
-    os.makedirs(logdir)
-    write_sample_logdir(logdir, n, SEED)
-    for _ in range(args.warmup):
-        oracle_pass(logdir, cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_pass(logdir, cores)
-    dt = (time.perf_counter() - t0) / args.steps
     import shutil
-    shutil.rmtree(work, ignore_errors=True)
-    v = n / dt
-    sample = "each step = first %d events of the mixed trace (60/35/5) through the CPU port of the reference path" % n
+    # Two sample sizes: the rate is the MARGINAL one, (n2 - n1) events / (t2 - t1), so that the fixed costs of a pass (pool
+    # start-up, imports, small-frame overheads) do not pass for per-event cost; both raw timings are reported.
+    n1, n2 = max(1000, n // 3), n
+    if n1 >= n2:
+        n1 = max(1, n2 // 2)
+    times = {}
+    for nn in (n1, n2):
+        work = tempfile.mkdtemp(prefix="sofa_ref_")
+        logdir = os.path.join(work, "sofalog") + "/"
+        os.makedirs(logdir)
+        write_sample_logdir(logdir, nn, SEED)
+        for _ in range(min(args.warmup, 1)):
+            oracle_pass(logdir, cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle_pass(logdir, cores)
+        times[nn] = (time.perf_counter() - t0) / args.steps
+        shutil.rmtree(work, ignore_errors=True)
+    dt = times[n2]
+    marginal = (n2 - n1) / max(1e-9, times[n2] - times[n1]) if times[n2] > times[n1] else n2 / dt
+    v = marginal
+    sample = ("CPU port of the reference path on the first %d and %d events of the mixed trace (60/35/5): %.2f s and %.2f s per pass; "
+              "value = marginal rate between the two sizes (whole-pass rate at %d events: %.0f events/s)"
+              % (n1, n2, times[n1], times[n2], n2, n2 / dt))
     line = {"impl": "reference", "metric": "trace events/s (preprocess+analyze)", "value": v, "unit": "events/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64/int64", "data": "synthetic",
             "config": {"workload": "100 M-event mixed perf+CUPTI+tcpdump trace with cpu_filters/gpu_filters tagging (BASELINE configs[2])",
-                       "sample": sample, "cpu_filters": CPU_FILTERS, "gpu_filters": GPU_KWS, "plot_ratio": 1},
+                       "sample": sample, "same_config": False, "cpu_filters": CPU_FILTERS, "gpu_filters": GPU_KWS, "plot_ratio": 1},
             "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -892,7 +925,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=100000000, help="events per GPU (default: BASELINE configs[2])")
-    ap.add_argument("--cpu-sample", type=int, default=150000, help="events in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=300000, help="events in the CPU baseline sample (the parity sample of the default arm; the larger of the two sizes of --impl reference)")
     ap.add_argument("--entry-events", type=int, default=10000000,
                     help="events of the logdir that goes through sofa_preprocess + sofa_analyze themselves (e2e_entrypoints; 0 = skip)")
     ap.add_argument("--strong", type=int, default=1,

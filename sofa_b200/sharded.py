@@ -196,7 +196,7 @@ def gather_source(eng, kind, dist, device, dst=0):
     import torch
     rank, world = dist.get_rank(), dist.get_world_size()
     d = eng.shard_export(kind)
-    own_text = d.text_bytes - (d.data_off if rank == 0 else 0)            # rank 0's buffer starts with the header rows
+    own_text = d.text_bytes            # rank 0's text keeps its header rows in front: the rows' line offsets count from the buffer start
     t = torch.tensor([d.n_rows, own_text], dtype=torch.int64, device=device)
     sizes = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(sizes, t)
@@ -210,7 +210,7 @@ def gather_source(eng, kind, dist, device, dst=0):
         reqs = []
         row0, text0 = 0, 0
         for r in range(world):
-            parts = [(g.text + text0, texts[r], d.text + (d.data_off if rank == 0 else 0))]
+            parts = [(g.text + text0, texts[r], d.text)]
             for q in range(ncols):
                 parts.append((g.cols[q] + row0 * g.col_elem[q], rows[r] * g.col_elem[q], d.cols[q]))
             for dptr, nb, sptr in parts:

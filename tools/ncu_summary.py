@@ -2,6 +2,7 @@
 """Summaries of ncu exports (how profiles/r01_summary.md's tables were produced).
 
   launches  FILE.csv[.gz]            aggregate a `--metrics gpu__time_duration.sum --csv` launch list per kernel
+  traffic   RAW.csv EVENTS           per-kernel DRAM bytes / bytes per row / lanes per instruction of a --set full capture, as JSON
   source    RAW.csv SRC.csv[.gz] [N] key metrics of `ncu -i rep --page raw --csv` plus the N hottest source lines of
                                      `ncu -i rep --page source --csv --print-source cuda,sass`: share of executed
                                      warp instructions, share of stall samples, average active lanes per line
@@ -86,9 +87,48 @@ def source(raw_path, src_path, top=24):
                                                                        kk[0], kk[1], text[kk]))
 
 
+def traffic(raw_path, events):
+    """`ncu -i rep --page raw --csv` of one `tools/profile_step.py EVENTS 1` capture of the hot kernels ->
+    JSON {kernel: dram bytes, bytes per row, duration, lanes per instruction, issue-active %}: what bench.py's
+    roofline.traffic is computed from (profiles/r02_ncu_traffic.json).  Rows per source follow bench.py's 60/35/5 mix."""
+    import json
+    rows_of = {"0": int(events * 0.60), "1": int(events * 0.35), "2": events - int(events * 0.60) - int(events * 0.35)}
+    raw = list(csv.reader(_open(raw_path)))
+    h = raw[0]
+    col = {w: h.index(w) for w in RAW_KEYS if w in h}
+    out = {}
+    for r in raw[2:]:
+        name = r[col["Kernel Name"]]
+        m = re.search(r"(k_parse_tma|k_parse|k_emit_fused)<\(?(?:int\))?(\d)(?:, \(?(?:int\))?(\d))?>", name)
+        if not m:
+            continue
+        key = "%s<%s%s>" % (m.group(1), m.group(2), "," + m.group(3) if m.group(3) else "")
+        if key in out:                      # first launch of a kind = the main series (filter series come later)
+            continue
+
+        def num(k):
+            return float(r[col[k]].replace(",", "")) if k in col and r[col[k]] else None
+        units = raw[1]
+        rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
+        rd *= scale.get(units[col["dram__bytes_read.sum"]], 1.0)
+        wr *= scale.get(units[col["dram__bytes_write.sum"]], 1.0)
+        t = num("gpu__time_duration.sum") * {"us": 1e-6, "ns": 1e-9, "ms": 1e-3, "s": 1.0}.get(units[col["gpu__time_duration.sum"]], 1e-6)
+        nrows = rows_of[m.group(2)]
+        out[key] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes_per_row": (rd + wr) / nrows, "rows": nrows,
+                    "duration_s": t, "dram_GBps": (rd + wr) / t / 1e9,
+                    "lanes_per_instruction": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                    "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "registers": num("launch__registers_per_thread"), "warp_instructions": num("smsp__inst_executed.sum")}
+    print(json.dumps({"capture": "ncu --set full --clock-control none, tools/profile_step.py %d 1 (first launch of each kernel = main series)" % events,
+                      "events": events, "kernels": out}, indent=1))
+
+
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif len(sys.argv) >= 4 and sys.argv[1] == "traffic":
+        traffic(sys.argv[2], int(sys.argv[3]))
     elif len(sys.argv) >= 4 and sys.argv[1] == "source":
         source(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 24)
     else:
