@@ -339,6 +339,9 @@ void launch_parse(int tpl_kind, unsigned grid, size_t smem, cudaStream_t st, con
                   uint32_t tile_bytes, uint32_t max_lines, const uint64_t* tile_row_base, const sofa::IngestCfg& cfg,
                   const sofa::AllCols& cols, unsigned long long* err);
 int csv_mask_newlines(sofa_ctx* c, char* text, uint64_t begin, uint64_t end, uint64_t* counts, uint64_t nchunks, int (*scan)(sofa_ctx*, uint64_t*, uint64_t));
+void launch_parse_csv(int kind, unsigned grid, size_t smem, cudaStream_t st, const char* text, uint64_t begin, uint64_t end,
+                      uint32_t tile_bytes, uint32_t max_lines, const uint64_t* tile_row_base, const sofa::IngestCfg& cfg,
+                      const sofa::AllCols& cols, unsigned long long* err);
 int parse_tma_occupancy(int kind, size_t smem);
 void launch_parse_tma(int kind, unsigned grid, size_t smem, cudaStream_t st, const char* text, uint64_t begin, uint64_t end,
                       uint32_t tile_bytes, uint32_t max_lines, uint64_t ntiles, const uint64_t* tile_row_base, const sofa::IngestCfg& cfg,

@@ -44,6 +44,20 @@ void inst_parse_tma_net(unsigned, size_t, cudaStream_t, const char*, uint64_t, u
 int inst_parse_tma_attr_net(void);
 int inst_parse_tma_occ_net(size_t);
 
+void inst_parse_csv_perf(unsigned, size_t, cudaStream_t, const char*, uint64_t, uint64_t, uint32_t, uint32_t, const uint64_t*, const IngestCfg&, const AllCols&, unsigned long long*);
+int inst_parse_csv_attr_perf(void);
+void inst_parse_csv_gpu(unsigned, size_t, cudaStream_t, const char*, uint64_t, uint64_t, uint32_t, uint32_t, const uint64_t*, const IngestCfg&, const AllCols&, unsigned long long*);
+int inst_parse_csv_attr_gpu(void);
+void inst_parse_csv_net(unsigned, size_t, cudaStream_t, const char*, uint64_t, uint64_t, uint32_t, uint32_t, const uint64_t*, const IngestCfg&, const AllCols&, unsigned long long*);
+int inst_parse_csv_attr_net(void);
+void launch_parse_csv(int kind, unsigned grid, size_t smem, cudaStream_t st, const char* text, uint64_t begin, uint64_t end,
+                      uint32_t tile_bytes, uint32_t max_lines, const uint64_t* tile_row_base, const IngestCfg& cfg,
+                      const AllCols& cols, unsigned long long* err) {
+    if (kind == SRC_PERF) inst_parse_csv_perf(grid, smem, st, text, begin, end, tile_bytes, max_lines, tile_row_base, cfg, cols, err);
+    else if (kind == SRC_GPU) inst_parse_csv_gpu(grid, smem, st, text, begin, end, tile_bytes, max_lines, tile_row_base, cfg, cols, err);
+    else inst_parse_csv_net(grid, smem, st, text, begin, end, tile_bytes, max_lines, tile_row_base, cfg, cols, err);
+}
+
 int parse_tma_occupancy(int kind, size_t smem) {
     return kind == SRC_PERF ? inst_parse_tma_occ_perf(smem) : (kind == SRC_GPU ? inst_parse_tma_occ_gpu(smem) : inst_parse_tma_occ_net(smem));
 }
@@ -113,6 +127,9 @@ int set_kernel_attrs(void) {
     if ((e = inst_emit_attr_sideout_json())) return e;
     if ((e = inst_emit_attr_sideout_aux())) return e;
     if ((e = set_gather_attr())) return e;
+    if ((e = inst_parse_csv_attr_perf())) return e;
+    if ((e = inst_parse_csv_attr_gpu())) return e;
+    if ((e = inst_parse_csv_attr_net())) return e;
     if ((e = inst_parse_tma_attr_perf())) return e;
     if ((e = inst_parse_tma_attr_gpu())) return e;
     if ((e = inst_parse_tma_attr_net())) return e;

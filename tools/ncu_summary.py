@@ -99,10 +99,12 @@ def traffic(raw_path, events):
     out = {}
     for r in raw[2:]:
         name = r[col["Kernel Name"]]
-        m = re.search(r"(k_parse_tma|k_parse|k_emit_fused)<\(?(?:int\))?(\d)(?:, \(?(?:int\))?(\d))?>", name)
+        m = re.search(r"(k_parse_tma|k_parse|k_emit_fused)<\(?(?:int\))?(\d)(?:, \(?(?:(?:int|bool)\))?(\w+))?>", name)
         if not m:
             continue
-        key = "%s<%s%s>" % (m.group(1), m.group(2), "," + m.group(3) if m.group(3) else "")
+        if m.group(1) == "k_parse" and m.group(3) in ("1", "true"):
+            continue                        # trace-CSV instantiation
+        key = "%s<%s%s>" % (m.group(1), m.group(2), "," + m.group(3) if (m.group(3) and m.group(1) == "k_emit_fused") else "")
         if key in out:                      # first launch of a kind = the main series (filter series come later)
             continue
 
