@@ -104,6 +104,8 @@ def traffic(raw_path, events):
             continue
         if m.group(1) == "k_parse" and m.group(3) in ("1", "true"):
             continue                        # trace-CSV instantiation
+        if m.group(2) not in rows_of:
+            continue                        # side-file sources
         key = "%s<%s%s>" % (m.group(1), m.group(2), "," + m.group(3) if (m.group(3) and m.group(1) == "k_emit_fused") else "")
         if key in out:                      # first launch of a kind = the main series (filter series come later)
             continue
