@@ -805,7 +805,10 @@ def product_pass(logdir, device):
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
         sofa_preprocess(cfg)
+        t1 = time.perf_counter()
         sofa_analyze(cfg)
+    product_pass.last = dict({k: round(v, 3) for k, v in getattr(cfg, "_timing", {}).items()},
+                             preprocess_total=round(t1 - t0, 3), analyze_total=round(time.perf_counter() - t1, 3))
     return time.perf_counter() - t0
 
 
@@ -823,7 +826,7 @@ def entrypoints_run(wl, n_events, device):
         dt = product_pass(logdir, device)
         out_bytes = sum(os.path.getsize(logdir + f) for f in os.listdir(logdir)) - in_bytes
         return {"events": n_events, "seconds": round(dt, 3), "events_per_s": n_events / dt, "input_bytes": in_bytes,
-                "output_bytes": out_bytes, "where": base,
+                "output_bytes": out_bytes, "where": base, "phases_s": getattr(product_pass, "last", None),
                 "what": "sofa_preprocess(cfg) + sofa_analyze(cfg): file reads, H2D, kernels, D2H, file writes, demangling, Python"}
     finally:
         shutil.rmtree(work, ignore_errors=True)

@@ -227,6 +227,36 @@ def _side_sources(cfg, eng, logdir):
     return out
 
 
+class _Timing(dict):
+    """wall-clock seconds per phase of one sofa_preprocess call (cfg._timing; reported by bench.py's e2e_entrypoints)"""
+    def add(self, key, t0):
+        import time
+        self[key] = self.get(key, 0.0) + (time.perf_counter() - t0)
+
+
+def _timed_engine(eng, tm):
+    """wrap the engine's bulk calls with the phase timers"""
+    import time
+
+    class T:
+        def __getattr__(self, name):
+            f = getattr(eng, name)
+            phase = {'load': 'upload+parse', 'csv': 'csv emit+fetch', 'json': 'json emit+fetch', 'json_series': 'json emit+fetch',
+                     'set_filters': 'filters', 'viz_mangled': 'viz names', 'set_demangled': 'viz names',
+                     'side_preprocess': 'side files', 'side_csv': 'side files', 'side_json': 'side files', 'side_aux': 'side files'}.get(name)
+            if phase is None or not callable(f):
+                return f
+
+            def g(*a, **k):
+                t0 = time.perf_counter()
+                try:
+                    return f(*a, **k)
+                finally:
+                    tm.add(phase, t0)
+            return g
+    return T()
+
+
 class PlainIO:
     """File access of an unsharded run.  sofa_b200.sharded.ShardIO has the same interface for one logical trace split
     over several ranks (byte ranges in, part files out, dtype flags all-reduced)."""
@@ -284,6 +314,9 @@ def sofa_preprocess(cfg, engine=None, io=None):
 
 
 def _preprocess(cfg, eng, io):
+    import time
+    tm = cfg._timing = _Timing()
+    eng = _timed_engine(eng, tm)
     cfg.time_base = 0
     logdir = cfg.logdir
     with open(logdir + 'misc.txt', 'r') as f:
@@ -433,7 +466,10 @@ def _preprocess(cfg, eng, io):
             body = eng.csv(SRC_PERF, 1)
             io.write_csv(logdir + 'cputrace.csv', CSV_HEADER, body)
             mangled = eng.viz_mangled(ratio)                  # unique _Z... viz names
-            eng.set_demangled([(m, demangle(m)) for m in mangled])
+            t0 = time.perf_counter()
+            pairs = [(m, demangle(m)) for m in mangled]
+            tm.add('demangle (host)', t0)
+            eng.set_demangled(pairs)
             kws = [flt.keyword for flt in cfg.cpu_filters]
             for kw in kws:
                 _check_keyword(kw)
@@ -481,5 +517,7 @@ def _preprocess(cfg, eng, io):
     series.extend(gpu_filter_series)
     if api_series is not None:
         series.append(api_series)
+    t0 = time.perf_counter()
     io.finish(series, logdir + 'report.js')
+    tm.add('write report.js', t0)
     print_progress(cfg, "Export Overhead Dynamics JSON File of CPU, Network and GPU traces -- end")
