@@ -802,13 +802,18 @@ def product_pass(logdir, device):
     os.environ["SOFA_B200_DEVICE"] = str(device)
     cfg = default_report_config(logdir, cpu_filters=CPU_FILTERS)
     cfg.keep_engine = True
+    from sofa_b200.engine import CudaEngine
     t0 = time.perf_counter()
+    eng = CudaEngine(device)                     # context + module load are part of what a user waits for
+    t_create = time.perf_counter() - t0
     with contextlib.redirect_stdout(io.StringIO()):
-        sofa_preprocess(cfg)
+        sofa_preprocess(cfg, engine=eng)
+        cfg._sofa_b200_engine = eng              # as `sofa report` does: analyze the resident rows, then close
         t1 = time.perf_counter()
         sofa_analyze(cfg)
     product_pass.last = dict({k: round(v, 3) for k, v in getattr(cfg, "_timing", {}).items()},
-                             preprocess_total=round(t1 - t0, 3), analyze_total=round(time.perf_counter() - t1, 3))
+                             engine_create=round(t_create, 3), preprocess_total=round(t1 - t0 - t_create, 3),
+                             analyze_total=round(time.perf_counter() - t1, 3))
     return time.perf_counter() - t0
 
 

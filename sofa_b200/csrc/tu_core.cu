@@ -450,7 +450,8 @@ int sofa_b200_shard_reserve(sofa_ctx* c, int k, uint64_t total_rows, uint64_t to
     memset(out, 0, sizeof *out);
     int slots[16]; uint32_t elem[16];
     out->n_cols = shard_layout(k, slots, elem);
-    for (int i = 0; i <= out->n_cols; i++) c->gather[i].release();
+    // (the buffers are kept between calls: after a commit they hold the previous shard's storage, which the next parse of
+    //  this source reuses through the swap - a steady-state step allocates nothing)
     uint64_t m = total_rows ? total_rows : 1;
     ENSURE(c->gather[0], total_text + 64);
     for (int i = 0; i < out->n_cols; i++) ENSURE(c->gather[1 + i], m * elem[i] + 64);
@@ -484,7 +485,6 @@ int sofa_b200_shard_commit(sofa_ctx* c, int k, int32_t nshards, const uint64_t* 
     CK(cudaGetLastError());
     std::swap(s.text, c->gather[0]);
     for (int q = 0; q < nc; q++) std::swap(s.cols[slots[q]], c->gather[1 + q]);
-    for (int i = 0; i <= nc; i++) c->gather[i].release();
     s.n_rows = rows; s.nbytes = text; s.data_off = 0; s.parsed = true; s.viz_ready = false; s.mask_stride = 0; s.nkw = 0; s.gather_ok = false;
     return 0;
 }

@@ -26,6 +26,7 @@ class ShardIO:
         self.rank, self.world, self.dist, self.device = rank, world, dist, device
         self.csv_parts = []            # (path, header) in emit order
         self.rows = {}
+        self.tm = None
 
     # ---- input: newline-aligned byte ranges
     def size(self, path):

@@ -261,6 +261,7 @@ class PlainIO:
     """File access of an unsharded run.  sofa_b200.sharded.ShardIO has the same interface for one logical trace split
     over several ranks (byte ranges in, part files out, dtype flags all-reduced)."""
     rank, world = 0, 1
+    tm = None
 
     def head(self, path, n):
         with open(path, 'rb') as f:
@@ -268,7 +269,13 @@ class PlainIO:
 
     def read(self, path, data_off=0):
         """(text of this rank's rows incl. the header on rank 0, offset of the first row in it)"""
-        return _read_bytes(path), data_off
+        import time
+        t0 = time.perf_counter()
+        try:
+            return _read_bytes(path), data_off
+        finally:
+            if self.tm is not None:
+                self.tm.add('read files', t0)
 
     def size(self, path):
         return os.path.getsize(path)
@@ -277,9 +284,13 @@ class PlainIO:
         pass
 
     def write_csv(self, path, header, body):
+        import time
+        t0 = time.perf_counter()
         with open(path, 'wb') as f:
             f.write(header)
             f.write(memoryview(body))
+        if self.tm is not None:
+            self.tm.add('write csv', t0)
 
     def series(self, s):
         return s
@@ -317,6 +328,7 @@ def _preprocess(cfg, eng, io):
     import time
     tm = cfg._timing = _Timing()
     eng = _timed_engine(eng, tm)
+    io.tm = tm
     cfg.time_base = 0
     logdir = cfg.logdir
     with open(logdir + 'misc.txt', 'r') as f:
@@ -365,7 +377,8 @@ def _preprocess(cfg, eng, io):
                 subprocess.check_call(["tcpdump", "-q", "-n", "-tt", "-r", "%s/sofa.pcap" % logdir],
                                       stdout=f, stderr=subprocess.DEVNULL)
         text, _ = io.read(logdir + 'net.tmp')
-        print_info(cfg, "Length of net_traces = %d" % text.count(b'\n'))
+        if cfg.verbose:
+            print_info(cfg, "Length of net_traces = %d" % text.count(b'\n'))
         if io.size(logdir + 'net.tmp') > 0:
             p = hl.base_params(SRC_NET, cfg.time_base, cfg.absolute_timestamp, 0.0)
             eng.load(SRC_NET, text, p)
@@ -457,7 +470,8 @@ def _preprocess(cfg, eng, io):
         if not os.path.isfile(logdir + 'perf.script'):
             raise IOError('perf.script')
         text, _ = io.read(logdir + 'perf.script')
-        print_info(cfg, "Length of cpu_traces = %d" % text.count(b'\n'))
+        if cfg.verbose:
+            print_info(cfg, "Length of cpu_traces = %d" % text.count(b'\n'))
         if io.size(logdir + 'perf.script') > 0:
             p = hl.base_params(SRC_PERF, cfg.time_base, cfg.absolute_timestamp, t_offset)
             p['perf_has_cycles'] = 1 if cfg.perf_events.find('cycles') != -1 else 0
