@@ -129,11 +129,10 @@ int sofa_b200_set_demangled(sofa_ctx*, uint32_t n, const char* mangled, const ui
 int sofa_b200_emit_json(sofa_ctx*, int src, uint32_t stride, int32_t filter_idx, uint64_t* nbytes,
                         uint64_t* n_records);
 
-/* Main series of a source plus its keyword filters in ONE formatting pass: the keywords are matched on each name
- * while the record is sized (same semantics as sofa_b200_set_filters: counts[k] = matching rows, masks kept for
- * sofa_b200_emit_json(filter_idx)), the records go to output buffer 1, and the byte offset of every record is
- * kept with the output so that the following sofa_b200_emit_json(src, stride, k) calls GATHER series k from this
- * output instead of formatting the rows again (a filter series holds the very same record bytes,
+/* Main series of a source plus its keyword filters: sofa_b200_set_filters (counts[k] = matching rows, masks kept
+ * for sofa_b200_emit_json(filter_idx)), then the records of the main series go to output buffer 1 and the byte
+ * offset of every record is kept with that output, so that the following sofa_b200_emit_json(src, stride, k) calls
+ * GATHER series k from it instead of formatting the rows again (a filter series holds the very same record bytes,
  * sofa_preprocess.py:1446-1452, 1819-1827).  Valid when the filters run on the frame of the main series: always
  * for the cpu filters, for the gpu filters when plot_ratio == 1. */
 int sofa_b200_emit_json_series(sofa_ctx*, int src, uint32_t stride, int32_t nkw, const char* const* keywords,

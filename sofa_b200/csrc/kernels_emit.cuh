@@ -255,12 +255,10 @@ struct FusedArgs {
     unsigned long long* total;
     unsigned int* overflow;
     uint32_t slot_bytes;           // dynamic shared memory available for slots
-    // report.js main series only: keyword filters matched on the name while it is being sized (one pass instead of
-    // a separate k_filter launch) and the byte offset of every record, so that the filter series can be gathered
-    // from this output instead of being formatted again (their records are the same bytes)
-    const PackedFilter* pf;        // null: no fused matching
-    uint8_t* mask_out;             // per candidate: bit k = keyword k occurs in the name
-    unsigned long long* kwcounts;  // [8] hit counters
+    // report.js main series only: the byte offset of every record, so that the filter series can be gathered from
+    // this output instead of being formatted again (their records are the same bytes).  (Matching the filter keywords
+    // inside this kernel as well was measured: 13.4 ms of extra time in here against 10.9 ms for the separate
+    // k_filter pass - 80 instead of 72 registers - so the masks come from k_filter.)
     unsigned long long* rec_off;   // [ncand + 1] byte offset of each record in `out`; null: not recorded
 };
 
@@ -315,36 +313,14 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
     // ---- phase 1: digit plans + exact row length (every float is analysed once)
     typename RowPlanOf<FMT>::type plan;
     plan.len = 0;
-    __shared__ PackedFilter spf;                 // JSON main series with fused keyword matching only (block-uniform a.pf)
-    if constexpr (FMT == FMT_JSON) {
-        if (a.pf) {
-            const uint32_t* g = reinterpret_cast<const uint32_t*>(a.pf);
-            uint32_t* sp = reinterpret_cast<uint32_t*>(&spf);
-            for (uint32_t i = threadIdx.x; i < sizeof(PackedFilter) / 4; i += blockDim.x) sp[i] = g[i];
-            __syncthreads();
-        }
-    }
-    uint32_t hit = 0;
     if (sel) {
         with_row<KIND, FMT == FMT_JSON>(src, row, c, [&](const RowVals& v, const auto& ng) {
             if constexpr (FMT == FMT_CSV) plan = csv_row_plan(v, a.fmask, ng);
             else if constexpr (FMT == FMT_COMM) plan = comm_row_plan(c, v, a.fmask);
             else if constexpr (FMT == FMT_AUX) plan = aux_row_plan(ng.r.ts, ng.r.f1, ng.r.f2);
-            else {
-                plan = json_row_plan(v, a.fmask, ng);
-                if (a.pf && v.valid) { PackedMatchSink ms(&spf); ng.gen(ms); hit = ms.hits(); }
-            }
+            else plan = json_row_plan(v, a.fmask, ng);
         });
         if (plan.len < 0) { report_error(a.err, row, plan.len == -2 ? E_UTF8 : E_FORMAT); plan.len = 0; }
-    }
-    if constexpr (FMT == FMT_JSON) {
-        if (a.pf) {
-            if (inr) a.mask_out[c] = (uint8_t)hit;
-            for (int k = 0; k < spf.nk; k++) {
-                unsigned bl = __ballot_sync(0xffffffffu, (hit >> k) & 1);
-                if (lane_id() == 0 && bl) atomicAdd(&a.kwcounts[k], (unsigned long long)__popc(bl));
-            }
-        }
     }
     const uint32_t len = (uint32_t)plan.len;
     uint32_t total, cnt_total;

@@ -4,7 +4,7 @@
 #include "kernels_gather.cuh"
 
 // report.js main series with fused keyword matching / record offsets (see FusedArgs)
-struct JsonFuse { const PackedFilter* pf; uint8_t* mask_out; unsigned long long* rec_off; bool keep_output; };
+struct JsonFuse { unsigned long long* rec_off; bool keep_output; };
 
 template <int FMT>
 static int emit_fused_t(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask, int bit, uint32_t fmask,
@@ -80,7 +80,6 @@ static int emit_fused_t(sofa_ctx* c, int k, uint32_t stride, const uint8_t* mask
         a.state = c->tiles.as<unsigned long long>(); a.ticket = c->d_flags + 4;
         a.err = c->d_err; a.count = c->d_err + 1; a.total = c->d_err + 11; a.overflow = c->d_flags + 2;
         a.slot_bytes = slot_bytes;
-        a.pf = jf ? jf->pf : nullptr; a.mask_out = jf ? jf->mask_out : nullptr; a.kwcounts = c->d_err + 2;
         a.rec_off = jf ? jf->rec_off : nullptr;
         int kk = FMT == FMT_JSON ? K_JSON_WRITE : K_CSV_WRITE;
         unsigned g = (unsigned)nblocks;
@@ -183,39 +182,22 @@ int sofa_b200_emit_json_series(sofa_ctx* c, int k, uint32_t stride, int32_t nkw,
     if (k == SRC_PERF && !(s.viz_ready && s.viz_stride == stride))
         FAIL(SOFA_ERR_STATE, "emit_json_series(perf): call viz_mangled + set_demangled for this stride first");
     s.gather_ok = false;
-    FilterTable ft;
-    memset(&ft, 0, sizeof ft);
-    size_t lens[8] = {0};
     for (int i = 0; i < nkw; i++) {
-        lens[i] = strlen(kws[i]);
-        if (lens[i] == 0 || lens[i] > 32) FAIL(SOFA_ERR_ARG, "emit_json_series: keyword length must be 1..32 bytes");
+        size_t l = strlen(kws[i]);
+        if (l == 0 || l > 32) FAIL(SOFA_ERR_ARG, "emit_json_series: keyword length must be 1..32 bytes");
     }
-    filter_table_build(&ft, nkw, kws, lens);
-    PackedFilter pf;
-    if (nkw == 0 || !packed_filter_from(ft, &pf)) {
-        // keywords longer than 64 bytes in total: unfused path (main series, then set_filters + formatted filter series)
-        r = sofa_b200_emit_json(c, k, stride, -1, nbytes, nrec);
-        if (r || nkw == 0) return r;
-        return sofa_b200_set_filters(c, k, stride, nkw, kws, counts);
-    }
+    if (nkw == 0) return sofa_b200_emit_json(c, k, stride, -1, nbytes, nrec);
+    // masks + hit counts of every keyword in one k_filter pass over the names (sofa_b200_set_filters), then the main
+    // series with the byte offset of every record kept
+    r = sofa_b200_set_filters(c, k, stride, nkw, kws, counts); if (r) return r;
     uint64_t ncand = cdiv(s.n_rows, stride);
-    ENSURE(c->ftable, sizeof(FilterTable));
-    ENSURE(s.mask, ncand + 16);
     ENSURE(s.rec_off, (ncand + 2) * 8);
-    CK_S(small_h2d(c, c->ftable.p, &pf, sizeof pf));
-    CK_S(stream_sync(c));
     uint32_t fmask = 0;
     r = fmask_for(c, k, stride, &fmask); if (r) return r;
-    JsonFuse jf{c->ftable.as<PackedFilter>(), s.mask.as<uint8_t>(), s.rec_off.as<unsigned long long>(), true};
+    JsonFuse jf{s.rec_off.as<unsigned long long>(), true};
     uint64_t nb = 0, nr = 0;
-    unsigned long long cn[8] = {0};
     r = emit_fused_t<FMT_JSON>(c, k, stride, nullptr, 0, fmask, 1, ncand, &nb, &nr, nullptr, &jf);
     if (r) return r;
-    CK_S(small_d2h(c, cn, c->d_err + 2, 64));
-    CK_S(stream_sync(c));
-    if (counts) for (int i = 0; i < nkw; i++) counts[i] = cn[i];
-    for (int i = 0; i < 8; i++) s.filter_counts[i] = i < nkw ? cn[i] : 0;
-    s.mask_stride = stride; s.nkw = nkw;
     s.gather_ok = nr > 0; s.gather_stride = stride; s.gather_total = (double)nb;
     if (nbytes) *nbytes = nb >= 2 ? nb - 2 : 0;
     if (nrec) *nrec = nr;
