@@ -67,6 +67,32 @@ __device__ __forceinline__ uint64_t block_excl_scan64(uint64_t v, uint64_t* tota
     return res;
 }
 
+// ---- bulk-asynchronous copies (TMA engine, sm_90+): global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (16-byte aligned addresses, size a multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+
 // first failing record wins: (row << 8) | code, smaller row first
 __device__ __forceinline__ void report_error(unsigned long long* err, uint64_t row, int code) {
     atomicMin(err, (unsigned long long)((row << 8) | (uint64_t)(code & 0xff)));
@@ -87,6 +113,29 @@ __device__ __forceinline__ void flush_staged(const unsigned char* stage, char* g
     for (uint32_t i = (v0 >> 4) + threadIdx.x; i < (v1 >> 4); i += blockDim.x) g4[i] = s4[i];
     uint32_t t0 = v1 > v0 ? v1 : v0;
     for (uint32_t i = t0 + threadIdx.x; i < hi; i += blockDim.x) g[i] = (char)stage[i];
+}
+
+// Same, with the 16-byte aligned interior written by ONE bulk-asynchronous copy (shared -> global, TMA engine) issued by
+// thread 0 instead of 128-bit stores from every thread: the block's warps spend no issue slots on the flush.  The
+// generic-proxy writes that filled the image are made visible to the async proxy first (fence.proxy.async), and thread 0
+// waits until the engine has READ the image before the block may retire.  All threads must call; ends with a barrier.
+__device__ __forceinline__ void flush_staged_bulk(const unsigned char* stage, char* gout_base, uint64_t tile_off, uint32_t total) {
+    uint32_t a = (uint32_t)(tile_off & 15);
+    char* g = gout_base + (tile_off - a);                 // 16-aligned, g[i] <-> stage[i]
+    uint32_t lo = a, hi = a + total;
+    uint32_t v0 = (lo + 15) & ~15u, v1 = hi & ~15u;
+    if (v1 < v0) { v0 = hi; v1 = hi; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0 && v1 > v0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(g + v0), "r"(smem_u32(stage + v0)), "r"(v1 - v0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    for (uint32_t i = lo + threadIdx.x; i < v0 && i < hi; i += blockDim.x) g[i] = (char)stage[i];
+    uint32_t t0 = v1 > v0 ? v1 : v0;
+    for (uint32_t i = t0 + threadIdx.x; i < hi; i += blockDim.x) g[i] = (char)stage[i];
+    if (threadIdx.x == 0 && v1 > v0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 }  // namespace sofa

@@ -386,9 +386,8 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_fused(SrcView src, FusedArgs 
             }
         });
     }
-    __syncthreads();
-    // ---- phase 4: 128-bit coalesced flush
-    if (staged && total) flush_staged(stage, a.out, base, total);
+    // ---- phase 4: the image goes out through one bulk-asynchronous store (block-uniform condition)
+    if (staged && total) flush_staged_bulk(stage, a.out, base, total);
 }
 
 

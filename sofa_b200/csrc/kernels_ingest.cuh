@@ -167,7 +167,10 @@ static __global__ void __launch_bounds__(1024) k_scan_add(uint64_t* a, uint64_t 
 
 // CSV = true: the text is a trace CSV (stand-alone `sofa analyze`); a separate instantiation so that the hot raw-log
 // kernels carry none of its code (one merged kernel cost 46 -> 52 ms per 100 M events)
-template <int KIND, bool CSV = false>
+// BULK: the tile is brought into shared memory by ONE cp.async.bulk issued by thread 0 (the copy engine moves the 24-32 KB
+// while no warp of the block spends issue slots on it; UBLKCP.S.G + SYNCS in SASS) instead of an LDG -> STS loop over all
+// threads; the block waits on the copy's mbarrier where it used to wait at the barrier after the loop.
+template <int KIND, bool CSV = false, bool BULK = (KIND <= SRC_NET && !CSV)>
 __global__ void __launch_bounds__(PARSE_TPB)
 k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t tile_bytes, uint32_t max_lines,
         const uint64_t* __restrict__ tile_row_base, IngestCfg cfg, AllCols cols, unsigned long long* err) {
@@ -183,12 +186,24 @@ k_parse(const char* __restrict__ text, uint64_t begin, uint64_t end, uint32_t ti
     uint32_t stage_len = (uint32_t)(((s1 + 15) & ~15ull) - s0);
     unsigned char* stage = smem;
     uint32_t* lstart = reinterpret_cast<uint32_t*>(smem + (((size_t)tile_bytes + OVERLAP_BYTES + 48) & ~(size_t)15));
-    {   // coalesced 128-bit staging (buffer is padded past `end`)
+    if constexpr (BULK) {
+        __shared__ __align__(8) uint64_t bar;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, stage_len);
+            bulk_g2s(stage, text + s0, stage_len, &bar);       // (s0 and stage_len are multiples of 16; the text is padded past `end`)
+        }
+        mbar_wait(&bar, 0);
+    } else {   // coalesced 128-bit staging (buffer is padded past `end`)
         const uint4* g4 = reinterpret_cast<const uint4*>(text + s0);
         uint4* s4 = reinterpret_cast<uint4*>(stage);
         for (uint32_t i = threadIdx.x; i < (stage_len >> 4); i += blockDim.x) s4[i] = g4[i];
+        __syncthreads();
     }
-    __syncthreads();
     // each thread scans an 8-byte-aligned chunk of the staged bytes for newlines in [qlo, qhi),
     // one 64-bit shared-memory load per 8 bytes (odd word stride: conflict free)
     uint32_t scan_len = (uint32_t)(qhi > s0 ? qhi - s0 : 0);
