@@ -439,7 +439,7 @@ def run_ours(args):
 
     strong = None
     if dist is not None and args.strong:
-        strong = run_strong(args, eng, dist, rank, world, local_rank, dev_ms / args.steps, barrier, max_over_ranks)
+        strong = run_strong(args, eng, dist, rank, world, local_rank, dev_ms / args.steps, kstats.get("analyze", (0, 0.0))[1], barrier, max_over_ranks)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -507,7 +507,7 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------- strong scaling: one trace over all ranks
-def run_strong(args, eng, dist, rank, world, local_rank, weak_ms, barrier, max_over_ranks):
+def run_strong(args, eng, dist, rank, world, local_rank, weak_ms, analyze_ms, barrier, max_over_ranks):
     """ONE logical trace of --events events (BASELINE configs[2] mix; configs[3] is the same at 500 M) split over the
     ranks as newline-aligned row ranges of every source.  Per step and rank: parse + CSV + every report.js series of its
     shard; dtype flags all-reduced (NCCL) before formatting; then the parsed gpu and packet shards are gathered on rank 0
@@ -534,9 +534,20 @@ def run_strong(args, eng, dist, rank, world, local_rank, weak_ms, barrier, max_o
     params[hl.SRC_GPU] = eng.make_params(p); keep.append(eng._keep)
     params[hl.SRC_PERF] = eng.make_params(hl.base_params(hl.SRC_PERF, TIME_BASE, False, PERF_T_OFFSET)); keep.append(eng._keep)
     params[hl.SRC_NET] = eng.make_params(hl.base_params(hl.SRC_NET, TIME_BASE, False, 0.0)); keep.append(eng._keep)
+    # Rank 0 also runs the analyze half over the gathered gpu / packet rows (analyze_ms of every step, which does not
+    # shard): it gets a smaller share of the rows so that all ranks finish together.  Shares: rank 0 carries
+    # max(10 %, T - A) of T = (S + A) / N, where S is the shardable part of a one-GPU step and A its analyze part.
+    A = max(0.0, max_over_ranks(float(analyze_ms)))          # the same number on every rank: the shard boundaries must agree
+    S = max(1.0, weak_ms - A)
+    T = (S + A) / world
+    w0 = max(0.1 * T, T - A)
+    weights = [w0] + [(S - w0) / (world - 1)] * (world - 1) if world > 1 else [1.0]
+    cum = [0.0]
+    for w in weights:
+        cum.append(cum[-1] + w / sum(weights))
     shard_rows = {}
     for kind, total, variant in ((hl.SRC_PERF, n[0], 0), (hl.SRC_GPU, n[1], 0), (hl.SRC_NET, n[2], 1)):
-        r0, r1 = total * rank // world, total * (rank + 1) // world
+        r0, r1 = int(total * cum[rank]), (int(total * cum[rank + 1]) if rank + 1 < world else total)
         shard_rows[kind] = (r0, r1)
 
     def regen(kind):
@@ -607,7 +618,7 @@ def run_strong(args, eng, dist, rank, world, local_rank, weak_ms, barrier, max_o
     return {"n_gpus": world, "events": sum(n), "ms_per_step": ms, "value": sum(n) / (ms * 1e-3), "unit": "events/s",
             "scaling": "strong", "collective_ms_per_step": cms, "collective_share": cms / ms if ms else None,
             "nccl_bytes_per_step_this_rank": coll["bytes"] / args.steps,
-            "one_gpu_ms_per_step": weak_ms, "speedup_vs_one_gpu": weak_ms / ms if ms else None,
+            "row_share_of_rank0": weights[0] / sum(weights), "one_gpu_ms_per_step": weak_ms, "speedup_vs_one_gpu": weak_ms / ms if ms else None,
             "efficiency": weak_ms / ms / world if ms else None,
             "note": "wall clock between device synchronisations, max over ranks, per step; side files and concurrency_breakdown are not part of this arm",
             "collectives": "all-reduce of dtype flags (per source), all-gather of shard sizes, send/recv of parsed gpu + packet shards to rank 0"}

@@ -124,8 +124,7 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_gather_records(GatherArgs a
             }
         }
     }
-    __syncthreads();
-    if (staged && total) flush_staged(stage, a.out, base, total);
+    if (staged && total) flush_staged_bulk(stage, a.out, base, total);       // one bulk-asynchronous store per block
 }
 
 }  // namespace sofa
