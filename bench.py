@@ -534,21 +534,25 @@ def run_strong(args, eng, dist, rank, world, local_rank, weak_ms, analyze_ms, ba
     params[hl.SRC_GPU] = eng.make_params(p); keep.append(eng._keep)
     params[hl.SRC_PERF] = eng.make_params(hl.base_params(hl.SRC_PERF, TIME_BASE, False, PERF_T_OFFSET)); keep.append(eng._keep)
     params[hl.SRC_NET] = eng.make_params(hl.base_params(hl.SRC_NET, TIME_BASE, False, 0.0)); keep.append(eng._keep)
-    # Rank 0 also runs the analyze half over the gathered gpu / packet rows (analyze_ms of every step, which does not
-    # shard): it gets a smaller share of the rows so that all ranks finish together.  Shares: rank 0 carries
-    # max(10 %, T - A) of T = (S + A) / N, where S is the shardable part of a one-GPU step and A its analyze part.
+    # Rank 0 also runs the analyze half (A ms, does not shard) after the gpu / packet shards were gathered on it.  The
+    # gpu and packet rows - everything BEFORE that gather - are split evenly; the perf rows, which come after it, are
+    # split so that rank 0's analyze + perf share ends with the other ranks' perf shares:
+    # A + p0 P = p1 P, p0 + (N - 1) p1 = 1, with P = the perf source's part of a one-GPU step (its share of the events).
     A = max(0.0, max_over_ranks(float(analyze_ms)))          # the same number on every rank: the shard boundaries must agree
     S = max(1.0, weak_ms - A)
-    T = (S + A) / world
-    w0 = max(0.1 * T, T - A)
-    weights = [w0] + [(S - w0) / (world - 1)] * (world - 1) if world > 1 else [1.0]
-    cum = [0.0]
-    for w in weights:
-        cum.append(cum[-1] + w / sum(weights))
+    P = S * n[0] / float(sum(n))
+    p1 = min(1.0 / max(1, world - 1), (1.0 + A / P) / world) if world > 1 else 1.0
+    p0 = max(0.02, 1.0 - (world - 1) * p1) if world > 1 else 1.0
+    perf_w = [p0] + [(1.0 - p0) / (world - 1)] * (world - 1) if world > 1 else [1.0]
     shard_rows = {}
     for kind, total, variant in ((hl.SRC_PERF, n[0], 0), (hl.SRC_GPU, n[1], 0), (hl.SRC_NET, n[2], 1)):
+        w = perf_w if kind == hl.SRC_PERF else [1.0 / world] * world
+        cum = [0.0]
+        for x in w:
+            cum.append(cum[-1] + x)
         r0, r1 = int(total * cum[rank]), (int(total * cum[rank + 1]) if rank + 1 < world else total)
         shard_rows[kind] = (r0, r1)
+    weights = perf_w
 
     def regen(kind):
         r0, r1 = shard_rows[kind]
@@ -618,7 +622,7 @@ def run_strong(args, eng, dist, rank, world, local_rank, weak_ms, analyze_ms, ba
     return {"n_gpus": world, "events": sum(n), "ms_per_step": ms, "value": sum(n) / (ms * 1e-3), "unit": "events/s",
             "scaling": "strong", "collective_ms_per_step": cms, "collective_share": cms / ms if ms else None,
             "nccl_bytes_per_step_this_rank": coll["bytes"] / args.steps,
-            "row_share_of_rank0": weights[0] / sum(weights), "one_gpu_ms_per_step": weak_ms, "speedup_vs_one_gpu": weak_ms / ms if ms else None,
+            "perf_row_share_of_rank0": weights[0] / sum(weights), "one_gpu_ms_per_step": weak_ms, "speedup_vs_one_gpu": weak_ms / ms if ms else None,
             "efficiency": weak_ms / ms / world if ms else None,
             "note": "wall clock between device synchronisations, max over ranks, per step; side files and concurrency_breakdown are not part of this arm",
             "collectives": "all-reduce of dtype flags (per source), all-gather of shard sizes, send/recv of parsed gpu + packet shards to rank 0"}
