@@ -576,26 +576,30 @@ def run_strong(args, eng, dist, rank, world, local_rank, weak_ms, analyze_ms, ba
         coll["ms"] += (time.perf_counter() - t0) * 1e3
         return r
 
-    def step():
-        for kind in (hl.SRC_NET, hl.SRC_GPU, hl.SRC_PERF):
-            eng.parse(kind, params[kind])
-            if kind != hl.SRC_PERF:
-                timed(lambda: io.sync_flags(eng, kind, 1))
-            eng.csv_device(kind, 1)
-            if kind == hl.SRC_NET:
-                eng.json_device(kind, 1, -1)
-            else:
-                if kind == hl.SRC_PERF:
-                    eng.set_demangled(dm(eng.viz_mangled(1)))
-                kws = GPU_KWS if kind == hl.SRC_GPU else CPU_KWS
-                eng.json_series_device(kind, 1, kws)
-                for i in range(len(kws)):
-                    eng.json_device(kind, 1, i)
+    def fmt(kind):
+        eng.parse(kind, params[kind])
+        if kind != hl.SRC_PERF:
+            timed(lambda: io.sync_flags(eng, kind, 1))
+        eng.csv_device(kind, 1)
+        if kind == hl.SRC_NET:
+            eng.json_device(kind, 1, -1)
+        else:
+            if kind == hl.SRC_PERF:
+                eng.set_demangled(dm(eng.viz_mangled(1)))
+            kws = GPU_KWS if kind == hl.SRC_GPU else CPU_KWS
+            eng.json_series_device(kind, 1, kws)
+            for i in range(len(kws)):
+                eng.json_device(kind, 1, i)
+
+    def step():             # gpu + packet shards first, so the gather and rank 0's analyze overlap the other ranks' perf shards
+        for kind in (hl.SRC_NET, hl.SRC_GPU):
+            fmt(kind)
         for kind in (hl.SRC_GPU, hl.SRC_NET):
             coll["bytes"] += timed(lambda: sharded.gather_source(eng, kind, dist, device, 0))
         if rank == 0:
             eng.gpu_profile()
             eng.net_profile(1)
+        fmt(hl.SRC_PERF)
 
     def restore():          # (untimed) the gathered state replaced rank 0's shard: put the shard's text back for the next step
         if rank == 0:
