@@ -592,6 +592,24 @@ def _has_rows(path):
     return nl >= 0 and (len(head) > nl + 1 or os.path.getsize(path) > nl + 1)
 
 
+class _Phase(object):
+    """Wall time of one analyze section, added to cfg._timing (read by bench.py's e2e_entrypoints)."""
+    def __init__(self, cfg, name):
+        self.cfg, self.name = cfg, 'analyze: ' + name
+
+    def __enter__(self):
+        import time
+        self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        import time
+        tm = getattr(self.cfg, '_timing', None)
+        if tm is None:
+            tm = self.cfg._timing = {}
+        tm[self.name] = tm.get(self.name, 0.0) + time.perf_counter() - self.t0
+        return False
+
+
 def sofa_analyze(cfg, engine=None):
     print_main_progress('SOFA analyzing...')
     logdir = cfg.logdir
@@ -632,13 +650,15 @@ def sofa_analyze(cfg, engine=None):
             if _has_rows(logdir + "nettrace.csv"):
                 if not resident and not load_net_source(cfg, eng):
                     raise IOError("nettrace.csv could not be loaded")
-                features = net_profile(logdir, cfg, eng, features)
+                with _Phase(cfg, 'net_profile'):
+                    features = net_profile(logdir, cfg, eng, features)
         else:
             print_warning(cfg, "%s is not found" % (logdir + "nettrace.csv"))
         # ---- netstat.csv (:925-931)
         if os.path.isfile(logdir + "netstat.csv"):
             if _has_rows(logdir + "netstat.csv"):
-                features = netbandwidth_profile(logdir, cfg, eng, features)
+                with _Phase(cfg, 'netbandwidth_profile'):
+                    features = netbandwidth_profile(logdir, cfg, eng, features)
         else:
             print_warning(cfg, "%s is not found" % (logdir + "netstat.csv"))
         # ---- blktrace / diskstat (:933-947): their profile functions are not built; the files make that explicit
@@ -651,31 +671,36 @@ def sofa_analyze(cfg, engine=None):
         # ---- vmstat (:949-955), mpstat (:957-963)
         if os.path.isfile(logdir + "vmstat.csv"):
             if _has_rows(logdir + "vmstat.csv"):
-                features = vmstat_profile(logdir, cfg, eng, features)
+                with _Phase(cfg, 'vmstat_profile'):
+                    features = vmstat_profile(logdir, cfg, eng, features)
         else:
             print_warning(cfg, "%s is not found" % (logdir + "vmstat.csv"))
         have_mpstat = False
         if os.path.isfile(logdir + "mpstat.csv"):
             if _has_rows(logdir + "mpstat.csv"):
                 have_mpstat = True
-                features = mpstat_profile(logdir, cfg, eng, features)
+                with _Phase(cfg, 'mpstat_profile'):
+                    features = mpstat_profile(logdir, cfg, eng, features)
         else:
             print_warning(cfg, "%s is not found" % (logdir + "mpstat.csv"))
         # ---- nvsmi (:965-969), gpu (:971-977)
         if os.path.isfile(logdir + "nvsmi_trace.csv"):
-            features = nvsmi_profile(logdir, cfg, eng, features)
+            with _Phase(cfg, 'nvsmi_profile'):
+                features = nvsmi_profile(logdir, cfg, eng, features)
         else:
             print_warning(cfg, "nvsmi_trace.csv is not found")
         if os.path.isfile(logdir + "gputrace.csv"):
             if _has_rows(logdir + "gputrace.csv"):
                 if (not resident or getattr(cfg, '_sofa_b200_gpu_slot_is_api', False)) and not load_gpu_source(cfg, eng):
                     raise IOError("gputrace.csv could not be loaded")
-                features += gpu_profile(cfg, eng)
+                with _Phase(cfg, 'gpu_profile'):
+                    features += gpu_profile(cfg, eng)
         else:
             print_warning(cfg, "%sgputrace.csv is not found. If there is no need to profile GPU, just ignore it." % logdir)
         # ---- concurrency_breakdown (:979-984)
         if have_mpstat:
-            features = concurrency_breakdown(logdir, cfg, eng, features)
+            with _Phase(cfg, 'concurrency_breakdown'):
+                features = concurrency_breakdown(logdir, cfg, eng, features)
     finally:
         if own:
             eng.close()
