@@ -270,6 +270,60 @@ int sofa_b200_side_preprocess(sofa_ctx*, int raw_src, const sofa_side_params_t*,
 int sofa_b200_side_emit_csv(sofa_ctx*, int raw_src, int list, uint64_t* nbytes, uint64_t* n_rows);
 int sofa_b200_side_emit_json(sofa_ctx*, int raw_src, int list, uint64_t* nbytes, uint64_t* n_records);
 int sofa_b200_side_emit_aux(sofa_ctx*, int raw_src, uint64_t* nbytes, uint64_t* n_rows);
+
+/* Recorder side files, second group: diskstat.txt (table 0; sofa_preprocess.py:548-673), blktrace.txt (1; :688-781),
+ * strace.txt (2; :1618-1704), pystacks.txt (3; :1706-1761) -> diskstat.csv / diskstat_vector.csv /
+ * diskstat_vector_ui.csv, blktrace.csv, strace.csv, pystacks.csv and the records of the diskstat,
+ * blktrace_starting_block, blktrace_time, strace and pystacks series of report.js.  One table at a time:
+ * sofa_b200_side2_preprocess (upload + parse + index), for diskstat sofa_b200_side2_dev_table / _set_devs, then
+ * sofa_b200_side2_emit per output into output buffer 0 (CSV) or 1 (report.js records); read with sofa_b200_fetch.
+ *   category / category_text: the `cpuid` an earlier section of sofa_preprocess left behind (the reference's strace and
+ *   pystacks rows carry it in their last column; a string when blktrace.txt set it);
+ *   info.total = total_strace_duration; info.last_span = byte range of the cpu token of the last accepted blktrace
+ *   line (what `cpuid` becomes), a == b when there is none; info.flags bit 0 = "blktrace maybe record failed!". */
+typedef struct {
+    double time_base, strace_min_time;
+    int64_t pid, category;
+    const char* category_text;
+    int32_t absolute_timestamp, plot_ratio, category_is_str, category_len;
+} sofa_side2_params_t;
+typedef struct {
+    uint64_t n_lines, n_entries, n_kept, n_devs;
+    double total;
+    uint32_t last_span_a, last_span_b;
+    int32_t flags, pad;
+} sofa_side2_info_t;
+#define SOFA_SIDE2_DEV_CAP 1024
+#define SOFA_SIDE2_CSV0 0
+#define SOFA_SIDE2_CSV1 1
+#define SOFA_SIDE2_JSON0 2
+#define SOFA_SIDE2_JSON1 3
+#define SOFA_SIDE2_VEC 4
+#define SOFA_SIDE2_VEC_UI 5
+int sofa_b200_side2_preprocess(sofa_ctx*, int table, const void* text, uint64_t nbytes, const sofa_side2_params_t* p,
+                               sofa_side2_info_t* info);
+/* diskstat: span[2 * slot], span[2 * slot + 1] = byte range of the device name held by table slot `slot` (a = 0xffffffff:
+ * empty slot); then per slot the sector size the host read from /sys/block/<dev>/queue/hw_sector_size (512 when absent,
+ * :563-570) and whether --diskstat_filters selects the device.  set_devs also finds the devices whose traffic never
+ * moved (dropped from every output, :650-653) and the dtype of the r_time / w_time / await_time columns. */
+int sofa_b200_side2_dev_table(sofa_ctx*, uint32_t* span, uint32_t cap_slots);
+int sofa_b200_side2_set_devs(sofa_ctx*, const int32_t* secsize, const uint8_t* ui_keep, uint32_t n_slots);
+int sofa_b200_side2_emit(sofa_ctx*, int table, int what, uint64_t* nbytes, uint64_t* n_rows);
+/* diskstat_profile (sofa_analyze.py:640-700) over the text of diskstat_vector.csv: one entry per device with the two
+ * order statistics pandas' groupby().quantile interpolates between, for q = 0.25, 0.5, 0.75 of d_read, d_write and
+ * d_disk_total (q_lo / q_hi[3 * column + q]), and groupby().mean() (Kahan sum in row order / count) of d_read, d_write,
+ * d_disk_total, r_iops, w_iops, iops, await_time.  span: as sofa_b200_side2_dev_table (the names, by slot).
+ * blktrace_latency (sofa_analyze.py:627-631) over the text of blktrace.csv: the rows whose event is 'C', the order
+ * statistics of their duration that numpy's linear quantile interpolates between. */
+typedef struct {
+    uint32_t slot, pad;
+    uint64_t count;
+    double q_lo[9], q_hi[9];
+    double mean[7];
+} sofa_disk_group_t;
+int sofa_b200_diskstat_profile(sofa_ctx*, const void* csv_text, uint64_t nbytes, sofa_disk_group_t* groups, uint32_t cap,
+                               uint32_t* n_groups, uint32_t* span);
+int sofa_b200_blktrace_latency(sofa_ctx*, const void* csv_text, uint64_t nbytes, uint64_t* count, double* q_lo, double* q_hi);
 /* CUDA-event stopwatch on the ctx stream: mark(0) ... mark(1); elapsed = ms between them */
 int sofa_b200_mark(sofa_ctx*, int which);
 int sofa_b200_elapsed_ms(sofa_ctx*, double* ms);

@@ -20,6 +20,8 @@ EXPORTS = [
     "sofa_b200_set_profiling", "sofa_b200_get_stats", "sofa_b200_reset_stats", "sofa_b200_kernel_name",
     "sofa_b200_synth", "sofa_b200_text_fetch", "sofa_b200_mark", "sofa_b200_elapsed_ms",
     "sofa_b200_upload_async", "sofa_b200_fetch_async", "sofa_b200_wait_fetch", "sofa_b200_sync", "sofa_b200_set_output_arena", "sofa_b200_emit_comm_csv", "sofa_b200_window_reduce",
+    "sofa_b200_side2_preprocess", "sofa_b200_side2_dev_table", "sofa_b200_side2_set_devs", "sofa_b200_side2_emit",
+    "sofa_b200_diskstat_profile", "sofa_b200_blktrace_latency",
     "sofa_b200_side_preprocess", "sofa_b200_side_emit_csv", "sofa_b200_side_emit_json", "sofa_b200_side_emit_aux", "sofa_b200_nvsmi_profile", "sofa_b200_net_profile",
 ]
 
@@ -78,6 +80,26 @@ class IterStats(ctypes.Structure):
 class NvsmiGroup(ctypes.Structure):
     _fields_ = [("dev", ctypes.c_int32), ("event", ctypes.c_int32), ("count", ctypes.c_uint64), ("sum", ctypes.c_int64),
                 ("q_lo", ctypes.c_double * 3), ("q_hi", ctypes.c_double * 3)]
+
+
+class Side2Params(ctypes.Structure):
+    _fields_ = [("time_base", ctypes.c_double), ("strace_min_time", ctypes.c_double), ("pid", ctypes.c_int64),
+                ("category", ctypes.c_int64), ("category_text", ctypes.c_char_p), ("absolute_timestamp", ctypes.c_int32),
+                ("plot_ratio", ctypes.c_int32), ("category_is_str", ctypes.c_int32), ("category_len", ctypes.c_int32)]
+
+
+class Side2Info(ctypes.Structure):
+    _fields_ = [("n_lines", ctypes.c_uint64), ("n_entries", ctypes.c_uint64), ("n_kept", ctypes.c_uint64),
+                ("n_devs", ctypes.c_uint64), ("total", ctypes.c_double), ("last_span_a", ctypes.c_uint32),
+                ("last_span_b", ctypes.c_uint32), ("flags", ctypes.c_int32), ("pad", ctypes.c_int32)]
+
+
+SIDE2_DEV_CAP = 1024
+
+
+class DiskGroup(ctypes.Structure):
+    _fields_ = [("slot", ctypes.c_uint32), ("pad", ctypes.c_uint32), ("count", ctypes.c_uint64),
+                ("q_lo", ctypes.c_double * 9), ("q_hi", ctypes.c_double * 9), ("mean", ctypes.c_double * 7)]
 
 
 class SideParams(ctypes.Structure):
@@ -171,6 +193,12 @@ def load_lib():
     lib.sofa_b200_side_emit_csv.argtypes = [vp, ctypes.c_int, ctypes.c_int, u64p, u64p]
     lib.sofa_b200_side_emit_json.argtypes = [vp, ctypes.c_int, ctypes.c_int, u64p, u64p]
     lib.sofa_b200_side_emit_aux.argtypes = [vp, ctypes.c_int, u64p, u64p]
+    lib.sofa_b200_side2_preprocess.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.POINTER(Side2Params), ctypes.POINTER(Side2Info)]
+    lib.sofa_b200_side2_dev_table.argtypes = [vp, vp, ctypes.c_uint32]
+    lib.sofa_b200_side2_set_devs.argtypes = [vp, vp, vp, ctypes.c_uint32]
+    lib.sofa_b200_side2_emit.argtypes = [vp, ctypes.c_int, ctypes.c_int, u64p, u64p]
+    lib.sofa_b200_diskstat_profile.argtypes = [vp, vp, ctypes.c_uint64, ctypes.POINTER(DiskGroup), ctypes.c_uint32, u32p, vp]
+    lib.sofa_b200_blktrace_latency.argtypes = [vp, vp, ctypes.c_uint64, u64p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.sofa_b200_set_profiling.argtypes = [vp, ctypes.c_int]
     lib.sofa_b200_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.sofa_b200_reset_stats.argtypes = [vp]

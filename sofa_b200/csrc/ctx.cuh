@@ -57,6 +57,16 @@ struct Source {
 
 struct TimedEvent { int kind; cudaEvent_t a, b; };
 
+// diskstat / blktrace / strace / pystacks (capi_side2.inc): one table at a time, preprocess -> emits
+struct Side2State {
+    DevBuf text, lstart, raw, mask, idx, lens, tab;
+    int table = -1; bool ready = false, devs_set = false;
+    uint64_t nbytes = 0, n_lines = 0, n = 0, n_kept = 0; int last_has_nl = 1;
+    int absolute = 0; double time_base = 0; int64_t pid = 0, cat = 0; int cat_is_str = 0; uint32_t cat_a = 0, cat_b = 0;
+    uint32_t n_dev = 0, disk_fl = 0; int dur_all_int = 0;
+    void release() { text.release(); lstart.release(); raw.release(); mask.release(); idx.release(); lens.release(); tab.release(); }
+};
+
 struct sofa_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -81,6 +91,7 @@ struct sofa_ctx {
     std::vector<SmallXfer> pending;
     char* out_ptr[3] = {nullptr, nullptr, nullptr};
     DevBuf tiles, rowlen, blockoff, scratch, ftable, keys, rows;
+    Side2State s2;
     DevBuf gather[17];                   // rank 0 of a sharded trace: text + columns being gathered (sofa_b200_shard_reserve)
     DevBuf sk0, sv0, sk1, sv1, hist, segs, sums, small, scanpart;
     void* pin_h = nullptr; size_t pin_cap = 0;  // pinned host scratch for larger read-backs (grown on demand)

@@ -5,11 +5,13 @@
 #include "kernels_sort.cuh"
 #include "kernels_window.cuh"
 #include "kernels_profiles.cuh"
+#include "kernels_side2.cuh"
 
 extern "C" {
 
 #include "capi_analyze.inc"
 #include "capi_window.inc"
 #include "capi_profiles.inc"
+#include "capi_side2.inc"
 
 }  // extern "C"

@@ -76,6 +76,7 @@ int sofa_b200_destroy(sofa_ctx* c) {
         for (auto& b : s.cols) b.release();
         if (k < 3) c->out[k].release();
     }
+    c->s2.release();
     c->tiles.release(); c->rowlen.release(); c->blockoff.release(); c->scratch.release(); c->ftable.release();
     c->keys.release(); c->rows.release();
     c->sk0.release(); c->sv0.release(); c->sk1.release(); c->sv1.release(); c->hist.release(); c->segs.release();

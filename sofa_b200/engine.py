@@ -400,6 +400,70 @@ class CudaEngine:
         self._check(self.lib.sofa_b200_side_emit_aux(self.ctx, raw_src, ctypes.byref(n), ctypes.byref(nr)))
         return self._fetch(0, n.value), nr.value
 
+    # ---- recorder side files, second group: diskstat.txt 0, blktrace.txt 1, strace.txt 2, pystacks.txt 3
+    def side2_preprocess(self, table, text, time_base, absolute_timestamp, plot_ratio=1, pid=0, strace_min_time=0.0, category=None):
+        """upload + parse + index one file; category: the `cpuid` an earlier section left behind (int, or bytes when
+        blktrace.txt set it).  -> dict(n_lines, n_entries, n_kept, n_devs, total, last_span, flags)"""
+        p = L.Side2Params()
+        p.time_base, p.strace_min_time, p.pid = float(time_base), float(strace_min_time), int(pid)
+        p.absolute_timestamp, p.plot_ratio = 1 if absolute_timestamp else 0, int(plot_ratio)
+        if isinstance(category, (bytes, str)):
+            cb = category.encode() if isinstance(category, str) else bytes(category)
+            p.category_text, p.category_is_str, p.category_len, p.category = cb, 1, len(cb), 0
+        else:
+            p.category_text, p.category_is_str, p.category_len, p.category = None, 0, 0, int(category or 0)
+        buf = np.frombuffer(text, dtype=np.uint8) if len(text) else np.zeros(1, dtype=np.uint8)
+        info = L.Side2Info()
+        self._check(self.lib.sofa_b200_side2_preprocess(self.ctx, table, ctypes.c_void_p(buf.ctypes.data), ctypes.c_uint64(len(text)),
+                                                        ctypes.byref(p), ctypes.byref(info)))
+        self._s2_text = text
+        return dict(n_lines=info.n_lines, n_entries=info.n_entries, n_kept=info.n_kept, n_devs=info.n_devs, total=info.total,
+                    last_span=(info.last_span_a, info.last_span_b), flags=info.flags)
+
+    def side2_dev_names(self):
+        """[(table slot, device name)] of the diskstat.txt just preprocessed"""
+        span = np.zeros(2 * L.SIDE2_DEV_CAP, dtype=np.uint32)
+        self._check(self.lib.sofa_b200_side2_dev_table(self.ctx, ctypes.c_void_p(span.ctypes.data), L.SIDE2_DEV_CAP))
+        text = bytes(self._s2_text)
+        return [(i, text[int(span[2 * i]):int(span[2 * i + 1])]) for i in range(L.SIDE2_DEV_CAP) if span[2 * i] != 0xffffffff]
+
+    def side2_set_devs(self, devs):
+        """devs: {slot: (sector size, selected by --diskstat_filters)}"""
+        sec = np.full(L.SIDE2_DEV_CAP, 512, dtype=np.int32)
+        ui = np.zeros(L.SIDE2_DEV_CAP, dtype=np.uint8)
+        for slot, (sz, keep) in devs.items():
+            sec[slot], ui[slot] = int(sz), 1 if keep else 0
+        self._check(self.lib.sofa_b200_side2_set_devs(self.ctx, ctypes.c_void_p(sec.ctypes.data), ctypes.c_void_p(ui.ctypes.data),
+                                                      L.SIDE2_DEV_CAP))
+
+    def side2_emit(self, table, what):
+        """what: 0 / 1 CSV rows of list 0 / 1, 2 / 3 report.js records of list 0 / 1, 4 diskstat_vector.csv, 5 diskstat_vector_ui.csv
+        -> (bytes, rows)"""
+        n, nr = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.sofa_b200_side2_emit(self.ctx, table, what, ctypes.byref(n), ctypes.byref(nr)))
+        return self._fetch(1 if what in (2, 3) else 0, n.value), nr.value
+
+    def diskstat_profile(self, csv_text):
+        """groups of diskstat_vector.csv by device: [(name, count, q_lo[9], q_hi[9], mean[7])] (see sofa_b200_diskstat_profile)"""
+        buf = np.frombuffer(csv_text, dtype=np.uint8) if len(csv_text) else np.zeros(1, dtype=np.uint8)
+        groups = (L.DiskGroup * 512)()
+        ng = ctypes.c_uint32()
+        span = np.zeros(2 * L.SIDE2_DEV_CAP, dtype=np.uint32)
+        self._check(self.lib.sofa_b200_diskstat_profile(self.ctx, ctypes.c_void_p(buf.ctypes.data), ctypes.c_uint64(len(csv_text)), groups, 512,
+                                                        ctypes.byref(ng), ctypes.c_void_p(span.ctypes.data)))
+        text = bytes(csv_text)
+        return [(text[int(span[2 * g.slot]):int(span[2 * g.slot + 1])].decode(), g.count, list(g.q_lo), list(g.q_hi), list(g.mean))
+                for g in groups[:ng.value]]
+
+    def blktrace_latency(self, csv_text):
+        """rows of blktrace.csv whose event is 'C': (count, q_lo[3], q_hi[3]) of their duration"""
+        buf = np.frombuffer(csv_text, dtype=np.uint8) if len(csv_text) else np.zeros(1, dtype=np.uint8)
+        n = ctypes.c_uint64()
+        lo, hi = (ctypes.c_double * 3)(), (ctypes.c_double * 3)()
+        self._check(self.lib.sofa_b200_blktrace_latency(self.ctx, ctypes.c_void_p(buf.ctypes.data), ctypes.c_uint64(len(csv_text)),
+                                                        ctypes.byref(n), lo, hi))
+        return n.value, list(lo), list(hi)
+
     # ---- stopwatch (CUDA events on the engine's stream)
     def mark(self, which):
         self._check(self.lib.sofa_b200_mark(self.ctx, which))

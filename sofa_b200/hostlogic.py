@@ -163,3 +163,24 @@ def api_t_base(text, data_off, first_corid=1):
                 break
             pos = e + 1
     return t_base
+
+
+def last_nvsmi_gpu(text, data_off):
+    """gpu index of the last nvsmi_query.txt row: the value the reference's `cpuid` local is left with after the
+    nvidia-smi query section (sofa_preprocess.py:1036, 1044) and that later lands in the strace / pystacks rows"""
+    for ln in reversed(bytes(text[data_off:]).split(b'\n')):
+        f = ln.split(b',')
+        if len(f) >= 5:
+            return int(f[2])
+    return None
+
+
+def last_dmon_gpu(text):
+    """gpu index of the last accepted `nvidia-smi dmon` line (sofa_preprocess.py:1108-1120): what `cpuid` keeps"""
+    for ln in reversed(bytes(text).split(b'\n')):
+        if ln.find(b'gpu') != -1 or ln.find(b'Idx') != -1:
+            continue
+        f = ln.split()
+        if len(f) >= 5:
+            return int(f[0])
+    return None

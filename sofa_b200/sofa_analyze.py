@@ -310,6 +310,71 @@ def netbandwidth_profile(logdir, cfg, eng, features):
     return features
 
 
+def blktrace_latency_profile(logdir, cfg, eng, features):
+    """sofa_analyze.py:596-638.  btt.txt / offset_all.txt are written by the recorder's `btt` run (sofa_preprocess.py:684-686);
+    when one is missing open() raises inside the driver's try block and the reference reports "blktrace.csv is not found".
+    The quartiles of the 'C' rows' duration come from the device; the block-offset chart needs matplotlib and is not drawn."""
+    with open('%s/btt.txt' % logdir) as f:
+        lines = f.readlines()
+    start = end = None
+    for i, line in enumerate(lines):
+        if '==================== All Devices ====================' in line:
+            start = i
+        if '==================== Device Merge Information ====================' in line:
+            end = i
+            break
+    if start is None or end is None:
+        raise NameError("btt.txt: the 'All Devices' / 'Device Merge Information' sections are missing (UnboundLocalError in the reference)")
+    bttoutput_result = lines[start:end]
+    open('%s/offset_all.txt' % logdir).close()                       # read for the chart only; must exist
+    print('Offset of Device Report is saved at %s/offset_of_device_report.pdf' % logdir)
+    if cfg.verbose:
+        print_title('Storage Profiling:')
+        print('Blktracae Latency (s):')
+        for btt in bttoutput_result:
+            print(btt[:-1])
+    with open(logdir + 'blktrace.csv', 'rb') as f:
+        n, lo, hi = eng.blktrace_latency(f.read())
+    qs = [(_np_quantile(lo[i], hi[i], n, 0.25 * (i + 1)) if n else float('nan')) for i in range(3)]
+    return features + [('blktrace_latency_q1', qs[0]), ('blktrace_latency_q2', qs[1]), ('blktrace_latency_q3', qs[2])]
+
+
+def diskstat_profile(logdir, cfg, eng, features):
+    """sofa_analyze.py:640-700.  Per device (groupby sorts the names): quartiles and means of diskstat_vector.csv's
+    columns from the device (order statistics + Kahan sums, sofa_b200_diskstat_profile); the string table is pandas'."""
+    import numpy as np
+    import pandas as pd
+    with open(logdir + 'diskstat_vector.csv', 'rb') as f:
+        groups = sorted(eng.diskstat_profile(f.read()), key=lambda g: g[0])
+
+    def gq(g, col, k):                                               # group_quantile, linear (pandas/_libs/groupby.pyx)
+        lo, hi, n = np.float64(g[2][col * 3 + k]), np.float64(g[3][col * 3 + k]), g[1]
+        q_idx = np.float64(0.25 * (k + 1)) * (n - 1)
+        frac = q_idx % 1
+        return lo if frac == 0.0 else lo + (hi - lo) * frac
+    columns = ['Q1 throughput(Read)', 'Q2 throughput(Read)', 'Q3 throughput(Read)', 'Avg throughput(Read)',
+               'Q1 throughput(Write)', 'Q2 throughput(Write)', 'Q3 throughput(Write)', 'Avg throughput(Write)',
+               'Q1 throughput(R+W)', 'Q2 throughput(R+W)', 'Q3 throughput(R+W)', 'Avg throughput(R+W)',
+               'Avg IOPS(Read)', 'Avg IOPS(Write)', 'Avg IOPS(R+W)', 'Avg Await time(ms)']
+    final_table = pd.DataFrame(columns=columns)
+    for g in groups:
+        mean = [np.float64(x) for x in g[4]]
+        cells = []
+        for col in range(3):                                         # read, write, read + write
+            cells += [_convertbytes(gq(g, col, 0)), _convertbytes(gq(g, col, 1)), _convertbytes(gq(g, col, 2)), _convertbytes(mean[col])]
+        cells += ['%d' % int(mean[3]), '%d' % int(mean[4]), '%d' % int(mean[5]), '%.3lf ms' % mean[6]]
+        final_table = pd.concat([final_table, pd.DataFrame([tuple(cells)], columns=columns, index=[g[0]])])
+    if cfg.verbose:
+        print_title('DISKSTAT Profiling:')
+        print('Disk Throughput Quartile :')
+        print(final_table.T)
+    feats = []
+    for k, nm in enumerate(('diskstat_q1', 'diskstat_q2', 'diskstat_q3')):
+        per_dev = np.array([gq(g, 2, k) for g in groups], dtype=np.float64)
+        feats.append((nm, per_dev.sum() / len(per_dev) if len(per_dev) else float('nan')))     # Series.mean()
+    return features + feats
+
+
 def vmstat_profile(logdir, cfg, eng, features):
     """sofa_analyze.py:712-733: means of bi / bo / in / cs parsed out of the name column of vmstat.csv."""
     _upload_side_csv(eng, logdir, SRC_MPSTAT_CSV, 'vmstat.csv', api_mode=2)
@@ -661,13 +726,22 @@ def sofa_analyze(cfg, engine=None):
                     features = netbandwidth_profile(logdir, cfg, eng, features)
         else:
             print_warning(cfg, "%s is not found" % (logdir + "netstat.csv"))
-        # ---- blktrace / diskstat (:933-947): their profile functions are not built; the files make that explicit
-        for fn, what in (("blktrace.csv", "blktrace_latency_profile"), ("diskstat_vector.csv", "diskstat_profile")):
-            if os.path.isfile(logdir + fn):
-                if _has_rows(logdir + fn):
-                    print_warning(cfg, "%s: %s is not implemented; its features are missing from the table" % (fn, what))
-            else:
-                print_warning(cfg, "%s is not found" % (logdir + fn))
+        # ---- blktrace (:933-939), diskstat (:941-947)
+        if os.path.isfile(logdir + "blktrace.csv"):
+            if _has_rows(logdir + "blktrace.csv"):
+                try:
+                    with _Phase(cfg, 'blktrace_latency_profile'):
+                        features = blktrace_latency_profile(logdir, cfg, eng, features)
+                except IOError:                                  # btt.txt / offset_all.txt missing: the reference's message
+                    print_warning(cfg, "%s is not found" % (logdir + "blktrace.csv"))
+        else:
+            print_warning(cfg, "%s is not found" % (logdir + "blktrace.csv"))
+        if os.path.isfile(logdir + "diskstat_vector.csv"):
+            if _has_rows(logdir + "diskstat_vector.csv"):
+                with _Phase(cfg, 'diskstat_profile'):
+                    features = diskstat_profile(logdir, cfg, eng, features)
+        else:
+            print_warning(cfg, "%s is not found" % (logdir + "diskstat_vector.csv"))
         # ---- vmstat (:949-955), mpstat (:957-963)
         if os.path.isfile(logdir + "vmstat.csv"):
             if _has_rows(logdir + "vmstat.csv"):

@@ -27,7 +27,9 @@ sofa_fieldnames = ["timestamp", "event", "duration", "deviceId", "copyKind", "pa
                    "bandwidth", "pkt_src", "pkt_dst", "pid", "tid", "name", "category"]
 CSV_HEADER = (",".join(sofa_fieldnames) + "\n").encode()
 
-NOT_YET = ['diskstat.txt', 'strace.txt', 'blktrace.txt', 'pystacks.txt']
+S2_DISK, S2_BLK, S2_STRACE, S2_PYSTACKS = 0, 1, 2, 3        # second group of side files (sofa_b200_side2_*)
+SYS_BLOCK = '/sys/block/'        # where diskstat's sector sizes are looked up (:563-570); tests point it at an empty directory
+VECTOR_HEADER = b"time,dev,r_iops,w_iops,iops,r_time,w_time,await_time,d_read,d_write,d_disk_total\n"
 RAW_MPSTAT, RAW_NVSMI, RAW_NETSTAT, RAW_VMSTAT, RAW_DMON = 6, 7, 8, 9, 10
 VMSTAT_LISTS = ('bi', 'bo', 'in', 'cs', 'wa', 'st', 'usr', 'sys')
 
@@ -162,12 +164,61 @@ def _side_sources(cfg, eng, logdir):
             out['mpstat_usr'] = eng.side_json(RAW_MPSTAT)
         else:
             print_warning(cfg, 'Empty list cannot be exported to mpstat.csv!')
+    # `cpuid`: a local of the reference that leaks from section to section and ends up in the last column of the strace
+    # and pystacks rows (blktrace.txt leaves a string, vmstat.txt -1, the nvidia-smi files a gpu index)
+    cfg._sofa_b200_cpuid = None
+    if os.path.isfile(logdir + 'blktrace.txt'):                          # :688-781
+        text = _read_bytes(logdir + 'blktrace.txt')
+        print_info(cfg, "Length of blktrace = %d" % (text.count(b'\n') + (1 if text and not text.endswith(b'\n') else 0)))
+        if len(text) > 0:
+            info = eng.side2_preprocess(S2_BLK, text, cfg.time_base, cfg.absolute_timestamp)
+            d_rows, nd = eng.side2_emit(S2_BLK, 0)
+            if nd > 0:
+                _write(logdir + 'blktrace.csv', CSV_HEADER, d_rows)
+                out['blktrace_starting_block'] = eng.side2_emit(S2_BLK, 2)
+            else:
+                print_warning(cfg, 'Empty list cannot be exported to blktrace.csv!')
+            c_rows, nc = eng.side2_emit(S2_BLK, 1)
+            if nc > 0:
+                with open(logdir + 'blktrace.csv', 'ab') as f:             # appended without a header (mode 'a')
+                    f.write(memoryview(c_rows))
+                out['blktrace_time'] = eng.side2_emit(S2_BLK, 3)
+            else:
+                print_warning(cfg, 'Empty list cannot be exported to blktrace.csv!')
+            if info['flags'] & 1:
+                print_warning(cfg, 'blktrace maybe record failed!')
+            a, b = info['last_span']
+            if b > a:
+                cfg._sofa_b200_cpuid = bytes(text[a:b])
+    if os.path.isfile(logdir + 'diskstat.txt'):                          # :548-673
+        text = _read_bytes(logdir + 'diskstat.txt')
+        eng.side2_preprocess(S2_DISK, text, cfg.time_base, cfg.absolute_timestamp)
+        flt = getattr(cfg, 'diskstat_filters', None)
+        devs = {}
+        for slot, name in eng.side2_dev_names():
+            secsize = 512
+            try:
+                with open(SYS_BLOCK + name.decode() + '/queue/hw_sector_size') as f:
+                    import re
+                    secsize = int(re.match(r"\d+", f.readline()).group())
+            except Exception:
+                pass
+            devs[slot] = (secsize, (not flt) or name.decode() == flt)
+        eng.side2_set_devs(devs)
+        if flt:
+            print(flt)                                                   # :662
+        body, _ = eng.side2_emit(S2_DISK, 0)
+        _write(logdir + 'diskstat.csv', CSV_HEADER, body)
+        _write(logdir + 'diskstat_vector.csv', VECTOR_HEADER, eng.side2_emit(S2_DISK, 4)[0])
+        _write(logdir + 'diskstat_vector_ui.csv', VECTOR_HEADER, eng.side2_emit(S2_DISK, 5)[0])
+        out['diskstat'] = eng.side2_emit(S2_DISK, 2)
     if os.path.isfile(logdir + 'vmstat.txt'):
         text = _read_bytes(logdir + 'vmstat.txt')
         print_info(cfg, "Length of vmstat_traces = %d" % text.count(b'\n'))
         if len(text) > 0:
             _, ncand, _ = eng.side_preprocess(RAW_VMSTAT, text, cfg.time_base, cfg.absolute_timestamp)
             if ncand > 0:
+                cfg._sofa_b200_cpuid = -1
                 _write(logdir + 'vmstat.csv', CSV_HEADER, *[eng.side_csv(RAW_VMSTAT, i)[0] for i in range(8)])
                 for i, nm in enumerate(VMSTAT_LISTS):
                     if nm in ('cs', 'bi', 'bo') or (cfg.enable_vmstat and nm in ('usr', 'sys', 'in')):
@@ -189,6 +240,7 @@ def _side_sources(cfg, eng, logdir):
         else:
             print_info(cfg, "Length of nvsmi_query_traces = %d" % n_lines)
             if ncand > 0:
+                cfg._sofa_b200_cpuid = hl.last_nvsmi_gpu(text, data_off)
                 sm, _ = eng.side_csv(RAW_NVSMI, 0)
                 mem, _ = eng.side_csv(RAW_NVSMI, 1)
                 _write(logdir + 'nvsmi_trace.csv', CSV_HEADER, sm, mem)
@@ -201,6 +253,9 @@ def _side_sources(cfg, eng, logdir):
             print_warning(cfg, 'No nvsmi data.')
         else:
             print_info(cfg, "Length of nvsmi_traces = %d" % n_lines)
+            last = hl.last_dmon_gpu(text)
+            if last is not None:
+                cfg._sofa_b200_cpuid = last
             enc, nrows = eng.side_csv(RAW_DMON, 0) if ncand > 0 else (b'', 0)
             if nrows > 0:
                 cfg.nvsmi_data = True
@@ -227,6 +282,46 @@ def _side_sources(cfg, eng, logdir):
     return out
 
 
+def _strace_pystacks(cfg, eng, logdir, ratio):
+    """strace.txt (:1618-1704) and pystacks.txt (:1706-1761): rows, CSV text and report.js records come from the device;
+    `cpuid` is whatever the side-file sections left behind (NameError in the reference when none did)."""
+    out = {}
+    cpuid = getattr(cfg, '_sofa_b200_cpuid', None)
+    total = 0
+    if os.path.isfile(logdir + 'strace.txt'):
+        text = _read_bytes(logdir + 'strace.txt')
+        n_lines = text.count(b'\n') + (1 if text and not text.endswith(b'\n') else 0)
+        print_info(cfg, "Length of straces = %d" % n_lines)
+        if n_lines > 1:
+            info = eng.side2_preprocess(S2_STRACE, text, cfg.time_base, cfg.absolute_timestamp, ratio, getattr(cfg, 'pid', 0),
+                                        getattr(cfg, 'strace_min_time', 1e-6), cpuid)
+            total = info['total']
+            body, nrows = eng.side2_emit(S2_STRACE, 0)
+            if nrows > 0 and cpuid is None:
+                raise PreprocessError("strace.txt: name 'cpuid' is not defined (the reference raises NameError: no side file "
+                                      "left a cpu / gpu id behind)")
+            print_info(cfg, 'strace.txt reading is done.')
+            if nrows > 0:
+                _write(logdir + 'strace.csv', CSV_HEADER, body)
+                out['strace'] = eng.side2_emit(S2_STRACE, 2)
+    print_info(cfg, 'Total strace duration: %.3lf' % total)
+    if os.path.isfile(logdir + 'pystacks.txt'):
+        text = _read_bytes(logdir + 'pystacks.txt')
+        info = eng.side2_preprocess(S2_PYSTACKS, text, cfg.time_base, cfg.absolute_timestamp, category=cpuid)
+        if info['n_kept'] == 0:
+            raise PreprocessError("pystacks.txt: no stack outside 'idle' (max() of an empty dict raises ValueError in the reference)")
+        if info['n_kept'] > 1:                                       # the reference builds one row per remaining stack
+            if cpuid is None:
+                raise PreprocessError("pystacks.txt: name 'cpuid' is not defined (the reference raises NameError)")
+            body, nrows = eng.side2_emit(S2_PYSTACKS, 0)
+            if nrows > 0:
+                _write(logdir + 'pystacks.csv', CSV_HEADER, body)
+                out['pystacks'] = eng.side2_emit(S2_PYSTACKS, 2)
+            else:
+                print_warning(cfg, 'Empty list cannot be exported to pystacks.csv!')
+    return out
+
+
 class _Timing(dict):
     """wall-clock seconds per phase of one sofa_preprocess call (cfg._timing; reported by bench.py's e2e_entrypoints)"""
     def add(self, key, t0):
@@ -243,7 +338,8 @@ def _timed_engine(eng, tm):
             f = getattr(eng, name)
             phase = {'load': 'upload+parse', 'csv': 'csv emit+fetch', 'json': 'json emit+fetch', 'json_series': 'json emit+fetch',
                      'set_filters': 'filters', 'viz_mangled': 'viz names', 'set_demangled': 'viz names',
-                     'side_preprocess': 'side files', 'side_csv': 'side files', 'side_json': 'side files', 'side_aux': 'side files'}.get(name)
+                     'side_preprocess': 'side files', 'side_csv': 'side files', 'side_json': 'side files', 'side_aux': 'side files',
+                     'side2_preprocess': 'side files', 'side2_emit': 'side files', 'side2_set_devs': 'side files'}.get(name)
             if phase is None or not callable(f):
                 return f
 
@@ -337,17 +433,6 @@ def _preprocess(cfg, eng, io):
             cfg.pid = int(lines[3].split()[1])
         else:
             print_warning(cfg, 'Incorrect misc.txt content. Some profiling information may not be available.')
-    for fn in NOT_YET:
-        if os.path.isfile(logdir + fn) and os.path.getsize(logdir + fn) > 0:
-            # the recorder writes diskstat.txt on every Linux run (sofa_record.py:271-276): a drop-in must not die on
-            # it.  Default: say so, skip the source (its series stays empty, its CSV is not written) and go on;
-            # SOFA_B200_STRICT=1 turns the gap into an error for runs that must match the reference file for file.
-            msg = ("%s: this source is not on the accelerated path (SURVEY.md §8f N1): its report.js series stays empty "
-                   "and its CSV is not written" % fn)
-            if os.environ.get('SOFA_B200_STRICT', '0') not in ('', '0'):
-                raise NotImplementedError(msg + " (SOFA_B200_STRICT is set)")
-            import sys
-            sys.stderr.write("[WARNING] " + msg + "\n")
     if int(os.system('command -v perf 1> /dev/null')) == 0 and os.path.isfile(logdir + 'perf.data'):
         with open(logdir + 'perf.script', 'w') as logfile:
             subprocess.call('perf script -F time,pid,tid,event,ip,sym,dso,symoff,period,brstack,brstacksym '
@@ -499,25 +584,28 @@ def _preprocess(cfg, eng, io):
     except IOError:
         print_warning(cfg, 'no perf traces.')
 
+    if io.rank == 0:
+        side.update(_strace_pystacks(cfg, eng, logdir, ratio))
+
     print_progress(cfg, "Export Overhead Dynamics JSON File of CPU, Network and GPU traces -- begin")
     # ---------------- series list (:1849-2102); sources off the hot path are empty here
     series = list(cpu_series)
-    for nm in ('blktrace_starting_block', 'blktrace_time'):
-        series.append(SeriesOut(nm, nm, ''))
+    series.append(SeriesOut('blktrace_starting_block', 'BLKTRACE_STARTING_BLOCK', 'Green', *side.get('blktrace_starting_block', (None, 0))))
+    series.append(SeriesOut('blktrace_time', 'BLKTRACE_TIME', 'DodgerBlue', *side.get('blktrace_time', (None, 0))))
     series.append(SeriesOut('vmstat_cs', 'VMSTAT_CS', 'Pink', *side.get('vmstat_cs', (None, 0))))
     series.append(SeriesOut('vmstat_bi', 'VMSTAT_BI', 'DarkOrange', *side.get('vmstat_bi', (None, 0))))
     series.append(SeriesOut('vmstat_bo', 'VMSTAT_BO', 'DarkOrchid', *side.get('vmstat_bo', (None, 0))))
     if cfg.enable_mpstat:
         series.append(SeriesOut('mpstat_usr', 'MPSTAT_USR', 'Cyan', *side.get('mpstat_usr', (None, 0))))
     if cfg.enable_diskstat:
-        series.append(SeriesOut('diskstat', 'DISK_USAGE (MB/s)', 'GreenYellow'))
+        series.append(SeriesOut('diskstat', 'DISK_USAGE (MB/s)', 'GreenYellow', *side.get('diskstat', (None, 0))))
     if cfg.enable_vmstat:
         series.append(SeriesOut('vmstat_usr', 'CPU_USAGE_USR', 'Magenta', *side.get('vmstat_usr', (None, 0))))
         series.append(SeriesOut('vmstat_sys', 'CPU_USAGE_SYS', 'LightBlue', *side.get('vmstat_sys', (None, 0))))
         series.append(SeriesOut('vmstat_in', 'VMSTAT_IN', 'DarkMagenta', *side.get('vmstat_in', (None, 0))))
         series.append(SeriesOut('vmstat_cs', 'VMSTAT_CS', 'DarkOliveGreen', *side.get('vmstat_cs', (None, 0))))
-    for nm in ('strace', 'pystacks'):
-        series.append(SeriesOut(nm, nm, ''))
+    series.append(SeriesOut('strace', 'STRACE.', 'DarkSlateGray', *side.get('strace', (None, 0))))
+    series.append(SeriesOut('pystacks', 'Python-stacks.', 'Tomato', *side.get('pystacks', (None, 0))))
     series.append(SeriesOut('nvsmi_mem', 'GPU_MEM_Util.', 'lightblue', *side.get('nvsmi_mem', (None, 0))))
     series.append(SeriesOut('nvsmi_sm', 'GPU_SM_Util.', 'red', *side.get('nvsmi_sm', (None, 0))))
     if getattr(cfg, 'enable_encode_decode', False):

@@ -12,6 +12,8 @@ TIME (the reference source is untouched, nothing of it is copied):
     copy-on-write (cpu_util prints 0 and --verbose dies on int(nan)).  The function is re-executed from its own
     source with those five statements spelled `df_summary.loc[i, 'USR'] = x` - what every pandas the reference
     was written for did.
+  * Index.format(), `series[-1]` on a string index (positional fallback), read_table(delim_whitespace=True)
+                                              diskstat_profile :676, :685; blktrace_latency_profile :607 (driver_disk)
 matplotlib is absent: `plt` is a stub whose figures swallow savefig (no PDF is written).
 
     python tests/golden/make_golden_driver.py
@@ -35,7 +37,8 @@ from sofa_b200 import synth  # noqa: E402
 
 OUT_FILES = ("netrank.csv", "performance.csv", "comm.csv")
 IN_FILES = ("misc.txt", "sofa_time.txt", "perf_events_used.txt", "perf_timebase.txt", "perf.script", "gputrace.tmp", "net.tmp",
-            "mpstat.txt", "nvsmi_query.txt", "netstat.txt", "vmstat.txt", "nvsmi.txt", "cpuinfo.txt")
+            "mpstat.txt", "nvsmi_query.txt", "netstat.txt", "vmstat.txt", "nvsmi.txt", "cpuinfo.txt",
+            "diskstat.txt", "strace.txt", "blktrace.txt", "pystacks.txt", "btt.txt", "offset_all.txt")
 
 CASES = {
     # name: (make_logdir kwargs, side kwargs, 1 Hz side files?, spotlight pattern?, cfg overrides)
@@ -44,6 +47,11 @@ CASES = {
     "driver_spotlight": (dict(seed=502, n_perf=500, n_gpu=300, n_net=0), dict(n_samples=80, n_cores=2, n_gpus=2), False, True,
                          dict(spotlight_gpu=True)),
     "driver_perf_only": (dict(seed=503, n_perf=400), dict(n_samples=30, n_cores=8, n_gpus=1), False, False, {}),
+    # + diskstat.txt, strace.txt, blktrace.txt (with the recorder's btt.txt / offset_all.txt), pystacks.txt: strace_profile,
+    # blktrace_latency_profile, diskstat_profile.  Device names that exist on no machine (no /sys/block lookups hit).
+    "driver_disk": (dict(seed=504, n_perf=300, n_gpu=200), dict(n_samples=50, n_cores=2, n_gpus=1), True, False, {},
+                    dict(disk=dict(n_samples=45, devs=("xda", "xda1", "fake0n1", "loopx", "dm-x")), strace=dict(n_strace=200, n_blk=300),
+                         btt=True)),
 }
 
 
@@ -61,6 +69,25 @@ def install_driver_shims():
     if not hasattr(pd.DataFrame, 'append'):
         pd.DataFrame.append = lambda self, other, **kw: pd.concat(
             [self, other.to_frame().T if isinstance(other, pd.Series) else other])
+    if not hasattr(pd.Index, 'format'):
+        pd.Index.format = lambda self: [str(x) for x in self]
+    _getitem = pd.Series.__getitem__
+
+    def _getitem_positional(self, key):     # pandas < 3: an int on a non-integer index is a position
+        try:
+            return _getitem(self, key)
+        except KeyError:
+            if isinstance(key, int):
+                return self.iloc[key]
+            raise
+    pd.Series.__getitem__ = _getitem_positional
+    _read_table = pd.read_table
+
+    def _read_table_ws(*a, **k):
+        if k.pop('delim_whitespace', False):
+            k['sep'] = r'\s+'
+        return _read_table(*a, **k)
+    pd.read_table = _read_table_ws
     from pandas.core.strings.accessor import StringMethods
 
     def _iter(self):                       # pandas < 2: yields the i-th element of every row until a column is all-NaN
@@ -95,7 +122,23 @@ def spotlight_nvsmi(logdir, n_samples, n_gpus):
                 f.write("%s, Tesla V100-SXM2-16GB, %d, %d %%, %d %%\n" % (ts, g, sm, (s * 11 + g) % 50))
 
 
-def run_case(name, mk, side, hz1, spot, ov):
+def write_btt(logdir, seed):
+    """btt.txt / offset_all.txt as the recorder's `btt -i blktrace.out -B offset` leaves them (sofa_preprocess.py:684-686)"""
+    with open(os.path.join(logdir, "btt.txt"), "w") as f:
+        f.write("==================== All Devices ====================\n\n")
+        f.write("            ALL           MIN           AVG           MAX           N\n")
+        f.write("--------------- ------------- ------------- ------------- -----------\n\n")
+        f.write("Q2Q               0.000001254   0.003412771   0.120034411         299\n")
+        f.write("D2C               0.000211341   0.004807392   0.031209876         143\n\n")
+        f.write("==================== Device Merge Information ====================\n\n")
+        f.write("       DEV |       #Q       #D   Ratio |   BLKmin   BLKavg   BLKmax    Total\n")
+    with open(os.path.join(logdir, "offset_all.txt"), "w") as f:
+        for i in range(40):
+            b = 691248304 + 1024 * ((i * 7 + seed) % 97)
+            f.write("%.9f %d %d\n" % (0.001 * i, b, b + 1024))
+
+
+def run_case(name, mk, side, hz1, spot, ov, extra=None):
     import sofa_preprocess as ref_pre
     import sofa_analyze as ref_an
     work = tempfile.mkdtemp(prefix="sofa_golden_drv_")
@@ -106,6 +149,12 @@ def run_case(name, mk, side, hz1, spot, ov):
         synth.write_side_raw_1hz(logdir, mk["seed"], n_seconds=12, n_gpus=side["n_gpus"])
     if spot:
         spotlight_nvsmi(logdir, side["n_samples"], side["n_gpus"])
+    if extra:
+        synth.write_diskstat(logdir, mk["seed"], **extra["disk"])
+        synth.write_strace_blktrace(logdir, mk["seed"], **extra["strace"])
+        synth.write_pystacks(logdir, mk["seed"])
+        if extra.get("btt"):
+            write_btt(logdir, mk["seed"])
     out = os.path.join(HERE, name)
     shutil.rmtree(out, ignore_errors=True)
     os.makedirs(out)
@@ -119,6 +168,8 @@ def run_case(name, mk, side, hz1, spot, ov):
     with contextlib.redirect_stdout(io.StringIO()):
         ref_pre.sofa_preprocess(cfg)
     meta = {"make_logdir": mk, "side": side, "hz1": hz1, "spotlight_pattern": spot, "cfg": ov, "variants": {}}
+    if extra:
+        meta["extra"] = extra
     for verbose in (False, True):
         cfg = mg.make_ref_cfg(logdir, dict(ov, verbose=verbose))
         cfg.roi_begin = cfg.roi_end = 0

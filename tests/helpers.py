@@ -60,10 +60,12 @@ def build_case_logdir(name, tmpdir):
 
 
 SIDE_INPUTS = ("mpstat.txt", "nvsmi_query.txt", "netstat.txt", "perf.script", "sofa_time.txt", "perf_events_used.txt",
-               "perf_timebase.txt", "misc.txt", "vmstat.txt", "nvsmi.txt")          # the last two only in some cases
+               "perf_timebase.txt", "misc.txt", "vmstat.txt", "nvsmi.txt",          # the last two only in some cases
+               "diskstat.txt", "strace.txt", "blktrace.txt", "pystacks.txt")         # disk_small / oracle_strace_blk
 SIDE_OUTPUTS = ("mpstat.csv", "usr_sys.csv", "nvsmi_trace.csv", "netstat.csv", "netbandwidth.csv", "cputrace.csv",
-                "report.js", "vmstat.csv")
-PREPROCESS_CFG_KEYS = ("absolute_timestamp", "enable_vmstat", "enable_encode_decode", "nvsmi_time_zone")
+                "report.js", "vmstat.csv", "diskstat.csv", "diskstat_vector.csv", "diskstat_vector_ui.csv", "strace.csv",
+                "blktrace.csv", "pystacks.csv")
+PREPROCESS_CFG_KEYS = ("absolute_timestamp", "enable_vmstat", "enable_encode_decode", "nvsmi_time_zone", "plot_ratio")
 
 
 def preprocess_overrides(case):
@@ -71,7 +73,9 @@ def preprocess_overrides(case):
 
 
 def side_cases():
-    return sorted(d for d in os.listdir(GOLDEN) if d.startswith("side_"))
+    """side_*: mpstat / vmstat / nvidia-smi / netstat; disk_small: + diskstat.txt; oracle_strace_blk: + strace.txt,
+    blktrace.txt, pystacks.txt (all of them files written by the unmodified reference, make_golden_side.py)"""
+    return sorted(d for d in os.listdir(GOLDEN) if d.startswith("side_")) + ["disk_small", "oracle_strace_blk"]
 
 
 def build_side_logdir(name, tmpdir):
@@ -81,9 +85,36 @@ def build_side_logdir(name, tmpdir):
     import time
     os.environ['TZ'] = 'UTC'
     time.tzset()
+    import sofa_b200.sofa_preprocess as sp
+    sp.SYS_BLOCK = "/nonexistent_sofa_b200/"        # diskstat sector sizes: the fixtures were made where none of the names exist
     logdir = os.path.join(str(tmpdir), "sofalog") + "/"
     os.makedirs(logdir)
     for fn in SIDE_INPUTS:
         if os.path.isfile(os.path.join(GOLDEN, name, fn)):
             shutil.copy(os.path.join(GOLDEN, name, fn), logdir + fn)
     return load_case(name), logdir
+
+
+STORAGE_OUTPUTS = ("diskstat.csv", "diskstat_vector.csv", "diskstat_vector_ui.csv", "blktrace.csv", "strace.csv", "pystacks.csv", "report.js")
+
+
+def make_storage_logdir(a, n_disk=3000, n_strace=20000, n_blk=30000, n_py=5000):
+    """A logdir whose diskstat / strace / blktrace / pystacks files span many thread blocks, plus the odd lines the
+    reference tolerates: a completion without a dispatch, a start block that is not a number, a short line."""
+    import time
+    import sofa_b200.sofa_preprocess as sp
+    sp.SYS_BLOCK = "/nonexistent_sofa_b200/"
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
+    synth.make_logdir(a, seed=31, n_perf=300)
+    synth.write_side_raw(a, seed=32, n_samples=40, n_cores=2, n_gpus=2)
+    synth.write_side_raw_1hz(a, seed=33, n_seconds=8, n_gpus=2)
+    synth.write_diskstat(a, 34, n_samples=n_disk, devs=("xda", "xda1", "fake0n1", "loop0", "dm-x", "y,z".replace(",", "_")))
+    synth.write_strace_blktrace(a, 35, n_strace=n_strace, n_blk=n_blk)
+    synth.write_pystacks(a, 36, n=n_py)
+    lines = open(a + "blktrace.txt").read().split("\n")
+    lines.insert(50, "  8,0    2      999    0.000300000     0  C   W 123456789 + 1024 [0]")          # no dispatch to complete
+    lines.insert(90, "  8,0    5     1000    0.000400000 31479  D   W notanumber + 1024 [dd]")      # -> start block 0, the warning
+    lines.insert(95, "  8,0    5     1001    0.000500000     0  C   W alsonot + 8 [0] [0] [0] [0]")      # completes block 0
+    lines.insert(120, "  8,0    1 short line")
+    open(a + "blktrace.txt", "w").write("\n".join(lines))

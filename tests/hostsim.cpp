@@ -277,3 +277,121 @@ extern "C" long hs_side(int table, const char* text, long nbytes, int absolute, 
     return -1;
 }
 extern "C" int hs_repr(double x, char* out) { JPlan p = repr_plan(x); if (p.kind == JP_BAD) return -1; int l = repr_emit(p, out); return l == p.len ? l : -2; }
+
+// ---------------------------------------------------------------- diskstat / blktrace / strace / pystacks (side2.cuh)
+// CPU mirror of sofa_b200_side2_preprocess + _set_devs + _emit: the same row functions; the indexing (line starts,
+// device-name table, 'D' -> 'C' links, ranks) is restated sequentially here.
+#include "../sofa_b200/csrc/side2.cuh"
+#include <map>
+struct HsSide2 {
+    double time_base, strace_min_time; long long pid, category; const char* category_text;
+    int absolute, plot_ratio, category_is_str, category_len;
+    const int* secsize; const unsigned char* ui_keep; int n_dev_given;       // per device in order of first appearance
+};
+struct HsSide2Info { long long n_lines, n_entries, n_kept, n_devs; double total; unsigned last_a, last_b; int flags, pad; };
+// returns -1 or (1000 * entry + err)
+extern "C" long hs_side2(int table, const char* text_in, long nbytes, const HsSide2* p, int what, char* out, long* outlen, long* nrows,
+                         HsSide2Info* info) {
+    std::vector<char> buf((size_t)nbytes + 256, '\n');
+    memcpy(buf.data(), text_in, (size_t)nbytes);
+    const unsigned cat_a = (unsigned)nbytes + 128;
+    if (p->category_is_str) memcpy(buf.data() + cat_a, p->category_text, (size_t)p->category_len);
+    const char* text = buf.data();
+    memset(info, 0, sizeof *info);
+    *outlen = 0; *nrows = 0;
+    std::vector<uint32_t> lstart; lstart.push_back(0);
+    for (long i = 0; i < nbytes; i++) if (text[i] == '\n') lstart.push_back((uint32_t)i + 1);
+    const bool last_has_nl = nbytes == 0 || text[nbytes - 1] == '\n';
+    if (!last_has_nl) lstart.push_back((uint32_t)nbytes + 1);
+    const uint64_t n_lines = lstart.size() - 1;
+    if (table == S2_PYSTACKS && (n_lines & 1)) return (long)(n_lines - 1) * 1000 + E_FEW_TOKENS;
+    const uint64_t n = table == S2_PYSTACKS ? n_lines / 2 : n_lines;
+    info->n_lines = (long long)n_lines; info->n_entries = (long long)n;
+    std::vector<S2Line> raw(n + 1);
+    for (uint64_t i = 0; i < n; i++) {
+        S2Line r = {};
+        int e = E_OK;
+        if (table == S2_PYSTACKS) {
+            e = s2_parse_py(text, lstart[2 * i], (int)(lstart[2 * i + 1] - lstart[2 * i]) - 1, lstart[2 * i + 1],
+                            (int)(lstart[2 * i + 2] - lstart[2 * i + 1]) - 1, &r);
+        } else {
+            const bool has_nl = (i + 1 != n_lines) || last_has_nl;
+            const int len = (int)(lstart[i + 1] - lstart[i]) - 1;
+            if (table == S2_DISK) e = s2_parse_disk(text, lstart[i], has_nl ? len : (len > 0 ? len - 1 : 0), &r);
+            else if (table == S2_BLK) e = s2_parse_blk(text, lstart[i], len, has_nl, &r);
+            else if (i % (uint64_t)p->plot_ratio) r.link = -1;
+            else e = s2_parse_strace(text, lstart[i], len, p->pid, p->absolute, p->time_base, p->strace_min_time, &r);
+        }
+        if (e) return (long)i * 1000 + e;
+        raw[i] = r;
+    }
+    S2View v; memset(&v, 0, sizeof v);
+    v.table = table; v.text = text; v.nbytes = (uint64_t)nbytes; v.lstart = lstart.data(); v.n_lines = n_lines; v.last_has_nl = last_has_nl;
+    v.raw = raw.data(); v.n = n; v.absolute = p->absolute; v.time_base = p->time_base;
+    v.pid = p->pid; v.cat = p->category; v.cat_is_str = p->category_is_str; v.cat_span.a = cat_a; v.cat_span.b = cat_a + (unsigned)p->category_len;
+    std::vector<uint32_t> kept;
+    std::vector<int32_t> secsize; std::vector<uint8_t> dflags;
+    if (table == S2_DISK) {
+        std::vector<std::string> names;
+        for (uint64_t i = 0; i < n; i++) {
+            std::string nm(text + raw[i].sp[0].a, text + raw[i].sp[0].b);
+            size_t k = 0;
+            while (k < names.size() && names[k] != nm) k++;
+            if (k == names.size()) names.push_back(nm);
+            raw[i].link = (int32_t)k;
+        }
+        v.n_dev = (uint32_t)names.size(); info->n_devs = (long long)names.size();
+        secsize.assign(names.size() + 1, 512); dflags.assign(names.size() + 1, 0);
+        for (size_t k = 0; k < names.size() && (int)k < p->n_dev_given; k++) { secsize[k] = p->secsize[k]; dflags[k] = p->ui_keep[k] ? 2 : 0; }
+        v.dev_secsize = secsize.data(); v.dev_flags = dflags.data();
+        std::vector<double> mx(names.size() + 1, 0.0); std::vector<char> has(names.size() + 1, 0);
+        for (uint64_t i = v.n_dev; i < n; i++) {
+            DiskRow d;
+            int e = s2_disk_row(raw[i], raw[i - v.n_dev], secsize[raw[i].link], p->absolute, p->time_base, &d);
+            if (e) return (long)i * 1000 + e;
+            int k = raw[i].link;
+            if (!has[k] || d.tbw > mx[k]) mx[k] = d.tbw;
+            has[k] = 1;
+            v.disk_fl |= (d.rt_f ? 1u : 0u) | (d.wt_f ? 2u : 0u) | (d.at_f ? 4u : 0u);
+        }
+        for (size_t k = 0; k < names.size(); k++) if (has[k] && mx[k] == 0.0) dflags[k] |= 1;
+    } else if (table == S2_BLK) {
+        std::map<int64_t, int32_t> last_d;
+        long last = -1;
+        for (uint64_t i = 0; i < n; i++) {
+            if (raw[i].cls) { last = (long)i; if (raw[i].flag & 1) info->flags |= 1; }
+            if (raw[i].cls == 1) last_d[raw[i].i[0]] = (int32_t)i;
+            if (raw[i].cls == 2) { auto it = last_d.find(raw[i].i[0]); raw[i].link = it == last_d.end() ? -1 : it->second; }
+        }
+        if (last >= 0) { info->last_a = raw[last].sp[0].a; info->last_b = raw[last].sp[0].b; }
+    } else if (table == S2_STRACE) {
+        double t = 0; unsigned f = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            if (raw[i].cls) t = d_add(t, raw[i].g);
+            if (raw[i].cls == 1) f |= (raw[i].flag & 1) ? 1u : 2u;
+        }
+        info->total = t;
+        v.dur_all_int = (f & 1) ? 0 : 1;
+    } else {
+        for (uint64_t i = 0; i < n; i++) if (raw[i].cls == 1) {
+            raw[i].link = (int32_t)kept.size();
+            if (!kept.empty() && !(raw[i].f > raw[kept.back()].f)) return (long)i * 1000 + E_UNSUPPORTED_NUM;
+            kept.push_back((uint32_t)i);
+        }
+        v.kept = kept.data(); v.n_kept = kept.size(); info->n_kept = (long long)kept.size();
+    }
+    if (what < 0) return -1;
+    long o = 0, cnt = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        S2Count kc;
+        int e = s2_emit_row(v, i, what, kc);
+        if (e > 0) return (long)i * 1000 + e;
+        if (e < 0) continue;
+        S2Write kw{out + o, 0};
+        s2_emit_row(v, i, what, kw);
+        if (kw.n != kc.len) return (long)i * 1000 + 99;
+        o += (long)kw.n; cnt++;
+    }
+    *outlen = o; *nrows = cnt;
+    return -1;
+}

@@ -30,7 +30,7 @@ def build_hostsim():
     so = os.path.join(HERE, "_build", "libhostsim.so")
     src = os.path.join(HERE, "hostsim.cpp")
     os.makedirs(os.path.dirname(so), exist_ok=True)
-    deps = [src] + [os.path.join(HERE, "..", "sofa_b200", "csrc", f) for f in ("num.cuh", "rows.cuh", "side.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "sofa_b200", "csrc", f) for f in ("num.cuh", "rows.cuh", "side.cuh", "side2.cuh")]
     if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                                "-o", so, src])
@@ -38,7 +38,21 @@ def build_hostsim():
     lib.hs_process.restype = ctypes.c_long
     lib.hs_fnv.restype = ctypes.c_ulonglong
     lib.hs_side.restype = ctypes.c_long
+    lib.hs_side2.restype = ctypes.c_long
     return lib
+
+
+class HsSide2(ctypes.Structure):
+    _fields_ = [("time_base", ctypes.c_double), ("strace_min_time", ctypes.c_double), ("pid", ctypes.c_longlong),
+                ("category", ctypes.c_longlong), ("category_text", ctypes.c_char_p), ("absolute", ctypes.c_int),
+                ("plot_ratio", ctypes.c_int), ("category_is_str", ctypes.c_int), ("category_len", ctypes.c_int),
+                ("secsize", ctypes.c_void_p), ("ui_keep", ctypes.c_void_p), ("n_dev_given", ctypes.c_int)]
+
+
+class HsSide2Info(ctypes.Structure):
+    _fields_ = [("n_lines", ctypes.c_longlong), ("n_entries", ctypes.c_longlong), ("n_kept", ctypes.c_longlong),
+                ("n_devs", ctypes.c_longlong), ("total", ctypes.c_double), ("last_a", ctypes.c_uint), ("last_b", ctypes.c_uint),
+                ("flags", ctypes.c_int), ("pad", ctypes.c_int)]
 
 
 class HostSimError(RuntimeError):
@@ -164,6 +178,91 @@ class HostSimEngine:
 
     def side_aux(self, raw_src):
         return self._side(raw_src, 32)[:2]
+
+    # ---- diskstat / blktrace / strace / pystacks: CPU build of side2.cuh (hs_side2), same interface as CudaEngine
+    def _side2(self, what):
+        st = self.s2
+        text = st['text']
+        p = HsSide2()
+        p.time_base, p.strace_min_time, p.pid = st['time_base'], st['min_time'], st['pid']
+        cat = st['category']
+        if isinstance(cat, (bytes, str)):
+            cb = cat.encode() if isinstance(cat, str) else cat
+            p.category_text, p.category_is_str, p.category_len, p.category = cb, 1, len(cb), 0
+        else:
+            p.category_text, p.category_is_str, p.category_len, p.category = None, 0, 0, int(cat or 0)
+        p.absolute, p.plot_ratio = st['absolute'], st['ratio']
+        sec = np.array(st.get('secsize', []), dtype=np.int32)
+        ui = np.array(st.get('ui', []), dtype=np.uint8)
+        p.secsize, p.ui_keep, p.n_dev_given = sec.ctypes.data, ui.ctypes.data, len(sec)
+        out = ctypes.create_string_buffer(len(text) * 24 + 4096)
+        outlen, nrows = ctypes.c_long(), ctypes.c_long()
+        info = HsSide2Info()
+        r = self.lib.hs_side2(st['table'], text, ctypes.c_long(len(text)), ctypes.byref(p), what, out, ctypes.byref(outlen),
+                              ctypes.byref(nrows), ctypes.byref(info))
+        if r != -1:
+            raise HostSimError("row %d: error %d" % (r // 1000, r % 1000))
+        return np.frombuffer(out.raw[:outlen.value], dtype=np.uint8), nrows.value, info
+
+    def side2_preprocess(self, table, text, time_base, absolute_timestamp, plot_ratio=1, pid=0, strace_min_time=0.0, category=None):
+        self.s2 = dict(table=table, text=bytes(text), time_base=float(time_base), absolute=1 if absolute_timestamp else 0,
+                       ratio=int(plot_ratio), pid=int(pid), min_time=float(strace_min_time), category=category)
+        info = self._side2(-1)[2]
+        return dict(n_lines=info.n_lines, n_entries=info.n_entries, n_kept=info.n_kept, n_devs=info.n_devs, total=info.total,
+                    last_span=(info.last_a, info.last_b), flags=info.flags)
+
+    def side2_dev_names(self):
+        """device names of diskstat.txt in table-slot order (here: order of first appearance)"""
+        names = []
+        for ln in self.s2['text'].split(b'\n'):
+            f = ln.split(b',')
+            if len(f) > 1 and f[1] not in names:
+                names.append(f[1])
+        return list(enumerate(names))
+
+    def side2_set_devs(self, devs):
+        n = len(self.side2_dev_names())
+        self.s2['secsize'] = [int(devs.get(i, (512, 0))[0]) for i in range(n)]
+        self.s2['ui'] = [1 if devs.get(i, (512, 0))[1] else 0 for i in range(n)]
+
+    def side2_emit(self, table, what):
+        out, n, _ = self._side2(what)
+        return (out[2:] if what in (2, 3) else out), n
+
+    def diskstat_profile(self, csv_text):
+        """plain-Python stand-in for sofa_b200_diskstat_profile (test infrastructure only)"""
+        rows = [ln.split(',') for ln in bytes(csv_text).decode().split('\n')[1:] if ln]
+        out = []
+        for dev in dict.fromkeys(r[1] for r in rows):
+            g = [r for r in rows if r[1] == dev]
+            n = len(g)
+            q_lo, q_hi, mean = [], [], []
+            for col in (8, 9, 10):
+                v = sorted(float(r[col]) for r in g)
+                for k in (1, 2, 3):
+                    num = (n - 1) * k
+                    q_lo.append(v[num // 4]); q_hi.append(v[num // 4 + (1 if num % 4 else 0)])
+            for col in (8, 9, 10, 2, 3, 4, 7):
+                s_, c_ = 0.0, 0.0
+                for r in g:                                           # Kahan, row order (pandas group_mean)
+                    y = float(r[col]) - c_
+                    t = s_ + y
+                    c_ = (t - s_) - y
+                    s_ = t
+                mean.append(s_ / n)
+            out.append((dev, n, q_lo, q_hi, mean))
+        return out
+
+    def blktrace_latency(self, csv_text):
+        """plain-Python stand-in for sofa_b200_blktrace_latency (test infrastructure only)"""
+        v = sorted(float(f[2]) for f in (ln.split(',') for ln in bytes(csv_text).decode().split('\n')[1:] if ln) if f[1] == 'C')
+        n = len(v)
+        lo, hi = [0.0] * 3, [0.0] * 3
+        for k in (1, 2, 3):
+            if n:
+                num = (n - 1) * k
+                lo[k - 1], hi[k - 1] = v[num // 4], v[num // 4 + (1 if num % 4 else 0)]
+        return n, lo, hi
 
     # ---- side tables: numpy stand-in for the device window reduction (test infrastructure only)
     def upload(self, kind, text, data_off=0):

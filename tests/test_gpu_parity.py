@@ -461,6 +461,42 @@ def test_side_sources_device_match_oracle_larger_and_edge_cases(tmp_path):
             _diff("side_large", fn, f.read(), g.read())
 
 
+@pytest.mark.parametrize("ratio,absolute", [(1, False), (3, True)])
+def test_storage_sources_device_match_oracle_larger(ratio, absolute, tmp_path):
+    """diskstat.txt / blktrace.txt / strace.txt / pystacks.txt (N1) on the device at sizes that span many blocks (scan
+    partitions, the radix sort behind the 'D' -> 'C' links, the device-name table) vs the oracle, byte for byte."""
+    import shutil
+    from helpers import make_storage_logdir, STORAGE_OUTPUTS
+    a = os.path.join(str(tmp_path), "gpu") + "/"
+    make_storage_logdir(a)
+    b = os.path.join(str(tmp_path), "cpu") + "/"
+    shutil.copytree(a, b)
+    cfg = default_report_config(a)
+    cfg.plot_ratio, cfg.absolute_timestamp, cfg.diskstat_filters = ratio, absolute, "xda1"
+    sofa_preprocess(cfg)
+    orc.preprocess(orc.OracleConfig(b, nprocs=1, plot_ratio=ratio, absolute_timestamp=absolute, diskstat_filters="xda1"), demangle=demangle)
+    for fn in STORAGE_OUTPUTS:
+        with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
+            _diff("storage_large", fn, f.read(), g.read())
+
+
+def test_storage_sources_device_errors(tmp_path):
+    """what the reference dies on must fail loudly here too: a diskstat line with too few fields, an unpaired pystacks stamp"""
+    from helpers import build_side_logdir
+    from sofa_b200._lib import SofaB200Error
+    _, d = build_side_logdir("disk_small", tmp_path / "short")
+    lines = open(d + "diskstat.txt").read().split("\n")
+    lines[7] = "1600000000.7,sda,1,2"
+    open(d + "diskstat.txt", "w").write("\n".join(lines))
+    with pytest.raises(SofaB200Error):
+        sofa_preprocess(default_report_config(d))
+    _, d = build_side_logdir("oracle_strace_blk", tmp_path / "odd")
+    with open(d + "pystacks.txt", "a") as f:
+        f.write("1600000009000000\n")
+    with pytest.raises(SofaB200Error):
+        sofa_preprocess(default_report_config(d))
+
+
 def test_side_sources_device_errors_and_no_data(tmp_path):
     from helpers import build_side_logdir
     from sofa_b200._lib import SofaB200Error
@@ -667,6 +703,8 @@ def test_analyze_driver_stdout_matches_reference(name, variant, tmp_path, capsys
     import json
     import shutil
     from sofa_b200.sofa_analyze import sofa_analyze
+    import sofa_b200.sofa_preprocess as sp
+    sp.SYS_BLOCK = "/nonexistent_sofa_b200/"      # diskstat sector sizes: the fixture's device names exist nowhere
     gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
     meta = json.load(open(os.path.join(gdir, "case.json")))
     a = os.path.join(str(tmp_path), "sofalog") + "/"

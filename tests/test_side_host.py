@@ -55,3 +55,45 @@ def run_nvsmi_case(name, tmp_path, engine, capsys):
 @pytest.mark.parametrize("name", SIDE)
 def test_nvsmi_profile_host_logic(name, tmp_path, capsys):
     run_nvsmi_case(name, tmp_path, HostSimEngine(), capsys)
+
+
+def test_storage_profiles_host_logic(tmp_path, capsys):
+    """strace / blktrace / diskstat sections of the analyze driver (sofa_analyze.py:379-382, 596-700) on the inputs of
+    tests/golden/driver_disk: the verbose tables and the features against the unmodified reference's stdout.  The
+    device parts (order statistics, Kahan means) are plain-Python stand-ins here; tests/test_gpu_parity.py runs the
+    same case through the CUDA library."""
+    import re
+    import shutil
+    from hostsim_engine import HostSimEngine
+    from sofa_b200.sofa_config import default_report_config
+    from sofa_b200.sofa_preprocess import sofa_preprocess
+    import sofa_b200.sofa_preprocess as sp
+    sp.SYS_BLOCK = "/nonexistent_sofa_b200/"
+    gdir = os.path.join(GOLDEN, "driver_disk")
+    a = os.path.join(str(tmp_path), "sofalog") + "/"
+    os.makedirs(a)
+    for fn in os.listdir(gdir):
+        if fn.endswith(".txt") and not fn.startswith("analyze_") or fn.endswith((".tmp", ".script")):
+            shutil.copy(os.path.join(gdir, fn), a + fn)
+    open(a + "gputrace1.nvvp", "w").close()
+    cfg = default_report_config(a)
+    eng = HostSimEngine()
+    sofa_preprocess(cfg, engine=eng)
+    for fn in ("diskstat.csv", "diskstat_vector.csv", "blktrace.csv", "strace.csv", "pystacks.csv"):
+        assert os.path.getsize(a + fn) > 200, fn
+    capsys.readouterr()
+    cfg.verbose = True
+    feats = an.blktrace_latency_profile(a, cfg, eng, [])
+    feats = an.diskstat_profile(a, cfg, eng, feats)
+    got = capsys.readouterr().out.replace(a, "LOGDIR/")
+    want = open(os.path.join(gdir, "analyze_verbose.txt")).read()
+    i, j = want.index("Offset of Device Report"), want.index("VMSTAT Profiling:")
+    j = want.rindex("\n\n\n", 0, j)
+    assert got.rstrip("\n") == want[i:j].rstrip("\n")
+    table = dict(re.findall(r"^\d+\s+(\w+)\s+(-?[\d.]+|nan)\s*$", want, flags=re.M))
+    assert [n for n, _ in feats] == ["blktrace_latency_q1", "blktrace_latency_q2", "blktrace_latency_q3", "diskstat_q1", "diskstat_q2", "diskstat_q3"]
+    for n, v in feats:
+        assert "%.3lf" % v == table[n], (n, v, table[n])
+    os.remove(a + "btt.txt")                       # without the recorder's btt output the reference reports the CSV itself as missing
+    with pytest.raises(IOError):
+        an.blktrace_latency_profile(a, cfg, eng, [])

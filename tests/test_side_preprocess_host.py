@@ -174,3 +174,19 @@ def test_repr_matches_python():
         elif r > 0:                                          # outside the guaranteed range: never wrong, may refuse
             assert buf.raw[:r].decode() == repr(v), (v, buf.raw[:r], repr(v))
     assert n_ok > 10000
+
+
+@pytest.mark.parametrize("ratio,absolute", [(1, False), (3, True)])
+def test_storage_sources_match_oracle_larger(ratio, absolute, tmp_path):
+    """diskstat / blktrace / strace / pystacks at sizes that span many blocks, with the odd lines the reference tolerates
+    (CPU build of side2.cuh through the product host logic vs the oracle; tests/test_gpu_parity.py repeats it on the device)"""
+    import shutil
+    from helpers import make_storage_logdir, STORAGE_OUTPUTS
+    a = str(tmp_path / "a") + "/"
+    make_storage_logdir(a, n_disk=400, n_strace=3000, n_blk=4000, n_py=700)
+    b = str(tmp_path / "b") + "/"
+    shutil.copytree(a, b)
+    run_product(a, HostSimEngine(), plot_ratio=ratio, absolute_timestamp=absolute, diskstat_filters="xda1")
+    orc.preprocess(orc.OracleConfig(b, nprocs=1, plot_ratio=ratio, absolute_timestamp=absolute, diskstat_filters="xda1"), demangle=demangle)
+    for fn in STORAGE_OUTPUTS:
+        assert_same(open(a + fn, "rb").read(), open(b + fn, "rb").read(), fn)
