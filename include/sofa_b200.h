@@ -333,6 +333,17 @@ int sofa_b200_elapsed_ms(sofa_ctx*, double* ms);
  * the inclusive byte offset at which block `block` (128 consecutive selected rows) of the LAST emit ends, read
  * from that emit's look-back state. */
 int sofa_b200_fetch_range(sofa_ctx*, int which, uint64_t off, uint64_t nbytes, void* host_out);
+
+/* Streaming I/O of the drop-in entry points (sofa_preprocess reads and writes files through one pinned staging buffer):
+ * a source text uploaded in pieces (the first piece sizes the device buffer, the last one makes the source ready for
+ * sofa_b200_parse), and outputs parked on the device until report.js is written - the reference's series order
+ * (sofa_preprocess.py:1849-2102) is not the order the series are produced in.  hold_output copies output `which`
+ * (report.js records without their leading ", ") device to device and returns a handle; hold_fetch reads a piece of
+ * it; hold_release(handle) frees it, hold_release(-1) all of them. */
+int sofa_b200_upload_chunk(sofa_ctx*, int src, uint64_t off, const void* piece, uint64_t nbytes, uint64_t total, uint64_t data_off);
+int sofa_b200_hold_output(sofa_ctx*, int which, int32_t* handle);
+int sofa_b200_hold_fetch(sofa_ctx*, int32_t handle, uint64_t off, uint64_t nbytes, void* host_out);
+int sofa_b200_hold_release(sofa_ctx*, int32_t handle);
 int sofa_b200_emit_block_end(sofa_ctx*, uint64_t block, uint64_t* end_bytes);
 
 /* One logical trace sharded over several contexts / GPUs (newline-aligned byte ranges, one per rank): a column's dtype

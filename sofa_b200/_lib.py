@@ -22,6 +22,7 @@ EXPORTS = [
     "sofa_b200_upload_async", "sofa_b200_fetch_async", "sofa_b200_wait_fetch", "sofa_b200_sync", "sofa_b200_set_output_arena", "sofa_b200_emit_comm_csv", "sofa_b200_window_reduce",
     "sofa_b200_side2_preprocess", "sofa_b200_side2_dev_table", "sofa_b200_side2_set_devs", "sofa_b200_side2_emit",
     "sofa_b200_diskstat_profile", "sofa_b200_blktrace_latency",
+    "sofa_b200_upload_chunk", "sofa_b200_hold_output", "sofa_b200_hold_fetch", "sofa_b200_hold_release",
     "sofa_b200_side_preprocess", "sofa_b200_side_emit_csv", "sofa_b200_side_emit_json", "sofa_b200_side_emit_aux", "sofa_b200_nvsmi_profile", "sofa_b200_net_profile",
 ]
 
@@ -197,6 +198,10 @@ def load_lib():
     lib.sofa_b200_side2_dev_table.argtypes = [vp, vp, ctypes.c_uint32]
     lib.sofa_b200_side2_set_devs.argtypes = [vp, vp, vp, ctypes.c_uint32]
     lib.sofa_b200_side2_emit.argtypes = [vp, ctypes.c_int, ctypes.c_int, u64p, u64p]
+    lib.sofa_b200_upload_chunk.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]
+    lib.sofa_b200_hold_output.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
+    lib.sofa_b200_hold_fetch.argtypes = [vp, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, vp]
+    lib.sofa_b200_hold_release.argtypes = [vp, ctypes.c_int32]
     lib.sofa_b200_diskstat_profile.argtypes = [vp, vp, ctypes.c_uint64, ctypes.POINTER(DiskGroup), ctypes.c_uint32, u32p, vp]
     lib.sofa_b200_blktrace_latency.argtypes = [vp, vp, ctypes.c_uint64, u64p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.sofa_b200_set_profiling.argtypes = [vp, ctypes.c_int]

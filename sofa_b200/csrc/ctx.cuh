@@ -92,6 +92,7 @@ struct sofa_ctx {
     char* out_ptr[3] = {nullptr, nullptr, nullptr};
     DevBuf tiles, rowlen, blockoff, scratch, ftable, keys, rows;
     Side2State s2;
+    std::vector<DevBuf> held; std::vector<uint64_t> held_n;      // outputs parked on the device until report.js is written (sofa_b200_hold_output)
     DevBuf gather[17];                   // rank 0 of a sharded trace: text + columns being gathered (sofa_b200_shard_reserve)
     DevBuf sk0, sv0, sk1, sv1, hist, segs, sums, small, scanpart;
     void* pin_h = nullptr; size_t pin_cap = 0;  // pinned host scratch for larger read-backs (grown on demand)

@@ -77,6 +77,7 @@ int sofa_b200_destroy(sofa_ctx* c) {
         if (k < 3) c->out[k].release();
     }
     c->s2.release();
+    for (auto& b : c->held) b.release();
     c->tiles.release(); c->rowlen.release(); c->blockoff.release(); c->scratch.release(); c->ftable.release();
     c->keys.release(); c->rows.release();
     c->sk0.release(); c->sv0.release(); c->sk1.release(); c->sv1.release(); c->hist.release(); c->segs.release();
@@ -108,6 +109,71 @@ int sofa_b200_upload(sofa_ctx* c, int k, const void* text, uint64_t nbytes, uint
     c->stats.h2d_bytes += nbytes;
     s.nbytes = nbytes; s.data_off = data_off; s.uploaded = true; s.parsed = false; s.viz_ready = false; s.n_rows = 0;
     s.mask_stride = 0; s.nkw = 0;
+    return 0;
+}
+
+// A source file read in pieces (pinned staging buffer of the caller): piece [off, off + n) of a text of `total` bytes.
+// The first piece (off == 0) sizes the device buffer, the last one (off + n == total) makes the source ready to parse.
+int sofa_b200_upload_chunk(sofa_ctx* c, int k, uint64_t off, const void* piece, uint64_t n, uint64_t total, uint64_t data_off) {
+    if (!c || k < 0 || k > 10 || (!piece && n) || off + n > total) FAIL(SOFA_ERR_ARG, "upload_chunk: bad argument");
+    if (data_off > total) FAIL(SOFA_ERR_ARG, "upload_chunk: data_off beyond the text");
+    CK(cudaSetDevice(c->device));
+    Source& s = c->src[k];
+    if (off == 0) {
+        CK_S(stream_sync(c));
+        ENSURE(s.text, total + 64);
+        s.uploaded = false; s.parsed = false; s.viz_ready = false; s.n_rows = 0; s.mask_stride = 0; s.nkw = 0;
+    } else if (s.text.cap < total + 64) FAIL(SOFA_ERR_STATE, "upload_chunk: pieces must start at offset 0");
+    if (n) {
+        CK(cudaMemcpyAsync(s.text.as<char>() + off, piece, n, cudaMemcpyHostToDevice, c->stream));
+        CK_S(stream_sync(c));                                     // the caller refills its staging buffer next
+        c->stats.h2d_bytes += n;
+    }
+    if (off + n == total) {
+        CK(cudaMemsetAsync(s.text.as<char>() + total, '\n', 64, c->stream));
+        CK_S(stream_sync(c));
+        s.nbytes = total; s.data_off = data_off; s.uploaded = true;
+    }
+    return 0;
+}
+
+// Park a copy of output `which` (0 csv, 1 report.js records without their leading ", ") on the device; read it back in
+// pieces later (the host writes report.js in series order, not in the order the series are produced).
+int sofa_b200_hold_output(sofa_ctx* c, int which, int32_t* handle) {
+    if (!c || which < 0 || which > 1 || !handle) FAIL(SOFA_ERR_ARG, "hold_output: bad argument");
+    CK(cudaSetDevice(c->device));
+    uint64_t n = c->out_n[which], skip = 0;
+    if (which == 1) { skip = n >= 2 ? 2 : n; n -= skip; }
+    DevBuf b;
+    if (n) {
+        if (b.ensure(n)) FAIL(SOFA_ERR_CUDA, "cudaMalloc failed (held output)");
+        CK(cudaMemcpyAsync(b.p, c->out_ptr[which] + skip, n, cudaMemcpyDeviceToDevice, c->stream));
+        CK_S(stream_sync(c));
+    }
+    int32_t h = -1;
+    for (size_t i = 0; i < c->held.size(); i++) if (!c->held[i].p && c->held_n[i] == ~0ull) { h = (int32_t)i; break; }
+    if (h < 0) { c->held.push_back(DevBuf()); c->held_n.push_back(~0ull); h = (int32_t)c->held.size() - 1; }
+    c->held[h] = b; c->held_n[h] = n;
+    *handle = h;
+    return 0;
+}
+int sofa_b200_hold_fetch(sofa_ctx* c, int32_t handle, uint64_t off, uint64_t n, void* host_out) {
+    if (!c || handle < 0 || (size_t)handle >= c->held.size() || c->held_n[handle] == ~0ull || (!host_out && n))
+        FAIL(SOFA_ERR_ARG, "hold_fetch: bad handle");
+    if (off + n > c->held_n[handle]) FAIL(SOFA_ERR_CAP, "hold_fetch: beyond the held output");
+    CK(cudaSetDevice(c->device));
+    if (n) {
+        CK(cudaMemcpyAsync(host_out, c->held[handle].as<char>() + off, n, cudaMemcpyDeviceToHost, c->stream));
+        CK_S(stream_sync(c));
+        c->stats.d2h_bytes += n;
+    }
+    return 0;
+}
+int sofa_b200_hold_release(sofa_ctx* c, int32_t handle) {
+    if (!c || handle < -1 || (handle >= 0 && (size_t)handle >= c->held.size())) FAIL(SOFA_ERR_ARG, "hold_release: bad handle");
+    CK(cudaSetDevice(c->device));
+    for (size_t i = 0; i < c->held.size(); i++)
+        if (handle < 0 || (size_t)handle == i) { c->held[i].release(); c->held_n[i] = ~0ull; }
     return 0;
 }
 

@@ -1,6 +1,7 @@
 """CudaEngine: the object sofa_preprocess / sofa_analyze drive.  A thin veneer over the
 C ABI: host buffers in, numpy byte arrays out.  No record-level work happens in Python."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -37,6 +38,9 @@ class CudaEngine:
 
     def close(self):
         if self.ctx:
+            if getattr(self, '_stage_buf', None) is not None:
+                self._stage_buf = None
+                self.lib.sofa_b200_host_free(ctypes.c_void_p(self._stage_ptr))
             self.lib.sofa_b200_destroy(self.ctx)
             self.ctx = None
 
@@ -147,6 +151,61 @@ class CudaEngine:
     def set_global_flags(self, kind, stride, flags):
         """sharded traces: the OR over all shards of row_flags (column dtypes are a property of the whole file)"""
         self._check(self.lib.sofa_b200_set_global_flags(self.ctx, kind, stride, int(flags)))
+
+    # ---- streaming I/O of the entry points: one pinned staging buffer between the files and the device
+    STAGE_BYTES = 64 << 20
+
+    def _stage(self):
+        if getattr(self, '_stage_buf', None) is None:
+            self.lib.sofa_b200_host_alloc.restype = ctypes.c_void_p
+            p = self.lib.sofa_b200_host_alloc(ctypes.c_uint64(self.STAGE_BYTES))
+            if not p:
+                raise MemoryError("cudaHostAlloc failed (staging buffer)")
+            self._stage_ptr = p
+            self._stage_buf = np.ctypeslib.as_array((ctypes.c_uint8 * self.STAGE_BYTES).from_address(p))
+        return self._stage_ptr, self._stage_buf
+
+    def load_file(self, kind, path, params, data_off=0):
+        """load() of a whole file, read through the pinned staging buffer (readinto + H2D per piece)"""
+        ptr, buf = self._stage()
+        total = os.path.getsize(path)
+        with open(path, 'rb', buffering=0) as f:
+            off = 0
+            while True:
+                m = f.readinto(memoryview(buf)[:min(self.STAGE_BYTES, total - off)]) if off < total else 0
+                self._check(self.lib.sofa_b200_upload_chunk(self.ctx, kind, off, ctypes.c_void_p(ptr), m or 0, total, data_off))
+                off += m or 0
+                if off >= total:
+                    break
+                if not m:
+                    raise IOError("%s shrank while it was read" % path)
+        n = self.parse(kind, params)
+        return n, self.row_flags(kind, 1)
+
+    def write_output(self, which, n, f):
+        """bytes [0, n) of output buffer `which` (report.js records: after their leading ', ') -> file object"""
+        ptr, buf = self._stage()
+        skip = 2 if which == 1 else 0
+        for off in range(0, n, self.STAGE_BYTES):
+            m = min(self.STAGE_BYTES, n - off)
+            self._check(self.lib.sofa_b200_fetch_range(self.ctx, which, off + skip, m, ctypes.c_void_p(ptr)))
+            f.write(memoryview(buf)[:m])
+
+    def hold_output(self, which):
+        """park the current output on the device -> handle (see HeldOutput)"""
+        h = ctypes.c_int32()
+        self._check(self.lib.sofa_b200_hold_output(self.ctx, which, ctypes.byref(h)))
+        return h.value
+
+    def hold_write(self, handle, n, f):
+        ptr, buf = self._stage()
+        for off in range(0, n, self.STAGE_BYTES):
+            m = min(self.STAGE_BYTES, n - off)
+            self._check(self.lib.sofa_b200_hold_fetch(self.ctx, handle, off, m, ctypes.c_void_p(ptr)))
+            f.write(memoryview(buf)[:m])
+
+    def hold_release(self, handle=-1):
+        self._check(self.lib.sofa_b200_hold_release(self.ctx, handle))
 
     # ---- outputs
     def _fetch(self, which, n, out=None):

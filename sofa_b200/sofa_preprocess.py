@@ -56,10 +56,37 @@ def demangle(name):
 
 
 class SeriesOut:
-    """One report.js series (sofa_models.py:1-7): device-produced record bytes."""
+    """One report.js series (sofa_models.py:1-7): device-produced record bytes (an array, or a HeldOutput still on the device)."""
     def __init__(self, name, title, color, records=None, nrec=0):
         self.name, self.title, self.color = name, title, color
         self.records, self.nrec = records, nrec
+
+
+class HeldOutput:
+    """Record bytes of a series parked on the device (sofa_b200_hold_output) until report.js is written: the reference's
+    series order is not the order the series are produced in, and the host need not hold the whole file in memory."""
+    def __init__(self, eng, handle, nbytes):
+        self.eng, self.handle, self.nbytes = eng, handle, nbytes
+
+    def write_to(self, f):
+        self.eng.hold_write(self.handle, self.nbytes, f)
+        self.eng.hold_release(self.handle)
+
+
+class DeviceOutput:
+    """The output buffer of the emit that just ran, written to a file straight from the device (pinned staging pieces)."""
+    def __init__(self, eng, which, nbytes):
+        self.eng, self.which, self.nbytes = eng, which, nbytes
+
+    def write_to(self, f):
+        self.eng.write_output(self.which, self.nbytes, f)
+
+
+def _put(f, data):
+    if hasattr(data, 'write_to'):
+        data.write_to(f)
+    else:
+        f.write(memoryview(data))
 
 
 def _json_str(s):
@@ -76,7 +103,7 @@ def write_report_js(series, path):
             if s.nrec > 0:
                 f.write(("%s = {\"name\": %s, \"color\": %s, \"data\": [" %
                          (s.name, _json_str(s.title), _json_str(s.color))).encode())
-                f.write(memoryview(s.records))
+                _put(f, s.records)
                 f.write(b"]}")
             f.write(b"\n\n")
         f.write(b"sofa_traces = [ ")
@@ -353,11 +380,55 @@ def _timed_engine(eng, tm):
     return T()
 
 
+class _FileText:
+    """A source file that goes to the device piece by piece through the engine's pinned staging buffer (never whole in
+    host memory)."""
+    def __init__(self, path):
+        self.path, self.size = path, os.path.getsize(path)
+
+    def __len__(self):
+        return self.size
+
+    def count(self, what):                      # (verbose length prints only)
+        n = 0
+        with open(self.path, 'rb') as f:
+            for piece in iter(lambda: f.read(1 << 24), b''):
+                n += piece.count(what)
+        return n
+
+
+def _streaming_engine(eng):
+    """csv / json / json_series / load of the engine with device-resident results: CSV bodies are written from the
+    output buffer of the emit that just ran, report.js records stay parked on the device until the file is assembled
+    in series order, source files are read through the staging buffer."""
+    class S:
+        def __getattr__(self, name):
+            return getattr(eng, name)
+
+        def load(self, kind, text, params, data_off=0):
+            if isinstance(text, _FileText):
+                return eng.load_file(kind, text.path, params, data_off)
+            return eng.load(kind, text, params, data_off)
+
+        def csv(self, kind, stride):
+            return DeviceOutput(eng, 0, eng.csv_device(kind, stride))
+
+        def json(self, kind, stride, filt):
+            n, nrec = eng.json_device(kind, stride, filt)
+            return HeldOutput(eng, eng.hold_output(1), n), nrec
+
+        def json_series(self, kind, stride, kws):
+            n, nrec, counts = eng.json_series_device(kind, stride, kws)
+            return HeldOutput(eng, eng.hold_output(1), n), nrec, counts
+    return S()
+
+
 class PlainIO:
     """File access of an unsharded run.  sofa_b200.sharded.ShardIO has the same interface for one logical trace split
     over several ranks (byte ranges in, part files out, dtype flags all-reduced)."""
     rank, world = 0, 1
     tm = None
+    streaming = True            # files <-> device through the engine's pinned staging buffer when the engine offers it
 
     def head(self, path, n):
         with open(path, 'rb') as f:
@@ -368,6 +439,8 @@ class PlainIO:
         import time
         t0 = time.perf_counter()
         try:
+            if getattr(self, 'lazy', False):
+                return _FileText(path), data_off          # read later, by the engine, into its staging buffer
             return _read_bytes(path), data_off
         finally:
             if self.tm is not None:
@@ -384,7 +457,7 @@ class PlainIO:
         t0 = time.perf_counter()
         with open(path, 'wb') as f:
             f.write(header)
-            f.write(memoryview(body))
+            _put(f, body)
         if self.tm is not None:
             self.tm.add('write csv', t0)
 
@@ -423,6 +496,10 @@ def sofa_preprocess(cfg, engine=None, io=None):
 def _preprocess(cfg, eng, io):
     import time
     tm = cfg._timing = _Timing()
+    if getattr(io, 'streaming', False) and hasattr(eng, 'hold_output') and os.environ.get('SOFA_B200_STREAM_IO', '1') != '0':
+        eng.hold_release(-1)
+        eng = _streaming_engine(eng)
+        io.lazy = True
     eng = _timed_engine(eng, tm)
     io.tm = tm
     cfg.time_base = 0
@@ -541,7 +618,7 @@ def _preprocess(cfg, eng, io):
             print_info(cfg, "Length of cuda_api_traces = %d" % n_rows)
             with open(logdir + 'cuda_api_trace.csv', 'wb') as f:
                 f.write(CSV_HEADER)
-                f.write(memoryview(eng.csv(SRC_GPU, 1)))
+                _put(f, eng.csv(SRC_GPU, 1))
             api_series.records, api_series.nrec = eng.json(SRC_GPU, ratio, -1)
         cfg._sofa_b200_gpu_slot_is_api = True
 

@@ -132,6 +132,45 @@ class HostSimEngine:
     def set_filters(self, kind, stride, kws):
         self.filters[kind] = (stride, list(kws))
 
+    # ---- the streaming interface of CudaEngine (device-resident outputs, files through a staging buffer), so that the
+    # `not gpu` suite drives the same host code path as the product
+    def load_file(self, kind, path, params, data_off=0):
+        with open(path, 'rb') as f:
+            return self.load(kind, f.read(), params, data_off)
+
+    def csv_device(self, kind, stride):
+        self._out = getattr(self, '_out', {})
+        self._out[0] = self.csv(kind, stride)
+        return len(self._out[0])
+
+    def json_device(self, kind, stride, filt):
+        self._out = getattr(self, '_out', {})
+        self._out[1], nrec = self.json(kind, stride, filt)
+        return len(self._out[1]), nrec
+
+    def json_series_device(self, kind, stride, kws):
+        self._out = getattr(self, '_out', {})
+        self._out[1], nrec, counts = self.json_series(kind, stride, kws)
+        return len(self._out[1]), nrec, counts
+
+    def write_output(self, which, n, f):
+        f.write(memoryview(self._out[which])[:n])
+
+    def hold_output(self, which):
+        self._held = getattr(self, '_held', {})
+        h = len(self._held)
+        self._held[h] = bytes(self._out[which])
+        return h
+
+    def hold_write(self, handle, n, f):
+        f.write(self._held[handle][:n])
+
+    def hold_release(self, handle=-1):
+        if handle < 0:
+            self._held = {}
+        else:
+            self._held[handle] = None
+
     def json_series(self, kind, stride, kws):
         """main series + keyword filters set for the following json(kind, stride, k) calls"""
         rec, n = self.json(kind, stride, -1)
