@@ -532,7 +532,9 @@ def concurrency_breakdown(logdir, cfg, eng, features):
     sample_time = (1 / float(cfg.sys_mon_rate))
     first_cpu = None
     if os.path.isfile(logdir + 'cputrace.csv'):
-        cb = _csv_body(logdir + 'cputrace.csv')
+        with open(logdir + 'cputrace.csv', 'rb') as f:           # only the first row's timestamp is needed (the file can be GBs)
+            head = f.read(1 << 12)
+        cb = head[head.find(b'\n') + 1:] if b'\n' in head else b''
         if cb:
             first_cpu = float(cb[:cb.find(b',')])
     ends = []

@@ -8,11 +8,10 @@ reading side files, the nvprof header rows, demangling the unique mangled symbol
 writing the series wrappers of report.js.  There is no CPU fallback: without the CUDA
 library this module raises.
 
-Sources handled: perf.script (a1), nvprof gpu trace (a2) and API trace (a4), tcpdump text (a3),
-and of SURVEY.md §8(f) N1 the recorder side files mpstat.txt, nvsmi_query.txt and netstat.txt.
-and of SURVEY.md §8(f) N1 also vmstat.txt and nvsmi.txt.  The remaining N1 sources (diskstat, strace, blktrace, pystacks) raise
-NotImplementedError when their input files are present, rather than silently producing a
-report.js that differs from the reference's.
+Sources handled: perf.script (a1), nvprof gpu trace (a2) and API trace (a4), tcpdump text (a3), and every recorder
+side file of SURVEY.md §8(f) N1: mpstat.txt, vmstat.txt, nvsmi_query.txt, nvsmi.txt, netstat.txt, diskstat.txt,
+blktrace.txt, strace.txt, pystacks.txt.  Files go to and from the device through the engine's pinned staging buffer;
+the host never holds a whole trace or output (PlainIO.streaming).
 """
 import ctypes
 import glob
