@@ -308,8 +308,7 @@ def preprocess_netstat(logdir, absolute_timestamp, time_base):
 
 def preprocess_diskstat(logdir, absolute_timestamp, time_base, diskstat_filters=None):
     """diskstat.txt -> diskstat.csv, diskstat_vector.csv, diskstat_vector_ui.csv.  sofa_preprocess.py:548-673.
-    (Not on the device path yet: the product refuses diskstat.txt; this restatement is pinned against the
-    reference so that the device version can be checked against it.)"""
+    Pinned against the reference (tests/golden/disk_small); the device version (side2.cuh) is checked against it."""
     with open(logdir + 'diskstat.txt') as f:
         diskstats = f.readlines()
     tmp_list = [d[:-1].split(',') for d in diskstats]
@@ -372,7 +371,7 @@ def preprocess_diskstat(logdir, absolute_timestamp, time_base, diskstat_filters=
 
 def preprocess_blktrace(logdir):
     """blktrace.txt -> blktrace.csv (D rows, then completion latencies).  sofa_preprocess.py:688-781.
-    Returns (starting-block frame, latency frame, cpuid left behind for later sections).  Oracle only so far."""
+    Returns (starting-block frame, latency frame, cpuid left behind for later sections)."""
     with open(logdir + 'blktrace.txt') as f:
         lines = f.readlines()
     d_dict, d_list, c_list = {}, [], []
@@ -404,8 +403,7 @@ def preprocess_blktrace(logdir):
 
 def preprocess_pystacks(logdir, absolute_timestamp, time_base, cpuid):
     """pystacks.txt -> pystacks.csv.  sofa_preprocess.py:1706-1761.  list_to_csv_and_traces drops the first element
-    of the list it is given; this list has no placeholder row, so the first stack is lost - as in the reference.
-    Oracle only so far."""
+    of the list it is given; this list has no placeholder row, so the first stack is lost - as in the reference."""
     import itertools
     ret = {}
     with open(logdir + 'pystacks.txt', 'r') as f:
@@ -437,7 +435,7 @@ STRACE_FILTER_KEYS = ('resume', 'nanosleep', 'clock_gettime', 'brk', 'stat', 'cl
 
 def preprocess_strace(logdir, absolute_timestamp, time_base, plot_ratio, pid, strace_min_time, cpuid):
     """strace.txt -> strace.csv.  sofa_preprocess.py:1618-1704.  `cpuid` is whatever an earlier section left in
-    that variable (the reference never sets it here).  Oracle only so far."""
+    that variable (the reference never sets it here)."""
     with open(logdir + 'strace.txt') as f:
         lines = f.readlines()
     rows = []

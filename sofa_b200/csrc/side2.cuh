@@ -177,22 +177,32 @@ SOFA_HD uint64_t s2_fnv(const char* s, int n) {
 // character of every line (`[:-1]`, the '\n' - or a real character of a last line that has none: n is that length)
 SOFA_HD int s2_parse_disk(const char* text, uint32_t base, int n, S2Line* r) {
     const char* s = text + base;
-    r->cls = 0; r->flag = 0; r->link = -1; r->g = 0; r->h = 0;
+    r->cls = 0; r->flag = 0; r->pad = 0; r->link = -1; r->f = 0; r->g = 0; r->h = 0;
+    for (int q = 0; q < 6; q++) r->i[q] = 0;
     int ca[8], nc = 0;
     for (int i = 0; i < n && nc < 8; i++) if (s[i] == ',') ca[nc++] = i;
     if (nc < 1) return E_FEW_TOKENS;                               // x[1] raises IndexError while the device list is built
     r->sp[0].a = base + ca[0] + 1; r->sp[0].b = base + (nc >= 2 ? ca[1] : n);
     r->h = s2_fnv(text + r->sp[0].a, (int)(r->sp[0].b - r->sp[0].a));
-    if (nc < 7) return E_FEW_TOKENS;                               // m[7] raises IndexError
+    // The reference converts a field only where a row uses it (float(m[0]) and int(m[2..5]) in every row the line takes
+    // part in, int(m[6]) / int(m[7]) only when that row saw reads / writes): a bad field is an error of the rows that
+    // need it.  flag bit q: field q + 2 is missing or not an int (bit 6: m[0] is not a float); pad bit q: Python takes
+    // the spelling, this codec does not.
     int st = parse_double(s, ca[0], &r->f);
-    if (st) return num_status_to_err(st, true);
+    if (st == P_UNSUPPORTED) r->pad |= 1u << 6; else if (st) r->flag |= 1u << 6;
     for (int q = 0; q < 6; q++) {
-        int a = ca[1 + q] + 1, b = (q == 5) ? (nc >= 8 ? ca[7] : n) : ca[2 + q];
+        if (nc < 2 + q) { r->flag |= (uint8_t)(1u << q); continue; }
+        int a = ca[1 + q] + 1, b = (nc >= 3 + q) ? ca[2 + q] : n;
         st = parse_i64(s + a, b - a, &r->i[q]);
-        if (st) return num_status_to_err(st, false);
-        if (r->i[q] > (1ll << 52) || r->i[q] < -(1ll << 52)) return E_RANGE;
+        if (st == P_UNSUPPORTED || (st == P_OK && (r->i[q] > (1ll << 52) || r->i[q] < -(1ll << 52)))) { r->pad |= (uint16_t)(1u << q); r->i[q] = 0; }
+        else if (st) { r->flag |= (uint8_t)(1u << q); r->i[q] = 0; }
     }
     r->cls = 1;
+    return E_OK;
+}
+SOFA_HD int s2_disk_need(const S2Line& x, unsigned bits) {           // the row needs the fields in `bits` (6 = m[0]) of line x
+    if (x.flag & bits) return (x.flag & bits & 0x40u) ? E_BAD_FLOAT : E_BAD_INT;
+    if (x.pad & bits) return E_UNSUPPORTED_NUM;
     return E_OK;
 }
 struct DiskRow {
@@ -203,6 +213,8 @@ struct DiskRow {
 SOFA_HD int s2_disk_row(const S2Line& m, const S2Line& l, int64_t secsize, int absolute, double time_base, DiskRow* o) {
     const int64_t lim = 1ll << 52;
     if (secsize <= 0 || secsize > (1 << 20)) return E_RANGE;
+    int need = s2_disk_need(m, 0x4fu); if (need) return need;       // m[0], m[2..5] of both lines
+    need = s2_disk_need(l, 0x4fu); if (need) return need;
     __int128 dr = ((__int128)m.i[0] - l.i[0]) * secsize, dw = ((__int128)m.i[1] - l.i[1]) * secsize;
     __int128 dt = dr + dw;
     if (dr >= lim || dr <= -lim || dw >= lim || dw <= -lim || dt >= lim || dt <= -lim) return E_RANGE;
@@ -216,6 +228,9 @@ SOFA_HD int s2_disk_row(const S2Line& m, const S2Line& l, int64_t secsize, int a
     if (!d_isfinite(o->tbw) || !d_isfinite(o->rbw) || !d_isfinite(o->wbw)) return E_FORMAT;
     if (!py_round2(d_div(o->tbw, 1048576.0), &o->thr)) return E_FORMAT;
     int64_t r_io = m.i[2] - l.i[2], w_io = m.i[3] - l.i[3];
+    const unsigned lazy = ((r_io > 0 || r_io + w_io > 0) ? 0x10u : 0u) | ((w_io > 0 || r_io + w_io > 0) ? 0x20u : 0u);
+    need = s2_disk_need(m, lazy); if (need) return need;            // int(m[6]) / int(m[7]) only where the reference evaluates them
+    need = s2_disk_need(l, lazy); if (need) return need;
     int64_t r_ms = m.i[4] - l.i[4], w_ms = m.i[5] - l.i[5];
     int e = trunc_i64(d_div((double)r_io, o->dur), &o->r_iops); if (e) return e;
     e = trunc_i64(d_div((double)w_io, o->dur), &o->w_iops); if (e) return e;
