@@ -27,9 +27,9 @@ CASES = {
     # + vmstat.txt and nvsmi.txt (1 Hz), every optional series switched on
     "side_full": (dict(seed=93, n_samples=50, n_cores=3, n_gpus=2, hz1=dict(n_seconds=30, n_gpus=2)),
                   dict(enable_vmstat=True, enable_encode_decode=True)),
-    # diskstat.txt (oracle-only fixture: the device path does not cover diskstat yet)
+    # diskstat.txt (+ the files of side_small)
     "disk_small": (dict(seed=95, n_samples=30, n_cores=2, n_gpus=1, disk=dict(n_samples=40)), dict()),
-    # strace.txt + blktrace.txt (oracle-only fixture, opt-in recorder outputs; vmstat / nvsmi give `cpuid` its value)
+    # strace.txt + blktrace.txt + pystacks.txt (opt-in recorder outputs; vmstat / nvsmi give `cpuid` its value)
     "oracle_strace_blk": (dict(seed=96, n_samples=30, n_cores=2, n_gpus=2, hz1=dict(n_seconds=10, n_gpus=2),
                                strace=dict(n_strace=300, n_blk=200)), dict(plot_ratio=2)),
     "side_abs": (dict(seed=94, n_samples=40, n_cores=2, n_gpus=3, hz1=dict(n_seconds=12, n_gpus=3)),

@@ -17,7 +17,7 @@ def golden_cases():
     out = []
     for name in sorted(os.listdir(GOLDEN)):
         p = os.path.join(GOLDEN, name, "case.json")
-        if os.path.isfile(p) and not name.startswith(("side_", "disk_", "oracle_", "driver_", "aisi_")):      # side-file fixtures (disk_* / oracle_*: oracle only)
+        if os.path.isfile(p) and not name.startswith(("side_", "disk_", "oracle_", "driver_", "aisi_")):      # fixtures of other test families (side files, driver stdout, AISI)
             out.append(name)
     return out
 

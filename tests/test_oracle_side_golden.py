@@ -49,7 +49,7 @@ def test_oracle_nvsmi_profile_matches_reference(name):
 
 
 def test_oracle_diskstat_matches_reference(tmp_path):
-    """diskstat.txt (N1, oracle only so far): diskstat.csv, both vector tables and the report.js series."""
+    """diskstat.txt (N1): diskstat.csv, both vector tables and the report.js series."""
     import shutil
     from helpers import demangle
     name = "disk_small"
@@ -67,7 +67,7 @@ def test_oracle_diskstat_matches_reference(tmp_path):
 
 
 def test_oracle_strace_blktrace_match_reference(tmp_path):
-    """strace.txt / blktrace.txt / pystacks.txt (N1, oracle only so far): their CSVs and report.js series."""
+    """strace.txt / blktrace.txt / pystacks.txt (N1): their CSVs and report.js series."""
     import shutil
     import time
     from helpers import demangle
