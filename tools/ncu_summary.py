@@ -99,7 +99,7 @@ def traffic(raw_path, events):
     out = {}
     for r in raw[2:]:
         name = r[col["Kernel Name"]]
-        m = re.search(r"(k_parse_tma|k_parse|k_emit_fused)<\(?(?:int\))?(\d)(?:, \(?(?:(?:int|bool)\))?(\w+))?>", name)
+        m = re.search(r"(k_parse_tma|k_parse|k_emit_fused)<\(?(?:int\))?(\d)(?:, \(?(?:(?:int|bool)\))?(\w+))?(?:, \(?(?:(?:int|bool)\))?\w+)?>", name)
         if not m:
             continue
         if m.group(1) == "k_parse" and m.group(3) in ("1", "true"):
