@@ -190,3 +190,41 @@ def test_storage_sources_match_oracle_larger(ratio, absolute, tmp_path):
     orc.preprocess(orc.OracleConfig(b, nprocs=1, plot_ratio=ratio, absolute_timestamp=absolute, diskstat_filters="xda1"), demangle=demangle)
     for fn in STORAGE_OUTPUTS:
         assert_same(open(a + fn, "rb").read(), open(b + fn, "rb").read(), fn)
+
+
+def test_storage_sources_edge_cases(tmp_path):
+    """empty / degenerate diskstat, blktrace, strace and pystacks files: the product writes (or leaves out) the same
+    files as the reference path"""
+    from helpers import STORAGE_OUTPUTS
+
+    def disk_one_sample(d):                      # fewer lines than devices: header-only CSVs, no series
+        open(d + "diskstat.txt", "w").write("1600000000.5,sda,1,2,3,4,5,6\n1600000000.5,sdb,1,2,3,4,5,6\n")
+        open(d + "vmstat.txt", "w").write(open(os.path.join(GOLDEN, "oracle_strace_blk", "vmstat.txt")).read())
+
+    def disk_empty(d):
+        open(d + "diskstat.txt", "w").close()
+
+    def disk_no_final_newline(d):                # the reference drops the last character of the last line
+        t = open(os.path.join(GOLDEN, "disk_small", "diskstat.txt")).read()
+        open(d + "diskstat.txt", "w").write(t.rstrip("\n") + "9")
+
+    def blk_footer_only(d):                      # no accepted line: both lists empty, no file, `cpuid` stays unset
+        open(d + "blktrace.txt", "w").write("CPU0 (8,0):\n Reads Queued:           0,        0KiB\t Writes Queued:         100,    51200KiB\n")
+
+    def blk_empty_and_short_strace(d):
+        open(d + "blktrace.txt", "w").close()
+        open(d + "strace.txt", "w").write("4242 1600000000.402969 read(3, \"abc\", 4096) = 4 <0.121879>\n")      # one line: ignored
+
+    def strace_all_filtered(d):
+        open(d + "vmstat.txt", "w").write(open(os.path.join(GOLDEN, "oracle_strace_blk", "vmstat.txt")).read())
+        open(d + "strace.txt", "w").write("1 1600000000.4 close(3) = 0 <0.1>\n2 1600000000.5 nanosleep({1}, NULL) = 0 <0.2>\n")
+
+    def py_two_stacks(d):                        # one row left after the last is deleted, and that one is lost: warning only
+        open(d + "vmstat.txt", "w").write(open(os.path.join(GOLDEN, "oracle_strace_blk", "vmstat.txt")).read())
+        open(d + "pystacks.txt", "w").write("1600000000500000\na;b\n1600000000600000\nc\n")
+
+    from helpers import GOLDEN
+    outputs = tuple(o for o in SIDE_OUTPUTS)
+    for mut in (disk_one_sample, disk_empty, disk_no_final_newline, blk_footer_only, blk_empty_and_short_strace, strace_all_filtered,
+                py_two_stacks):
+        oracle_vs_product(tmp_path / mut.__name__, mut)
