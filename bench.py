@@ -876,6 +876,18 @@ def parity_sample(oracle_dir, product_dir):
     return compared
 
 
+def reference_available():
+    """oracle/_ref/bin (the reference's own modules, copied there by oracle/build_ref.py) travelled with this checkout"""
+    from oracle import ref_runner
+    return ref_runner.available()
+
+
+def reference_pass_timed(logdir, repeat=1):
+    """the UNMODIFIED reference's sofa_preprocess(cfg) + sofa_analyze(cfg) on logdir, in a child interpreter -> seconds per pass"""
+    from oracle import ref_runner
+    return ref_runner.run_in_subprocess(logdir, CPU_FILTERS, repeat)
+
+
 def cpu_baseline_sample(args, wl):
     import multiprocessing as mp
     n = args.cpu_sample
@@ -889,17 +901,45 @@ def cpu_baseline_sample(args, wl):
     pdir = os.path.join(work, "product") + "/"
     shutil.copytree(logdir, pdir)
     cores = mp.cpu_count()
-    t0 = time.perf_counter()
-    oracle_pass(logdir, cores)
-    dt = time.perf_counter() - t0
+    use_ref = reference_available() and args.cpu_baseline != "port"
+    ref_error = None
+    if use_ref:
+        # the reference itself (oracle/_ref), and the same logdir through the oracle port: the restatement is checked here too
+        odir = os.path.join(work, "port") + "/"
+        shutil.copytree(logdir, odir)
+        try:
+            dt = reference_pass_timed(logdir)[0]
+        except Exception as e:                                    # never lose the bench line to the baseline leg
+            ref_error = str(e)[-400:]
+            use_ref = False
+            shutil.rmtree(logdir)
+            shutil.copytree(odir, logdir)
+        if use_ref:
+            t0 = time.perf_counter()
+            oracle_pass(odir, cores)
+            dt_port = time.perf_counter() - t0
+            parity_sample(logdir, odir)
+    if not use_ref:
+        t0 = time.perf_counter()
+        oracle_pass(logdir, cores)
+        dt = time.perf_counter() - t0
+        dt_port = dt
     # the same logdir through the CUDA path's public entry points: every output file must be byte-identical
     pdt = product_pass(pdir, wl.eng_device)
     files = parity_sample(logdir, pdir)
     shutil.rmtree(work, ignore_errors=True)
-    return {"value": n / dt, "unit": "events/s", "cores": cores, "kind": "port",
-            "sample": "first %d events of the same mixed trace (60/35/5), oracle preprocess (trace + side files) + gpu/net/nvsmi profiles + concurrency_breakdown, %.1f s" % (n, dt),
-            "parity_sample": "identical", "parity_files": files,
-            "entrypoints_s_on_sample": round(pdt, 3)}
+    what = ("the UNMODIFIED reference (oracle/_ref: sofa_preprocess(cfg) + sofa_analyze(cfg), run-time import stubs and pandas-3 shims)"
+            if use_ref else "oracle preprocess (trace + side files) + gpu/net/nvsmi profiles + concurrency_breakdown")
+    out = {"value": n / dt, "unit": "events/s", "cores": cores, "kind": "reference" if use_ref else "port",
+           "sample": "first %d events of the same mixed trace (60/35/5), %s, %.1f s" % (n, what, dt),
+           "parity_sample": "identical", "parity_against": "reference" if use_ref else "port", "parity_files": files,
+           "entrypoints_s_on_sample": round(pdt, 3)}
+    if use_ref:
+        out["port_value"] = n / dt_port
+        out["port_equals_reference_on_sample"] = True
+    if ref_error:
+        out["reference_error"] = ref_error
+    return out
 
 
 def run_reference(args):
@@ -910,38 +950,66 @@ def run_reference(args):
     cores = mp.cpu_count()
     n = args.cpu_sample
     import shutil
-    # Two sample sizes: the rate is the MARGINAL one, (n2 - n1) events / (t2 - t1), so that the fixed costs of a pass (pool
-    # start-up, imports, small-frame overheads) do not pass for per-event cost; both raw timings are reported.
-    n1, n2 = max(1000, n // 3), n
-    if n1 >= n2:
-        n1 = max(1, n2 // 2)
-    times = {}
-    for nn in (n1, n2):
+    use_ref = reference_available() and args.cpu_baseline != "port"
+
+    state = {"use_ref": use_ref, "error": None}
+
+    def one_pass(logdir, repeat):
+        if state["use_ref"]:
+            try:
+                return reference_pass_timed(logdir, repeat)
+            except Exception as e:                                # fall back to the port rather than print nothing
+                state["use_ref"], state["error"] = False, str(e)[-400:]
+        out = []
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            oracle_pass(logdir, cores)
+            out.append(time.perf_counter() - t0)
+        return out
+
+    def sample_dir(nn):
         work = tempfile.mkdtemp(prefix="sofa_ref_")
         logdir = os.path.join(work, "sofalog") + "/"
         os.makedirs(logdir)
         write_sample_logdir(logdir, nn, SEED)
-        for _ in range(min(args.warmup, 1)):
-            oracle_pass(logdir, cores)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            oracle_pass(logdir, cores)
-        times[nn] = (time.perf_counter() - t0) / args.steps
+        return work, logdir
+    # Two sample sizes: the rate is the MARGINAL one, (n2 - n1) events / (t2 - t1), so that the fixed costs of a pass (pool
+    # start-up, imports, small-frame overheads) do not pass for per-event cost; both raw timings are reported.  The sizes are
+    # chosen from a calibration pass so that `--steps K` passes of both fit ~150 s whatever K the driver asks for.
+    n0 = max(1000, min(n, 20000))
+    work, logdir = sample_dir(n0)
+    t_cal = one_pass(logdir, 1 + min(args.warmup, 1))[-1]
+    shutil.rmtree(work, ignore_errors=True)
+    budget = float(os.environ.get("SOFA_B200_REF_BUDGET_S", "150"))
+    n2 = int(max(n0, min(n, (n0 / t_cal) * budget / (1.4 * max(1, args.steps)))))
+    n1 = max(1000, n2 // 3)
+    if n1 >= n2:
+        n1 = max(1, n2 // 2)
+    times = {}
+    for nn in (n1, n2):
+        work, logdir = sample_dir(nn)
+        ts = one_pass(logdir, args.steps)
+        times[nn] = sum(ts) / len(ts)
         shutil.rmtree(work, ignore_errors=True)
     dt = times[n2]
     marginal = (n2 - n1) / max(1e-9, times[n2] - times[n1]) if times[n2] > times[n1] else n2 / dt
     v = marginal
-    sample = ("CPU port of the reference path on the first %d and %d events of the mixed trace (60/35/5): %.2f s and %.2f s per pass; "
+    use_ref = state["use_ref"]
+    who = ("the UNMODIFIED reference (oracle/_ref, sofa_preprocess + sofa_analyze, %d host cores)" % cores if use_ref
+           else "CPU port of the reference path")
+    sample = ("%s on the first %d and %d events of the mixed trace (60/35/5): %.2f s and %.2f s per pass; "
               "value = marginal rate between the two sizes (whole-pass rate at %d events: %.0f events/s)"
-              % (n1, n2, times[n1], times[n2], n2, n2 / dt))
+              % (who, n1, n2, times[n1], times[n2], n2, n2 / dt))
     line = {"impl": "reference", "metric": "trace events/s (preprocess+analyze)", "value": v, "unit": "events/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64/int64", "data": "synthetic",
             "config": {"workload": "100 M-event mixed perf+CUPTI+tcpdump trace with cpu_filters/gpu_filters tagging (BASELINE configs[2])",
                        "sample": sample, "same_config": False, "cpu_filters": CPU_FILTERS, "gpu_filters": GPU_KWS, "plot_ratio": 1},
-            "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "reference" if use_ref else "port", "sample": sample},
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if state["error"]:
+        line["config"]["reference_error"] = state["error"]
     print(json.dumps(line))
 
 
@@ -953,6 +1021,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=100000000, help="events per GPU (default: BASELINE configs[2])")
     ap.add_argument("--cpu-sample", type=int, default=300000, help="events in the CPU baseline sample (the parity sample of the default arm; the larger of the two sizes of --impl reference)")
+    ap.add_argument("--cpu-baseline", default="auto", choices=["auto", "reference", "port"],
+                    help="auto: the unmodified reference from oracle/_ref when it travelled with the checkout, else the oracle port")
     ap.add_argument("--entry-events", type=int, default=10000000,
                     help="events of the logdir that goes through sofa_preprocess + sofa_analyze themselves (e2e_entrypoints; 0 = skip)")
     ap.add_argument("--strong", type=int, default=1,

@@ -26,7 +26,9 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert KEYS <= set(d)
     assert d["impl"] == "reference" and d["unit"] == "events/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    if os.path.isfile(os.path.join(REPO, "oracle", "_ref", "bin", "sofa_preprocess.py")):
+        assert d["cpu_baseline"]["kind"] == "reference" and "reference_error" not in d["config"]     # the unmodified reference ran
     assert d["e2e"] == {"value": d["value"], "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None and d["gpu_launches"] == 0
 
@@ -35,3 +37,23 @@ def test_reference_arm_other_ranks_stay_silent():
     out = run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29599"})
     assert out.returncode == 0, out.stderr[-2000:]
     assert not [ln for ln in out.stdout.split("\n") if ln.startswith("{")]
+
+
+def test_port_equals_the_unmodified_reference_on_a_bench_sample(tmp_path):
+    """oracle/_ref (the reference's own modules, oracle/build_ref.py) and the oracle port on the same 20 k-event slice of the
+    bench workload: all twelve output files byte-identical.  Skipped where the reference was never built into oracle/_ref."""
+    import shutil
+    import pytest
+    sys.path.insert(0, REPO)
+    import bench
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref is not built (needs /root/reference at build time)")
+    a, b = str(tmp_path / "ref") + "/", str(tmp_path / "port") + "/"
+    os.makedirs(a)
+    bench.write_sample_logdir(a, 20000, bench.SEED)
+    shutil.copytree(a, b)
+    secs = ref_runner.run_in_subprocess(a, bench.CPU_FILTERS)
+    assert len(secs) == 1 and secs[0] > 0
+    bench.oracle_pass(b, 4)
+    assert set(bench.parity_sample(a, b)) == set(bench.PARITY_FILES)
