@@ -57,3 +57,21 @@ def test_port_equals_the_unmodified_reference_on_a_bench_sample(tmp_path):
     assert len(secs) == 1 and secs[0] > 0
     bench.oracle_pass(b, 4)
     assert set(bench.parity_sample(a, b)) == set(bench.PARITY_FILES)
+
+
+def test_oracle_ref_holds_the_reference_unmodified():
+    """oracle/_ref/bin is a byte-for-byte copy of the modules under /root/reference/bin (build container only) and is
+    kept out of the history"""
+    import glob
+    import pytest
+    if not os.path.isdir("/root/reference/bin"):
+        pytest.skip("no /root/reference here")
+    sys.path.insert(0, REPO)
+    from oracle import build_ref
+    assert build_ref.build_ref() >= 10
+    for p in glob.glob("/root/reference/bin/*.py"):
+        q = os.path.join(REPO, "oracle", "_ref", "bin", os.path.basename(p))
+        assert open(p, "rb").read() == open(q, "rb").read(), q
+    tracked = subprocess.run(["git", "ls-files", "oracle/_ref"], capture_output=True, text=True, cwd=REPO).stdout.strip()
+    assert tracked == ""
+    assert "oracle/_ref/" in open(os.path.join(REPO, ".gitignore")).read()
