@@ -66,7 +66,7 @@ def reference_pass(logdir, overrides=None, analyze=True):
     return cfg
 
 
-def run_in_subprocess(logdir, cpu_filters=None, repeat=1, timeout=3600):
+def run_in_subprocess(logdir, cpu_filters=None, repeat=1, timeout=3600, overrides=None, analyze=True):
     """reference_pass in a child interpreter (its import stubs and pandas shims stay out of the caller's process);
     -> list of wall-clock seconds of `sofa_preprocess(cfg) + sofa_analyze(cfg)`, one per repeat (imports excluded)"""
     import json
@@ -74,6 +74,10 @@ def run_in_subprocess(logdir, cpu_filters=None, repeat=1, timeout=3600):
     cmd = [sys.executable, os.path.abspath(__file__), logdir, "--repeat", str(repeat)]
     if cpu_filters:
         cmd += ["--cpu_filters", cpu_filters]
+    if overrides:
+        cmd += ["--overrides", json.dumps(overrides)]
+    if not analyze:
+        cmd += ["--no-analyze"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     if out.returncode != 0:
         raise RuntimeError("the reference failed on %s:\n%s" % (logdir, out.stderr[-3000:]))
@@ -89,6 +93,8 @@ if __name__ == "__main__":
     ap.add_argument("logdir")
     ap.add_argument("--cpu_filters")
     ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--overrides", help="JSON dict of cfg attributes (plot_ratio, absolute_timestamp, ...)")
+    ap.add_argument("--no-analyze", action="store_true")
     a = ap.parse_args()
     if not available():
         sys.exit("oracle/_ref/bin is not built (python oracle/build_ref.py in the build container)")
@@ -96,6 +102,9 @@ if __name__ == "__main__":
     secs = []
     for _ in range(a.repeat):
         t0 = time.perf_counter()
-        reference_pass(a.logdir, dict(cpu_filters=a.cpu_filters) if a.cpu_filters else None)
+        ov = json.loads(a.overrides) if a.overrides else {}
+        if a.cpu_filters:
+            ov["cpu_filters"] = a.cpu_filters
+        reference_pass(a.logdir, ov, analyze=not a.no_analyze)
         secs.append(time.perf_counter() - t0)
     print(json.dumps({"seconds": secs}))

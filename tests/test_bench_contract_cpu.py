@@ -39,11 +39,15 @@ def test_reference_arm_other_ranks_stay_silent():
     assert not [ln for ln in out.stdout.split("\n") if ln.startswith("{")]
 
 
-def test_port_equals_the_unmodified_reference_on_a_bench_sample(tmp_path):
-    """oracle/_ref (the reference's own modules, oracle/build_ref.py) and the oracle port on the same 20 k-event slice of the
-    bench workload: all twelve output files byte-identical.  Skipped where the reference was never built into oracle/_ref."""
+import pytest
+
+
+@pytest.mark.parametrize("n_events", [20000, 100000])
+def test_port_equals_the_unmodified_reference_on_a_bench_sample(n_events, tmp_path):
+    """oracle/_ref (the reference's own modules, oracle/build_ref.py) and the oracle port on the same slice of the bench
+    workload (preprocess + the whole analyze driver): all twelve output files byte-identical.  Skipped where the
+    reference was never built into oracle/_ref."""
     import shutil
-    import pytest
     sys.path.insert(0, REPO)
     import bench
     from oracle import ref_runner
@@ -51,7 +55,7 @@ def test_port_equals_the_unmodified_reference_on_a_bench_sample(tmp_path):
         pytest.skip("oracle/_ref is not built (needs /root/reference at build time)")
     a, b = str(tmp_path / "ref") + "/", str(tmp_path / "port") + "/"
     os.makedirs(a)
-    bench.write_sample_logdir(a, 20000, bench.SEED)
+    bench.write_sample_logdir(a, n_events, bench.SEED)
     shutil.copytree(a, b)
     secs = ref_runner.run_in_subprocess(a, bench.CPU_FILTERS)
     assert len(secs) == 1 and secs[0] > 0

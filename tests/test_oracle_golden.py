@@ -59,3 +59,27 @@ def test_oracle_net_profile_matches_reference(name, tmp_path):
     assert [(n, float(v)) for n, v in feats] == [tuple(x) for x in case["features"]["__net_features__"][1:]]
     with open(logdir + "netrank.csv", "rb") as f:
         assert f.read() == golden_bytes(name, "netrank.csv")
+
+
+@pytest.mark.parametrize("kw,ratio", [
+    (dict(seed=101, n_perf=30000, n_gpu=20000, n_net=10000, non_ip_pct=1), 7),
+    (dict(seed=102, n_perf=25000, cpu_col=True, n_gpu=15000, units="ms_us_KB", p2p_cols=True, n_net=5000, non_ip_pct=0), 1),
+])
+def test_oracle_equals_unmodified_reference_on_the_larger_gpu_test_logs(kw, ratio, tmp_path):
+    """The logdirs of tests/test_gpu_parity.py::test_cuda_path_matches_oracle_on_larger_logs through the UNMODIFIED reference
+    (oracle/_ref, child interpreter) and through the oracle: the device is compared with the oracle there, the oracle with
+    the reference here - at sizes far beyond the golden fixtures."""
+    import shutil
+    from sofa_b200 import synth
+    from helpers import demangle
+    from oracle import ref_runner
+    from oracle import sofa_oracle as orc
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref is not built (needs /root/reference at build time)")
+    a, b = str(tmp_path / "ref") + "/", str(tmp_path / "orc") + "/"
+    synth.make_logdir(a, **kw)
+    shutil.copytree(a, b)
+    ref_runner.run_in_subprocess(a, "idle:black,tensorflow:orange", overrides=dict(plot_ratio=ratio), analyze=False)
+    orc.preprocess(orc.OracleConfig(b, plot_ratio=ratio, cpu_filters="idle:black,tensorflow:orange"), demangle=demangle)
+    for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+        assert open(a + fn, "rb").read() == open(b + fn, "rb").read(), fn

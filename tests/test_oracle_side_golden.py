@@ -82,3 +82,64 @@ def test_oracle_strace_blktrace_match_reference(tmp_path):
     orc.preprocess(orc.OracleConfig(logdir, nprocs=1, **case["cfg"]), demangle=demangle)
     for fn in ("strace.csv", "blktrace.csv", "pystacks.csv", "vmstat.csv", "nvsmi_trace.csv", "report.js"):
         assert open(logdir + fn, "rb").read() == open(os.path.join(d, fn), "rb").read(), fn
+
+
+def test_oracle_equals_unmodified_reference_on_storage_logdir(tmp_path):
+    """The logdir the GPU test feeds to the device (diskstat / blktrace / strace / pystacks at several thousand lines, with
+    the odd lines the reference tolerates) through the UNMODIFIED reference (oracle/_ref, child interpreter) and through
+    the oracle: every file identical.  Together with tests/test_gpu_parity.py::test_storage_sources_device_match_oracle_larger
+    this ties the device output to the reference itself beyond the small golden fixtures."""
+    import shutil
+    import pytest
+    from helpers import make_storage_logdir, STORAGE_OUTPUTS, SIDE_OUTPUTS, demangle
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref is not built (needs /root/reference at build time)")
+    for k, over in enumerate((dict(plot_ratio=1), dict(plot_ratio=3, absolute_timestamp=True, diskstat_filters="xda1"))):
+        a = str(tmp_path / ("ref%d" % k)) + "/"
+        make_storage_logdir(a, n_disk=300, n_strace=2500, n_blk=3000, n_py=500)
+        b = str(tmp_path / ("orc%d" % k)) + "/"
+        shutil.copytree(a, b)
+        ref_runner.run_in_subprocess(a, None, overrides=over, analyze=False)
+        orc.preprocess(orc.OracleConfig(b, nprocs=1, **over), demangle=demangle)
+        for fn in sorted(set(STORAGE_OUTPUTS) | set(SIDE_OUTPUTS)):
+            ea, eb = os.path.isfile(a + fn), os.path.isfile(b + fn)
+            assert ea == eb, fn
+            if ea:
+                assert open(a + fn, "rb").read() == open(b + fn, "rb").read(), (over, fn)
+
+
+def test_oracle_equals_unmodified_reference_on_the_larger_side_logdir(tmp_path):
+    """The side-file logdir of tests/test_gpu_parity.py::test_side_sources_device_match_oracle_larger_and_edge_cases (620 samples
+    x 64 cores x 8 GPUs, 3000 s of 1 Hz files, repeated nvidia-smi blocks, malformed mpstat lines) through the UNMODIFIED
+    reference and through the oracle."""
+    import shutil
+    import time
+    import pytest
+    from sofa_b200 import synth
+    from helpers import demangle
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref is not built (needs /root/reference at build time)")
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
+    a = str(tmp_path / "ref") + "/"
+    synth.make_logdir(a, seed=11, n_perf=500)
+    synth.write_side_raw(a, seed=12, n_samples=620, n_cores=64, n_gpus=8)
+    synth.write_side_raw_1hz(a, seed=13, n_seconds=3000, n_gpus=8)
+    with open(a + "nvsmi_query.txt", "a") as f:
+        body = open(a + "nvsmi_query.txt").read().split("\n")[1:-1]
+        for rep in range(3):
+            f.write("\n".join(body) + "\n")
+    lines = open(a + "mpstat.txt").read().split("\n")
+    lines.insert(1000, "1600000004.1,2,77")
+    lines.insert(2000, "")
+    lines[3000] += ",1"
+    open(a + "mpstat.txt", "w").write("\n".join(lines))
+    b = str(tmp_path / "orc") + "/"
+    shutil.copytree(a, b)
+    over = dict(nvsmi_time_zone=-5, enable_vmstat=True, enable_encode_decode=True)
+    ref_runner.run_in_subprocess(a, None, overrides=over, analyze=False)
+    orc.preprocess(orc.OracleConfig(b, nprocs=1, **over), demangle=demangle)
+    for fn in ("mpstat.csv", "usr_sys.csv", "nvsmi_trace.csv", "netstat.csv", "netbandwidth.csv", "vmstat.csv", "report.js"):
+        assert open(a + fn, "rb").read() == open(b + fn, "rb").read(), fn
