@@ -66,6 +66,23 @@ def reference_pass(logdir, overrides=None, analyze=True):
     return cfg
 
 
+def run_batch_in_subprocess(items, timeout=3600):
+    """items: [(logdir, overrides dict)] -> [{"ok": True} | {"raised": "<exception type>"}], preprocess only, all in ONE
+    child interpreter (fuzz tests: what does the reference do with this input?)"""
+    import json
+    import subprocess
+    spec = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump([[d, ov] for d, ov in items], spec)
+    spec.close()
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--batch", spec.name], capture_output=True, text=True, timeout=timeout)
+    finally:
+        os.unlink(spec.name)
+    if out.returncode != 0:
+        raise RuntimeError("the reference batch failed:\n%s" % out.stderr[-3000:])
+    return json.loads([ln for ln in out.stdout.split("\n") if ln.startswith("[")][-1])
+
+
 def run_in_subprocess(logdir, cpu_filters=None, repeat=1, timeout=3600, overrides=None, analyze=True):
     """reference_pass in a child interpreter (its import stubs and pandas shims stay out of the caller's process);
     -> list of wall-clock seconds of `sofa_preprocess(cfg) + sofa_analyze(cfg)`, one per repeat (imports excluded)"""
@@ -90,7 +107,8 @@ if __name__ == "__main__":
     import json
     import time
     ap = argparse.ArgumentParser()
-    ap.add_argument("logdir")
+    ap.add_argument("logdir", nargs="?")
+    ap.add_argument("--batch", help="JSON file: [[logdir, overrides], ...]; preprocess only, one result per entry")
     ap.add_argument("--cpu_filters")
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--overrides", help="JSON dict of cfg attributes (plot_ratio, absolute_timestamp, ...)")
@@ -99,6 +117,18 @@ if __name__ == "__main__":
     if not available():
         sys.exit("oracle/_ref/bin is not built (python oracle/build_ref.py in the build container)")
     _setup()
+    if a.batch:
+        res = []
+        for d, ov in json.load(open(a.batch)):
+            try:
+                reference_pass(d, ov, analyze=False)
+                res.append({"ok": True})
+            except SystemExit as e:
+                res.append({"raised": "SystemExit"})
+            except BaseException as e:                     # what the reference raises is the answer
+                res.append({"raised": type(e).__name__})
+        print(json.dumps(res))
+        sys.exit(0)
     secs = []
     for _ in range(a.repeat):
         t0 = time.perf_counter()

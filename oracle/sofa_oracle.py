@@ -689,20 +689,30 @@ def preprocess(cfg, demangle=lambda s: s, emit_json=True):
             write_trace_csv(frame(res), logdir + 'cuda_api_trace.csv')
             api_viz = frame(downsample(res, cfg.plot_ratio))
 
-    # ---- CPU  :1786-1838
+    # ---- CPU  :1783-1838.  The reference wraps this whole section in a bare `except:` (:1836-1837): a sample that cannot be
+    # converted costs the CPU trace ("no perf traces."), not the run - unlike the nvprof and tcpdump sections, which raise.
     if os.path.isfile(logdir + 'perf.script'):
-        with open(logdir + 'perf.script') as f:
-            samples = f.readlines()
-        if len(samples) > 0:
-            res = _pmap(partial(parse_perf_sample, absolute_timestamp=cfg.absolute_timestamp,
-                                time_base=time_base, t_offset=cpu_t_offset, mhz_xp=xp, mhz_fp=fp,
-                                perf_events=perf_events), samples, cfg.nprocs)
-            cpu_traces = frame(res)
-            write_trace_csv(cpu_traces, logdir + 'cputrace.csv')
-            cpu_viz = frame(downsample(res, cfg.plot_ratio))
-            cpu_viz['name'] = cpu_viz['name'].apply(lambda x: viz_name(x, demangle))
-            for kw, color in cfg.cpu_filters:                    # :1819-1827
-                filtered_cpu.append((kw, color, cpu_viz[cpu_viz['name'].str.contains(kw)]))
+        viz_assigned = False
+        try:
+            with open(logdir + 'perf.script') as f:
+                samples = f.readlines()
+            if len(samples) > 0:
+                res = _pmap(partial(parse_perf_sample, absolute_timestamp=cfg.absolute_timestamp,
+                                    time_base=time_base, t_offset=cpu_t_offset, mhz_xp=xp, mhz_fp=fp,
+                                    perf_events=perf_events), samples, cfg.nprocs)
+                cpu_traces = frame(res)
+                write_trace_csv(cpu_traces, logdir + 'cputrace.csv')
+                cpu_viz = frame(downsample(res, cfg.plot_ratio))
+                viz_assigned = True
+                cpu_viz['name'] = cpu_viz['name'].apply(lambda x: viz_name(x, demangle))
+                for kw, color in cfg.cpu_filters:                # :1819-1827
+                    filtered_cpu.append((kw, color, cpu_viz[cpu_viz['name'].str.contains(kw)]))
+        except Exception:
+            print('[WARNING] no perf traces.')
+            if viz_assigned:
+                # past the point where cpu_traces_viz holds rows (:1808), e.g. cxxfilt.InvalidName: the swallowed exception
+                # leaves `filtered_groups` unassigned and the series assembly (:1861) dies on it
+                raise UnboundLocalError("cannot access local variable 'filtered_groups' where it is not associated with a value")
 
     # ---- strace  :1618-1704 (after the trace sources in the reference; it only needs `cpuid` from above)
     if os.path.isfile(logdir + 'strace.txt'):

@@ -659,6 +659,14 @@ def _preprocess(cfg, eng, io):
                     cpu_series.append(SeriesOut(flt.keyword, '[keyword]' + flt.keyword, flt.color, rec, nrec))
     except IOError:
         print_warning(cfg, 'no perf traces.')
+    except Exception as e:
+        # The reference wraps its whole perf section in a bare `except:` (:1783-1837): a sample it cannot convert (too few
+        # fields, float() / int() ValueError) costs the CPU trace - this warning, no cputrace.csv, no cpu series - not the
+        # run; the nvprof and tcpdump sections have no such net and raise.  Spellings only this codec refuses stay loud.
+        if getattr(e, 'row_code', None) not in (1, 2, 3, 5):
+            raise
+        print_warning(cfg, 'no perf traces.')
+        cpu_series = []
 
     if io.rank == 0:
         side.update(_strace_pystacks(cfg, eng, logdir, ratio))

@@ -56,7 +56,16 @@ class HsSide2Info(ctypes.Structure):
 
 
 class HostSimError(RuntimeError):
-    pass
+    """row errors carry `row_code` like sofa_b200._lib.SofaB200Error"""
+    row_code = None
+
+
+def _row_error(r):
+    e = HostSimError("row %d: error %d" % (r // 1000, r % 1000))
+    e.row_code = r % 1000
+    return e
+
+
 
 
 class HostSimEngine:
@@ -96,7 +105,7 @@ class HostSimEngine:
                                 ctypes.c_uint(fmask), kw.encode() if kw else None, d, out,
                                 ctypes.byref(outlen), ctypes.byref(flags), ctypes.byref(nrec))
         if r != -1:
-            raise HostSimError("row %d: error %d" % (r // 1000, r % 1000))
+            raise _row_error(r)
         return np.frombuffer(out.raw[:outlen.value], dtype=np.uint8), flags.value, nrec.value
 
     def load(self, kind, text, params, data_off=0):
@@ -196,7 +205,7 @@ class HostSimEngine:
                              ctypes.c_longlong(local_off), ctypes.c_double(tz_add), mode, out, ctypes.byref(outlen),
                              ctypes.byref(nrec), ctypes.byref(nlines), ctypes.byref(ncand), ctypes.byref(nodata))
         if r != -1:
-            raise HostSimError("row %d: error %d" % (r // 1000, r % 1000))
+            raise _row_error(r)
         return np.frombuffer(out.raw[:outlen.value], dtype=np.uint8), nrec.value, nlines.value, ncand.value, bool(nodata.value)
 
     def side_preprocess(self, raw_src, text, time_base, absolute_timestamp, local_utc_offset=0, nvsmi_tz_add=0.0,
@@ -240,7 +249,7 @@ class HostSimEngine:
         r = self.lib.hs_side2(st['table'], text, ctypes.c_long(len(text)), ctypes.byref(p), what, out, ctypes.byref(outlen),
                               ctypes.byref(nrows), ctypes.byref(info))
         if r != -1:
-            raise HostSimError("row %d: error %d" % (r // 1000, r % 1000))
+            raise _row_error(r)
         return np.frombuffer(out.raw[:outlen.value], dtype=np.uint8), nrows.value, info
 
     def side2_preprocess(self, table, text, time_base, absolute_timestamp, plot_ratio=1, pid=0, strace_min_time=0.0, category=None):

@@ -86,15 +86,24 @@ def test_columns_bit_exact(tmp_path):
 
 
 def test_malformed_line_fails_loudly(tmp_path):
+    """nvprof / tcpdump text: a record the reference dies on (IndexError / ValueError inside Pool.map) is an error that names
+    its row.  perf.script: the reference swallows every exception of its perf section (sofa_preprocess.py:1783-1837) - the
+    CPU trace is dropped with a warning and the run goes on; so does this (oracle pinned on it by tests/test_fuzz_ref_cpu.py)."""
     from sofa_b200._lib import SofaB200Error
     logdir = os.path.join(str(tmp_path), "l") + "/"
-    synth.make_logdir(logdir, seed=9, n_perf=100)
+    synth.make_logdir(logdir, seed=9, n_perf=100, n_gpu=100)
     with open(logdir + "perf.script", "a") as f:
         f.write("garbage line\n")
-    cfg = default_report_config(logdir)
+    sofa_preprocess(default_report_config(logdir))
+    assert not os.path.isfile(logdir + "cputrace.csv") and os.path.isfile(logdir + "gputrace.csv")
+    with open(logdir + "report.js") as f:
+        js = f.read()
+    assert "cpu_trace = " not in js and "gpu_kernel_trace = " in js
+    with open(logdir + "gputrace.tmp", "a") as f:
+        f.write("garbage line\n")
     with pytest.raises(SofaB200Error) as ei:
-        sofa_preprocess(cfg)
-    assert ei.value.row == 100
+        sofa_preprocess(default_report_config(logdir))
+    assert ei.value.row in (100, 103) and ei.value.row_code in (1, 2, 3)      # row 100 of the data rows (103 counting the header rows)
 
 
 def test_empty_and_unterminated_inputs(tmp_path):

@@ -45,3 +45,40 @@ def test_net_profile_host_logic(name, tmp_path):
     feats = an.net_profile(logdir, cfg, eng, [])
     assert float(dict(feats)["net_time"]) == case["features"]["__net_features__"][1][1]
     assert open(logdir + "netrank.csv", "rb").read() == golden_bytes(name, "netrank.csv")
+
+
+def test_unconvertible_perf_sample_costs_the_cpu_trace_not_the_run(tmp_path):
+    """The reference wraps its perf section in a bare `except:` (sofa_preprocess.py:1783-1837): a blank or malformed
+    perf.script line drops the CPU trace ("no perf traces.", no cputrace.csv, no cpu series) and the run goes on - while
+    a malformed nvprof or tcpdump line raises.  Product (host logic + CPU build of the row codecs) against the oracle,
+    which is pinned on exactly this against the unmodified reference by the fuzz of tests/test_fuzz_ref_cpu.py."""
+    import os
+    import shutil
+    import pytest
+    from helpers import demangle
+    from hostsim_engine import HostSimEngine, HostSimError
+    from oracle import sofa_oracle as orc
+    from sofa_b200 import synth
+    from sofa_b200.sofa_config import default_report_config
+    from sofa_b200.sofa_preprocess import sofa_preprocess
+    for k, bad in enumerate(("\n", " 4242/4242     5000.000404: 12x4 cycles:      7fbb9bbb4eaa memcpy+0x7cb (/lib/libc.so)\n", "4242\n")):
+        a, b = str(tmp_path / ("a%d" % k)) + "/", str(tmp_path / ("b%d" % k)) + "/"
+        synth.make_logdir(a, seed=77 + k, n_perf=50, n_gpu=30, n_net=20)
+        lines = open(a + "perf.script").read().splitlines(True)
+        lines.insert(20, bad)
+        open(a + "perf.script", "w").write("".join(lines))
+        shutil.copytree(a, b)
+        sofa_preprocess(default_report_config(a), engine=HostSimEngine())
+        orc.preprocess(orc.OracleConfig(b, nprocs=1), demangle=demangle)
+        assert not os.path.isfile(a + "cputrace.csv") and not os.path.isfile(b + "cputrace.csv")
+        for fn in ("gputrace.csv", "nettrace.csv", "report.js"):
+            assert open(a + fn, "rb").read() == open(b + fn, "rb").read(), fn
+        assert b"cpu_trace" not in open(a + "report.js", "rb").read()
+    # the same damage in the nvprof text is an error in the reference, and here
+    a = str(tmp_path / "g") + "/"
+    synth.make_logdir(a, seed=80, n_perf=20, n_gpu=30)
+    lines = open(a + "gputrace.tmp").read().splitlines(True)
+    lines.insert(10, "garbage\n")
+    open(a + "gputrace.tmp", "w").write("".join(lines))
+    with pytest.raises(HostSimError):
+        sofa_preprocess(default_report_config(a), engine=HostSimEngine())
