@@ -118,3 +118,29 @@ def make_storage_logdir(a, n_disk=3000, n_strace=20000, n_blk=30000, n_py=5000):
     lines.insert(95, "  8,0    5     1001    0.000500000     0  C   W alsonot + 8 [0] [0] [0] [0]")      # completes block 0
     lines.insert(120, "  8,0    1 short line")
     open(a + "blktrace.txt", "w").write("\n".join(lines))
+
+
+def make_full_logdir(a, seed=0):
+    """perf + nvprof + tcpdump text and every recorder side file in one small logdir (config-space fuzz)"""
+    make_storage_logdir(a, n_disk=60, n_strace=300, n_blk=400, n_py=80)
+    synth.make_logdir(a, seed=31 + seed, n_perf=300, n_gpu=200, n_net=150, non_ip_pct=3)
+    synth.write_side_raw(a, seed=32, n_samples=40, n_cores=2, n_gpus=2)
+    synth.write_side_raw_1hz(a, seed=33, n_seconds=8, n_gpus=2)
+
+
+def random_overrides(rng):
+    """a random point of the report options that reach sofa_preprocess (bin/sofa:161-312)"""
+    over = {}
+    if rng.random() < 0.5: over['plot_ratio'] = rng.choice([2, 3, 5, 11])
+    if rng.random() < 0.4: over['absolute_timestamp'] = True
+    if rng.random() < 0.4: over['cpu_time_offset'] = rng.choice([0.001, -0.25, 3.5])
+    if rng.random() < 0.4: over['nvsmi_time_zone'] = rng.choice([-8, 3, 9])
+    if rng.random() < 0.5: over['enable_vmstat'] = True
+    if rng.random() < 0.5: over['enable_encode_decode'] = True
+    if rng.random() < 0.3: over['strace_min_time'] = rng.choice([0.0, 0.01, 0.1])
+    if rng.random() < 0.3: over['diskstat_filters'] = rng.choice(['xda', 'dm-x', 'nosuch'])
+    if rng.random() < 0.6: over['cpu_filters'] = rng.choice(['idle:black', 'idle:black,tensorflow:orange', 'memcpy:red,nccl:blue,page_fault:green'])
+    return over
+
+
+ALL_PREPROCESS_OUTPUTS = tuple(sorted(set(STORAGE_OUTPUTS) | set(SIDE_OUTPUTS) | {'gputrace.csv', 'nettrace.csv'}))

