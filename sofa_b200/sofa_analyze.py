@@ -9,9 +9,9 @@ keeps the scalar logic and the printing of the small result tables (a few hundre
 reference does.
 
 Profile functions: cpu_profile, strace_profile (a title), net_profile (+ --verbose matrices), netbandwidth_profile,
-vmstat_profile, mpstat_profile, nvsmi_profile, gpu_profile (+ comm_profile, get_top_k_events), concurrency_breakdown.
-Not built: blktrace_latency_profile / diskstat_profile (their inputs come from `btt` and diskstat_vector.csv), the PDF
-charts (no matplotlib), nvlink ring search, POTATO, AISI driver hook.
+blktrace_latency_profile, diskstat_profile, vmstat_profile, mpstat_profile, nvsmi_profile, gpu_profile (+ comm_profile,
+get_top_k_events), concurrency_breakdown.  Not built: the PDF charts (no matplotlib), nvlink ring search, POTATO, the AISI
+driver hook (sofa_b200.sofa_aisi.iter_profile is the device part of it).
 
 Like the reference, a stand-alone `sofa analyze` (or `sofa report --skip_preprocess`) reads only the CSV files of the
 logdir: cputrace.csv / gputrace.csv / nettrace.csv are parsed on the device as pd.read_csv would see them (quoted,
