@@ -62,8 +62,68 @@ class ShardIO:
                 if self.rank + 1 < self.world else size
         return lo, max(lo, hi)
 
-    def read(self, path, data_off=0):
+    # ---- plot_ratio > 1: the reference keeps rows i % plot_ratio == 0 of the WHOLE file (list_downsample, :51-57); a shard
+    # must therefore start at a row whose global index is a multiple of the ratio.  Line counts of the byte ranges are
+    # all-gathered, and every rank hands the first (-global_start) % ratio lines of its range to its predecessor.
+    ratio = 1
+
+    @staticmethod
+    def _count_lines(path, lo, hi, size):
+        n, last = 0, b'\n'
+        with open(path, 'rb') as f:
+            f.seek(lo)
+            left = hi - lo
+            while left > 0:
+                chunk = f.read(min(left, 1 << 24))
+                if not chunk:
+                    break
+                n += chunk.count(b'\n')
+                last = chunk[-1:]
+                left -= len(chunk)
+        return n + (1 if hi > lo and hi == size and last != b'\n' else 0)      # an unterminated last line is a row too
+
+    @staticmethod
+    def _skip_lines(path, lo, hi, k):
+        """offset of the line k lines after the one starting at lo (never beyond hi)"""
+        if k <= 0:
+            return lo
+        with open(path, 'rb') as f:
+            f.seek(lo)
+            pos = lo
+            while pos < hi:
+                chunk = f.read(min(hi - pos, 1 << 16))
+                if not chunk:
+                    break
+                i = -1
+                while k > 0:
+                    i = chunk.find(b'\n', i + 1)
+                    if i < 0:
+                        break
+                    k -= 1
+                if k == 0:
+                    return pos + i + 1
+                pos += len(chunk)
+        return hi
+
+    def aligned_range(self, path, data_off=0):
         lo, hi = self.byte_range(path, data_off)
+        if self.ratio <= 1 or self.world == 1:
+            return lo, hi
+        size = os.path.getsize(path)
+        per = self.all_gather_counts([self._count_lines(path, lo, hi, size), lo, hi])
+        start, skip = 0, []
+        for r in range(self.world):
+            skip.append((-start) % self.ratio if r else 0)
+            start += per[r][0]
+        if any(skip[r] > per[r][0] for r in range(self.world)):
+            raise NotImplementedError("%s: a shard holds fewer rows than plot_ratio; use fewer ranks for so small a trace" % path)
+        new_lo = self._skip_lines(path, lo, hi, skip[self.rank])
+        new_hi = self._skip_lines(path, per[self.rank + 1][1], per[self.rank + 1][2], skip[self.rank + 1]) \
+            if self.rank + 1 < self.world else hi
+        return new_lo, max(new_lo, new_hi)
+
+    def read(self, path, data_off=0):
+        lo, hi = self.aligned_range(path, data_off)
         with open(path, 'rb') as f:
             if self.rank == 0:                       # rank 0 keeps the header rows in front of its shard
                 return f.read(hi), data_off
@@ -250,6 +310,8 @@ class SegmentIO(ShardIO):
     the text: a 100 GB perf.script does not fit 180 GB of HBM in one piece), and the logdir's outputs are assembled
     from the segments' part files exactly as a sharded run assembles its ranks'.  The file-level dtype flags are
     collected by a parse-only pass over the gpu / packet segments first (state['flags'])."""
+
+    segmented = True            # (plot_ratio 1 only: pass 1 collects the dtype flags over all rows)
 
     def __init__(self, index, count, state):
         ShardIO.__init__(self, index, count, None)

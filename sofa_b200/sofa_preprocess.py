@@ -523,7 +523,9 @@ def _preprocess(cfg, eng, io):
         raise PreprocessError("plot_ratio must be >= 1")
 
     if io.world > 1 and ratio != 1:
-        raise NotImplementedError("a trace sharded over several GPUs needs plot_ratio 1 (the down-sampling phase of a shard is not carried yet)")
+        if not hasattr(io, 'aligned_range') or getattr(io, 'segmented', False):
+            raise NotImplementedError("this way of splitting a trace needs plot_ratio 1 (the down-sampling phase of a part is not carried)")
+        io.ratio = ratio              # shards start at rows whose global index is a multiple of plot_ratio (ShardIO.aligned_range)
     side = _side_sources(cfg, eng, logdir) if io.rank == 0 else {}
     net_series = SeriesOut('net_trace', 'NET', 'blue')
     net_filter_series = []

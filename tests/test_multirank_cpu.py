@@ -80,13 +80,15 @@ def _shard_worker(rank, world, port, workdir):
         import sofa_b200.sofa_preprocess as pre
         from helpers import demangle
         pre.demangle = demangle
-        for case in ("mixed", "gpu_only_kernels", "net_nan_late"):
+        for case in sorted(os.listdir(workdir)):
             cfg = default_report_config(os.path.join(workdir, case, "sharded"), cpu_filters="idle:black,tensorflow:orange")
+            if "_ratio" in case:
+                cfg.plot_ratio = int(case.split("_ratio")[1])
             io = sharded.ShardIO(rank, world, dist)
             lo, hi = io.byte_range(cfg.logdir + "perf.script") if os.path.isfile(cfg.logdir + "perf.script") else (0, 0)
             eng = HostSimEngine()
             pre.sofa_preprocess(cfg, engine=eng, io=io)
-            if os.path.isfile(cfg.logdir + "perf.script"):
+            if os.path.isfile(cfg.logdir + "perf.script") and "_ratio" not in case:
                 off, total = io.row_offsets(open(cfg.logdir + "perf.script", "rb").read()[lo:hi].count(b"\n"))
                 assert total == open(cfg.logdir + "perf.script", "rb").read().count(b"\n")
                 assert (off == 0) == (rank == 0)
@@ -113,7 +115,10 @@ def test_two_shards_equal_one_shard_gloo():
     with tempfile.TemporaryDirectory() as workdir:
         for case, kw in (("mixed", dict(seed=41, n_perf=700, n_gpu=500, n_net=300, non_ip_pct=2)),
                          ("gpu_only_kernels", dict(seed=42, n_gpu=400)),
-                         ("net_nan_late", dict(seed=43, n_net=400, non_ip_pct=0))):
+                         ("net_nan_late", dict(seed=43, n_net=400, non_ip_pct=0)),
+                         # plot_ratio > 1: shards must start at rows whose GLOBAL index is a multiple of the ratio
+                         ("mixed_ratio3", dict(seed=44, n_perf=701, n_gpu=503, n_net=307, non_ip_pct=2)),
+                         ("mixed_ratio7", dict(seed=45, n_perf=1000, n_gpu=333, n_net=200, non_ip_pct=4))):
             a = os.path.join(workdir, case, "single") + "/"
             synth.make_logdir(a, **kw)
             if case == "gpu_only_kernels":
@@ -130,9 +135,11 @@ def test_two_shards_equal_one_shard_gloo():
                 open(a + "net.tmp", "w").write("".join(lines))
             shutil.copytree(a, os.path.join(workdir, case, "sharded"))
             cfg = default_report_config(a, cpu_filters="idle:black,tensorflow:orange")
+            if "_ratio" in case:
+                cfg.plot_ratio = int(case.split("_ratio")[1])
             pre.sofa_preprocess(cfg, engine=HostSimEngine())
         mp.spawn(_shard_worker, args=(world, port, workdir), nprocs=world, join=True)
-        for case in ("mixed", "gpu_only_kernels", "net_nan_late"):
+        for case in ("mixed", "gpu_only_kernels", "net_nan_late", "mixed_ratio3", "mixed_ratio7"):
             a, b = os.path.join(workdir, case, "single") + "/", os.path.join(workdir, case, "sharded") + "/"
             for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
                 if os.path.isfile(a + fn):
@@ -165,3 +172,31 @@ def test_segmented_preprocess_equals_whole(tmp_path):
         with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
             assert f.read() == g.read(), fn
     assert not [f for f in os.listdir(b) if ".shard" in f]
+
+
+def test_three_shards_with_plot_ratio_gloo():
+    """three ranks, plot_ratio 5: the middle shard both hands lines to its predecessor and takes lines from its successor"""
+    import shutil
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, HERE)
+    from hostsim_engine import HostSimEngine
+    from helpers import demangle
+    from sofa_b200 import synth
+    from sofa_b200.sofa_config import default_report_config
+    import sofa_b200.sofa_preprocess as pre
+    pre.demangle = demangle
+    world = 3
+    port = 29700 + (os.getpid() % 90)
+    with tempfile.TemporaryDirectory() as workdir:
+        case = "three_ratio5"
+        a = os.path.join(workdir, case, "single") + "/"
+        synth.make_logdir(a, seed=46, n_perf=997, n_gpu=611, n_net=401, non_ip_pct=3)
+        shutil.copytree(a, os.path.join(workdir, case, "sharded"))
+        cfg = default_report_config(a, cpu_filters="idle:black,tensorflow:orange")
+        cfg.plot_ratio = 5
+        pre.sofa_preprocess(cfg, engine=HostSimEngine())
+        mp.spawn(_shard_worker, args=(world, port, workdir), nprocs=world, join=True)
+        b = os.path.join(workdir, case, "sharded") + "/"
+        for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js"):
+            with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
+                assert f.read() == g.read(), fn
