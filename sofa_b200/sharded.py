@@ -105,12 +105,15 @@ class ShardIO:
                 pos += len(chunk)
         return hi
 
+    def _all_ranges(self, path, data_off, lo, hi):
+        """[[lines, lo, hi] of every rank's byte range]"""
+        return self.all_gather_counts([self._count_lines(path, lo, hi, os.path.getsize(path)), lo, hi])
+
     def aligned_range(self, path, data_off=0):
         lo, hi = self.byte_range(path, data_off)
         if self.ratio <= 1 or self.world == 1:
             return lo, hi
-        size = os.path.getsize(path)
-        per = self.all_gather_counts([self._count_lines(path, lo, hi, size), lo, hi])
+        per = self._all_ranges(path, data_off, lo, hi)
         start, skip = 0, []
         for r in range(self.world):
             skip.append((-start) % self.ratio if r else 0)
@@ -311,11 +314,22 @@ class SegmentIO(ShardIO):
     from the segments' part files exactly as a sharded run assembles its ranks'.  The file-level dtype flags are
     collected by a parse-only pass over the gpu / packet segments first (state['flags'])."""
 
-    segmented = True            # (plot_ratio 1 only: pass 1 collects the dtype flags over all rows)
-
     def __init__(self, index, count, state):
         ShardIO.__init__(self, index, count, None)
         self.state = state
+        self.ratio = state.get('ratio', 1)
+
+    def _all_ranges(self, path, data_off, lo, hi):           # no peers to ask: the segments of a file are walked once and cached
+        key = (path, data_off)
+        cache = self.state.setdefault('ranges', {})
+        if key not in cache:
+            size = os.path.getsize(path)
+            out = []
+            for r in range(self.world):
+                a, b = ShardIO(r, self.world, None).byte_range(path, data_off)
+                out.append([self._count_lines(path, a, b, size), a, b])
+            cache[key] = out
+        return cache[key]
 
     def sync_flags(self, eng, kind, stride):
         eng.set_global_flags(kind, stride, self.state['flags'].get(kind, 0))
@@ -336,14 +350,15 @@ def sofa_preprocess_segmented(cfg, engine, segment_bytes):
     from . import hostlogic as hl
     from .sofa_preprocess import sofa_preprocess
     logdir = cfg.logdir
-    if int(cfg.plot_ratio) != 1 or getattr(cfg, 'cuda_api_tracing', False):
-        raise NotImplementedError("segmented preprocess needs plot_ratio 1 and no --cuda_api_tracing")
+    if getattr(cfg, 'cuda_api_tracing', False):
+        raise NotImplementedError("segmented preprocess does not cover --cuda_api_tracing")
+    ratio = int(cfg.plot_ratio)
     files = {hl.SRC_PERF: logdir + 'perf.script', hl.SRC_GPU: logdir + 'gputrace.tmp', hl.SRC_NET: logdir + 'net.tmp'}
     sizes = [os.path.getsize(p) for p in files.values() if os.path.isfile(p)]
     K = max(1, max([-(-sz // int(segment_bytes)) for sz in sizes] or [1]))
     if K == 1:
         return sofa_preprocess(cfg, engine=engine)
-    state = {'flags': {}, 'counts': []}
+    state = {'flags': {}, 'counts': [], 'ratio': ratio}          # plot_ratio > 1: segments start at multiples of it (aligned_range)
     # ---- pass 1: file-level dtype flags of the gpu and packet sources (parse only)
     time_base = hl.read_time_base(logdir, cfg.cpu_time_offset)
     for kind in (hl.SRC_NET, hl.SRC_GPU):
@@ -364,7 +379,8 @@ def sofa_preprocess_segmented(cfg, engine, segment_bytes):
         fl = 0
         for i in range(K):
             text, off = SegmentIO(i, K, state).read(path, data_off)
-            fl |= engine.load(kind, text, p, off)[1]
+            engine.load(kind, text, p, off)
+            fl |= engine.row_flags(kind, ratio if kind == hl.SRC_NET else 1)     # nettrace.csv holds the down-sampled rows
         state['flags'][kind] = fl
     # ---- pass 2: every segment through the ordinary preprocess
     for i in range(K):

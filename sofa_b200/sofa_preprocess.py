@@ -480,7 +480,7 @@ def sofa_preprocess(cfg, engine=None, io=None):
             budget = int(os.environ.get('SOFA_B200_SEGMENT_BYTES', 16 << 30))
             big = [fn for fn in ('perf.script', 'gputrace.tmp', 'net.tmp')
                    if os.path.isfile(cfg.logdir + fn) and os.path.getsize(cfg.logdir + fn) > budget]
-            if big and int(cfg.plot_ratio) == 1 and not getattr(cfg, 'cuda_api_tracing', False):
+            if big and not getattr(cfg, 'cuda_api_tracing', False):
                 from .sharded import sofa_preprocess_segmented
                 return sofa_preprocess_segmented(cfg, engine, budget)
         return _preprocess(cfg, engine, io or PlainIO())
@@ -523,9 +523,9 @@ def _preprocess(cfg, eng, io):
         raise PreprocessError("plot_ratio must be >= 1")
 
     if io.world > 1 and ratio != 1:
-        if not hasattr(io, 'aligned_range') or getattr(io, 'segmented', False):
+        if not hasattr(io, 'aligned_range'):
             raise NotImplementedError("this way of splitting a trace needs plot_ratio 1 (the down-sampling phase of a part is not carried)")
-        io.ratio = ratio              # shards start at rows whose global index is a multiple of plot_ratio (ShardIO.aligned_range)
+        io.ratio = ratio              # shards / segments start at rows whose global index is a multiple of plot_ratio (ShardIO.aligned_range)
     side = _side_sources(cfg, eng, logdir) if io.rank == 0 else {}
     net_series = SeriesOut('net_trace', 'NET', 'blue')
     net_filter_series = []

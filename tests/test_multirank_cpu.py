@@ -148,7 +148,8 @@ def test_two_shards_equal_one_shard_gloo():
             assert not [f for f in os.listdir(b) if ".shard" in f]
 
 
-def test_segmented_preprocess_equals_whole(tmp_path):
+@pytest.mark.parametrize("ratio", [1, 4])
+def test_segmented_preprocess_equals_whole(ratio, tmp_path):
     """sofa_preprocess_segmented (bounded device memory: the sources walked in K newline-aligned segments, outputs assembled
     from part files) writes the same bytes as the one-piece run."""
     import shutil
@@ -165,9 +166,12 @@ def test_segmented_preprocess_equals_whole(tmp_path):
     synth.make_logdir(a, seed=51, n_perf=900, n_gpu=700, n_net=300, non_ip_pct=1)
     synth.write_side_raw(a, 51, n_samples=20, n_cores=2, n_gpus=2)
     shutil.copytree(a, b)
-    pre.sofa_preprocess(default_report_config(a, cpu_filters="idle:black,tensorflow:orange"), engine=HostSimEngine())
+    ca = default_report_config(a, cpu_filters="idle:black,tensorflow:orange")
+    cb = default_report_config(b, cpu_filters="idle:black,tensorflow:orange")
+    ca.plot_ratio = cb.plot_ratio = ratio            # > 1: segments start at multiples of the ratio; packet dtype flags over the kept rows
+    pre.sofa_preprocess(ca, engine=HostSimEngine())
     eng = HostSimEngine()
-    sharded.sofa_preprocess_segmented(default_report_config(b, cpu_filters="idle:black,tensorflow:orange"), eng, 20000)
+    sharded.sofa_preprocess_segmented(cb, eng, 20000)
     for fn in ("cputrace.csv", "gputrace.csv", "nettrace.csv", "report.js", "mpstat.csv", "nvsmi_trace.csv", "netstat.csv"):
         with open(a + fn, "rb") as f, open(b + fn, "rb") as g:
             assert f.read() == g.read(), fn
